@@ -1,0 +1,180 @@
+/*
+ * mlbp.h -- C ABI of libmlbp.so: the B200 (sm_100a) loopy-belief-propagation hot path of
+ * MacaronicUserModeling.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference has no FFI of its own: its seam is two Python modules:
+ *     LBP.py                          (FactorGraph / VariableNode / FactorNode message loop)
+ *     array_utils/c_array_utils.pyx   (Cython helpers, imported as `au` at LBP.py:6)
+ * Every entry point below cites the reference lines it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (MLBP_OK) or an MLBP_ERR_* code; mlbp_last_error() gives the text.
+ *   - all data pointers are DEVICE pointers unless the parameter name starts with h_ (host).
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises.
+ *   - the caller owns every buffer; the library owns only plan handles (host memory).
+ *   - rows of "[rows, ld]" arrays are padded: ld is a multiple of 64 elements and >= V.
+ *   - messages are scale-free: every consumer renormalises, so producers may emit any positive scale.
+ */
+#ifndef MLBP_H_
+#define MLBP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLBP_OK               0
+#define MLBP_ERR_INVALID      1   /* bad argument (shape, alignment, null pointer)            */
+#define MLBP_ERR_CUDA         2   /* a CUDA runtime / driver call failed                      */
+#define MLBP_ERR_UNSUPPORTED  3   /* e.g. device is not sm_100, more than 2 variables/factor  */
+#define MLBP_ERR_ALLOC        4
+
+#define MLBP_N_PLANES        14   /* fp16 operand planes written by mlbp_build_pairwise_tables */
+#define MLBP_N_TABLES         7   /* plane pairs (hi, lo): see MLBP_TABLE_*                    */
+#define MLBP_TABLE_T          0   /* B[n=a][k=b] = T[a,b]      : message to the dim-0 variable, gap > 1 (LBP.py:509) */
+#define MLBP_TABLE_TT         1   /* B[n=b][k=a] = T[a,b]      : message to the dim-1 variable, gap > 1 (LBP.py:518) */
+#define MLBP_TABLE_T1         2   /* same two with the gap == 1 table pot_en_en_w1 (LBP.py:460-461)                 */
+#define MLBP_TABLE_T1T        3
+#define MLBP_TABLE_G          4   /* T  o PMI     : pairwise belief expectation of the pmi feature (LBP.py:566-569, :610) */
+#define MLBP_TABLE_G1         5   /* T1 o PMI                                                                         */
+#define MLBP_TABLE_G1W        6   /* T1 o PMI_w1  : expectation of the pmi_w1 feature, gap == 1 factors only          */
+
+#define MLBP_A_SCALE_LOG2    14   /* var->factor rows are stored as 2^14 * normalised message, split hi + lo fp16 */
+
+const char *mlbp_last_error(void);
+int mlbp_version(void);
+/* 1 if the current device is compute capability 10.x, else 0 (also 0 when there is no device). */
+int mlbp_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) array_utils/c_array_utils.pyx dense helpers, float64 like the reference.
+ * ------------------------------------------------------------------------------------------------ */
+/* pyx:12-16  np.multiply(m1, m2)  (LBP.py:728) */
+int mlbp_pointwise_multiply_f64(const double *m1, const double *m2, double *out, int64_t n, void *stream);
+/* pyx:29-40  s = sum(m1); s > 0 ? m1 / s : zero-fill.  *d_sum (device, 1 double) receives s. (LBP.py:540,569,653) */
+int mlbp_normalize_f64(const double *m1, double *out, int64_t n, double *d_sum, void *stream);
+/* pyx:90-91  m1.dot(m2), row-major (m,k) x (k,n): the GEMV / outer product of LBP.py:509,518,566 */
+int mlbp_dense_dot_f64(const double *m1, const double *m2, double *out, int m, int k, int n, void *stream);
+/* pyx:93-94  np.multiply(m1, m2) on 2-D arrays (LBP.py:568) */
+int mlbp_dense_pointwise_multiply_f64(const double *m1, const double *m2, double *out, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) potentials that depend on theta only -- replaces the per-sentence rebuild of train.py:218-253.
+ * ------------------------------------------------------------------------------------------------ */
+/* K2.  pmi, pmi_w1: [V, ldf] fp32 row-major feature planes (train.py:589-595).
+ *   T  = exp(th[0]*pmi + th[2]),  T1 = exp(th[0]*pmi + th[1]*pmi_w1 + th[2])            (train.py:218-219, :252-253)
+ *   planes: MLBP_N_PLANES fp16 arrays [V, ldv], plane p at planes + p*plane_stride, in the order
+ *           T.hi T.lo Tt.hi Tt.lo T1.hi T1.lo T1t.hi T1t.lo G.hi G.lo G1.hi G1.lo G1w.hi G1w.lo,
+ *           every value multiplied by 2^scale_exp before the hi/lo split (hi + lo carries 22 bits).
+ *   colsums: [5, V] float64, UNscaled: sum_e T[e,y], sum_e T1[e,y], sum_e G[e,y], sum_e G1[e,y], sum_e G1w[e,y]
+ *           (the normaliser and feature expectations of the unary en_en factors, LBP.py:540, :600-603).
+ *   with_grad_planes = 0 skips planes 8..13 (inference only).                                        */
+int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1, int V, int ldf, const double *h_theta_ee,
+                               int scale_exp, void *planes, int64_t plane_stride, int ldv, double *colsums,
+                               int with_grad_planes, void *stream);
+/* edT, pedT: [Vd, ldf] fp32, de-major (row d = phi_en_de[:, d, k] of LBP.py:602 made contiguous).
+ *   edstats[d] = { sum_e psi, sum_e psi*ed, sum_e psi*ped },  psi = exp(th[0]*ed + th[1]*ped + th[5])  (train.py:240,251) */
+int mlbp_build_unary_tables(const float *edT, const float *pedT, int V, int Vd, int ldf, const double *h_theta_ed,
+                            double *edstats, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) unary factors of a batch of sentences (LBP.py:492-498, :540, :600-603; train.py:176-215, :255-297)
+ *     nv variables; variable v observes German word var_de[v], has supervised label var_label[v],
+ *     sparse per-sentence en_de features sp_*[sp_off[v] .. sp_off[v+1]) already filtered to de == var_de[v],
+ *     and unary en_en factors giv_*[giv_off[v] .. giv_off[v+1]) (label of the given token, gap == 1 flag).
+ * ------------------------------------------------------------------------------------------------ */
+/* per-variable normaliser and the closed-form unary gradient terms:
+ *   inv_sigma[v]  = 1 / sum_e psi_v(e)                      (psi_v includes the sparse features)
+ *   g_unary[v][9] = sum over v's unary factors of  phi[label, obs, :] - sum_e belief(e) phi[e, obs, :]
+ *                   laid out [pmi, pmi_w1, bias | ed, ped, correct, full_history, hit_history, bias]   */
+int mlbp_unary_stats(int nv, const int32_t *var_de, const int32_t *var_label, const int32_t *sp_off,
+                     const int32_t *sp_en, const int32_t *sp_feat, const float *sp_val, const int32_t *giv_off,
+                     const int32_t *giv_label, const int32_t *giv_gap1, const float *pmi, const float *pmi_w1,
+                     const float *edT, const float *pedT, int V, int ldf, const double *h_theta_ed,
+                     const double *edstats, const double *colsums, double *inv_sigma, double *g_unary, void *stream);
+/* K1.  U[v, e] = V^(1+g) * prod over v's unary factors of their normalised message (mean-one scaling),
+ *   the en_de factor recomputed from the de-major feature rows (coalesced gather-dot + exp), the en_en
+ *   factors read as rows of the transposed table planes.  U: [nv, ldv] fp32.                            */
+int mlbp_unary_products(int nv, const int32_t *var_de, const int32_t *sp_off, const int32_t *sp_en,
+                        const int32_t *sp_feat, const float *sp_val, const int32_t *giv_off,
+                        const int32_t *giv_label, const int32_t *giv_gap1, const float *edT, const float *pedT,
+                        int V, int ldf, const double *h_theta_ed, const double *inv_sigma, const void *planes,
+                        int64_t plane_stride, int ldv, int scale_exp, const double *colsums, float *U, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) message kernels
+ * ------------------------------------------------------------------------------------------------ */
+/* uniform 1/V messages of FactorGraph.initialize (LBP.py:211-216) as fp16 hi/lo rows: rows[i] of A := 2^14 / V */
+int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t *rows, int n_rows, void *stream);
+/* K3.  VariableNode.update_message_to (LBP.py:377-389) for n_groups (variable, level) groups at once.
+ *   group g multiplies U[grp_u[g]] with the factor->variable rows D[in_row[i]], i in [grp_off[g], grp_off[g+1]);
+ *   for every i with destinations it emits the leave-one-out product (all inputs except i), renormalised
+ *   (sum <= 0 or non-finite -> uniform, LBP.py:650-657; nan_to_num LBP.py:729), scaled by 2^14 and split into
+ *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]).  in_row < 0 means "uniform message".               */
+int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
+                       const int32_t *dest_off, const int32_t *dest, const float *U, const float *D, int ldv, int V,
+                       void *A_hi, void *A_lo, int max_in, void *stream);
+/* K4.  FactorNode.update_message_to for pairwise factors (LBP.py:499-526; au.dense_dot pyx:90-91), batched:
+ *   D[d_row0 + r, n] = alpha * sum_k (A_hi + A_lo)[a_row0 + r, k] * (B_hi + B_lo)[n, k],  r < n_rows, n < V
+ *   as three tcgen05 passes hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory.
+ *   A_*: [a_rows_total, ldv] fp16, B_*: one plane pair [V, ldv] fp16, D: [*, ldd] fp32.
+ *   impl: 0 = tcgen05 (product path), 1 = SIMT cross-check kernel (tests only).                           */
+int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
+                            const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
+                            float alpha, int impl, void *stream);
+/* K5.  VariableNode.get_marginal / get_posterior_probs / get_precision_counts / argmax
+ *   (LBP.py:392-411, :247-259, :80-106).  Same group layout as K3, all inputs multiplied.
+ *   logp[g] = log b[label] (-99.99 if b[label] == 0), top1[g] = argmax b (first index on ties),
+ *   rank[g] = #{e : b[e] > b[label]}, beliefs (optional, may be NULL): [n_groups, ldv] fp32 normalised.   */
+int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
+                   const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
+                   int32_t *top1, int32_t *rank, float *beliefs, void *stream);
+/* K6a. pairwise factor beliefs contracted with the features (LBP.py:544-569 + :610) in closed form:
+ *   stats[f] = { c.u0, c.u1, c.u2 } with c = (A_hi + A_lo)[c_row[f]], u* = D[u*_row[f]] (u2_row < 0 -> 0).  */
+int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *u0_row, const int32_t *u1_row,
+                           const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D, int ldv, int V,
+                           double *stats, void *stream);
+/* K6b. FactorGraph.get_unregularized_gradeint (LBP.py:301-320) as a segmented reduction:
+ *   grad[s][9] = sum_{v in sentence s} g_unary[v] + sum_{pairwise f in s} (phi[l0,l1,:] - E_f[phi])
+ *   sentence s owns variables [sent_var_off[s], sent_var_off[s+1]) and factors [sent_fac_off[s], ..).
+ *   logp_sent[s] = sum of logp_var over the sentence (LBP.py:247-259).                                     */
+int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t *sent_fac_off, const double *g_unary,
+                         const double *pair_stats, const int32_t *pair_l0, const int32_t *pair_l1,
+                         const int32_t *pair_gap1, const float *pmi, const float *pmi_w1, int ldf,
+                         const double *logp_var, double *grad, double *logp_sent, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) host-side schedule compiler: FactorGraph.initialize / has_loops / get_message_schedule /
+ *     treelike_inference (LBP.py:155-245) for a batch of graphs, lowered to dependency levels.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mlbp_plan mlbp_plan;
+/* Graph g has variables [var_off[g], var_off[g+1]) and pairwise factors [pair_off[g], pair_off[g+1]) listed in the
+ * order they were attached (defines facset order, LBP.py:367-369).  pair_v0/pair_v1 are variable indices LOCAL to
+ * the graph (v0 = dim 0, v1 = dim 1 of the potential table), pair_gap1 selects pot_en_en_w1 (LBP.py:456-463).
+ * roots: local variable index per graph and draw, [n_graphs, 1 + sweeps] (draw 0 = has_loops, LBP.py:176).
+ * flags: bit 0 = plan the gradient stage, bit 1 = plan the marginal stage.                              */
+int mlbp_plan_compile(int n_graphs, const int32_t *h_var_off, const int32_t *h_pair_off, const int32_t *h_pair_v0,
+                      const int32_t *h_pair_v1, const int32_t *h_pair_gap1, const int32_t *h_roots, int sweeps,
+                      int flags, mlbp_plan **out);
+/* sizes[0..15]: see MLBP_PLAN_* below */
+int mlbp_plan_sizes(const mlbp_plan *p, int64_t *h_sizes);
+/* copies the flat int32 blob (sizes[MLBP_PLAN_BLOB_WORDS] words) that the kernels index into */
+int mlbp_plan_export(const mlbp_plan *p, int32_t *h_blob);
+void mlbp_plan_destroy(mlbp_plan *p);
+
+#define MLBP_PLAN_BLOB_WORDS   0   /* length of the exported blob in int32 words                              */
+#define MLBP_PLAN_A_ROWS       1   /* rows of the A_hi / A_lo buffers                                         */
+#define MLBP_PLAN_D_ROWS       2   /* rows of the D buffer (row 0 is the constant-one row)                    */
+#define MLBP_PLAN_N_LEVELS     3
+#define MLBP_PLAN_N_PAIR       4   /* live pairwise factors in the gradient stage                             */
+#define MLBP_PLAN_N_GEMM_ROWS  5   /* total GEMM rows (message + gradient), = algorithmic GEMV count          */
+#define MLBP_PLAN_MAX_IN       6   /* largest number of incoming pairwise messages of any variable            */
+#define MLBP_PLAN_HDR_WORDS    7   /* blob header length; layout documented in csrc/plan.cpp                  */
+#define MLBP_PLAN_N_DEAD       8   /* updates removed because nothing reads their result                      */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLBP_H_ */

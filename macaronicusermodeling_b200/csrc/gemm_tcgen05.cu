@@ -1,0 +1,373 @@
+// K4: pairwise factor -> variable messages as a split-precision tcgen05 GEMM (sm_100a).
+//
+// Reference: FactorNode.update_message_to, LBP.py:499-526 -- one float64 dgemv  T.m  or  m'.T  per pairwise factor
+// and direction (au.dense_dot, c_array_utils.pyx:90-91).  All messages of one schedule level that share a
+// potential table are stacked into the rows of A, so the level becomes  D = alpha * A . B^T  with B one of the
+// table planes of K2 (K-major for both orientations because K2 also stores the transposed tables).
+//
+// Precision: the reference is float64 and parity needs bit-exact top-1 and 1e-4 beliefs, so a single fp16/bf16
+// rounding of either operand is not enough.  Both operands are stored as fp16 hi + lo
+// (22 significant bits) and the product is issued as three MMAs  hi*hi + hi*lo + lo*hi  into one fp32 TMEM
+// accumulator (the dropped lo*lo term is 2^-22 relative).  Roofline flops are counted once (2*M*N*K).
+//
+// Structure (one 128 x BN output tile per CTA, K = V streamed in 64-wide slabs):
+//   warp 0 lane 0 : TMA producer  -- 4 cp.async.bulk.tensor loads per stage (A.hi A.lo B.hi B.lo, swizzle-128B)
+//   warp 1 lane 0 : MMA issuer    -- 3 x (BK/16) tcgen05.mma.cta_group::1.kind::f16 per stage, tcgen05.commit
+//   warp 2        : TMEM allocate / free (BN fp32 columns)
+//   warps 4..7    : epilogue      -- tcgen05.ld 32x32b.x32, scale by alpha, 16-byte stores (row per thread)
+// full/empty mbarriers ring the shared-memory stages; one more mbarrier hands the accumulator to the epilogue.
+// CTAs are rasterised 16 M-tiles deep so that co-resident CTAs share A and B slabs in L2.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace mlbp {
+
+int launch_gemm_simt(const void *, const void *, int64_t, int, int, const void *, const void *, int, int, float *,
+                     int64_t, int, float, cudaStream_t);
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 fp16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int GROUP_M = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr unsigned long long WAIT_LIMIT_CYCLES = 8000000000ull;  // ~4 s: a stuck barrier traps instead of hanging the GPU
+
+template <int BN, int STAGES>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N");
+};
+
+// ------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > WAIT_LIMIT_CYCLES) {
+            if (err_flag) atomicExch(err_flag, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzle-128B shared-memory matrix descriptor: rows are 128 bytes, 8-row core-matrix groups are
+// 1024 bytes apart (SBO), LBO unused for a single swizzle atom along K, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+    d |= (uint64_t)0 << 16;                               // leading byte offset (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                               // version = 1
+    d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 accumulator, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------- kernel
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                      float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
+                      int m_tiles, int n_tiles, int *err_flag) {
+    using C = Cfg<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(STAGES + s); };
+    const uint32_t accum_bar = bar_base + 8u * (uint32_t)(2 * STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // rasterisation: GROUP_M m-tiles deep, then along n
+    const int per_group = GROUP_M * n_tiles;
+    const int grp = blockIdx.x / per_group, in_grp = blockIdx.x % per_group;
+    const int first_m = grp * GROUP_M;
+    const int gsize = min(GROUP_M, m_tiles - first_m);
+    const int m_blk = first_m + in_grp % gsize, n_blk = in_grp / gsize;
+    const int num_kb = (V + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            const int row_a = a_row0 + m_blk * BM, row_b = n_blk * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u, err_flag, 1);
+                mbar_expect_tx(full_bar(s), (uint32_t)C::STAGE_BYTES);
+                const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
+                tma_load_2d(&tm_a_hi, full_bar(s), st, kb * BK, row_a);
+                tma_load_2d(&tm_a_lo, full_bar(s), st + C::A_BYTES, kb * BK, row_a);
+                tma_load_2d(&tm_b_hi, full_bar(s), st + 2 * C::A_BYTES, kb * BK, row_b);
+                tma_load_2d(&tm_b_lo, full_bar(s), st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(full_bar(s), ph, err_flag, 2);
+                tc_fence_after();
+                const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::A_BYTES);
+                const uint64_t b_hi = umma_desc_sw128(st + 2 * C::A_BYTES);
+                const uint64_t b_lo = umma_desc_sw128(st + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K step inside the atom
+                    tc_mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_mma_f16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                    tc_mma_f16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                tc_commit(empty_bar(s));          // frees the stage when the MMAs above have read it
+            }
+            tc_commit(accum_bar);                 // accumulator complete
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        mbar_wait(accum_bar, 0u, err_flag, 3);
+        tc_fence_after();
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int m = m_blk * BM + q * 32 + lane;
+        const bool row_ok = m < n_rows;
+        float *drow = D + (d_row0 + (int64_t)m) * (int64_t)ldd;
+        const int n0 = n_blk * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            const int nc = n0 + c * 32;
+            if (row_ok && nc < ldd) {                             // ldd is a multiple of 64: chunk is all-in or all-out
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o;
+                    o.x = __uint_as_float(r[4 * j + 0]) * alpha;
+                    o.y = __uint_as_float(r[4 * j + 1]) * alpha;
+                    o.z = __uint_as_float(r[4 * j + 2]) * alpha;
+                    o.w = __uint_as_float(r[4 * j + 3]) * alpha;
+                    *reinterpret_cast<float4 *>(drow + nc + 4 * j) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2-D fp16 [rows, cols] tensor with row pitch ld elements; box = [box_rows, 64 cols], swizzle-128B, zero OOB fill
+static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MLBP_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MLBP_ERR_CUDA; }
+    return MLBP_OK;
+}
+
+struct MapKey {
+    const void *ptr; int64_t rows; int cols, ld, box;
+    bool operator<(const MapKey &o) const {
+        return std::tie(ptr, rows, cols, ld, box) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.box);
+    }
+};
+static std::map<MapKey, CUtensorMap> g_maps;
+static std::mutex g_maps_mu;
+
+static int cached_map(CUtensorMap *out, const void *ptr, int64_t rows, int cols, int ld, int box) {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    MapKey k{ptr, rows, cols, ld, box};
+    auto it = g_maps.find(k);
+    if (it == g_maps.end()) {
+        CUtensorMap m;
+        int rc = make_map(&m, ptr, rows, cols, ld, box);
+        if (rc != MLBP_OK) return rc;
+        if (g_maps.size() > 4096) g_maps.clear();
+        it = g_maps.emplace(k, m).first;
+    }
+    *out = it->second;
+    return MLBP_OK;
+}
+
+static int *g_err_flag = nullptr;   // pinned, mapped: the kernel records which barrier timed out before trapping
+
+template <int BN, int STAGES>
+static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
+                     const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
+                     cudaStream_t st) {
+    using C = Cfg<BN, STAGES>;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = cached_map(&ma_hi, A_hi, a_rows_total, V, ldv, BM)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&ma_lo, A_lo, a_rows_total, V, ldv, BM)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&mb_hi, B_hi, V, V, ldv, BN)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, BN)) != MLBP_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::SMEM_BYTES));
+        attr_set = true;
+    }
+    if (!g_err_flag) {
+        int *h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped) == cudaSuccess) { *h = 0; g_err_flag = h; }
+    }
+    int *d_flag = nullptr;
+    if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
+    const int m_tiles = (n_rows + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
+    gemm_split_f16_kernel<BN, STAGES><<<m_tiles * n_tiles, GEMM_THREADS, C::SMEM_BYTES, st>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, d_flag);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+}  // namespace mlbp
+
+using namespace mlbp;
+
+extern "C" int mlbp_gemm_barrier_timeout_code(void) { return g_err_flag ? *g_err_flag : 0; }
+
+extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
+                                       int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
+                                       int64_t d_row0, int ldd, float alpha, int impl, void *stream) {
+    if (n_rows == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(A_hi && A_lo && B_hi && B_lo && D, "factor_to_var_gemm: null pointer");
+    MLBP_CHECK_ARG(n_rows > 0 && V > 0 && a_row0 >= 0 && a_row0 + (int64_t)n_rows <= a_rows_total,
+                   "factor_to_var_gemm: row range [%d, %d) outside the A buffer (%lld rows)", a_row0, a_row0 + n_rows,
+                   (long long)a_rows_total);
+    MLBP_CHECK_ARG((ldv % 64) == 0 && ldv >= V && (ldd % 64) == 0 && ldd >= V, "factor_to_var_gemm: ld must be a multiple of 64 and >= V");
+    MLBP_CHECK_ARG((reinterpret_cast<uintptr_t>(A_hi) % 128) == 0 && (reinterpret_cast<uintptr_t>(A_lo) % 128) == 0 &&
+                   (reinterpret_cast<uintptr_t>(B_hi) % 128) == 0 && (reinterpret_cast<uintptr_t>(B_lo) % 128) == 0 &&
+                   (reinterpret_cast<uintptr_t>(D) % 16) == 0, "factor_to_var_gemm: misaligned buffer");
+    cudaStream_t st = as_stream(stream);
+    if (impl == 1)
+        return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
+    MLBP_CHECK_ARG(impl == 0, "factor_to_var_gemm: impl must be 0 (tcgen05) or 1 (SIMT cross-check)");
+    // BN = 256 halves the A re-reads; small vocabularies use the narrower tile to fill more SMs
+    if (V > 2048) return launch_tc<256, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
+    return launch_tc<128, 3>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
+}

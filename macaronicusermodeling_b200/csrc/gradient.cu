@@ -1,0 +1,106 @@
+// K6: observed-minus-expected feature counts of the pairwise factors and the per-sentence reduction.
+//
+// The reference materialises the dense V x V belief  normalize((c r') o T)  per pairwise factor and contracts it
+// with the (V,V,3) feature tensor (LBP.py:544-569, :610): ~7 passes over V^2 doubles per factor.  In closed form
+//  only three inner products per factor are needed,
+//     Z = c . (T r),   N1 = c . ((T o PMI) r),   N2 = c . ((T1 o PMI_w1) r)
+// where the matrix-vector products are rows of the batched GEMM (K4).  This file does the inner products (K6a)
+// and the segmented sum over each sentence's factors and variables (K6b).
+#include "common.cuh"
+
+namespace mlbp {
+
+// one CTA per pairwise factor
+__global__ void __launch_bounds__(256)
+pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__restrict__ u0_row,
+                         const int32_t *__restrict__ u1_row, const int32_t *__restrict__ u2_row,
+                         const __half *__restrict__ A_hi, const __half *__restrict__ A_lo, const float *__restrict__ D,
+                         int ldv, int V, double *__restrict__ stats) {
+    __shared__ double red[32];
+    const int f = blockIdx.x;
+    const __half *ch = A_hi + (size_t)c_row[f] * ldv, *cl = A_lo + (size_t)c_row[f] * ldv;
+    const float *u0 = D + (size_t)u0_row[f] * ldv, *u1 = D + (size_t)u1_row[f] * ldv;
+    const float *u2 = u2_row[f] >= 0 ? D + (size_t)u2_row[f] * ldv : nullptr;
+    double z = 0, n1 = 0, n2 = 0;
+    for (int e = threadIdx.x; e < V; e += blockDim.x) {
+        const double c = (double)__half2float(ch[e]) + (double)__half2float(cl[e]);
+        z += c * (double)__ldg(u0 + e);
+        n1 += c * (double)__ldg(u1 + e);
+        if (u2) n2 += c * (double)__ldg(u2 + e);
+    }
+    z = block_sum(z, red); n1 = block_sum(n1, red); n2 = block_sum(n2, red);
+    if (threadIdx.x == 0) { stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2; }
+}
+
+// one warp per sentence; deterministic (no atomics)
+__global__ void gradient_reduce_kernel(int n_sent, const int32_t *__restrict__ sent_var_off,
+                                       const int32_t *__restrict__ sent_fac_off, const double *__restrict__ g_unary,
+                                       const double *__restrict__ pair_stats, const int32_t *__restrict__ l0,
+                                       const int32_t *__restrict__ l1, const int32_t *__restrict__ gap1,
+                                       const float *__restrict__ pmi, const float *__restrict__ w1, int ldf,
+                                       const double *__restrict__ logp_var, double *__restrict__ grad,
+                                       double *__restrict__ logp_sent) {
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= n_sent) return;
+    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double lp = 0.0;
+    for (int v = sent_var_off[s] + lane; v < sent_var_off[s + 1]; v += 32) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g[i] += g_unary[(size_t)v * 9 + i];
+        if (logp_var) lp += logp_var[v];
+    }
+    for (int f = sent_fac_off[s] + lane; f < sent_fac_off[s + 1]; f += 32) {
+        const double z = pair_stats[3 * (size_t)f];
+        const size_t cell = (size_t)l0[f] * ldf + l1[f];
+        // Z <= 0: the reference's normalize zero-fills the belief (pyx:39-40) -> expected counts are 0
+        const double e1 = z > 0.0 ? pair_stats[3 * (size_t)f + 1] / z : 0.0;
+        g[0] += (double)pmi[cell] - e1;
+        if (gap1[f]) {
+            const double e2 = z > 0.0 ? pair_stats[3 * (size_t)f + 2] / z : 0.0;
+            g[1] += (double)w1[cell] - e2;
+        }
+        g[2] += z > 0.0 ? 0.0 : 1.0;  // bias: 1 - sum(belief)
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g[i] = warp_sum(g[i]);
+    lp = warp_sum(lp);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) grad[(size_t)s * 9 + i] = g[i];
+        if (logp_sent) logp_sent[s] = lp;
+    }
+}
+
+}  // namespace mlbp
+
+using namespace mlbp;
+
+extern "C" int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *u0_row,
+                                      const int32_t *u1_row, const int32_t *u2_row, const void *A_hi,
+                                      const void *A_lo, const float *D, int ldv, int V, double *stats,
+                                      void *stream) {
+    if (n_factors == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(n_factors > 0 && c_row && u0_row && u1_row && u2_row && A_hi && A_lo && D && stats,
+                   "pair_expectations: null pointer");
+    pair_expectations_kernel<<<n_factors, 256, 0, as_stream(stream)>>>(c_row, u0_row, u1_row, u2_row,
+                                                                       (const __half *)A_hi, (const __half *)A_lo, D,
+                                                                       ldv, V, stats);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t *sent_fac_off,
+                                    const double *g_unary, const double *pair_stats, const int32_t *pair_l0,
+                                    const int32_t *pair_l1, const int32_t *pair_gap1, const float *pmi,
+                                    const float *pmi_w1, int ldf, const double *logp_var, double *grad,
+                                    double *logp_sent, void *stream) {
+    if (n_sent == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(n_sent > 0 && sent_var_off && sent_fac_off && g_unary && pmi && pmi_w1 && grad,
+                   "gradient_reduce: null pointer");
+    const int threads = 128, warps_per_block = threads / 32;
+    gradient_reduce_kernel<<<(n_sent + warps_per_block - 1) / warps_per_block, threads, 0, as_stream(stream)>>>(
+        n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, pair_l0, pair_l1, pair_gap1, pmi, pmi_w1, ldf,
+        logp_var, grad, logp_sent);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}

@@ -1,0 +1,224 @@
+// K3 (variable -> factor messages) and K5 (marginals / log-posterior / argmax / rank).
+//
+// Both multiply the messages coming into one variable.  The reference does it one np.multiply per incoming
+// message and per OUTGOING edge (LBP.py:377-389, :717-730): O(deg^2) vector passes per variable and sweep.
+// Here one CTA owns one (variable, schedule level) group, reads each incoming row once per phase and emits
+// every needed leave-one-out product from a prefix / suffix product in registers.  Products are carried in
+// float64: a variable can have ~40 incoming messages and the raw product of fp32 values would leave the fp32
+// range (the reference multiplies fp64 values of size 1/V and never rescales, LBP.py:381-385).
+//
+// Phase 1 sums every outgoing product (the renormalisation of Message.renormalize, LBP.py:649-657);
+// phase 2 recomputes it (the inputs are then L2 hits), scales to 2^14 / sum and splits into the fp16 hi / lo
+// operand rows the pairwise GEMM (K4) consumes through TMA.
+#include "common.cuh"
+
+namespace mlbp {
+
+constexpr int K3_THREADS = 256;
+
+__global__ void fill_uniform_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int ldv, int V,
+                                         const int32_t *__restrict__ rows) {
+    const size_t r = (size_t)rows[blockIdx.x];
+    __half hi, lo;
+    split_f16(ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V, hi, lo);
+    const __half z = __float2half_rn(0.f);
+    for (int e = threadIdx.x; e < ldv; e += blockDim.x) {
+        A_hi[r * ldv + e] = e < V ? hi : z;
+        A_lo[r * ldv + e] = e < V ? lo : z;
+    }
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(K3_THREADS)
+var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
+                     const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
+                     const int32_t *__restrict__ dest, const float *__restrict__ U, const float *__restrict__ D,
+                     int ldv, int V, __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
+    __shared__ const float *s_src[NMAX];
+    __shared__ int s_d0[NMAX], s_d1[NMAX];
+    __shared__ double s_scale[NMAX];
+    __shared__ double red[32];
+    const int g = blockIdx.x;
+    const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
+    const float *urow = U + (size_t)grp_u[g] * ldv;
+    if (threadIdx.x < NMAX) {
+        const int j = threadIdx.x;
+        if (j < n) {
+            const int r = in_row[i0 + j];
+            s_src[j] = r >= 0 ? D + (size_t)r * ldv : nullptr;   // nullptr: uniform message (scale-free -> 1)
+            s_d0[j] = dest_off[i0 + j];
+            s_d1[j] = dest_off[i0 + j + 1];
+        } else {
+            s_src[j] = nullptr; s_d0[j] = 0; s_d1[j] = 0;
+        }
+    }
+    __syncthreads();
+
+    double acc[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) acc[j] = 0.0;
+
+    // ---- phase 1: sums of the leave-one-out products
+    for (int e = threadIdx.x; e < V; e += K3_THREADS) {
+        float d[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? __ldg(s_src[j] + e) : 1.0f;
+        double pre[NMAX];
+        double p = (double)__ldg(urow + e);
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (double)d[j]; }
+        double suf = 1.0;
+#pragma unroll
+        for (int j = NMAX - 1; j >= 0; --j) {
+            acc[j] += pre[j] * suf;
+            suf *= (double)d[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+        if (j < n && s_d1[j] > s_d0[j]) {                         // block-uniform condition
+            const double s = block_sum(acc[j], red);
+            if (threadIdx.x == 0)
+                s_scale[j] = (s > 0.0 && isfinite(s)) ? ldexp(1.0, MLBP_A_SCALE_LOG2) / s : -1.0;  // -1: uniform fallback
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: recompute, normalise, split, scatter to the consuming GEMM blocks
+    const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
+    for (int e = threadIdx.x; e < V; e += K3_THREADS) {
+        float d[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? __ldg(s_src[j] + e) : 1.0f;
+        double pre[NMAX];
+        double p = (double)__ldg(urow + e);
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (double)d[j]; }
+        double suf = 1.0;
+#pragma unroll
+        for (int j = NMAX - 1; j >= 0; --j) {
+            if (j < n && s_d1[j] > s_d0[j]) {
+                const double sc = s_scale[j];
+                const float x = sc > 0.0 ? (float)(pre[j] * suf * sc) : uni;
+                __half hi, lo;
+                split_f16(x, hi, lo);
+                for (int t = s_d0[j]; t < s_d1[j]; ++t) {
+                    const size_t o = (size_t)dest[t] * ldv + e;
+                    A_hi[o] = hi;
+                    A_lo[o] = lo;
+                }
+            }
+            suf *= (double)d[j];
+        }
+    }
+}
+
+// one CTA per variable: total product of all incoming messages
+__global__ void __launch_bounds__(256)
+marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
+                 const int32_t *__restrict__ in_row, const int32_t *__restrict__ label, const float *__restrict__ U,
+                 const float *__restrict__ D, int ldv, int V, double *__restrict__ logp, int32_t *__restrict__ top1,
+                 int32_t *__restrict__ rank, float *__restrict__ beliefs) {
+    __shared__ double red[32];
+    __shared__ double s_best[8];
+    __shared__ int s_besti[8];
+    const int g = blockIdx.x;
+    const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
+    const float *urow = U + (size_t)grp_u[g] * ldv;
+    const int lab = label[g];
+    auto prod = [&](int e) {
+        double p = (double)__ldg(urow + e);
+        for (int j = 0; j < n; ++j) {
+            const int r = in_row[i0 + j];
+            if (r >= 0) p *= (double)__ldg(D + (size_t)r * ldv + e);
+        }
+        return p;
+    };
+    const double plab = prod(lab);
+    double s = 0.0, best = -1.0;
+    int besti = 0x7fffffff, cnt = 0;
+    for (int e = threadIdx.x; e < V; e += blockDim.x) {
+        const double p = prod(e);
+        s += p;
+        cnt += (p > plab) ? 1 : 0;
+        if (p > best) { best = p; besti = e; }                    // strided ascending e: first index wins per thread
+    }
+    s = block_sum(s, red);
+    const double c = block_sum((double)cnt, red);
+    // argmax with first-index tie break (np.argmax)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_besti[threadIdx.x >> 5] = besti; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_best[w] > best || (s_best[w] == best && s_besti[w] < besti)) { best = s_best[w]; besti = s_besti[w]; }
+        const bool ok = s > 0.0 && isfinite(s);
+        // renormalize falls back to uniform when the sum is not positive (LBP.py:650-657)
+        const double b = ok ? plab / s : 1.0 / (double)V;
+        logp[g] = b > 0.0 ? log(b) : -99.99;                      // LBP.py:252-258
+        top1[g] = ok ? besti : 0;
+        rank[g] = ok ? (int)(c + 0.5) : 0;
+    }
+    if (beliefs) {
+        const bool ok = s > 0.0 && isfinite(s);
+        float *brow = beliefs + (size_t)g * ldv;
+        for (int e = threadIdx.x; e < V; e += blockDim.x) brow[e] = ok ? (float)(prod(e) / s) : 1.0f / (float)V;
+    }
+}
+
+}  // namespace mlbp
+
+using namespace mlbp;
+
+extern "C" int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t *rows, int n_rows,
+                                      void *stream) {
+    if (n_rows == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(A_hi && A_lo && rows && n_rows > 0 && V > 0 && ldv >= V, "fill_uniform_rows: bad argument");
+    fill_uniform_rows_kernel<<<n_rows, 256, 0, as_stream(stream)>>>((__half *)A_hi, (__half *)A_lo, ldv, V, rows);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
+                                  const int32_t *dest_off, const int32_t *dest, const float *U, const float *D,
+                                  int ldv, int V, void *A_hi, void *A_lo, int max_in, void *stream) {
+    if (n_groups == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && U && D && A_hi && A_lo,
+                   "var_to_factor: null pointer");
+    MLBP_CHECK_ARG(V > 0 && ldv >= V, "var_to_factor: bad V/ldv");
+    cudaStream_t st = as_stream(stream);
+#define MLBP_K3_LAUNCH(N)                                                                                          \
+    var_to_factor_kernel<N><<<n_groups, K3_THREADS, 0, st>>>(grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, \
+                                                             (__half *)A_hi, (__half *)A_lo)
+    if (max_in <= 4) MLBP_K3_LAUNCH(4);
+    else if (max_in <= 8) MLBP_K3_LAUNCH(8);
+    else if (max_in <= 16) MLBP_K3_LAUNCH(16);
+    else if (max_in <= 24) MLBP_K3_LAUNCH(24);
+    else if (max_in <= 32) MLBP_K3_LAUNCH(32);
+    else if (max_in <= 48) MLBP_K3_LAUNCH(48);
+    else {
+        set_error("var_to_factor: a variable with %d pairwise factors exceeds the supported 48", max_in);
+        return MLBP_ERR_UNSUPPORTED;
+    }
+#undef MLBP_K3_LAUNCH
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
+                              const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
+                              int32_t *top1, int32_t *rank, float *beliefs, void *stream) {
+    if (n_groups == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && label && U && D && logp && top1 && rank,
+                   "marginals: null pointer");
+    marginals_kernel<<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V, logp,
+                                                              top1, rank, beliefs);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}

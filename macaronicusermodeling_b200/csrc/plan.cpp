@@ -1,0 +1,444 @@
+// Host-side schedule compiler (C++, no CUDA): FactorGraph.initialize / has_loops / get_message_schedule /
+// treelike_inference (LBP.py:155-245) for a batch of sentence graphs, lowered to dependency levels.
+//
+// The reference executes the BFS schedule sequentially and in place (Gauss-Seidel), one Python call per message.
+// Results after 3 sweeps depend on that order, so it is reproduced literally: the same FIFO BFS with pop-time
+// `seen` marking (duplicate edges included), UP pass over reversed(S), DOWN pass over S, one root per sweep.
+// Each update is then given the earliest level at which all messages it reads have their sequential value
+// (RAW) and nothing it overwrites is still to be read (WAR / WAW).  Updates of one level are independent, so a
+// level of the whole batch is ONE leave-one-out launch (K3) plus ONE GEMM launch per potential table (K4).
+//
+// Unary factors never appear here: their messages are constants (LBP.py:492-498) folded into the per-variable
+// unary product U (K1), var->unary-factor messages do not exist (LBP.py:237), and as leaves of the BFS they do
+// not change the relative order of the other nodes.
+//
+// Storage: every message VERSION gets fresh rows, so there are no physical hazards:
+//   - a factor->variable update is one GEMM row: it reads row i of its (level, table) block of A and writes row i
+//     of the matching block of D;
+//   - a variable->factor update writes its result into the A-block row of every later GEMM row that reads that
+//     version (0..n destinations; versions nobody reads are dead code and dropped, as are their producers);
+//   - messages still at their initial uniform value are filled by mlbp_fill_uniform_rows / read as "row -1".
+//
+// Blob layout (int32 words), header first:
+//   [H_*] fixed header, then per-level records (LEV_WORDS each), then the index arrays they point to.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/mlbp.h"
+
+namespace mlbp {
+void set_error(const char *fmt, ...);
+}
+
+namespace {
+
+enum {
+    H_NLEVELS = 0, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
+    H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
+    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_WORDS = 32
+};
+enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_WORDS = 8 };
+enum { GEMM_TABLE = 0, GEMM_A0, GEMM_D0, GEMM_N, GEMM_WORDS = 4 };
+
+struct Op {
+    int32_t kind;      // 0: variable -> factor, 1: factor -> variable
+    int32_t f, side;   // pairwise factor (local) and which of its variables the message leaves from / goes to
+    int32_t level;
+    int32_t live;
+    int32_t in0, in1;  // range in Graph::inputs (producer op indices, -1 = initial uniform message)
+    int32_t row;       // kind 1: index inside its (level, table) block; global A / D row after assignment
+    int32_t table;
+};
+
+struct Graph {
+    int nv = 0, np = 0;
+    std::vector<int32_t> v0, v1, gap1;
+    std::vector<std::vector<int32_t>> facset;   // incident pairwise factors per variable, attach order
+    std::vector<Op> ops;
+    std::vector<int32_t> inputs;                // flat producer lists
+    std::vector<int32_t> in_edge;               // parallel to inputs: edge id (f * 2 + side) of the message read
+    std::vector<int32_t> fin_v2f, fin_f2v;      // producer op of the final version per edge (f * 2 + side)
+    std::vector<int32_t> slot;                  // edge (f * 2 + side) -> position of f in facset[variable of that side]
+    int n_levels = 0;
+};
+
+struct Plan {
+    std::vector<int32_t> blob;
+    int64_t sizes[16];
+};
+
+inline int var_of(const Graph &g, int f, int side) { return side == 0 ? g.v0[f] : g.v1[f]; }
+
+bool has_loops(const Graph &g, int root) {                       // LBP.py:174-190
+    std::vector<char> seenV(g.nv, 0), seenF(g.np, 0);
+    struct It { int node; bool is_var; int parent; };
+    std::vector<It> st;
+    st.push_back({root, true, -1});
+    while (!st.empty()) {
+        It n = st.back();
+        st.pop_back();
+        char &s = n.is_var ? seenV[n.node] : seenF[n.node];
+        if (s) return true;
+        s = 1;
+        if (n.is_var) {
+            for (int f : g.facset[n.node])
+                if (f != n.parent) st.push_back({f, false, n.node});
+        } else {
+            const int vs[2] = {g.v0[n.node], g.v1[n.node]};
+            for (int v : vs)
+                if (v != n.parent) st.push_back({v, true, n.node});
+        }
+    }
+    return false;
+}
+
+struct Edge { int child; bool child_is_var; int parent; };     // (child, parent) of LBP.py:165,168
+
+void schedule(const Graph &g, int root, std::vector<Edge> &S) {  // LBP.py:155-172
+    S.clear();
+    std::vector<char> seenV(g.nv, 0), seenF(g.np, 0);
+    struct Nd { int node; bool is_var; };
+    std::vector<Nd> q;
+    size_t head = 0;
+    q.push_back({root, true});
+    while (head < q.size()) {
+        Nd n = q[head++];
+        char &s = n.is_var ? seenV[n.node] : seenF[n.node];
+        if (s) continue;
+        s = 1;
+        if (n.is_var) {
+            for (int f : g.facset[n.node])
+                if (!seenF[f]) { S.push_back({f, false, n.node}); q.push_back({f, false}); }
+        } else {
+            const int vs[2] = {g.v0[n.node], g.v1[n.node]};
+            for (int v : vs)
+                if (!seenV[v]) { S.push_back({v, true, n.node}); q.push_back({v, true}); }
+        }
+    }
+}
+
+// append one update to the sequence, computing its level from the versions it touches
+struct Tracker {
+    std::vector<int32_t> cur_v2f, cur_f2v;     // producer op per edge, -1 = init
+    std::vector<int32_t> rd_v2f, rd_f2v;       // highest level that read the current version
+};
+
+inline int lvl_of(const Graph &g, int op) { return op < 0 ? 0 : g.ops[op].level; }
+
+void add_f2v(Graph &g, Tracker &t, int f, int side) {           // FactorNode.update_message_to, LBP.py:499-526
+    const int e_out = 2 * f + side, e_in = 2 * f + (1 - side);
+    Op op{};
+    op.kind = 1; op.f = f; op.side = side; op.live = 0; op.row = -1;
+    op.table = g.gap1[f] ? (side == 0 ? MLBP_TABLE_T1 : MLBP_TABLE_T1T) : (side == 0 ? MLBP_TABLE_T : MLBP_TABLE_TT);
+    op.in0 = (int32_t)g.inputs.size();
+    g.inputs.push_back(t.cur_v2f[e_in]);
+    g.in_edge.push_back(e_in);
+    op.in1 = (int32_t)g.inputs.size();
+    int lv = std::max(lvl_of(g, t.cur_v2f[e_in]), std::max(t.rd_f2v[e_out], lvl_of(g, t.cur_f2v[e_out])));
+    op.level = lv + 1;
+    t.rd_v2f[e_in] = std::max(t.rd_v2f[e_in], op.level);
+    t.cur_f2v[e_out] = (int32_t)g.ops.size();
+    t.rd_f2v[e_out] = 0;
+    g.ops.push_back(op);
+}
+
+void add_v2f(Graph &g, Tracker &t, int v, int f) {              // VariableNode.update_message_to, LBP.py:377-389
+    const int side = (g.v0[f] == v) ? 0 : 1;
+    const int e_out = 2 * f + side;
+    Op op{};
+    op.kind = 0; op.f = f; op.side = side; op.live = 0; op.row = -1; op.table = -1;
+    op.in0 = (int32_t)g.inputs.size();
+    int lv = std::max(t.rd_v2f[e_out], lvl_of(g, t.cur_v2f[e_out]));
+    for (int of : g.facset[v]) {
+        if (of == f) continue;
+        const int e = 2 * of + ((g.v0[of] == v) ? 0 : 1);
+        g.inputs.push_back(t.cur_f2v[e]);
+        g.in_edge.push_back(e);
+        lv = std::max(lv, lvl_of(g, t.cur_f2v[e]));
+    }
+    op.in1 = (int32_t)g.inputs.size();
+    op.level = lv + 1;
+    for (int i = op.in0; i < op.in1; ++i) t.rd_f2v[g.in_edge[i]] = std::max(t.rd_f2v[g.in_edge[i]], op.level);
+    t.cur_v2f[e_out] = (int32_t)g.ops.size();
+    t.rd_v2f[e_out] = 0;
+    g.ops.push_back(op);
+}
+
+void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
+    Tracker t;
+    t.cur_v2f.assign(2 * g.np, -1); t.cur_f2v.assign(2 * g.np, -1);
+    t.rd_v2f.assign(2 * g.np, 0);   t.rd_f2v.assign(2 * g.np, 0);
+    const bool loopy = g.np > 0 && has_loops(g, roots[0]);
+    const int n_it = loopy ? sweeps : 1;                         // LBP.py:219
+    std::vector<Edge> S;
+    for (int it = 0; it < n_it && g.np > 0; ++it) {
+        schedule(g, roots[1 + it], S);
+        for (size_t i = S.size(); i-- > 0;) {                    // leaves -> root: child sends to parent (LBP.py:227-233)
+            const Edge &e = S[i];
+            if (e.child_is_var) add_v2f(g, t, e.child, e.parent);
+            else add_f2v(g, t, e.child, (g.v0[e.child] == e.parent) ? 0 : 1);
+        }
+        for (const Edge &e : S) {                                // root -> leaves: parent sends to child (LBP.py:236-242)
+            if (e.child_is_var) add_f2v(g, t, e.parent, (g.v0[e.parent] == e.child) ? 0 : 1);
+            else add_v2f(g, t, e.parent, e.child);
+        }
+    }
+    g.fin_v2f = t.cur_v2f;
+    g.fin_f2v = t.cur_f2v;
+    g.n_levels = 0;
+    for (const Op &o : g.ops) g.n_levels = std::max(g.n_levels, (int)o.level);
+}
+
+}  // namespace
+
+extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int32_t *pair_off, const int32_t *pair_v0,
+                                 const int32_t *pair_v1, const int32_t *pair_gap1, const int32_t *roots, int sweeps,
+                                 int flags, mlbp_plan **out) {
+    if (!out || n_graphs < 0 || sweeps < 1 || !var_off || !pair_off || !roots) {
+        mlbp::set_error("plan_compile: bad argument");
+        return MLBP_ERR_INVALID;
+    }
+    const bool want_grad = flags & 1, want_marg = flags & 2;
+    std::vector<Graph> G(n_graphs);
+    int n_levels = 0, max_in = 0;
+    int64_t n_dead = 0;
+    for (int gi = 0; gi < n_graphs; ++gi) {
+        Graph &g = G[gi];
+        g.nv = var_off[gi + 1] - var_off[gi];
+        g.np = pair_off[gi + 1] - pair_off[gi];
+        if (g.nv <= 0) { mlbp::set_error("plan_compile: graph %d has no variables", gi); return MLBP_ERR_INVALID; }
+        g.facset.assign(g.nv, {});
+        g.v0.resize(g.np); g.v1.resize(g.np); g.gap1.resize(g.np);
+        for (int f = 0; f < g.np; ++f) {
+            const int a = pair_v0[pair_off[gi] + f], b = pair_v1[pair_off[gi] + f];
+            if (a < 0 || b < 0 || a >= g.nv || b >= g.nv || a == b) {
+                mlbp::set_error("plan_compile: graph %d factor %d has invalid variables (%d, %d)", gi, f, a, b);
+                return MLBP_ERR_INVALID;
+            }
+            g.v0[f] = a; g.v1[f] = b; g.gap1[f] = pair_gap1[pair_off[gi] + f] ? 1 : 0;
+            g.slot.resize(2 * (size_t)g.np);
+            g.slot[2 * f] = (int32_t)g.facset[a].size();
+            g.facset[a].push_back(f);
+            g.slot[2 * f + 1] = (int32_t)g.facset[b].size();
+            g.facset[b].push_back(f);
+        }
+        const int32_t *r = roots + (size_t)gi * (1 + sweeps);
+        for (int i = 0; i <= sweeps; ++i)
+            if (r[i] < 0 || r[i] >= g.nv) { mlbp::set_error("plan_compile: graph %d root %d out of range", gi, r[i]); return MLBP_ERR_INVALID; }
+        build_sequence(g, r, sweeps);
+        // liveness, reverse pass: an update is live iff a live update (or a final stage) reads its result
+        std::vector<char> needed(g.ops.size(), 0);
+        for (int e = 0; e < 2 * g.np; ++e) {
+            if (want_grad && g.fin_v2f[e] >= 0) needed[g.fin_v2f[e]] = 1;
+            if (want_marg && g.fin_f2v[e] >= 0) needed[g.fin_f2v[e]] = 1;
+        }
+        for (size_t i = g.ops.size(); i-- > 0;) {
+            Op &o = g.ops[i];
+            o.live = needed[i];
+            if (!o.live) { ++n_dead; continue; }
+            for (int k = o.in0; k < o.in1; ++k)
+                if (g.inputs[k] >= 0) needed[g.inputs[k]] = 1;
+        }
+        n_levels = std::max(n_levels, g.n_levels);
+        for (int v = 0; v < g.nv; ++v) max_in = std::max(max_in, (int)g.facset[v].size());
+    }
+
+    // ---- row assignment: one A/D block per (level, table)
+    std::vector<int64_t> cnt((size_t)(n_levels + 1) * 4, 0);
+    for (Graph &g : G)
+        for (Op &o : g.ops)
+            if (o.live && o.kind == 1) o.row = (int32_t)cnt[(size_t)o.level * 4 + o.table]++;
+    std::vector<int64_t> base((size_t)(n_levels + 1) * 4, 0);
+    int64_t a_rows = 0;
+    for (int L = 1; L <= n_levels; ++L)
+        for (int t = 0; t < 4; ++t) { base[(size_t)L * 4 + t] = a_rows; a_rows += cnt[(size_t)L * 4 + t]; }
+    const int64_t n_msg_rows = a_rows;
+    // D rows mirror A rows shifted by one (D row 0 is the constant-one row standing for uniform messages)
+    for (Graph &g : G)
+        for (Op &o : g.ops)
+            if (o.live && o.kind == 1) o.row = (int32_t)(base[(size_t)o.level * 4 + o.table] + o.row);
+    // gradient stage: r rows (gap>1 block, gap==1 block), then the c rows
+    int64_t n_pair = 0, n_gap0 = 0, n_gap1 = 0;
+    if (want_grad)
+        for (Graph &g : G) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.gap1[f] ? n_gap1 : n_gap0)++; }
+    const int64_t a_r0 = a_rows, a_r1 = a_r0 + n_gap0, a_c = a_r1 + n_gap1;
+    a_rows = a_c + n_pair;
+    int64_t d_rows = 1 + n_msg_rows;
+    const int64_t d_u0_0 = d_rows, d_u1_0 = d_u0_0 + n_gap0, d_u0_1 = d_u1_0 + n_gap0, d_u1_1 = d_u0_1 + n_gap1,
+                  d_u2_1 = d_u1_1 + n_gap1;
+    if (want_grad) d_rows = d_u2_1 + n_gap1;
+    if (a_rows > 0x7fffff00ll || d_rows > 0x7fffff00ll) { mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
+
+    // ---- destinations of every variable->factor version: the A rows of the GEMM rows that read it
+    std::vector<std::vector<std::vector<int32_t>>> dests(n_graphs);
+    std::vector<int32_t> init_rows;
+    std::vector<int32_t> pair_c, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1;
+    {
+        int64_t i0 = 0, i1 = 0, ip = 0;
+        for (int gi = 0; gi < n_graphs; ++gi) {
+            Graph &g = G[gi];
+            dests[gi].assign(g.ops.size(), {});
+            for (Op &o : g.ops) {
+                if (!o.live || o.kind != 1) continue;
+                const int prod = g.inputs[o.in0];
+                if (prod >= 0) dests[gi][prod].push_back(o.row);
+                else init_rows.push_back(o.row);
+            }
+            if (!want_grad) continue;
+            for (int f = 0; f < g.np; ++f) {
+                const int pr = g.fin_v2f[2 * f + 1], pc = g.fin_v2f[2 * f + 0];
+                const int64_t rrow = g.gap1[f] ? a_r1 + i1 : a_r0 + i0;
+                const int64_t crow = a_c + ip;
+                if (pr >= 0) dests[gi][pr].push_back((int32_t)rrow); else init_rows.push_back((int32_t)rrow);
+                if (pc >= 0) dests[gi][pc].push_back((int32_t)crow); else init_rows.push_back((int32_t)crow);
+                pair_c.push_back((int32_t)crow);
+                if (g.gap1[f]) {
+                    pair_u0.push_back((int32_t)(d_u0_1 + i1)); pair_u1.push_back((int32_t)(d_u1_1 + i1));
+                    pair_u2.push_back((int32_t)(d_u2_1 + i1)); ++i1;
+                } else {
+                    pair_u0.push_back((int32_t)(d_u0_0 + i0)); pair_u1.push_back((int32_t)(d_u1_0 + i0));
+                    pair_u2.push_back(-1); ++i0;
+                }
+                pair_g1.push_back(g.gap1[f]);
+                pair_gv0.push_back(var_off[gi] + g.v0[f]);
+                pair_gv1.push_back(var_off[gi] + g.v1[f]);
+                ++ip;
+            }
+        }
+    }
+
+    // ---- emit
+    Plan *P = new (std::nothrow) Plan();
+    if (!P) { mlbp::set_error("plan_compile: out of memory"); return MLBP_ERR_ALLOC; }
+    std::vector<int32_t> &B = P->blob;
+    B.assign(H_WORDS + (size_t)n_levels * LEV_WORDS, 0);
+    auto append = [&](const std::vector<int32_t> &v) { int32_t o = (int32_t)B.size(); B.insert(B.end(), v.begin(), v.end()); return o; };
+    B[H_NLEVELS] = n_levels; B[H_LEVELS_OFF] = H_WORDS; B[H_NGRAPHS] = n_graphs;
+    B[H_A_ROWS] = (int32_t)a_rows; B[H_D_ROWS] = (int32_t)d_rows; B[H_MAX_IN] = max_in; B[H_NVARS] = var_off[n_graphs];
+
+    // D row of a factor->variable version (producer op) or -1 for the initial uniform message
+    auto d_row_of = [&](const Graph &g, int prod) -> int32_t { return prod < 0 ? -1 : 1 + g.ops[prod].row; };
+
+    // per level: leave-one-out groups keyed by (graph, variable)
+    std::vector<std::vector<std::pair<int, int>>> lev_ops(n_levels + 1);   // (graph, op) of live kind-0 ops per level
+    for (int gi = 0; gi < n_graphs; ++gi)
+        for (size_t i = 0; i < G[gi].ops.size(); ++i) {
+            const Op &o = G[gi].ops[i];
+            if (o.live && o.kind == 0) lev_ops[o.level].push_back({gi, (int)i});
+        }
+    for (int L = 1; L <= n_levels; ++L) {
+        std::vector<int32_t> grp_u, grp_off, in_row, dest_off, dest;
+        grp_off.push_back(0);
+        dest_off.push_back(0);
+        auto &lo = lev_ops[L];
+        // group ops of the same (graph, variable); ops arrive graph-major, so sort within graph by variable (stable)
+        std::stable_sort(lo.begin(), lo.end(), [&](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+            if (x.first != y.first) return x.first < y.first;
+            const Graph &g = G[x.first];
+            return var_of(g, g.ops[x.second].f, g.ops[x.second].side) < var_of(g, g.ops[y.second].f, g.ops[y.second].side);
+        });
+        size_t i = 0;
+        while (i < lo.size()) {
+            const int gi = lo[i].first;
+            const Graph &g = G[gi];
+            const int v = var_of(g, g.ops[lo[i].second].f, g.ops[lo[i].second].side);
+            size_t j = i;
+            while (j < lo.size() && lo[j].first == gi && var_of(g, g.ops[lo[j].second].f, g.ops[lo[j].second].side) == v) ++j;
+            const auto &fs = g.facset[v];
+            std::vector<int32_t> ver(fs.size(), -2);            // producer seen by a reader in this group; -2 = nobody reads
+            std::vector<int32_t> tgt(fs.size(), -1);            // op that targets this edge
+            for (size_t k = i; k < j; ++k) {
+                const Op &o = g.ops[lo[k].second];
+                tgt[g.slot[2 * o.f + o.side]] = lo[k].second;
+                for (int q = o.in0; q < o.in1; ++q) ver[g.slot[g.in_edge[q]]] = g.inputs[q];
+            }
+            grp_u.push_back(var_off[gi] + v);
+            for (size_t s = 0; s < fs.size(); ++s) {
+                in_row.push_back(ver[s] == -2 ? -1 : d_row_of(g, ver[s]));
+                if (tgt[s] >= 0) dest.insert(dest.end(), dests[gi][tgt[s]].begin(), dests[gi][tgt[s]].end());
+                dest_off.push_back((int32_t)dest.size());
+            }
+            grp_off.push_back((int32_t)in_row.size());
+            i = j;
+        }
+        std::vector<int32_t> gemm;
+        for (int t = 0; t < 4; ++t)
+            if (cnt[(size_t)L * 4 + t] > 0) {
+                gemm.push_back(t);
+                gemm.push_back((int32_t)base[(size_t)L * 4 + t]);
+                gemm.push_back((int32_t)(1 + base[(size_t)L * 4 + t]));
+                gemm.push_back((int32_t)cnt[(size_t)L * 4 + t]);
+            }
+        const size_t rec = H_WORDS + (size_t)(L - 1) * LEV_WORDS;
+        const int32_t ng = (int32_t)grp_u.size();
+        const int32_t o_u = append(grp_u), o_off = append(grp_off), o_in = append(in_row), o_doff = append(dest_off),
+                      o_dest = append(dest), o_gemm = append(gemm);
+        B[rec + LEV_NGROUPS] = ng; B[rec + LEV_GRP_U] = o_u; B[rec + LEV_GRP_OFF] = o_off; B[rec + LEV_IN_ROW] = o_in;
+        B[rec + LEV_DEST_OFF] = o_doff; B[rec + LEV_DEST] = o_dest; B[rec + LEV_NGEMM] = (int32_t)(gemm.size() / GEMM_WORDS);
+        B[rec + LEV_GEMM] = o_gemm;
+    }
+    B[H_INIT_N] = (int32_t)init_rows.size();
+    B[H_INIT_OFF] = append(init_rows);
+    B[H_NPAIR] = (int32_t)n_pair;
+    B[H_PAIR_C] = append(pair_c); B[H_PAIR_U0] = append(pair_u0); B[H_PAIR_U1] = append(pair_u1);
+    B[H_PAIR_U2] = append(pair_u2); B[H_PAIR_GAP1] = append(pair_g1);
+    B[H_PAIR_V0] = append(pair_gv0); B[H_PAIR_V1] = append(pair_gv1);
+    {
+        std::vector<int32_t> gg;
+        auto call = [&](int table, int64_t a0, int64_t d0, int64_t n) {
+            if (n > 0) { gg.push_back(table); gg.push_back((int32_t)a0); gg.push_back((int32_t)d0); gg.push_back((int32_t)n); }
+        };
+        if (want_grad) {
+            call(MLBP_TABLE_T, a_r0, d_u0_0, n_gap0);  call(MLBP_TABLE_G, a_r0, d_u1_0, n_gap0);
+            call(MLBP_TABLE_T1, a_r1, d_u0_1, n_gap1); call(MLBP_TABLE_G1, a_r1, d_u1_1, n_gap1);
+            call(MLBP_TABLE_G1W, a_r1, d_u2_1, n_gap1);
+        }
+        B[H_NGRAD_GEMM] = (int32_t)(gg.size() / GEMM_WORDS);
+        B[H_GRAD_GEMM_OFF] = append(gg);
+    }
+    {
+        std::vector<int32_t> mu, moff, min_;
+        moff.push_back(0);
+        if (want_marg)
+            for (int gi = 0; gi < n_graphs; ++gi) {
+                const Graph &g = G[gi];
+                for (int v = 0; v < g.nv; ++v) {
+                    mu.push_back(var_off[gi] + v);
+                    for (int f : g.facset[v]) min_.push_back(d_row_of(g, g.fin_f2v[2 * f + ((g.v0[f] == v) ? 0 : 1)]));
+                    moff.push_back((int32_t)min_.size());
+                }
+            }
+        B[H_MARG_N] = (int32_t)mu.size();
+        B[H_MARG_U] = append(mu); B[H_MARG_OFF] = append(moff); B[H_MARG_IN] = append(min_);
+    }
+    int64_t gemm_rows = n_msg_rows + (want_grad ? 2 * n_gap0 + 3 * n_gap1 : 0);
+    std::memset(P->sizes, 0, sizeof(P->sizes));
+    P->sizes[MLBP_PLAN_BLOB_WORDS] = (int64_t)B.size();
+    P->sizes[MLBP_PLAN_A_ROWS] = a_rows;
+    P->sizes[MLBP_PLAN_D_ROWS] = d_rows;
+    P->sizes[MLBP_PLAN_N_LEVELS] = n_levels;
+    P->sizes[MLBP_PLAN_N_PAIR] = n_pair;
+    P->sizes[MLBP_PLAN_N_GEMM_ROWS] = gemm_rows;
+    P->sizes[MLBP_PLAN_MAX_IN] = max_in;
+    P->sizes[MLBP_PLAN_HDR_WORDS] = H_WORDS;
+    P->sizes[MLBP_PLAN_N_DEAD] = n_dead;
+    *out = reinterpret_cast<mlbp_plan *>(P);
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_plan_sizes(const mlbp_plan *p, int64_t *h_sizes) {
+    if (!p || !h_sizes) { mlbp::set_error("plan_sizes: null"); return MLBP_ERR_INVALID; }
+    std::memcpy(h_sizes, reinterpret_cast<const Plan *>(p)->sizes, sizeof(int64_t) * 16);
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_plan_export(const mlbp_plan *p, int32_t *h_blob) {
+    if (!p || !h_blob) { mlbp::set_error("plan_export: null"); return MLBP_ERR_INVALID; }
+    const Plan *P = reinterpret_cast<const Plan *>(p);
+    std::memcpy(h_blob, P->blob.data(), P->blob.size() * sizeof(int32_t));
+    return MLBP_OK;
+}
+
+extern "C" void mlbp_plan_destroy(mlbp_plan *p) { delete reinterpret_cast<Plan *>(p); }

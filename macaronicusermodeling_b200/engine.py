@@ -1,0 +1,407 @@
+"""Batched LBP executor: many sentence graphs -> level-batched sm_100a kernels behind the C ABI (include/mlbp.h).
+
+Replaces, for a whole batch of sentences at once, the reference's per-sentence sequence
+    create_factor_graph (train.py:133-305) -> fg.initialize (LBP.py:192-216) -> fg.treelike_inference (:218-245)
+    -> fg.get_unregularized_gradeint (:301-320) -> fg.get_posterior_probs (:247-259) -> get_precision_counts (:80-106)
+
+Data layout in HBM (all rows padded to ld = roundup(V, 64) elements):
+    Model   pmi, pmi_w1 [V, ld] fp32; edT, pedT [Vd, ld] fp32 (de-major)            resident, like weights
+    Tables  planes [14, V, ld] fp16 (hi/lo operand planes), colsums [5, V], edstats  rebuilt once per theta (K2)
+    U       [NV, ld] fp32   product of each variable's unary messages (K1)
+    A_hi/lo [RA, ld] fp16   variable->factor messages, one row per GEMM row that reads them (K3 -> K4)
+    D       [RD, ld] fp32   factor->variable messages, one row per GEMM row (K4 -> K3/K5/K6)
+PyTorch is used for device memory and streams only; all arithmetic is in libmlbp.so.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# plan blob header (csrc/plan.cpp)
+(H_NLEVELS, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
+ H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
+ H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS) = range(23)
+H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 8, 4
+(PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
+ PLAN_N_DEAD) = range(9)
+A_SCALE_LOG2 = 14
+N_PLANES = 14
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _p(t, word_off=0):
+    """device (or host) pointer of a tensor, optionally offset by int32 words"""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr() + 4 * word_off)
+
+
+def _hp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Kernels(object):
+    """The product back end: libmlbp.so on the current CUDA device.  Constructing it without a B200 raises."""
+
+    def __init__(self):
+        self.lib = _lib.require_device()
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+    @staticmethod
+    def stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def call(self, name, *args):
+        _lib.check(getattr(self.lib, name)(*args, self.stream()))
+
+
+class Model(object):
+    """Feature planes resident on the device (what train.py:589-612 loads once and wraps in PhiWrapper)."""
+
+    def __init__(self, pmi, pmi_w1, ed, ped, device):
+        pmi, pmi_w1, ed, ped = (np.asarray(x) for x in (pmi, pmi_w1, ed, ped))
+        V, Vd = ed.shape
+        assert pmi.shape == (V, V) and pmi_w1.shape == (V, V) and ped.shape == (V, Vd)
+        self.V, self.Vd, self.ld = V, Vd, round_up(V, 64)
+        self.device = device
+
+        def padded(a):
+            t = torch.zeros((a.shape[0], self.ld), dtype=torch.float32)
+            t[:, :V] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+            return t.to(device)
+
+        self.pmi, self.w1 = padded(pmi), padded(pmi_w1)
+        self.edT, self.pedT = padded(ed.T), padded(ped.T)
+        self.frange = (float(pmi.min()), float(pmi.max()), float(pmi_w1.min()), float(pmi_w1.max()))
+
+    @classmethod
+    def from_dict(cls, m, device):
+        return cls(m['pmi'], m['pmi_w1'], m['ed'], m['ped'], device)
+
+
+class Corpus(object):
+    """Sentences lowered to the flat integer arrays the kernels index (host numpy + lazily cached device copy).
+
+    Restates train.py:255-297: one variable per PREDICTED position (sentence order), one en_de unary factor per
+    variable, a unary en_en factor per (predicted, given) pair and a pairwise en_en factor per predicted pair,
+    gap = |i - j| (gap == 1 selects pot_en_en_w1, LBP.py:456-463).  Sparse per-sentence en_de features
+    (train.py:176-215) are kept only where their German index equals the variable's observed word: the only
+    column of phi_en_de the variable's factor ever reads (LBP.py:602, :702-703)."""
+
+    FIELDS = ('var_off', 'var_de', 'var_label', 'var_pos', 'sp_off', 'sp_en', 'sp_feat', 'sp_val', 'giv_off',
+              'giv_label', 'giv_gap1', 'pair_off', 'pair_v0', 'pair_v1', 'pair_gap1')
+
+    def __init__(self, sentences=None, **arrays):
+        if sentences is None:
+            for k in self.FIELDS:
+                setattr(self, k, arrays[k])
+        else:
+            self._build(sentences)
+        self._dev = {}
+
+    def _build(self, sentences):
+        var_off, var_de, var_label, var_pos = [0], [], [], []
+        sp_off, sp_en, sp_feat, sp_val = [0], [], [], []
+        giv_off, giv_label, giv_gap1 = [0], [], []
+        pair_off, pair_v0, pair_v1, pair_gap1 = [0], [], [], []
+        for s in sentences:
+            kind, label, de = s.kind, s.label, s.de
+            pred = [p for p in range(len(kind)) if kind[p] == 1]
+            given = [p for p in range(len(kind)) if kind[p] == 0]
+            if not pred:
+                raise ValueError('sentence without predicted tokens has no factor graph (LBP.py:193)')
+            for p in pred:
+                var_de.append(int(de[p])); var_label.append(int(label[p])); var_pos.append(p)
+                for e, d, f, val in s.sparse:
+                    if int(d) == int(de[p]):
+                        sp_en.append(int(e)); sp_feat.append(int(f)); sp_val.append(float(val))
+                sp_off.append(len(sp_en))
+                for q in given:
+                    giv_label.append(int(label[q])); giv_gap1.append(1 if abs(p - q) == 1 else 0)
+                giv_off.append(len(giv_label))
+            for a in range(len(pred)):
+                for b in range(a + 1, len(pred)):
+                    pair_v0.append(a); pair_v1.append(b); pair_gap1.append(1 if pred[b] - pred[a] == 1 else 0)
+            var_off.append(len(var_de)); pair_off.append(len(pair_v0))
+        i32 = lambda x: np.asarray(x, dtype=np.int32)
+        self.var_off, self.var_de, self.var_label, self.var_pos = i32(var_off), i32(var_de), i32(var_label), i32(var_pos)
+        self.sp_off, self.sp_en, self.sp_feat = i32(sp_off), i32(sp_en), i32(sp_feat)
+        self.sp_val = np.asarray(sp_val, dtype=np.float32)
+        self.giv_off, self.giv_label, self.giv_gap1 = i32(giv_off), i32(giv_label), i32(giv_gap1)
+        self.pair_off, self.pair_v0, self.pair_v1, self.pair_gap1 = i32(pair_off), i32(pair_v0), i32(pair_v1), i32(pair_gap1)
+
+    @property
+    def n_sent(self):
+        return len(self.var_off) - 1
+
+    @property
+    def n_vars(self):
+        return int(self.var_off[-1])
+
+    @property
+    def n_pairs(self):
+        return int(self.pair_off[-1])
+
+    def slice(self, lo, hi):
+        """sentences [lo, hi) as a Corpus with rebased offsets"""
+        v0, v1 = int(self.var_off[lo]), int(self.var_off[hi])
+        p0, p1 = int(self.pair_off[lo]), int(self.pair_off[hi])
+        s0, s1 = int(self.sp_off[v0]), int(self.sp_off[v1])
+        g0, g1 = int(self.giv_off[v0]), int(self.giv_off[v1])
+        return Corpus(var_off=self.var_off[lo:hi + 1] - v0, var_de=self.var_de[v0:v1], var_label=self.var_label[v0:v1],
+                      var_pos=self.var_pos[v0:v1], sp_off=self.sp_off[v0:v1 + 1] - s0, sp_en=self.sp_en[s0:s1],
+                      sp_feat=self.sp_feat[s0:s1], sp_val=self.sp_val[s0:s1], giv_off=self.giv_off[v0:v1 + 1] - g0,
+                      giv_label=self.giv_label[g0:g1], giv_gap1=self.giv_gap1[g0:g1],
+                      pair_off=self.pair_off[lo:hi + 1] - p0, pair_v0=self.pair_v0[p0:p1], pair_v1=self.pair_v1[p0:p1],
+                      pair_gap1=self.pair_gap1[p0:p1])
+
+    def roots_from_positions(self, roots_pos):
+        """reference roots are variable ids = sentence positions; the plan wants indices local to the sentence"""
+        out = np.zeros((self.n_sent, len(roots_pos[0])), dtype=np.int32)
+        for s in range(self.n_sent):
+            pos = self.var_pos[self.var_off[s]:self.var_off[s + 1]].tolist()
+            out[s] = [pos.index(int(r)) for r in roots_pos[s]]
+        return out
+
+    def gemm_rows_estimate(self, sweeps, grad):
+        k = np.diff(self.var_off).astype(np.int64)
+        rows = sweeps * k * (k - 1) + (3 * k * (k - 1) // 2 + k * (k - 1) // 2 if grad else 0)
+        return rows
+
+    def dev(self, name, device):
+        key = (name, str(device))
+        if key not in self._dev:
+            a = getattr(self, name)
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if len(a) == 0:
+                t = torch.zeros(1, dtype=t.dtype)          # keep a valid pointer for empty CSR payloads
+            self._dev[key] = t.to(device)
+        return self._dev[key]
+
+
+class Result(object):
+    """Outputs of one Engine.run: tensors stay on the device until read."""
+
+    def __init__(self, grad, logp, logp_var, top1, rank, beliefs, stats):
+        self.grad, self.logp, self.logp_var, self.top1, self.rank, self.beliefs, self.stats = \
+            grad, logp, logp_var, top1, rank, beliefs, stats
+
+    def precision_counts(self):
+        """FactorGraph.get_precision_counts (LBP.py:80-106) summed over the batch: (p@0, p@25, p@50, total)"""
+        r = self.rank
+        return int((r == 0).sum()), int((r < 26).sum()), int((r < 50).sum()), int(r.numel())
+
+
+class Engine(object):
+    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0):
+        self.k = kernels if kernels is not None else Kernels()
+        self.device = self.k.device
+        self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
+        self.V, self.Vd, self.ld = self.model.V, self.model.Vd, self.model.ld
+        self.workspace_bytes = int(workspace_bytes)
+        self.gemm_impl = gemm_impl
+        self.theta_ee = None
+        self.theta_ed = None
+        self.planes = None
+        self.colsums = torch.zeros((5, self.V), dtype=torch.float64, device=self.device)
+        self.edstats = torch.zeros((self.Vd, 3), dtype=torch.float64, device=self.device)
+        self.with_grad_planes = False
+        self._A = self._D = self._U = None
+        self._blob_host = None
+        self._blob_dev = None
+        self._blob_event = None     # H2D copy of the previous plan blob (the pinned buffer is reused)
+        self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
+        self.gemm_rows = 0          # GEMM rows executed (algorithmic GEMV count)
+
+    # ------------------------------------------------------------------ theta -> tables (K2)
+    def set_theta(self, theta_ee, theta_ed, with_grad=True):
+        te = np.ascontiguousarray(np.asarray(theta_ee, dtype=np.float64).reshape(3))
+        td = np.ascontiguousarray(np.asarray(theta_ed, dtype=np.float64).reshape(6))
+        self.theta_ee, self.theta_ed = te, td
+        pmin, pmax, wmin, wmax = self.model.frange
+        zmax = te[2] + max(te[0] * pmin, te[0] * pmax) + max(te[1] * wmin, te[1] * wmax, 0.0)
+        fabs = max(1.0, abs(pmin), abs(pmax), abs(wmin), abs(wmax))
+        self.scale_exp = 13 - int(math.ceil((zmax / math.log(2.0)) + math.log2(fabs)))
+        n_planes = N_PLANES if with_grad else 8
+        if self.planes is None or self.planes.shape[0] < n_planes:
+            self.planes = torch.zeros((n_planes, self.V, self.ld), dtype=torch.float16, device=self.device)
+        self.with_grad_planes = with_grad
+        m = self.model
+        self.k.call('mlbp_build_pairwise_tables', _p(m.pmi), _p(m.w1), self.V, self.ld, _hp(te), self.scale_exp,
+                    _p(self.planes), self.V * self.ld, self.ld, _p(self.colsums), 1 if with_grad else 0)
+        self.k.call('mlbp_build_unary_tables', _p(m.edT), _p(m.pedT), self.V, self.Vd, self.ld, _hp(td), _p(self.edstats))
+        self.launches += 2
+
+    def plane(self, table, lo):
+        return self.planes[2 * table + (1 if lo else 0)]
+
+    # ------------------------------------------------------------------ workspace
+    def rows_budget(self):
+        """GEMM rows (A and D rows) that fit the workspace: 4 bytes (A hi+lo) + 4 bytes (D) per element"""
+        return max(1024, self.workspace_bytes // (8 * self.ld))
+
+    def _ensure(self, a_rows, d_rows, n_vars, blob_words):
+        ld, dev = self.ld, self.device
+        if self._A is None or self._A.shape[1] < a_rows:
+            cap = max(a_rows, 0 if self._A is None else int(self._A.shape[1] * 1.25))
+            self._A = None
+            self._A = torch.empty((2, cap, ld), dtype=torch.float16, device=dev)
+        if self._D is None or self._D.shape[0] < d_rows:
+            cap = max(d_rows, 0 if self._D is None else int(self._D.shape[0] * 1.25))
+            self._D = None
+            self._D = torch.empty((cap, ld), dtype=torch.float32, device=dev)
+        if self._U is None or self._U.shape[0] < n_vars:
+            self._U = torch.empty((max(n_vars, 0 if self._U is None else int(self._U.shape[0] * 1.25)), ld),
+                                  dtype=torch.float32, device=dev)
+        if self._blob_host is None or self._blob_host.numel() < blob_words:
+            n = int(blob_words * 1.25) + 1024
+            pin = self.device.type == 'cuda'
+            self._blob_host = torch.empty(n, dtype=torch.int32, pin_memory=pin)
+            self._blob_dev = torch.empty(n, dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------ one microbatch
+    def compile(self, corpus, roots, sweeps, want_grad, want_marg):
+        roots = np.ascontiguousarray(roots, dtype=np.int32)
+        assert roots.shape == (corpus.n_sent, 1 + sweeps), roots.shape
+        handle = ctypes.c_void_p()
+        lib = _lib.load()
+        flags = (1 if want_grad else 0) | (2 if want_marg else 0)
+        _lib.check(lib.mlbp_plan_compile(corpus.n_sent, _hp(corpus.var_off), _hp(corpus.pair_off), _hp(corpus.pair_v0),
+                                         _hp(corpus.pair_v1), _hp(corpus.pair_gap1), _hp(roots), sweeps, flags,
+                                         ctypes.byref(handle)))
+        sizes = np.zeros(16, dtype=np.int64)
+        _lib.check(lib.mlbp_plan_sizes(handle, _hp(sizes)))
+        return handle, sizes
+
+    def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False):
+        """All sentences of `corpus` (must fit the workspace; use run_many to micro-batch).  `roots`: int
+        [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176)."""
+        assert self.theta_ee is not None, 'set_theta first'
+        assert not want_grad or self.with_grad_planes
+        lib = _lib.load()
+        handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg)
+        try:
+            words = int(sizes[PLAN_BLOB_WORDS])
+            nv = corpus.n_vars
+            if self._blob_event is not None:
+                self._blob_event.synchronize()
+            self._ensure(int(sizes[PLAN_A_ROWS]), int(sizes[PLAN_D_ROWS]), nv, words)
+            _lib.check(lib.mlbp_plan_export(handle, ctypes.c_void_p(self._blob_host.data_ptr())))
+        finally:
+            lib.mlbp_plan_destroy(handle)
+        blob = self._blob_host.numpy()[:words]
+        self._blob_dev[:words].copy_(self._blob_host[:words], non_blocking=True)
+        if self.device.type == 'cuda':
+            self._blob_event = torch.cuda.Event()
+            self._blob_event.record()
+        bd = self._blob_dev
+        dev, ld, V, k, m = self.device, self.ld, self.V, self.k, self.model
+        A_hi, A_lo, D, U = self._A[0], self._A[1], self._D, self._U
+        a_cap = int(self._A.shape[1])
+        td = self.theta_ed
+        c = lambda name: _p(corpus.dev(name, dev))
+
+        inv_sigma = torch.empty(max(nv, 1), dtype=torch.float64, device=dev)
+        g_unary = torch.empty((max(nv, 1), 9), dtype=torch.float64, device=dev)
+        k.call('mlbp_unary_stats', nv, c('var_de'), c('var_label'), c('sp_off'), c('sp_en'), c('sp_feat'), c('sp_val'),
+               c('giv_off'), c('giv_label'), c('giv_gap1'), _p(m.pmi), _p(m.w1), _p(m.edT), _p(m.pedT), V, ld, _hp(td),
+               _p(self.edstats), _p(self.colsums), _p(inv_sigma), _p(g_unary))
+        k.call('mlbp_unary_products', nv, c('var_de'), c('sp_off'), c('sp_en'), c('sp_feat'), c('sp_val'), c('giv_off'),
+               c('giv_label'), c('giv_gap1'), _p(m.edT), _p(m.pedT), V, ld, _hp(td), _p(inv_sigma), _p(self.planes),
+               V * ld, ld, self.scale_exp, _p(self.colsums), _p(U))
+        self.launches += 2
+        if blob[H_INIT_N]:
+            k.call('mlbp_fill_uniform_rows', _p(A_hi), _p(A_lo), ld, V, _p(bd, int(blob[H_INIT_OFF])), int(blob[H_INIT_N]))
+            self.launches += 1
+        alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp)))
+        max_in = int(blob[H_MAX_IN])
+
+        def gemm_calls(off, n):
+            for i in range(n):
+                t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
+                k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0, rows, _p(self.plane(t, 0)),
+                       _p(self.plane(t, 1)), V, ld, _p(D), d0, ld, alpha, self.gemm_impl)
+                self.launches += 1
+                self.gemm_rows += rows
+
+        for L in range(int(blob[H_NLEVELS])):
+            rec = blob[H_WORDS + LEV_WORDS * L: H_WORDS + LEV_WORDS * (L + 1)]
+            if rec[0]:
+                k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])), _p(bd, int(rec[3])),
+                       _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), max_in)
+                self.launches += 1
+            gemm_calls(int(rec[7]), int(rec[6]))
+
+        n_pair = int(blob[H_NPAIR])
+        pair_stats = torch.zeros((max(n_pair, 1), 3), dtype=torch.float64, device=dev)
+        pair_l0 = pair_l1 = None
+        if want_grad and n_pair:
+            gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]))
+            k.call('mlbp_pair_expectations', n_pair, _p(bd, int(blob[H_PAIR_C])), _p(bd, int(blob[H_PAIR_U0])),
+                   _p(bd, int(blob[H_PAIR_U1])), _p(bd, int(blob[H_PAIR_U2])), _p(A_hi), _p(A_lo), _p(D), ld, V,
+                   _p(pair_stats))
+            self.launches += 1
+            lab = corpus.dev('var_label', dev)
+            o0, o1 = int(blob[H_PAIR_V0]), int(blob[H_PAIR_V1])
+            pair_l0 = lab[bd[o0:o0 + n_pair].long()].contiguous()
+            pair_l1 = lab[bd[o1:o1 + n_pair].long()].contiguous()
+        logp_var = top1 = rank = beliefs = None
+        if want_marg:
+            n_m = int(blob[H_MARG_N])
+            logp_var = torch.empty(n_m, dtype=torch.float64, device=dev)
+            top1 = torch.empty(n_m, dtype=torch.int32, device=dev)
+            rank = torch.empty(n_m, dtype=torch.int32, device=dev)
+            beliefs = torch.empty((n_m, ld), dtype=torch.float32, device=dev) if want_beliefs else None
+            k.call('mlbp_marginals', n_m, _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])),
+                   _p(bd, int(blob[H_MARG_IN])), c('var_label'), _p(U), _p(D), ld, V, _p(logp_var), _p(top1), _p(rank),
+                   _p(beliefs))
+            self.launches += 1
+        grad = torch.zeros((corpus.n_sent, 9), dtype=torch.float64, device=dev)
+        logp = torch.zeros(corpus.n_sent, dtype=torch.float64, device=dev)
+        if want_grad:
+            zero_off = torch.zeros(corpus.n_sent + 1, dtype=torch.int32, device=dev)
+            k.call('mlbp_gradient_reduce', corpus.n_sent, c('var_off'), c('pair_off') if n_pair else _p(zero_off),
+                   _p(g_unary), _p(pair_stats), _p(pair_l0) if n_pair else _p(zero_off),
+                   _p(pair_l1) if n_pair else _p(zero_off), _p(bd, int(blob[H_PAIR_GAP1])) if n_pair else _p(zero_off),
+                   _p(m.pmi), _p(m.w1), ld, _p(logp_var), _p(grad), _p(logp))
+            self.launches += 1
+        elif want_marg:
+            seg = torch.from_numpy(np.repeat(np.arange(corpus.n_sent), np.diff(corpus.var_off))).to(dev)
+            logp.index_add_(0, seg, logp_var)
+        stats = {'a_rows': int(sizes[PLAN_A_ROWS]), 'd_rows': int(sizes[PLAN_D_ROWS]), 'levels': int(sizes[PLAN_N_LEVELS]),
+                 'gemm_rows': int(sizes[PLAN_N_GEMM_ROWS]), 'dead': int(sizes[PLAN_N_DEAD]), 'blob_words': words}
+        return Result(grad, logp, logp_var, top1, rank, beliefs, stats)
+
+    # ------------------------------------------------------------------ micro-batching
+    def microbatches(self, corpus, sweeps, want_grad):
+        """split [0, n_sent) so that each piece's GEMM rows fit the workspace"""
+        rows = corpus.gemm_rows_estimate(sweeps, want_grad) + 2 * np.diff(corpus.pair_off) + 8
+        budget = self.rows_budget()
+        out, lo, acc = [], 0, 0
+        for s in range(corpus.n_sent):
+            if acc + rows[s] > budget and s > lo:
+                out.append((lo, s))
+                lo, acc = s, 0
+            acc += int(rows[s])
+        out.append((lo, corpus.n_sent))
+        return out
+
+    def run_many(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True):
+        """Micro-batched run over a large corpus; returns (grad [B, 9], logp [B], top1 [NV], rank [NV]) on device.
+        Launches are asynchronous: the host compiles the next micro-batch's schedule while the GPU works."""
+        roots = np.ascontiguousarray(roots, dtype=np.int32)
+        grads, logps, top1s, ranks = [], [], [], []
+        for lo, hi in self.microbatches(corpus, sweeps, want_grad):
+            r = self.run(corpus.slice(lo, hi) if (lo, hi) != (0, corpus.n_sent) else corpus, roots[lo:hi], sweeps,
+                         want_grad, want_marg)
+            grads.append(r.grad); logps.append(r.logp)
+            if want_marg:
+                top1s.append(r.top1); ranks.append(r.rank)
+        cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs)
+        return cat(grads), cat(logps), (cat(top1s) if top1s else None), (cat(ranks) if ranks else None)

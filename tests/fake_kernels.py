@@ -1,0 +1,236 @@
+"""TEST DOUBLE for libmlbp.so's device kernels: the same C-ABI calls, emulated with NumPy on host pointers.
+
+Lets the CPU-only test tier run the REAL host logic (engine.py orchestration + the C++ schedule compiler in
+csrc/plan.cpp) end to end against the oracle without a GPU.  It mirrors the kernels' storage formats (fp16 hi/lo
+split, 2^14 message scale, dropped lo*lo term), not their speed.  Never imported by the package."""
+import ctypes
+
+import numpy as np
+import torch
+
+A_SCALE = 2.0 ** 14
+
+
+def _arr(ptr, dtype, count):
+    if ptr is None:
+        return None
+    addr = ptr.value if isinstance(ptr, ctypes.c_void_p) else int(ptr)
+    if addr is None:
+        return None
+    dt = np.dtype(dtype)
+    buf = (ctypes.c_char * (count * dt.itemsize)).from_address(addr)
+    return np.frombuffer(buf, dtype=dt, count=count)
+
+
+def _split(x):
+    x32 = x.astype(np.float32)
+    hi = x32.astype(np.float16)
+    lo = (x32 - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+class FakeKernels(object):
+    def __init__(self):
+        self.device = torch.device('cpu')
+        self.calls = []
+
+    def call(self, name, *args):
+        self.calls.append(name)
+        getattr(self, name)(*args)
+
+    # ---- K2
+    def mlbp_build_pairwise_tables(self, pmi, w1, V, ldf, th, scale_exp, planes, ps, ldv, colsums, with_grad):
+        P = _arr(pmi, np.float32, V * ldf).reshape(V, ldf)[:, :V].astype(np.float64)
+        W = _arr(w1, np.float32, V * ldf).reshape(V, ldf)[:, :V].astype(np.float64)
+        t = _arr(th, np.float64, 3)
+        T = np.exp(t[0] * P + t[2]); T1 = np.exp(t[0] * P + t[1] * W + t[2])
+        mats = [T, T.T, T1, T1.T, T * P, T1 * P, T1 * W]
+        pl = _arr(planes, np.float16, (14 if with_grad else 8) * ps)
+        for i, M in enumerate(mats[: 7 if with_grad else 4]):
+            hi, lo = _split(np.ldexp(M, scale_exp))
+            for j, h in enumerate((hi, lo)):
+                v = pl[(2 * i + j) * ps:(2 * i + j) * ps + V * ldv].reshape(V, ldv)
+                v[:, :V] = h
+        cs = _arr(colsums, np.float64, 5 * V).reshape(5, V)
+        cs[0], cs[1], cs[2], cs[3], cs[4] = T.sum(0), T1.sum(0), (T * P).sum(0), (T1 * P).sum(0), (T1 * W).sum(0)
+
+    def mlbp_build_unary_tables(self, edT, pedT, V, Vd, ldf, th, edstats):
+        E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
+        Pd = _arr(pedT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
+        t = _arr(th, np.float64, 6)
+        psi = np.exp(t[0] * E + t[1] * Pd + t[5])
+        st = _arr(edstats, np.float64, Vd * 3).reshape(Vd, 3)
+        st[:, 0], st[:, 1], st[:, 2] = psi.sum(1), (psi * E).sum(1), (psi * Pd).sum(1)
+
+    # ---- unary factors
+    def _unary_common(self, nv, var_de, sp_off, sp_en, sp_feat, sp_val, giv_off, giv_label, giv_gap1):
+        de = _arr(var_de, np.int32, nv)
+        so = _arr(sp_off, np.int32, nv + 1); go = _arr(giv_off, np.int32, nv + 1)
+        ns, ng = int(so[-1]), int(go[-1])
+        return (de, so, _arr(sp_en, np.int32, max(ns, 1)), _arr(sp_feat, np.int32, max(ns, 1)),
+                _arr(sp_val, np.float32, max(ns, 1)), go, _arr(giv_label, np.int32, max(ng, 1)),
+                _arr(giv_gap1, np.int32, max(ng, 1)))
+
+    def mlbp_unary_stats(self, nv, var_de, var_label, sp_off, sp_en, sp_feat, sp_val, giv_off, giv_label, giv_gap1, pmi,
+                         w1, edT, pedT, V, ldf, th, edstats, colsums, inv_sigma, g_unary):
+        de, so, se, sf, sv, go, gl, gg = self._unary_common(nv, var_de, sp_off, sp_en, sp_feat, sp_val, giv_off,
+                                                            giv_label, giv_gap1)
+        lab = _arr(var_label, np.int32, nv)
+        Vd = int(de.max()) + 1
+        E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf); Pd = _arr(pedT, np.float32, Vd * ldf).reshape(Vd, ldf)
+        P = _arr(pmi, np.float32, V * ldf).reshape(V, ldf); W = _arr(w1, np.float32, V * ldf).reshape(V, ldf)
+        t = _arr(th, np.float64, 6)
+        st = _arr(edstats, np.float64, Vd * 3).reshape(Vd, 3)
+        cs = _arr(colsums, np.float64, 5 * V).reshape(5, V)
+        isg = _arr(inv_sigma, np.float64, nv); gu = _arr(g_unary, np.float64, nv * 9).reshape(nv, 9)
+        for v in range(nv):
+            d, y = int(de[v]), int(lab[v])
+            S0, S1, S2 = st[d]
+            ent = [(int(se[s]), int(sf[s]), float(sv[s])) for s in range(so[v], so[v + 1])]
+            base = lambda e: np.exp(t[0] * float(E[d, e]) + t[1] * float(Pd[d, e]) + t[5])
+            delta = lambda e: sum(t[f] * val for (ee, f, val) in ent if ee == e)
+            for e in sorted(set(e for e, _, _ in ent)):
+                b = base(e); f = b * np.exp(delta(e))
+                S0 += f - b; S1 += (f - b) * float(E[d, e]); S2 += (f - b) * float(Pd[d, e])
+            g = np.zeros(9)
+            g[3] = float(E[d, y]) - S1 / S0
+            g[4] = float(Pd[d, y]) - S2 / S0
+            for e, f, val in ent:
+                g[3 + f] += val * ((1.0 if e == y else 0.0) - base(e) * np.exp(delta(e)) / S0)
+            for j in range(go[v], go[v + 1]):
+                o = int(gl[j])
+                if gg[j]:
+                    g[0] += float(P[y, o]) - cs[3, o] / cs[1, o]
+                    g[1] += float(W[y, o]) - cs[4, o] / cs[1, o]
+                else:
+                    g[0] += float(P[y, o]) - cs[2, o] / cs[0, o]
+            isg[v] = 1.0 / S0
+            gu[v] = g
+
+    def mlbp_unary_products(self, nv, var_de, sp_off, sp_en, sp_feat, sp_val, giv_off, giv_label, giv_gap1, edT, pedT, V,
+                            ldf, th, inv_sigma, planes, ps, ldv, scale_exp, colsums, U):
+        de, so, se, sf, sv, go, gl, gg = self._unary_common(nv, var_de, sp_off, sp_en, sp_feat, sp_val, giv_off,
+                                                            giv_label, giv_gap1)
+        Vd = int(de.max()) + 1
+        E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
+        Pd = _arr(pedT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
+        t = _arr(th, np.float64, 6)
+        isg = _arr(inv_sigma, np.float64, nv)
+        pl = _arr(planes, np.float16, 8 * ps)
+        cs = _arr(colsums, np.float64, 5 * V).reshape(5, V)
+        Uo = _arr(U, np.float32, nv * ldv).reshape(nv, ldv)
+        for v in range(nv):
+            d = int(de[v])
+            z = t[0] * E[d] + t[1] * Pd[d] + t[5]
+            for s in range(so[v], so[v + 1]):
+                z[int(se[s])] += t[int(sf[s])] * float(sv[s])
+            u = np.exp(z) * V * isg[v]
+            for j in range(go[v], go[v + 1]):
+                o, tp = int(gl[j]), (6 if gg[j] else 2)
+                row = (pl[tp * ps + o * ldv: tp * ps + o * ldv + V].astype(np.float64) +
+                       pl[(tp + 1) * ps + o * ldv:(tp + 1) * ps + o * ldv + V].astype(np.float64))
+                u = u * row * np.ldexp(1.0, -scale_exp) * V / cs[1 if gg[j] else 0, o]
+            Uo[v, :V] = u
+            Uo[v, V:] = 0
+
+    # ---- messages
+    def mlbp_fill_uniform_rows(self, A_hi, A_lo, ldv, V, rows, n_rows):
+        r = _arr(rows, np.int32, n_rows)
+        hi, lo = _split(np.array([A_SCALE / V]))
+        n = (int(r.max()) + 1) * ldv
+        H, L = _arr(A_hi, np.float16, n).reshape(-1, ldv), _arr(A_lo, np.float16, n).reshape(-1, ldv)
+        H[r, :V], L[r, :V] = hi[0], lo[0]
+        H[r, V:], L[r, V:] = 0, 0
+
+    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, A_hi, A_lo, max_in):
+        gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
+        n_in = int(go[-1])
+        ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
+        de = _arr(dest, np.int32, max(int(do[-1]), 1))
+        big = 1 << 40
+        Uo = _arr(U, np.float32, (int(gu.max()) + 1) * ldv).reshape(-1, ldv)
+        Dm = _arr(D, np.float32, (max(int(ir.max()), 0) + 1) * ldv).reshape(-1, ldv)
+        amax = (int(de[:int(do[-1])].max()) + 1) if int(do[-1]) else 1
+        H, L = _arr(A_hi, np.float16, amax * ldv).reshape(-1, ldv), _arr(A_lo, np.float16, amax * ldv).reshape(-1, ldv)
+        assert big
+        for g in range(n_groups):
+            rows = ir[go[g]:go[g + 1]]
+            assert len(rows) <= max_in
+            ins = [Dm[r, :V].astype(np.float64) if r >= 0 else np.ones(V) for r in rows]
+            u = Uo[gu[g], :V].astype(np.float64)
+            for j in range(len(rows)):
+                i = go[g] + j
+                if do[i + 1] == do[i]:
+                    continue
+                p = u.copy()
+                for q, m in enumerate(ins):
+                    if q != j:
+                        p = p * m
+                s = p.sum()
+                x = p * (A_SCALE / s) if (s > 0 and np.isfinite(s)) else np.full(V, A_SCALE / V)
+                hi, lo = _split(x)
+                for tdest in de[do[i]:do[i + 1]]:
+                    H[tdest, :V], L[tdest, :V] = hi, lo
+
+    def mlbp_factor_to_var_gemm(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
+                                impl):
+        H = _arr(A_hi, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, :V].astype(np.float64)
+        L = _arr(A_lo, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, :V].astype(np.float64)
+        Bh = _arr(B_hi, np.float16, V * ldv).reshape(V, ldv)[:, :V].astype(np.float64)
+        Bl = _arr(B_lo, np.float16, V * ldv).reshape(V, ldv)[:, :V].astype(np.float64)
+        out = H @ Bh.T + H @ Bl.T + L @ Bh.T
+        Dm = _arr(D, np.float32, (d_row0 + n_rows) * ldd).reshape(-1, ldd)
+        Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
+
+    def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs):
+        gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
+        ir = _arr(in_row, np.int32, max(int(go[-1]), 1)); lab = _arr(label, np.int32, n_groups)
+        Uo = _arr(U, np.float32, (int(gu.max()) + 1) * ldv).reshape(-1, ldv)
+        Dm = _arr(D, np.float32, (max(int(ir.max()), 0) + 1) * ldv).reshape(-1, ldv)
+        lp, t1, rk = _arr(logp, np.float64, n_groups), _arr(top1, np.int32, n_groups), _arr(rank, np.int32, n_groups)
+        B = _arr(beliefs, np.float32, n_groups * ldv).reshape(-1, ldv) if beliefs is not None and beliefs.value else None
+        for g in range(n_groups):
+            p = Uo[gu[g], :V].astype(np.float64)
+            for r in ir[go[g]:go[g + 1]]:
+                if r >= 0:
+                    p = p * Dm[r, :V].astype(np.float64)
+            s = p.sum()
+            b = p / s if s > 0 else np.full(V, 1.0 / V)
+            lp[g] = np.log(b[lab[g]]) if b[lab[g]] > 0 else -99.99
+            t1[g] = int(np.argmax(b)); rk[g] = int((b > b[lab[g]]).sum())
+            if B is not None:
+                B[g, :V] = b
+
+    def mlbp_pair_expectations(self, n_factors, c_row, u0_row, u1_row, u2_row, A_hi, A_lo, D, ldv, V, stats):
+        cr, r0, r1, r2 = (_arr(x, np.int32, n_factors) for x in (c_row, u0_row, u1_row, u2_row))
+        H = _arr(A_hi, np.float16, (int(cr.max()) + 1) * ldv).reshape(-1, ldv)
+        L = _arr(A_lo, np.float16, (int(cr.max()) + 1) * ldv).reshape(-1, ldv)
+        Dm = _arr(D, np.float32, (max(int(r0.max()), int(r1.max()), int(r2.max())) + 1) * ldv).reshape(-1, ldv)
+        st = _arr(stats, np.float64, n_factors * 3).reshape(-1, 3)
+        for f in range(n_factors):
+            c = H[cr[f], :V].astype(np.float64) + L[cr[f], :V].astype(np.float64)
+            st[f, 0] = c @ Dm[r0[f], :V].astype(np.float64)
+            st[f, 1] = c @ Dm[r1[f], :V].astype(np.float64)
+            st[f, 2] = c @ Dm[r2[f], :V].astype(np.float64) if r2[f] >= 0 else 0.0
+
+    def mlbp_gradient_reduce(self, n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, l0, l1, gap1, pmi, w1, ldf,
+                             logp_var, grad, logp_sent):
+        vo, fo = _arr(sent_var_off, np.int32, n_sent + 1), _arr(sent_fac_off, np.int32, n_sent + 1)
+        nv, nf = int(vo[-1]), int(fo[-1])
+        gu = _arr(g_unary, np.float64, nv * 9).reshape(-1, 9)
+        st = _arr(pair_stats, np.float64, max(nf, 1) * 3).reshape(-1, 3)
+        a0, a1, g1 = (_arr(x, np.int32, max(nf, 1)) for x in (l0, l1, gap1))
+        V = ldf   # only cells are read
+        lv = _arr(logp_var, np.float64, nv) if logp_var is not None and logp_var.value else None
+        G = _arr(grad, np.float64, n_sent * 9).reshape(-1, 9); LS = _arr(logp_sent, np.float64, n_sent)
+        for s in range(n_sent):
+            g = gu[vo[s]:vo[s + 1]].sum(0)
+            for f in range(fo[s], fo[s + 1]):
+                cell = int(a0[f]) * ldf + int(a1[f])
+                z = st[f, 0]
+                g[0] += float(_arr(pmi, np.float32, cell + 1)[cell]) - (st[f, 1] / z if z > 0 else 0.0)
+                if g1[f]:
+                    g[1] += float(_arr(w1, np.float32, cell + 1)[cell]) - (st[f, 2] / z if z > 0 else 0.0)
+                g[2] += 0.0 if z > 0 else 1.0
+            G[s] = g
+            LS[s] = lv[vo[s]:vo[s + 1]].sum() if lv is not None else 0.0
