@@ -1,0 +1,55 @@
+"""Time the K4 message GEMM alone at a given size (CUDA events, L2 flushed by size: operands >> 126 MB)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from macaronicusermodeling_b200 import _lib, build  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--M', type=int, default=16384)
+    ap.add_argument('--V', type=int, default=10000)
+    ap.add_argument('--iters', type=int, default=5)
+    ap.add_argument('--impl', type=int, default=0)
+    a = ap.parse_args()
+    build.build()
+    lib = _lib.require_device()
+    V, M = a.V, a.M
+    ld = (V + 63) // 64 * 64
+    g = torch.Generator(device='cuda').manual_seed(1)
+    Ah = (torch.rand((M, ld), device='cuda', generator=g) * 4).half()
+    Al = (torch.rand((M, ld), device='cuda', generator=g) * 1e-3).half()
+    Bh = (torch.rand((V, ld), device='cuda', generator=g) * 4).half()
+    Bl = (torch.rand((V, ld), device='cuda', generator=g) * 1e-3).half()
+    D = torch.empty((M, ld), dtype=torch.float32, device='cuda')
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run():
+        _lib.check(lib.mlbp_factor_to_var_gemm(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, a.impl, st))
+
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    flops = 2.0 * M * V * V
+    ref = (Ah[:64, :V].double() + Al[:64, :V].double()) @ (Bh[:, :V].double() + Bl[:, :V].double()).T
+    err = ((D[:64, :V].double() - ref).abs().max() / ref.abs().max()).item()
+    print(json.dumps({'M': M, 'V': V, 'ms': ms, 'algorithmic_tflops': flops / ms / 1e9, 'executed_tflops': 3 * flops / ms / 1e9,
+                      'rel_err_first_rows': err, 'timeout_code': lib.mlbp_gemm_barrier_timeout_code()}))
+
+
+if __name__ == '__main__':
+    main()
