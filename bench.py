@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""LBP training throughput on B200 (BASELINE.json metric) next to the CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (torchrun launches N ranks for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  the CPU arm: the oracle port of the reference's path
+
+A step = one synchronous minibatch SGD step of the hot path over one batch of synthetic macaronic sentences:
+table build for the current theta (K2), unary products (K1), 3 sweeps of level-batched message passing
+(K3 + K4), gradient (K4 + K6), marginals / log-posterior / precision counts (K5), the 16-float64 all-reduce and
+the theta update.  Workload at N = 1 is BASELINE config C3 (4096 sentences, V = 10 000, Vd = 2 000, k = 20
+predicted tokens, 3 sweeps); with N > 1 every rank gets its own 4096 sentences (weak scaling, no data-path
+collective besides the theta-gradient all-reduce).
+
+`value` is measured with the sentence index arrays already resident in HBM; `e2e` re-measures the same steps
+through the public API with HOST sentence arrays (H2D of the index arrays and schedules, D2H of the reduced
+gradient inside the timed region).  The feature planes are model state (the reference loads them once,
+train.py:589-612) and stay resident in both.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = 'LBP sentences/sec (train, 3 iters, V=10k)'
+UNIT = 'sentences/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sentences', type=int, default=4096, help='sentences per GPU per step')
+    ap.add_argument('--V', type=int, default=10000)
+    ap.add_argument('--Vd', type=int, default=2000)
+    ap.add_argument('--k', type=int, default=20)
+    ap.add_argument('--g', type=int, default=0)
+    ap.add_argument('--sweeps', type=int, default=3)
+    ap.add_argument('--workspace-gb', type=float, default=48.0)
+    ap.add_argument('--cpu-sample', type=int, default=6, help='sentences timed on the CPU for cpu_baseline')
+    ap.add_argument('--ref-sample', type=int, default=2, help='sentences per step of the --impl reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ('C3 batched training: %d sentences/GPU/step, V=%d, Vd=%d, k=%d predicted + %d given tokens, %d sweeps, '
+            'shared pairwise tables' % (a.sentences, a.V, a.Vd, a.k, a.g, a.sweeps))
+
+
+def make_inputs(a, rank, n_sent):
+    from macaronicusermodeling_b200 import synth
+    model = synth.make_model(a.V, a.Vd, seed=1234, dtype=np.float32)
+    sents = synth.make_corpus(model, n_sent, k=a.k, g=a.g, seed=1234 + 7919 * rank)
+    return model, sents
+
+
+def theta0():
+    # mid-training magnitudes (theta = 0, the reference's start, makes every potential 1 and every belief tie)
+    return np.array([0.8, 0.5, -0.3]), np.array([1.0, -0.6, 0.5, 0.3, 0.4, -0.2])
+
+
+def local_roots(corpus, sweeps, rng):
+    k = np.diff(corpus.var_off)
+    return (rng.random((corpus.n_sent, 1 + sweeps)) * k[:, None]).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith('active') and not v.lower().startswith('not'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_run(a, n_sent, model=None, sents=None):
+    """the oracle's fast evaluator (hoisted potentials, closed-form gradient, level-batched BLAS) -- the strongest
+    fair CPU variant of the reference's path, all host threads"""
+    from oracle import lbp_oracle as orc
+    from macaronicusermodeling_b200 import synth
+    if model is None:
+        model, sents = make_inputs(a, 0, n_sent)
+    m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
+    te, td = theta0()
+    roots = synth.draw_roots(sents[:n_sent], a.sweeps, seed=5)
+    t0 = time.perf_counter()
+    tb = orc.Tables(m64, te, td)
+    t_tables = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for s, r in zip(sents[:n_sent], roots):
+        orc.run_fast(tb, s, r, a.sweeps)
+    t_sent = time.perf_counter() - t0
+    return t_tables, t_sent, tb
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def reference_arm(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import lbp_oracle as orc
+    from macaronicusermodeling_b200 import synth
+    n = a.ref_sample
+    model, sents = make_inputs(a, 0, max(n, 1))
+    m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
+    te, td = theta0()
+    roots = synth.draw_roots(sents, a.sweeps, seed=5)
+
+    def step():
+        tb = orc.Tables(m64, te, td)       # theta changes every SGD step: the tables are rebuilt once per step
+        for s, r in zip(sents[:n], roots[:n]):
+            orc.run_fast(tb, s, r, a.sweeps)
+
+    for _ in range(a.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * a.steps / dt
+    cores = host_threads()
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': 1e3 * dt / a.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload_name(a),
+                       'note': 'CPU arm: oracle port of the reference path, fast variant (potentials hoisted to once '
+                               'per step, closed-form gradient, level-batched dgemm); each step is a bounded sample of '
+                               '%d sentences of the workload' % n},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d sentences x %d steps, tables rebuilt per step' % (n, a.steps)},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def ours(a):
+    import torch
+    import torch.distributed as dist
+    from macaronicusermodeling_b200.engine import Corpus, Engine
+    from macaronicusermodeling_b200.trainer import Trainer
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert world == a.gpus or world == 1, (world, a.gpus)
+
+    model, sents = make_inputs(a, rank, a.sentences)
+    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)))
+    tr = Trainer(eng, reg_param=0.2, N=a.sentences * world, sweeps=a.sweeps)
+    tr.theta_ee, tr.theta_ed = theta0()
+    corpus = Corpus(sents)
+    parts = eng.prepare(corpus, a.sweeps, True)
+    rng = np.random.default_rng(99 + rank)
+    lr = 1e-3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        red = tr.step(parts, local_roots(corpus, a.sweeps, rng), lr)
+        return tr.apply(red, lr)
+
+    def step_e2e():
+        c = Corpus(**{f: getattr(corpus, f) for f in Corpus.FIELDS})      # fresh host arrays: nothing cached on device
+        red = tr.step(c, local_roots(c, a.sweeps, rng), lr)
+        h = tr.apply(red, lr)
+        return c, h
+
+    for _ in range(a.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, g0 = eng.launches, eng.gemm_launches
+    eng.profile_gemm = True
+    eng.gemm_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    eng.profile_gemm = False
+    launches = eng.launches - l0
+    gemm_ms = sum(x.elapsed_time(y) for x, y, _ in eng.gemm_events)
+    gemm_rows = sum(r for _, _, r in eng.gemm_events)
+    n_gemm = len(eng.gemm_events)
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = a.sentences * world * a.steps / (ms / 1e3)
+
+    # ---- e2e: host sentence arrays in, reduced gradient out, every step
+    e2e = None
+    if not a.no_e2e:
+        step_e2e()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        blob0 = eng.blob_bytes
+        f0.record()
+        for _ in range(a.steps):
+            step_e2e()
+        f1.record()
+        barrier()
+        t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms2 = float(t2.item())
+        # index arrays of every micro-batch slice + roots are re-uploaded; schedules (plan blobs) are uploaded in both modes
+        idx_bytes = sum(getattr(corpus, f).nbytes for f in Corpus.FIELDS if f != 'var_pos')
+        e2e = {'value': a.sentences * world * a.steps / (ms2 / 1e3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(idx_bytes + corpus.n_sent * (1 + a.sweeps) * 4 + (eng.blob_bytes - blob0) / a.steps), 'd2h_bytes_per_step': 16 * 8,
+               'ms_per_step': ms2 / a.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    which = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    flops = 2.0 * gemm_rows * a.V * a.V
+    ach = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_split_f16_kernel (K4)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': ach / peak_tf, 'traffic': None, 'peak_source': which,
+                'executed_tflops': 3.0 * ach, 'executed_frac': 3.0 * ach / peak_tf,
+                'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(n_gemm, 1),
+                'algorithmic_flops_per_launch': flops / max(n_gemm, 1), 'share_of_step': gemm_ms / ms,
+                'note': 'algorithmic flops 2*rows*V*V counted once; the kernel issues 3 fp16 MMA passes (hi*hi, hi*lo, lo*hi)'}
+    cpu_baseline = None
+    if not a.no_cpu_baseline:
+        n = a.cpu_sample
+        t_tab, t_sent, _ = cpu_run(a, n, model, sents)
+        # one table build per SGD step is amortised over the step's sentences exactly like on the GPU
+        per_sent = t_sent / n + t_tab / float(a.sentences)
+        cpu_baseline = {'value': 1.0 / per_sent, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
+                        'sample': '%d sentences of the workload (%.1f s) + one table build (%.1f s, amortised over %d '
+                                  'sentences/step); oracle fast variant, float64, all BLAS threads' % (n, t_sent, t_tab, a.sentences)}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 accumulate over fp16 hi+lo split operands; f64 message products', 'data': 'synthetic',
+            'config': {'workload': workload_name(a), 'global_sentences_per_step': a.sentences * world,
+                       'parallelism': 'dp%d (sentences sharded, 16 x f64 all-reduce per step)' % world,
+                       'l2': 'inputs larger than L2: table planes 2.8 GB, message blocks > 10 GB per micro-batch',
+                       'micro_batches_per_step': len(parts)},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        reference_arm(a)
+    else:
+        ours(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -10,12 +10,20 @@
 // (22 significant bits) and the product is issued as three MMAs  hi*hi + hi*lo + lo*hi  into one fp32 TMEM
 // accumulator (the dropped lo*lo term is 2^-22 relative).  Roofline flops are counted once (2*M*N*K).
 //
+// Accumulation: measured on B200, the tensor core aligns every product to the accumulator's exponent and
+// truncates, so a K-long accumulation in TMEM is biased by about (K/4) * 2^-24 relative (1.8e-4 at K = 10^4) with
+// an element-dependent part of the same order -- enough to flip near-tied arg-maxes.  The accumulator is therefore
+// kept SHORT: every CHUNK_KB k-blocks (CHUNK_KB * 64 products) the MMA issuer switches to the other of two TMEM
+// accumulators and the epilogue warps drain the finished one into fp32 registers (round-to-nearest adds), which
+// brings the error back to ~1e-6 relative.
+//
 // Structure (one 128 x BN output tile per CTA, K = V streamed in 64-wide slabs):
 //   warp 0 lane 0 : TMA producer  -- 4 cp.async.bulk.tensor loads per stage (A.hi A.lo B.hi B.lo, swizzle-128B)
 //   warp 1 lane 0 : MMA issuer    -- 3 x (BK/16) tcgen05.mma.cta_group::1.kind::f16 per stage, tcgen05.commit
-//   warp 2        : TMEM allocate / free (BN fp32 columns)
-//   warps 4..7    : epilogue      -- tcgen05.ld 32x32b.x32, scale by alpha, 16-byte stores (row per thread)
-// full/empty mbarriers ring the shared-memory stages; one more mbarrier hands the accumulator to the epilogue.
+//   warp 2        : TMEM allocate / free (2 x BN fp32 columns)
+//   warps 4..     : epilogue      -- one warp per (32 TMEM lanes, 128 columns): tcgen05.ld 32x32b.x32 per chunk into
+//                                    128 register accumulators, finally scale by alpha and 16-byte stores
+// full/empty mbarriers ring the shared-memory stages; tmem_full/tmem_empty mbarriers ring the two accumulators.
 // CTAs are rasterised 16 M-tiles deep so that co-resident CTAs share A and B slabs in L2.
 #include <cuda.h>
 
@@ -34,18 +42,20 @@ constexpr int BM = 128;
 constexpr int BK = 64;            // 64 fp16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int GROUP_M = 16;
-constexpr int GEMM_THREADS = 256;
 constexpr unsigned long long WAIT_LIMIT_CYCLES = 8000000000ull;  // ~4 s: a stuck barrier traps instead of hanging the GPU
 
 template <int BN, int STAGES>
 struct Cfg {
+    static constexpr int EPI_WARPS = 4 * (BN / 128);          // one warp per (lane quarter, 128-column half)
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+    static constexpr int TMEM_COLS = 2 * BN;                   // two accumulators
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N");
+    static_assert(BN == 128 || BN == 256, "UMMA N");
 };
 
 // ------------------------------------------------------------------------------------------------- PTX wrappers
@@ -57,6 +67,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -134,8 +149,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int STAGES, int CHUNK_KB>
+__global__ void __launch_bounds__(Cfg<BN, STAGES>::THREADS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                       float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
@@ -144,12 +159,13 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(STAGES + s); };
-    const uint32_t accum_bar = bar_base + 8u * (uint32_t)(2 * STAGES);
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * STAGES + 2 + b); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -160,6 +176,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     const int gsize = min(GROUP_M, m_tiles - first_m);
     const int m_blk = first_m + in_grp % gsize, n_blk = in_grp / gsize;
     const int num_kb = (V + BK - 1) / BK;
+    const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
@@ -167,12 +184,12 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), C::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BN)
+                     "r"((uint32_t)C::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -181,8 +198,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {
+    if (warp < 4) {
+        if (warp == 0 && lane == 0) {
             // ===================== TMA producer =====================
             const int row_a = a_row0 + m_blk * BM, row_b = n_blk * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -196,16 +213,21 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                 tma_load_2d(&tm_b_hi, full_bar(s), st + 2 * C::A_BYTES, kb * BK, row_b);
                 tma_load_2d(&tm_b_lo, full_bar(s), st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
             constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                const int chunk = kb / CHUNK_KB, in_chunk = kb % CHUNK_KB;
+                const int buf = chunk & 1;
+                if (in_chunk == 0) {                              // accumulator must have been drained
+                    mbar_wait(tempty_bar(buf), ((uint32_t)(chunk >> 1) & 1u) ^ 1u, err_flag, 4);
+                    tc_fence_after();
+                }
                 mbar_wait(full_bar(s), ph, err_flag, 2);
                 tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
                 const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::A_BYTES);
                 const uint64_t b_hi = umma_desc_sw128(st + 2 * C::A_BYTES);
@@ -213,38 +235,50 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K step inside the atom
-                    tc_mma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_mma_f16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                    tc_mma_f16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+                    tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
+                    tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    tc_mma_f16(acc, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
-                tc_commit(empty_bar(s));          // frees the stage when the MMAs above have read it
+                tc_commit(empty_bar(s));                          // frees the stage when the MMAs above have read it
+                if (in_chunk == CHUNK_KB - 1 || kb == num_kb - 1) tc_commit(tfull_bar(buf));   // chunk accumulator complete
             }
-            tc_commit(accum_bar);                 // accumulator complete
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        mbar_wait(accum_bar, 0u, err_flag, 3);
-        tc_fence_after();
+    } else {
+        // ===================== epilogue: drain every chunk into fp32 registers =====================
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int m = m_blk * BM + q * 32 + lane;
-        const bool row_ok = m < n_rows;
-        float *drow = D + (d_row0 + (int64_t)m) * (int64_t)ldd;
-        const int n0 = n_blk * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            const int nc = n0 + c * 32;
-            if (row_ok && nc < ldd) {                             // ldd is a multiple of 64: chunk is all-in or all-out
+        const int half = (warp - 4) >> 2;                         // which 128-column half of the tile
+        float acc[128];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+        for (int c = 0; c < num_chunks; ++c) {
+            const int buf = c & 1;
+            mbar_wait(tfull_bar(buf), (uint32_t)(c >> 1) & 1u, err_flag, 3);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t r[32];
+                tmem_ld_32x32(t0 + (uint32_t)(j * 32), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        const int m = m_blk * BM + q * 32 + lane;
+        if (m < n_rows) {
+            float *drow = D + (d_row0 + (int64_t)m) * (int64_t)ldd;
+            const int n0 = n_blk * BN + half * 128;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int nc = n0 + 4 * j;
+                if (nc < ldd) {                                   // ldd is a multiple of 64: a float4 is all-in or all-out
                     float4 o;
-                    o.x = __uint_as_float(r[4 * j + 0]) * alpha;
-                    o.y = __uint_as_float(r[4 * j + 1]) * alpha;
-                    o.z = __uint_as_float(r[4 * j + 2]) * alpha;
-                    o.w = __uint_as_float(r[4 * j + 3]) * alpha;
-                    *reinterpret_cast<float4 *>(drow + nc + 4 * j) = o;
+                    o.x = acc[4 * j + 0] * alpha; o.y = acc[4 * j + 1] * alpha;
+                    o.z = acc[4 * j + 2] * alpha; o.w = acc[4 * j + 3] * alpha;
+                    *reinterpret_cast<float4 *>(drow + nc) = o;
                 }
             }
         }
@@ -252,7 +286,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
     }
 }
 
@@ -315,7 +350,7 @@ static int cached_map(CUtensorMap *out, const void *ptr, int64_t rows, int cols,
 
 static int *g_err_flag = nullptr;   // pinned, mapped: the kernel records which barrier timed out before trapping
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CHUNK_KB>
 static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                      const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
                      cudaStream_t st) {
@@ -328,7 +363,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, BN)) != MLBP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, STAGES, CHUNK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
         attr_set = true;
     }
@@ -339,7 +374,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     int *d_flag = nullptr;
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_tiles = (n_rows + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
-    gemm_split_f16_kernel<BN, STAGES><<<m_tiles * n_tiles, GEMM_THREADS, C::SMEM_BYTES, st>>>(
+    gemm_split_f16_kernel<BN, STAGES, CHUNK_KB><<<m_tiles * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
@@ -366,8 +401,22 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
     cudaStream_t st = as_stream(stream);
     if (impl == 1)
         return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
-    MLBP_CHECK_ARG(impl == 0, "factor_to_var_gemm: impl must be 0 (tcgen05) or 1 (SIMT cross-check)");
-    // BN = 256 halves the A re-reads; small vocabularies use the narrower tile to fill more SMs
-    if (V > 2048) return launch_tc<256, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
-    return launch_tc<128, 3>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
+    // impl 0: product configuration.  impl 10..: tuning variants exposed for scripts/gemm_probe.py only.
+#define MLBP_TC(BN_, ST_, CH_) \
+    return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st)
+    switch (impl) {
+        case 0: if (V > 2048) { MLBP_TC(256, 2, 2); } else { MLBP_TC(128, 3, 2); }
+        case 10: MLBP_TC(256, 2, 1);
+        case 11: MLBP_TC(256, 2, 2);
+        case 12: MLBP_TC(256, 2, 4);
+        case 13: MLBP_TC(256, 2, 1 << 20);      // never flush: one TMEM accumulation over all of K
+        case 14: MLBP_TC(128, 3, 1);
+        case 15: MLBP_TC(128, 3, 2);
+        case 16: MLBP_TC(128, 3, 4);
+        case 17: MLBP_TC(128, 3, 1 << 20);
+        default: break;
+    }
+#undef MLBP_TC
+    set_error("factor_to_var_gemm: unknown impl %d", impl);
+    return MLBP_ERR_INVALID;
 }

@@ -181,6 +181,7 @@ class Corpus(object):
             t = torch.from_numpy(np.ascontiguousarray(a))
             if len(a) == 0:
                 t = torch.zeros(1, dtype=t.dtype)          # keep a valid pointer for empty CSR payloads
+            self.h2d_bytes = getattr(self, 'h2d_bytes', 0) + t.numel() * t.element_size()
             self._dev[key] = t.to(device)
         return self._dev[key]
 
@@ -218,6 +219,10 @@ class Engine(object):
         self._blob_event = None     # H2D copy of the previous plan blob (the pinned buffer is reused)
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
         self.gemm_rows = 0          # GEMM rows executed (algorithmic GEMV count)
+        self.gemm_launches = 0
+        self.blob_bytes = 0         # schedule bytes uploaded (H2D) so far
+        self.profile_gemm = False   # record a CUDA-event pair around every K4 launch (bench.py roofline)
+        self.gemm_events = []
 
     # ------------------------------------------------------------------ theta -> tables (K2)
     def set_theta(self, theta_ee, theta_ed, with_grad=True):
@@ -297,6 +302,7 @@ class Engine(object):
             lib.mlbp_plan_destroy(handle)
         blob = self._blob_host.numpy()[:words]
         self._blob_dev[:words].copy_(self._blob_host[:words], non_blocking=True)
+        self.blob_bytes += 4 * words
         if self.device.type == 'cuda':
             self._blob_event = torch.cuda.Event()
             self._blob_event.record()
@@ -325,9 +331,16 @@ class Engine(object):
         def gemm_calls(off, n):
             for i in range(n):
                 t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
+                if self.profile_gemm:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0, rows, _p(self.plane(t, 0)),
                        _p(self.plane(t, 1)), V, ld, _p(D), d0, ld, alpha, self.gemm_impl)
+                if self.profile_gemm:
+                    e1.record()
+                    self.gemm_events.append((e0, e1, rows))
                 self.launches += 1
+                self.gemm_launches += 1
                 self.gemm_rows += rows
 
         for L in range(int(blob[H_NLEVELS])):
@@ -391,6 +404,28 @@ class Engine(object):
             acc += int(rows[s])
         out.append((lo, corpus.n_sent))
         return out
+
+    def prepare(self, corpus, sweeps=3, want_grad=True):
+        """Micro-batch slices of `corpus` with their index arrays already resident on the device."""
+        parts = []
+        for lo, hi in self.microbatches(corpus, sweeps, want_grad):
+            c = corpus.slice(lo, hi) if (lo, hi) != (0, corpus.n_sent) else corpus
+            for name in Corpus.FIELDS:
+                if name != 'var_pos':
+                    c.dev(name, self.device)
+            parts.append((lo, hi, c))
+        return parts
+
+    def run_prepared(self, parts, roots, sweeps=3, want_grad=True, want_marg=True):
+        roots = np.ascontiguousarray(roots, dtype=np.int32)
+        grads, logps, top1s, ranks = [], [], [], []
+        for lo, hi, c in parts:
+            r = self.run(c, roots[lo:hi], sweeps, want_grad, want_marg)
+            grads.append(r.grad); logps.append(r.logp)
+            if want_marg:
+                top1s.append(r.top1); ranks.append(r.rank)
+        cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs)
+        return cat(grads), cat(logps), (cat(top1s) if top1s else None), (cat(ranks) if ranks else None)
 
     def run_many(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True):
         """Micro-batched run over a large corpus; returns (grad [B, 9], logp [B], top1 [NV], rank [NV]) on device.

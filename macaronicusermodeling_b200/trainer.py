@@ -1,0 +1,87 @@
+"""Trainer-level semantics of train.py / train_mp.py on top of the batched engine.
+
+Reference (one sentence per step, train.py:357-416, :617-638):
+    g_ee, g_ed = fg.return_gradient()       # lr * (g - (reg_param / N) * theta)        LBP.py:293-299, :322-327
+    theta += g                              # in place, before the next sentence      train.py:404-405
+train_mp.py ships sentences to a multiprocessing.Pool and sums the returned gradients under a lock
+(:405-424, :634-649) -- asynchronous SGD with stale theta.  Here a *minibatch* of sentences sees the same theta,
+per-GPU partial sums are all-reduced (one NCCL all-reduce of 16 float64 per step) and every rank applies the
+identical update
+    theta += lr * (sum_s g_s - n * (reg_param / N) * theta)
+which for a minibatch of one sentence on one GPU is exactly train.py's step (tests/test_gpu_trainer.py).
+"""
+import numpy as np
+import torch
+
+from .engine import Corpus, Engine
+
+
+def dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class Trainer(object):
+    def __init__(self, engine, reg_param=0.2, N=None, sweeps=3, init_lr=0.1):
+        self.engine = engine
+        self.reg_param = float(reg_param)
+        self.N = N                                  # len(training_instances), train.py:619 (reg = reg_param / N, :158)
+        self.sweeps = sweeps
+        self.init_lr = init_lr
+        self.theta_ee = np.zeros(3)                 # train.py:511
+        self.theta_ed = np.zeros(6)                 # train.py:514
+        self._red = None
+
+    def lr(self, epoch):
+        return self.init_lr / float(1.0 + epoch * 0.3)           # train.py:621
+
+    def step(self, parts_or_corpus, roots, lr, all_reduce=True):
+        """One synchronous minibatch SGD step over this rank's sentences.  Returns the 16-vector
+        [g_ee(3), g_ed(6), sum logp, p@0, p@25, p@50, n_vars, n_sent, 0] summed over all ranks (device tensor)."""
+        eng = self.engine
+        eng.set_theta(self.theta_ee, self.theta_ed)
+        if isinstance(parts_or_corpus, Corpus):
+            grad, logp, top1, rank = eng.run_many(parts_or_corpus, roots, self.sweeps, True, True)
+        else:
+            grad, logp, top1, rank = eng.run_prepared(parts_or_corpus, roots, self.sweeps, True, True)
+        red = torch.zeros(16, dtype=torch.float64, device=grad.device)
+        red[:9] = grad.sum(dim=0)
+        red[9] = logp.sum()
+        red[10] = (rank == 0).sum()
+        red[11] = (rank < 26).sum()
+        red[12] = (rank < 50).sum()
+        red[13] = rank.numel()
+        red[14] = grad.shape[0]
+        if all_reduce and dist_info()[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
+        self._red = red
+        return red
+
+    def apply(self, red, lr):
+        """theta update from the reduced vector (the only host<-device read of a step)"""
+        h = red.cpu().numpy()
+        n = h[14]
+        reg = self.reg_param / float(self.N if self.N else n)
+        self.theta_ee = self.theta_ee + lr * (h[0:3] - n * reg * self.theta_ee)
+        self.theta_ed = self.theta_ed + lr * (h[3:9] - n * reg * self.theta_ed)
+        return h
+
+
+def batch_sgd_many(engine, sentences, theta_ee, theta_ed, lr, roots_pos, reg_param=0.2, N=None, sweeps=3):
+    """train.batch_sgd (train.py:357-397) for MANY sentences at one theta: returns the reference's result list
+    [sent_id, logp, g_en_en (1,3), g_en_de (1,6), None] per sentence (gradients already lr * (g - reg * theta))."""
+    corpus = Corpus(sentences)
+    engine.set_theta(theta_ee, theta_ed)
+    roots = corpus.roots_from_positions(roots_pos)
+    grad, logp, _, _ = engine.run_many(corpus, roots, sweeps, True, True)
+    g, lp = grad.cpu().numpy(), logp.cpu().numpy()
+    reg = float(reg_param) / float(N if N else len(sentences))
+    te = np.asarray(theta_ee, dtype=np.float64).reshape(1, 3)
+    td = np.asarray(theta_ed, dtype=np.float64).reshape(1, 6)
+    out = []
+    for i, s in enumerate(sentences):
+        out.append([s.sent_id, float(lp[i]), lr * (g[i:i + 1, :3] - reg * te), lr * (g[i:i + 1, 3:] - reg * td), None])
+    return out

@@ -16,7 +16,7 @@ def main():
     ap.add_argument('--M', type=int, default=16384)
     ap.add_argument('--V', type=int, default=10000)
     ap.add_argument('--iters', type=int, default=5)
-    ap.add_argument('--impl', type=int, default=0)
+    ap.add_argument('--impl', type=int, nargs='+', default=[0])
     a = ap.parse_args()
     build.build()
     lib = _lib.require_device()
@@ -31,24 +31,28 @@ def main():
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def run():
-        _lib.check(lib.mlbp_factor_to_var_gemm(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, a.impl, st))
-
-    for _ in range(2):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.iters):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.iters
-    flops = 2.0 * M * V * V
     ref = (Ah[:64, :V].double() + Al[:64, :V].double()) @ (Bh[:, :V].double() + Bl[:, :V].double()).T
-    err = ((D[:64, :V].double() - ref).abs().max() / ref.abs().max()).item()
-    print(json.dumps({'M': M, 'V': V, 'ms': ms, 'algorithmic_tflops': flops / ms / 1e9, 'executed_tflops': 3 * flops / ms / 1e9,
-                      'rel_err_first_rows': err, 'timeout_code': lib.mlbp_gemm_barrier_timeout_code()}))
+    ref -= Al[:64, :V].double() @ Bl[:, :V].double().T          # the kernel drops lo*lo by design
+    for impl in a.impl:
+        def run():
+            _lib.check(lib.mlbp_factor_to_var_gemm(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, impl, st))
+
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        flops = 2.0 * M * V * V
+        rel = ((D[:64, :V].double() - ref) / ref)
+        print(json.dumps({'impl': impl, 'M': M, 'V': V, 'ms': round(ms, 4), 'algorithmic_tflops': round(flops / ms / 1e9, 1),
+                          'executed_tflops': round(3 * flops / ms / 1e9, 1), 'rel_err_max': rel.abs().max().item(),
+                          'rel_err_mean': rel.mean().item(), 'rel_err_std': rel.std().item(),
+                          'timeout_code': lib.mlbp_gemm_barrier_timeout_code()}), flush=True)
 
 
 if __name__ == '__main__':
