@@ -216,7 +216,7 @@ def ours(a):
     corpus = Corpus(sents)
     parts = eng.prepare(corpus, a.sweeps, True)
     rng = np.random.default_rng(99 + rank)
-    lr = 1e-3
+    lr = 0.1 / float(a.sentences * world)      # minibatch sum of gradients: the reference's 0.1 per sentence, averaged
 
     def barrier():
         if world > 1:

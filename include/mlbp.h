@@ -41,6 +41,8 @@ extern "C" {
 #define MLBP_TABLE_G1         5   /* T1 o PMI                                                                         */
 #define MLBP_TABLE_G1W        6   /* T1 o PMI_w1  : expectation of the pmi_w1 feature, gap == 1 factors only          */
 
+#define MLBP_N_SUMS           7   /* per-theta sum vectors written by mlbp_build_pairwise_tables                */
+#define MLBP_D_CONST_ROWS     5   /* D rows 1..4 hold the constant messages of the 4 message tables (row 0 spare) */
 #define MLBP_A_SCALE_LOG2    14   /* var->factor rows are stored as 2^14 * normalised message, split hi + lo fp16 */
 
 const char *mlbp_last_error(void);
@@ -68,8 +70,10 @@ int mlbp_dense_pointwise_multiply_f64(const double *m1, const double *m2, double
  *   planes: MLBP_N_PLANES fp16 arrays [V, ldv], plane p at planes + p*plane_stride, in the order
  *           T.hi T.lo Tt.hi Tt.lo T1.hi T1.lo T1t.hi T1t.lo G.hi G.lo G1.hi G1.lo G1w.hi G1w.lo,
  *           every value multiplied by 2^scale_exp before the hi/lo split (hi + lo carries 22 bits).
- *   colsums: [5, V] float64, UNscaled: sum_e T[e,y], sum_e T1[e,y], sum_e G[e,y], sum_e G1[e,y], sum_e G1w[e,y]
- *           (the normaliser and feature expectations of the unary en_en factors, LBP.py:540, :600-603).
+ *   colsums: [MLBP_N_SUMS, V] float64, UNscaled: sum_e T[e,y], sum_e T1[e,y], sum_e G[e,y], sum_e G1[e,y], sum_e G1w[e,y]
+ *           (the normaliser and feature expectations of the unary en_en factors, LBP.py:540, :600-603), then the
+ *           row sums sum_b T[a,b], sum_b T1[a,b]: together with the column sums they are the factor->variable
+ *           messages of a pairwise factor whose incoming message is still the uniform initial one (LBP.py:211-216).
  *   with_grad_planes = 0 skips planes 8..13 (inference only).                                        */
 int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1, int V, int ldf, const double *h_theta_ee,
                                int scale_exp, void *planes, int64_t plane_stride, int ldv, double *colsums,

@@ -17,13 +17,19 @@
 //     of the matching block of D;
 //   - a variable->factor update writes its result into the A-block row of every later GEMM row that reads that
 //     version (0..n destinations; versions nobody reads are dead code and dropped, as are their producers);
-//   - messages still at their initial uniform value are filled by mlbp_fill_uniform_rows / read as "row -1".
+//   - messages still at their initial uniform value are filled by mlbp_fill_uniform_rows / read as "row -1";
+//   - a factor->variable update that READS an initial uniform message is constant-folded: its result is the
+//     table's row / column sums (D rows 1..4, written once per theta), so sweep 1's first level costs no GEMM.
 //
 // Blob layout (int32 words), header first:
 //   [H_*] fixed header, then per-level records (LEV_WORDS each), then the index arrays they point to.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 #include "../../include/mlbp.h"
@@ -49,6 +55,7 @@ struct Op {
     int32_t live;
     int32_t in0, in1;  // range in Graph::inputs (producer op indices, -1 = initial uniform message)
     int32_t row;       // kind 1: index inside its (level, table) block; global A / D row after assignment
+    int32_t folded;    // kind 1 reading the initial uniform message: result is a per-table constant row, no GEMM row
     int32_t table;
 };
 
@@ -131,6 +138,7 @@ void add_f2v(Graph &g, Tracker &t, int f, int side) {           // FactorNode.up
     const int e_out = 2 * f + side, e_in = 2 * f + (1 - side);
     Op op{};
     op.kind = 1; op.f = f; op.side = side; op.live = 0; op.row = -1;
+    op.folded = t.cur_v2f[e_in] < 0 ? 1 : 0;
     op.table = g.gap1[f] ? (side == 0 ? MLBP_TABLE_T1 : MLBP_TABLE_T1T) : (side == 0 ? MLBP_TABLE_T : MLBP_TABLE_TT);
     op.in0 = (int32_t)g.inputs.size();
     g.inputs.push_back(t.cur_v2f[e_in]);
@@ -193,6 +201,20 @@ void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
 
 }  // namespace
 
+// per-thread output of the emit phase for a contiguous range of graphs
+struct ChunkOut {
+    std::vector<std::vector<int32_t>> grp_u, grp_off, in_row, dest_off, dest;   // [level]
+    std::vector<int32_t> init_rows, pair_c, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
+};
+
+template <class F>
+static void parallel_for_chunks(int n_chunks, F f) {
+    std::vector<std::thread> th;
+    for (int c = 1; c < n_chunks; ++c) th.emplace_back([=] { f(c); });
+    f(0);
+    for (auto &t : th) t.join();
+}
+
 extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int32_t *pair_off, const int32_t *pair_v0,
                                  const int32_t *pair_v1, const int32_t *pair_gap1, const int32_t *roots, int sweeps,
                                  int flags, mlbp_plan **out) {
@@ -201,190 +223,258 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         return MLBP_ERR_INVALID;
     }
     const bool want_grad = flags & 1, want_marg = flags & 2;
+    const bool prof = std::getenv("MLBP_PLAN_PROFILE") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_a = tnow();
     std::vector<Graph> G(n_graphs);
+    unsigned hw = std::thread::hardware_concurrency();
+    const char *env = std::getenv("MLBP_PLAN_THREADS");
+    int n_chunks = env ? std::atoi(env) : (int)std::min<unsigned>(hw ? hw : 1, 32);
+    n_chunks = std::max(1, std::min(n_chunks, (n_graphs + 15) / 16));
+    auto chunk_lo = [&](int c) { return (int)((int64_t)n_graphs * c / n_chunks); };
+
+    // ---- phase A (parallel): sequence, levels, liveness per graph
+    std::vector<int> err(n_chunks, 0), c_levels(n_chunks, 0), c_maxin(n_chunks, 0);
+    std::vector<int64_t> c_dead(n_chunks, 0);
+    parallel_for_chunks(n_chunks, [&](int c) {
+        std::vector<char> needed;
+        for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
+            Graph &g = G[gi];
+            g.nv = var_off[gi + 1] - var_off[gi];
+            g.np = pair_off[gi + 1] - pair_off[gi];
+            if (g.nv <= 0) { err[c] = 1; return; }
+            g.facset.assign(g.nv, {});
+            g.v0.resize(g.np); g.v1.resize(g.np); g.gap1.resize(g.np);
+            g.slot.resize(2 * (size_t)g.np);
+            for (int f = 0; f < g.np; ++f) {
+                const int a = pair_v0[pair_off[gi] + f], b = pair_v1[pair_off[gi] + f];
+                if (a < 0 || b < 0 || a >= g.nv || b >= g.nv || a == b) { err[c] = 2; return; }
+                g.v0[f] = a; g.v1[f] = b; g.gap1[f] = pair_gap1[pair_off[gi] + f] ? 1 : 0;
+                g.slot[2 * f] = (int32_t)g.facset[a].size();
+                g.facset[a].push_back(f);
+                g.slot[2 * f + 1] = (int32_t)g.facset[b].size();
+                g.facset[b].push_back(f);
+            }
+            const int32_t *r = roots + (size_t)gi * (1 + sweeps);
+            for (int i = 0; i <= sweeps; ++i)
+                if (r[i] < 0 || r[i] >= g.nv) { err[c] = 3; return; }
+            build_sequence(g, r, sweeps);
+            // liveness, reverse pass: an update is live iff a live update (or a final stage) reads its result
+            needed.assign(g.ops.size(), 0);
+            for (int e = 0; e < 2 * g.np; ++e) {
+                if (want_grad && g.fin_v2f[e] >= 0) needed[g.fin_v2f[e]] = 1;
+                if (want_marg && g.fin_f2v[e] >= 0) needed[g.fin_f2v[e]] = 1;
+            }
+            for (size_t i = g.ops.size(); i-- > 0;) {
+                Op &o = g.ops[i];
+                o.live = needed[i];
+                if (!o.live) { ++c_dead[c]; continue; }
+                for (int k = o.in0; k < o.in1; ++k)
+                    if (g.inputs[k] >= 0) needed[g.inputs[k]] = 1;
+            }
+            c_levels[c] = std::max(c_levels[c], g.n_levels);
+            for (int v = 0; v < g.nv; ++v) c_maxin[c] = std::max(c_maxin[c], (int)g.facset[v].size());
+        }
+    });
     int n_levels = 0, max_in = 0;
     int64_t n_dead = 0;
-    for (int gi = 0; gi < n_graphs; ++gi) {
-        Graph &g = G[gi];
-        g.nv = var_off[gi + 1] - var_off[gi];
-        g.np = pair_off[gi + 1] - pair_off[gi];
-        if (g.nv <= 0) { mlbp::set_error("plan_compile: graph %d has no variables", gi); return MLBP_ERR_INVALID; }
-        g.facset.assign(g.nv, {});
-        g.v0.resize(g.np); g.v1.resize(g.np); g.gap1.resize(g.np);
-        for (int f = 0; f < g.np; ++f) {
-            const int a = pair_v0[pair_off[gi] + f], b = pair_v1[pair_off[gi] + f];
-            if (a < 0 || b < 0 || a >= g.nv || b >= g.nv || a == b) {
-                mlbp::set_error("plan_compile: graph %d factor %d has invalid variables (%d, %d)", gi, f, a, b);
-                return MLBP_ERR_INVALID;
-            }
-            g.v0[f] = a; g.v1[f] = b; g.gap1[f] = pair_gap1[pair_off[gi] + f] ? 1 : 0;
-            g.slot.resize(2 * (size_t)g.np);
-            g.slot[2 * f] = (int32_t)g.facset[a].size();
-            g.facset[a].push_back(f);
-            g.slot[2 * f + 1] = (int32_t)g.facset[b].size();
-            g.facset[b].push_back(f);
+    for (int c = 0; c < n_chunks; ++c) {
+        if (err[c]) {
+            mlbp::set_error("plan_compile: invalid graph (code %d: 1 = no variables, 2 = bad factor variables, 3 = root out of range)", err[c]);
+            return MLBP_ERR_INVALID;
         }
-        const int32_t *r = roots + (size_t)gi * (1 + sweeps);
-        for (int i = 0; i <= sweeps; ++i)
-            if (r[i] < 0 || r[i] >= g.nv) { mlbp::set_error("plan_compile: graph %d root %d out of range", gi, r[i]); return MLBP_ERR_INVALID; }
-        build_sequence(g, r, sweeps);
-        // liveness, reverse pass: an update is live iff a live update (or a final stage) reads its result
-        std::vector<char> needed(g.ops.size(), 0);
-        for (int e = 0; e < 2 * g.np; ++e) {
-            if (want_grad && g.fin_v2f[e] >= 0) needed[g.fin_v2f[e]] = 1;
-            if (want_marg && g.fin_f2v[e] >= 0) needed[g.fin_f2v[e]] = 1;
-        }
-        for (size_t i = g.ops.size(); i-- > 0;) {
-            Op &o = g.ops[i];
-            o.live = needed[i];
-            if (!o.live) { ++n_dead; continue; }
-            for (int k = o.in0; k < o.in1; ++k)
-                if (g.inputs[k] >= 0) needed[g.inputs[k]] = 1;
-        }
-        n_levels = std::max(n_levels, g.n_levels);
-        for (int v = 0; v < g.nv; ++v) max_in = std::max(max_in, (int)g.facset[v].size());
+        n_levels = std::max(n_levels, c_levels[c]); max_in = std::max(max_in, c_maxin[c]); n_dead += c_dead[c];
     }
 
-    // ---- row assignment: one A/D block per (level, table)
-    std::vector<int64_t> cnt((size_t)(n_levels + 1) * 4, 0);
-    for (Graph &g : G)
+    double t_b = tnow();
+    // ---- phase B (serial, cheap): one A/D block per (level, table); rows inside a block in graph order
+    const size_t LT = (size_t)(n_levels + 1) * 4;
+    std::vector<int64_t> cnt(LT, 0);
+    std::vector<int64_t> gbase((size_t)n_graphs * LT);            // first row index (inside the block) of each graph
+    std::vector<int64_t> g_i0(n_graphs), g_i1(n_graphs), g_ip(n_graphs);
+    int64_t n_pair = 0, n_gap0 = 0, n_gap1 = 0;
+    for (int gi = 0; gi < n_graphs; ++gi) {
+        Graph &g = G[gi];
+        int64_t *gb = &gbase[(size_t)gi * LT];
+        for (size_t i = 0; i < LT; ++i) gb[i] = cnt[i];
         for (Op &o : g.ops)
-            if (o.live && o.kind == 1) o.row = (int32_t)cnt[(size_t)o.level * 4 + o.table]++;
-    std::vector<int64_t> base((size_t)(n_levels + 1) * 4, 0);
+            if (o.live && o.kind == 1 && !o.folded) o.row = (int32_t)(cnt[(size_t)o.level * 4 + o.table]++ - gb[(size_t)o.level * 4 + o.table]);
+        g_i0[gi] = n_gap0; g_i1[gi] = n_gap1; g_ip[gi] = n_pair;
+        if (want_grad) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.gap1[f] ? n_gap1 : n_gap0)++; }
+    }
+    std::vector<int64_t> base(LT, 0);
     int64_t a_rows = 0;
     for (int L = 1; L <= n_levels; ++L)
         for (int t = 0; t < 4; ++t) { base[(size_t)L * 4 + t] = a_rows; a_rows += cnt[(size_t)L * 4 + t]; }
     const int64_t n_msg_rows = a_rows;
-    // D rows mirror A rows shifted by one (D row 0 is the constant-one row standing for uniform messages)
-    for (Graph &g : G)
-        for (Op &o : g.ops)
-            if (o.live && o.kind == 1) o.row = (int32_t)(base[(size_t)o.level * 4 + o.table] + o.row);
-    // gradient stage: r rows (gap>1 block, gap==1 block), then the c rows
-    int64_t n_pair = 0, n_gap0 = 0, n_gap1 = 0;
-    if (want_grad)
-        for (Graph &g : G) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.gap1[f] ? n_gap1 : n_gap0)++; }
+    // gradient stage: r rows (gap>1 block, gap==1 block), then the c rows; D row = 1 + A row for message rows
     const int64_t a_r0 = a_rows, a_r1 = a_r0 + n_gap0, a_c = a_r1 + n_gap1;
     a_rows = a_c + n_pair;
-    int64_t d_rows = 1 + n_msg_rows;
+    int64_t d_rows = MLBP_D_CONST_ROWS + n_msg_rows;
     const int64_t d_u0_0 = d_rows, d_u1_0 = d_u0_0 + n_gap0, d_u0_1 = d_u1_0 + n_gap0, d_u1_1 = d_u0_1 + n_gap1,
                   d_u2_1 = d_u1_1 + n_gap1;
     if (want_grad) d_rows = d_u2_1 + n_gap1;
     if (a_rows > 0x7fffff00ll || d_rows > 0x7fffff00ll) { mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
 
-    // ---- destinations of every variable->factor version: the A rows of the GEMM rows that read it
-    std::vector<std::vector<std::vector<int32_t>>> dests(n_graphs);
-    std::vector<int32_t> init_rows;
-    std::vector<int32_t> pair_c, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1;
-    {
-        int64_t i0 = 0, i1 = 0, ip = 0;
-        for (int gi = 0; gi < n_graphs; ++gi) {
+    double t_c = tnow();
+    // ---- phase C (parallel): global rows, destinations, leave-one-out groups per chunk
+    std::vector<ChunkOut> CO(n_chunks);
+    parallel_for_chunks(n_chunks, [&](int c) {
+        ChunkOut &co = CO[c];
+        co.grp_u.resize(n_levels + 1); co.grp_off.resize(n_levels + 1); co.in_row.resize(n_levels + 1);
+        co.dest_off.resize(n_levels + 1); co.dest.resize(n_levels + 1);
+        std::vector<int32_t> dcount, dstart, dflat, ver, tgt;
+        std::vector<std::vector<int32_t>> lev_ops(n_levels + 1);
+        for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
             Graph &g = G[gi];
-            dests[gi].assign(g.ops.size(), {});
-            for (Op &o : g.ops) {
-                if (!o.live || o.kind != 1) continue;
-                const int prod = g.inputs[o.in0];
-                if (prod >= 0) dests[gi][prod].push_back(o.row);
-                else init_rows.push_back(o.row);
-            }
-            if (!want_grad) continue;
-            for (int f = 0; f < g.np; ++f) {
-                const int pr = g.fin_v2f[2 * f + 1], pc = g.fin_v2f[2 * f + 0];
-                const int64_t rrow = g.gap1[f] ? a_r1 + i1 : a_r0 + i0;
-                const int64_t crow = a_c + ip;
-                if (pr >= 0) dests[gi][pr].push_back((int32_t)rrow); else init_rows.push_back((int32_t)rrow);
-                if (pc >= 0) dests[gi][pc].push_back((int32_t)crow); else init_rows.push_back((int32_t)crow);
-                pair_c.push_back((int32_t)crow);
-                if (g.gap1[f]) {
-                    pair_u0.push_back((int32_t)(d_u0_1 + i1)); pair_u1.push_back((int32_t)(d_u1_1 + i1));
-                    pair_u2.push_back((int32_t)(d_u2_1 + i1)); ++i1;
-                } else {
-                    pair_u0.push_back((int32_t)(d_u0_0 + i0)); pair_u1.push_back((int32_t)(d_u1_0 + i0));
-                    pair_u2.push_back(-1); ++i0;
+            const int64_t *gb = &gbase[(size_t)gi * LT];
+            for (Op &o : g.ops)
+                if (o.live && o.kind == 1 && !o.folded) o.row = (int32_t)(base[(size_t)o.level * 4 + o.table] + gb[(size_t)o.level * 4 + o.table] + o.row);
+            // destinations of every variable->factor version = A rows of the GEMM rows that read it (counting sort)
+            const size_t nops = g.ops.size();
+            dcount.assign(nops + 1, 0);
+            auto each_consumer = [&](auto &&fn) {
+                for (const Op &o : g.ops) {
+                    if (!o.live || o.kind != 1 || o.folded) continue;
+                    fn(g.inputs[o.in0], o.row);
                 }
-                pair_g1.push_back(g.gap1[f]);
-                pair_gv0.push_back(var_off[gi] + g.v0[f]);
-                pair_gv1.push_back(var_off[gi] + g.v1[f]);
-                ++ip;
+                if (want_grad) {
+                    int64_t i0 = g_i0[gi], i1 = g_i1[gi], ip = g_ip[gi];
+                    for (int f = 0; f < g.np; ++f) {
+                        const int64_t rrow = g.gap1[f] ? a_r1 + i1 : a_r0 + i0;
+                        fn(g.fin_v2f[2 * f + 1], (int32_t)rrow);
+                        fn(g.fin_v2f[2 * f + 0], (int32_t)(a_c + ip));
+                        (g.gap1[f] ? i1 : i0)++; ++ip;
+                    }
+                }
+            };
+            each_consumer([&](int prod, int32_t row) { if (prod >= 0) ++dcount[prod]; else co.init_rows.push_back(row); });
+            dstart.assign(nops + 1, 0);
+            for (size_t i = 0; i < nops; ++i) dstart[i + 1] = dstart[i] + dcount[i];
+            dflat.resize(dstart[nops]);
+            std::fill(dcount.begin(), dcount.end(), 0);
+            each_consumer([&](int prod, int32_t row) { if (prod >= 0) dflat[dstart[prod] + dcount[prod]++] = row; });
+            if (want_grad) {
+                int64_t i0 = g_i0[gi], i1 = g_i1[gi], ip = g_ip[gi];
+                for (int f = 0; f < g.np; ++f) {
+                    co.pair_c.push_back((int32_t)(a_c + ip));
+                    if (g.gap1[f]) {
+                        co.pair_u0.push_back((int32_t)(d_u0_1 + i1)); co.pair_u1.push_back((int32_t)(d_u1_1 + i1));
+                        co.pair_u2.push_back((int32_t)(d_u2_1 + i1)); ++i1;
+                    } else {
+                        co.pair_u0.push_back((int32_t)(d_u0_0 + i0)); co.pair_u1.push_back((int32_t)(d_u1_0 + i0));
+                        co.pair_u2.push_back(-1); ++i0;
+                    }
+                    co.pair_g1.push_back(g.gap1[f]);
+                    co.pair_gv0.push_back(var_off[gi] + g.v0[f]);
+                    co.pair_gv1.push_back(var_off[gi] + g.v1[f]);
+                    ++ip;
+                }
             }
+            auto d_row_of = [&](int prod) -> int32_t {
+                if (prod < 0) return -1;
+                return g.ops[prod].folded ? 1 + g.ops[prod].table : MLBP_D_CONST_ROWS + g.ops[prod].row;
+            };
+            // leave-one-out groups: live variable->factor updates of one (level, variable)
+            for (auto &v : lev_ops) v.clear();
+            for (size_t i = 0; i < nops; ++i)
+                if (g.ops[i].live && g.ops[i].kind == 0) lev_ops[g.ops[i].level].push_back((int32_t)i);
+            for (int L = 1; L <= g.n_levels; ++L) {
+                auto &lo = lev_ops[L];
+                if (lo.empty()) continue;
+                std::stable_sort(lo.begin(), lo.end(), [&](int32_t x, int32_t y) {
+                    return var_of(g, g.ops[x].f, g.ops[x].side) < var_of(g, g.ops[y].f, g.ops[y].side);
+                });
+                size_t i = 0;
+                while (i < lo.size()) {
+                    const int v = var_of(g, g.ops[lo[i]].f, g.ops[lo[i]].side);
+                    size_t j = i;
+                    while (j < lo.size() && var_of(g, g.ops[lo[j]].f, g.ops[lo[j]].side) == v) ++j;
+                    const auto &fs = g.facset[v];
+                    ver.assign(fs.size(), -2);                   // producer seen by a reader in this group; -2 = nobody reads
+                    tgt.assign(fs.size(), -1);                   // update that targets this edge
+                    for (size_t k = i; k < j; ++k) {
+                        const Op &o = g.ops[lo[k]];
+                        tgt[g.slot[2 * o.f + o.side]] = lo[k];
+                        for (int q = o.in0; q < o.in1; ++q) ver[g.slot[g.in_edge[q]]] = g.inputs[q];
+                    }
+                    co.grp_u[L].push_back(var_off[gi] + v);
+                    for (size_t s = 0; s < fs.size(); ++s) {
+                        co.in_row[L].push_back(ver[s] == -2 ? -1 : d_row_of(ver[s]));
+                        if (tgt[s] >= 0)
+                            co.dest[L].insert(co.dest[L].end(), dflat.begin() + dstart[tgt[s]], dflat.begin() + dstart[tgt[s] + 1]);
+                        co.dest_off[L].push_back((int32_t)co.dest[L].size());
+                    }
+                    co.grp_off[L].push_back((int32_t)co.in_row[L].size());
+                    i = j;
+                }
+            }
+            if (want_marg)
+                for (int v = 0; v < g.nv; ++v) {
+                    co.mu.push_back(var_off[gi] + v);
+                    for (int f : g.facset[v]) co.min_.push_back(d_row_of(g.fin_f2v[2 * f + ((g.v0[f] == v) ? 0 : 1)]));
+                    co.moff.push_back((int32_t)co.min_.size());
+                }
         }
-    }
+    });
 
-    // ---- emit
+    double t_d = tnow();
+    // ---- phase D: merge the chunks into the blob
     Plan *P = new (std::nothrow) Plan();
     if (!P) { mlbp::set_error("plan_compile: out of memory"); return MLBP_ERR_ALLOC; }
     std::vector<int32_t> &B = P->blob;
     B.assign(H_WORDS + (size_t)n_levels * LEV_WORDS, 0);
     auto append = [&](const std::vector<int32_t> &v) { int32_t o = (int32_t)B.size(); B.insert(B.end(), v.begin(), v.end()); return o; };
+    // concatenation of one member over the chunks; `shift` adds a running offset (CSR offsets) and prepends a 0
+    auto concat = [&](auto member, bool csr) {
+        const int32_t o = (int32_t)B.size();
+        int32_t run = 0;
+        if (csr) B.push_back(0);
+        for (int c = 0; c < n_chunks; ++c) {
+            const std::vector<int32_t> &v = member(CO[c]);
+            if (csr) { for (int32_t x : v) B.push_back(x + run); if (!v.empty()) run += v.back(); }
+            else B.insert(B.end(), v.begin(), v.end());
+        }
+        return o;
+    };
     B[H_NLEVELS] = n_levels; B[H_LEVELS_OFF] = H_WORDS; B[H_NGRAPHS] = n_graphs;
     B[H_A_ROWS] = (int32_t)a_rows; B[H_D_ROWS] = (int32_t)d_rows; B[H_MAX_IN] = max_in; B[H_NVARS] = var_off[n_graphs];
-
-    // D row of a factor->variable version (producer op) or -1 for the initial uniform message
-    auto d_row_of = [&](const Graph &g, int prod) -> int32_t { return prod < 0 ? -1 : 1 + g.ops[prod].row; };
-
-    // per level: leave-one-out groups keyed by (graph, variable)
-    std::vector<std::vector<std::pair<int, int>>> lev_ops(n_levels + 1);   // (graph, op) of live kind-0 ops per level
-    for (int gi = 0; gi < n_graphs; ++gi)
-        for (size_t i = 0; i < G[gi].ops.size(); ++i) {
-            const Op &o = G[gi].ops[i];
-            if (o.live && o.kind == 0) lev_ops[o.level].push_back({gi, (int)i});
-        }
     for (int L = 1; L <= n_levels; ++L) {
-        std::vector<int32_t> grp_u, grp_off, in_row, dest_off, dest;
-        grp_off.push_back(0);
-        dest_off.push_back(0);
-        auto &lo = lev_ops[L];
-        // group ops of the same (graph, variable); ops arrive graph-major, so sort within graph by variable (stable)
-        std::stable_sort(lo.begin(), lo.end(), [&](const std::pair<int, int> &x, const std::pair<int, int> &y) {
-            if (x.first != y.first) return x.first < y.first;
-            const Graph &g = G[x.first];
-            return var_of(g, g.ops[x.second].f, g.ops[x.second].side) < var_of(g, g.ops[y.second].f, g.ops[y.second].side);
-        });
-        size_t i = 0;
-        while (i < lo.size()) {
-            const int gi = lo[i].first;
-            const Graph &g = G[gi];
-            const int v = var_of(g, g.ops[lo[i].second].f, g.ops[lo[i].second].side);
-            size_t j = i;
-            while (j < lo.size() && lo[j].first == gi && var_of(g, g.ops[lo[j].second].f, g.ops[lo[j].second].side) == v) ++j;
-            const auto &fs = g.facset[v];
-            std::vector<int32_t> ver(fs.size(), -2);            // producer seen by a reader in this group; -2 = nobody reads
-            std::vector<int32_t> tgt(fs.size(), -1);            // op that targets this edge
-            for (size_t k = i; k < j; ++k) {
-                const Op &o = g.ops[lo[k].second];
-                tgt[g.slot[2 * o.f + o.side]] = lo[k].second;
-                for (int q = o.in0; q < o.in1; ++q) ver[g.slot[g.in_edge[q]]] = g.inputs[q];
-            }
-            grp_u.push_back(var_off[gi] + v);
-            for (size_t s = 0; s < fs.size(); ++s) {
-                in_row.push_back(ver[s] == -2 ? -1 : d_row_of(g, ver[s]));
-                if (tgt[s] >= 0) dest.insert(dest.end(), dests[gi][tgt[s]].begin(), dests[gi][tgt[s]].end());
-                dest_off.push_back((int32_t)dest.size());
-            }
-            grp_off.push_back((int32_t)in_row.size());
-            i = j;
-        }
+        int32_t ng = 0;
+        for (int c = 0; c < n_chunks; ++c) ng += (int32_t)CO[c].grp_u[L].size();
+        const int32_t o_u = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.grp_u[L]; }, false);
+        const int32_t o_off = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.grp_off[L]; }, true);
+        const int32_t o_in = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.in_row[L]; }, false);
+        const int32_t o_doff = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.dest_off[L]; }, true);
+        const int32_t o_dest = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.dest[L]; }, false);
         std::vector<int32_t> gemm;
         for (int t = 0; t < 4; ++t)
             if (cnt[(size_t)L * 4 + t] > 0) {
                 gemm.push_back(t);
                 gemm.push_back((int32_t)base[(size_t)L * 4 + t]);
-                gemm.push_back((int32_t)(1 + base[(size_t)L * 4 + t]));
+                gemm.push_back((int32_t)(MLBP_D_CONST_ROWS + base[(size_t)L * 4 + t]));
                 gemm.push_back((int32_t)cnt[(size_t)L * 4 + t]);
             }
+        const int32_t o_gemm = append(gemm);
         const size_t rec = H_WORDS + (size_t)(L - 1) * LEV_WORDS;
-        const int32_t ng = (int32_t)grp_u.size();
-        const int32_t o_u = append(grp_u), o_off = append(grp_off), o_in = append(in_row), o_doff = append(dest_off),
-                      o_dest = append(dest), o_gemm = append(gemm);
         B[rec + LEV_NGROUPS] = ng; B[rec + LEV_GRP_U] = o_u; B[rec + LEV_GRP_OFF] = o_off; B[rec + LEV_IN_ROW] = o_in;
         B[rec + LEV_DEST_OFF] = o_doff; B[rec + LEV_DEST] = o_dest; B[rec + LEV_NGEMM] = (int32_t)(gemm.size() / GEMM_WORDS);
         B[rec + LEV_GEMM] = o_gemm;
     }
-    B[H_INIT_N] = (int32_t)init_rows.size();
-    B[H_INIT_OFF] = append(init_rows);
+    {
+        int32_t n_init = 0;
+        for (int c = 0; c < n_chunks; ++c) n_init += (int32_t)CO[c].init_rows.size();
+        B[H_INIT_N] = n_init;
+        B[H_INIT_OFF] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.init_rows; }, false);
+    }
     B[H_NPAIR] = (int32_t)n_pair;
-    B[H_PAIR_C] = append(pair_c); B[H_PAIR_U0] = append(pair_u0); B[H_PAIR_U1] = append(pair_u1);
-    B[H_PAIR_U2] = append(pair_u2); B[H_PAIR_GAP1] = append(pair_g1);
-    B[H_PAIR_V0] = append(pair_gv0); B[H_PAIR_V1] = append(pair_gv1);
+    B[H_PAIR_C] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_c; }, false);
+    B[H_PAIR_U0] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u0; }, false);
+    B[H_PAIR_U1] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u1; }, false);
+    B[H_PAIR_U2] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u2; }, false);
+    B[H_PAIR_GAP1] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_g1; }, false);
+    B[H_PAIR_V0] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_gv0; }, false);
+    B[H_PAIR_V1] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_gv1; }, false);
     {
         std::vector<int32_t> gg;
         auto call = [&](int table, int64_t a0, int64_t d0, int64_t n) {
@@ -399,19 +489,12 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         B[H_GRAD_GEMM_OFF] = append(gg);
     }
     {
-        std::vector<int32_t> mu, moff, min_;
-        moff.push_back(0);
-        if (want_marg)
-            for (int gi = 0; gi < n_graphs; ++gi) {
-                const Graph &g = G[gi];
-                for (int v = 0; v < g.nv; ++v) {
-                    mu.push_back(var_off[gi] + v);
-                    for (int f : g.facset[v]) min_.push_back(d_row_of(g, g.fin_f2v[2 * f + ((g.v0[f] == v) ? 0 : 1)]));
-                    moff.push_back((int32_t)min_.size());
-                }
-            }
-        B[H_MARG_N] = (int32_t)mu.size();
-        B[H_MARG_U] = append(mu); B[H_MARG_OFF] = append(moff); B[H_MARG_IN] = append(min_);
+        int32_t nm = 0;
+        for (int c = 0; c < n_chunks; ++c) nm += (int32_t)CO[c].mu.size();
+        B[H_MARG_N] = nm;
+        B[H_MARG_U] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.mu; }, false);
+        B[H_MARG_OFF] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.moff; }, true);
+        B[H_MARG_IN] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.min_; }, false);
     }
     int64_t gemm_rows = n_msg_rows + (want_grad ? 2 * n_gap0 + 3 * n_gap1 : 0);
     std::memset(P->sizes, 0, sizeof(P->sizes));
@@ -424,6 +507,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     P->sizes[MLBP_PLAN_MAX_IN] = max_in;
     P->sizes[MLBP_PLAN_HDR_WORDS] = H_WORDS;
     P->sizes[MLBP_PLAN_N_DEAD] = n_dead;
+    if (prof) std::fprintf(stderr, "plan_compile: A %.1f ms  B %.1f ms  C %.1f ms  D %.1f ms (chunks %d)\n", 1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_d - t_c), 1e3 * (tnow() - t_d), n_chunks);
     *out = reinterpret_cast<mlbp_plan *>(P);
     return MLBP_OK;
 }

@@ -26,6 +26,7 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
     double cs[5] = {0, 0, 0, 0, 0};
     for (int r = ty; r < TS; r += 4) {
         const int a = a0 + r;
+        double rs_t = 0.0, rs_t1 = 0.0;
         __half h[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) h[i] = __float2half_rn(0.f);
@@ -36,6 +37,7 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
             const double t = exp(z), t1 = exp(z + th.w1 * w);
             const double g = t * p, g1 = t1 * p, g1w = t1 * w;
             cs[0] += t; cs[1] += t1; cs[2] += g; cs[3] += g1; cs[4] += g1w;
+            rs_t = t; rs_t1 = t1;
             const double v[5] = {t, t1, g, g1, g1w};
 #pragma unroll
             for (int i = 0; i < 5; ++i) split_f16((float)ldexp(v[i], scale_exp), h[2 * i], h[2 * i + 1]);
@@ -49,6 +51,12 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
             }
         }
         sT[0][r][tx] = h[0]; sT[1][r][tx] = h[1]; sT[2][r][tx] = h[2]; sT[3][r][tx] = h[3];
+        // row sums of T and T1 (message of a pairwise factor whose input is still the uniform initial message)
+        rs_t = warp_sum(rs_t); rs_t1 = warp_sum(rs_t1);
+        if ((threadIdx.x & 31) == 0 && a < V) {
+            atomicAdd(&colsums[(size_t)5 * V + a], rs_t);
+            atomicAdd(&colsums[(size_t)6 * V + a], rs_t1);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) sSum[i][ty][tx] = cs[i];
@@ -102,7 +110,7 @@ extern "C" int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1,
     MLBP_CHECK_ARG(V > 0 && ldf >= V && ldv >= V && (ldv % 64) == 0, "build_pairwise_tables: bad V/ld (%d,%d,%d)", V, ldf, ldv);
     MLBP_CHECK_ARG(plane_stride >= (int64_t)V * ldv, "build_pairwise_tables: plane_stride too small");
     cudaStream_t st = as_stream(stream);
-    MLBP_CUDA(cudaMemsetAsync(colsums, 0, sizeof(double) * 5 * (size_t)V, st));
+    MLBP_CUDA(cudaMemsetAsync(colsums, 0, sizeof(double) * MLBP_N_SUMS * (size_t)V, st));
     ThetaEE th{h_theta_ee[0], h_theta_ee[1], h_theta_ee[2]};
     dim3 grid((V + TS - 1) / TS, (V + TS - 1) / TS);
     build_pairwise_tables_kernel<<<grid, 256, 0, st>>>(pmi, pmi_w1, V, ldf, th, scale_exp, (__half *)planes,

@@ -29,6 +29,8 @@ H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 8, 4
  PLAN_N_DEAD) = range(9)
 A_SCALE_LOG2 = 14
 N_PLANES = 14
+N_SUMS = 7
+D_CONST_ROWS = 5
 
 
 def round_up(x, m):
@@ -210,7 +212,8 @@ class Engine(object):
         self.theta_ee = None
         self.theta_ed = None
         self.planes = None
-        self.colsums = torch.zeros((5, self.V), dtype=torch.float64, device=self.device)
+        self.colsums = torch.zeros((N_SUMS, self.V), dtype=torch.float64, device=self.device)
+        self.const_rows = None      # factor->variable messages of a pairwise factor fed the uniform initial message
         self.edstats = torch.zeros((self.Vd, 3), dtype=torch.float64, device=self.device)
         self.with_grad_planes = False
         self._A = self._D = self._U = None
@@ -242,6 +245,9 @@ class Engine(object):
                     _p(self.planes), self.V * self.ld, self.ld, _p(self.colsums), 1 if with_grad else 0)
         self.k.call('mlbp_build_unary_tables', _p(m.edT), _p(m.pedT), self.V, self.Vd, self.ld, _hp(td), _p(self.edstats))
         self.launches += 2
+        # constant rows by table id (T: row sums, Tt: column sums, T1, T1t), mean-one scaled (messages are scale-free)
+        cs = self.colsums[[5, 0, 6, 1]]
+        self.const_rows = (cs / cs.mean(dim=1, keepdim=True)).to(torch.float32)
 
     def plane(self, table, lo):
         return self.planes[2 * table + (1 if lo else 0)]
@@ -257,6 +263,7 @@ class Engine(object):
             cap = max(a_rows, 0 if self._A is None else int(self._A.shape[1] * 1.25))
             self._A = None
             self._A = torch.empty((2, cap, ld), dtype=torch.float16, device=dev)
+        d_rows = max(d_rows, D_CONST_ROWS)
         if self._D is None or self._D.shape[0] < d_rows:
             cap = max(d_rows, 0 if self._D is None else int(self._D.shape[0] * 1.25))
             self._D = None
@@ -313,6 +320,7 @@ class Engine(object):
         td = self.theta_ed
         c = lambda name: _p(corpus.dev(name, dev))
 
+        D[1:D_CONST_ROWS, :V].copy_(self.const_rows)
         inv_sigma = torch.empty(max(nv, 1), dtype=torch.float64, device=dev)
         g_unary = torch.empty((max(nv, 1), 9), dtype=torch.float64, device=dev)
         k.call('mlbp_unary_stats', nv, c('var_de'), c('var_label'), c('sp_off'), c('sp_en'), c('sp_feat'), c('sp_val'),

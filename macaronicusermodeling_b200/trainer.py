@@ -67,6 +67,8 @@ class Trainer(object):
         reg = self.reg_param / float(self.N if self.N else n)
         self.theta_ee = self.theta_ee + lr * (h[0:3] - n * reg * self.theta_ee)
         self.theta_ed = self.theta_ed + lr * (h[3:9] - n * reg * self.theta_ed)
+        if not (np.isfinite(self.theta_ee).all() and np.isfinite(self.theta_ed).all()):
+            raise FloatingPointError('theta diverged (learning rate too large for a summed minibatch gradient?)')
         return h
 
 

@@ -51,8 +51,9 @@ class FakeKernels(object):
             for j, h in enumerate((hi, lo)):
                 v = pl[(2 * i + j) * ps:(2 * i + j) * ps + V * ldv].reshape(V, ldv)
                 v[:, :V] = h
-        cs = _arr(colsums, np.float64, 5 * V).reshape(5, V)
+        cs = _arr(colsums, np.float64, 7 * V).reshape(7, V)
         cs[0], cs[1], cs[2], cs[3], cs[4] = T.sum(0), T1.sum(0), (T * P).sum(0), (T1 * P).sum(0), (T1 * W).sum(0)
+        cs[5], cs[6] = T.sum(1), T1.sum(1)
 
     def mlbp_build_unary_tables(self, edT, pedT, V, Vd, ldf, th, edstats):
         E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)

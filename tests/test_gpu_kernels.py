@@ -84,7 +84,7 @@ def test_pairwise_tables(lib):
     w1 = torch.zeros((V, ld)); w1[:, :V] = torch.from_numpy(model['pmi_w1'].astype(np.float32))
     pmi, w1 = pmi.cuda(), w1.cuda()
     planes = torch.zeros((14, V, ld), dtype=torch.float16, device='cuda')
-    cols = torch.zeros((5, V), dtype=torch.float64, device='cuda')
+    cols = torch.zeros((7, V), dtype=torch.float64, device='cuda')
     s = 9
     _lib.check(lib.mlbp_build_pairwise_tables(P(pmi), P(w1), V, ld, te.ctypes.data_as(ctypes.c_void_p), s, P(planes),
                                               V * ld, ld, P(cols), 1, S()))
@@ -100,6 +100,8 @@ def test_pairwise_tables(lib):
     c = cols.cpu().numpy()
     for i, W in enumerate([T, T1, T * p32, T1 * p32, T1 * w32]):
         np.testing.assert_allclose(c[i], W.sum(0), rtol=1e-12)
+    np.testing.assert_allclose(c[5], T.sum(1), rtol=1e-12)
+    np.testing.assert_allclose(c[6], T1.sum(1), rtol=1e-12)
 
 
 def test_dense_array_utils(lib):
