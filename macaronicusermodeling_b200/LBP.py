@@ -1,0 +1,758 @@
+"""Drop-in for the reference's ``LBP.py``: same classes, constructor orders, attribute and method names, return
+shapes and exceptions, executed by the batched B200 engine instead of per-message NumPy calls.
+
+How it runs.  The object graph built through ``add_varset_with_potentials`` / ``add_factor`` is only RECORDED.
+``initialize()`` and ``treelike_inference(n)`` record the BFS roots they draw from the global ``random`` (the
+same one draw per call site as LBP.py:176 and :223).  The first method that needs numbers (marginals, gradient,
+log-posterior, ``graph.messages[...]``) lowers the recorded graph + roots to index arrays, lets the C++ schedule
+compiler reproduce the reference's sequential update order exactly, and executes everything on the GPU in one go.
+Asking for more sweeps later re-runs from the uniform initial messages with the longer root list (inference is a
+deterministic function of the roots).
+
+Supported graphs: the macaronic model the reference's callers build (train.py:255-297): factors with
+``factor_type`` 'en_de' (unary, observed German word) or 'en_en' (unary with an observed English word, or pairwise),
+tables selected by ``gap`` like FactorNode.get_pot (LBP.py:456-467), features as stacked by train.py:594-609
+(phi_en_en = [pmi, 0, 1], phi_en_en_w1 = [pmi, pmi_w1, 1], phi_en_de = [ed, ped, correct, full_history,
+hit_history, 1]).  Explicit ``PotentialTable(table=...)`` graphs (the stale run.py demo) and direct per-node
+``update_message_to`` calls raise NotImplementedError.  There is no CPU fallback: without libmlbp.so and a B200 the
+first computation raises.
+"""
+import random
+import sys
+import time
+
+import numpy as np
+from numpy import float64 as DTYPE
+
+from .array_utils import c_array_utils as au
+
+VAR_TYPE_PREDICTED = 'var_type_predicted'
+VAR_TYPE_GIVEN = 'var_type_given'
+VAR_TYPE_LATENT = 'var_type_latent'
+UNARY_FACTOR = 'unary_factor'
+BINARY_FACTOR = 'binary_factor'
+
+_ENGINES = {}      # (id(phi_en_en), id(phi_en_en_w1), id(phi_en_de)) -> Engine : feature planes stay resident
+_DOMAIN_INDEX = {}  # id(domain list) -> {word: index}
+_KERNELS_FACTORY = None   # test hook: the CPU test tier injects an emulation of the device kernels here
+
+
+def _engine_for(graph):
+    from .engine import Engine, Model
+    key = (id(graph.phi_en_en), id(graph.phi_en_en_w1), id(graph.phi_en_de))
+    ent = _ENGINES.get(key)
+    if ent is None or ent[1] is not graph.phi_en_en:
+        ee, ee1, ed = graph.phi_en_en, graph.phi_en_en_w1, graph.phi_en_de
+        if ee.ndim != 3 or ee.shape[2] != 3 or ee1.shape != ee.shape or ed.ndim != 3 or ed.shape[2] != 6:
+            raise NotImplementedError('feature tensors must be the (V,V,3) / (V,Vd,6) stacks of train.py:594-609')
+        from .engine import Kernels
+        k = _KERNELS_FACTORY() if _KERNELS_FACTORY is not None else Kernels()
+        model = Model(ee[:, :, 0], ee1[:, :, 1], ed[:, :, 0], ed[:, :, 1], k.device)
+        _ENGINES.clear()                     # one resident model at a time (V x V planes are large)
+        ent = (Engine(model, kernels=k), ee)
+        _ENGINES[key] = ent
+    return ent[0]
+
+
+def _index_of(domain, label):
+    d = _DOMAIN_INDEX.get(id(domain))
+    if d is None or d[0] is not domain:
+        d = (domain, dict((w, i) for i, w in reversed(list(enumerate(domain)))))
+        if len(_DOMAIN_INDEX) > 8:
+            _DOMAIN_INDEX.clear()
+        _DOMAIN_INDEX[id(domain)] = d
+    return d[1].get(label)
+
+
+class FactorGraph():
+    def __init__(self,
+                 theta_en_en_names,
+                 theta_en_de_names,
+                 theta_en_en,
+                 theta_en_de,
+                 phi_en_en_w1,
+                 phi_en_en,
+                 phi_en_de):
+        self.theta_en_en = theta_en_en
+        self.theta_en_de = theta_en_de
+        self.theta_en_en_names = theta_en_en_names
+        self.theta_en_de_names = theta_en_de_names
+        self.phi_en_en = phi_en_en
+        self.phi_en_en_w1 = phi_en_en_w1
+        self.phi_en_de = phi_en_de
+        self.pot_en_en = None
+        self.pot_en_en_w1 = None
+        self.pot_en_de = None
+        self.variables = {}
+        self.factors = []
+        self.normalize_messages = True
+        self.isLoopy = None
+        self.regularization_param = 0.01
+        self.learning_rate = 0.1
+        self.report_times = False
+        self.bb_times = []
+        self.ub_times = []
+        self.it_times = []
+        self.gg_times = []
+        self.sgg_times = []
+        self.active_domains = {}
+        self.use_approx_inference = False
+        self.use_approx_beliefs = False
+        if isinstance(self.theta_en_en_names, tuple):
+            self.theta_en_en_names = self.theta_en_en_names[0]
+        if isinstance(self.theta_en_de_names, tuple):
+            self.theta_en_de_names = self.theta_en_de_names[0]
+        # recorder state
+        self._roots = []          # [has_loops draw, sweep roots...] as variable ids
+        self._sweeps = 0
+        self._initialized = False
+        self._res = None          # cached engine outputs for (_sweeps, theta snapshot)
+        self._messages = None
+
+    # ------------------------------------------------------------------ reference API: bookkeeping
+    def display_timing_info(self):
+        if self.report_times:
+            for name, ts in (('ubtimes', self.ub_times), ('bbtimes', self.bb_times), ('ggtimes', self.gg_times),
+                             ('sggtimes', self.sgg_times), ('it_times', self.it_times)):
+                if len(ts) > 0:
+                    print(name.ljust(11) + ':', np.sum(ts) / len(ts), 'total', np.sum(ts), 'len', len(ts))
+            print('num vars   :', len(self.variables))
+        return True
+
+    def add_factor(self, fac):
+        if __debug__: assert fac not in self.factors
+        self.factors.append(fac)
+        fac.graph = self
+        for v in fac.varset:
+            if v.id not in self.variables:
+                self.variables[v.id] = v
+                v.graph = self
+        self._res = None
+
+    def get_message_schedule(self, root):
+        """LBP.py:155-172 (host logic; the engine's C++ compiler follows the same walk)"""
+        if __debug__: assert isinstance(root, VariableNode)
+        _schedule = []
+        _seen = []
+        _stack = [root]
+        while len(_stack) > 0:
+            _n = _stack.pop(0)
+            if str(_n) not in _seen:
+                _seen.append(str(_n))
+                if isinstance(_n, VariableNode):
+                    nb = [_fn for _fn in _n.facset if str(_fn) not in _seen]
+                elif isinstance(_n, FactorNode):
+                    nb = [_vn for _vn in _n.varset if str(_vn) not in _seen]
+                else:
+                    raise NotImplementedError("Only handles 2 kinds of nodes, variables and factors")
+                _schedule.extend((m, _n) for m in nb)
+                _stack.extend(nb)
+        return _schedule
+
+    def _draw_root(self):
+        return random.sample(sorted(self.variables.keys()), 1)[0]
+
+    def has_loops(self, _root_id=None):
+        """LBP.py:174-190"""
+        _seen = []
+        _rand_key = self._draw_root() if _root_id is None else _root_id
+        self._last_loop_root = _rand_key
+        _root = self.variables[_rand_key]
+        _stack = [(_root, None)]
+        while len(_stack) > 0:
+            _n, _nparent = _stack.pop()
+            if str(_n) in _seen:
+                return True
+            _seen.append(str(_n))
+            if isinstance(_n, VariableNode):
+                [_stack.append((_fn, _n)) for _fn in _n.facset if _fn is not _nparent]
+            elif isinstance(_n, FactorNode):
+                [_stack.append((_vn, _n)) for _vn in _n.varset if _vn is not _nparent]
+            else:
+                raise NotImplementedError("Only handles 2 kinds of nodes, variables and factors")
+        return False
+
+    def initialize(self, root=None):
+        """LBP.py:192-216.  ``root`` (optional, not in the reference) pins the has_loops draw."""
+        if __debug__: assert len(self.variables) > 0
+        if __debug__: assert len(self.factors) > 0
+        fs = sorted([(f.id, f) for f in self.factors], key=lambda t: t[0])
+        self.factors = [f for fid, f in fs]
+        self.isLoopy = self.has_loops(root)
+        for f in self.factors:
+            if __debug__: assert len(f.potential_table.var_id2dim) == len(f.varset)
+            if f.potential_table.explicit:
+                raise NotImplementedError('explicit PotentialTable(table=...) graphs are not supported by the B200 engine')
+        self._roots = [self._last_loop_root]
+        self._sweeps = 0
+        self._initialized = True
+        self._res = None
+        self._messages = None
+
+    def treelike_inference(self, iterations, roots=None):
+        """LBP.py:218-245.  ``roots`` (optional, not in the reference) pins the per-sweep BFS roots."""
+        if not self._initialized:
+            raise KeyError('messages are not initialised: call initialize() first')
+        iterations = iterations if self.isLoopy else 1
+        for i in range(iterations):
+            if self.report_times: it = time.time()
+            self._roots.append(self._draw_root() if roots is None else roots[i])
+            self._sweeps += 1
+            if self.report_times: self.it_times.append(time.time() - it)
+        self._res = None
+        self._messages = None
+        return True
+
+    # ------------------------------------------------------------------ lowering + execution
+    def _theta_key(self):
+        return (np.asarray(self.theta_en_en, dtype=np.float64).tobytes(), np.asarray(self.theta_en_de, dtype=np.float64).tobytes())
+
+    def _lower(self):
+        """recorded object graph -> engine Corpus (one sentence).  Pairwise factors in attach order (facset order)."""
+        from .engine import Corpus
+        vids = sorted(self.variables.keys())
+        local = dict((vid, i) for i, vid in enumerate(vids))
+        var_de, var_label = [-1] * len(vids), [0] * len(vids)
+        giv = [[] for _ in vids]
+        pairs = []
+        for f in self.factors:
+            if len(f.varset) == 1:
+                v = f.varset[0]
+                od = f.potential_table.observed_dim
+                if f.factor_type == 'en_de':
+                    if var_de[local[v.id]] != -1:
+                        raise NotImplementedError('more than one en_de factor on a variable')
+                    var_de[local[v.id]] = int(od)
+                elif f.factor_type == 'en_en':
+                    giv[local[v.id]].append((int(od), 1 if self._gap_class(f) else 0))
+                else:
+                    raise BaseException('only 2 kinds of factors allowed...')
+            elif len(f.varset) == 2:
+                if f.factor_type != 'en_en':
+                    raise BaseException("only two kinds of potentials are supported...")
+                d = f.potential_table.var_id2dim
+                a, b = sorted(f.varset, key=lambda v: d[v.id])
+                pairs.append((f._attach_seq, local[a.id], local[b.id], 1 if self._gap_class(f) else 0, f))
+            else:
+                raise BaseException("only unary or binary factors are supported...")
+        pairs.sort(key=lambda t: t[0])
+        sp_off, sp_en, sp_feat, sp_val = [0], [], [], []
+        phi = self.phi_en_de
+        for i, vid in enumerate(vids):
+            var_label[i] = int(self.variables[vid].supervised_label_index)
+            d = var_de[i]
+            if d >= 0:                                   # train.py:176-215 wrote the dynamic features into phi_en_de in place
+                col = phi[:, d, 2:5]
+                e_idx, k_idx = np.nonzero(col)
+                for e, k in zip(e_idx.tolist(), k_idx.tolist()):
+                    sp_en.append(e); sp_feat.append(2 + k); sp_val.append(float(col[e, k]))
+            sp_off.append(len(sp_en))
+        giv_off, giv_label, giv_gap1 = [0], [], []
+        for g in giv:
+            for od, g1 in g:
+                giv_label.append(od); giv_gap1.append(g1)
+            giv_off.append(len(giv_label))
+        i32 = lambda x: np.asarray(x, dtype=np.int32)
+        corpus = Corpus(var_off=i32([0, len(vids)]), var_de=i32(var_de), var_label=i32(var_label), var_pos=i32(vids),
+                        sp_off=i32(sp_off), sp_en=i32(sp_en), sp_feat=i32(sp_feat), sp_val=np.asarray(sp_val, dtype=np.float32),
+                        giv_off=i32(giv_off), giv_label=i32(giv_label), giv_gap1=i32(giv_gap1),
+                        pair_off=i32([0, len(pairs)]), pair_v0=i32([p[1] for p in pairs]), pair_v1=i32([p[2] for p in pairs]),
+                        pair_gap1=i32([p[3] for p in pairs]))
+        return corpus, vids, [p[4] for p in pairs]
+
+    @staticmethod
+    def _gap_class(f):
+        if f.gap is None:
+            raise TypeError("'>' not supported between instances of 'NoneType' and 'int'")
+        if f.gap > 1:
+            return False
+        elif f.gap == 1:
+            return True
+        raise BaseException("only 2 kinds of distances are supported ...")
+
+    def _run(self):
+        if self._res is not None and self._res['key'] == (self._sweeps, self._theta_key()):
+            return self._res
+        if not self._initialized:
+            raise KeyError('messages are not initialised: call initialize() first')
+        eng = _engine_for(self)
+        corpus, vids, pair_factors = self._lower()
+        eng.set_theta(np.asarray(self.theta_en_en, dtype=np.float64).reshape(-1),
+                      np.asarray(self.theta_en_de, dtype=np.float64).reshape(-1))
+        roots = corpus.roots_from_positions([list(self._roots)])
+        r = eng.run(corpus, roots, self._sweeps, want_grad=True, want_marg=True, want_beliefs=True, want_messages=True)
+        V = eng.V
+        # name the final pairwise messages like the reference's dict keys
+        final = {}
+        local = dict((vid, i) for i, vid in enumerate(vids))
+        uni = np.full(V, 1.0 / V)
+        slot = dict((i, 0) for i in range(len(vids)))
+        for p, f in enumerate(pair_factors):                  # attach order == facset order of every variable
+            d = f.potential_table.var_id2dim
+            a, b = sorted(f.varset, key=lambda v: d[v.id])
+            final[str(a), str(f)], final[str(b), str(f)] = r.messages['v2f'][p]
+            for v in (a, b):
+                m = r.messages['f2v'][local[v.id]][slot[local[v.id]]]
+                final[str(f), str(v)] = uni.copy() if m is None else m
+                slot[local[v.id]] += 1
+        self._res = {'key': (self._sweeps, self._theta_key()), 'vids': vids, 'pairs': pair_factors,
+                     'beliefs': r.beliefs.cpu().numpy()[:, :V].astype(np.float64), 'grad': r.grad.cpu().numpy()[0],
+                     'logp_var': r.logp_var.cpu().numpy(), 'top1': r.top1.cpu().numpy(), 'rank': r.rank.cpu().numpy(),
+                     'final': final}
+        return self._res
+
+    @property
+    def messages(self):
+        """graph.messages[(str(src), str(dst))] -> Message, like the dict the reference keeps (LBP.py:40)"""
+        if self._messages is None:
+            res = self._run()
+            msgs = {}
+            fin = res['final']
+            for (a, b), m in fin.items():
+                msgs[a, b] = Message(m.reshape(-1, 1))
+            eng = _engine_for(self)
+            for f in self.factors:                        # unary factor -> variable: normalize(copy(table)), LBP.py:492-498
+                if len(f.varset) == 1:
+                    msgs[str(f), str(f.varset[0])] = Message(eng.unary_message(f.factor_type, f.potential_table.observed_dim,
+                                                                             self._gap_class(f) if f.factor_type == 'en_en' else False,
+                                                                             self._sparse_for(f)).reshape(-1, 1))
+            self._messages = msgs
+        return self._messages
+
+    def _sparse_for(self, f):
+        if f.factor_type != 'en_de':
+            return []
+        col = self.phi_en_de[:, f.potential_table.observed_dim, 2:5]
+        e_idx, k_idx = np.nonzero(col)
+        return [(int(e), 2 + int(k), float(col[e, k])) for e, k in zip(e_idx, k_idx)]
+
+    # ------------------------------------------------------------------ reference API: results
+    def get_posterior_probs(self):
+        """LBP.py:247-259"""
+        res = self._run()
+        log_posterior = 0.0
+        for _l in res['logp_var']:
+            if _l <= -99.99:
+                sys.stderr.write('err -inf' + str(0.0))
+            log_posterior += float(_l)
+        return log_posterior
+
+    def get_max_postior_label(self, top=10):
+        label_guesses = []
+        for v_key, v in self.variables.items():
+            s, sp, g = v.get_max_vocab(top)
+            g_str = ' '.join([i + ' ' + p for i, p in g])
+            label_guesses.append(s + ' ' + sp + ' ' + g_str)
+        return label_guesses
+
+    def get_precision_counts(self):
+        """LBP.py:80-106"""
+        p_at_0 = p_at_25 = p_at_50 = totals = 0
+        for f in self.factors:
+            if f.factor_type == 'en_de':
+                sl, slp, prediction = f.varset[0].get_max_vocab(50)
+                totals += 1
+                for rank, (p_label, p_prob) in enumerate(prediction):
+                    if sl == p_label:
+                        if rank == 0:
+                            p_at_0 += 1; p_at_25 += 1; p_at_50 += 1
+                        elif rank < 26:
+                            p_at_25 += 1; p_at_50 += 1
+                        elif rank < 51:
+                            p_at_50 += 1
+        return p_at_0, p_at_25, p_at_50, totals
+
+    def to_string(self):
+        """LBP.py:109-123"""
+        position_factors = sorted([(f.position, f) for f in self.factors if f.position is not None], key=lambda t: t[0])
+        fg_dct = {}
+        for p, f in position_factors:
+            if f.factor_type == 'en_de':
+                de_label = f.word_label
+                sl, slp, pred = f.varset[0].get_max_vocab(50)
+                pred = ' '.join([p1 + ' ' + p2 for p1, p2 in pred])
+                fg_dct[p] = ' '.join([de_label, sl, slp, pred])
+            if f.factor_type == 'en_en':
+                guess_label = f.word_label
+                fg_dct[p] = ' '.join(['', guess_label, ''])
+        return [fg_dct[k] for k in sorted(fg_dct)]
+
+    def to_dist(self):
+        """LBP.py:125-143"""
+        factor_dist = []
+        position_factors = sorted([(f.position, f) for f in self.factors if f.position is not None], key=lambda t: t[0])
+        for p, f in position_factors:
+            if f.factor_type == 'en_de':
+                v = f.varset[0]
+                truth = v.truth_label if v.truth_label is not None else 'None'
+                guess = v.supervised_label if v.supervised_label is not None else 'None'
+                m = v.get_marginal()
+                with np.errstate(divide='ignore'):
+                    i = ' '.join(['%0.6f' % i for i in np.log(m.m)])
+                factor_dist.append(' ||| '.join([truth, guess, i]))
+        return '\n'.join(factor_dist)
+
+    def hw_inf(self, iterations):
+        raise BaseException("This method assumes self.variables is a list.. depricated...")
+
+    def get_unregularized_gradeint(self):
+        """LBP.py:301-320 -> (grad_en_en (1,3), grad_en_de (1,6))"""
+        for f in self.factors:
+            if f.factor_type not in ('en_en', 'en_de'):
+                raise BaseException('only 2 kinds of factors allowed...')
+        g = self._run()['grad']
+        grad_en_en = np.zeros_like(self.theta_en_en, dtype=DTYPE)
+        grad_en_de = np.zeros_like(self.theta_en_de, dtype=DTYPE)
+        grad_en_en += g[:3].reshape(grad_en_en.shape)
+        grad_en_de += g[3:].reshape(grad_en_de.shape)
+        return grad_en_en, grad_en_de
+
+    def get_gradient(self):
+        """LBP.py:293-299 -> (grad_en_de, grad_en_en)   [sic: note the order]"""
+        grad_en_en, grad_en_de = self.get_unregularized_gradeint()
+        grad_en_en -= self.regularization_param * self.theta_en_en
+        grad_en_de -= self.regularization_param * self.theta_en_de
+        return grad_en_de, grad_en_en
+
+    def return_gradient(self):
+        """LBP.py:322-327 -> (lr * g_en_en, lr * g_en_de)"""
+        grad_en_de, grad_en_en = self.get_gradient()
+        return self.learning_rate * grad_en_en, self.learning_rate * grad_en_de
+
+    def update_theta(self):
+        """LBP.py:329-333 (in place, like the reference)"""
+        grad_en_de, grad_en_en = self.get_gradient()
+        self.theta_en_en += (self.learning_rate * grad_en_en)
+        self.theta_en_de += (self.learning_rate * grad_en_de)
+        return self.theta_en_en, self.theta_en_de
+
+
+class VariableNode():
+    def __init__(self, id, var_type, domain_type, domain, supervised_label):
+        if not isinstance(id, int):
+            print('id ', id, 'not an int')
+        idx = _index_of(domain, supervised_label)
+        if idx is None:
+            print(supervised_label, 'not in', 'domain of size %d' % len(domain))
+            exit(-1)
+        self.id = id
+        self.var_type = var_type
+        self.domain = domain
+        self.facset = []
+        self.graph = None
+        self.supervised_label = supervised_label
+        self.supervised_label_index = idx
+        self.domain_type = domain_type
+        self.truth_label = None
+        self.truth_label_index = None
+
+    def set_truth_label(self, tl):
+        self.truth_label = tl
+
+    def __str__(self):
+        return "X_" + str(self.id)
+
+    def __eq__(self, other):
+        return isinstance(other, VariableNode) and self.id == other.id
+
+    __hash__ = None
+
+    def display(self, m):
+        raise NotImplementedError()
+
+    def add_factor(self, fc):
+        if __debug__: assert isinstance(fc, FactorNode)
+        self.facset.append(fc)
+
+    def init_message_to(self, fc, init_m):
+        raise AttributeError("VariableNode instance has no attribute 'messages'")      # LBP.py:375 is broken the same way
+
+    def update_message_to(self, fc):
+        raise NotImplementedError('single-message updates are scheduled by FactorGraph.treelike_inference on the GPU')
+
+    def get_marginal(self):
+        """LBP.py:392-400"""
+        res = self.graph._run()
+        return Message(res['beliefs'][res['vids'].index(self.id)].reshape(-1, 1))
+
+    def get_max_vocab(self, top):
+        """LBP.py:402-411"""
+        m = self.get_marginal()
+        a = np.reshape(m.m, (np.size(m.m, )))
+        max_idx = np.argpartition(a, -top)[-top:]
+        max_idx = max_idx[np.argsort(a[max_idx])]
+        with np.errstate(divide='ignore'):
+            al = np.log(a)
+        max_vocab = [(self.domain[i], '%0.4f' % al[i]) for i in max_idx]
+        max_vocab.reverse()
+        return self.supervised_label, '%0.4f' % al[self.supervised_label_index], max_vocab
+
+
+class FactorNode():
+    _seq = [0]
+
+    def __init__(self, id, factor_type=None, observed_domain_type=None, observed_value=None, observed_domain_size=None):
+        if __debug__: assert isinstance(id, int)
+        self.id = id
+        self.varset = []
+        self.potential_table = None
+        self.factor_type = factor_type
+        self.graph = None
+        self.observed_domain_type = observed_domain_type
+        self.observed_value = observed_value
+        self.observed_domain_size = observed_domain_size
+        self.position = None
+        self.word_label = None
+        self.gap = None
+        self.connect_type = None
+        self._attach_seq = -1
+
+    def __str__(self):
+        return 'F_' + str(self.id)
+
+    def __eq__(self, other):
+        return isinstance(other, FactorNode) and self.id == other.id
+
+    __hash__ = None
+
+    def init_message_to(self, var, init_m):
+        raise NotImplementedError('messages live on the GPU; initialize() resets them to uniform')
+
+    def add_varset_with_potentials(self, varset, ptable):
+        if __debug__: assert isinstance(ptable, PotentialTable)
+        if len(varset) == 2:
+            if __debug__: assert varset[0] != varset[1]
+        if __debug__: assert len(varset) == len(ptable.var_id2dim)
+        if len(varset) > 2:
+            raise NotImplementedError("Currently supporting unary and pairwise factors...")
+        for v in varset:
+            if __debug__: assert v not in self.varset
+            self.varset.append(v)
+            v.add_factor(self)
+        ptable.add_factor(self)
+        self.potential_table = ptable
+        FactorNode._seq[0] += 1
+        self._attach_seq = FactorNode._seq[0]
+
+    def get_pot(self):
+        """LBP.py:456-467"""
+        if self.factor_type == 'en_en':
+            if self.gap > 1:
+                return self.graph.pot_en_en
+            elif self.gap == 1:
+                return self.graph.pot_en_en_w1
+            else:
+                raise BaseException("only 2 kinds of distances are supported ...")
+        elif self.factor_type == 'en_de':
+            return self.graph.pot_en_de
+        else:
+            raise BaseException("only two kinds of potentials are supported...")
+
+    def get_phi(self):
+        """LBP.py:469-480"""
+        if self.factor_type == 'en_en':
+            if self.gap > 1:
+                return self.graph.phi_en_en
+            elif self.gap == 1:
+                return self.graph.phi_en_en_w1
+            else:
+                raise BaseException("only 2 distances supported at the moment")
+        elif self.factor_type == 'en_de':
+            return self.graph.phi_en_de
+        else:
+            raise BaseException("only 2 feature value types are supported right now..")
+
+    def get_shape(self):
+        if len(self.varset) == 1:
+            return len(self.varset[0].domain), self.observed_domain_size
+        elif len(self.varset) == 2:
+            return len(self.varset[0].domain), len(self.varset[1].domain)
+        else:
+            raise BaseException("only unary or binary factors are supported...")
+
+    def update_message_to(self, var):
+        raise NotImplementedError('single-message updates are scheduled by FactorGraph.treelike_inference on the GPU')
+
+    def _table(self):
+        """the factor's potential table as a float64 array, computed on the GPU from theta and the features"""
+        from . import LBP as _self  # noqa: F401
+        eng = _engine_for(self.graph)
+        g = self.graph
+        eng.set_theta(np.asarray(g.theta_en_en, dtype=np.float64).reshape(-1), np.asarray(g.theta_en_de, dtype=np.float64).reshape(-1))
+        if len(self.varset) == 1:
+            gap1 = FactorGraph._gap_class(self) if self.factor_type == 'en_en' else False
+            return eng.unary_message(self.factor_type, self.potential_table.observed_dim, gap1, g._sparse_for(self),
+                                     normalized=False).reshape(-1, 1)
+        return eng.dense_table(FactorGraph._gap_class(self))
+
+    def get_factor_beliefs(self):
+        """LBP.py:528-574: unary -> normalize(table) (incoming messages ignored); pairwise -> normalize((c r') o T)"""
+        if len(self.varset) == 1:
+            if self.graph.report_times: ub = time.time()
+            beliefs = au.normalize(self._table())
+            if self.graph.report_times: self.graph.ub_times.append(time.time() - ub)
+            return beliefs
+        if self.graph.report_times: bb = time.time()
+        r = c = None
+        for v in self.varset:
+            vd = self.potential_table.var_id2dim[v.id]
+            m = self.graph.messages[str(v), str(self)]
+            if vd == 0:
+                c = np.reshape(m.m, (np.size(m.m), 1))
+            elif vd == 1:
+                r = np.reshape(m.m, (1, np.size(m.m)))
+            else:
+                raise NotImplementedError("only supports pairwise factors..")
+        marginals = au.dense_dot(np.ascontiguousarray(c), np.ascontiguousarray(r))
+        beliefs = au.normalize(au.dense_pointwise_multiply(marginals, self._table()))
+        if self.graph.report_times: self.graph.bb_times.append(time.time() - bb)
+        return beliefs
+
+    def get_observed_factor_as_array(self):
+        cell = sorted([(self.potential_table.var_id2dim[v.id], v.supervised_label_index) for v in self.varset])
+        return [tuple([o for d, o in cell])]
+
+    def get_observed_factor(self):
+        """LBP.py:584-589"""
+        shape = (len(self.varset[0].domain), 1) if len(self.varset) == 1 else self.get_shape()
+        of = np.zeros(shape, dtype=DTYPE)
+        cell = sorted([(self.potential_table.var_id2dim[v.id], v.supervised_label_index) for v in self.varset])
+        cell = tuple([o for d, o in cell])
+        of[cell if len(cell) == 2 else (cell[0], 0)] = 1.0
+        return of
+
+    def cell_gradient(self):
+        return self.get_observed_factor() - self.get_factor_beliefs()
+
+    def cell_gradient_alt(self):
+        d = -self.get_factor_beliefs()
+        for c in self.get_observed_factor_as_array():
+            d[c if len(c) == 2 else (c[0], 0)] = 1.0 + d[c if len(c) == 2 else (c[0], 0)]
+        return d
+
+    def get_gradient(self):
+        """LBP.py:592-613 -> (1, F)"""
+        g = self.cell_gradient()
+        if self.graph.report_times: gg = time.time()
+        if self.potential_table.observed_dim is not None:
+            phi_g = self.get_phi()[:, self.potential_table.observed_dim, :]
+            grad = au.dense_dot(np.ascontiguousarray(g.T), np.ascontiguousarray(phi_g, dtype=np.float64))
+        else:
+            phi = self.get_phi()
+            grad = np.array([float(au.dense_dot(np.ascontiguousarray(g.reshape(1, -1)),
+                                                np.ascontiguousarray(phi[:, :, k].reshape(-1, 1), dtype=np.float64))[0, 0])
+                             for k in range(phi.shape[2])])
+        grad = np.reshape(grad, (1, np.size(grad)))
+        if self.graph.report_times: self.graph.gg_times.append(time.time() - gg)
+        return grad
+
+
+class ObservedFactor(FactorNode):
+    def __init__(self, id, observed_domain_type, observed_value):
+        FactorNode.__init__(self, id, factor_type=UNARY_FACTOR)
+        self.observed_domain_type = observed_domain_type
+        self.observed_value = observed_value
+
+
+class Message():
+    def __init__(self, m):
+        if __debug__: assert isinstance(m, np.ndarray)
+        if __debug__: assert np.size(m[m < 0.0]) == 0
+        if np.shape(m) != (np.size(m), 1):
+            self.m = np.reshape(m, (np.size(m), 1))
+        else:
+            self.m = m
+
+    def __str__(self):
+        return np.array_str(self.m)
+
+    def renormalize(self):
+        """LBP.py:649-659"""
+        s = np.sum(self.m)
+        if s > 0:
+            self.m = au.normalize(self.m)
+        else:
+            e = np.empty_like(self.m)
+            e.fill(1.0 / np.size(self.m))
+            self.m = e
+        if __debug__: assert np.size(self.m[self.m < 0.0]) == 0
+        if __debug__: assert np.abs(np.sum(self.m) - 1.0) < 1e-10
+
+    @staticmethod
+    def new_message(domain, init):
+        m = np.empty((len(domain), 1))
+        m.fill(init)
+        if m.dtype != DTYPE:
+            m = m.astype(DTYPE)
+        return Message(m)
+
+
+class PotentialTable():
+    def __init__(self, v_id2dim, table=None, observed_dim=None):
+        self.factor = None
+        self.observed_dim = observed_dim
+        self.var_id2dim = v_id2dim
+        self.explicit = table is not None
+        self.table = None
+        if table is not None:
+            if __debug__: assert isinstance(table, np.ndarray)
+            if observed_dim is not None:
+                if __debug__: assert len(v_id2dim) == 1
+                if v_id2dim[list(v_id2dim.keys())[0]] == 0:
+                    self.table = np.reshape(table[:, observed_dim], (np.shape(table)[0], 1))
+                else:
+                    raise NotImplementedError("a unary factor should always be a column vector")
+            else:
+                self.table = table
+            if self.table.dtype != DTYPE:
+                self.table = self.table.astype(DTYPE)
+
+    def slice_potentials(self):
+        """LBP.py:695-710.  When the caller computed graph.pot_* (train.py:251-253) the table is sliced from it like the
+        reference does (a view / column copy, no arithmetic); the GPU engine never reads it -- it rebuilds the potentials
+        from theta and the features."""
+        table = self.factor.get_pot()
+        if table is None:
+            self.table = None
+            return
+        table = np.reshape(table, self.factor.get_shape())
+        if self.observed_dim is not None:
+            table = np.reshape(table[:, self.observed_dim], (np.shape(table)[0], 1))
+        self.table = table
+        if self.table.dtype != DTYPE:
+            self.table = self.table.astype(DTYPE)
+
+    def add_factor(self, factor):
+        if __debug__: assert isinstance(factor, FactorNode)
+        if __debug__: assert self.factor is None
+        self.factor = factor
+
+
+def pointwise_multiply(m1, m2):
+    """LBP.py:717-730"""
+    if __debug__: assert isinstance(m1, Message)
+    if __debug__: assert isinstance(m2, Message)
+    if m2 is None:
+        return m1
+    elif m1 is None:
+        return m2
+    else:
+        if __debug__: assert np.shape(m1.m) == np.shape(m2.m)
+        new_m = au.pointwise_multiply(m1.m, m2.m)
+        new_m = np.nan_to_num(new_m)
+    return Message(new_m)
+
+
+class PhiWrapper:
+    def __init__(self, phi_en_en, phi_en_en_w1, phi_en_de):
+        self.phi_en_en = phi_en_en
+        self.phi_en_en_w1 = phi_en_en_w1
+        self.phi_en_de = phi_en_de
+
+
+class ThetaWrapper(object):
+    def __init__(self, theta_en_en_names, theta_en_en, theta_en_de_names, theta_en_de):
+        self.theta_en_en_names = theta_en_en_names
+        self.theta_en_de_names = theta_en_de_names
+        self.theta_en_en = theta_en_en
+        self.theta_en_de = theta_en_de

@@ -43,7 +43,7 @@ namespace {
 enum {
     H_NLEVELS = 0, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
     H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
-    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_WORDS = 32
+    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_WORDS = 32
 };
 enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_WORDS = 8 };
 enum { GEMM_TABLE = 0, GEMM_A0, GEMM_D0, GEMM_N, GEMM_WORDS = 4 };
@@ -179,7 +179,7 @@ void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
     t.cur_v2f.assign(2 * g.np, -1); t.cur_f2v.assign(2 * g.np, -1);
     t.rd_v2f.assign(2 * g.np, 0);   t.rd_f2v.assign(2 * g.np, 0);
     const bool loopy = g.np > 0 && has_loops(g, roots[0]);
-    const int n_it = loopy ? sweeps : 1;                         // LBP.py:219
+    const int n_it = sweeps == 0 ? 0 : (loopy ? sweeps : 1);    // LBP.py:219 (0: initialize() only, no treelike_inference yet)
     std::vector<Edge> S;
     for (int it = 0; it < n_it && g.np > 0; ++it) {
         schedule(g, roots[1 + it], S);
@@ -204,7 +204,7 @@ void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
 // per-thread output of the emit phase for a contiguous range of graphs
 struct ChunkOut {
     std::vector<std::vector<int32_t>> grp_u, grp_off, in_row, dest_off, dest;   // [level]
-    std::vector<int32_t> init_rows, pair_c, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
+    std::vector<int32_t> init_rows, pair_c, pair_r, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
 };
 
 template <class F>
@@ -218,7 +218,7 @@ static void parallel_for_chunks(int n_chunks, F f) {
 extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int32_t *pair_off, const int32_t *pair_v0,
                                  const int32_t *pair_v1, const int32_t *pair_gap1, const int32_t *roots, int sweeps,
                                  int flags, mlbp_plan **out) {
-    if (!out || n_graphs < 0 || sweeps < 1 || !var_off || !pair_off || !roots) {
+    if (!out || n_graphs < 0 || sweeps < 0 || !var_off || !pair_off || !roots) {
         mlbp::set_error("plan_compile: bad argument");
         return MLBP_ERR_INVALID;
     }
@@ -358,6 +358,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
                 int64_t i0 = g_i0[gi], i1 = g_i1[gi], ip = g_ip[gi];
                 for (int f = 0; f < g.np; ++f) {
                     co.pair_c.push_back((int32_t)(a_c + ip));
+                    co.pair_r.push_back((int32_t)(g.gap1[f] ? a_r1 + i1 : a_r0 + i0));
                     if (g.gap1[f]) {
                         co.pair_u0.push_back((int32_t)(d_u0_1 + i1)); co.pair_u1.push_back((int32_t)(d_u1_1 + i1));
                         co.pair_u2.push_back((int32_t)(d_u2_1 + i1)); ++i1;
@@ -469,6 +470,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     }
     B[H_NPAIR] = (int32_t)n_pair;
     B[H_PAIR_C] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_c; }, false);
+    B[H_PAIR_R] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_r; }, false);
     B[H_PAIR_U0] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u0; }, false);
     B[H_PAIR_U1] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u1; }, false);
     B[H_PAIR_U2] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u2; }, false);

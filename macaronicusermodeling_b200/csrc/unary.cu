@@ -39,7 +39,10 @@ __global__ void unary_stats_kernel(int nv, const int32_t *__restrict__ var_de, c
     if (v >= nv) return;
     const int d = var_de[v], y = var_label[v];
     const int s0 = sp_off[v], s1 = sp_off[v + 1];
-    double S0 = edstats[3 * d], S1 = edstats[3 * d + 1], S2 = edstats[3 * d + 2];
+    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double S0 = 1.0, S1 = 0.0, S2 = 0.0;
+    if (d >= 0) {                                          // d < 0: the variable has no en_de factor
+    S0 = edstats[3 * d]; S1 = edstats[3 * d + 1]; S2 = edstats[3 * d + 2];
     for (int s = s0; s < s1; ++s) {  // every DISTINCT touched english index once
         const int e = sp_en[s];
         bool first = true;
@@ -51,13 +54,13 @@ __global__ void unary_stats_kernel(int nv, const int32_t *__restrict__ var_de, c
         S1 += (f - b) * (double)edT[(size_t)d * ldf + e];
         S2 += (f - b) * (double)pedT[(size_t)d * ldf + e];
     }
-    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     g[3] = (double)edT[(size_t)d * ldf + y] - S1 / S0;    // ed
     g[4] = (double)pedT[(size_t)d * ldf + y] - S2 / S0;   // ped
     for (int s = s0; s < s1; ++s) {                        // correct / full_history / hit_history
         const int e = sp_en[s];
         const double f = psi_base(edT, pedT, ldf, d, e, th) * exp(sparse_delta(sp_en, sp_feat, sp_val, s0, s1, e, th));
         g[3 + sp_feat[s]] += (double)sp_val[s] * ((e == y ? 1.0 : 0.0) - f / S0);
+    }
     }
     // bias features: observed 1 - expected 1 (the reference yields ~1e-16 noise here)
     const double *csT = colsums, *csT1 = colsums + V, *csG = colsums + 2 * (size_t)V, *csG1 = colsums + 3 * (size_t)V,
@@ -92,12 +95,14 @@ unary_products_kernel(const int32_t *__restrict__ var_de, const int32_t *__restr
     const double scale0 = (double)V * inv_sigma[v];
     float *urow = U + (size_t)v * ldv;
     if (e0 < V) {
-        const float4 ed4 = *reinterpret_cast<const float4 *>(edT + (size_t)d * ldf + e0);
-        const float4 pd4 = *reinterpret_cast<const float4 *>(pedT + (size_t)d * ldf + e0);
-        const float ed[4] = {ed4.x, ed4.y, ed4.z, ed4.w}, pd[4] = {pd4.x, pd4.y, pd4.z, pd4.w};
-        double u[4];
+        double u[4] = {1.0, 1.0, 1.0, 1.0};                // d < 0: no en_de factor on this variable
+        if (d >= 0) {
+            const float4 ed4 = *reinterpret_cast<const float4 *>(edT + (size_t)d * ldf + e0);
+            const float4 pd4 = *reinterpret_cast<const float4 *>(pedT + (size_t)d * ldf + e0);
+            const float ed[4] = {ed4.x, ed4.y, ed4.z, ed4.w}, pd[4] = {pd4.x, pd4.y, pd4.z, pd4.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = exp(th.t[0] * (double)ed[i] + th.t[1] * (double)pd[i] + th.t[5]) * scale0;
+            for (int i = 0; i < 4; ++i) u[i] = exp(th.t[0] * (double)ed[i] + th.t[1] * (double)pd[i] + th.t[5]) * scale0;
+        }
         for (int j = g0; j < g1; ++j) {
             const int o = giv_label[j];
             const int tp = giv_gap1[j] ? 6 : 2;  // T1t / Tt plane pair: row o = column o of T1 / T
@@ -122,7 +127,7 @@ unary_products_kernel(const int32_t *__restrict__ var_de, const int32_t *__restr
     }
     // sparse per-sentence features (train.py:176-215): re-evaluate the touched entries of this chunk
     const int s0 = sp_off[v], s1 = sp_off[v + 1];
-    if (s1 > s0) {
+    if (s1 > s0 && d >= 0) {
         __syncthreads();
         const int c0 = blockIdx.y * 1024, c1 = min(c0 + 1024, V);
         for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {

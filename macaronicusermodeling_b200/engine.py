@@ -23,7 +23,7 @@ from . import _lib
 # plan blob header (csrc/plan.cpp)
 (H_NLEVELS, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
  H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
- H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS) = range(23)
+ H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R) = range(24)
 H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 8, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
  PLAN_N_DEAD) = range(9)
@@ -191,9 +191,10 @@ class Corpus(object):
 class Result(object):
     """Outputs of one Engine.run: tensors stay on the device until read."""
 
-    def __init__(self, grad, logp, logp_var, top1, rank, beliefs, stats):
+    def __init__(self, grad, logp, logp_var, top1, rank, beliefs, stats, messages=None):
         self.grad, self.logp, self.logp_var, self.top1, self.rank, self.beliefs, self.stats = \
             grad, logp, logp_var, top1, rank, beliefs, stats
+        self.messages = messages     # final pairwise messages (want_messages): see Engine.run
 
     def precision_counts(self):
         """FactorGraph.get_precision_counts (LBP.py:80-106) summed over the batch: (p@0, p@25, p@50, total)"""
@@ -252,6 +253,42 @@ class Engine(object):
     def plane(self, table, lo):
         return self.planes[2 * table + (1 if lo else 0)]
 
+    # ------------------------------------------------------------------ API read-back helpers (LBP.py drop-in)
+    def unary_message(self, factor_type, observed_dim, gap1=False, sparse=(), normalized=True):
+        """Message / table column of ONE unary factor as float64 [V] (LBP.py:492-498, :702-703), computed by K1 on a
+        pseudo-variable that owns only this factor."""
+        en_de = factor_type == 'en_de'
+        i32 = lambda x: np.asarray(x, dtype=np.int32)
+        sp = list(sparse) if en_de else []
+        c = Corpus(var_off=i32([0, 1]), var_de=i32([observed_dim if en_de else -1]), var_label=i32([0]), var_pos=i32([0]),
+                   sp_off=i32([0, len(sp)]), sp_en=i32([x[0] for x in sp]), sp_feat=i32([x[1] for x in sp]),
+                   sp_val=np.asarray([x[2] for x in sp], dtype=np.float32), giv_off=i32([0, 0 if en_de else 1]),
+                   giv_label=i32([] if en_de else [observed_dim]), giv_gap1=i32([] if en_de else [1 if gap1 else 0]),
+                   pair_off=i32([0, 0]), pair_v0=i32([]), pair_v1=i32([]), pair_gap1=i32([]))
+        dev, ld, V, m = self.device, self.ld, self.V, self.model
+        d = lambda name: _p(c.dev(name, dev))
+        inv_sigma = torch.empty(1, dtype=torch.float64, device=dev)
+        g_unary = torch.empty((1, 9), dtype=torch.float64, device=dev)
+        U = torch.empty((1, ld), dtype=torch.float32, device=dev)
+        self.k.call('mlbp_unary_stats', 1, d('var_de'), d('var_label'), d('sp_off'), d('sp_en'), d('sp_feat'), d('sp_val'),
+                    d('giv_off'), d('giv_label'), d('giv_gap1'), _p(m.pmi), _p(m.w1), _p(m.edT), _p(m.pedT), V, ld,
+                    _hp(self.theta_ed), _p(self.edstats), _p(self.colsums), _p(inv_sigma), _p(g_unary))
+        self.k.call('mlbp_unary_products', 1, d('var_de'), d('sp_off'), d('sp_en'), d('sp_feat'), d('sp_val'), d('giv_off'),
+                    d('giv_label'), d('giv_gap1'), _p(m.edT), _p(m.pedT), V, ld, _hp(self.theta_ed), _p(inv_sigma),
+                    _p(self.planes), V * ld, ld, self.scale_exp, _p(self.colsums), _p(U))
+        self.launches += 2
+        u = U[0, :V].double() / V                                        # normalised message
+        if not normalized:
+            norm = (1.0 / inv_sigma[0]) if en_de else self.colsums[1 if gap1 else 0, observed_dim]
+            u = u * norm
+        return u.cpu().numpy()
+
+    def dense_table(self, gap1):
+        """pot_en_en (gap > 1) or pot_en_en_w1 (gap == 1) as float64 [V, V], from the operand planes (22 bits)"""
+        t = 2 if gap1 else 0
+        T = (self.plane(t, 0)[:, :self.V].double() + self.plane(t, 1)[:, :self.V].double()) * (2.0 ** -self.scale_exp)
+        return T.cpu().numpy()
+
     # ------------------------------------------------------------------ workspace
     def rows_budget(self):
         """GEMM rows (A and D rows) that fit the workspace: 4 bytes (A hi+lo) + 4 bytes (D) per element"""
@@ -280,7 +317,8 @@ class Engine(object):
     # ------------------------------------------------------------------ one microbatch
     def compile(self, corpus, roots, sweeps, want_grad, want_marg):
         roots = np.ascontiguousarray(roots, dtype=np.int32)
-        assert roots.shape == (corpus.n_sent, 1 + sweeps), roots.shape
+        assert roots.shape[0] == corpus.n_sent and roots.shape[1] >= 1 + sweeps, roots.shape
+        roots = np.ascontiguousarray(roots[:, :1 + sweeps])
         handle = ctypes.c_void_p()
         lib = _lib.load()
         flags = (1 if want_grad else 0) | (2 if want_marg else 0)
@@ -291,7 +329,7 @@ class Engine(object):
         _lib.check(lib.mlbp_plan_sizes(handle, _hp(sizes)))
         return handle, sizes
 
-    def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False):
+    def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False):
         """All sentences of `corpus` (must fit the workspace; use run_many to micro-batch).  `roots`: int
         [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176)."""
         assert self.theta_ee is not None, 'set_theta first'
@@ -395,9 +433,30 @@ class Engine(object):
         elif want_marg:
             seg = torch.from_numpy(np.repeat(np.arange(corpus.n_sent), np.diff(corpus.var_off))).to(dev)
             logp.index_add_(0, seg, logp_var)
+        messages = None
+        if want_messages:
+            # final pairwise messages, normalised, float64 on the host (API read-back for LBP.FactorGraph.messages):
+            #   'v2f'[p] = (message of the dim-0 variable, message of the dim-1 variable) into pairwise factor p
+            #   'f2v'[v] = factor->variable messages of variable v in facset (attach) order; None = still uniform
+            assert want_grad and want_marg
+            messages = {'v2f': [], 'f2v': []}
+            if n_pair:
+                oc, orr = int(blob[H_PAIR_C]), int(blob[H_PAIR_R])
+                rows = torch.cat([bd[oc:oc + n_pair], bd[orr:orr + n_pair]]).long()
+                m = ((A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)).cpu().numpy()
+                messages['v2f'] = [(m[i], m[n_pair + i]) for i in range(n_pair)]
+            mo, mi = int(blob[H_MARG_OFF]), int(blob[H_MARG_IN])
+            n_m = int(blob[H_MARG_N])
+            off = blob[mo:mo + n_m + 1]
+            rows = blob[mi:mi + int(off[-1])]
+            if len(rows):
+                dr = D[torch.from_numpy(np.maximum(rows, 0).astype(np.int64)).to(dev), :V].double()
+                dr = (dr / dr.sum(dim=1, keepdim=True)).cpu().numpy()
+            for v in range(n_m):
+                messages['f2v'].append([dr[j] if rows[j] >= 0 else None for j in range(int(off[v]), int(off[v + 1]))])
         stats = {'a_rows': int(sizes[PLAN_A_ROWS]), 'd_rows': int(sizes[PLAN_D_ROWS]), 'levels': int(sizes[PLAN_N_LEVELS]),
                  'gemm_rows': int(sizes[PLAN_N_GEMM_ROWS]), 'dead': int(sizes[PLAN_N_DEAD]), 'blob_words': words}
-        return Result(grad, logp, logp_var, top1, rank, beliefs, stats)
+        return Result(grad, logp, logp_var, top1, rank, beliefs, stats, messages)
 
     # ------------------------------------------------------------------ micro-batching
     def microbatches(self, corpus, sweeps, want_grad):

@@ -77,7 +77,7 @@ class FakeKernels(object):
         de, so, se, sf, sv, go, gl, gg = self._unary_common(nv, var_de, sp_off, sp_en, sp_feat, sp_val, giv_off,
                                                             giv_label, giv_gap1)
         lab = _arr(var_label, np.int32, nv)
-        Vd = int(de.max()) + 1
+        Vd = max(int(de.max()) + 1, 1)
         E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf); Pd = _arr(pedT, np.float32, Vd * ldf).reshape(Vd, ldf)
         P = _arr(pmi, np.float32, V * ldf).reshape(V, ldf); W = _arr(w1, np.float32, V * ldf).reshape(V, ldf)
         t = _arr(th, np.float64, 6)
@@ -86,6 +86,18 @@ class FakeKernels(object):
         isg = _arr(inv_sigma, np.float64, nv); gu = _arr(g_unary, np.float64, nv * 9).reshape(nv, 9)
         for v in range(nv):
             d, y = int(de[v]), int(lab[v])
+            if d < 0:
+                g = np.zeros(9)
+                for j in range(go[v], go[v + 1]):
+                    o = int(gl[j])
+                    if gg[j]:
+                        g[0] += float(P[y, o]) - cs[3, o] / cs[1, o]
+                        g[1] += float(W[y, o]) - cs[4, o] / cs[1, o]
+                    else:
+                        g[0] += float(P[y, o]) - cs[2, o] / cs[0, o]
+                isg[v] = 1.0
+                gu[v] = g
+                continue
             S0, S1, S2 = st[d]
             ent = [(int(se[s]), int(sf[s]), float(sv[s])) for s in range(so[v], so[v + 1])]
             base = lambda e: np.exp(t[0] * float(E[d, e]) + t[1] * float(Pd[d, e]) + t[5])
@@ -112,7 +124,7 @@ class FakeKernels(object):
                             ldf, th, inv_sigma, planes, ps, ldv, scale_exp, colsums, U):
         de, so, se, sf, sv, go, gl, gg = self._unary_common(nv, var_de, sp_off, sp_en, sp_feat, sp_val, giv_off,
                                                             giv_label, giv_gap1)
-        Vd = int(de.max()) + 1
+        Vd = max(int(de.max()) + 1, 1)
         E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
         Pd = _arr(pedT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
         t = _arr(th, np.float64, 6)
@@ -122,10 +134,13 @@ class FakeKernels(object):
         Uo = _arr(U, np.float32, nv * ldv).reshape(nv, ldv)
         for v in range(nv):
             d = int(de[v])
-            z = t[0] * E[d] + t[1] * Pd[d] + t[5]
-            for s in range(so[v], so[v + 1]):
-                z[int(se[s])] += t[int(sf[s])] * float(sv[s])
-            u = np.exp(z) * V * isg[v]
+            if d >= 0:
+                z = t[0] * E[d] + t[1] * Pd[d] + t[5]
+                for s in range(so[v], so[v + 1]):
+                    z[int(se[s])] += t[int(sf[s])] * float(sv[s])
+                u = np.exp(z) * V * isg[v]
+            else:
+                u = np.ones(V)
             for j in range(go[v], go[v + 1]):
                 o, tp = int(gl[j]), (6 if gg[j] else 2)
                 row = (pl[tp * ps + o * ldv: tp * ps + o * ldv + V].astype(np.float64) +

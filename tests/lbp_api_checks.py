@@ -1,0 +1,71 @@
+"""Checks of the drop-in LBP / train_compat modules against the reference fixtures, shared by the CPU tier
+(emulated kernels) and the GPU tier."""
+import io
+import json
+
+import numpy as np
+
+from macaronicusermodeling_b200 import train_compat as tc
+
+
+def graph_from_fixture(z):
+    V, Vd = z['pmi'].shape[0], z['ed'].shape[1]
+    en_domain = ['e%d' % i for i in range(V)]
+    de_domain = ['d%d' % i for i in range(Vd)]
+    en2id = dict((e, i) for i, e in enumerate(en_domain))
+    de2id = dict((d, i) for i, d in enumerate(de_domain))
+    pw = tc.make_phi_wrapper(z['pmi'], z['pmi_w1'], z['ed'], z['ped'])
+    spec = json.loads(str(z['spec']))
+    t_ee = np.array(z['theta_ee'], dtype=np.float64).reshape(1, 3)
+    t_ed = np.array(z['theta_ed'], dtype=np.float64).reshape(1, 6)
+    opts = tc.default_options(session_history=True)
+    fg = tc.create_factor_graph(str(z['sentence']), spec.get('lr', 0.1), tc.F_EN_EN_NAMES, tc.F_EN_DE_NAMES, t_ee, t_ed, pw,
+                                en_domain, de2id, en2id, {}, options=opts, N=spec.get('N', 10), de_domain=de_domain)
+    return fg, spec
+
+
+def check_lbp_api_fixture(path, check_messages=True):
+    z = np.load(path, allow_pickle=False)
+    fg, spec = graph_from_fixture(z)
+    roots = [int(r) for r in z['roots']]
+    fg.initialize(roots[0])
+    assert bool(fg.isLoopy) == bool(int(z['is_loopy']))
+    fg.treelike_inference(spec['sweeps'], roots[1:])
+    # graph wiring (train.py:255-297)
+    desc = np.array([[f.id, 0 if f.factor_type == 'en_de' else 1, len(f.varset), f.varset[0].id,
+                      f.varset[1].id if len(f.varset) > 1 else -1, f.gap,
+                      -1 if f.potential_table.observed_dim is None else f.potential_table.observed_dim] for f in fg.factors])
+    np.testing.assert_array_equal(desc, z['factor_desc'])
+    assert sorted(fg.variables.keys()) == list(z['var_ids'])
+    marg = np.stack([fg.variables[v].get_marginal().m[:, 0] for v in sorted(fg.variables.keys())])
+    assert np.abs(marg - z['marginals']).max() < 1e-6
+    np.testing.assert_allclose(fg.get_posterior_probs(), float(z['logp']), rtol=2e-6)
+    g_ee, g_ed = fg.get_unregularized_gradeint()
+    assert g_ee.shape == (1, 3) and g_ed.shape == (1, 6)
+    np.testing.assert_allclose(g_ee, z['g_ee_unreg'], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(g_ed, z['g_ed_unreg'], rtol=1e-4, atol=2e-6)
+    r_ee, r_ed = fg.return_gradient()
+    np.testing.assert_allclose(r_ee, z['g_ee_ret'], rtol=1e-4, atol=2e-7)
+    np.testing.assert_allclose(r_ed, z['g_ed_ret'], rtol=1e-4, atol=2e-7)
+    if 'zeros' not in path:
+        np.testing.assert_array_equal(np.array(fg.get_precision_counts()), z['precision_counts'])
+        assert fg.to_string() == [str(s) for s in z['to_string']]
+    if check_messages:
+        keys = [k for k in z.files if k.startswith('msg|')]
+        assert len(keys) == len(fg.messages)
+        for k in keys:
+            _, a, b = k.split('|')
+            m = fg.messages[a, b].m
+            assert m.shape == (len(z[k]), 1)
+            assert np.abs(m[:, 0] - z[k]).max() < 1e-6, k
+
+
+def check_params_roundtrip(tmp_path):
+    ee = np.array([[0.123456789, -1.5, 0.0]])
+    ed = np.array([[1.0, 2.0, -3.25, 0.5, 0.25, 0.125]])
+    p = str(tmp_path / 'params')
+    tc.save_params(io.open(p, 'w', encoding='utf8'), ee, ed, list(tc.F_EN_EN_NAMES), list(tc.F_EN_DE_NAMES), {})
+    een, eet, edn, edt, d2t = tc.read_params(p)
+    assert een == tc.F_EN_EN_NAMES and edn == tc.F_EN_DE_NAMES and d2t == {}
+    np.testing.assert_allclose(eet, ee, atol=5e-7)
+    np.testing.assert_allclose(edt, ed, atol=5e-7)

@@ -1,0 +1,40 @@
+"""CPU tier: the drop-in LBP.py / train_compat API (recording, lowering, read-back) on emulated kernels."""
+import glob
+import os
+
+import pytest
+
+import lbp_api_checks
+from fake_kernels import FakeKernels
+from macaronicusermodeling_b200 import LBP, build
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+CASES = sorted(glob.glob(os.path.join(GOLDEN, 'graph_*.npz')))
+
+
+@pytest.fixture(autouse=True)
+def _fake_backend():
+    build.build()
+    LBP._KERNELS_FACTORY = FakeKernels
+    LBP._ENGINES.clear()
+    yield
+    LBP._KERNELS_FACTORY = None
+    LBP._ENGINES.clear()
+
+
+@pytest.mark.parametrize('path', CASES, ids=[os.path.basename(p)[6:-4] for p in CASES])
+def test_lbp_api_matches_reference_fixture(path):
+    lbp_api_checks.check_lbp_api_fixture(path)
+
+
+def test_params_roundtrip(tmp_path):
+    lbp_api_checks.check_params_roundtrip(tmp_path)
+
+
+def test_import_surface():
+    """train.py:9 imports exactly these names from LBP"""
+    from macaronicusermodeling_b200.LBP import (FactorGraph, FactorNode, PhiWrapper, PotentialTable, VariableNode,  # noqa: F401
+                                                VAR_TYPE_GIVEN, VAR_TYPE_PREDICTED)
+    from macaronicusermodeling_b200.array_utils import c_array_utils as au
+    for name in ('pointwise_multiply', 'normalize', 'dense_dot', 'dense_pointwise_multiply'):
+        assert callable(getattr(au, name))
