@@ -49,7 +49,16 @@ def check_lbp_api_fixture(path, check_messages=True):
     np.testing.assert_allclose(r_ed, z['g_ed_ret'], rtol=1e-4, atol=2e-7)
     if 'zeros' not in path:
         np.testing.assert_array_equal(np.array(fg.get_precision_counts()), z['precision_counts'])
-        assert fg.to_string() == [str(s) for s in z['to_string']]
+        got, want = fg.to_string(), [str(s) for s in z['to_string']]
+        assert len(got) == len(want)
+        for a, b in zip(got, want):            # same words in the same order; '%0.4f' log-probs may differ in the last digit
+            ta, tb = a.split(' '), b.split(' ')
+            assert len(ta) == len(tb)
+            for x, y in zip(ta, tb):
+                try:
+                    assert abs(float(x) - float(y)) <= 1.5e-4, (x, y)
+                except ValueError:
+                    assert x == y, (x, y)
     if check_messages:
         keys = [k for k in z.files if k.startswith('msg|')]
         assert len(keys) == len(fg.messages)

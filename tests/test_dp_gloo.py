@@ -1,0 +1,58 @@
+"""N > 1 host logic on the CPU: two gloo ranks shard the sentences (like train_mp.py hands them to pool workers,
+train_mp.py:634-649), all-reduce the 16-float64 gradient vector and must end at the single-process theta."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def _setup():
+    from fake_kernels import FakeKernels
+    from macaronicusermodeling_b200 import synth
+    from macaronicusermodeling_b200.engine import Corpus, Engine
+    from macaronicusermodeling_b200.trainer import Trainer
+    model = synth.make_model(64, 16, seed=2)
+    sents = synth.make_corpus(model, 8, k=4, g=1, seed=4)
+    roots = Corpus(sents).roots_from_positions(synth.draw_roots(sents, 3, seed=6))
+    return FakeKernels, Corpus, Engine, Trainer, model, sents, roots
+
+
+def _one_step(Trainer, Engine, Corpus, FakeKernels, model, sents, roots, N):
+    tr = Trainer(Engine(model, kernels=FakeKernels()), reg_param=0.2, N=N)
+    tr.theta_ee = np.array([0.3, 0.2, -0.1]); tr.theta_ed = np.array([0.5, -0.2, 0.3, 0.1, 0.2, 0.0])
+    red = tr.step(Corpus(sents), roots, 0.01)
+    h = tr.apply(red, 0.01)
+    return tr, h
+
+
+def _worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    FakeKernels, Corpus, Engine, Trainer, model, sents, roots = _setup()
+    lo, hi = rank * len(sents) // world, (rank + 1) * len(sents) // world
+    tr, h = _one_step(Trainer, Engine, Corpus, FakeKernels, model, sents[lo:hi], roots[lo:hi], len(sents))
+    out[rank] = np.concatenate([tr.theta_ee, tr.theta_ed, h]).tolist()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process():
+    from macaronicusermodeling_b200 import build
+    build.build()
+    FakeKernels, Corpus, Engine, Trainer, model, sents, roots = _setup()
+    tr, h = _one_step(Trainer, Engine, Corpus, FakeKernels, model, sents, roots, len(sents))
+    want = np.concatenate([tr.theta_ee, tr.theta_ed, h])
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    for r in (0, 1):
+        np.testing.assert_allclose(np.array(out[r]), want, rtol=1e-10, atol=1e-12)
+    assert want[9 + 14] == len(sents)
