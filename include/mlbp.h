@@ -116,10 +116,12 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   group g multiplies U[grp_u[g]] with the factor->variable rows D[in_row[i]], i in [grp_off[g], grp_off[g+1]);
  *   for every i with destinations it emits the leave-one-out product (all inputs except i), renormalised
  *   (sum <= 0 or non-finite -> uniform, LBP.py:650-657; nan_to_num LBP.py:729), scaled by 2^14 and split into
- *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]).  in_row < 0 means "uniform message".               */
+ *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]).  in_row < 0 means "uniform message".
+ *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
+ *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow). */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const float *U, const float *D, int ldv, int V,
-                       void *A_hi, void *A_lo, int max_in, void *stream);
+                       void *A_hi, void *A_lo, int max_in, float range_log2, void *stream);
 /* K4.  FactorNode.update_message_to for pairwise factors (LBP.py:499-526; au.dense_dot pyx:90-91), batched:
  *   D[d_row0 + r, n] = alpha * sum_k (A_hi + A_lo)[a_row0 + r, k] * (B_hi + B_lo)[n, k],  r < n_rows, n < V
  *   as three tcgen05 passes hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory.

@@ -18,7 +18,7 @@ _SIGNATURES = {
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
     'mlbp_fill_uniform_rows': 'ppiipip',
-    'mlbp_var_to_factor': 'ippppp' + 'ppii' + 'ppip',
+    'mlbp_var_to_factor': 'ippppp' + 'ppii' + 'ppifp',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppp',
     'mlbp_pair_expectations': 'ipppp' + 'pppii' + 'pp',

@@ -143,9 +143,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 constexpr int K3_STAGES = 4;
 
-// K3, pipelined: same contract as var_to_factor_kernel.  Dynamic shared memory: K3_STAGES stages of (rows + 1) x E
+// K3, pipelined: same contract as var_to_factor_kernel.  T = float when the caller guarantees (range_log2) that no
+// leave-one-out product can leave the fp32 range, else double.  Measured on B200: the fp64 pipe issues only ~3
+// lanes/clk/SM, so the double variant is compute-bound (~20x below the HBM roofline); it is the safe fallback.  Dynamic shared memory: K3_STAGES stages of (rows + 1) x E
 // floats (row 0 = U chunk, rows 1..n = incoming message chunks), then K3_STAGES mbarriers.
-template <int NMAX>
+template <int NMAX, typename T>
 __global__ void __launch_bounds__(K3_THREADS)
 var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                           const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
@@ -196,9 +198,9 @@ var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__re
     if (threadIdx.x == 0)
         for (int it = 0; it < K3_STAGES && it < total; ++it) issue(it);
 
-    double acc[NMAX];
+    T acc[NMAX];
 #pragma unroll
-    for (int j = 0; j < NMAX; ++j) acc[j] = 0.0;
+    for (int j = 0; j < NMAX; ++j) acc[j] = (T)0;
     const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
 
     for (int it = 0; it < total; ++it) {
@@ -209,7 +211,7 @@ var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__re
 #pragma unroll
             for (int j = 0; j < NMAX; ++j) {
                 if (j < n && s_d1[j] > s_d0[j]) {                 // block-uniform condition
-                    const double sum = block_sum(acc[j], red);
+                    const double sum = block_sum((double)acc[j], red);
                     if (threadIdx.x == 0)
                         s_scale[j] = (sum > 0.0 && isfinite(sum)) ? ldexp(1.0, MLBP_A_SCALE_LOG2) / sum : -1.0;
                 }
@@ -221,16 +223,16 @@ var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__re
             float d[NMAX];
 #pragma unroll
             for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? st[(size_t)(1 + j) * E + el] : 1.0f;
-            double pre[NMAX];
-            double p = (double)st[el];
+            T pre[NMAX];
+            T p = (T)st[el];
 #pragma unroll
-            for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (double)d[j]; }
-            double suf = 1.0;
+            for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (T)d[j]; }
+            T suf = (T)1;
             if (it < nchunks) {
 #pragma unroll
                 for (int j = NMAX - 1; j >= 0; --j) {
                     acc[j] += pre[j] * suf;
-                    suf *= (double)d[j];
+                    suf *= (T)d[j];
                 }
             } else {
                 const size_t e = (size_t)(e0 + el);
@@ -238,7 +240,7 @@ var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__re
                 for (int j = NMAX - 1; j >= 0; --j) {
                     if (j < n && s_d1[j] > s_d0[j]) {
                         const double sc = s_scale[j];
-                        const float x = sc > 0.0 ? (float)(pre[j] * suf * sc) : uni;
+                        const float x = sc > 0.0 ? (float)(pre[j] * suf * (T)sc) : uni;
                         __half hi, lo;
                         split_f16(x, hi, lo);
                         for (int t = s_d0[j]; t < s_d1[j]; ++t) {
@@ -247,7 +249,7 @@ var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__re
                             A_lo[o] = lo;
                         }
                     }
-                    suf *= (double)d[j];
+                    suf *= (T)d[j];
                 }
             }
         }
@@ -330,10 +332,11 @@ extern "C" int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, co
 
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                                   const int32_t *dest_off, const int32_t *dest, const float *U, const float *D,
-                                  int ldv, int V, void *A_hi, void *A_lo, int max_in, void *stream) {
+                                  int ldv, int V, void *A_hi, void *A_lo, int max_in, float range_log2, void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
+    const bool fp32_ok = range_log2 >= 0.f && range_log2 < 100.f;   // products provably stay inside 2^+-100
     MLBP_CHECK_ARG(V > 0 && ldv >= V && (ldv % 4) == 0, "var_to_factor: bad V/ldv");
     cudaStream_t st = as_stream(stream);
     // stage geometry: (max_in + 1) rows x E floats per stage, K3_STAGES stages (+ barriers) within 200 KB
@@ -345,13 +348,18 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     do {                                                                                                              \
         static bool attr_done = false;                                                                                \
         if (!attr_done) {                                                                                             \
-            MLBP_CUDA(cudaFuncSetAttribute(var_to_factor_pipe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           200 * 1024 + 64));                                                         \
+            MLBP_CUDA(cudaFuncSetAttribute(var_to_factor_pipe_kernel<N, float>,                                       \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64));            \
+            MLBP_CUDA(cudaFuncSetAttribute(var_to_factor_pipe_kernel<N, double>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64));            \
             attr_done = true;                                                                                         \
         }                                                                                                             \
-        var_to_factor_pipe_kernel<N><<<n_groups, K3_THREADS, smem, st>>>(grp_u, grp_off, in_row, dest_off, dest, U,   \
-                                                                         D, ldv, V, (__half *)A_hi, (__half *)A_lo,   \
-                                                                         E, stage_rows);                              \
+        if (fp32_ok)                                                                                                  \
+            var_to_factor_pipe_kernel<N, float><<<n_groups, K3_THREADS, smem, st>>>(                                  \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, E, stage_rows); \
+        else                                                                                                          \
+            var_to_factor_pipe_kernel<N, double><<<n_groups, K3_THREADS, smem, st>>>(                                 \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, E, stage_rows); \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);

@@ -81,6 +81,7 @@ class Model(object):
         self.pmi, self.w1 = padded(pmi), padded(pmi_w1)
         self.edT, self.pedT = padded(ed.T), padded(ped.T)
         self.frange = (float(pmi.min()), float(pmi.max()), float(pmi_w1.min()), float(pmi_w1.max()))
+        self.ed_range = (float(ed.max() - ed.min()), float(ped.max() - ped.min()))
 
     @classmethod
     def from_dict(cls, m, device):
@@ -237,6 +238,13 @@ class Engine(object):
         zmax = te[2] + max(te[0] * pmin, te[0] * pmax) + max(te[1] * wmin, te[1] * wmax, 0.0)
         fabs = max(1.0, abs(pmin), abs(pmax), abs(wmin), abs(wmax))
         self.scale_exp = 13 - int(math.ceil((zmax / math.log(2.0)) + math.log2(fabs)))
+        # log2 range of the factor->variable messages: D[r, a] is a convex combination of T[a, .], so after the
+        # power-of-two centring folded into the GEMM's alpha every element lies within 2^(+-half_range_log2)
+        zmin = te[2] + min(te[0] * pmin, te[0] * pmax) + min(te[1] * wmin, te[1] * wmax, 0.0)
+        self.centre_exp = int(round((zmin + zmax) / 2.0 / math.log(2.0)))
+        self.half_range_log2 = (zmax - zmin) / 2.0 / math.log(2.0) + 0.5
+        erange, prange = self.model.ed_range
+        self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
         n_planes = N_PLANES if with_grad else 8
         if self.planes is None or self.planes.shape[0] < n_planes:
             self.planes = torch.zeros((n_planes, self.V, self.ld), dtype=torch.float16, device=self.device)
@@ -371,8 +379,10 @@ class Engine(object):
         if blob[H_INIT_N]:
             k.call('mlbp_fill_uniform_rows', _p(A_hi), _p(A_lo), ld, V, _p(bd, int(blob[H_INIT_OFF])), int(blob[H_INIT_N]))
             self.launches += 1
-        alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp)))
         max_in = int(blob[H_MAX_IN])
+        alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp + self.centre_exp)))
+        g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
+        range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
 
         def gemm_calls(off, n):
             for i in range(n):
@@ -393,7 +403,7 @@ class Engine(object):
             rec = blob[H_WORDS + LEV_WORDS * L: H_WORDS + LEV_WORDS * (L + 1)]
             if rec[0]:
                 k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])), _p(bd, int(rec[3])),
-                       _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), max_in)
+                       _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), max_in, range_log2)
                 self.launches += 1
             gemm_calls(int(rec[7]), int(rec[6]))
 

@@ -158,7 +158,7 @@ class FakeKernels(object):
         H[r, :V], L[r, :V] = hi[0], lo[0]
         H[r, V:], L[r, V:] = 0, 0
 
-    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, A_hi, A_lo, max_in):
+    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         n_in = int(go[-1])
         ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
