@@ -10,6 +10,8 @@
 // Phase 1 sums every outgoing product (the renormalisation of Message.renormalize, LBP.py:649-657);
 // phase 2 recomputes it (the inputs are then L2 hits), scales to 2^14 / sum and splits into the fp16 hi / lo
 // operand rows the pairwise GEMM (K4) consumes through TMA.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mlbp {
@@ -28,7 +30,7 @@ __global__ void fill_uniform_rows_kernel(__half *__restrict__ A_hi, __half *__re
     }
 }
 
-template <int NMAX>
+template <int NMAX, typename T>
 __global__ void __launch_bounds__(K3_THREADS)
 var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
@@ -54,30 +56,30 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     }
     __syncthreads();
 
-    double acc[NMAX];
+    T acc[NMAX];
 #pragma unroll
-    for (int j = 0; j < NMAX; ++j) acc[j] = 0.0;
+    for (int j = 0; j < NMAX; ++j) acc[j] = (T)0;
 
     // ---- phase 1: sums of the leave-one-out products
     for (int e = threadIdx.x; e < V; e += K3_THREADS) {
         float d[NMAX];
 #pragma unroll
         for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? __ldg(s_src[j] + e) : 1.0f;
-        double pre[NMAX];
-        double p = (double)__ldg(urow + e);
+        T pre[NMAX];
+        T p = (T)__ldg(urow + e);
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (double)d[j]; }
-        double suf = 1.0;
+        for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (T)d[j]; }
+        T suf = (T)1;
 #pragma unroll
         for (int j = NMAX - 1; j >= 0; --j) {
             acc[j] += pre[j] * suf;
-            suf *= (double)d[j];
+            suf *= (T)d[j];
         }
     }
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) {
         if (j < n && s_d1[j] > s_d0[j]) {                         // block-uniform condition
-            const double s = block_sum(acc[j], red);
+            const double s = block_sum((double)acc[j], red);
             if (threadIdx.x == 0)
                 s_scale[j] = (s > 0.0 && isfinite(s)) ? ldexp(1.0, MLBP_A_SCALE_LOG2) / s : -1.0;  // -1: uniform fallback
         }
@@ -90,16 +92,16 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
         float d[NMAX];
 #pragma unroll
         for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? __ldg(s_src[j] + e) : 1.0f;
-        double pre[NMAX];
-        double p = (double)__ldg(urow + e);
+        T pre[NMAX];
+        T p = (T)__ldg(urow + e);
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (double)d[j]; }
-        double suf = 1.0;
+        for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (T)d[j]; }
+        T suf = (T)1;
 #pragma unroll
         for (int j = NMAX - 1; j >= 0; --j) {
             if (j < n && s_d1[j] > s_d0[j]) {
                 const double sc = s_scale[j];
-                const float x = sc > 0.0 ? (float)(pre[j] * suf * sc) : uni;
+                const float x = sc > 0.0 ? (float)(pre[j] * suf * (T)sc) : uni;
                 __half hi, lo;
                 split_f16(x, hi, lo);
                 for (int t = s_d0[j]; t < s_d1[j]; ++t) {
@@ -108,7 +110,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
                     A_lo[o] = lo;
                 }
             }
-            suf *= (double)d[j];
+            suf *= (T)d[j];
         }
     }
 }
@@ -337,6 +339,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
     const bool fp32_ok = range_log2 >= 0.f && range_log2 < 100.f;   // products provably stay inside 2^+-100
+    static const int k3_impl = [] { const char *e = getenv("MLBP_K3_IMPL"); return e ? atoi(e) : 1; }();   // 1 = direct loads (default), 0 = bulk-async staging (slower: 2 KB bulk copies)
     MLBP_CHECK_ARG(V > 0 && ldv >= V && (ldv % 4) == 0, "var_to_factor: bad V/ldv");
     cudaStream_t st = as_stream(stream);
     // stage geometry: (max_in + 1) rows x E floats per stage, K3_STAGES stages (+ barriers) within 200 KB
@@ -354,7 +357,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64));            \
             attr_done = true;                                                                                         \
         }                                                                                                             \
-        if (fp32_ok)                                                                                                  \
+        if (k3_impl == 1 && fp32_ok)                                                                                  \
+            var_to_factor_kernel<N, float><<<n_groups, K3_THREADS, 0, st>>>(                                          \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);                \
+        else if (k3_impl == 1)                                                                                        \
+            var_to_factor_kernel<N, double><<<n_groups, K3_THREADS, 0, st>>>(                                         \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);                \
+        else if (fp32_ok)                                                                                             \
             var_to_factor_pipe_kernel<N, float><<<n_groups, K3_THREADS, smem, st>>>(                                  \
                 grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, E, stage_rows); \
         else                                                                                                          \
