@@ -39,13 +39,14 @@ int launch_gemm_simt(const void *, const void *, int64_t, int, int, const void *
                      int64_t, int, float, cudaStream_t);
 
 constexpr int BM = 128;
-constexpr int BK = 64;            // 64 fp16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int GROUP_M = 16;
 constexpr unsigned long long WAIT_LIMIT_CYCLES = 8000000000ull;  // ~4 s: a stuck barrier traps instead of hanging the GPU
 
-template <int BN, int STAGES>
+// BK = 64 fp16 = 128-byte rows (swizzle-128B) or BK = 32 = 64-byte rows (swizzle-64B: twice the stages per KB)
+template <int BN, int STAGES, int BK = 64>
 struct Cfg {
+    static_assert(BK == 64 || BK == 32, "BK");
     static constexpr int EPI_WARPS = 4 * (BN / 128);          // one warp per (lane quarter, 128-column half)
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int TMEM_COLS = 2 * BN;                   // two accumulators
@@ -133,13 +134,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, swizzle-128B shared-memory matrix descriptor: rows are 128 bytes, 8-row core-matrix groups are
 // 1024 bytes apart (SBO), LBO unused for a single swizzle atom along K, descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+    constexpr uint64_t row_bytes = BK * 2;                // 128 (SWIZZLE_128B = 2) or 64 (SWIZZLE_64B = 4)
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
     d |= (uint64_t)0 << 16;                               // leading byte offset (ignored)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset, bits [32,46)
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;          // stride byte offset: 8-row core-matrix group, bits [32,46)
     d |= (uint64_t)1 << 46;                               // version = 1
-    d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
+    d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;              // layout type
     return d;
 }
 // kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 accumulator, both K-major, M x N tile.
@@ -149,13 +152,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------- kernel
-template <int BN, int STAGES, int CHUNK_KB>
-__global__ void __launch_bounds__(Cfg<BN, STAGES>::THREADS, 1)
+template <int BN, int STAGES, int CHUNK_KB, int BK>
+__global__ void __launch_bounds__(Cfg<BN, STAGES, BK>::THREADS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                       float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
                       int m_tiles, int n_tiles, int *err_flag) {
-    using C = Cfg<BN, STAGES>;
+    using C = Cfg<BN, STAGES, BK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
@@ -229,9 +232,9 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                 tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
-                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::A_BYTES);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * C::A_BYTES);
-                const uint64_t b_lo = umma_desc_sw128(st + 2 * C::A_BYTES + C::B_BYTES);
+                const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + C::A_BYTES);
+                const uint64_t b_hi = umma_desc_kmajor<BK>(st + 2 * C::A_BYTES);
+                const uint64_t b_lo = umma_desc_kmajor<BK>(st + 2 * C::A_BYTES + C::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K step inside the atom
@@ -310,36 +313,37 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp16 [rows, cols] tensor with row pitch ld elements; box = [box_rows, 64 cols], swizzle-128B, zero OOB fill
-static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int cols, int ld, int box_rows) {
+static int make_map(CUtensorMap *m, const void *ptr, int64_t rows, int cols, int ld, int box_rows, int bk) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MLBP_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MLBP_ERR_CUDA; }
     return MLBP_OK;
 }
 
 struct MapKey {
-    const void *ptr; int64_t rows; int cols, ld, box;
+    const void *ptr; int64_t rows; int cols, ld, box, bk;
     bool operator<(const MapKey &o) const {
-        return std::tie(ptr, rows, cols, ld, box) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.box);
+        return std::tie(ptr, rows, cols, ld, box, bk) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.box, o.bk);
     }
 };
 static std::map<MapKey, CUtensorMap> g_maps;
 static std::mutex g_maps_mu;
 
-static int cached_map(CUtensorMap *out, const void *ptr, int64_t rows, int cols, int ld, int box) {
+static int cached_map(CUtensorMap *out, const void *ptr, int64_t rows, int cols, int ld, int box, int bk) {
     std::lock_guard<std::mutex> lk(g_maps_mu);
-    MapKey k{ptr, rows, cols, ld, box};
+    MapKey k{ptr, rows, cols, ld, box, bk};
     auto it = g_maps.find(k);
     if (it == g_maps.end()) {
         CUtensorMap m;
-        int rc = make_map(&m, ptr, rows, cols, ld, box);
+        int rc = make_map(&m, ptr, rows, cols, ld, box, bk);
         if (rc != MLBP_OK) return rc;
         if (g_maps.size() > 4096) g_maps.clear();
         it = g_maps.emplace(k, m).first;
@@ -350,20 +354,20 @@ static int cached_map(CUtensorMap *out, const void *ptr, int64_t rows, int cols,
 
 static int *g_err_flag = nullptr;   // pinned, mapped: the kernel records which barrier timed out before trapping
 
-template <int BN, int STAGES, int CHUNK_KB>
+template <int BN, int STAGES, int CHUNK_KB, int BK = 64>
 static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                      const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
                      cudaStream_t st) {
-    using C = Cfg<BN, STAGES>;
+    using C = Cfg<BN, STAGES, BK>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = cached_map(&ma_hi, A_hi, a_rows_total, V, ldv, BM)) != MLBP_OK) return rc;
-    if ((rc = cached_map(&ma_lo, A_lo, a_rows_total, V, ldv, BM)) != MLBP_OK) return rc;
-    if ((rc = cached_map(&mb_hi, B_hi, V, V, ldv, BN)) != MLBP_OK) return rc;
-    if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, BN)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&ma_hi, A_hi, a_rows_total, V, ldv, BM, BK)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&ma_lo, A_lo, a_rows_total, V, ldv, BM, BK)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&mb_hi, B_hi, V, V, ldv, BN, BK)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, BN, BK)) != MLBP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, STAGES, CHUNK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, STAGES, CHUNK_KB, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
         attr_set = true;
     }
@@ -374,7 +378,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     int *d_flag = nullptr;
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_tiles = (n_rows + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
-    gemm_split_f16_kernel<BN, STAGES, CHUNK_KB><<<m_tiles * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
+    gemm_split_f16_kernel<BN, STAGES, CHUNK_KB, BK><<<m_tiles * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
@@ -414,6 +418,9 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
+        case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
+        case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
+        case 22: return launch_tc<128, 6, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st);
         default: break;
     }
 #undef MLBP_TC
