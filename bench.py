@@ -204,6 +204,8 @@ def ours(a):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    lws = int(os.environ.get('LOCAL_WORLD_SIZE', str(world)))
+    os.environ.setdefault('MLBP_PLAN_THREADS', str(max(2, min(16, (os.cpu_count() or 8) // max(lws, 1)))))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))

@@ -133,10 +133,11 @@ int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_t
 /* K5.  VariableNode.get_marginal / get_posterior_probs / get_precision_counts / argmax
  *   (LBP.py:392-411, :247-259, :80-106).  Same group layout as K3, all inputs multiplied.
  *   logp[g] = log b[label] (-99.99 if b[label] == 0), top1[g] = argmax b (first index on ties),
- *   rank[g] = #{e : b[e] > b[label]}, beliefs (optional, may be NULL): [n_groups, ldv] fp32 normalised.   */
+ *   rank[g] = #{e : b[e] > b[label]}, beliefs (optional, may be NULL): [n_groups, ldv] fp32 normalised.
+ *   range_log2 as in mlbp_var_to_factor (bound for ALL incoming messages of a variable; at most 64 of them).    */
 int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                    const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
-                   int32_t *top1, int32_t *rank, float *beliefs, void *stream);
+                   int32_t *top1, int32_t *rank, float *beliefs, float range_log2, void *stream);
 /* K6a. pairwise factor beliefs contracted with the features (LBP.py:544-569 + :610) in closed form:
  *   stats[f] = { c.u0, c.u1, c.u2 } with c = (A_hi + A_lo)[c_row[f]], u* = D[u*_row[f]] (u2_row < 0 -> 0).  */
 int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *u0_row, const int32_t *u1_row,

@@ -20,7 +20,7 @@ _SIGNATURES = {
     'mlbp_fill_uniform_rows': 'ppiipip',
     'mlbp_var_to_factor': 'ippppp' + 'ppii' + 'ppifp',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
-    'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppp',
+    'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppfp',
     'mlbp_pair_expectations': 'ipppp' + 'pppii' + 'pp',
     'mlbp_gradient_reduce': 'ippppppp' + 'ppi' + 'pppp',
     'mlbp_plan_compile': 'ipppppp' + 'iip',

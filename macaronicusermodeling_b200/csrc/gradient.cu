@@ -21,14 +21,16 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
     const __half *ch = A_hi + (size_t)c_row[f] * ldv, *cl = A_lo + (size_t)c_row[f] * ldv;
     const float *u0 = D + (size_t)u0_row[f] * ldv, *u1 = D + (size_t)u1_row[f] * ldv;
     const float *u2 = u2_row[f] >= 0 ? D + (size_t)u2_row[f] * ldv : nullptr;
-    double z = 0, n1 = 0, n2 = 0;
+    // fp32 products, short per-thread fp32 partial sums (V / 256 terms), float64 across the block: the fp64 pipe of
+    // B200 issues ~3 lanes/clk/SM, and the ratio N/Z only needs ~1e-6
+    float zf = 0.f, n1f = 0.f, n2f = 0.f;
     for (int e = threadIdx.x; e < V; e += blockDim.x) {
-        const double c = (double)__half2float(ch[e]) + (double)__half2float(cl[e]);
-        z += c * (double)__ldg(u0 + e);
-        n1 += c * (double)__ldg(u1 + e);
-        if (u2) n2 += c * (double)__ldg(u2 + e);
+        const float c = __half2float(ch[e]) + __half2float(cl[e]);
+        zf = fmaf(c, __ldg(u0 + e), zf);
+        n1f = fmaf(c, __ldg(u1 + e), n1f);
+        if (u2) n2f = fmaf(c, __ldg(u2 + e), n2f);
     }
-    z = block_sum(z, red); n1 = block_sum(n1, red); n2 = block_sum(n2, red);
+    double z = block_sum((double)zf, red), n1 = block_sum((double)n1f, red), n2 = block_sum((double)n2f, red);
     if (threadIdx.x == 0) { stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2; }
 }
 

@@ -260,42 +260,48 @@ var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__re
     }
 }
 
-// one CTA per variable: total product of all incoming messages
+// one CTA per variable: total product of all incoming messages (T = float under the same range bound as K3)
+template <typename T>
 __global__ void __launch_bounds__(256)
 marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                  const int32_t *__restrict__ in_row, const int32_t *__restrict__ label, const float *__restrict__ U,
                  const float *__restrict__ D, int ldv, int V, double *__restrict__ logp, int32_t *__restrict__ top1,
                  int32_t *__restrict__ rank, float *__restrict__ beliefs) {
     __shared__ double red[32];
-    __shared__ double s_best[8];
+    __shared__ T s_best[8];
     __shared__ int s_besti[8];
     const int g = blockIdx.x;
     const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
     const float *urow = U + (size_t)grp_u[g] * ldv;
     const int lab = label[g];
+    __shared__ const float *s_rows[64];
+    const int nn = min(n, 64);
+    if (threadIdx.x < 64) {
+        const int r = threadIdx.x < nn ? in_row[i0 + threadIdx.x] : -1;
+        s_rows[threadIdx.x] = r >= 0 ? D + (size_t)r * ldv : nullptr;
+    }
+    __syncthreads();
     auto prod = [&](int e) {
-        double p = (double)__ldg(urow + e);
-        for (int j = 0; j < n; ++j) {
-            const int r = in_row[i0 + j];
-            if (r >= 0) p *= (double)__ldg(D + (size_t)r * ldv + e);
-        }
+        T p = (T)__ldg(urow + e);
+        for (int j = 0; j < nn; ++j)
+            if (s_rows[j]) p *= (T)__ldg(s_rows[j] + e);
         return p;
     };
-    const double plab = prod(lab);
-    double s = 0.0, best = -1.0;
+    const T plab = prod(lab);
+    T sp = (T)0, best = (T)-1;
     int besti = 0x7fffffff, cnt = 0;
     for (int e = threadIdx.x; e < V; e += blockDim.x) {
-        const double p = prod(e);
-        s += p;
+        const T p = prod(e);
+        sp += p;
         cnt += (p > plab) ? 1 : 0;
         if (p > best) { best = p; besti = e; }                    // strided ascending e: first index wins per thread
     }
-    s = block_sum(s, red);
+    double s = block_sum((double)sp, red);
     const double c = block_sum((double)cnt, red);
     // argmax with first-index tie break (np.argmax)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const T ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
         if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
@@ -307,7 +313,7 @@ marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ 
             if (s_best[w] > best || (s_best[w] == best && s_besti[w] < besti)) { best = s_best[w]; besti = s_besti[w]; }
         const bool ok = s > 0.0 && isfinite(s);
         // renormalize falls back to uniform when the sum is not positive (LBP.py:650-657)
-        const double b = ok ? plab / s : 1.0 / (double)V;
+        const double b = ok ? (double)plab / s : 1.0 / (double)V;
         logp[g] = b > 0.0 ? log(b) : -99.99;                      // LBP.py:252-258
         top1[g] = ok ? besti : 0;
         rank[g] = ok ? (int)(c + 0.5) : 0;
@@ -315,7 +321,7 @@ marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ 
     if (beliefs) {
         const bool ok = s > 0.0 && isfinite(s);
         float *brow = beliefs + (size_t)g * ldv;
-        for (int e = threadIdx.x; e < V; e += blockDim.x) brow[e] = ok ? (float)(prod(e) / s) : 1.0f / (float)V;
+        for (int e = threadIdx.x; e < V; e += blockDim.x) brow[e] = ok ? (float)((double)prod(e) / s) : 1.0f / (float)V;
     }
 }
 
@@ -387,12 +393,16 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
 
 extern "C" int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                               const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
-                              int32_t *top1, int32_t *rank, float *beliefs, void *stream) {
+                              int32_t *top1, int32_t *rank, float *beliefs, float range_log2, void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && label && U && D && logp && top1 && rank,
                    "marginals: null pointer");
-    marginals_kernel<<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V, logp,
-                                                              top1, rank, beliefs);
+    if (range_log2 >= 0.f && range_log2 < 100.f)
+        marginals_kernel<float><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V,
+                                                                         logp, top1, rank, beliefs);
+    else
+        marginals_kernel<double><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V,
+                                                                          logp, top1, rank, beliefs);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

@@ -95,34 +95,37 @@ unary_products_kernel(const int32_t *__restrict__ var_de, const int32_t *__restr
     const double scale0 = (double)V * inv_sigma[v];
     float *urow = U + (size_t)v * ldv;
     if (e0 < V) {
-        double u[4] = {1.0, 1.0, 1.0, 1.0};                // d < 0: no en_de factor on this variable
+        // fp32 exp / products here (1 ulp expf, 1e-7 relative): the fp64 pipe of B200 issues ~3 lanes/clk/SM.  The
+        // normaliser inv_sigma and the sparse fix-ups below stay in float64 (a handful of values per variable).
+        float u[4] = {1.f, 1.f, 1.f, 1.f};                  // d < 0: no en_de factor on this variable
         if (d >= 0) {
             const float4 ed4 = *reinterpret_cast<const float4 *>(edT + (size_t)d * ldf + e0);
             const float4 pd4 = *reinterpret_cast<const float4 *>(pedT + (size_t)d * ldf + e0);
             const float ed[4] = {ed4.x, ed4.y, ed4.z, ed4.w}, pd[4] = {pd4.x, pd4.y, pd4.z, pd4.w};
+            const float t0 = (float)th.t[0], t1 = (float)th.t[1], lsc = (float)(th.t[5] + log(scale0));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) u[i] = exp(th.t[0] * (double)ed[i] + th.t[1] * (double)pd[i] + th.t[5]) * scale0;
+            for (int i = 0; i < 4; ++i) u[i] = expf(fmaf(t0, ed[i], fmaf(t1, pd[i], lsc)));
         }
         for (int j = g0; j < g1; ++j) {
             const int o = giv_label[j];
             const int tp = giv_gap1[j] ? 6 : 2;  // T1t / Tt plane pair: row o = column o of T1 / T
             const double cs = colsums[(size_t)(giv_gap1[j] ? 1 : 0) * V + o];
-            const double f = unscale * (double)V / cs;
+            const float f = (float)(unscale * (double)V / cs);
             const __half2 *hi = reinterpret_cast<const __half2 *>(planes + (size_t)tp * ps + (size_t)o * ldv + e0);
             const __half2 *lo = reinterpret_cast<const __half2 *>(planes + (size_t)(tp + 1) * ps + (size_t)o * ldv + e0);
             const float2 h0 = __half22float2(hi[0]), h1 = __half22float2(hi[1]);
             const float2 l0 = __half22float2(lo[0]), l1 = __half22float2(lo[1]);
-            u[0] *= ((double)h0.x + (double)l0.x) * f;
-            u[1] *= ((double)h0.y + (double)l0.y) * f;
-            u[2] *= ((double)h1.x + (double)l1.x) * f;
-            u[3] *= ((double)h1.y + (double)l1.y) * f;
+            u[0] *= (h0.x + l0.x) * f;
+            u[1] *= (h0.y + l0.y) * f;
+            u[2] *= (h1.x + l1.x) * f;
+            u[3] *= (h1.y + l1.y) * f;
         }
         // columns >= V of the padded row stay zero (ldf, ldv are multiples of 4; reads stay inside the row)
         float4 o4;
-        o4.x = (e0 + 0 < V) ? (float)u[0] : 0.f;
-        o4.y = (e0 + 1 < V) ? (float)u[1] : 0.f;
-        o4.z = (e0 + 2 < V) ? (float)u[2] : 0.f;
-        o4.w = (e0 + 3 < V) ? (float)u[3] : 0.f;
+        o4.x = (e0 + 0 < V) ? u[0] : 0.f;
+        o4.y = (e0 + 1 < V) ? u[1] : 0.f;
+        o4.z = (e0 + 2 < V) ? u[2] : 0.f;
+        o4.w = (e0 + 3 < V) ? u[3] : 0.f;
         *reinterpret_cast<float4 *>(urow + e0) = o4;
     }
     // sparse per-sentence features (train.py:176-215): re-evaluate the touched entries of this chunk

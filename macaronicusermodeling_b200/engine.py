@@ -429,7 +429,7 @@ class Engine(object):
             beliefs = torch.empty((n_m, ld), dtype=torch.float32, device=dev) if want_beliefs else None
             k.call('mlbp_marginals', n_m, _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])),
                    _p(bd, int(blob[H_MARG_IN])), c('var_label'), _p(U), _p(D), ld, V, _p(logp_var), _p(top1), _p(rank),
-                   _p(beliefs))
+                   _p(beliefs), range_log2 + self.half_range_log2)
             self.launches += 1
         grad = torch.zeros((corpus.n_sent, 9), dtype=torch.float64, device=dev)
         logp = torch.zeros(corpus.n_sent, dtype=torch.float64, device=dev)

@@ -198,7 +198,7 @@ class FakeKernels(object):
         Dm = _arr(D, np.float32, (d_row0 + n_rows) * ldd).reshape(-1, ldd)
         Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
 
-    def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs):
+    def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs, range_log2):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         ir = _arr(in_row, np.int32, max(int(go[-1]), 1)); lab = _arr(label, np.int32, n_groups)
         Uo = _arr(U, np.float32, (int(gu.max()) + 1) * ldv).reshape(-1, ldv)

@@ -68,3 +68,59 @@ def test_microbatched_equals_whole():
     g, lp, t1, rk = eng.run_many(corpus, roots, 3)
     np.testing.assert_allclose(g.cpu().numpy(), whole.grad.cpu().numpy(), rtol=1e-9, atol=1e-12)
     np.testing.assert_array_equal(t1.cpu().numpy(), whole.top1.cpu().numpy())
+
+
+def test_c3_full_size_vs_oracle():
+    """BASELINE config C3 shape at full size: V = 10 000, Vd = 2 000, k = 20 predicted tokens, 3 sweeps.  Two sentences
+    against the float64 oracle (its fast evaluator, itself pinned to the reference): exact top-1, beliefs, gradient."""
+    model = synth.make_model(10000, 2000, seed=1234, dtype=np.float32)
+    sents = synth.make_corpus(model, 2, k=20, g=0, seed=77)
+    roots = synth.draw_roots(sents, 3, seed=8)
+    m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
+    worst = common_checks.check_against_oracle(make_engine, m64, sents, roots, [0.8, 0.5, -0.3],
+                                               [1.0, -0.6, 0.5, 0.3, 0.4, -0.2])
+    assert worst < 1e-7          # beliefs are O(1e-3) here: 1e-7 absolute is ~1e-4 relative
+    print('C3 worst belief abs err', worst)
+
+
+def test_c5_inference_only_many_sweeps():
+    """BASELINE config C5 shape scaled to what the oracle can check: inference only, 10 sweeps, k = 12; dead-update
+    elimination must not change any belief."""
+    model = synth.make_model(3000, 300, seed=21)
+    sents = synth.make_corpus(model, 3, k=12, g=2, seed=9)
+    roots = synth.draw_roots(sents, 10, seed=5)
+    te, td = [1.2, 0.7, -0.2], [1.5, -0.9, 0.5, 0.3, 0.4, 0.1]
+    r, corpus = common_checks.run_engine(make_engine, model, sents, te, td, roots, 10, beliefs=True, grad=False)
+    from oracle import lbp_oracle as orc
+    tb = orc.Tables(model, te, td)
+    off = corpus.var_off
+    B, T1 = r.beliefs.cpu().numpy(), r.top1.cpu().numpy()
+    for i, s in enumerate(sents):
+        o = orc.run_fast(tb, s, roots[i], 10, want_grad=False)
+        assert np.abs(B[off[i]:off[i + 1], :3000] - o['marginals']).max() < 1e-6
+        np.testing.assert_array_equal(T1[off[i]:off[i + 1]], o['top1'])
+    assert r.stats['dead'] > 0
+
+
+def test_properties_at_scale():
+    """size-independent properties on a batch too big for the oracle: beliefs normalised, the two GEMM
+    implementations (tcgen05 vs CUDA-core float64 accumulate) give the same arg-max and log-posterior, bias gradient 0"""
+    model = synth.make_model(4096, 512, seed=31, dtype=np.float32)
+    sents = synth.make_corpus(model, 24, k=10, g=3, seed=12)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=2))
+    te, td = [0.9, 0.4, -0.1], [1.1, -0.5, 0.5, 0.3, 0.4, -0.2]
+    out = []
+    for impl in (0, 1):
+        eng = Engine(model, gemm_impl=impl)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_grad=True, want_marg=True, want_beliefs=True)
+        out.append((r.beliefs.cpu().numpy()[:, :4096], r.top1.cpu().numpy(), r.logp.cpu().numpy(), r.grad.cpu().numpy()))
+    b0, t0, l0, g0 = out[0]
+    b1, t1, l1, g1 = out[1]
+    np.testing.assert_allclose(b0.sum(axis=1), 1.0, atol=1e-5)
+    assert (b0 >= 0).all()
+    np.testing.assert_array_equal(t0, t1)
+    np.testing.assert_allclose(l0, l1, rtol=2e-6)
+    np.testing.assert_allclose(g0, g1, rtol=1e-4, atol=2e-6)
+    assert np.abs(g0[:, 2]).max() < 1e-9 and np.abs(g0[:, 8]).max() < 1e-9      # bias components (SURVEY.md §3.4)
