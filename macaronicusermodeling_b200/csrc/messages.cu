@@ -8,8 +8,13 @@
 // range (the reference multiplies fp64 values of size 1/V and never rescales, LBP.py:381-385).
 //
 // Phase 1 sums every outgoing product (the renormalisation of Message.renormalize, LBP.py:649-657);
-// phase 2 recomputes it (the inputs are then L2 hits), scales to 2^14 / sum and splits into the fp16 hi / lo
-// operand rows the pairwise GEMM (K4) consumes through TMA.
+// phase 2 recomputes it, scales to 2^14 / sum and splits into the fp16 hi / lo operand rows the pairwise GEMM
+// (K4) consumes through TMA.
+//
+// T = float when the caller's bound (range_log2) proves that no product can leave the fp32 range, else double.
+// Measured on B200 the fp64 pipe issues only ~3 lanes/clk/SM (profiles/README.md), so the double variant is
+// compute-bound at ~16 % of HBM bandwidth; it is the always-safe fallback.  A bulk-async (cp.async.bulk + mbarrier)
+// shared-memory staging of the inputs was tried in round 1 and was slower than these plain coalesced loads.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -115,151 +120,6 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     }
 }
 
-// ---- bulk-async staging shared by the pipelined kernels: one thread streams a chunk of every input row into a ring of
-// shared-memory stages with cp.async.bulk (the copies in flight are not limited by registers), all threads consume.
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const uint32_t a = smem_addr(bar);
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-
-constexpr int K3_STAGES = 4;
-
-// K3, pipelined: same contract as var_to_factor_kernel.  T = float when the caller guarantees (range_log2) that no
-// leave-one-out product can leave the fp32 range, else double.  Measured on B200: the fp64 pipe issues only ~3
-// lanes/clk/SM, so the double variant is compute-bound (~20x below the HBM roofline); it is the safe fallback.  Dynamic shared memory: K3_STAGES stages of (rows + 1) x E
-// floats (row 0 = U chunk, rows 1..n = incoming message chunks), then K3_STAGES mbarriers.
-template <int NMAX, typename T>
-__global__ void __launch_bounds__(K3_THREADS)
-var_to_factor_pipe_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
-                          const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
-                          const int32_t *__restrict__ dest, const float *__restrict__ U, const float *__restrict__ D,
-                          int ldv, int V, __half *__restrict__ A_hi, __half *__restrict__ A_lo, int E, int stage_rows) {
-    extern __shared__ __align__(128) unsigned char k3_smem[];
-    __shared__ const float *s_src[NMAX];
-    __shared__ int s_d0[NMAX], s_d1[NMAX];
-    __shared__ double s_scale[NMAX];
-    __shared__ double red[32];
-    float *buf = reinterpret_cast<float *>(k3_smem);
-    const int stage_floats = stage_rows * E;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(k3_smem + (size_t)K3_STAGES * stage_floats * sizeof(float));
-    const int g = blockIdx.x;
-    const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
-    const float *urow = U + (size_t)grp_u[g] * ldv;
-    if (threadIdx.x < NMAX) {
-        const int j = threadIdx.x;
-        if (j < n) {
-            const int r = in_row[i0 + j];
-            s_src[j] = r >= 0 ? D + (size_t)r * ldv : nullptr;   // nullptr: uniform message (scale-free -> 1)
-            s_d0[j] = dest_off[i0 + j];
-            s_d1[j] = dest_off[i0 + j + 1];
-        } else {
-            s_src[j] = nullptr; s_d0[j] = 0; s_d1[j] = 0;
-        }
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < K3_STAGES; ++s) bar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int Vr = (V + 3) & ~3;                                  // bulk copies move multiples of 16 bytes
-    const int nchunks = (V + E - 1) / E;
-    const int total = 2 * nchunks;                                // phase 1 (sums) then phase 2 (normalise + write)
-    int n_real = 1;
-    for (int j = 0; j < n; ++j) n_real += s_src[j] ? 1 : 0;
-
-    auto issue = [&](int it) {                                    // thread 0 only
-        const int s = it % K3_STAGES, e0 = (it % nchunks) * E;
-        const uint32_t bytes = (uint32_t)(min(E, Vr - e0) * 4);
-        float *st = buf + (size_t)s * stage_floats;
-        bar_expect_tx(&bars[s], bytes * (uint32_t)n_real);
-        bulk_g2s(st, urow + e0, bytes, &bars[s]);
-        for (int j = 0; j < n; ++j)
-            if (s_src[j]) bulk_g2s(st + (size_t)(1 + j) * E, s_src[j] + e0, bytes, &bars[s]);
-    };
-    if (threadIdx.x == 0)
-        for (int it = 0; it < K3_STAGES && it < total; ++it) issue(it);
-
-    T acc[NMAX];
-#pragma unroll
-    for (int j = 0; j < NMAX; ++j) acc[j] = (T)0;
-    const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
-
-    for (int it = 0; it < total; ++it) {
-        const int s = it % K3_STAGES, e0 = (it % nchunks) * E;
-        const int cnt = min(E, V - e0);
-        const float *st = buf + (size_t)s * stage_floats;
-        if (it == nchunks) {                                      // between the phases: renormalisation constants
-#pragma unroll
-            for (int j = 0; j < NMAX; ++j) {
-                if (j < n && s_d1[j] > s_d0[j]) {                 // block-uniform condition
-                    const double sum = block_sum((double)acc[j], red);
-                    if (threadIdx.x == 0)
-                        s_scale[j] = (sum > 0.0 && isfinite(sum)) ? ldexp(1.0, MLBP_A_SCALE_LOG2) / sum : -1.0;
-                }
-            }
-            __syncthreads();
-        }
-        bar_wait(&bars[s], (uint32_t)(it / K3_STAGES) & 1u);
-        for (int el = threadIdx.x; el < cnt; el += K3_THREADS) {
-            float d[NMAX];
-#pragma unroll
-            for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? st[(size_t)(1 + j) * E + el] : 1.0f;
-            T pre[NMAX];
-            T p = (T)st[el];
-#pragma unroll
-            for (int j = 0; j < NMAX; ++j) { pre[j] = p; p *= (T)d[j]; }
-            T suf = (T)1;
-            if (it < nchunks) {
-#pragma unroll
-                for (int j = NMAX - 1; j >= 0; --j) {
-                    acc[j] += pre[j] * suf;
-                    suf *= (T)d[j];
-                }
-            } else {
-                const size_t e = (size_t)(e0 + el);
-#pragma unroll
-                for (int j = NMAX - 1; j >= 0; --j) {
-                    if (j < n && s_d1[j] > s_d0[j]) {
-                        const double sc = s_scale[j];
-                        const float x = sc > 0.0 ? (float)(pre[j] * suf * (T)sc) : uni;
-                        __half hi, lo;
-                        split_f16(x, hi, lo);
-                        for (int t = s_d0[j]; t < s_d1[j]; ++t) {
-                            const size_t o = (size_t)dest[t] * ldv + e;
-                            A_hi[o] = hi;
-                            A_lo[o] = lo;
-                        }
-                    }
-                    suf *= (T)d[j];
-                }
-            }
-        }
-        __syncthreads();                                          // everyone is done with stage s
-        if (threadIdx.x == 0 && it + K3_STAGES < total) issue(it + K3_STAGES);
-    }
-}
-
 // one CTA per variable: total product of all incoming messages (T = float under the same range bound as K3)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -345,36 +205,16 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
     const bool fp32_ok = range_log2 >= 0.f && range_log2 < 100.f;   // products provably stay inside 2^+-100
-    static const int k3_impl = [] { const char *e = getenv("MLBP_K3_IMPL"); return e ? atoi(e) : 1; }();   // 1 = direct loads (default), 0 = bulk-async staging (slower: 2 KB bulk copies)
     MLBP_CHECK_ARG(V > 0 && ldv >= V && (ldv % 4) == 0, "var_to_factor: bad V/ldv");
     cudaStream_t st = as_stream(stream);
-    // stage geometry: (max_in + 1) rows x E floats per stage, K3_STAGES stages (+ barriers) within 200 KB
-    const int stage_rows = max_in + 1;
-    int E = 512;
-    while (E > 64 && (size_t)K3_STAGES * stage_rows * E * 4 + 64 > 200 * 1024) E >>= 1;
-    const size_t smem = (size_t)K3_STAGES * stage_rows * E * 4 + 64;
-#define MLBP_K3_LAUNCH(N)                                                                                             \
-    do {                                                                                                              \
-        static bool attr_done = false;                                                                                \
-        if (!attr_done) {                                                                                             \
-            MLBP_CUDA(cudaFuncSetAttribute(var_to_factor_pipe_kernel<N, float>,                                       \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64));            \
-            MLBP_CUDA(cudaFuncSetAttribute(var_to_factor_pipe_kernel<N, double>,                                      \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64));            \
-            attr_done = true;                                                                                         \
-        }                                                                                                             \
-        if (k3_impl == 1 && fp32_ok)                                                                                  \
-            var_to_factor_kernel<N, float><<<n_groups, K3_THREADS, 0, st>>>(                                          \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);                \
-        else if (k3_impl == 1)                                                                                        \
-            var_to_factor_kernel<N, double><<<n_groups, K3_THREADS, 0, st>>>(                                         \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);                \
-        else if (fp32_ok)                                                                                             \
-            var_to_factor_pipe_kernel<N, float><<<n_groups, K3_THREADS, smem, st>>>(                                  \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, E, stage_rows); \
-        else                                                                                                          \
-            var_to_factor_pipe_kernel<N, double><<<n_groups, K3_THREADS, smem, st>>>(                                 \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, E, stage_rows); \
+#define MLBP_K3_LAUNCH(N)                                                                                        \
+    do {                                                                                                         \
+        if (fp32_ok)                                                                                             \
+            var_to_factor_kernel<N, float><<<n_groups, K3_THREADS, 0, st>>>(                                     \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+        else                                                                                                     \
+            var_to_factor_kernel<N, double><<<n_groups, K3_THREADS, 0, st>>>(                                    \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);

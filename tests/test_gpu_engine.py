@@ -124,3 +124,26 @@ def test_properties_at_scale():
     np.testing.assert_allclose(l0, l1, rtol=2e-6)
     np.testing.assert_allclose(g0, g1, rtol=1e-4, atol=2e-6)
     assert np.abs(g0[:, 2]).max() < 1e-9 and np.abs(g0[:, 8]).max() < 1e-9      # bias components
+
+
+@pytest.mark.parametrize('V,Vd', [(203, 37), (1001, 129), (67, 5)])
+def test_odd_vocabulary_sizes(V, Vd):
+    """V not a multiple of 4 / 8 / 64: padded rows, TMA out-of-bounds zero fill, partial tiles"""
+    model = synth.make_model(V, Vd, seed=V)
+    layouts = ['ppp', 'gpppp', 'pgpgp', 'pp', 'p', 'pppppp']
+    sents = [synth.sentence_to_arrays(synth.make_sentence(model, l, seed=V + i, n_history=2)) for i, l in enumerate(layouts)]
+    roots = synth.draw_roots(sents, 3, seed=1)
+    common_checks.check_against_oracle(make_engine, model, sents, roots, [0.5, 0.6, -0.2], [0.7, -0.4, 0.5, 0.2, 0.3, 0.1])
+
+
+def test_wide_theta_uses_fp64_products():
+    """|theta| so large that products of messages may leave the fp32 range: the range bound switches K3 / K5 to their
+    float64 variants; results must still match the oracle"""
+    model = synth.make_model(128, 16, seed=5)
+    sents = synth.make_corpus(model, 3, k=6, g=2, seed=3)
+    roots = synth.draw_roots(sents, 3, seed=2)
+    te, td = [14.0, 9.0, -2.0], [6.0, -5.0, 2.0, 1.0, 1.0, 0.5]
+    eng = make_engine(model)
+    eng.set_theta(te, td)
+    assert (6 + 4) * eng.half_range_log2 + eng.unary_range_log2 > 100
+    common_checks.check_against_oracle(make_engine, model, sents, roots, te, td)
