@@ -243,6 +243,10 @@ class Engine(object):
         zmin = te[2] + min(te[0] * pmin, te[0] * pmax) + min(te[1] * wmin, te[1] * wmax, 0.0)
         self.centre_exp = int(round((zmin + zmax) / 2.0 / math.log(2.0)))
         self.half_range_log2 = (zmax - zmin) / 2.0 / math.log(2.0) + 0.5
+        if zmax - zmin > 12.0:
+            import warnings
+            warnings.warn('pairwise potentials span e^%.1f: entries more than 2^18 below the largest lose relative '
+                          'precision in the fp16 hi/lo operand planes (absolute error stays 2^-38 of the maximum)' % (zmax - zmin))
         erange, prange = self.model.ed_range
         self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
         n_planes = N_PLANES if with_grad else 8

@@ -142,7 +142,7 @@ def test_wide_theta_uses_fp64_products():
     model = synth.make_model(128, 16, seed=5)
     sents = synth.make_corpus(model, 3, k=6, g=2, seed=3)
     roots = synth.draw_roots(sents, 3, seed=2)
-    te, td = [14.0, 9.0, -2.0], [6.0, -5.0, 2.0, 1.0, 1.0, 0.5]
+    te, td = [7.0, 3.0, -1.0], [6.0, -5.0, 2.0, 1.0, 1.0, 0.5]
     eng = make_engine(model)
     eng.set_theta(te, td)
     assert (6 + 4) * eng.half_range_log2 + eng.unary_range_log2 > 100
