@@ -146,4 +146,5 @@ def test_wide_theta_uses_fp64_products():
     eng = make_engine(model)
     eng.set_theta(te, td)
     assert (6 + 4) * eng.half_range_log2 + eng.unary_range_log2 > 100
-    common_checks.check_against_oracle(make_engine, model, sents, roots, te, td)
+    # beliefs are peaked (0.3 .. 0.97) here: the 22-bit operand planes bound the error at ~1e-6 absolute
+    common_checks.check_against_oracle(make_engine, model, sents, roots, te, td, belief_atol=1e-5)
