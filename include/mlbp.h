@@ -110,8 +110,10 @@ int mlbp_unary_products(int nv, const int32_t *var_de, const int32_t *sp_off, co
 /* ------------------------------------------------------------------------------------------------
  * (4) message kernels
  * ------------------------------------------------------------------------------------------------ */
-/* uniform 1/V messages of FactorGraph.initialize (LBP.py:211-216) as fp16 hi/lo rows: rows[i] of A := 2^14 / V */
-int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t *rows, int n_rows, void *stream);
+/* uniform 1/V messages of FactorGraph.initialize (LBP.py:211-216) as fp16 hi/lo rows: rows[i] of A := 2^14 / V.
+ * keep (optional, may be NULL): uint8 [V]; entries with keep[e] == 0 are written as 0 (top-K mask of a uniform message). */
+int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t *rows, int n_rows,
+                           const uint8_t *keep, void *stream);
 /* K3.  VariableNode.update_message_to (LBP.py:377-389) for n_groups (variable, level) groups at once.
  *   group g multiplies U[grp_u[g]] with the factor->variable rows D[in_row[i]], i in [grp_off[g], grp_off[g+1]);
  *   for every i with destinations it emits the leave-one-out product (all inputs except i), renormalised
@@ -122,6 +124,11 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const float *U, const float *D, int ldv, int V,
                        void *A_hi, void *A_lo, int max_in, float range_log2, void *stream);
+/* Approximate paths (use_approx_inference LBP.py:506-507, :515-516 -> au.sparse_vec_mat_dot pyx:193-205;
+ *   use_approx_beliefs LBP.py:554-563 -> au.sparse_dot / sparse_pointwise_multiply / sparse_normalize pyx:108-129, :23-26):
+ *   keep the K largest entries of each of the n_rows operand rows A[row0 ..], zero the others (K = 100 in the reference);
+ *   the dense kernels then produce exactly the reference's restricted sums.  No-op when K >= V.                  */
+int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, int n_rows, int K, void *stream);
 /* K4.  FactorNode.update_message_to for pairwise factors (LBP.py:499-526; au.dense_dot pyx:90-91), batched:
  *   D[d_row0 + r, n] = alpha * sum_k (A_hi + A_lo)[a_row0 + r, k] * (B_hi + B_lo)[n, k],  r < n_rows, n < V
  *   as three tcgen05 passes hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory.
@@ -161,7 +168,8 @@ typedef struct mlbp_plan mlbp_plan;
  * order they were attached (defines facset order, LBP.py:367-369).  pair_v0/pair_v1 are variable indices LOCAL to
  * the graph (v0 = dim 0, v1 = dim 1 of the potential table), pair_gap1 selects pot_en_en_w1 (LBP.py:456-463).
  * roots: local variable index per graph and draw, [n_graphs, 1 + sweeps] (draw 0 = has_loops, LBP.py:176).
- * flags: bit 0 = plan the gradient stage, bit 1 = plan the marginal stage.                              */
+ * flags: bit 0 = plan the gradient stage, bit 1 = plan the marginal stage, bit 2 = do NOT constant-fold updates
+ *        that read an initial uniform message (needed by the top-K approximate mode, which masks that message). */
 int mlbp_plan_compile(int n_graphs, const int32_t *h_var_off, const int32_t *h_pair_off, const int32_t *h_pair_v0,
                       const int32_t *h_pair_v1, const int32_t *h_pair_gap1, const int32_t *h_roots, int sweeps,
                       int flags, mlbp_plan **out);

@@ -271,7 +271,8 @@ class FactorGraph():
         raise BaseException("only 2 kinds of distances are supported ...")
 
     def _run(self):
-        if self._res is not None and self._res['key'] == (self._sweeps, self._theta_key()):
+        if self._res is not None and self._res['key'] == (self._sweeps, self._theta_key(), bool(self.use_approx_inference),
+                                                          bool(self.use_approx_beliefs)):
             return self._res
         if not self._initialized:
             raise KeyError('messages are not initialised: call initialize() first')
@@ -280,7 +281,8 @@ class FactorGraph():
         eng.set_theta(np.asarray(self.theta_en_en, dtype=np.float64).reshape(-1),
                       np.asarray(self.theta_en_de, dtype=np.float64).reshape(-1))
         roots = corpus.roots_from_positions([list(self._roots)])
-        r = eng.run(corpus, roots, self._sweeps, want_grad=True, want_marg=True, want_beliefs=True, want_messages=True)
+        r = eng.run(corpus, roots, self._sweeps, want_grad=True, want_marg=True, want_beliefs=True, want_messages=True,
+                    approx_inference=bool(self.use_approx_inference), approx_beliefs=bool(self.use_approx_beliefs))
         V = eng.V
         # name the final pairwise messages like the reference's dict keys
         final = {}
@@ -295,7 +297,8 @@ class FactorGraph():
                 m = r.messages['f2v'][local[v.id]][slot[local[v.id]]]
                 final[str(f), str(v)] = uni.copy() if m is None else m
                 slot[local[v.id]] += 1
-        self._res = {'key': (self._sweeps, self._theta_key()), 'vids': vids, 'pairs': pair_factors,
+        self._res = {'key': (self._sweeps, self._theta_key(), bool(self.use_approx_inference), bool(self.use_approx_beliefs)),
+                     'vids': vids, 'pairs': pair_factors,
                      'beliefs': r.beliefs.cpu().numpy()[:, :V].astype(np.float64), 'grad': r.grad.cpu().numpy()[0],
                      'logp_var': r.logp_var.cpu().numpy(), 'top1': r.top1.cpu().numpy(), 'rank': r.rank.cpu().numpy(),
                      'final': final}

@@ -17,8 +17,9 @@ _SIGNATURES = {
     'mlbp_build_unary_tables': 'ppiiippp',
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
-    'mlbp_fill_uniform_rows': 'ppiipip',
+    'mlbp_fill_uniform_rows': 'ppiipipp',
     'mlbp_var_to_factor': 'ippppp' + 'ppii' + 'ppifp',
+    'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppfp',
     'mlbp_pair_expectations': 'ipppp' + 'pppii' + 'pp',

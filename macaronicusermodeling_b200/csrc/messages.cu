@@ -24,14 +24,15 @@ namespace mlbp {
 constexpr int K3_THREADS = 256;
 
 __global__ void fill_uniform_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int ldv, int V,
-                                         const int32_t *__restrict__ rows) {
+                                         const int32_t *__restrict__ rows, const uint8_t *__restrict__ keep) {
     const size_t r = (size_t)rows[blockIdx.x];
     __half hi, lo;
     split_f16(ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V, hi, lo);
     const __half z = __float2half_rn(0.f);
     for (int e = threadIdx.x; e < ldv; e += blockDim.x) {
-        A_hi[r * ldv + e] = e < V ? hi : z;
-        A_lo[r * ldv + e] = e < V ? lo : z;
+        const bool on = e < V && (!keep || keep[e]);
+        A_hi[r * ldv + e] = on ? hi : z;
+        A_lo[r * ldv + e] = on ? lo : z;
     }
 }
 
@@ -120,6 +121,47 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     }
 }
 
+// Top-K masking of message rows: the reference's approximate paths (use_approx_inference / use_approx_beliefs,
+// LBP.py:506-507, :515-516, :554-563) contract only the K = 100 largest entries of a message
+// (au.sparse_vec_mat_dot pyx:193-205, au.sparse_dot pyx:117-129).  Zeroing every other entry of the operand row and
+// running the same dense GEMM gives the same sums.  One CTA per row: 4-pass radix select (8 bits per pass) on the bit
+// patterns of hi + lo (non-negative floats order like their bits), then one masking pass; ties at the threshold are
+// kept in arbitrary order up to K, like np.argpartition.
+__global__ void __launch_bounds__(256)
+topk_mask_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int ldv, int V, int64_t row0, int K) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_need, s_taken;
+    __half *hi = A_hi + (size_t)(row0 + blockIdx.x) * ldv, *lo = A_lo + (size_t)(row0 + blockIdx.x) * ldv;
+    auto bits_of = [&](int e) { return __float_as_uint(__half2float(hi[e]) + __half2float(lo[e])); };
+    if (threadIdx.x == 0) { s_prefix = 0u; s_need = (unsigned)K; s_taken = 0u; }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        for (int e = threadIdx.x; e < V; e += 256) {
+            const unsigned b = bits_of(e);
+            if (shift == 24 || (b >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned cum = 0, need = s_need;
+            for (int b = 255; b >= 0; --b) {
+                if (cum + hist[b] >= need) { s_need = need - cum; s_prefix = prefix | ((unsigned)b << shift); break; }
+                cum += hist[b];
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned thr = s_prefix, need = s_need;     // K-th largest bit pattern; keep `need` of the entries equal to it
+    const __half z = __float2half_rn(0.f);
+    for (int e = threadIdx.x; e < V; e += 256) {
+        const unsigned b = bits_of(e);
+        bool keep = b > thr;
+        if (b == thr) keep = atomicAdd(&s_taken, 1u) < need;
+        if (!keep) { hi[e] = z; lo[e] = z; }
+    }
+}
+
 // one CTA per variable: total product of all incoming messages (T = float under the same range bound as K3)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -190,10 +232,10 @@ marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ 
 using namespace mlbp;
 
 extern "C" int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t *rows, int n_rows,
-                                      void *stream) {
+                                      const uint8_t *keep, void *stream) {
     if (n_rows == 0) return MLBP_OK;
     MLBP_CHECK_ARG(A_hi && A_lo && rows && n_rows > 0 && V > 0 && ldv >= V, "fill_uniform_rows: bad argument");
-    fill_uniform_rows_kernel<<<n_rows, 256, 0, as_stream(stream)>>>((__half *)A_hi, (__half *)A_lo, ldv, V, rows);
+    fill_uniform_rows_kernel<<<n_rows, 256, 0, as_stream(stream)>>>((__half *)A_hi, (__half *)A_lo, ldv, V, rows, keep);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -227,6 +269,14 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
 #undef MLBP_K3_LAUNCH
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, int n_rows, int K, void *stream) {
+    if (n_rows == 0 || K >= V) return MLBP_OK;
+    MLBP_CHECK_ARG(A_hi && A_lo && n_rows > 0 && K > 0 && row0 >= 0 && ldv >= V, "topk_mask_rows: bad argument");
+    topk_mask_rows_kernel<<<n_rows, 256, 0, as_stream(stream)>>>((__half *)A_hi, (__half *)A_lo, ldv, V, row0, K);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

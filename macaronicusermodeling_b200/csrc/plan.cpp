@@ -61,6 +61,7 @@ struct Op {
 
 struct Graph {
     int nv = 0, np = 0;
+    bool fold = true;                           // constant-fold updates that read the initial uniform message
     std::vector<int32_t> v0, v1, gap1;
     std::vector<std::vector<int32_t>> facset;   // incident pairwise factors per variable, attach order
     std::vector<Op> ops;
@@ -138,7 +139,7 @@ void add_f2v(Graph &g, Tracker &t, int f, int side) {           // FactorNode.up
     const int e_out = 2 * f + side, e_in = 2 * f + (1 - side);
     Op op{};
     op.kind = 1; op.f = f; op.side = side; op.live = 0; op.row = -1;
-    op.folded = t.cur_v2f[e_in] < 0 ? 1 : 0;
+    op.folded = (g.fold && t.cur_v2f[e_in] < 0) ? 1 : 0;
     op.table = g.gap1[f] ? (side == 0 ? MLBP_TABLE_T1 : MLBP_TABLE_T1T) : (side == 0 ? MLBP_TABLE_T : MLBP_TABLE_TT);
     op.in0 = (int32_t)g.inputs.size();
     g.inputs.push_back(t.cur_v2f[e_in]);
@@ -240,6 +241,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         std::vector<char> needed;
         for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
             Graph &g = G[gi];
+            g.fold = !(flags & 4);
             g.nv = var_off[gi + 1] - var_off[gi];
             g.np = pair_off[gi + 1] - pair_off[gi];
             if (g.nv <= 0) { err[c] = 1; return; }

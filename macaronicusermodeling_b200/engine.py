@@ -327,13 +327,13 @@ class Engine(object):
             self._blob_dev = torch.empty(n, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------ one microbatch
-    def compile(self, corpus, roots, sweeps, want_grad, want_marg):
+    def compile(self, corpus, roots, sweeps, want_grad, want_marg, fold=True):
         roots = np.ascontiguousarray(roots, dtype=np.int32)
         assert roots.shape[0] == corpus.n_sent and roots.shape[1] >= 1 + sweeps, roots.shape
         roots = np.ascontiguousarray(roots[:, :1 + sweeps])
         handle = ctypes.c_void_p()
         lib = _lib.load()
-        flags = (1 if want_grad else 0) | (2 if want_marg else 0)
+        flags = (1 if want_grad else 0) | (2 if want_marg else 0) | (0 if fold else 4)
         _lib.check(lib.mlbp_plan_compile(corpus.n_sent, _hp(corpus.var_off), _hp(corpus.pair_off), _hp(corpus.pair_v0),
                                          _hp(corpus.pair_v1), _hp(corpus.pair_gap1), _hp(roots), sweeps, flags,
                                          ctypes.byref(handle)))
@@ -341,13 +341,14 @@ class Engine(object):
         _lib.check(lib.mlbp_plan_sizes(handle, _hp(sizes)))
         return handle, sizes
 
-    def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False):
+    def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False,
+            approx_inference=False, approx_beliefs=False, topk=100):
         """All sentences of `corpus` (must fit the workspace; use run_many to micro-batch).  `roots`: int
         [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176)."""
         assert self.theta_ee is not None, 'set_theta first'
         assert not want_grad or self.with_grad_planes
         lib = _lib.load()
-        handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg)
+        handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference)
         try:
             words = int(sizes[PLAN_BLOB_WORDS])
             nv = corpus.n_vars
@@ -381,16 +382,29 @@ class Engine(object):
                V * ld, ld, self.scale_exp, _p(self.colsums), _p(U))
         self.launches += 2
         if blob[H_INIT_N]:
-            k.call('mlbp_fill_uniform_rows', _p(A_hi), _p(A_lo), ld, V, _p(bd, int(blob[H_INIT_OFF])), int(blob[H_INIT_N]))
+            keep = None
+            if (approx_inference or approx_beliefs) and topk < V:
+                # The reference takes the top-K of the still-uniform initial message too; which K of the V equal entries
+                # survive is decided by NumPy's argpartition (pyx:198, :203).  Ask the same NumPy (indices only, no arithmetic).
+                km = np.zeros(V, dtype=np.uint8)
+                km[np.argpartition(-np.full(V, 1.0 / V), topk - 1)[:topk]] = 1
+                keep = torch.from_numpy(km).to(dev)
+            k.call('mlbp_fill_uniform_rows', _p(A_hi), _p(A_lo), ld, V, _p(bd, int(blob[H_INIT_OFF])), int(blob[H_INIT_N]),
+                   _p(keep))
             self.launches += 1
         max_in = int(blob[H_MAX_IN])
         alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp + self.centre_exp)))
         g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
         range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
 
-        def gemm_calls(off, n):
+        def gemm_calls(off, n, mask):
+            masked = set()
             for i in range(n):
                 t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
+                if mask and (a0, rows) not in masked:             # reference's top-K approximations (pyx:193-205)
+                    k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, a0, rows, topk)
+                    masked.add((a0, rows))
+                    self.launches += 1
                 if self.profile_gemm:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
@@ -409,13 +423,22 @@ class Engine(object):
                 k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])), _p(bd, int(rec[3])),
                        _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), max_in, range_log2)
                 self.launches += 1
-            gemm_calls(int(rec[7]), int(rec[6]))
+            gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
         n_pair = int(blob[H_NPAIR])
         pair_stats = torch.zeros((max(n_pair, 1), 3), dtype=torch.float64, device=dev)
         pair_l0 = pair_l1 = None
+        v2f_rows = None
+        if want_messages and n_pair:                              # before any gradient-stage masking
+            oc, orr = int(blob[H_PAIR_C]), int(blob[H_PAIR_R])
+            rows = torch.cat([bd[oc:oc + n_pair], bd[orr:orr + n_pair]]).long()
+            v2f_rows = (A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)
         if want_grad and n_pair:
-            gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]))
+            gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs)
+            if approx_beliefs:                                    # the c rows follow the r rows in the A buffer
+                c0 = int(blob[int(blob[H_PAIR_C])])
+                k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, c0, n_pair, topk)
+                self.launches += 1
             k.call('mlbp_pair_expectations', n_pair, _p(bd, int(blob[H_PAIR_C])), _p(bd, int(blob[H_PAIR_U0])),
                    _p(bd, int(blob[H_PAIR_U1])), _p(bd, int(blob[H_PAIR_U2])), _p(A_hi), _p(A_lo), _p(D), ld, V,
                    _p(pair_stats))
@@ -455,9 +478,7 @@ class Engine(object):
             assert want_grad and want_marg
             messages = {'v2f': [], 'f2v': []}
             if n_pair:
-                oc, orr = int(blob[H_PAIR_C]), int(blob[H_PAIR_R])
-                rows = torch.cat([bd[oc:oc + n_pair], bd[orr:orr + n_pair]]).long()
-                m = ((A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)).cpu().numpy()
+                m = v2f_rows.cpu().numpy()
                 messages['v2f'] = [(m[i], m[n_pair + i]) for i in range(n_pair)]
             mo, mi = int(blob[H_MARG_OFF]), int(blob[H_MARG_IN])
             n_m = int(blob[H_MARG_N])

@@ -189,6 +189,12 @@ def golden_case_specs():
         'zeros': dict(V=64, Vd=20, layout='ppgp', sweeps=3, model_seed=8, sent_seed=18, theta_ee=[0.0, 0.0, 0.0],
                       theta_ed=[0.0] * 6),
         'k8': dict(V=128, Vd=32, layout='pppppppp', sweeps=3, model_seed=9, sent_seed=19, theta_ee=t_ee, theta_ed=t_ed),
+        'approx_inf': dict(V=160, Vd=24, layout='pgppp', sweeps=3, model_seed=11, sent_seed=21, theta_ee=[2.0, 1.0, -0.5],
+                           theta_ed=[2.0, -1.0, 0.5, 0.3, 0.4, -0.1], approx_inference=True),
+        'approx_both': dict(V=160, Vd=24, layout='ppgpp', sweeps=3, model_seed=12, sent_seed=22, theta_ee=[2.0, 1.0, -0.5],
+                            theta_ed=[2.0, -1.0, 0.5, 0.3, 0.4, -0.1], approx_inference=True, approx_beliefs=True),
+        'approx_bel': dict(V=160, Vd=24, layout='pppp', sweeps=3, model_seed=13, sent_seed=23, theta_ee=[2.0, 1.0, -0.5],
+                           theta_ed=[2.0, -1.0, 0.5, 0.3, 0.4, -0.1], approx_beliefs=True),
         'sweeps5': dict(V=64, Vd=20, layout='pgppp', sweeps=5, model_seed=10, sent_seed=20, theta_ee=t_ee, theta_ed=t_ed),
     }
 

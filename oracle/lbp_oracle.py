@@ -145,6 +145,19 @@ def dense_phi_en_en(model):
     return phi, phi_w1
 
 
+TOPK = 100   # hard-coded K of the reference's sparse approximations (c_array_utils.pyx:118, :194)
+
+
+def _topk_mask(m, k=TOPK):
+    """keep the k largest entries of a vector, zero the rest: what au.sparse_vec_mat_dot (pyx:193-205) and au.sparse_dot
+    (pyx:117-129) do to a message before contracting it (same NumPy argpartition call, so ties resolve alike)"""
+    v = np.asarray(m).reshape(-1)
+    idx = np.argpartition(-v, k - 1)[:k]
+    out = np.zeros_like(v)
+    out[idx] = v[idx]
+    return out.reshape(np.shape(m))
+
+
 def _normalize(m):
     """c_array_utils.pyx:29-40 via Message.renormalize LBP.py:649-657."""
     s = np.sum(m)
@@ -154,7 +167,8 @@ def _normalize(m):
 
 
 # ----------------------------------------------------------------------------------------- literal evaluator
-def run_literal(model, sent, theta_ee, theta_ed, roots, sweeps=3, reg=0.0, lr=1.0, keep_messages=True):
+def run_literal(model, sent, theta_ee, theta_ed, roots, sweeps=3, reg=0.0, lr=1.0, keep_messages=True,
+                approx_inference=False, approx_beliefs=False):
     """One sentence through create_factor_graph / initialize / treelike_inference / get_gradient exactly as
     the reference computes it.  Returns a dict (messages keyed like the reference's graph.messages)."""
     theta_ee = np.asarray(theta_ee, dtype=np.float64).reshape(1, 3)
@@ -209,6 +223,8 @@ def run_literal(model, sent, theta_ee, theta_ed, roots, sweeps=3, reg=0.0, lr=1.
         o = f.vars[1] if f.vars[0] == v else f.vars[0]
         o_dim = f.vars.index(o)                                                   # var_id2dim: vars[0]->0, vars[1]->1
         m = msgs[('X', o), ('F', fid)]
+        if approx_inference:                                                      # LBP.py:506-507, :515-516
+            m = _topk_mask(m)
         if o_dim == 1:
             r = tables[fid].dot(m)                                                # LBP.py:509
         else:
@@ -248,6 +264,8 @@ def run_literal(model, sent, theta_ee, theta_ed, roots, sweeps=3, reg=0.0, lr=1.
         else:
             c = msgs[('X', f.vars[0]), ('F', f.id)].reshape(V, 1)                 # LBP.py:544-553
             r = msgs[('X', f.vars[1]), ('F', f.id)].reshape(1, V)
+            if approx_beliefs:                                                    # LBP.py:554-563: top-K x top-K block only
+                c, r = _topk_mask(c), _topk_mask(r)
             b = np.multiply(c.dot(r), tb)                                         # LBP.py:566-568
             s = np.sum(b)
             beliefs = b / s if s > 0 else np.zeros_like(b)
@@ -314,7 +332,8 @@ class Tables(object):
         self.model = model
 
 
-def run_fast(tables, sent, roots, sweeps=3, reg=0.0, lr=1.0, want_grad=True):
+def run_fast(tables, sent, roots, sweeps=3, reg=0.0, lr=1.0, want_grad=True, approx_inference=False,
+             approx_beliefs=False):
     """Same results as run_literal; GEMVs of one dependency level batched into one dgemm."""
     model = tables.model
     te, td = tables.te, tables.td
@@ -376,7 +395,7 @@ def run_fast(tables, sent, roots, sweeps=3, reg=0.0, lr=1.0, want_grad=True):
             to_dim0 = (f.vars[0] == v)
             o = f.vars[1] if to_dim0 else f.vars[0]
             key = (f.gap == 1, to_dim0)
-            groups.setdefault(key, []).append((fid, v, v2f[o, fid]))
+            groups.setdefault(key, []).append((fid, v, _topk_mask(v2f[o, fid]) if approx_inference else v2f[o, fid]))
         for (w1, to_dim0), items in groups.items():
             M = np.stack([it[2] for it in items])
             if to_dim0:
@@ -411,6 +430,9 @@ def run_fast(tables, sent, roots, sweeps=3, reg=0.0, lr=1.0, want_grad=True):
                 continue
             R = np.stack([v2f[f.vars[1], f.id] for f in fs])
             C = np.stack([v2f[f.vars[0], f.id] for f in fs])
+            if approx_beliefs:
+                R = np.stack([_topk_mask(x) for x in R])
+                C = np.stack([_topk_mask(x) for x in C])
             U0 = R.dot(tables.T1t if gap1 else tables.Tt)
             U1 = R.dot((tables.G1 if gap1 else tables.G).T)
             Z = np.einsum('ij,ij->i', C, U0)

@@ -23,17 +23,18 @@ def load_fixture(path):
     return z, model, json.loads(str(z['spec'])), synth.sentence_to_arrays(str(z['sentence']))
 
 
-def run_engine(make_engine, model, sents, theta_ee, theta_ed, roots_pos, sweeps, beliefs=True, grad=True):
+def run_engine(make_engine, model, sents, theta_ee, theta_ed, roots_pos, sweeps, beliefs=True, grad=True, **kw):
     eng = make_engine(model)
     eng.set_theta(theta_ee, theta_ed, with_grad=grad)
     corpus = Corpus(sents)
     roots = corpus.roots_from_positions(roots_pos)
-    return eng.run(corpus, roots, sweeps, want_grad=grad, want_marg=True, want_beliefs=beliefs), corpus
+    return eng.run(corpus, roots, sweeps, want_grad=grad, want_marg=True, want_beliefs=beliefs, **kw), corpus
 
 
 def check_fixture(make_engine, path):
     z, model, spec, sent = load_fixture(path)
-    r, corpus = run_engine(make_engine, model, [sent], z['theta_ee'], z['theta_ed'], [list(z['roots'])], spec['sweeps'])
+    r, corpus = run_engine(make_engine, model, [sent], z['theta_ee'], z['theta_ed'], [list(z['roots'])], spec['sweeps'],
+                           approx_inference=spec.get('approx_inference', False), approx_beliefs=spec.get('approx_beliefs', False))
     V = model['V']
     b = r.beliefs.cpu().numpy()[:, :V]
     assert np.abs(b - z['marginals']).max() < BELIEF_ATOL

@@ -150,12 +150,13 @@ class FakeKernels(object):
             Uo[v, V:] = 0
 
     # ---- messages
-    def mlbp_fill_uniform_rows(self, A_hi, A_lo, ldv, V, rows, n_rows):
+    def mlbp_fill_uniform_rows(self, A_hi, A_lo, ldv, V, rows, n_rows, keep):
         r = _arr(rows, np.int32, n_rows)
         hi, lo = _split(np.array([A_SCALE / V]))
         n = (int(r.max()) + 1) * ldv
         H, L = _arr(A_hi, np.float16, n).reshape(-1, ldv), _arr(A_lo, np.float16, n).reshape(-1, ldv)
-        H[r, :V], L[r, :V] = hi[0], lo[0]
+        km = _arr(keep, np.uint8, V) if keep is not None and keep.value else np.ones(V, dtype=np.uint8)
+        H[r, :V], L[r, :V] = np.where(km, hi[0], 0), np.where(km, lo[0], 0)
         H[r, V:], L[r, V:] = 0, 0
 
     def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2):
@@ -187,6 +188,18 @@ class FakeKernels(object):
                 hi, lo = _split(x)
                 for tdest in de[do[i]:do[i + 1]]:
                     H[tdest, :V], L[tdest, :V] = hi, lo
+
+    def mlbp_topk_mask_rows(self, A_hi, A_lo, ldv, V, row0, n_rows, K):
+        if K >= V:
+            return
+        H = _arr(A_hi, np.float16, (row0 + n_rows) * ldv).reshape(-1, ldv)
+        L = _arr(A_lo, np.float16, (row0 + n_rows) * ldv).reshape(-1, ldv)
+        for r in range(row0, row0 + n_rows):
+            v = H[r, :V].astype(np.float32) + L[r, :V].astype(np.float32)
+            drop = np.ones(V, dtype=bool)
+            drop[np.argpartition(-v, K - 1)[:K]] = False
+            H[r, :V][drop] = 0
+            L[r, :V][drop] = 0
 
     def mlbp_factor_to_var_gemm(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
                                 impl):

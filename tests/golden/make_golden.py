@@ -126,8 +126,8 @@ def import_reference(work):
 
 
 # ----------------------------------------------------------------------------- driving the reference
-def ref_options(session_history=True, history=True):
-    return argparse.Namespace(use_approx_beliefs=False, use_approx_inference=False, report_times=False,
+def ref_options(session_history=True, history=True, approx_inference=False, approx_beliefs=False):
+    return argparse.Namespace(use_approx_beliefs=approx_beliefs, use_approx_inference=approx_inference, report_times=False,
                               reg_param='0.2', reg_param_ua_scale='1.0', user_adapt=False,
                               experience_adapt=False, use_correct_feat=True, history=history,
                               session_history=session_history)
@@ -293,7 +293,9 @@ def main():
             theta_ee = spec['theta_ee']
             theta_ed = spec['theta_ed']
             out = run_graph_case(LBP, train, feeder, model, sent, theta_ee, theta_ed, roots, spec['sweeps'],
-                                 N=spec.get('N', 10), lr=spec.get('lr', 0.1), opts=ref_options())
+                                 N=spec.get('N', 10), lr=spec.get('lr', 0.1),
+                                 opts=ref_options(approx_inference=spec.get('approx_inference', False),
+                                                  approx_beliefs=spec.get('approx_beliefs', False)))
             np.savez_compressed(os.path.join(args.out, 'graph_%s.npz' % name),
                                 spec=json.dumps(spec), sentence=synth.sentence_to_json(sent), roots=np.array(roots),
                                 pmi=model['pmi'], pmi_w1=model['pmi_w1'], ed=model['ed'], ped=model['ped'],

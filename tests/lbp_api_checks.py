@@ -18,7 +18,8 @@ def graph_from_fixture(z):
     spec = json.loads(str(z['spec']))
     t_ee = np.array(z['theta_ee'], dtype=np.float64).reshape(1, 3)
     t_ed = np.array(z['theta_ed'], dtype=np.float64).reshape(1, 6)
-    opts = tc.default_options(session_history=True)
+    opts = tc.default_options(session_history=True, use_approx_inference=spec.get('approx_inference', False),
+                              use_approx_beliefs=spec.get('approx_beliefs', False))
     fg = tc.create_factor_graph(str(z['sentence']), spec.get('lr', 0.1), tc.F_EN_EN_NAMES, tc.F_EN_DE_NAMES, t_ee, t_ed, pw,
                                 en_domain, de2id, en2id, {}, options=opts, N=spec.get('N', 10), de_domain=de_domain)
     return fg, spec

@@ -30,7 +30,8 @@ def test_literal_oracle_matches_reference(path):
     z, model, spec, sent = load_case(path)
     N, lr = spec.get('N', 10), spec.get('lr', 0.1)
     out = orc.run_literal(model, sent, z['theta_ee'], z['theta_ed'], list(z['roots']), spec['sweeps'],
-                          reg=0.2 / N, lr=lr)
+                          reg=0.2 / N, lr=lr, approx_inference=spec.get('approx_inference', False),
+                          approx_beliefs=spec.get('approx_beliefs', False))
     assert int(out['is_loopy']) == int(z['is_loopy'])
     assert list(out['var_ids']) == list(z['var_ids'])
     # graph construction: factor ids / types / variables / gaps / observed dims (train.py:255-297)
@@ -60,7 +61,8 @@ def test_fast_oracle_matches_reference(path):
     z, model, spec, sent = load_case(path)
     N, lr = spec.get('N', 10), spec.get('lr', 0.1)
     tb = orc.Tables(model, z['theta_ee'], z['theta_ed'])
-    out = orc.run_fast(tb, sent, list(z['roots']), spec['sweeps'], reg=0.2 / N, lr=lr)
+    out = orc.run_fast(tb, sent, list(z['roots']), spec['sweeps'], reg=0.2 / N, lr=lr,
+                       approx_inference=spec.get('approx_inference', False), approx_beliefs=spec.get('approx_beliefs', False))
     np.testing.assert_allclose(out['marginals'], z['marginals'], rtol=1e-10)
     np.testing.assert_array_equal(out['top1'], z['top1'])
     np.testing.assert_allclose(out['logp'], float(z['logp']), rtol=1e-11)
