@@ -102,6 +102,10 @@ class FactorGraph():
             self.theta_en_en_names = self.theta_en_en_names[0]
         if isinstance(self.theta_en_de_names, tuple):
             self.theta_en_de_names = self.theta_en_de_names[0]
+        # --user_adapt / --experience_adapt: train.py:224-229, :242-245 build the potentials from the active domain's
+        # theta INSTEAD of theta_en_en / theta_en_de (which still regularise and receive the update); None = no adaptation
+        self.pot_theta_en_en = None
+        self.pot_theta_en_de = None
         # recorder state
         self._roots = []          # [has_loops draw, sweep roots...] as variable ids
         self._sweeps = 0
@@ -204,8 +208,14 @@ class FactorGraph():
         return True
 
     # ------------------------------------------------------------------ lowering + execution
+    def _pot_thetas(self):
+        te = self.theta_en_en if self.pot_theta_en_en is None else self.pot_theta_en_en
+        td = self.theta_en_de if self.pot_theta_en_de is None else self.pot_theta_en_de
+        return np.asarray(te, dtype=np.float64).reshape(-1), np.asarray(td, dtype=np.float64).reshape(-1)
+
     def _theta_key(self):
-        return (np.asarray(self.theta_en_en, dtype=np.float64).tobytes(), np.asarray(self.theta_en_de, dtype=np.float64).tobytes())
+        te, td = self._pot_thetas()
+        return (te.tobytes(), td.tobytes())
 
     def _lower(self):
         """recorded object graph -> engine Corpus (one sentence).  Pairwise factors in attach order (facset order)."""
@@ -278,8 +288,7 @@ class FactorGraph():
             raise KeyError('messages are not initialised: call initialize() first')
         eng = _engine_for(self)
         corpus, vids, pair_factors = self._lower()
-        eng.set_theta(np.asarray(self.theta_en_en, dtype=np.float64).reshape(-1),
-                      np.asarray(self.theta_en_de, dtype=np.float64).reshape(-1))
+        eng.set_theta(*self._pot_thetas())
         roots = corpus.roots_from_positions([list(self._roots)])
         r = eng.run(corpus, roots, self._sweeps, want_grad=True, want_marg=True, want_beliefs=True, want_messages=True,
                     approx_inference=bool(self.use_approx_inference), approx_beliefs=bool(self.use_approx_beliefs))
@@ -581,7 +590,7 @@ class FactorNode():
         from . import LBP as _self  # noqa: F401
         eng = _engine_for(self.graph)
         g = self.graph
-        eng.set_theta(np.asarray(g.theta_en_en, dtype=np.float64).reshape(-1), np.asarray(g.theta_en_de, dtype=np.float64).reshape(-1))
+        eng.set_theta(*g._pot_thetas())
         if len(self.varset) == 1:
             gap1 = FactorGraph._gap_class(self) if self.factor_type == 'en_en' else False
             return eng.unary_message(self.factor_type, self.potential_table.observed_dim, gap1, g._sparse_for(self),

@@ -95,8 +95,15 @@ def create_factor_graph(ti, learning_rate, theta_en_en_names, theta_en_de_names,
     fg.use_approx_inference = options.use_approx_inference
     fg.report_times = options.report_times
     fg.regularization_param = float(options.reg_param) / float(N)               # train.py:158
-    if options.user_adapt or options.experience_adapt:
-        raise NotImplementedError('per-user / per-experience theta (train.py:160-173, :224-245) is a SURVEY.md §8(f) "next" row')
+    if options.user_adapt and options.experience_adapt:
+        raise BaseException("2 domains not supported simultaniously")
+    if options.user_adapt or options.experience_adapt:                            # train.py:160-173
+        d = ti['user_id'] if options.user_adapt else len(ti['past_sentences_seen'])
+        fg.active_domains['en_en', d] = 1
+        fg.active_domains['en_de', d] = 1
+        sys.stderr.write('+' if options.user_adapt else '=')
+        fg.pot_theta_en_en = d2t['en_en', d]                                      # train.py:224-229: REPLACES the base theta
+        fg.pot_theta_en_de = d2t['en_de', d]                                      # train.py:242-245
     # per-sentence dynamic features written into the SHARED phi_en_de planes (train.py:176-215)
     phi_ed = fg.phi_en_de
     if options.use_correct_feat:
@@ -167,10 +174,22 @@ def batch_sgd(training_instance, theta_en_en_names, theta_en_de_names, theta_en_
                              de2id, en2id, d2t, options, N, de_domain)
     fg.initialize(None if roots is None else roots[0])
     fg.treelike_inference(3, None if roots is None else roots[1:])
-    g_en_en, g_en_de = fg.return_gradient()
+    if options is not None and (options.user_adapt or options.experience_adapt):  # train.py:379-390
+        g_en_en, g_en_de = fg.get_unregularized_gradeint()
+        sample_ag = {}
+        r, l = fg.regularization_param, fg.learning_rate
+        scale_reg = float(options.reg_param_ua_scale)
+        for f_type, d in fg.active_domains:
+            g = g_en_en.copy() if f_type == 'en_en' else g_en_de.copy()
+            sample_ag[f_type, d] = apply_regularization(r * scale_reg, g, l, d2t[f_type, d])
+        g_en_en = apply_regularization(r, g_en_en, l, fg.theta_en_en)
+        g_en_de = apply_regularization(r, g_en_de, l, fg.theta_en_de)
+    else:
+        sample_ag = None
+        g_en_en, g_en_de = fg.return_gradient()
     fg.display_timing_info()
     p = fg.get_posterior_probs()
-    return [sent_id, p, g_en_en, g_en_de, None]
+    return [sent_id, p, g_en_en, g_en_de, sample_ag]
 
 
 def batch_predictions(training_instance, theta_en_en_names, theta_en_de_names, theta_en_en, theta_en_de, phi_wrapper, lr,
@@ -191,10 +210,14 @@ def batch_predictions(training_instance, theta_en_en_names, theta_en_de_names, t
     return [p, fgs, factor_dist, fg.get_precision_counts()]
 
 
-def batch_sgd_accumulate(result, f_en_en_theta, f_en_de_theta):
-    """train.py:400-416: in-place theta update; returns the log-probability to add to train_prediction_probs"""
+def batch_sgd_accumulate(result, f_en_en_theta, f_en_de_theta, domain2theta=None):
+    """train.py:400-416: in-place theta update (and, when adapting, of the active domains' thetas, :406-409); returns
+    the log-probability to add to train_prediction_probs"""
     f_en_en_theta += result[2]
     f_en_de_theta += result[3]
+    if result[4] is not None:
+        for key, ag in result[4].items():
+            domain2theta[key] += ag
     sys.stderr.write('*')
     return result[1]
 

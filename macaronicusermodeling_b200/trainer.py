@@ -87,3 +87,42 @@ def batch_sgd_many(engine, sentences, theta_ee, theta_ed, lr, roots_pos, reg_par
     for i, s in enumerate(sentences):
         out.append([s.sent_id, float(lp[i]), lr * (g[i:i + 1, :3] - reg * te), lr * (g[i:i + 1, 3:] - reg * td), None])
     return out
+
+
+class AdaptTrainer(Trainer):
+    """--user_adapt / --experience_adapt (train.py:160-173, :224-245, :379-390, :402-409), batched per domain.
+
+    Each adaptation domain d (a user, or an experience level) owns a theta pair that REPLACES the base theta when that
+    domain's potentials are built, so the sentences of a domain form their own batch with their own table planes.  One
+    step = for every domain of this rank: K2 for theta_d, one engine pass over the domain's sentences, then
+        theta_d    += lr * (sum g - n_d * reg * ua_scale * theta_d)          (stays on this rank: no collective)
+        theta_base += lr * (sum over all domains and ranks of g - n * reg * theta_base)   (the 16 x f64 all-reduce)
+    With one sentence per domain batch this is train.py's update, sentence by sentence."""
+
+    def __init__(self, engine, domains, reg_param=0.2, ua_scale=1.0, N=None, sweeps=3, init_lr=0.1):
+        Trainer.__init__(self, engine, reg_param, N, sweeps, init_lr)
+        self.ua_scale = float(ua_scale)
+        self.domain2theta = {d: (np.zeros(3), np.zeros(6)) for d in domains}
+
+    def step_domains(self, batches, lr):
+        """batches: list of (domain, Corpus, roots).  Returns the reduced 16-vector like Trainer.step."""
+        eng = self.engine
+        total = torch.zeros(16, dtype=torch.float64, device=eng.device)
+        reg = self.reg_param / float(self.N if self.N else sum(c.n_sent for _, c, _ in batches))
+        for d, corpus, roots in batches:
+            te, td = self.domain2theta[d]
+            eng.set_theta(te, td)
+            grad, logp, top1, rank = eng.run_many(corpus, roots, self.sweeps, True, True)
+            g = grad.sum(dim=0)
+            total[:9] += g
+            total[9] += logp.sum()
+            total[10] += (rank == 0).sum(); total[11] += (rank < 26).sum(); total[12] += (rank < 50).sum()
+            total[13] += rank.numel(); total[14] += grad.shape[0]
+            h = g.cpu().numpy()
+            n = corpus.n_sent
+            self.domain2theta[d] = (te + lr * (h[:3] - n * reg * self.ua_scale * te),
+                                    td + lr * (h[3:] - n * reg * self.ua_scale * td))
+        if dist_info()[1] > 1:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        return total

@@ -485,3 +485,31 @@ def sgd_trajectory(model, sentences, roots_per_epoch, epochs=2, reg_param=0.2, i
             logps.append(r['logp'])
             traj.append(np.concatenate([te[0], td[0]]))
     return np.array(traj), np.array(logps)
+
+
+def sgd_trajectory_user_adapt(model, sentences, users_of, roots_per_epoch, users, epochs=2, reg_param=0.2, ua_scale=1.0,
+                              init_lr=0.1, sweeps=3):
+    """train.py --user_adapt: the per-user theta REPLACES the base theta when the potentials are built (:224-229,
+    :242-245); the unregularised gradient then updates BOTH the base theta (regularised with reg) and the user's theta
+    (regularised with reg * reg_param_ua_scale), :379-390 and :402-409."""
+    te, td = np.zeros((1, 3)), np.zeros((1, 6))
+    d2t = {u: (np.zeros((1, 3)), np.zeros((1, 6))) for u in users}
+    reg = float(reg_param) / float(len(sentences))
+    traj = []
+    for epoch in range(epochs):
+        lr = init_lr / float(1.0 + epoch * 0.3)
+        for si, s in enumerate(sentences):
+            u = users_of[si]
+            ue, ud = d2t[u]
+            r = run_fast(Tables(model, ue, ud), s, roots_per_epoch[epoch][si], sweeps)
+            g_ee, g_ed = r['g_ee_unreg'], r['g_ed_unreg']
+            ue_new = ue + lr * (g_ee - reg * ua_scale * ue)
+            ud_new = ud + lr * (g_ed - reg * ua_scale * ud)
+            te = te + lr * (g_ee - reg * te)
+            td = td + lr * (g_ed - reg * td)
+            d2t[u] = (ue_new, ud_new)
+            row = [te[0], td[0]]
+            for uu in users:
+                row += [d2t[uu][0][0], d2t[uu][1][0]]
+            traj.append(np.concatenate(row))
+    return np.array(traj)

@@ -126,9 +126,10 @@ def import_reference(work):
 
 
 # ----------------------------------------------------------------------------- driving the reference
-def ref_options(session_history=True, history=True, approx_inference=False, approx_beliefs=False):
+def ref_options(session_history=True, history=True, approx_inference=False, approx_beliefs=False, user_adapt=False,
+                ua_scale='1.0'):
     return argparse.Namespace(use_approx_beliefs=approx_beliefs, use_approx_inference=approx_inference, report_times=False,
-                              reg_param='0.2', reg_param_ua_scale='1.0', user_adapt=False,
+                              reg_param='0.2', reg_param_ua_scale=ua_scale, user_adapt=user_adapt,
                               experience_adapt=False, use_correct_feat=True, history=history,
                               session_history=session_history)
 
@@ -219,6 +220,44 @@ def run_batch_sgd(LBP, train, feeder, model, sents, theta_ee, theta_ed, roots_pe
         feeder.queue = []
         res.append(r)
     return res
+
+
+def run_sgd_trajectory_user_adapt(LBP, train, feeder, model, sents, roots, epochs, opts, users):
+    """train.py:617-638 with --user_adapt: per-user theta REPLACES the base theta in the potentials (:224-229, :242-245);
+    both get the gradient, with their own regularisation (:379-390, :402-409)."""
+    V, Vd = model['pmi'].shape[0], model['ed'].shape[1]
+    en_domain = ['e%d' % i for i in range(V)]
+    de_domain = ['d%d' % i for i in range(Vd)]
+    en2id = dict((e, i) for i, e in enumerate(en_domain))
+    de2id = dict((d, i) for i, d in enumerate(de_domain))
+    phi_ee, phi_ee_w1, phi_ed = make_phi(model)
+    pw = LBP.PhiWrapper(phi_ee, phi_ee_w1, phi_ed)
+    train.options = opts
+    train.N = len(sents)
+    train.de_domain = de_domain
+    train.f_en_en_theta = np.zeros((1, 3))
+    train.f_en_de_theta = np.zeros((1, 6))
+    train.train_prediction_probs = 0.0
+    d2t = {}
+    for u in users:
+        d2t['en_en', u] = np.zeros((1, 3))
+        d2t['en_de', u] = np.zeros((1, 6))
+    train.domain2theta = d2t
+    traj = []
+    for epoch in range(epochs):
+        lr = 0.1 / float(1.0 + epoch * 0.3)
+        for si, s in enumerate(sents):
+            feeder.queue = list(roots[epoch][si])
+            r = train.batch_sgd(synth.sentence_to_json(s), ['pmi', 'pmi_w1', 'bias'],
+                                ['ed', 'ped', 'correct', 'full_history', 'hit_history', 'bias'],
+                                train.f_en_en_theta, train.f_en_de_theta, pw, lr, en_domain, de2id, en2id, d2t)
+            feeder.queue = []
+            train.batch_sgd_accumulate(r)
+            row = [train.f_en_en_theta[0], train.f_en_de_theta[0]]
+            for u in users:
+                row += [d2t['en_en', u][0], d2t['en_de', u][0]]
+            traj.append(np.concatenate(row))
+    return np.array(traj)
 
 
 def run_sgd_trajectory(LBP, train, feeder, model, sents, roots, epochs, opts):
@@ -315,6 +354,15 @@ def main():
                             roots=np.array(roots), traj=traj, logps=logps,
                             pmi=model['pmi'], pmi_w1=model['pmi_w1'], ed=model['ed'], ped=model['ped'])
         print('sgd trajectory final theta', traj[-1])
+        users = ['ua', 'ub']
+        sents_u = [synth.make_sentence(model, l, seed=400 + i, n_history=3, user_id=users[i % 2]) for i, l in enumerate(layouts)]
+        traj_u = run_sgd_trajectory_user_adapt(LBP, train, feeder, model, sents_u, roots, 2,
+                                               ref_options(user_adapt=True, ua_scale='0.5'), users)
+        np.savez_compressed(os.path.join(args.out, 'sgd_trajectory_user_adapt.npz'),
+                            sentences=np.array([synth.sentence_to_json(s) for s in sents_u]), roots=np.array(roots),
+                            traj=traj_u, users=np.array(users), pmi=model['pmi'], pmi_w1=model['pmi_w1'], ed=model['ed'],
+                            ped=model['ped'])
+        print('user-adapt trajectory final', traj_u[-1][:9])
     finally:
         shutil.rmtree(work, ignore_errors=True)
 

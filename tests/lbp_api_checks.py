@@ -79,3 +79,64 @@ def check_params_roundtrip(tmp_path):
     assert een == tc.F_EN_EN_NAMES and edn == tc.F_EN_DE_NAMES and d2t == {}
     np.testing.assert_allclose(eet, ee, atol=5e-7)
     np.testing.assert_allclose(edt, ed, atol=5e-7)
+
+
+def _adapt_fixture():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'sgd_trajectory_user_adapt.npz'), allow_pickle=False)
+    V, Vd = z['pmi'].shape[0], z['ed'].shape[1]
+    en_domain = ['e%d' % i for i in range(V)]
+    de_domain = ['d%d' % i for i in range(Vd)]
+    return z, en_domain, de_domain, dict((e, i) for i, e in enumerate(en_domain)), dict((d, i) for i, d in enumerate(de_domain))
+
+
+def check_user_adapt_drop_in():
+    """train.py's loop with --user_adapt written against the drop-in API (batch_sgd + batch_sgd_accumulate)"""
+    z, en_domain, de_domain, en2id, de2id = _adapt_fixture()
+    pw = tc.make_phi_wrapper(z['pmi'], z['pmi_w1'], z['ed'], z['ped'])
+    users = [str(u) for u in z['users']]
+    te, td = np.zeros((1, 3)), np.zeros((1, 6))
+    d2t = {}
+    for u in users:
+        d2t['en_en', u], d2t['en_de', u] = np.zeros((1, 3)), np.zeros((1, 6))
+    opts = tc.default_options(session_history=True, user_adapt=True, reg_param_ua_scale='0.5')
+    sents = [str(s) for s in z['sentences']]
+    roots = z['roots'].tolist()
+    traj = []
+    for epoch in range(2):
+        lr = 0.1 / float(1.0 + epoch * 0.3)
+        for si, s in enumerate(sents):
+            res = tc.batch_sgd(s, tc.F_EN_EN_NAMES, tc.F_EN_DE_NAMES, te, td, pw, lr, en_domain, de2id, en2id, d2t,
+                               options=opts, N=len(sents), de_domain=de_domain, roots=roots[epoch][si])
+            tc.batch_sgd_accumulate(res, te, td, d2t)
+            row = [te[0], td[0]]
+            for u in users:
+                row += [d2t['en_en', u][0], d2t['en_de', u][0]]
+            traj.append(np.concatenate(row))
+    np.testing.assert_allclose(np.array(traj), z['traj'], rtol=1e-4, atol=3e-7)
+
+
+def check_adapt_trainer(make_engine):
+    """trainer.AdaptTrainer with one-sentence domain batches == the reference's --user_adapt trajectory"""
+    from macaronicusermodeling_b200 import synth
+    from macaronicusermodeling_b200.engine import Corpus
+    from macaronicusermodeling_b200.trainer import AdaptTrainer
+    z, *_ = _adapt_fixture()
+    model = {'V': z['pmi'].shape[0], 'Vd': z['ed'].shape[1], 'pmi': z['pmi'], 'pmi_w1': z['pmi_w1'], 'ed': z['ed'], 'ped': z['ped']}
+    raw = [json.loads(str(s)) for s in z['sentences']]
+    sents = [synth.sentence_to_arrays(r) for r in raw]
+    users = [str(u) for u in z['users']]
+    roots = z['roots'].tolist()
+    tr = AdaptTrainer(make_engine(model), users, reg_param=0.2, ua_scale=0.5, N=len(sents))
+    traj = []
+    for epoch in range(2):
+        lr = tr.lr(epoch)
+        for si, s in enumerate(sents):
+            c = Corpus([s])
+            red = tr.step_domains([(raw[si]['user_id'], c, c.roots_from_positions([roots[epoch][si]]))], lr)
+            tr.apply(red, lr)
+            row = [tr.theta_ee, tr.theta_ed]
+            for u in users:
+                row += list(tr.domain2theta[u])
+            traj.append(np.concatenate(row))
+    np.testing.assert_allclose(np.array(traj), z['traj'], rtol=1e-4, atol=3e-7)

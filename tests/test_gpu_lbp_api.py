@@ -86,3 +86,11 @@ def test_unsupported_gap_raises_like_reference():
     f.graph = LBP.FactorGraph(tc.F_EN_EN_NAMES, tc.F_EN_DE_NAMES, np.zeros((1, 3)), np.zeros((1, 6)), None, None, None)
     with pytest.raises(BaseException):
         f.get_pot()
+
+
+def test_user_adapt_drop_in_trajectory():
+    lbp_api_checks.check_user_adapt_drop_in()
+
+
+def test_adapt_trainer_trajectory():
+    lbp_api_checks.check_adapt_trainer(lambda m: __import__('macaronicusermodeling_b200.engine', fromlist=['Engine']).Engine(m))

@@ -38,3 +38,11 @@ def test_import_surface():
     from macaronicusermodeling_b200.array_utils import c_array_utils as au
     for name in ('pointwise_multiply', 'normalize', 'dense_dot', 'dense_pointwise_multiply'):
         assert callable(getattr(au, name))
+
+
+def test_user_adapt_drop_in_trajectory():
+    lbp_api_checks.check_user_adapt_drop_in()
+
+
+def test_adapt_trainer_trajectory():
+    lbp_api_checks.check_adapt_trainer(lambda m: __import__('macaronicusermodeling_b200.engine', fromlist=['Engine']).Engine(m, kernels=FakeKernels()))

@@ -104,3 +104,16 @@ def test_message_invariants():
         assert abs(m.sum() - 1.0) < 1e-10
     # bias feature gradient is identically zero up to rounding
     assert abs(out['g_ee_unreg'][0, 2]) < 1e-9 and abs(out['g_ed_unreg'][0, 5]) < 1e-9
+
+
+def test_user_adapt_trajectory_matches_reference():
+    """--user_adapt semantics (train.py:160-173, :224-245, :379-390, :402-409)"""
+    z = np.load(os.path.join(GOLDEN, 'sgd_trajectory_user_adapt.npz'), allow_pickle=False)
+    model = {'V': z['pmi'].shape[0], 'Vd': z['ed'].shape[1], 'pmi': z['pmi'], 'pmi_w1': z['pmi_w1'],
+             'ed': z['ed'], 'ped': z['ped']}
+    raw = [json.loads(str(s)) for s in z['sentences']]
+    sents = [synth.sentence_to_arrays(r) for r in raw]
+    users = [str(u) for u in z['users']]
+    traj = orc.sgd_trajectory_user_adapt(model, sents, [r['user_id'] for r in raw], z['roots'].tolist(), users,
+                                         epochs=2, ua_scale=0.5)
+    np.testing.assert_allclose(traj, z['traj'], rtol=1e-8, atol=1e-12)
