@@ -321,7 +321,7 @@ def ours(a):
                                   'sentences/step); oracle fast variant, float64, all BLAS threads' % (n, t_sent, t_tab, a.sentences)}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 accumulate over fp16 hi+lo split operands; f64 message products', 'data': 'synthetic',
+            'dtype': 'f32 (tensor-core operands split into fp16 hi+lo, fp32 accumulate; fp32 message products, f64 sums)', 'data': 'synthetic',
             'config': {'workload': workload_name(a), 'global_sentences_per_step': a.sentences * world,
                        'parallelism': 'dp%d (sentences sharded, 16 x f64 all-reduce per step)' % world,
                        'l2': 'inputs larger than L2: table planes 2.8 GB, message blocks > 10 GB per micro-batch',

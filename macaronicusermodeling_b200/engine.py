@@ -460,16 +460,14 @@ class Engine(object):
             self.launches += 1
         grad = torch.zeros((corpus.n_sent, 9), dtype=torch.float64, device=dev)
         logp = torch.zeros(corpus.n_sent, dtype=torch.float64, device=dev)
-        if want_grad:
-            zero_off = torch.zeros(corpus.n_sent + 1, dtype=torch.int32, device=dev)
-            k.call('mlbp_gradient_reduce', corpus.n_sent, c('var_off'), c('pair_off') if n_pair else _p(zero_off),
-                   _p(g_unary), _p(pair_stats), _p(pair_l0) if n_pair else _p(zero_off),
-                   _p(pair_l1) if n_pair else _p(zero_off), _p(bd, int(blob[H_PAIR_GAP1])) if n_pair else _p(zero_off),
-                   _p(m.pmi), _p(m.w1), ld, _p(logp_var), _p(grad), _p(logp))
-            self.launches += 1
-        elif want_marg:
-            seg = torch.from_numpy(np.repeat(np.arange(corpus.n_sent), np.diff(corpus.var_off))).to(dev)
-            logp.index_add_(0, seg, logp_var)
+        # per-sentence segmented sums (deterministic, no atomics); without the gradient stage only log-posteriors matter
+        zero_off = torch.zeros(corpus.n_sent + 1, dtype=torch.int32, device=dev)
+        use_pairs = want_grad and n_pair > 0
+        k.call('mlbp_gradient_reduce', corpus.n_sent, c('var_off'), c('pair_off') if use_pairs else _p(zero_off),
+               _p(g_unary), _p(pair_stats), _p(pair_l0) if use_pairs else _p(zero_off),
+               _p(pair_l1) if use_pairs else _p(zero_off), _p(bd, int(blob[H_PAIR_GAP1])) if use_pairs else _p(zero_off),
+               _p(m.pmi), _p(m.w1), ld, _p(logp_var), _p(grad), _p(logp))
+        self.launches += 1
         messages = None
         if want_messages:
             # final pairwise messages, normalised, float64 on the host (API read-back for LBP.FactorGraph.messages):
