@@ -66,3 +66,39 @@ def test_bench_line_small():
     for key in ('metric', 'value', 'unit', 'n_gpus', 'ms_per_step', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
         assert key in line
     assert line['gpu_launches'] > 0 and line['value'] > 0 and line['e2e']['value'] > 0
+
+
+def test_adapt_trainer_batched_domains_vs_oracle():
+    """BASELINE config C4 semantics (users sharded, per-user theta): AdaptTrainer with several sentences per user batch --
+    every user's sentences see that user's theta; the base theta receives the sum over all users"""
+    from macaronicusermodeling_b200.trainer import AdaptTrainer
+    from oracle import lbp_oracle as orc
+    model = synth.make_model(96, 20, seed=8)
+    users = ['u0', 'u1', 'u2']
+    sents = {u: synth.make_corpus(model, 3, k=4, g=1, seed=20 + i) for i, u in enumerate(users)}
+    roots = {u: synth.draw_roots(sents[u], 3, seed=30 + i) for i, u in enumerate(users)}
+    tr = AdaptTrainer(Engine(model), users, reg_param=0.2, ua_scale=0.5, N=9)
+    rng = np.random.default_rng(0)
+    for u in users:
+        tr.domain2theta[u] = (rng.normal(size=3) * 0.3, rng.normal(size=6) * 0.3)
+    before = {u: (tr.domain2theta[u][0].copy(), tr.domain2theta[u][1].copy()) for u in users}
+    batches = []
+    for u in users:
+        c = Corpus(sents[u])
+        batches.append((u, c, c.roots_from_positions(roots[u])))
+    lr = 0.05
+    red = tr.step_domains(batches, lr).cpu().numpy()
+    tot = np.zeros(9)
+    reg = 0.2 / 9
+    for u in users:
+        te, td = before[u]
+        tb = orc.Tables(model, te, td)
+        g = np.zeros(9)
+        for s, r in zip(sents[u], roots[u]):
+            o = orc.run_fast(tb, s, r, 3)
+            g += np.concatenate([o['g_ee_unreg'][0], o['g_ed_unreg'][0]])
+        tot += g
+        np.testing.assert_allclose(tr.domain2theta[u][0], te + lr * (g[:3] - 3 * reg * 0.5 * te), rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(tr.domain2theta[u][1], td + lr * (g[3:] - 3 * reg * 0.5 * td), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(red[:9], tot, rtol=1e-4, atol=2e-6)
+    assert red[14] == 9
