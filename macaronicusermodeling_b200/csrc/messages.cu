@@ -14,7 +14,8 @@
 // T = float when the caller's bound (range_log2) proves that no product can leave the fp32 range, else double.
 // Measured on B200 the fp64 pipe issues only ~3 lanes/clk/SM (profiles/README.md), so the double variant is
 // compute-bound at ~16 % of HBM bandwidth; it is the always-safe fallback.  A bulk-async (cp.async.bulk + mbarrier)
-// shared-memory staging of the inputs was tried in round 1 and was slower than these plain coalesced loads.
+// shared-memory staging of the inputs, and a cluster/DSMEM single-read variant (8 CTAs per group, slices kept in shared
+// memory between the phases), were both tried in round 1 and were slower than these plain coalesced loads.
 #include <stdlib.h>
 
 #include "common.cuh"
