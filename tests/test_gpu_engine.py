@@ -148,3 +148,24 @@ def test_wide_theta_uses_fp64_products():
     assert (6 + 4) * eng.half_range_log2 + eng.unary_range_log2 > 100
     # beliefs are peaked (0.3 .. 0.97) here: the 22-bit operand planes bound the error at ~1e-6 absolute
     common_checks.check_against_oracle(make_engine, model, sents, roots, te, td, belief_atol=1e-5)
+
+
+@pytest.mark.parametrize('sweeps', [1, 2, 7])
+def test_random_layout_sweep_vs_oracle(sweeps):
+    """randomised ragged batch: 1..30 predicted tokens, 0..12 given / revealed tokens, duplicate sparse features,
+    different sweep counts (exercises the NMAX = 4..32 instantiations of K3 and every level pattern of the scheduler)"""
+    rng = np.random.default_rng(100 + sweeps)
+    model = synth.make_model(1500, 150, seed=3 + sweeps, w1_density=0.5)
+    sents = []
+    for i in range(14):
+        k = int(rng.integers(1, 31)) if i else 30
+        g = int(rng.integers(0, 13))
+        lay = ['p'] * k + [('g' if rng.random() < 0.7 else 'r') for _ in range(g)]
+        rng.shuffle(lay)
+        raw = synth.make_sentence(model, ''.join(lay), seed=int(rng.integers(1 << 30)), n_history=int(rng.integers(0, 7)))
+        if raw['past_correct_guesses']:
+            raw['past_correct_guesses'].append(dict(raw['past_correct_guesses'][0]))      # duplicate entry accumulates
+        sents.append(synth.sentence_to_arrays(raw))
+    roots = synth.draw_roots(sents, sweeps, seed=sweeps)
+    common_checks.check_against_oracle(make_engine, model, sents, roots, [1.1, 0.6, -0.4], [1.3, -0.8, 0.7, 0.4, 0.5, -0.1],
+                                       sweeps=sweeps)
