@@ -45,7 +45,7 @@ def parse():
     ap.add_argument('--k', type=int, default=20)
     ap.add_argument('--g', type=int, default=0)
     ap.add_argument('--sweeps', type=int, default=3)
-    ap.add_argument('--workspace-gb', type=float, default=48.0)
+    ap.add_argument('--workspace-gb', type=float, default=96.0)
     ap.add_argument('--cpu-sample', type=int, default=6, help='sentences timed on the CPU for cpu_baseline')
     ap.add_argument('--ref-sample', type=int, default=2, help='sentences per step of the --impl reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')

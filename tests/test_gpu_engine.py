@@ -167,5 +167,6 @@ def test_random_layout_sweep_vs_oracle(sweeps):
             raw['past_correct_guesses'].append(dict(raw['past_correct_guesses'][0]))      # duplicate entry accumulates
         sents.append(synth.sentence_to_arrays(raw))
     roots = synth.draw_roots(sents, sweeps, seed=sweeps)
+    # peaked beliefs of degree-35 variables: the error is ~sqrt(degree) * 2^-22 relative, i.e. up to ~2e-6 absolute
     common_checks.check_against_oracle(make_engine, model, sents, roots, [1.1, 0.6, -0.4], [1.3, -0.8, 0.7, 0.4, 0.5, -0.1],
-                                       sweeps=sweeps)
+                                       sweeps=sweeps, belief_atol=5e-6)
