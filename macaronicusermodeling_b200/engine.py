@@ -185,7 +185,9 @@ class Corpus(object):
             if len(a) == 0:
                 t = torch.zeros(1, dtype=t.dtype)          # keep a valid pointer for empty CSR payloads
             self.h2d_bytes = getattr(self, 'h2d_bytes', 0) + t.numel() * t.element_size()
-            self._dev[key] = t.to(device)
+            if torch.device(device).type == 'cuda':
+                t = t.pin_memory()                        # asynchronous H2D: the host does not wait for queued GPU work
+            self._dev[key] = t.to(device, non_blocking=True)
         return self._dev[key]
 
 
