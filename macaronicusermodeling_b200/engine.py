@@ -349,6 +349,13 @@ class Engine(object):
         [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176)."""
         assert self.theta_ee is not None, 'set_theta first'
         assert not want_grad or self.with_grad_planes
+        if corpus.n_sent == 0:                                    # empty batch: nothing to launch
+            dev = self.device
+            z = lambda *shape, dt=torch.float64: torch.zeros(shape, dtype=dt, device=dev)
+            return Result(z(0, 9), z(0), z(0), z(0, dt=torch.int32), z(0, dt=torch.int32),
+                          z(0, self.ld, dt=torch.float32) if want_beliefs else None,
+                          {'a_rows': 0, 'd_rows': 0, 'levels': 0, 'gemm_rows': 0, 'dead': 0, 'blob_words': 0},
+                          {'v2f': [], 'f2v': []} if want_messages else None)
         lib = _lib.load()
         handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference)
         try:

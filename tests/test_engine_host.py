@@ -73,3 +73,17 @@ def test_inference_only_drops_dead_updates():
     assert inf.stats['dead'] > full.stats['dead']
     np.testing.assert_allclose(inf.beliefs.numpy(), full.beliefs.numpy(), rtol=1e-6)
     np.testing.assert_allclose(inf.logp.numpy(), full.logp.numpy(), rtol=1e-9)
+
+
+def test_empty_and_degenerate_inputs():
+    """empty batch -> empty result; a sentence without predicted tokens has no factor graph (LBP.py:193 asserts)"""
+    model = synth.make_model(64, 16, seed=5)
+    eng = make_engine(model)
+    eng.set_theta([0.1, 0.2, 0.3], [0.1] * 6)
+    r = eng.run(Corpus([]), np.zeros((0, 4), dtype=np.int32), 3)
+    assert r.grad.shape == (0, 9) and r.logp.shape == (0,) and r.top1.shape == (0,)
+    g, lp, t1, rk = eng.run_many(Corpus([]), np.zeros((0, 4), dtype=np.int32), 3)
+    assert g.shape == (0, 9)
+    only_given = synth.sentence_to_arrays(synth.make_sentence(model, 'ggg', seed=1))
+    with pytest.raises(ValueError):
+        Corpus([only_given])
