@@ -250,6 +250,8 @@ def ours(a):
     l0, g0 = eng.launches, eng.gemm_launches
     eng.profile_gemm = True
     eng.gemm_events = []
+    eng.profile_kernels = True
+    eng.kernel_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -259,6 +261,7 @@ def ours(a):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     eng.profile_gemm = False
+    eng.profile_kernels = False
     launches = eng.launches - l0
     gemm_ms = sum(x.elapsed_time(y) for x, y, _ in eng.gemm_events)
     gemm_rows = sum(r for _, _, r in eng.gemm_events)
@@ -310,6 +313,17 @@ def ours(a):
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(n_gemm, 1),
                 'algorithmic_flops_per_launch': flops / max(n_gemm, 1), 'share_of_step': gemm_ms / ms,
                 'note': 'algorithmic flops 2*rows*V*V counted once; the kernel issues 3 fp16 MMA passes (hi*hi, hi*lo, lo*hi)'}
+    # HBM-bound kernels: algorithmic bytes (each input / output row counted once) over the CUDA-event time of every launch
+    peak_gbs = float(peaks.get('hbm_gbs', 6500.0))
+    hbm = {}
+    for name, x, y, nbytes in eng.kernel_events:
+        d = hbm.setdefault(name, {'launches': 0, 'ms': 0.0, 'bytes': 0.0})
+        d['launches'] += 1; d['ms'] += x.elapsed_time(y); d['bytes'] += nbytes
+    for name, d in hbm.items():
+        gbs = d['bytes'] / (d['ms'] / 1e3) / 1e9 if d['ms'] > 0 else 0.0
+        hbm[name] = {'bound': 'hbm', 'launches': d['launches'], 'achieved': gbs, 'peak': peak_gbs, 'unit': 'GB/s',
+                     'frac': gbs / peak_gbs, 'algorithmic_bytes_per_launch': d['bytes'] / max(d['launches'], 1),
+                     'avg_launch_ms': d['ms'] / max(d['launches'], 1), 'share_of_step': d['ms'] / ms}
     cpu_baseline = None
     if not a.no_cpu_baseline:
         n = a.cpu_sample
@@ -326,7 +340,8 @@ def ours(a):
                        'parallelism': 'dp%d (sentences sharded, 16 x f64 all-reduce per step)' % world,
                        'l2': 'inputs larger than L2: table planes 2.8 GB, message blocks > 10 GB per micro-batch',
                        'micro_batches_per_step': len(parts)},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline}
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'hbm_kernels': hbm,
+            'cpu_baseline': cpu_baseline}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -118,7 +118,8 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   group g multiplies U[grp_u[g]] with the factor->variable rows D[in_row[i]], i in [grp_off[g], grp_off[g+1]);
  *   for every i with destinations it emits the leave-one-out product (all inputs except i), renormalised
  *   (sum <= 0 or non-finite -> uniform, LBP.py:650-657; nan_to_num LBP.py:729), scaled by 2^14 and split into
- *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]).  in_row < 0 means "uniform message".
+ *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]).  in_row < 0 means "uniform message": the kernels read the
+ *   constant-one row D[0] in its place (messages are scale-free), so the caller keeps D row 0 filled with 1.0f.
  *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
  *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow). */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
@@ -146,10 +147,13 @@ int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, c
                    const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
                    int32_t *top1, int32_t *rank, float *beliefs, float range_log2, void *stream);
 /* K6a. pairwise factor beliefs contracted with the features (LBP.py:544-569 + :610) in closed form:
- *   stats[f] = { c.u0, c.u1, c.u2 } with c = (A_hi + A_lo)[c_row[f]], u* = D[u*_row[f]] (u2_row < 0 -> 0).  */
-int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *u0_row, const int32_t *u1_row,
-                           const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D, int ldv, int V,
-                           double *stats, void *stream);
+ *   stats[f] = { z.u0, c.u1, c.u2 } with c = (A_hi + A_lo)[c_row[f]], z = (A_hi + A_lo)[z_row[f]],
+ *   u* = D[u*_row[f]] (u2_row < 0 -> 0).  z_row == c_row with u0 = T r, or z_row = the r row with u0 = T'c
+ *   (the plan reuses the D row of the factor's last message update when it read the final message).        */
+int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *z_row, const int32_t *u0_row,
+                           const int32_t *u1_row,
+const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D,
+                           int ldv, int V, double *stats, void *stream);
 /* K6b. FactorGraph.get_unregularized_gradeint (LBP.py:301-320) as a segmented reduction:
  *   grad[s][9] = sum_{v in sentence s} g_unary[v] + sum_{pairwise f in s} (phi[l0,l1,:] - E_f[phi])
  *   sentence s owns variables [sent_var_off[s], sent_var_off[s+1]) and factors [sent_fac_off[s], ..).
@@ -169,7 +173,9 @@ typedef struct mlbp_plan mlbp_plan;
  * the graph (v0 = dim 0, v1 = dim 1 of the potential table), pair_gap1 selects pot_en_en_w1 (LBP.py:456-463).
  * roots: local variable index per graph and draw, [n_graphs, 1 + sweeps] (draw 0 = has_loops, LBP.py:176).
  * flags: bit 0 = plan the gradient stage, bit 1 = plan the marginal stage, bit 2 = do NOT constant-fold updates
- *        that read an initial uniform message (needed by the top-K approximate mode, which masks that message). */
+ *        that read an initial uniform message (needed by the top-K approximate mode, which masks that message),
+ *        bit 3 = give every pairwise belief normaliser Z its own GEMM row instead of reusing the D row of the factor's
+ *        last message update (needed whenever message rows are masked: top-K approximate modes).              */
 int mlbp_plan_compile(int n_graphs, const int32_t *h_var_off, const int32_t *h_pair_off, const int32_t *h_pair_v0,
                       const int32_t *h_pair_v1, const int32_t *h_pair_gap1, const int32_t *h_roots, int sweeps,
                       int flags, mlbp_plan **out);

@@ -22,7 +22,7 @@ _SIGNATURES = {
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppfp',
-    'mlbp_pair_expectations': 'ipppp' + 'pppii' + 'pp',
+    'mlbp_pair_expectations': 'ippppp' + 'pppii' + 'pp',
     'mlbp_gradient_reduce': 'ippppppp' + 'ppi' + 'pppp',
     'mlbp_plan_compile': 'ipppppp' + 'iip',
     'mlbp_plan_sizes': 'pp',

@@ -3,7 +3,7 @@
 // The reference materialises the dense V x V belief  normalize((c r') o T)  per pairwise factor and contracts it
 // with the (V,V,3) feature tensor (LBP.py:544-569, :610): ~7 passes over V^2 doubles per factor.  In closed form
 //  only three inner products per factor are needed,
-//     Z = c . (T r),   N1 = c . ((T o PMI) r),   N2 = c . ((T1 o PMI_w1) r)
+//     Z = c . (T r) = r . (T'c),   N1 = c . ((T o PMI) r),   N2 = c . ((T1 o PMI_w1) r)
 // where the matrix-vector products are rows of the batched GEMM (K4).  This file does the inner products (K6a)
 // and the segmented sum over each sentence's factors and variables (K6b).
 #include "common.cuh"
@@ -12,13 +12,17 @@ namespace mlbp {
 
 // one CTA per pairwise factor
 __global__ void __launch_bounds__(256)
-pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__restrict__ u0_row,
+pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__restrict__ z_row,
+                         const int32_t *__restrict__ u0_row,
                          const int32_t *__restrict__ u1_row, const int32_t *__restrict__ u2_row,
                          const __half *__restrict__ A_hi, const __half *__restrict__ A_lo, const float *__restrict__ D,
                          int ldv, int V, double *__restrict__ stats) {
     __shared__ double red[32];
     const int f = blockIdx.x;
     const __half *ch = A_hi + (size_t)c_row[f] * ldv, *cl = A_lo + (size_t)c_row[f] * ldv;
+    // Z = z . u0: (z, u0) = (c, T r) in general, or (r, T'c) when the plan reuses the D row of a message update
+    const bool zc = z_row[f] == c_row[f];
+    const __half *zh = A_hi + (size_t)z_row[f] * ldv, *zl = A_lo + (size_t)z_row[f] * ldv;
     const float *u0 = D + (size_t)u0_row[f] * ldv, *u1 = D + (size_t)u1_row[f] * ldv;
     const float *u2 = u2_row[f] >= 0 ? D + (size_t)u2_row[f] * ldv : nullptr;
     // fp32 products, short per-thread fp32 partial sums (V / 256 terms), float64 across the block: the fp64 pipe of
@@ -26,7 +30,8 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
     float zf = 0.f, n1f = 0.f, n2f = 0.f;
     for (int e = threadIdx.x; e < V; e += blockDim.x) {
         const float c = __half2float(ch[e]) + __half2float(cl[e]);
-        zf = fmaf(c, __ldg(u0 + e), zf);
+        const float zz = zc ? c : __half2float(zh[e]) + __half2float(zl[e]);
+        zf = fmaf(zz, __ldg(u0 + e), zf);
         n1f = fmaf(c, __ldg(u1 + e), n1f);
         if (u2) n2f = fmaf(c, __ldg(u2 + e), n2f);
     }
@@ -77,14 +82,14 @@ __global__ void gradient_reduce_kernel(int n_sent, const int32_t *__restrict__ s
 
 using namespace mlbp;
 
-extern "C" int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *u0_row,
-                                      const int32_t *u1_row, const int32_t *u2_row, const void *A_hi,
+extern "C" int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *z_row,
+                                      const int32_t *u0_row, const int32_t *u1_row, const int32_t *u2_row, const void *A_hi,
                                       const void *A_lo, const float *D, int ldv, int V, double *stats,
                                       void *stream) {
     if (n_factors == 0) return MLBP_OK;
-    MLBP_CHECK_ARG(n_factors > 0 && c_row && u0_row && u1_row && u2_row && A_hi && A_lo && D && stats,
+    MLBP_CHECK_ARG(n_factors > 0 && c_row && z_row && u0_row && u1_row && u2_row && A_hi && A_lo && D && stats,
                    "pair_expectations: null pointer");
-    pair_expectations_kernel<<<n_factors, 256, 0, as_stream(stream)>>>(c_row, u0_row, u1_row, u2_row,
+    pair_expectations_kernel<<<n_factors, 256, 0, as_stream(stream)>>>(c_row, z_row, u0_row, u1_row, u2_row,
                                                                        (const __half *)A_hi, (const __half *)A_lo, D,
                                                                        ldv, V, stats);
     MLBP_LAUNCH_CHECK();

@@ -18,11 +18,17 @@
 // memory between the phases), were both tried in round 1 and were slower than these plain coalesced loads.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mlbp {
 
 constexpr int K3_THREADS = 256;
+constexpr int K3_WARPS = K3_THREADS / 32;
+constexpr int K3_RESIDENT_SMEM = 100 * 1024;     // per CTA: two CTAs per SM keep loads and stores overlapped
 
 __global__ void fill_uniform_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int ldv, int V,
                                          const int32_t *__restrict__ rows, const uint8_t *__restrict__ keep) {
@@ -37,41 +43,60 @@ __global__ void fill_uniform_rows_kernel(__half *__restrict__ A_hi, __half *__re
     }
 }
 
-template <int NMAX, typename T>
-__global__ void __launch_bounds__(K3_THREADS)
+// One output element of a leave-one-out product -> fp16 hi/lo rows of every GEMM block that reads this message.
+// `first` = element offset of the first destination row (the common case: exactly one reader); further readers are
+// walked by a rolled loop so that the unrolled per-input code around it stays small (instruction-cache resident).
+__device__ __forceinline__ void k3_store(float x, size_t first, int nd, const int32_t *__restrict__ dest, int d0, int ldv,
+                                         int col, __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
+    __half hi, lo;
+    split_f16(x, hi, lo);
+    A_hi[first] = hi;
+    A_lo[first] = lo;
+    if (nd > 1) {
+#pragma unroll 1
+        for (int t = 1; t < nd; ++t) {
+            const size_t o = (size_t)dest[d0 + t] * ldv + col;
+            A_hi[o] = hi;
+            A_lo[o] = lo;
+        }
+    }
+}
+
+template <int NMAX, typename T, int OCC>
+__global__ void __launch_bounds__(K3_THREADS, OCC)
 var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                      const int32_t *__restrict__ dest, const float *__restrict__ U, const float *__restrict__ D,
                      int ldv, int V, __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
     __shared__ const float *s_src[NMAX];
-    __shared__ int s_d0[NMAX], s_d1[NMAX];
-    __shared__ double s_scale[NMAX];
-    __shared__ double red[32];
+    __shared__ int s_d0[NMAX], s_nd[NMAX];
+    __shared__ size_t s_first[NMAX];
+    __shared__ double s_warp[K3_WARPS][NMAX];
+    __shared__ float s_scale[NMAX];
     const int g = blockIdx.x;
     const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
     const float *urow = U + (size_t)grp_u[g] * ldv;
     if (threadIdx.x < NMAX) {
         const int j = threadIdx.x;
-        if (j < n) {
-            const int r = in_row[i0 + j];
-            s_src[j] = r >= 0 ? D + (size_t)r * ldv : nullptr;   // nullptr: uniform message (scale-free -> 1)
-            s_d0[j] = dest_off[i0 + j];
-            s_d1[j] = dest_off[i0 + j + 1];
-        } else {
-            s_src[j] = nullptr; s_d0[j] = 0; s_d1[j] = 0;
-        }
+        // a message still at its uniform initial value, and the unused slots up to NMAX, read the constant-one row
+        // D[0] (messages are scale-free): every load below is unconditional
+        const int r = j < n ? in_row[i0 + j] : -1;
+        s_src[j] = D + (size_t)(r >= 0 ? r : 0) * ldv;
+        const int d0 = j < n ? dest_off[i0 + j] : 0, d1 = j < n ? dest_off[i0 + j + 1] : 0;
+        s_d0[j] = d0;
+        s_nd[j] = d1 - d0;
+        s_first[j] = d1 > d0 ? (size_t)dest[d0] * ldv : 0;
     }
     __syncthreads();
 
+    // ---- phase 1: sums of the leave-one-out products
     T acc[NMAX];
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) acc[j] = (T)0;
-
-    // ---- phase 1: sums of the leave-one-out products
     for (int e = threadIdx.x; e < V; e += K3_THREADS) {
         float d[NMAX];
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? __ldg(s_src[j] + e) : 1.0f;
+        for (int j = 0; j < NMAX; ++j) d[j] = __ldg(s_src[j] + e);
         T pre[NMAX];
         T p = (T)__ldg(urow + e);
 #pragma unroll
@@ -83,22 +108,29 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
             suf *= (T)d[j];
         }
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) {
-        if (j < n && s_d1[j] > s_d0[j]) {                         // block-uniform condition
-            const double s = block_sum((double)acc[j], red);
-            if (threadIdx.x == 0)
-                s_scale[j] = (s > 0.0 && isfinite(s)) ? ldexp(1.0, MLBP_A_SCALE_LOG2) / s : -1.0;  // -1: uniform fallback
-        }
+        const double w = warp_sum((double)acc[j]);
+        if (lane == 0) s_warp[warp][j] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < NMAX) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < K3_WARPS; ++w) t += s_warp[w][threadIdx.x];
+        // sum <= 0 or non-finite -> uniform (Message.renormalize, LBP.py:650-657); flagged by a negative scale
+        s_scale[threadIdx.x] = (t > 0.0 && isfinite(t)) ? (float)(ldexp(1.0, MLBP_A_SCALE_LOG2) / t) : -1.0f;
     }
     __syncthreads();
 
     // ---- phase 2: recompute, normalise, split, scatter to the consuming GEMM blocks
+    // (walking the columns backwards to catch the L2-resident tail of phase 1 was measured 12 % slower)
     const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
     for (int e = threadIdx.x; e < V; e += K3_THREADS) {
         float d[NMAX];
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j) d[j] = (j < n && s_src[j]) ? __ldg(s_src[j] + e) : 1.0f;
+        for (int j = 0; j < NMAX; ++j) d[j] = __ldg(s_src[j] + e);
         T pre[NMAX];
         T p = (T)__ldg(urow + e);
 #pragma unroll
@@ -106,20 +138,187 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
         T suf = (T)1;
 #pragma unroll
         for (int j = NMAX - 1; j >= 0; --j) {
-            if (j < n && s_d1[j] > s_d0[j]) {
-                const double sc = s_scale[j];
-                const float x = sc > 0.0 ? (float)(pre[j] * suf * (T)sc) : uni;
-                __half hi, lo;
-                split_f16(x, hi, lo);
-                for (int t = s_d0[j]; t < s_d1[j]; ++t) {
-                    const size_t o = (size_t)dest[t] * ldv + e;
-                    A_hi[o] = hi;
-                    A_lo[o] = lo;
-                }
+            const int nd = s_nd[j];                               // 0 beyond n and for messages nobody reads
+            if (nd > 0) {
+                const float sc = s_scale[j];
+                const float x = sc > 0.f ? (float)(pre[j] * suf * (T)sc) : uni;
+                k3_store(x, s_first[j] + e, nd, dest, s_d0[j], ldv, e, A_hi, A_lo);
             }
             suf *= (T)d[j];
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3, single-read variant.  The leave-one-out sums need every input element before the first output element can be
+// scaled, so a streaming kernel reads its inputs twice.  Here a thread-block CLUSTER owns one (variable, level) group:
+// CTA q of C keeps the column slice [q*S, (q+1)*S) of all NIN+1 input rows in shared memory (bulk-async copies,
+// cp.async.bulk + one mbarrier: the whole slice is in flight at once), phase 1 sums from shared memory, the C partial
+// sums per output are exchanged through distributed shared memory in fixed rank order (deterministic), and phase 2
+// re-reads shared memory, not HBM.  DRAM traffic = each input once + each output once.  The grid is persistent
+// (resident clusters walk over the groups); the index records of the next group are fetched while the copies of
+// the current one are in flight.  NIN is the exact row count the shared-memory slices are sized for.
+__device__ __forceinline__ uint32_t k3_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NIN>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
+                              const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
+                              const int32_t *__restrict__ dest, const float *__restrict__ U,
+                              const float *__restrict__ D, int ldv, int V, int S, __half *__restrict__ A_hi,
+                              __half *__restrict__ A_lo) {
+    extern __shared__ __align__(128) float s_rows[];          // [1 + NIN][S]: row 0 = U slice, row 1 + j = input j
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ const float *s_src[2][NIN + 1];                // [buffer][0] = U row, [1 + j] = input j (nullptr: ones)
+    __shared__ int s_d0[2][NIN], s_nd[2][NIN];
+    __shared__ size_t s_first[2][NIN];
+    __shared__ double s_warp[K3_WARPS][NIN];
+    __shared__ double s_part[NIN];
+    __shared__ double s_gather[8][NIN];
+    __shared__ float s_scale[NIN];
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned C = cl.num_blocks(), q = cl.block_rank();
+    const int n_clusters = gridDim.x / C;
+    const int col0 = (int)q * S;
+    const int ncol = max(0, min(S, V - col0));                 // columns this CTA owns (S is a multiple of 4)
+    const uint32_t bytes = (uint32_t)((ncol + 3) & ~3) * 4u;   // rows are padded to ld >= roundup(V, 64): in bounds
+    const uint32_t bar = k3_smem_u32(&s_bar);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
+
+    // index records of group g -> shared-memory buffer b (threads 0..NIN; thread 0 also owns the U row)
+    auto fetch = [&](int g, int b) {
+        if (threadIdx.x <= NIN) {
+            const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
+            if (threadIdx.x == 0) {
+                s_src[b][0] = U + (size_t)grp_u[g] * ldv + col0;
+            } else {
+                const int j = threadIdx.x - 1;
+                const int r = j < n ? in_row[i0 + j] : -1;
+                s_src[b][1 + j] = r >= 0 ? D + (size_t)r * ldv + col0 : nullptr;
+                const int d0 = j < n ? dest_off[i0 + j] : 0, d1 = j < n ? dest_off[i0 + j + 1] : 0;
+                s_d0[b][j] = d0;
+                s_nd[b][j] = d1 - d0;
+                s_first[b][j] = d1 > d0 ? (size_t)dest[d0] * ldv + col0 : 0;
+            }
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int g = blockIdx.x / C, b = 0;
+    if (g < n_groups) fetch(g, 0);
+    __syncthreads();
+    uint32_t parity = 0;
+    bool first = true;
+    for (; g < n_groups; g += n_clusters, b ^= 1) {
+        if (ncol > 0) {
+            if (threadIdx.x == 0) {
+                int present = 0;
+                for (int j = 0; j <= NIN; ++j) present += s_src[b][j] ? 1 : 0;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * present) : "memory");
+            }
+            if (threadIdx.x <= NIN) {
+                const float *src = s_src[b][threadIdx.x];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses before the async writes
+                if (src)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(k3_smem_u32(s_rows + (size_t)threadIdx.x * S)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+            }
+        }
+        if (g + n_clusters < n_groups) fetch(g + n_clusters, b ^ 1);          // overlaps the copies in flight
+        if (ncol > 0) {
+            // inputs still at their uniform initial value, and unused slots, multiply by one
+#pragma unroll 1
+            for (int j = 1; j <= NIN; ++j)
+                if (!s_src[b][j])
+                    for (int e = threadIdx.x; e < ncol; e += K3_THREADS) s_rows[(size_t)j * S + e] = 1.0f;
+            uint32_t ok = 0;
+            const unsigned long long t0 = clock64();
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                if (!ok && clock64() - t0 > 4000000000ull) __trap();   // a lost copy traps (launch error) instead of hanging the GPU
+            }
+            parity ^= 1u;
+        }
+        __syncthreads();
+
+        // ---- phase 1: partial sums of the leave-one-out products over this CTA's columns
+        float acc[NIN];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) acc[j] = 0.f;
+        for (int e = threadIdx.x; e < ncol; e += K3_THREADS) {
+            const float *col = s_rows + e;
+            float d[NIN];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * S];
+            float pre[NIN];
+            float p = col[0];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) { pre[j] = p; p *= d[j]; }
+            float suf = 1.f;
+#pragma unroll
+            for (int j = NIN - 1; j >= 0; --j) {
+                acc[j] += pre[j] * suf;
+                suf *= d[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) {
+            const double w = warp_sum((double)acc[j]);
+            if (lane == 0) s_warp[warp][j] = w;
+        }
+        __syncthreads();
+        if (!first) cl.barrier_wait();                             // peers have read this CTA's previous partial sums
+        if (threadIdx.x < NIN) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < K3_WARPS; ++w) t += s_warp[w][threadIdx.x];
+            s_part[threadIdx.x] = t;
+        }
+        cl.sync();
+        for (int i = threadIdx.x; i < NIN * (int)C; i += K3_THREADS) {
+            const int r = i / NIN, j = i - r * NIN;
+            s_gather[r][j] = *cl.map_shared_rank(&s_part[j], r);
+        }
+        __syncthreads();
+        cl.barrier_arrive();                                       // done with the peers' shared memory
+        if (threadIdx.x < NIN) {
+            double t = 0.0;
+            for (unsigned r = 0; r < C; ++r) t += s_gather[r][threadIdx.x];      // fixed order: deterministic
+            s_scale[threadIdx.x] = (t > 0.0 && isfinite(t)) ? (float)(ldexp(1.0, MLBP_A_SCALE_LOG2) / t) : -1.0f;
+        }
+        __syncthreads();
+
+        // ---- phase 2: recompute from shared memory, normalise, split, scatter to the consuming GEMM blocks
+        for (int e = threadIdx.x; e < ncol; e += K3_THREADS) {
+            const float *col = s_rows + e;
+            float d[NIN];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * S];
+            float pre[NIN];
+            float p = col[0];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) { pre[j] = p; p *= d[j]; }
+            float suf = 1.f;
+#pragma unroll
+            for (int j = NIN - 1; j >= 0; --j) {
+                const int nd = s_nd[b][j];                         // 0 beyond n and for messages nobody reads
+                if (nd > 0) {
+                    const float sc = s_scale[j];
+                    const float x = sc > 0.f ? pre[j] * suf * sc : uni;
+                    k3_store(x, s_first[b][j] + e, nd, dest, s_d0[b][j], ldv, col0 + e, A_hi, A_lo);
+                }
+                suf *= d[j];
+            }
+        }
+        __syncthreads();                                           // shared memory is reused by the next group
+        first = false;
+    }
+    if (!first) cl.barrier_wait();                                 // no CTA leaves while a peer may still read it
 }
 
 // Top-K masking of message rows: the reference's approximate paths (use_approx_inference / use_approx_beliefs,
@@ -241,6 +440,46 @@ extern "C" int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, co
     return MLBP_OK;
 }
 
+// resident (single-read) launch: cluster of C CTAs per group, (NIN + 1) * S floats of dynamic shared memory per CTA
+template <int NIN>
+static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, const int32_t *grp_u,
+                                   const int32_t *grp_off, const int32_t *in_row, const int32_t *dest_off,
+                                   const int32_t *dest, const float *U, const float *D, int ldv, int V, __half *A_hi,
+                                   __half *A_lo) {
+    static bool configured = false;
+    auto kern = var_to_factor_resident_kernel<NIN>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_RESIDENT_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const size_t smem = (size_t)(NIN + 1) * S * sizeof(float);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C * 148u * 2u);
+    cfg.blockDim = dim3(K3_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent grid: as many clusters as the device keeps resident for this shared-memory size (queried once per C)
+    static int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!resident[C]) {
+        int nc = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        resident[C] = nc > 0 ? nc : 1;
+        if (getenv("MLBP_DEBUG")) fprintf(stderr, "mlbp K3 resident<%d>: cluster %d, %zu B smem, %d resident clusters\n", NIN, C, smem, nc);
+    }
+    const int n_clusters = n_groups < resident[C] ? n_groups : resident[C];
+    cfg.gridDim = dim3((unsigned)n_clusters * (unsigned)C);
+    return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, S, A_hi, A_lo);
+}
+
+constexpr int K3_RESIDENT_MAX_IN = 24;
+
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                                   const int32_t *dest_off, const int32_t *dest, const float *U, const float *D,
                                   int ldv, int V, void *A_hi, void *A_lo, int max_in, float range_log2, void *stream) {
@@ -249,26 +488,62 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
                    "var_to_factor: null pointer");
     const bool fp32_ok = range_log2 >= 0.f && range_log2 < 100.f;   // products provably stay inside 2^+-100
     MLBP_CHECK_ARG(V > 0 && ldv >= V && (ldv % 4) == 0, "var_to_factor: bad V/ldv");
+    MLBP_CHECK_ARG(max_in >= 0, "var_to_factor: bad max_in");
+    if (max_in > 48) {
+        set_error("var_to_factor: a variable with %d pairwise factors exceeds the supported 48", max_in);
+        return MLBP_ERR_UNSUPPORTED;
+    }
     cudaStream_t st = as_stream(stream);
+    // MLBP_K3_IMPL (probing): unset / 1 = streaming kernel, 2 = resident single-read kernel whenever the slices fit
+    const char *env_impl = getenv("MLBP_K3_IMPL");
+    const int forced = env_impl ? atoi(env_impl) : 1;
+    const int nin = max_in < 1 ? 1 : max_in;
+    int C = 0, S = 0;
+    if (fp32_ok && forced != 1 && nin <= K3_RESIDENT_MAX_IN && (((uintptr_t)U | (uintptr_t)D) & 15) == 0)
+        for (int c = 1; c <= 8 && !C; c *= 2) {
+            const int s4 = (((V + c - 1) / c) + 3) & ~3, s32 = (s4 + 31) & ~31;    // 128-byte slices when they still fit
+            if ((size_t)(nin + 1) * s32 * sizeof(float) <= (size_t)K3_RESIDENT_SMEM) { C = c; S = s32; }
+            else if ((size_t)(nin + 1) * s4 * sizeof(float) <= (size_t)K3_RESIDENT_SMEM) { C = c; S = s4; }
+        }
+    if (C) {
+        if ((int64_t)n_groups * C > 0x7fffffffll) { set_error("var_to_factor: too many groups"); return MLBP_ERR_INVALID; }
+#define MLBP_K3_RES(N)                                                                                             \
+        case N:                                                                                                    \
+            MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, \
+                                         (__half *)A_hi, (__half *)A_lo));                                         \
+            break;
+        switch (nin) {
+            MLBP_K3_RES(1) MLBP_K3_RES(2) MLBP_K3_RES(3) MLBP_K3_RES(4) MLBP_K3_RES(5) MLBP_K3_RES(6) MLBP_K3_RES(7)
+            MLBP_K3_RES(8) MLBP_K3_RES(9) MLBP_K3_RES(10) MLBP_K3_RES(11) MLBP_K3_RES(12) MLBP_K3_RES(13) MLBP_K3_RES(14)
+            MLBP_K3_RES(15) MLBP_K3_RES(16) MLBP_K3_RES(17) MLBP_K3_RES(18) MLBP_K3_RES(19) MLBP_K3_RES(20)
+            MLBP_K3_RES(21) MLBP_K3_RES(22) MLBP_K3_RES(23) MLBP_K3_RES(24)
+        }
+#undef MLBP_K3_RES
+        MLBP_LAUNCH_CHECK();
+        return MLBP_OK;
+    }
+    const char *env_occ = getenv("MLBP_K3_OCC");                     // probing only: 2 = do not cap registers for 3 CTAs per SM
+    const bool occ3 = !(env_occ && atoi(env_occ) == 2);
 #define MLBP_K3_LAUNCH(N)                                                                                        \
     do {                                                                                                         \
-        if (fp32_ok)                                                                                             \
-            var_to_factor_kernel<N, float><<<n_groups, K3_THREADS, 0, st>>>(                                     \
+        if (fp32_ok && occ3 && N <= 20)                                                                          \
+            var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
+                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+        else if (fp32_ok)                                                                                        \
+            var_to_factor_kernel<N, float, 1><<<n_groups, K3_THREADS, 0, st>>>(                                  \
                 grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else                                                                                                     \
-            var_to_factor_kernel<N, double><<<n_groups, K3_THREADS, 0, st>>>(                                    \
+            var_to_factor_kernel<N, double, 1><<<n_groups, K3_THREADS, 0, st>>>(                                 \
                 grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);
+    else if (max_in <= 12) MLBP_K3_LAUNCH(12);
     else if (max_in <= 16) MLBP_K3_LAUNCH(16);
+    else if (max_in <= 20) MLBP_K3_LAUNCH(20);
     else if (max_in <= 24) MLBP_K3_LAUNCH(24);
     else if (max_in <= 32) MLBP_K3_LAUNCH(32);
-    else if (max_in <= 48) MLBP_K3_LAUNCH(48);
-    else {
-        set_error("var_to_factor: a variable with %d pairwise factors exceeds the supported 48", max_in);
-        return MLBP_ERR_UNSUPPORTED;
-    }
+    else MLBP_K3_LAUNCH(48);
 #undef MLBP_K3_LAUNCH
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;

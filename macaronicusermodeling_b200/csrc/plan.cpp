@@ -20,6 +20,9 @@
 //   - messages still at their initial uniform value are filled by mlbp_fill_uniform_rows / read as "row -1";
 //   - a factor->variable update that READS an initial uniform message is constant-folded: its result is the
 //     table's row / column sums (D rows 1..4, written once per theta), so sweep 1's first level costs no GEMM.
+//   - gradient stage: the normaliser Z = c'Tr of a pairwise belief (LBP.py:566-569) needs the row T r (or T'c) of
+//     the FINAL messages c, r.  The last factor->variable update of the factor usually read exactly that final
+//     version (its producer ran earlier in the same sweep), so its D row is reused and no extra GEMM row is spent.
 //
 // Blob layout (int32 words), header first:
 //   [H_*] fixed header, then per-level records (LEV_WORDS each), then the index arrays they point to.
@@ -43,7 +46,7 @@ namespace {
 enum {
     H_NLEVELS = 0, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
     H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
-    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_WORDS = 32
+    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_WORDS = 32
 };
 enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_WORDS = 8 };
 enum { GEMM_TABLE = 0, GEMM_A0, GEMM_D0, GEMM_N, GEMM_WORDS = 4 };
@@ -69,6 +72,7 @@ struct Graph {
     std::vector<int32_t> in_edge;               // parallel to inputs: edge id (f * 2 + side) of the message read
     std::vector<int32_t> fin_v2f, fin_f2v;      // producer op of the final version per edge (f * 2 + side)
     std::vector<int32_t> slot;                  // edge (f * 2 + side) -> position of f in facset[variable of that side]
+    std::vector<int8_t> zmode;                  // gradient stage, per factor: where Z = c'Tr comes from (see phase A)
     int n_levels = 0;
 };
 
@@ -205,7 +209,7 @@ void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
 // per-thread output of the emit phase for a contiguous range of graphs
 struct ChunkOut {
     std::vector<std::vector<int32_t>> grp_u, grp_off, in_row, dest_off, dest;   // [level]
-    std::vector<int32_t> init_rows, pair_c, pair_r, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
+    std::vector<int32_t> init_rows, pair_c, pair_r, pair_z, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
 };
 
 template <class F>
@@ -223,7 +227,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         mlbp::set_error("plan_compile: bad argument");
         return MLBP_ERR_INVALID;
     }
-    const bool want_grad = flags & 1, want_marg = flags & 2;
+    const bool want_grad = flags & 1, want_marg = flags & 2, reuse_z = !(flags & 8);
     const bool prof = std::getenv("MLBP_PLAN_PROFILE") != nullptr;
     auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_a = tnow();
@@ -274,6 +278,16 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
                 for (int k = o.in0; k < o.in1; ++k)
                     if (g.inputs[k] >= 0) needed[g.inputs[k]] = 1;
             }
+            // Z source per factor: 1 = D row of the last f->v0 update (= T r, dot with c), 2 = D row of the last
+            // f->v1 update (= T'c, dot with r), 0 = a GEMM row of its own
+            g.zmode.assign(g.np, 0);
+            if (want_grad && reuse_z)
+                for (int f = 0; f < g.np; ++f)
+                    for (int side = 0; side < 2 && !g.zmode[f]; ++side) {
+                        const int o = g.fin_f2v[2 * f + side], src = g.fin_v2f[2 * f + (1 - side)];
+                        if (o >= 0 && src >= 0 && g.ops[o].live && !g.ops[o].folded && g.inputs[g.ops[o].in0] == src)
+                            g.zmode[f] = (int8_t)(1 + side);
+                    }
             c_levels[c] = std::max(c_levels[c], g.n_levels);
             for (int v = 0; v < g.nv; ++v) c_maxin[c] = std::max(c_maxin[c], (int)g.facset[v].size());
         }
@@ -293,17 +307,21 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     const size_t LT = (size_t)(n_levels + 1) * 4;
     std::vector<int64_t> cnt(LT, 0);
     std::vector<int64_t> gbase((size_t)n_graphs * LT);            // first row index (inside the block) of each graph
-    std::vector<int64_t> g_i0(n_graphs), g_i1(n_graphs), g_ip(n_graphs);
-    int64_t n_pair = 0, n_gap0 = 0, n_gap1 = 0;
+    // gradient-stage r rows per gap class: first the factors that need a Z GEMM row (z), then the others (n)
+    std::vector<int64_t> g_iz[2], g_in[2], g_ip(n_graphs);
+    for (int k = 0; k < 2; ++k) { g_iz[k].resize(n_graphs); g_in[k].resize(n_graphs); }
+    int64_t n_pair = 0, n_z[2] = {0, 0}, n_n[2] = {0, 0};
     for (int gi = 0; gi < n_graphs; ++gi) {
         Graph &g = G[gi];
         int64_t *gb = &gbase[(size_t)gi * LT];
         for (size_t i = 0; i < LT; ++i) gb[i] = cnt[i];
         for (Op &o : g.ops)
             if (o.live && o.kind == 1 && !o.folded) o.row = (int32_t)(cnt[(size_t)o.level * 4 + o.table]++ - gb[(size_t)o.level * 4 + o.table]);
-        g_i0[gi] = n_gap0; g_i1[gi] = n_gap1; g_ip[gi] = n_pair;
-        if (want_grad) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.gap1[f] ? n_gap1 : n_gap0)++; }
+        for (int k = 0; k < 2; ++k) { g_iz[k][gi] = n_z[k]; g_in[k][gi] = n_n[k]; }
+        g_ip[gi] = n_pair;
+        if (want_grad) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.zmode[f] ? n_n : n_z)[g.gap1[f]]++; }
     }
+    const int64_t n_gap0 = n_z[0] + n_n[0], n_gap1 = n_z[1] + n_n[1];
     std::vector<int64_t> base(LT, 0);
     int64_t a_rows = 0;
     for (int L = 1; L <= n_levels; ++L)
@@ -313,7 +331,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     const int64_t a_r0 = a_rows, a_r1 = a_r0 + n_gap0, a_c = a_r1 + n_gap1;
     a_rows = a_c + n_pair;
     int64_t d_rows = MLBP_D_CONST_ROWS + n_msg_rows;
-    const int64_t d_u0_0 = d_rows, d_u1_0 = d_u0_0 + n_gap0, d_u0_1 = d_u1_0 + n_gap0, d_u1_1 = d_u0_1 + n_gap1,
+    const int64_t d_u0_0 = d_rows, d_u1_0 = d_u0_0 + n_z[0], d_u0_1 = d_u1_0 + n_gap0, d_u1_1 = d_u0_1 + n_z[1],
                   d_u2_1 = d_u1_1 + n_gap1;
     if (want_grad) d_rows = d_u2_1 + n_gap1;
     if (a_rows > 0x7fffff00ll || d_rows > 0x7fffff00ll) { mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
@@ -335,18 +353,23 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
             // destinations of every variable->factor version = A rows of the GEMM rows that read it (counting sort)
             const size_t nops = g.ops.size();
             dcount.assign(nops + 1, 0);
+            // A row of the gradient-stage copy of r for factor f; advances the per-class counters
+            auto r_row_of = [&](const Graph &gg, int f, int64_t *iz, int64_t *in) -> int64_t {
+                const int k = gg.gap1[f];
+                const int64_t blk = k ? a_r1 : a_r0;
+                return gg.zmode[f] ? blk + n_z[k] + in[k]++ : blk + iz[k]++;
+            };
             auto each_consumer = [&](auto &&fn) {
                 for (const Op &o : g.ops) {
                     if (!o.live || o.kind != 1 || o.folded) continue;
                     fn(g.inputs[o.in0], o.row);
                 }
                 if (want_grad) {
-                    int64_t i0 = g_i0[gi], i1 = g_i1[gi], ip = g_ip[gi];
+                    int64_t iz[2] = {g_iz[0][gi], g_iz[1][gi]}, in[2] = {g_in[0][gi], g_in[1][gi]}, ip = g_ip[gi];
                     for (int f = 0; f < g.np; ++f) {
-                        const int64_t rrow = g.gap1[f] ? a_r1 + i1 : a_r0 + i0;
-                        fn(g.fin_v2f[2 * f + 1], (int32_t)rrow);
+                        fn(g.fin_v2f[2 * f + 1], (int32_t)r_row_of(g, f, iz, in));
                         fn(g.fin_v2f[2 * f + 0], (int32_t)(a_c + ip));
-                        (g.gap1[f] ? i1 : i0)++; ++ip;
+                        ++ip;
                     }
                 }
             };
@@ -357,17 +380,22 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
             std::fill(dcount.begin(), dcount.end(), 0);
             each_consumer([&](int prod, int32_t row) { if (prod >= 0) dflat[dstart[prod] + dcount[prod]++] = row; });
             if (want_grad) {
-                int64_t i0 = g_i0[gi], i1 = g_i1[gi], ip = g_ip[gi];
+                int64_t iz[2] = {g_iz[0][gi], g_iz[1][gi]}, in[2] = {g_in[0][gi], g_in[1][gi]}, ip = g_ip[gi];
                 for (int f = 0; f < g.np; ++f) {
+                    const int k = g.gap1[f];
+                    const int64_t rrow = r_row_of(g, f, iz, in), ri = rrow - (k ? a_r1 : a_r0);   // index inside the class block
                     co.pair_c.push_back((int32_t)(a_c + ip));
-                    co.pair_r.push_back((int32_t)(g.gap1[f] ? a_r1 + i1 : a_r0 + i0));
-                    if (g.gap1[f]) {
-                        co.pair_u0.push_back((int32_t)(d_u0_1 + i1)); co.pair_u1.push_back((int32_t)(d_u1_1 + i1));
-                        co.pair_u2.push_back((int32_t)(d_u2_1 + i1)); ++i1;
+                    co.pair_r.push_back((int32_t)rrow);
+                    if (g.zmode[f]) {                            // Z from the D row of a message update
+                        const int side = g.zmode[f] - 1;
+                        co.pair_u0.push_back(MLBP_D_CONST_ROWS + g.ops[g.fin_f2v[2 * f + side]].row);
+                        co.pair_z.push_back((int32_t)(side == 0 ? a_c + ip : rrow));
                     } else {
-                        co.pair_u0.push_back((int32_t)(d_u0_0 + i0)); co.pair_u1.push_back((int32_t)(d_u1_0 + i0));
-                        co.pair_u2.push_back(-1); ++i0;
+                        co.pair_u0.push_back((int32_t)((k ? d_u0_1 : d_u0_0) + ri));
+                        co.pair_z.push_back((int32_t)(a_c + ip));
                     }
+                    co.pair_u1.push_back((int32_t)((k ? d_u1_1 : d_u1_0) + ri));
+                    co.pair_u2.push_back(k ? (int32_t)(d_u2_1 + ri) : -1);
                     co.pair_g1.push_back(g.gap1[f]);
                     co.pair_gv0.push_back(var_off[gi] + g.v0[f]);
                     co.pair_gv1.push_back(var_off[gi] + g.v1[f]);
@@ -473,6 +501,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     B[H_NPAIR] = (int32_t)n_pair;
     B[H_PAIR_C] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_c; }, false);
     B[H_PAIR_R] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_r; }, false);
+    B[H_PAIR_Z] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_z; }, false);
     B[H_PAIR_U0] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u0; }, false);
     B[H_PAIR_U1] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u1; }, false);
     B[H_PAIR_U2] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_u2; }, false);
@@ -485,8 +514,8 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
             if (n > 0) { gg.push_back(table); gg.push_back((int32_t)a0); gg.push_back((int32_t)d0); gg.push_back((int32_t)n); }
         };
         if (want_grad) {
-            call(MLBP_TABLE_T, a_r0, d_u0_0, n_gap0);  call(MLBP_TABLE_G, a_r0, d_u1_0, n_gap0);
-            call(MLBP_TABLE_T1, a_r1, d_u0_1, n_gap1); call(MLBP_TABLE_G1, a_r1, d_u1_1, n_gap1);
+            call(MLBP_TABLE_T, a_r0, d_u0_0, n_z[0]);  call(MLBP_TABLE_G, a_r0, d_u1_0, n_gap0);
+            call(MLBP_TABLE_T1, a_r1, d_u0_1, n_z[1]); call(MLBP_TABLE_G1, a_r1, d_u1_1, n_gap1);
             call(MLBP_TABLE_G1W, a_r1, d_u2_1, n_gap1);
         }
         B[H_NGRAD_GEMM] = (int32_t)(gg.size() / GEMM_WORDS);
@@ -500,7 +529,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         B[H_MARG_OFF] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.moff; }, true);
         B[H_MARG_IN] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.min_; }, false);
     }
-    int64_t gemm_rows = n_msg_rows + (want_grad ? 2 * n_gap0 + 3 * n_gap1 : 0);
+    int64_t gemm_rows = n_msg_rows + (want_grad ? n_z[0] + n_gap0 + n_z[1] + 2 * n_gap1 : 0);
     std::memset(P->sizes, 0, sizeof(P->sizes));
     P->sizes[MLBP_PLAN_BLOB_WORDS] = (int64_t)B.size();
     P->sizes[MLBP_PLAN_A_ROWS] = a_rows;

@@ -23,7 +23,7 @@ from . import _lib
 # plan blob header (csrc/plan.cpp)
 (H_NLEVELS, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
  H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
- H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R) = range(24)
+ H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z) = range(25)
 H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 8, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
  PLAN_N_DEAD) = range(9)
@@ -230,6 +230,19 @@ class Engine(object):
         self.blob_bytes = 0         # schedule bytes uploaded (H2D) so far
         self.profile_gemm = False   # record a CUDA-event pair around every K4 launch (bench.py roofline)
         self.gemm_events = []
+        self.profile_kernels = False  # same for the HBM-bound kernels: (name, event, event, algorithmic bytes)
+        self.kernel_events = []
+
+    def _timed(self, name, nbytes, fn):
+        """launch through fn(); with profile_kernels the launch is bracketed by CUDA events on the launching stream and
+        recorded with its ALGORITHMIC bytes (each input and output counted once; `nbytes` may be a callable)"""
+        if not self.profile_kernels:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.kernel_events.append((name, e0, e1, float(nbytes() if callable(nbytes) else nbytes)))
 
     # ------------------------------------------------------------------ theta -> tables (K2)
     def set_theta(self, theta_ee, theta_ed, with_grad=True):
@@ -256,8 +269,10 @@ class Engine(object):
             self.planes = torch.zeros((n_planes, self.V, self.ld), dtype=torch.float16, device=self.device)
         self.with_grad_planes = with_grad
         m = self.model
-        self.k.call('mlbp_build_pairwise_tables', _p(m.pmi), _p(m.w1), self.V, self.ld, _hp(te), self.scale_exp,
-                    _p(self.planes), self.V * self.ld, self.ld, _p(self.colsums), 1 if with_grad else 0)
+        self._timed('K2 build_pairwise_tables', 2.0 * self.V * self.V * 4 + n_planes * self.V * self.V * 2.0,
+                    lambda: self.k.call('mlbp_build_pairwise_tables', _p(m.pmi), _p(m.w1), self.V, self.ld, _hp(te),
+                                        self.scale_exp, _p(self.planes), self.V * self.ld, self.ld, _p(self.colsums),
+                                        1 if with_grad else 0))
         self.k.call('mlbp_build_unary_tables', _p(m.edT), _p(m.pedT), self.V, self.Vd, self.ld, _hp(td), _p(self.edstats))
         self.launches += 2
         # constant rows by table id (T: row sums, Tt: column sums, T1, T1t), mean-one scaled (messages are scale-free)
@@ -329,13 +344,13 @@ class Engine(object):
             self._blob_dev = torch.empty(n, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------ one microbatch
-    def compile(self, corpus, roots, sweeps, want_grad, want_marg, fold=True):
+    def compile(self, corpus, roots, sweeps, want_grad, want_marg, fold=True, reuse_z=True):
         roots = np.ascontiguousarray(roots, dtype=np.int32)
         assert roots.shape[0] == corpus.n_sent and roots.shape[1] >= 1 + sweeps, roots.shape
         roots = np.ascontiguousarray(roots[:, :1 + sweeps])
         handle = ctypes.c_void_p()
         lib = _lib.load()
-        flags = (1 if want_grad else 0) | (2 if want_marg else 0) | (0 if fold else 4)
+        flags = (1 if want_grad else 0) | (2 if want_marg else 0) | (0 if fold else 4) | (0 if reuse_z else 8)
         _lib.check(lib.mlbp_plan_compile(corpus.n_sent, _hp(corpus.var_off), _hp(corpus.pair_off), _hp(corpus.pair_v0),
                                          _hp(corpus.pair_v1), _hp(corpus.pair_gap1), _hp(roots), sweeps, flags,
                                          ctypes.byref(handle)))
@@ -357,7 +372,9 @@ class Engine(object):
                           {'a_rows': 0, 'd_rows': 0, 'levels': 0, 'gemm_rows': 0, 'dead': 0, 'blob_words': 0},
                           {'v2f': [], 'f2v': []} if want_messages else None)
         lib = _lib.load()
-        handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference)
+        # masked (top-K) message rows: the pairwise normaliser Z must come from its own GEMM row of the final messages
+        handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference,
+                                     reuse_z=not (approx_inference or approx_beliefs))
         try:
             words = int(sizes[PLAN_BLOB_WORDS])
             nv = corpus.n_vars
@@ -380,15 +397,18 @@ class Engine(object):
         td = self.theta_ed
         c = lambda name: _p(corpus.dev(name, dev))
 
+        D[0].fill_(1.0)                                           # the constant-one row: messages still uniform read it
         D[1:D_CONST_ROWS, :V].copy_(self.const_rows)
         inv_sigma = torch.empty(max(nv, 1), dtype=torch.float64, device=dev)
         g_unary = torch.empty((max(nv, 1), 9), dtype=torch.float64, device=dev)
         k.call('mlbp_unary_stats', nv, c('var_de'), c('var_label'), c('sp_off'), c('sp_en'), c('sp_feat'), c('sp_val'),
                c('giv_off'), c('giv_label'), c('giv_gap1'), _p(m.pmi), _p(m.w1), _p(m.edT), _p(m.pedT), V, ld, _hp(td),
                _p(self.edstats), _p(self.colsums), _p(inv_sigma), _p(g_unary))
-        k.call('mlbp_unary_products', nv, c('var_de'), c('sp_off'), c('sp_en'), c('sp_feat'), c('sp_val'), c('giv_off'),
-               c('giv_label'), c('giv_gap1'), _p(m.edT), _p(m.pedT), V, ld, _hp(td), _p(inv_sigma), _p(self.planes),
-               V * ld, ld, self.scale_exp, _p(self.colsums), _p(U))
+        self._timed('K1 unary_products', lambda: (3.0 * nv + len(corpus.giv_label)) * V * 4,
+                    lambda: k.call('mlbp_unary_products', nv, c('var_de'), c('sp_off'), c('sp_en'), c('sp_feat'),
+                                   c('sp_val'), c('giv_off'), c('giv_label'), c('giv_gap1'), _p(m.edT), _p(m.pedT), V, ld,
+                                   _hp(td), _p(inv_sigma), _p(self.planes), V * ld, ld, self.scale_exp,
+                                   _p(self.colsums), _p(U)))
         self.launches += 2
         if blob[H_INIT_N]:
             keep = None
@@ -429,8 +449,16 @@ class Engine(object):
         for L in range(int(blob[H_NLEVELS])):
             rec = blob[H_WORDS + LEV_WORDS * L: H_WORDS + LEV_WORDS * (L + 1)]
             if rec[0]:
-                k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])), _p(bd, int(rec[3])),
-                       _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), max_in, range_log2)
+                def k3_bytes(rec=rec):
+                    ng = int(rec[0])
+                    n_in = int(blob[int(rec[2]) + ng])
+                    present = int((blob[int(rec[3]):int(rec[3]) + n_in] >= 0).sum())
+                    n_dest = int(blob[int(rec[4]) + n_in])
+                    return (ng + present + n_dest) * V * 4.0           # U row + D rows read (fp32), A hi+lo rows written
+                self._timed('K3 var_to_factor', k3_bytes,
+                            lambda: k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])),
+                                           _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld,
+                                           V, _p(A_hi), _p(A_lo), max_in, range_log2))
                 self.launches += 1
             gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
@@ -448,9 +476,15 @@ class Engine(object):
                 c0 = int(blob[int(blob[H_PAIR_C])])
                 k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, c0, n_pair, topk)
                 self.launches += 1
-            k.call('mlbp_pair_expectations', n_pair, _p(bd, int(blob[H_PAIR_C])), _p(bd, int(blob[H_PAIR_U0])),
-                   _p(bd, int(blob[H_PAIR_U1])), _p(bd, int(blob[H_PAIR_U2])), _p(A_hi), _p(A_lo), _p(D), ld, V,
-                   _p(pair_stats))
+            def k6_bytes():
+                o = lambda h: blob[int(blob[h]):int(blob[h]) + n_pair]
+                rows = 3 * n_pair + int((o(H_PAIR_U2) >= 0).sum()) + int((o(H_PAIR_Z) != o(H_PAIR_C)).sum())
+                return rows * V * 4.0                                  # c (hi+lo), u0, u1 [, u2] [, z] rows read
+            self._timed('K6a pair_expectations', k6_bytes,
+                        lambda: k.call('mlbp_pair_expectations', n_pair, _p(bd, int(blob[H_PAIR_C])),
+                                       _p(bd, int(blob[H_PAIR_Z])), _p(bd, int(blob[H_PAIR_U0])),
+                                       _p(bd, int(blob[H_PAIR_U1])), _p(bd, int(blob[H_PAIR_U2])), _p(A_hi), _p(A_lo),
+                                       _p(D), ld, V, _p(pair_stats)))
             self.launches += 1
             lab = corpus.dev('var_label', dev)
             o0, o1 = int(blob[H_PAIR_V0]), int(blob[H_PAIR_V1])
@@ -463,9 +497,14 @@ class Engine(object):
             top1 = torch.empty(n_m, dtype=torch.int32, device=dev)
             rank = torch.empty(n_m, dtype=torch.int32, device=dev)
             beliefs = torch.empty((n_m, ld), dtype=torch.float32, device=dev) if want_beliefs else None
-            k.call('mlbp_marginals', n_m, _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])),
-                   _p(bd, int(blob[H_MARG_IN])), c('var_label'), _p(U), _p(D), ld, V, _p(logp_var), _p(top1), _p(rank),
-                   _p(beliefs), range_log2 + self.half_range_log2)
+            def k5_bytes():
+                mo, mi = int(blob[H_MARG_OFF]), int(blob[H_MARG_IN])
+                n_in = int(blob[mo + n_m])
+                return (n_m + int((blob[mi:mi + n_in] >= 0).sum()) + (n_m if want_beliefs else 0)) * V * 4.0
+            self._timed('K5 marginals', k5_bytes,
+                        lambda: k.call('mlbp_marginals', n_m, _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])),
+                                       _p(bd, int(blob[H_MARG_IN])), c('var_label'), _p(U), _p(D), ld, V, _p(logp_var),
+                                       _p(top1), _p(rank), _p(beliefs), range_log2 + self.half_range_log2))
             self.launches += 1
         grad = torch.zeros((corpus.n_sent, 9), dtype=torch.float64, device=dev)
         logp = torch.zeros(corpus.n_sent, dtype=torch.float64, device=dev)

@@ -230,15 +230,16 @@ class FakeKernels(object):
             if B is not None:
                 B[g, :V] = b
 
-    def mlbp_pair_expectations(self, n_factors, c_row, u0_row, u1_row, u2_row, A_hi, A_lo, D, ldv, V, stats):
-        cr, r0, r1, r2 = (_arr(x, np.int32, n_factors) for x in (c_row, u0_row, u1_row, u2_row))
+    def mlbp_pair_expectations(self, n_factors, c_row, z_row, u0_row, u1_row, u2_row, A_hi, A_lo, D, ldv, V, stats):
+        cr, zr, r0, r1, r2 = (_arr(x, np.int32, n_factors) for x in (c_row, z_row, u0_row, u1_row, u2_row))
         H = _arr(A_hi, np.float16, (int(cr.max()) + 1) * ldv).reshape(-1, ldv)
         L = _arr(A_lo, np.float16, (int(cr.max()) + 1) * ldv).reshape(-1, ldv)
         Dm = _arr(D, np.float32, (max(int(r0.max()), int(r1.max()), int(r2.max())) + 1) * ldv).reshape(-1, ldv)
         st = _arr(stats, np.float64, n_factors * 3).reshape(-1, 3)
         for f in range(n_factors):
             c = H[cr[f], :V].astype(np.float64) + L[cr[f], :V].astype(np.float64)
-            st[f, 0] = c @ Dm[r0[f], :V].astype(np.float64)
+            z = H[zr[f], :V].astype(np.float64) + L[zr[f], :V].astype(np.float64)
+            st[f, 0] = z @ Dm[r0[f], :V].astype(np.float64)
             st[f, 1] = c @ Dm[r1[f], :V].astype(np.float64)
             st[f, 2] = c @ Dm[r2[f], :V].astype(np.float64) if r2[f] >= 0 else 0.0
 
