@@ -18,7 +18,7 @@ _SIGNATURES = {
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
     'mlbp_fill_uniform_rows': 'ppiipipp',
-    'mlbp_var_to_factor': 'ippppp' + 'ppii' + 'ppifp',
+    'mlbp_var_to_factor': 'ipppppp' + 'ppii' + 'ppifp',
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppfp',
@@ -63,7 +63,8 @@ def load():
 
 def exported_symbols():
     """Every symbol include/mlbp.h declares (used by the CPU-side ABI test)."""
-    return sorted(list(_SIGNATURES) + ['mlbp_last_error', 'mlbp_version', 'mlbp_device_ok', 'mlbp_plan_destroy'])
+    return sorted(list(_SIGNATURES) + ['mlbp_last_error', 'mlbp_version', 'mlbp_device_ok', 'mlbp_plan_destroy',
+                                       'mlbp_debug_k3_times'])
 
 
 def require_device():

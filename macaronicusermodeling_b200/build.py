@@ -22,7 +22,7 @@ def _digest():
                 with open(os.path.join(root, name), 'rb') as f:
                     h.update(name.encode())
                     h.update(f.read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update((' '.join(NVCC_FLAGS) + os.environ.get('MLBP_EXTRA_NVCC_FLAGS', '')).encode())
     return h.hexdigest()
 
 
@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
+    flags = [f for f in NVCC_FLAGS if f != '--use_fast_math=false'] + os.environ.get('MLBP_EXTRA_NVCC_FLAGS', '').split()
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)

@@ -45,6 +45,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum_t(float v) { return warp_sum_f32(v); }
+__device__ __forceinline__ double warp_sum_t(double v) { return warp_sum(v); }
+
 // Block-wide sum of one double per thread; result valid in every thread. `red` : >= 32 doubles of shared memory.
 __device__ __forceinline__ double block_sum(double v, double *red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

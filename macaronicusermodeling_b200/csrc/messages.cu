@@ -66,8 +66,9 @@ template <int NMAX, typename T, int OCC>
 __global__ void __launch_bounds__(K3_THREADS, OCC)
 var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
-                     const int32_t *__restrict__ dest, const float *__restrict__ U, const float *__restrict__ D,
-                     int ldv, int V, __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
+                     const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
+                     const float *__restrict__ U, const float *__restrict__ D, int ldv, int V,
+                     __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
     __shared__ const float *s_src[NMAX];
     __shared__ int s_d0[NMAX], s_nd[NMAX];
     __shared__ size_t s_first[NMAX];
@@ -85,7 +86,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
         const int d0 = j < n ? dest_off[i0 + j] : 0, d1 = j < n ? dest_off[i0 + j + 1] : 0;
         s_d0[j] = d0;
         s_nd[j] = d1 - d0;
-        s_first[j] = d1 > d0 ? (size_t)dest[d0] * ldv : 0;
+        s_first[j] = d1 > d0 ? (size_t)first_dest[i0 + j] * ldv : 0;
     }
     __syncthreads();
 
@@ -149,6 +150,27 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     }
 }
 
+// Messages with more than one reader (final versions read by a message GEMM row and by the gradient stage): the slice
+// just written to the first reader's row is copied into the other readers' rows (L1/L2 hits).  The caller puts a
+// __syncthreads() between the writes and this copy.
+template <int NIN>
+__device__ __forceinline__ void k3_copy_extras(const int *__restrict__ s_nd, const int *__restrict__ s_d0,
+                                               const size_t *__restrict__ s_first, const int32_t *__restrict__ dest,
+                                               int ldv, int col0, int ncol, __half *A_hi, __half *A_lo) {
+#pragma unroll 1
+    for (int j = 0; j < NIN; ++j) {
+        const int nd = s_nd[j];
+#pragma unroll 1
+        for (int t = 1; t < nd; ++t) {
+            const size_t src = s_first[j], dst = (size_t)dest[s_d0[j] + t] * ldv + col0;
+            for (int e = threadIdx.x; e < ncol; e += K3_THREADS) {
+                A_hi[dst + e] = A_hi[src + e];
+                A_lo[dst + e] = A_lo[src + e];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // K3, single-read variant.  The leave-one-out sums need every input element before the first output element can be
 // scaled, so a streaming kernel reads its inputs twice.  Here a thread-block CLUSTER owns one (variable, level) group:
@@ -164,9 +186,15 @@ template <int NIN>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                               const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
-                              const int32_t *__restrict__ dest, const float *__restrict__ U,
-                              const float *__restrict__ D, int ldv, int V, int S, __half *__restrict__ A_hi,
-                              __half *__restrict__ A_lo) {
+                              const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
+                              const float *__restrict__ U, const float *__restrict__ D, int ldv, int V, int S,
+                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, long long *dbg) {
+#ifdef MLBP_K3_STAGE_TIMES                                      // scripts/k3_probe.py: cycles per stage, per CTA
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define K3_TICK(i) do { const long long tn_ = clock64(); tacc[i] += tn_ - tprev; tprev = tn_; } while (0)
+#else
+#define K3_TICK(i) do { } while (0)
+#endif
     extern __shared__ __align__(128) float s_rows[];          // [1 + NIN][S]: row 0 = U slice, row 1 + j = input j
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ const float *s_src[2][NIN + 1];                // [buffer][0] = U row, [1 + j] = input j (nullptr: ones)
@@ -186,20 +214,33 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
 
-    // index records of group g -> shared-memory buffer b (threads 0..NIN; thread 0 also owns the U row)
-    auto fetch = [&](int g, int b) {
+    // Index records of a group -> shared-memory buffer b (threads 0..NIN; thread 0 also owns the U row).  The chain
+    // grp_off -> in_row / dest_off / first_dest is software-pipelined: (i0, n, u) of a group are loaded one iteration
+    // before they are needed, so only ONE dependent load level is left, and it overlaps the bulk copies in flight.
+    int nx_i0 = 0, nx_n = 0, nx_u = 0;
+    auto fetch_head = [&](int g) {
+        if (threadIdx.x <= NIN && g < n_groups) {
+            nx_i0 = grp_off[g];
+            nx_n = grp_off[g + 1] - nx_i0;
+            nx_u = grp_u[g];
+        }
+    };
+    auto fetch_body = [&](int b) {
         if (threadIdx.x <= NIN) {
-            const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
+            const int i0 = nx_i0, n = nx_n;
             if (threadIdx.x == 0) {
-                s_src[b][0] = U + (size_t)grp_u[g] * ldv + col0;
+                s_src[b][0] = U + (size_t)nx_u * ldv + col0;
             } else {
                 const int j = threadIdx.x - 1;
                 const int r = j < n ? in_row[i0 + j] : -1;
-                s_src[b][1 + j] = r >= 0 ? D + (size_t)r * ldv + col0 : nullptr;
+                // a message still uniform, and the unused slots, copy the constant-one row D[0] (scale-free): every
+                // group moves the same number of bytes and phase 1 / 2 need no special cases
+                s_src[b][1 + j] = D + (size_t)(r >= 0 ? r : 0) * ldv + col0;
                 const int d0 = j < n ? dest_off[i0 + j] : 0, d1 = j < n ? dest_off[i0 + j + 1] : 0;
+                const int f = j < n ? first_dest[i0 + j] : -1;
                 s_d0[b][j] = d0;
                 s_nd[b][j] = d1 - d0;
-                s_first[b][j] = d1 > d0 ? (size_t)dest[d0] * ldv + col0 : 0;
+                s_first[b][j] = f >= 0 ? (size_t)f * ldv + col0 : 0;
             }
         }
     };
@@ -209,32 +250,32 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     int g = blockIdx.x / C, b = 0;
-    if (g < n_groups) fetch(g, 0);
+    fetch_head(g);
+    if (g < n_groups) fetch_body(0);
+    fetch_head(g + n_clusters);
     __syncthreads();
     uint32_t parity = 0;
     bool first = true;
+    // Two adjacent columns per thread: 8-byte shared-memory loads, packed fp32x2 multiplies (FMUL2 on sm_100), fp16x2
+    // conversions and 4-byte stores.  With 100 KB of shared memory per CTA only 16 warps are resident per SM, so the
+    // loops are written as straight-line code (no branch on a value loaded inside the loop): measured with clock64
+    // per stage, a data-dependent branch per input cost ~100 cycles per input and column pair.
+    const int npair = (ncol + 1) >> 1;
     for (; g < n_groups; g += n_clusters, b ^= 1) {
         if (ncol > 0) {
-            if (threadIdx.x == 0) {
-                int present = 0;
-                for (int j = 0; j <= NIN; ++j) present += s_src[b][j] ? 1 : 0;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * present) : "memory");
-            }
+            if (threadIdx.x == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (NIN + 1)) : "memory");
             if (threadIdx.x <= NIN) {
-                const float *src = s_src[b][threadIdx.x];
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses before the async writes
-                if (src)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(k3_smem_u32(s_rows + (size_t)threadIdx.x * S)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads before the async writes
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(k3_smem_u32(s_rows + (size_t)threadIdx.x * S)), "l"(s_src[b][threadIdx.x]), "r"(bytes), "r"(bar) : "memory");
             }
         }
-        if (g + n_clusters < n_groups) fetch(g + n_clusters, b ^ 1);          // overlaps the copies in flight
+        K3_TICK(0);
+        if (g + n_clusters < n_groups) fetch_body(b ^ 1);                     // overlaps the copies in flight
+        fetch_head(g + 2 * n_clusters);
+        K3_TICK(1);
         if (ncol > 0) {
-            // inputs still at their uniform initial value, and unused slots, multiply by one
-#pragma unroll 1
-            for (int j = 1; j <= NIN; ++j)
-                if (!s_src[b][j])
-                    for (int e = threadIdx.x; e < ncol; e += K3_THREADS) s_rows[(size_t)j * S + e] = 1.0f;
             uint32_t ok = 0;
             const unsigned long long t0 = clock64();
             while (!ok) {
@@ -243,35 +284,42 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                 if (!ok && clock64() - t0 > 4000000000ull) __trap();   // a lost copy traps (launch error) instead of hanging the GPU
             }
             parity ^= 1u;
+            if (ncol & 1) {                                        // odd V, last slice: the pair partner of the final column
+                if (threadIdx.x <= NIN) s_rows[(size_t)threadIdx.x * S + ncol] = 1.0f;   // is row padding -> make it finite
+                __syncthreads();
+            }
         }
-        __syncthreads();
+        K3_TICK(2);
 
         // ---- phase 1: partial sums of the leave-one-out products over this CTA's columns
         float acc[NIN];
 #pragma unroll
         for (int j = 0; j < NIN; ++j) acc[j] = 0.f;
-        for (int e = threadIdx.x; e < ncol; e += K3_THREADS) {
-            const float *col = s_rows + e;
-            float d[NIN];
+        for (int e2 = threadIdx.x; e2 < npair; e2 += K3_THREADS) {
+            const float2 *col = reinterpret_cast<const float2 *>(s_rows) + e2;
+            const bool odd = 2 * e2 + 1 >= ncol;                  // the second column is padding
+            float2 d[NIN];
 #pragma unroll
-            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * S];
-            float pre[NIN];
-            float p = col[0];
+            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * (S >> 1)];
+            float2 pre[NIN];
+            float2 p = col[0];
 #pragma unroll
-            for (int j = 0; j < NIN; ++j) { pre[j] = p; p *= d[j]; }
-            float suf = 1.f;
+            for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
+            float2 suf = make_float2(1.f, odd ? 0.f : 1.f);         // zero kills the padding column's contribution
 #pragma unroll
             for (int j = NIN - 1; j >= 0; --j) {
-                acc[j] += pre[j] * suf;
-                suf *= d[j];
+                acc[j] = fmaf(pre[j].x, suf.x, acc[j]);
+                acc[j] = fmaf(pre[j].y, suf.y, acc[j]);
+                suf = __fmul2_rn(suf, d[j]);
             }
         }
 #pragma unroll
         for (int j = 0; j < NIN; ++j) {
-            const double w = warp_sum((double)acc[j]);
-            if (lane == 0) s_warp[warp][j] = w;
+            const float w = warp_sum_f32(acc[j]);                  // fp32: the fp64 pipe is ~3 lanes/clk/SM, and the
+            if (lane == 0) s_warp[warp][j] = (double)w;            // scale only has to be deterministic, not exact
         }
         __syncthreads();
+        K3_TICK(3);
         if (!first) cl.barrier_wait();                             // peers have read this CTA's previous partial sums
         if (threadIdx.x < NIN) {
             double t = 0.0;
@@ -289,35 +337,64 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         if (threadIdx.x < NIN) {
             double t = 0.0;
             for (unsigned r = 0; r < C; ++r) t += s_gather[r][threadIdx.x];      // fixed order: deterministic
+            // sum <= 0 or non-finite -> uniform (Message.renormalize, LBP.py:650-657): flagged by a negative scale
             s_scale[threadIdx.x] = (t > 0.0 && isfinite(t)) ? (float)(ldexp(1.0, MLBP_A_SCALE_LOG2) / t) : -1.0f;
         }
         __syncthreads();
+        K3_TICK(4);
 
         // ---- phase 2: recompute from shared memory, normalise, split, scatter to the consuming GEMM blocks
-        for (int e = threadIdx.x; e < ncol; e += K3_THREADS) {
-            const float *col = s_rows + e;
-            float d[NIN];
+        unsigned omask = 0, multi = 0;                             // bit j: message j has a reader / several readers
 #pragma unroll
-            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * S];
-            float pre[NIN];
-            float p = col[0];
+        for (int j = 0; j < NIN; ++j) {
+            const int nd = s_nd[b][j];
+            omask |= (nd > 0 ? 1u : 0u) << j;
+            multi |= (nd > 1 ? 1u : 0u) << j;
+        }
+        for (int e2 = threadIdx.x; e2 < npair; e2 += K3_THREADS) {
+            const float2 *col = reinterpret_cast<const float2 *>(s_rows) + e2;
+            const bool odd = 2 * e2 + 1 >= ncol;
+            float2 d[NIN];
 #pragma unroll
-            for (int j = 0; j < NIN; ++j) { pre[j] = p; p *= d[j]; }
-            float suf = 1.f;
+            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * (S >> 1)];
+            float2 pre[NIN];
+            float2 p = col[0];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
+            float2 suf = make_float2(1.f, 1.f);
 #pragma unroll
             for (int j = NIN - 1; j >= 0; --j) {
-                const int nd = s_nd[b][j];                         // 0 beyond n and for messages nobody reads
-                if (nd > 0) {
+                if ((omask >> j) & 1u) {                           // register test: no load feeds this branch
                     const float sc = s_scale[j];
-                    const float x = sc > 0.f ? pre[j] * suf * sc : uni;
-                    k3_store(x, s_first[b][j] + e, nd, dest, s_d0[b][j], ldv, col0 + e, A_hi, A_lo);
+                    float2 x = __fmul2_rn(__fmul2_rn(pre[j], suf), make_float2(sc, sc));
+                    if (!(sc > 0.f)) x = make_float2(uni, uni);
+                    const __half2 hi = __float22half2_rn(x);
+                    const float2 back = __half22float2(hi);
+                    const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
+                    const size_t o = s_first[b][j] + 2 * (size_t)e2;          // even: 4-byte aligned
+                    if (!odd) {
+                        *reinterpret_cast<__half2 *>(A_hi + o) = hi;
+                        *reinterpret_cast<__half2 *>(A_lo + o) = lo;
+                    } else {
+                        A_hi[o] = __low2half(hi);
+                        A_lo[o] = __low2half(lo);
+                    }
                 }
-                suf *= d[j];
+                suf = __fmul2_rn(suf, d[j]);
             }
         }
+        if (multi) {                                               // block-uniform
+            __syncthreads();                                       // the copy below reads elements other threads wrote
+            k3_copy_extras<NIN>(s_nd[b], s_d0[b], s_first[b], dest, ldv, col0, ncol, A_hi, A_lo);
+        }
         __syncthreads();                                           // shared memory is reused by the next group
+        K3_TICK(5);
         first = false;
     }
+#ifdef MLBP_K3_STAGE_TIMES
+    if (dbg && threadIdx.x == 0)
+        for (int i = 0; i < 6; ++i) dbg[(size_t)blockIdx.x * 6 + i] = tacc[i];
+#endif
     if (!first) cl.barrier_wait();                                 // no CTA leaves while a peer may still read it
 }
 
@@ -440,12 +517,15 @@ extern "C" int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, co
     return MLBP_OK;
 }
 
+static long long *g_k3_dbg = nullptr;
+extern "C" void mlbp_debug_k3_times(long long *p) { g_k3_dbg = p; }
+
 // resident (single-read) launch: cluster of C CTAs per group, (NIN + 1) * S floats of dynamic shared memory per CTA
 template <int NIN>
 static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, const int32_t *grp_u,
                                    const int32_t *grp_off, const int32_t *in_row, const int32_t *dest_off,
-                                   const int32_t *dest, const float *U, const float *D, int ldv, int V, __half *A_hi,
-                                   __half *A_lo) {
+                                   const int32_t *dest, const int32_t *first_dest, const float *U, const float *D,
+                                   int ldv, int V, __half *A_hi, __half *A_lo) {
     static bool configured = false;
     auto kern = var_to_factor_resident_kernel<NIN>;
     if (!configured) {
@@ -475,16 +555,18 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     }
     const int n_clusters = n_groups < resident[C] ? n_groups : resident[C];
     cfg.gridDim = dim3((unsigned)n_clusters * (unsigned)C);
-    return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, S, A_hi, A_lo);
+    return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, S,
+                              A_hi, A_lo, g_k3_dbg);
 }
 
 constexpr int K3_RESIDENT_MAX_IN = 24;
 
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
-                                  const int32_t *dest_off, const int32_t *dest, const float *U, const float *D,
-                                  int ldv, int V, void *A_hi, void *A_lo, int max_in, float range_log2, void *stream) {
+                                  const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
+                                  const float *U, const float *D, int ldv, int V, void *A_hi, void *A_lo, int max_in,
+                                  float range_log2, void *stream) {
     if (n_groups == 0) return MLBP_OK;
-    MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && U && D && A_hi && A_lo,
+    MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
     const bool fp32_ok = range_log2 >= 0.f && range_log2 < 100.f;   // products provably stay inside 2^+-100
     MLBP_CHECK_ARG(V > 0 && ldv >= V && (ldv % 4) == 0, "var_to_factor: bad V/ldv");
@@ -494,12 +576,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = as_stream(stream);
-    // MLBP_K3_IMPL (probing): unset / 1 = streaming kernel, 2 = resident single-read kernel whenever the slices fit
+    // The resident single-read kernel runs whenever the products fit fp32 and the cluster's slices fit shared memory;
+    // MLBP_K3_IMPL=1 forces the streaming two-read kernel (used by scripts/k3_probe.py to time both).
     const char *env_impl = getenv("MLBP_K3_IMPL");
-    const int forced = env_impl ? atoi(env_impl) : 1;
+    const int forced = env_impl ? atoi(env_impl) : 2;
     const int nin = max_in < 1 ? 1 : max_in;
     int C = 0, S = 0;
-    if (fp32_ok && forced != 1 && nin <= K3_RESIDENT_MAX_IN && (((uintptr_t)U | (uintptr_t)D) & 15) == 0)
+    if (fp32_ok && forced == 2 && nin <= K3_RESIDENT_MAX_IN && (((uintptr_t)U | (uintptr_t)D) & 15) == 0)
         for (int c = 1; c <= 8 && !C; c *= 2) {
             const int s4 = (((V + c - 1) / c) + 3) & ~3, s32 = (s4 + 31) & ~31;    // 128-byte slices when they still fit
             if ((size_t)(nin + 1) * s32 * sizeof(float) <= (size_t)K3_RESIDENT_SMEM) { C = c; S = s32; }
@@ -509,7 +592,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         if ((int64_t)n_groups * C > 0x7fffffffll) { set_error("var_to_factor: too many groups"); return MLBP_ERR_INVALID; }
 #define MLBP_K3_RES(N)                                                                                             \
         case N:                                                                                                    \
-            MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, \
+            MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, \
                                          (__half *)A_hi, (__half *)A_lo));                                         \
             break;
         switch (nin) {
@@ -528,13 +611,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     do {                                                                                                         \
         if (fp32_ok && occ3 && N <= 20)                                                                          \
             var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else if (fp32_ok)                                                                                        \
             var_to_factor_kernel<N, float, 1><<<n_groups, K3_THREADS, 0, st>>>(                                  \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else                                                                                                     \
             var_to_factor_kernel<N, double, 1><<<n_groups, K3_THREADS, 0, st>>>(                                 \
-                grp_u, grp_off, in_row, dest_off, dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);

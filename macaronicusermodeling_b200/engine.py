@@ -24,7 +24,7 @@ from . import _lib
 (H_NLEVELS, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
  H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
  H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z) = range(25)
-H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 8, 4
+H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
  PLAN_N_DEAD) = range(9)
 A_SCALE_LOG2 = 14
@@ -457,7 +457,7 @@ class Engine(object):
                     return (ng + present + n_dest) * V * 4.0           # U row + D rows read (fp32), A hi+lo rows written
                 self._timed('K3 var_to_factor', k3_bytes,
                             lambda: k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])),
-                                           _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(U), _p(D), ld,
+                                           _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(U), _p(D), ld,
                                            V, _p(A_hi), _p(A_lo), max_in, range_log2))
                 self.launches += 1
             gemm_calls(int(rec[7]), int(rec[6]), approx_inference)

@@ -38,6 +38,11 @@ def main():
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
     if os.path.exists(pk):
         peak = float(json.load(open(pk)).get('hbm_gbs', peak))
+    # per-stage clock64 totals: only when the library was built with MLBP_EXTRA_NVCC_FLAGS=-DMLBP_K3_STAGE_TIMES
+    dbg = torch.zeros((148 * 2 * 8, 6), dtype=torch.int64, device=dev)
+    lib.mlbp_debug_k3_times.argtypes = [ctypes.c_void_p]
+    lib.mlbp_debug_k3_times.restype = None
+    lib.mlbp_debug_k3_times(ctypes.c_void_p(dbg.data_ptr()))
     out = {}
     for shape, (ng, outs) in {'down (18 outputs)': (G, list(range(1, n))), 'up-b (1 output)': (G, [5 % n]),
                               'root (19 outputs, 128 groups)': (min(128, G), list(range(n)))}.items():
@@ -48,15 +53,16 @@ def main():
         has = np.zeros(n, dtype=np.int32); has[outs] = 1
         dest_off[1:] = np.cumsum(np.tile(has, ng))
         dest = np.arange(int(dest_off[-1]), dtype=np.int32)
+        first = np.where(np.diff(dest_off) > 0, dest[np.minimum(dest_off[:-1], len(dest) - 1)], -1).astype(np.int32)
         t = lambda x: torch.from_numpy(x).to(dev)
-        d_u, d_off, d_in, d_doff, d_dest = t(grp_u), t(grp_off), t(in_row), t(dest_off), t(dest)
+        d_u, d_off, d_in, d_doff, d_dest, d_first = t(grp_u), t(grp_off), t(in_row), t(dest_off), t(dest), t(first)
         nbytes = (ng + ng * n + len(dest)) * V * 4.0
         res = {}
-        for variant, impl, occ in (('streaming_occ2', '1', '2'), ('streaming', '1', '3'), ('resident', '2', '3')):
+        for variant, impl, occ in (('streaming', '1', '3'), ('resident', '2', '3')):
             os.environ['MLBP_K3_IMPL'] = impl
             os.environ['MLBP_K3_OCC'] = occ
             Ah, Al = A[0 if impl == '1' else 1, 0], A[0 if impl == '1' else 1, 1]
-            call = lambda: _lib.check(lib.mlbp_var_to_factor(ng, _p(d_u), _p(d_off), _p(d_in), _p(d_doff), _p(d_dest), _p(U),
+            call = lambda: _lib.check(lib.mlbp_var_to_factor(ng, _p(d_u), _p(d_off), _p(d_in), _p(d_doff), _p(d_dest), _p(d_first), _p(U),
                                                              _p(D), ld, V, _p(Ah), _p(Al), n, 30.0, st))
             for _ in range(2):
                 call()
@@ -68,6 +74,10 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.reps
+            if variant == 'resident' and bool((dbg.sum(1) > 0).any()):
+                dd = dbg[dbg.sum(1) > 0].double()
+                print('   resident stage cycles per CTA (issue, fetch, wait, phase1, sync, phase2) mean:', [int(x) for x in dd.mean(0).tolist()], 'CTAs', dd.shape[0], 'groups/cluster', ng / max(dd.shape[0] / 8, 1))
+                dbg.zero_()
             res[variant] = {'ms': ms, 'GB/s': nbytes / ms / 1e6, 'frac_of_hbm_peak': nbytes / ms / 1e6 / peak}
         nd = len(dest)
         x0 = A[0, 0, :nd, :V].float() + A[0, 1, :nd, :V].float()
