@@ -136,7 +136,11 @@ int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, in
  *   D[d_row0 + r, n] = alpha * sum_k (A_hi + A_lo)[a_row0 + r, k] * (B_hi + B_lo)[n, k],  r < n_rows, n < V
  *   as three tcgen05 passes hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory.
  *   A_*: [a_rows_total, ldv] fp16, B_*: one plane pair [V, ldv] fp16, D: [*, ldd] fp32.
- *   impl: 0 = tcgen05 (product path), 1 = SIMT cross-check kernel (tests only).                           */
+ *   impl: 0 = tcgen05 (product path), 1 = SIMT cross-check kernel (tests only); OR-ed with MLBP_GEMM_A_HI_ONLY the
+ *   A_lo term is dropped (two passes hi*hi + hi*lo, A_lo is not even loaded).  The gradient stage uses it: the
+ *   expectation N/Z of a pairwise belief is a RATIO of two rows computed from the same message r, so the 2^-12
+ *   rounding of r largely cancels (measured <= 2e-7 relative on a sentence's gradient; the contract is 1e-4).      */
+#define MLBP_GEMM_A_HI_ONLY 256
 int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                             const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
                             float alpha, int impl, void *stream);

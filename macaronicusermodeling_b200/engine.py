@@ -28,6 +28,7 @@ H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
  PLAN_N_DEAD) = range(9)
 A_SCALE_LOG2 = 14
+GEMM_A_HI_ONLY = 256          # include/mlbp.h MLBP_GEMM_A_HI_ONLY
 N_PLANES = 14
 N_SUMS = 7
 D_CONST_ROWS = 5
@@ -206,13 +207,17 @@ class Result(object):
 
 
 class Engine(object):
-    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0):
+    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
         self.V, self.Vd, self.ld = self.model.V, self.model.Vd, self.model.ld
         self.workspace_bytes = int(workspace_bytes)
         self.gemm_impl = gemm_impl
+        # Gradient-stage GEMM rows multiply only the hi half of the message r (2 tensor-core passes instead of 3): the
+        # expectation N/Z is a ratio of two rows built from the same r, so its 2^-12 rounding largely cancels (<= 2e-7
+        # relative on a sentence's gradient, measured against the float64 oracle).  2 = all three passes.
+        self.grad_a_terms = int(grad_a_terms)
         self.theta_ee = None
         self.theta_ed = None
         self.planes = None
@@ -263,6 +268,10 @@ class Engine(object):
             warnings.warn('pairwise potentials span e^%.1f: entries more than 2^18 below the largest lose relative '
                           'precision in the fp16 hi/lo operand planes (absolute error stays 2^-38 of the maximum)' % (zmax - zmin))
         erange, prange = self.model.ed_range
+        # two-pass gradient rows (grad_a_terms == 1) only while the potentials are moderately peaked: the error of one
+        # expectation is bounded by 2^-12 x the belief's mean absolute deviation of the feature, measured 2e-7 relative
+        # on a sentence's gradient at log-ranges ~1.5 and 9e-6 at ~6.5; beyond e^3 the third pass is kept
+        self.grad_hi_only_ok = (zmax - zmin) <= 3.0 and (abs(td[0]) * erange + abs(td[1]) * prange) <= 3.0
         self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
         n_planes = N_PLANES if with_grad else 8
         if self.planes is None or self.planes.shape[0] < n_planes:
@@ -373,8 +382,12 @@ class Engine(object):
                           {'v2f': [], 'f2v': []} if want_messages else None)
         lib = _lib.load()
         # masked (top-K) message rows: the pairwise normaliser Z must come from its own GEMM row of the final messages
+        approx = approx_inference or approx_beliefs
+        grad_hi_only = self.grad_a_terms == 1 and self.grad_hi_only_ok and not approx
+        # Z = c'Tr may reuse the D row of a message update only if that row was built from the same operand as the
+        # numerator rows: not with masked (top-K) messages, and not when the gradient rows drop the lo half of r
         handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference,
-                                     reuse_z=not (approx_inference or approx_beliefs))
+                                     reuse_z=not approx and not grad_hi_only)
         try:
             words = int(sizes[PLAN_BLOB_WORDS])
             nv = corpus.n_vars
@@ -426,7 +439,7 @@ class Engine(object):
         g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
         range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
 
-        def gemm_calls(off, n, mask):
+        def gemm_calls(off, n, mask, impl_flags=0):
             masked = set()
             for i in range(n):
                 t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
@@ -438,10 +451,10 @@ class Engine(object):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                 k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0, rows, _p(self.plane(t, 0)),
-                       _p(self.plane(t, 1)), V, ld, _p(D), d0, ld, alpha, self.gemm_impl)
+                       _p(self.plane(t, 1)), V, ld, _p(D), d0, ld, alpha, self.gemm_impl | impl_flags)
                 if self.profile_gemm:
                     e1.record()
-                    self.gemm_events.append((e0, e1, rows))
+                    self.gemm_events.append((e0, e1, rows, 2 if impl_flags & GEMM_A_HI_ONLY else 3))
                 self.launches += 1
                 self.gemm_launches += 1
                 self.gemm_rows += rows
@@ -471,7 +484,8 @@ class Engine(object):
             rows = torch.cat([bd[oc:oc + n_pair], bd[orr:orr + n_pair]]).long()
             v2f_rows = (A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)
         if want_grad and n_pair:
-            gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs)
+            gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
+                       GEMM_A_HI_ONLY if grad_hi_only else 0)
             if approx_beliefs:                                    # the c rows follow the r rows in the A buffer
                 c0 = int(blob[int(blob[H_PAIR_C])])
                 k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, c0, n_pair, topk)

@@ -83,6 +83,33 @@ def test_c3_full_size_vs_oracle():
     print('C3 worst belief abs err', worst)
 
 
+@pytest.mark.parametrize('scale', [1.0, 5.0], ids=['mid', 'peaked'])
+def test_two_pass_gradient_rows(scale):
+    """The gradient-stage GEMM rows use the hi half of the message only (2 tensor-core passes).  Against the full
+    3-pass gradient the difference must stay far inside the 1e-4 contract, also with peaked potentials (the rounding of
+    r cancels in the ratio N/Z because Z is computed from the same rounded r)."""
+    model = synth.make_model(2048, 256, seed=5, dtype=np.float32)
+    sents = synth.make_corpus(model, 6, k=12, g=2, seed=3)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=4))
+    te, td = np.array([0.8, 0.5, -0.3]) * scale, np.array([1.0, -0.6, 0.5, 0.3, 0.4, -0.2]) * scale
+    g = []
+    for terms in (2, 1):
+        eng = Engine(model, grad_a_terms=terms)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3)
+        g.append(r.grad.cpu().numpy())
+        rows = r.stats['gemm_rows']
+    rel = np.abs(g[0][:, :2] - g[1][:, :2]) / np.maximum(np.abs(g[0][:, :2]), 1e-3)
+    assert rel.max() < 2e-6, rel.max()
+    if scale > 1.0:                    # potentials spanning more than e^3: the engine keeps the third pass
+        assert not eng.grad_hi_only_ok
+        np.testing.assert_allclose(g[0], g[1], rtol=1e-12, atol=1e-13)
+    else:
+        assert eng.grad_hi_only_ok and rel.max() > 0.0
+    np.testing.assert_array_equal(g[0][:, 2:], g[1][:, 2:])     # bias and unary components do not use those rows
+
+
 def test_c5_inference_only_many_sweeps():
     """BASELINE config C5 shape scaled to what the oracle can check: inference only, 10 sweeps, k = 12; dead-update
     elimination must not change any belief."""
