@@ -308,8 +308,16 @@ def ours(a):
     which = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
     flops = 2.0 * gemm_rows * a.V * a.V
     ach = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic, traffic_note = None, None
+    tr_path = os.path.join(REPO, 'profiles', 'r1b_k4_traffic.json')
+    if os.path.exists(tr_path) and a.V == 10000:
+        tr = json.load(open(tr_path))
+        traffic = tr['dram_bytes_per_launch']
+        traffic_note = ('dram__bytes_read+write per launch from the committed ncu --set full capture (%d-row launches: %.2fx their '
+                        'algorithmic A + D + table bytes); launches of this run average %d rows'
+                        % (tr['rows_per_launch'], tr['ratio'], gemm_rows // max(n_gemm, 1)))
     roofline = {'bound': 'tensor', 'kernel': 'gemm_split_f16_kernel (K4)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': ach / peak_tf, 'traffic': None, 'peak_source': which,
+                'frac': ach / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': which,
                 'executed_tflops': ach * gemm_pass_rows / max(gemm_rows, 1), 'executed_frac': ach * gemm_pass_rows / max(gemm_rows, 1) / peak_tf,
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(n_gemm, 1),
                 'algorithmic_flops_per_launch': flops / max(n_gemm, 1), 'share_of_step': gemm_ms / ms,

@@ -13,9 +13,16 @@ Supported graphs: the macaronic model the reference's callers build (train.py:25
 ``factor_type`` 'en_de' (unary, observed German word) or 'en_en' (unary with an observed English word, or pairwise),
 tables selected by ``gap`` like FactorNode.get_pot (LBP.py:456-467), features as stacked by train.py:594-609
 (phi_en_en = [pmi, 0, 1], phi_en_en_w1 = [pmi, pmi_w1, 1], phi_en_de = [ed, ped, correct, full_history,
-hit_history, 1]).  Explicit ``PotentialTable(table=...)`` graphs (the stale run.py demo) and direct per-node
-``update_message_to`` calls raise NotImplementedError.  There is no CPU fallback: without libmlbp.so and a B200 the
-first computation raises.
+hit_history, 1]).
+
+Eager mode.  The reference's one-message-at-a-time API -- ``VariableNode.update_message_to(fc)`` /
+``FactorNode.update_message_to(var)`` (LBP.py:377-389, :490-526) -- and graphs built from explicit
+``PotentialTable(table=...)`` arrays (run.py / toy style) bypass the batched engine: ``graph.messages`` becomes the
+state, each update is the same ``au`` call the reference makes (a device kernel per pointwise product, dot product and
+normalisation), ``treelike_inference`` walks the schedule literally, marginals and gradients are computed factor by
+factor.  It is the reference's cost model (one launch per tiny op) and exists for API completeness and debugging; the
+fast path is the lazy batched mode above.  There is no CPU fallback: without libmlbp.so and a B200 the first
+computation raises.
 """
 import random
 import sys
@@ -112,6 +119,12 @@ class FactorGraph():
         self._initialized = False
         self._res = None          # cached engine outputs for (_sweeps, theta snapshot)
         self._messages = None
+        # Eager mode: the reference's one-message-at-a-time API (VariableNode / FactorNode.update_message_to) and
+        # graphs with explicit PotentialTable(table=...) arrays.  graph.messages then IS the state, every update is
+        # one `au` device op exactly where the reference calls au (LBP.py:377-389, :490-526), and the batched engine
+        # is bypassed.  None = lazy batched mode (the fast path).
+        self._eager = None
+        self._explicit = False
 
     # ------------------------------------------------------------------ reference API: bookkeeping
     def display_timing_info(self):
@@ -183,15 +196,41 @@ class FactorGraph():
         fs = sorted([(f.id, f) for f in self.factors], key=lambda t: t[0])
         self.factors = [f for fid, f in fs]
         self.isLoopy = self.has_loops(root)
+        self._explicit = False
         for f in self.factors:
             if __debug__: assert len(f.potential_table.var_id2dim) == len(f.varset)
             if f.potential_table.explicit:
-                raise NotImplementedError('explicit PotentialTable(table=...) graphs are not supported by the B200 engine')
+                self._explicit = True
         self._roots = [self._last_loop_root]
         self._sweeps = 0
         self._initialized = True
         self._res = None
         self._messages = None
+        self._eager = self._uniform_messages() if self._explicit else None
+
+    def _uniform_messages(self):
+        """LBP.py:200-216: unary factors only send, pairwise factors exchange messages in both directions"""
+        msgs = {}
+        for f in self.factors:
+            if len(f.varset) == 1:
+                v = f.varset[0]
+                msgs[str(f), str(v)] = Message.new_message(v.domain, 1.0 / len(v.domain))
+            else:
+                for v in f.varset:
+                    msgs[str(v), str(f)] = Message.new_message(v.domain, 1.0 / len(v.domain))
+                    msgs[str(f), str(v)] = Message.new_message(v.domain, 1.0 / len(v.domain))
+        return msgs
+
+    def _enter_eager(self):
+        """Switch to the one-message-at-a-time mode, starting from the current messages (the batched result of the
+        sweeps recorded so far, or the uniform initial messages)."""
+        if self._eager is None:
+            if not self._initialized:
+                raise KeyError('messages are not initialised: call initialize() first')
+            self._eager = self._uniform_messages() if self._sweeps == 0 else dict(self.messages)
+            self._res = None
+            self._messages = None
+        return self._eager
 
     def treelike_inference(self, iterations, roots=None):
         """LBP.py:218-245.  ``roots`` (optional, not in the reference) pins the per-sweep BFS roots."""
@@ -200,8 +239,17 @@ class FactorGraph():
         iterations = iterations if self.isLoopy else 1
         for i in range(iterations):
             if self.report_times: it = time.time()
-            self._roots.append(self._draw_root() if roots is None else roots[i])
+            root = self._draw_root() if roots is None else roots[i]
+            self._roots.append(root)
             self._sweeps += 1
+            if self._eager is not None:                  # LBP.py:225-243, one update at a time
+                _schedule = self.get_message_schedule(self.variables[root])
+                for frm, to in reversed(_schedule):
+                    if not (isinstance(to, FactorNode) and len(to.varset) < 2):
+                        frm.update_message_to(to)
+                for to, frm in _schedule:
+                    if not (isinstance(to, FactorNode) and len(to.varset) < 2):
+                        frm.update_message_to(to)
             if self.report_times: self.it_times.append(time.time() - it)
         self._res = None
         self._messages = None
@@ -316,6 +364,8 @@ class FactorGraph():
     @property
     def messages(self):
         """graph.messages[(str(src), str(dst))] -> Message, like the dict the reference keeps (LBP.py:40)"""
+        if self._eager is not None:
+            return self._eager
         if self._messages is None:
             res = self._run()
             msgs = {}
@@ -341,8 +391,19 @@ class FactorGraph():
     # ------------------------------------------------------------------ reference API: results
     def get_posterior_probs(self):
         """LBP.py:247-259"""
-        res = self._run()
         log_posterior = 0.0
+        if self._eager is not None:
+            for v_key, v in self.variables.items():
+                p = v.get_marginal().m[v.supervised_label_index]
+                with np.errstate(divide='ignore'):
+                    _l = np.log(p)
+                if _l == float('-inf'):
+                    sys.stderr.write('err -inf' + str(p))
+                    log_posterior += -99.99
+                else:
+                    log_posterior += np.sum(_l)
+            return log_posterior
+        res = self._run()
         for _l in res['logp_var']:
             if _l <= -99.99:
                 sys.stderr.write('err -inf' + str(0.0))
@@ -412,9 +473,17 @@ class FactorGraph():
         for f in self.factors:
             if f.factor_type not in ('en_en', 'en_de'):
                 raise BaseException('only 2 kinds of factors allowed...')
-        g = self._run()['grad']
         grad_en_en = np.zeros_like(self.theta_en_en, dtype=DTYPE)
         grad_en_de = np.zeros_like(self.theta_en_de, dtype=DTYPE)
+        if self._eager is not None:                      # LBP.py:304-319, factor by factor
+            for f in self.factors:
+                g = f.get_gradient()
+                if f.factor_type == 'en_en':
+                    grad_en_en += g
+                else:
+                    grad_en_de += g
+            return grad_en_en, grad_en_de
+        g = self._run()['grad']
         grad_en_en += g[:3].reshape(grad_en_en.shape)
         grad_en_de += g[3:].reshape(grad_en_de.shape)
         return grad_en_en, grad_en_de
@@ -480,10 +549,30 @@ class VariableNode():
         raise AttributeError("VariableNode instance has no attribute 'messages'")      # LBP.py:375 is broken the same way
 
     def update_message_to(self, fc):
-        raise NotImplementedError('single-message updates are scheduled by FactorGraph.treelike_inference on the GPU')
+        """LBP.py:377-389: leave-one-out product of the incoming factor messages, one au.pointwise_multiply (device) per
+        message, then renormalise.  Switches the graph to eager mode."""
+        if __debug__: assert isinstance(fc, FactorNode)
+        if __debug__: assert fc in self.facset
+        msgs = self.graph._enter_eager()
+        new_m = Message.new_message(self.domain, 1.0 / len(self.domain))
+        for other_fc in self.facset:
+            if other_fc is not fc:
+                m = msgs[str(other_fc), str(self)]
+                new_m = pointwise_multiply(m, new_m)
+                if __debug__: assert np.shape(new_m.m) == np.shape(m.m)
+        if self.graph.normalize_messages:
+            new_m.renormalize()
+        msgs[str(self), str(fc)] = new_m
 
     def get_marginal(self):
         """LBP.py:392-400"""
+        if self.graph._eager is not None:
+            new_m = Message.new_message(self.domain, 1.0 / len(self.domain))
+            for fc in self.facset:
+                new_m = pointwise_multiply(self.graph._eager[str(fc), str(self)], new_m)
+            if self.graph.normalize_messages:
+                new_m.renormalize()
+            return new_m
         res = self.graph._run()
         return Message(res['beliefs'][res['vids'].index(self.id)].reshape(-1, 1))
 
@@ -583,10 +672,38 @@ class FactorNode():
             raise BaseException("only unary or binary factors are supported...")
 
     def update_message_to(self, var):
-        raise NotImplementedError('single-message updates are scheduled by FactorGraph.treelike_inference on the GPU')
+        """LBP.py:490-526: unary -> normalize(copy(table)); pairwise -> T.m or m'.T through au.dense_dot (device), or
+        au.sparse_vec_mat_dot with use_approx_inference; then renormalise.  Switches the graph to eager mode."""
+        msgs = self.graph._enter_eager()
+        other_vars = [v for v in self.varset if v.id != var.id]
+        if len(other_vars) == 0:
+            new_m = Message(np.copy(self._table()))
+        else:
+            o_var = other_vars[0]
+            o_var_dim = self.potential_table.var_id2dim[o_var.id]
+            msg = msgs[str(o_var), str(self)]
+            table = np.ascontiguousarray(self._table())
+            if o_var_dim == 1:
+                if self.graph.use_approx_inference:
+                    marginalized = au.sparse_vec_mat_dot(msg.m, table)
+                else:
+                    marginalized = au.dense_dot(table, msg.m)
+            else:
+                if self.graph.use_approx_inference:
+                    marginalized = au.sparse_vec_mat_dot(np.ascontiguousarray(msg.m.T), table)
+                else:
+                    marginalized = au.dense_dot(np.ascontiguousarray(msg.m.T), table)
+            new_m = Message(marginalized)
+        if self.graph.normalize_messages:
+            new_m.renormalize()
+        if __debug__: assert np.shape(new_m.m) == np.shape(msgs[str(self), str(var)].m)
+        msgs[str(self), str(var)] = new_m
 
     def _table(self):
-        """the factor's potential table as a float64 array, computed on the GPU from theta and the features"""
+        """the factor's potential table as a float64 array: the explicit array of PotentialTable(table=...), else
+        computed on the GPU from theta and the features"""
+        if self.potential_table.explicit:
+            return self.potential_table.table
         from . import LBP as _self  # noqa: F401
         eng = _engine_for(self.graph)
         g = self.graph

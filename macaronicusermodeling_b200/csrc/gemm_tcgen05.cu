@@ -219,7 +219,10 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+            // the last N tile is usually narrow (V = 10 000: 16 of 256 columns): issue it with the matching UMMA N so that
+            // it costs 1/16 of a full tile instead of multiplying 240 zero-filled rows of B
+            const int n_valid = min(BN, V - n_blk * BN);
+            const uint32_t idesc = umma_idesc_f16(BM, (n_valid + 15) & ~15);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -279,9 +282,9 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
             for (int j = 0; j < 32; ++j) {
                 const int nc = n0 + 4 * j;
                 if (nc < ldd) {                                   // ldd is a multiple of 64: a float4 is all-in or all-out
-                    float4 o;
-                    o.x = acc[4 * j + 0] * alpha; o.y = acc[4 * j + 1] * alpha;
-                    o.z = acc[4 * j + 2] * alpha; o.w = acc[4 * j + 3] * alpha;
+                    float4 o;                                     // columns >= V (row padding) are written as zeros
+                    o.x = nc + 0 < V ? acc[4 * j + 0] * alpha : 0.f; o.y = nc + 1 < V ? acc[4 * j + 1] * alpha : 0.f;
+                    o.z = nc + 2 < V ? acc[4 * j + 2] * alpha : 0.f; o.w = nc + 3 < V ? acc[4 * j + 3] * alpha : 0.f;
                     *reinterpret_cast<float4 *>(drow + nc) = o;
                 }
             }

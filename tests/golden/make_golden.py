@@ -308,17 +308,101 @@ def au_cases(au):
     return out
 
 
+def au_cases_more(au):
+    """the remaining c_array_utils functions (none of them is called by LBP.py; kept for API completeness)"""
+    rng = np.random.default_rng(11)
+    out = {}
+    a = rng.random((160, 1))
+    b = rng.random((160, 1))
+    d1 = rng.random((40, 30))
+    d2 = rng.random((40, 30))
+    W = rng.random((12, 160))
+    out['a'], out['b'], out['d1'], out['d2'], out['W'] = a, b, d1, d2, W
+    out['induce_s_pointwise_multiply_clip'] = au.induce_s_pointwise_multiply_clip(d1, d2)
+    out['induce_s'] = au.induce_s(a.copy())
+    out['induce_s_small'] = au.induce_s(a[:50].copy())
+    out['induce_s_mutliply_clip'] = au.induce_s_mutliply_clip(a - 0.5, W)
+    d = au.make_sparse_and_dot(a, np.ascontiguousarray(b.T))
+    keys = sorted(d.keys())
+    out['msd_keys'] = np.array(keys, dtype=np.int64)
+    out['msd_vals'] = np.array([d[k] for k in keys])
+    M = rng.random((160, 160))
+    out['M'] = M
+    mz, md = au.sparse_multiply_and_normalize(d, M)
+    out['smn_dense'] = mz
+    out['smn_vals'] = np.array([md[k] for k in keys])
+    out['sd_matrix_multiply'] = au.sd_matrix_multiply(d1, d2.T.copy())
+    out['ss_matix_multiply'] = au.ss_matix_multiply(d1.T.copy(), d2)
+    phi = rng.random((7, 3))
+    out['phi'] = phi
+    ap = au.make_adapt_phi(phi, 4)
+    out['make_adapt_phi'] = ap.copy()
+    out['set_adaptation'] = au.set_adaptation(3, ap.copy(), [1, 3]).copy()
+    out['set_adaptation_off'] = au.set_adaptation_off(3, au.set_adaptation(3, ap.copy(), [1, 3]), [3]).copy()
+    out['set_original'] = au.set_original(phi * 2.0, ap.copy()).copy()
+    return out
+
+
+def explicit_table_case(LBP):
+    """a graph built from explicit PotentialTable(table=...) arrays (the run.py / toy style): messages and marginals"""
+    rng = np.random.default_rng(3)
+    V = 60
+    dom = ['w%d' % i for i in range(V)]
+    fg = LBP.FactorGraph(theta_en_en_names=['a'], theta_en_de_names=['b'], theta_en_en=np.zeros((1, 1)),
+                         theta_en_de=np.zeros((1, 1)), phi_en_en_w1=None, phi_en_en=None, phi_en_de=None)
+    vs = [LBP.VariableNode(id=i, var_type=LBP.VAR_TYPE_PREDICTED, domain_type='en', domain=dom, supervised_label=dom[(7 * i + 3) % V])
+          for i in range(4)]
+    unary = rng.random((4, V, 5)) + 0.05
+    pair = {}
+    fid = 0
+    for i, v in enumerate(vs):
+        f = LBP.FactorNode(id=fid, factor_type='en_de', observed_domain_size=5)
+        f.add_varset_with_potentials(varset=[v], ptable=LBP.PotentialTable(v_id2dim={v.id: 0}, table=unary[i], observed_dim=i % 5))
+        fg.add_factor(f)
+        fid += 1
+    for i, j in ((0, 1), (1, 2), (0, 2), (2, 3)):
+        t = rng.random((V, V)) + 0.01
+        pair['%d_%d' % (i, j)] = t
+        f = LBP.FactorNode(id=fid, factor_type='en_en')
+        f.add_varset_with_potentials(varset=[vs[i], vs[j]], ptable=LBP.PotentialTable(v_id2dim={vs[i].id: 0, vs[j].id: 1}, table=t))
+        fg.add_factor(f)
+        fid += 1
+    return fg, vs, unary, pair
+
+
+def run_explicit_case(LBP, feeder):
+    fg, vs, unary, pair = explicit_table_case(LBP)
+    roots = [1, 2, 0, 3]
+    feeder.queue = [roots[0]]
+    fg.initialize()
+    feeder.queue = list(roots[1:])
+    fg.treelike_inference(3)
+    out = {'roots': np.array(roots), 'unary': unary, 'is_loopy': np.array(int(fg.isLoopy))}
+    for k, t in pair.items():
+        out['pair_' + k] = t
+    for (a, b), m in fg.messages.items():
+        out['msg|%s|%s' % (a, b)] = m.m[:, 0]
+    out['marginals'] = np.stack([v.get_marginal().m[:, 0] for v in vs])
+    out['logp'] = np.array(fg.get_posterior_probs())
+    return out
+
+
 # ----------------------------------------------------------------------------- cases
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
     ap.add_argument('--out', default=HERE)
+    ap.add_argument('--only-new', action='store_true', help='write only au_cases_more.npz and graphx_explicit.npz')
     args = ap.parse_args()
     work = tempfile.mkdtemp(prefix='mlbp_ref_')
     try:
         build_patched_reference(args.ref, work)
         LBP, train, feeder = import_reference(work)
         au = importlib.import_module('array_utils.c_array_utils')
+        np.savez_compressed(os.path.join(args.out, 'au_cases_more.npz'), **au_cases_more(au))
+        np.savez_compressed(os.path.join(args.out, 'graphx_explicit.npz'), **run_explicit_case(LBP, feeder))
+        if args.only_new:
+            return
         np.savez_compressed(os.path.join(args.out, 'au_cases.npz'), **au_cases(au))
 
         # ---- graph cases (BASELINE config C1-style toy graphs + structural edge cases)

@@ -140,3 +140,122 @@ def check_adapt_trainer(make_engine):
                 row += list(tr.domain2theta[u])
             traj.append(np.concatenate(row))
     np.testing.assert_allclose(np.array(traj), z['traj'], rtol=1e-4, atol=3e-7)
+
+
+# ----------------------------------------------------------------------------- eager (one message at a time) mode
+def explicit_graph_from_fixture(z):
+    """the explicit PotentialTable(table=...) graph of tests/golden/make_golden.py::explicit_table_case, through the drop-in"""
+    from macaronicusermodeling_b200 import LBP
+    V = z['unary'].shape[1]
+    dom = ['w%d' % i for i in range(V)]
+    fg = LBP.FactorGraph(theta_en_en_names=['a'], theta_en_de_names=['b'], theta_en_en=np.zeros((1, 1)),
+                         theta_en_de=np.zeros((1, 1)), phi_en_en_w1=None, phi_en_en=None, phi_en_de=None)
+    vs = [LBP.VariableNode(id=i, var_type=LBP.VAR_TYPE_PREDICTED, domain_type='en', domain=dom,
+                           supervised_label=dom[(7 * i + 3) % V]) for i in range(4)]
+    fid = 0
+    for i, v in enumerate(vs):
+        f = LBP.FactorNode(id=fid, factor_type='en_de', observed_domain_size=5)
+        f.add_varset_with_potentials(varset=[v], ptable=LBP.PotentialTable(v_id2dim={v.id: 0}, table=z['unary'][i],
+                                                                          observed_dim=i % 5))
+        fg.add_factor(f)
+        fid += 1
+    for i, j in ((0, 1), (1, 2), (0, 2), (2, 3)):
+        f = LBP.FactorNode(id=fid, factor_type='en_en')
+        f.add_varset_with_potentials(varset=[vs[i], vs[j]],
+                                     ptable=LBP.PotentialTable(v_id2dim={vs[i].id: 0, vs[j].id: 1}, table=z['pair_%d_%d' % (i, j)]))
+        fg.add_factor(f)
+        fid += 1
+    return fg, vs
+
+
+def check_explicit_graph_structure(z):
+    """no arithmetic: initialize() of an explicit-table graph creates the reference's uniform messages (LBP.py:200-216)"""
+    fg, vs = explicit_graph_from_fixture(z)
+    fg.initialize(int(z['roots'][0]))
+    assert bool(fg.isLoopy) == bool(int(z['is_loopy']))
+    keys = sorted(k[4:] for k in z.files if k.startswith('msg|'))
+    assert sorted('%s|%s' % k for k in fg.messages.keys()) == keys
+    for m in fg.messages.values():
+        np.testing.assert_array_equal(m.m, np.full((60, 1), 1.0 / 60))
+
+
+def check_explicit_graph(z):
+    fg, vs = explicit_graph_from_fixture(z)
+    roots = [int(r) for r in z['roots']]
+    fg.initialize(roots[0])
+    fg.treelike_inference(3, roots[1:])
+    for k in z.files:
+        if k.startswith('msg|'):
+            _, a, b = k.split('|')
+            np.testing.assert_allclose(fg.messages[a, b].m[:, 0], z[k], rtol=1e-11, atol=1e-300)
+    marg = np.stack([v.get_marginal().m[:, 0] for v in vs])
+    np.testing.assert_allclose(marg, z['marginals'], rtol=1e-11)
+    np.testing.assert_allclose(fg.get_posterior_probs(), float(z['logp']), rtol=1e-11)
+
+
+def check_per_node_updates(path):
+    """The reference's treelike_inference loop (LBP.py:225-243) written by the CALLER with the per-node API:
+    get_message_schedule + VariableNode / FactorNode.update_message_to, then marginals and the per-factor gradient."""
+    from macaronicusermodeling_b200 import LBP
+    z = np.load(path, allow_pickle=False)
+    fg, spec = graph_from_fixture(z)
+    roots = [int(r) for r in z['roots']]
+    fg.initialize(roots[0])
+    n_sweeps = spec['sweeps'] if fg.isLoopy else 1
+    for it in range(n_sweeps):
+        schedule = fg.get_message_schedule(fg.variables[roots[1 + it]])
+        for frm, to in reversed(schedule):
+            if not (isinstance(to, LBP.FactorNode) and len(to.varset) < 2):
+                frm.update_message_to(to)
+        for to, frm in schedule:
+            if not (isinstance(to, LBP.FactorNode) and len(to.varset) < 2):
+                frm.update_message_to(to)
+    keys = [k for k in z.files if k.startswith('msg|')]
+    assert len(keys) == len(fg.messages)
+    for k in keys:
+        _, a, b = k.split('|')
+        assert np.abs(fg.messages[a, b].m[:, 0] - z[k]).max() < 1e-6, k
+    marg = np.stack([fg.variables[v].get_marginal().m[:, 0] for v in sorted(fg.variables.keys())])
+    assert np.abs(marg - z['marginals']).max() < 1e-6
+    np.testing.assert_allclose(fg.get_posterior_probs(), float(z['logp']), rtol=2e-6)
+    g_ee, g_ed = fg.get_unregularized_gradeint()
+    np.testing.assert_allclose(g_ee, z['g_ee_unreg'], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(g_ed, z['g_ed_unreg'], rtol=1e-4, atol=2e-6)
+
+
+def check_au_remaining(au):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'au_cases_more.npz'), allow_pickle=False)
+    a, b, d1, d2, W, M, phi = (z[k] for k in ('a', 'b', 'd1', 'd2', 'W', 'M', 'phi'))
+    tol = dict(rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(au.induce_s_pointwise_multiply_clip(d1, d2), z['induce_s_pointwise_multiply_clip'], **tol)
+    np.testing.assert_array_equal(au.induce_s(a.copy()), z['induce_s'])
+    np.testing.assert_array_equal(au.induce_s(a[:50].copy()), z['induce_s_small'])
+    np.testing.assert_allclose(au.induce_s_mutliply_clip(a - 0.5, W), z['induce_s_mutliply_clip'], rtol=1e-11, atol=1e-13)
+    d = au.make_sparse_and_dot(a, np.ascontiguousarray(b.T))
+    keys = sorted(d.keys())
+    np.testing.assert_array_equal(np.array(keys, dtype=np.int64), z['msd_keys'])
+    np.testing.assert_allclose(np.array([d[k] for k in keys]), z['msd_vals'], **tol)
+    mz, md = au.sparse_multiply_and_normalize(d, M)
+    np.testing.assert_allclose(mz, z['smn_dense'], rtol=1e-11)
+    np.testing.assert_allclose(np.array([md[k] for k in keys]), z['smn_vals'], rtol=1e-11)
+    np.testing.assert_allclose(au.sd_matrix_multiply(d1, d2.T.copy()), z['sd_matrix_multiply'], rtol=1e-12)
+    np.testing.assert_allclose(au.ss_matix_multiply(d1.T.copy(), d2), z['ss_matix_multiply'], rtol=1e-12)
+    ap = au.make_adapt_phi(phi, 4)
+    np.testing.assert_array_equal(ap, z['make_adapt_phi'])
+    np.testing.assert_array_equal(au.set_adaptation(3, ap.copy(), [1, 3]), z['set_adaptation'])
+    np.testing.assert_array_equal(au.set_adaptation_off(3, au.set_adaptation(3, ap.copy(), [1, 3]), [3]), z['set_adaptation_off'])
+    np.testing.assert_array_equal(au.set_original(phi * 2.0, ap.copy()), z['set_original'])
+    # the first fixture's top-K functions (they are what LBP.py's approximate paths call)
+    y = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'au_cases.npz'), allow_pickle=False)
+    a, b, T = y['a'], y['b'], y['T']
+    np.testing.assert_allclose(au.sparse_vec_mat_dot(a, T), y['sparse_vec_mat_dot_col'], rtol=1e-12)
+    np.testing.assert_allclose(au.sparse_vec_mat_dot(np.ascontiguousarray(a.T), T), y['sparse_vec_mat_dot_row'], rtol=1e-12)
+    sd, ci, ri = au.sparse_dot(a, np.ascontiguousarray(b.T))
+    np.testing.assert_allclose(sd, y['sparse_dot_out'], rtol=1e-12)
+    np.testing.assert_array_equal(np.sort(ci), y['sparse_dot_cidx'])
+    np.testing.assert_array_equal(np.sort(ri), y['sparse_dot_ridx'])
+    spm = au.sparse_pointwise_multiply(sd, ci.astype(np.int64), ri.astype(np.int64), T)
+    np.testing.assert_allclose(spm, y['sparse_pointwise_multiply'], rtol=1e-12)
+    np.testing.assert_allclose(au.sparse_normalize(spm.copy(), ci, ri), y['sparse_normalize'], rtol=1e-11)
+    np.testing.assert_array_equal(au.clip(y['clip_in'].copy()), y['clip'])

@@ -94,3 +94,19 @@ def test_user_adapt_drop_in_trajectory():
 
 def test_adapt_trainer_trajectory():
     lbp_api_checks.check_adapt_trainer(lambda m: __import__('macaronicusermodeling_b200.engine', fromlist=['Engine']).Engine(m))
+
+
+@pytest.mark.parametrize('name', ['toy3', 'tree2', 'revealed', 'k8'])
+def test_per_node_update_api(name):
+    """VariableNode / FactorNode.update_message_to (eager mode): the caller drives the schedule one message at a time"""
+    lbp_api_checks.check_per_node_updates(os.path.join(GOLDEN, 'graph_%s.npz' % name))
+
+
+def test_explicit_potential_table_graph():
+    """PotentialTable(table=...) graphs (run.py / toy style) run through the eager path, pinned on a reference fixture"""
+    lbp_api_checks.check_explicit_graph(np.load(os.path.join(GOLDEN, 'graphx_explicit.npz'), allow_pickle=False))
+
+
+def test_au_all_functions():
+    from macaronicusermodeling_b200.array_utils import c_array_utils as au
+    lbp_api_checks.check_au_remaining(au)

@@ -27,6 +27,23 @@ def test_lbp_api_matches_reference_fixture(path):
     lbp_api_checks.check_lbp_api_fixture(path)
 
 
+def test_explicit_table_graph_initialises_like_the_reference():
+    import numpy as np
+    lbp_api_checks.check_explicit_graph_structure(np.load(os.path.join(GOLDEN, 'graphx_explicit.npz'), allow_pickle=False))
+
+
+def test_au_surface_is_complete():
+    """every function of c_array_utils.pyx exists under the same name"""
+    from macaronicusermodeling_b200.array_utils import c_array_utils as au
+    for name in ('pointwise_multiply', 'clip', 'sparse_normalize', 'normalize', 'induce_s_pointwise_multiply_clip', 'induce_s',
+                 'induce_s_mutliply_clip', 'induce_s_multiply_threshold', 'dense_dot', 'dense_pointwise_multiply',
+                 'make_sparse_and_dot', 'sparse_pointwise_multiply', 'sparse_dot', 'sparse_multiply_and_normalize',
+                 'sd_matrix_multiply', 'sd_pointwise_multiply', 'ss_matix_multiply', 'make_adapt_phi', 'set_adaptation',
+                 'set_adaptation_off', 'set_original', 'sparse_vec_mat_dot'):
+        assert callable(getattr(au, name)), name
+    assert au.K == 100
+
+
 def test_params_roundtrip(tmp_path):
     lbp_api_checks.check_params_roundtrip(tmp_path)
 
