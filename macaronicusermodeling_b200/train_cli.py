@@ -80,6 +80,48 @@ def lower(lines, options, en2id, de2id):
             for l in lines if l.strip()]
 
 
+def domain_of(raw, options):
+    """adaptation domain of a training instance: the user (train.py:160-164) or the experience level (:165-169)"""
+    if options.user_adapt:
+        return str(raw['user_id'])
+    return str(len(raw.get('past_sentences_seen', [])))
+
+
+def read_domains(options):
+    """train.py:488-505: <ti>.users / <ti>.experience list the adaptation domains"""
+    ext = '.users' if options.user_adapt else '.experience'
+    try:
+        return [d.strip() for d in codecs.open(options.training_instances + ext).readlines() if d.strip()]
+    except IOError:
+        sys.stderr.write('%s option can not find %s file. (looked for: %s)\n'
+                         % ('user_adapt' if options.user_adapt else 'experience_adapt', ext, options.training_instances + ext))
+        raise SystemExit(1)
+
+
+def adapt_ext(options):
+    return '.user_adapt' if options.user_adapt else ('.exp_adapt' if options.experience_adapt else '')
+
+
+def read_params_adapt(path, options):
+    """train.py:524-531: try <file><ext>, then <file>"""
+    for cand in (path + adapt_ext(options), path):
+        try:
+            print('trying to read:', cand)
+            return read_params(cand)
+        except IOError:
+            continue
+    raise IOError('no parameter file: ' + path)
+
+
+def d2t_arrays(tr):
+    """AdaptTrainer.domain2theta -> the reference's {('en_en', d): (1,3), ('en_de', d): (1,6)} dict (save_params)"""
+    d2t = {}
+    for d, (te, td) in tr.domain2theta.items():
+        d2t['en_en', d] = np.asarray(te, dtype=np.float64).reshape(1, -1)
+        d2t['en_de', d] = np.asarray(td, dtype=np.float64).reshape(1, -1)
+    return d2t
+
+
 def draw_roots(corpus, sweeps, rng):
     k = np.diff(corpus.var_off)
     return np.array([[rng.randrange(int(kk)) for _ in range(1 + sweeps)] for kk in k], dtype=np.int32)
@@ -135,12 +177,13 @@ def main(argv=None):
     if '' in need or (options.save_params_file == '' and options.load_params_file == '' and options.save_predictions_file == ''):
         error_msg()
         return 1
-    if options.user_adapt or options.experience_adapt:
-        sys.stderr.write('adaptation modes run through trainer.AdaptTrainer / train_compat.batch_sgd, not this CLI yet\n')
+    if options.user_adapt and options.experience_adapt:
+        sys.stderr.write('Currently only supports 1 type of adaptation.')                  # train.py:489-491
         return 1
+    adapt = options.user_adapt or options.experience_adapt
     import torch
     from .engine import Corpus, Engine
-    from .trainer import Trainer, dist_info
+    from .trainer import AdaptTrainer, Trainer, dist_info
     random.seed(options.seed)
     rng = random.Random(options.seed + 1)
     en_domain, de_domain, en2id, de2id, model = load_inputs(options)
@@ -152,9 +195,58 @@ def main(argv=None):
     mode = 'training' if options.save_predictions_file == '' else 'predicting'
     f_en_en_names, f_en_de_names = list(F_EN_EN_NAMES), list(F_EN_DE_NAMES)
     theta_ee, theta_ed = np.zeros((1, 3)), np.zeros((1, 6))
+    d2t_loaded = {}
     if options.load_params_file:
-        f_en_en_names, theta_ee, f_en_de_names, theta_ed, _ = read_params(options.load_params_file)
+        f_en_en_names, theta_ee, f_en_de_names, theta_ed, d2t_loaded = read_params_adapt(options.load_params_file, options)
     rank, world = dist_info()
+    if mode == 'training' and adapt:
+        # --user_adapt / --experience_adapt (train.py:160-173, :224-245, :379-390, :402-409): the sentences of a minibatch are
+        # grouped by domain; each domain's theta builds its own potentials and stays on the rank that owns the domain
+        domains = read_domains(options)
+        raws = [json.loads(l) for l in train_lines]
+        sents = lower(train_lines, options, en2id, de2id)
+        doms = [domain_of(r, options) for r in raws]
+        for d in doms:
+            if d not in domains:
+                domains.append(d)
+        owner = dict((d, i % world) for i, d in enumerate(domains))
+        mb = options.minibatch or (4 if options.cpus.strip() == '' else int(options.cpus))
+        tr = AdaptTrainer(engine, domains, reg_param=float(options.reg_param), ua_scale=float(options.reg_param_ua_scale),
+                          N=len(train_lines))
+        tr.theta_ee, tr.theta_ed = theta_ee.reshape(-1).copy(), theta_ed.reshape(-1).copy()
+        for (ft, d), t in d2t_loaded.items():
+            te, td = tr.domain2theta.get(d, (np.zeros(3), np.zeros(6)))
+            tr.domain2theta[d] = (t.reshape(-1).copy(), td) if ft == 'en_en' else (te, t.reshape(-1).copy())
+        order = list(range(len(sents)))
+        ext = adapt_ext(options)
+        for epoch in range(options.epochs):
+            lr = tr.lr(epoch)
+            random.shuffle(order)
+            logp = 0.0
+            for lo in range(0, len(order), mb):
+                groups = {}
+                for i in order[lo:lo + mb]:
+                    if owner[doms[i]] == rank:
+                        groups.setdefault(doms[i], []).append(sents[i])
+                batches = []
+                for d in sorted(groups):
+                    c = Corpus(groups[d])
+                    batches.append((d, c, draw_roots(c, 3, rng)))
+                red = tr.step_domains(batches, lr)
+                logp += tr.apply(red, lr)[9]
+            print('\nepoch:', epoch)
+            print(f_en_en_names, tr.theta_ee)
+            print(f_en_de_names, tr.theta_ed)
+            print('\ntrain prediction probs:', logp / float(len(sents)))
+            if rank == 0 and options.save_params_file:
+                save_params(codecs.open(options.save_params_file + ext + '.iter' + str(epoch), 'w', 'utf8'),
+                            tr.theta_ee.reshape(1, -1), tr.theta_ed.reshape(1, -1), f_en_en_names, f_en_de_names, d2t_arrays(tr))
+                print('saved params')
+        print('\ntheta final:', tr.theta_ee, tr.theta_ed)
+        if rank == 0 and options.save_params_file:
+            save_params(codecs.open(options.save_params_file + ext, 'w', 'utf8'), tr.theta_ee.reshape(1, -1),
+                        tr.theta_ed.reshape(1, -1), f_en_en_names, f_en_de_names, d2t_arrays(tr))
+        return 0
     if mode == 'training':
         mb = options.minibatch or (4 if options.cpus.strip() == '' else int(options.cpus))     # train_mp.py:493
         tr = Trainer(engine, reg_param=float(options.reg_param), N=len(train_lines))
@@ -193,10 +285,26 @@ def main(argv=None):
                         f_en_en_names, f_en_de_names, {})
         return 0
     # ---- predicting (train.py:678-757)
-    engine.set_theta(theta_ee.reshape(-1), theta_ed.reshape(-1), with_grad=True)
     raw = [json.loads(l) for l in train_lines]
-    lp, preds, dists, (p0, p25, p50, tot) = predict(engine, lower(train_lines, options, en2id, de2id), raw, en_domain,
+    all_sents = lower(train_lines, options, en2id, de2id)
+    if adapt:
+        # every sentence is scored with its domain's theta (train.py:224-245 via create_factor_graph); results keep file order
+        doms = [domain_of(r, options) for r in raw]
+        lp, p0, p25, p50, tot = 0.0, 0, 0, 0, 0
+        preds, dists = [None] * len(raw), [None] * len(raw)
+        for d in sorted(set(doms)):
+            idx = [i for i, x in enumerate(doms) if x == d]
+            engine.set_theta(d2t_loaded['en_en', d].reshape(-1), d2t_loaded['en_de', d].reshape(-1), with_grad=True)
+            l_, pr, di, (a0, a25, a50, at) = predict(engine, [all_sents[i] for i in idx], [raw[i] for i in idx], en_domain,
                                                      de_domain, options, rng, options.quick_predict)
+            lp += l_; p0 += a0; p25 += a25; p50 += a50; tot += at
+            for j, i in enumerate(idx):
+                if pr:
+                    preds[i], dists[i] = pr[j], di[j]
+    else:
+        engine.set_theta(theta_ee.reshape(-1), theta_ed.reshape(-1), with_grad=True)
+        lp, preds, dists, (p0, p25, p50, tot) = predict(engine, all_sents, raw, en_domain, de_domain, options, rng,
+                                                         options.quick_predict)
     if not options.quick_predict:
         with codecs.open(options.save_predictions_file, 'w', 'utf8') as w, \
                 codecs.open(options.save_predictions_file + '.dist', 'w', 'utf8') as wd:
