@@ -298,6 +298,227 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------- CTA-pair kernel
+// The one-CTA kernel above moves (BM + BN) * BK * 4 bytes from L2 into shared memory per 3 * 2 * BM * BN * BK flops:
+// 128 flop/B, i.e. ~9 300 B/clk over 148 SMs at full tensor rate -- above the ~6 300 B/clk the L2 slices deliver, so it
+// is L2-bandwidth-bound (75 % tensor-pipe active measured; the two-pass gradient rows gained only 10 %).
+// A CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256) halves the B traffic: each CTA loads its own 128 rows
+// of A and only HALF of the 256-row B tile, and the tensor cores of both SMs read both halves (192 flop/B).  Per CTA a
+// stage is 64 KB (A.hi A.lo B.hi/2 B.lo/2), so three stages fit.  Rank 0 (leader) issues the MMAs for the pair; both
+// CTAs' TMA loads signal the leader's full barrier (mbarrier address with the peer bit cleared); tcgen05.commit
+// multicasts to the empty / tmem-full barriers of both CTAs; both CTAs' epilogue warps drain their own TMEM (their 128
+// rows) and arrive on the leader's tmem-empty barrier.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the even CTA of a pair
+
+template <int STAGES>
+struct PairCfg {
+    static constexpr int BN = 256, BK = 64;
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int A_BYTES = BM * BK * 2;                // 128 rows of A (this CTA's half of M = 256)
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {            // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t rank) {   // arrive on the leader CTA's barrier
+    if (rank == 0) {
+        mbar_arrive(bar);
+    } else {
+        asm volatile(
+            "{\n\t.reg .b32 rem;\n\t"
+            "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+            "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}"
+            ::"r"(bar), "r"(0) : "memory");
+    }
+}
+
+template <int STAGES, int CHUNK_KB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES>::THREADS, 1)
+gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                           float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
+                           int m_pairs, int n_tiles, int a_terms, int *err_flag) {
+    using C = PairCfg<STAGES>;
+    constexpr int BN = C::BN, BK = C::BK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (uint32_t)(2 * STAGES + 2 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                      // 0 = leader of the pair
+    const int pair = blockIdx.x >> 1;
+
+    // rasterisation: GROUP_M / 2 pairs deep (the same 16 M-tiles as the one-CTA kernel), then along n
+    constexpr int GROUP_P = GROUP_M / 2;
+    const int per_group = GROUP_P * n_tiles;
+    const int grp = pair / per_group, in_grp = pair % per_group;
+    const int first_p = grp * GROUP_P;
+    const int gsize = min(GROUP_P, m_pairs - first_p);
+    const int p_blk = first_p + in_grp % gsize, n_blk = in_grp / gsize;
+    const int m_blk = 2 * p_blk + (int)rank;                      // this CTA's 128-row tile
+    const int num_kb = (V + BK - 1) / BK;
+    const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
+    const int n_valid = min(BN, V - n_blk * BN);
+    const int n_cur = (n_valid + 15) & ~15;                       // UMMA N of this tile (cta_group::2: multiples of 16)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * C::EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    cluster_sync_all();                                           // the peer's barriers exist before anything targets them
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            const int row_a = a_row0 + m_blk * BM;
+            const int row_b = n_blk * BN + (int)rank * (n_cur >> 1);      // this CTA's half of the N extent in use
+            const uint32_t bytes_cta = (uint32_t)(a_terms == 2 ? C::STAGE_BYTES : C::STAGE_BYTES - C::A_BYTES);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u, err_flag, 1);
+                if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes_cta);      // bytes of BOTH CTAs land on the leader
+                const uint32_t lb = full_bar(s) & PEER_BIT_MASK;
+                const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
+                tma_load_2d_pair(&tm_a_hi, lb, st, kb * BK, row_a);
+                if (a_terms == 2) tma_load_2d_pair(&tm_a_lo, lb, st + C::A_BYTES, kb * BK, row_a);
+                tma_load_2d_pair(&tm_b_hi, lb, st + 2 * C::A_BYTES, kb * BK, row_b);
+                tma_load_2d_pair(&tm_b_lo, lb, st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
+            }
+        } else if (warp == 1 && lane == 0 && rank == 0) {
+            // ===================== MMA issuer (leader only, for both SMs) =====================
+            const uint32_t idesc = umma_idesc_f16(2 * BM, n_cur);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                const int chunk = kb / CHUNK_KB, in_chunk = kb % CHUNK_KB;
+                const int buf = chunk & 1;
+                if (in_chunk == 0) {                              // both CTAs have drained this accumulator
+                    mbar_wait(tempty_bar(buf), ((uint32_t)(chunk >> 1) & 1u) ^ 1u, err_flag, 4);
+                    tc_fence_after();
+                }
+                mbar_wait(full_bar(s), ph, err_flag, 2);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + C::A_BYTES);
+                const uint64_t b_hi = umma_desc_kmajor<BK>(st + 2 * C::A_BYTES);
+                const uint64_t b_lo = umma_desc_kmajor<BK>(st + 2 * C::A_BYTES + C::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                    tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
+                    tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    if (a_terms == 2) tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                tc_commit_pair(empty_bar(s));                     // frees the stage in both CTAs
+                if (in_chunk == CHUNK_KB - 1 || kb == num_kb - 1) tc_commit_pair(tfull_bar(buf));
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs): drain every chunk into fp32 registers =====================
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+        for (int c = 0; c < num_chunks; ++c) {
+            const int buf = c & 1;
+            mbar_wait(tfull_bar(buf), (uint32_t)(c >> 1) & 1u, err_flag, 3);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t r[32];
+                tmem_ld_32x32(t0 + (uint32_t)(j * 32), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty_bar(buf), rank);
+        }
+        const int m = m_blk * BM + q * 32 + lane;
+        if (m < n_rows) {
+            float *drow = D + (d_row0 + (int64_t)m) * (int64_t)ldd;
+            const int n0 = n_blk * BN + half * 128;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int nc = n0 + 4 * j;
+                if (nc < ldd) {
+                    float4 o;                                     // columns >= V (row padding) are written as zeros
+                    o.x = nc + 0 < V ? acc[4 * j + 0] * alpha : 0.f; o.y = nc + 1 < V ? acc[4 * j + 1] * alpha : 0.f;
+                    o.z = nc + 2 < V ? acc[4 * j + 2] * alpha : 0.f; o.w = nc + 3 < V ? acc[4 * j + 3] * alpha : 0.f;
+                    *reinterpret_cast<float4 *>(drow + nc) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // neither CTA frees tensor memory the pair still uses
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -388,6 +609,36 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     return MLBP_OK;
 }
 
+template <int STAGES, int CHUNK_KB>
+static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
+                       const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
+                       cudaStream_t st) {
+    using C = PairCfg<STAGES>;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = cached_map(&ma_hi, A_hi, a_rows_total, V, ldv, BM, C::BK)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&ma_lo, A_lo, a_rows_total, V, ldv, BM, C::BK)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&mb_hi, B_hi, V, V, ldv, C::BN / 2, C::BK)) != MLBP_OK) return rc;
+    if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, C::BN / 2, C::BK)) != MLBP_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_pair_kernel<STAGES, CHUNK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::SMEM_BYTES));
+        attr_set = true;
+    }
+    if (!g_err_flag) {
+        int *h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped) == cudaSuccess) { *h = 0; g_err_flag = h; }
+    }
+    int *d_flag = nullptr;
+    if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
+    const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
+    gemm_split_f16_pair_kernel<STAGES, CHUNK_KB><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, a_terms, d_flag);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
 }  // namespace mlbp
 
 using namespace mlbp;
@@ -411,11 +662,14 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
     impl &= ~MLBP_GEMM_A_HI_ONLY;
     if (impl == 1)
         return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
-    // impl 0: product configuration.  impl 10..: tuning variants exposed for scripts/gemm_probe.py only.
+    // impl 0: product configuration (CTA-pair kernel for large V).  impl 10..: one-CTA variants, impl 30..: CTA-pair
+    // variants, exposed for scripts/gemm_probe.py and the kernel tests only.
 #define MLBP_TC(BN_, ST_, CH_) \
     return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st)
     switch (impl) {
-        case 0: if (V > 2048) { MLBP_TC(256, 2, 2); } else { MLBP_TC(128, 3, 2); }
+        case 0:                                       // product configuration
+            if (V > 2048) return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
+            MLBP_TC(128, 3, 2);
         case 10: MLBP_TC(256, 2, 1);
         case 11: MLBP_TC(256, 2, 2);
         case 12: MLBP_TC(256, 2, 4);
@@ -424,6 +678,9 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
+        case 30: return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
+        case 31: return launch_pair<3, 1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
+        case 32: return launch_pair<2, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
         case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
         case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
         case 22: return launch_tc<128, 6, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);

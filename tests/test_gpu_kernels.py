@@ -51,7 +51,7 @@ def gemm(lib, A, B, M, V, impl, a_row0=0, alpha=1.0):
 
 
 @pytest.mark.parametrize('M,V', [(128, 256), (5, 200), (300, 1000), (131, 2112), (700, 2500), (257, 4100)])
-@pytest.mark.parametrize('impl', [1, 0], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('impl', [1, 0, 30, 11], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
 def test_message_gemm_matches_float64(lib, M, V, impl):
     rng = np.random.default_rng(M * 7 + V)
     A = rng.random((M + 9, V)) * 2.0 ** 14 / V * 2       # message-like magnitudes (2^14 * normalised)
@@ -65,7 +65,7 @@ def test_message_gemm_matches_float64(lib, M, V, impl):
 
 
 @pytest.mark.parametrize('M,V', [(131, 2112), (300, 1000), (257, 4100)])
-@pytest.mark.parametrize('impl', [1, 0], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('impl', [1, 0, 30, 11], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
 def test_gradient_gemm_a_hi_only(lib, M, V, impl):
     """MLBP_GEMM_A_HI_ONLY (gradient rows): exactly  A_hi . (B_hi + B_lo)'  -- the A_lo plane must not contribute"""
     rng = np.random.default_rng(M + V)
