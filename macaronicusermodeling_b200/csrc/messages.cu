@@ -28,6 +28,8 @@ namespace mlbp {
 
 constexpr int K3_THREADS = 256;
 constexpr int K3_WARPS = K3_THREADS / 32;
+constexpr int K3R_THREADS = 256;                  // resident kernel (224 = three balanced passes over 640 column pairs: measured no faster)
+constexpr int K3R_WARPS = K3R_THREADS / 32;
 constexpr int K3_RESIDENT_SMEM = 100 * 1024;     // per CTA: two CTAs per SM keep loads and stores overlapped
 
 __global__ void fill_uniform_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int ldv, int V,
@@ -183,7 +185,7 @@ __device__ __forceinline__ void k3_copy_extras(const int *__restrict__ s_nd, con
 __device__ __forceinline__ uint32_t k3_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int NIN>
-__global__ void __launch_bounds__(K3_THREADS, 2)
+__global__ void __launch_bounds__(K3R_THREADS, 2)
 var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                               const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                               const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
@@ -200,9 +202,9 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     __shared__ const float *s_src[2][NIN + 1];                // [buffer][0] = U row, [1 + j] = input j (nullptr: ones)
     __shared__ int s_d0[2][NIN], s_nd[2][NIN];
     __shared__ size_t s_first[2][NIN];
-    __shared__ double s_warp[K3_WARPS][NIN];
-    __shared__ double s_part[NIN];
-    __shared__ double s_gather[8][NIN];
+    __shared__ double s_warp[K3R_WARPS][NIN];
+    __shared__ double s_gather[2][8][NIN];                     // [exchange parity][source rank][output]
+    __shared__ __align__(8) unsigned long long s_gbar[2];
     __shared__ float s_scale[NIN];
     cg::cluster_group cl = cg::this_cluster();
     const unsigned C = cl.num_blocks(), q = cl.block_rank();
@@ -247,15 +249,21 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
 
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+        for (int k = 0; k < 2; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k3_smem_u32(&s_gbar[k])), "r"(1) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(k3_smem_u32(&s_gbar[k])), "r"((uint32_t)(NIN * C * sizeof(double))) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    cl.sync();                                                     // once: every peer's barriers exist before the first push
+    int it = 0;
     int g = blockIdx.x / C, b = 0;
     fetch_head(g);
     if (g < n_groups) fetch_body(0);
     fetch_head(g + n_clusters);
     __syncthreads();
     uint32_t parity = 0;
-    bool first = true;
     // Two adjacent columns per thread: 8-byte shared-memory loads, packed fp32x2 multiplies (FMUL2 on sm_100), fp16x2
     // conversions and 4-byte stores.  With 100 KB of shared memory per CTA only 16 warps are resident per SM, so the
     // loops are written as straight-line code (no branch on a value loaded inside the loop): measured with clock64
@@ -295,7 +303,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         float acc[NIN];
 #pragma unroll
         for (int j = 0; j < NIN; ++j) acc[j] = 0.f;
-        for (int e2 = threadIdx.x; e2 < npair; e2 += K3_THREADS) {
+        for (int e2 = threadIdx.x; e2 < npair; e2 += K3R_THREADS) {
             const float2 *col = reinterpret_cast<const float2 *>(s_rows) + e2;
             const bool odd = 2 * e2 + 1 >= ncol;                  // the second column is padding
             float2 d[NIN];
@@ -320,27 +328,46 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         }
         __syncthreads();
         K3_TICK(3);
-        if (!first) cl.barrier_wait();                             // peers have read this CTA's previous partial sums
-        if (threadIdx.x < NIN) {
-            double t = 0.0;
+        // Exchange of the partial sums: every CTA PUSHES its NIN partial sums into each peer's gather buffer with
+        // st.async, which completes on the PEER's mbarrier; a CTA only waits on its own barrier.  No cluster barrier in
+        // the loop: barrier.cluster.arrive.release made every iteration wait for the previous phase-2 stores to drain
+        // (7 % membar + 6 % cluster-barrier stalls in the ncu source view).  Buffers alternate by iteration parity; a
+        // CTA can run at most one exchange ahead of a peer, because finishing exchange i needs the peer's sums of i.
+        {
+            const int par = it & 1;
+            for (int i = threadIdx.x; i < NIN * (int)C; i += K3R_THREADS) {
+                const int r = i / NIN, j = i - r * NIN;
+                double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < K3_WARPS; ++w) t += s_warp[w][threadIdx.x];
-            s_part[threadIdx.x] = t;
-        }
-        cl.sync();
-        for (int i = threadIdx.x; i < NIN * (int)C; i += K3_THREADS) {
-            const int r = i / NIN, j = i - r * NIN;
-            s_gather[r][j] = *cl.map_shared_rank(&s_part[j], r);
+                for (int w = 0; w < K3R_WARPS; ++w) t += s_warp[w][j];
+                const uint32_t dst = k3_smem_u32(&s_gather[par][q][j]), rb = k3_smem_u32(&s_gbar[par]);
+                asm volatile(
+                    "{\n\t.reg .b32 ra, rm;\n\t"
+                    "mapa.shared::cluster.u32 ra, %0, %2;\n\t"
+                    "mapa.shared::cluster.u32 rm, %1, %2;\n\t"
+                    "st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [ra], %3, [rm];\n\t}"
+                    ::"r"(dst), "r"(rb), "r"(r), "l"(__double_as_longlong(t)) : "memory");
+            }
+            const uint32_t gb = k3_smem_u32(&s_gbar[par]), gpar = (uint32_t)(it >> 1) & 1u;
+            uint32_t ok = 0;
+            const unsigned long long t0 = clock64();
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(gb), "r"(gpar) : "memory");
+                if (!ok && clock64() - t0 > 4000000000ull) __trap();
+            }
+            if (threadIdx.x < NIN) {
+                double t = 0.0;
+                for (unsigned r = 0; r < C; ++r) t += s_gather[par][r][threadIdx.x];     // fixed order: deterministic
+                // sum <= 0 or non-finite -> uniform (Message.renormalize, LBP.py:650-657): flagged by a negative scale
+                s_scale[threadIdx.x] = (t > 0.0 && isfinite(t)) ? (float)(ldexp(1.0, MLBP_A_SCALE_LOG2) / t) : -1.0f;
+            }
         }
         __syncthreads();
-        cl.barrier_arrive();                                       // done with the peers' shared memory
-        if (threadIdx.x < NIN) {
-            double t = 0.0;
-            for (unsigned r = 0; r < C; ++r) t += s_gather[r][threadIdx.x];      // fixed order: deterministic
-            // sum <= 0 or non-finite -> uniform (Message.renormalize, LBP.py:650-657): flagged by a negative scale
-            s_scale[threadIdx.x] = (t > 0.0 && isfinite(t)) ? (float)(ldexp(1.0, MLBP_A_SCALE_LOG2) / t) : -1.0f;
-        }
-        __syncthreads();
+        if (threadIdx.x == 0)                                      // re-arm this parity's barrier for exchange it + 2
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(k3_smem_u32(&s_gbar[it & 1])), "r"((uint32_t)(NIN * C * sizeof(double))) : "memory");
+        ++it;
         K3_TICK(4);
 
         // ---- phase 2: recompute from shared memory, normalise, split, scatter to the consuming GEMM blocks
@@ -351,7 +378,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
             omask |= (nd > 0 ? 1u : 0u) << j;
             multi |= (nd > 1 ? 1u : 0u) << j;
         }
-        for (int e2 = threadIdx.x; e2 < npair; e2 += K3_THREADS) {
+        for (int e2 = threadIdx.x; e2 < npair; e2 += K3R_THREADS) {
             const float2 *col = reinterpret_cast<const float2 *>(s_rows) + e2;
             const bool odd = 2 * e2 + 1 >= ncol;
             float2 d[NIN];
@@ -362,25 +389,40 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
 #pragma unroll
             for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
             float2 suf = make_float2(1.f, 1.f);
+            // one output: scale, split into fp16 hi / lo pairs, store to the first reader's row
+            auto emit = [&](int j, float2 sufj) {
+                const float sc = s_scale[j];
+                float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
+                if (!(sc > 0.f)) x = make_float2(uni, uni);
+                const __half2 hi = __float22half2_rn(x);
+                const float2 back = __half22float2(hi);
+                const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
+                const size_t o = s_first[b][j] + 2 * (size_t)e2;              // even: 4-byte aligned
+                if (!odd) {
+                    *reinterpret_cast<__half2 *>(A_hi + o) = hi;
+                    *reinterpret_cast<__half2 *>(A_lo + o) = lo;
+                } else {
+                    A_hi[o] = __low2half(hi);
+                    A_lo[o] = __low2half(lo);
+                }
+            };
+            // Outputs are walked four at a time: when all four have a reader (the common case) their chains are emitted
+            // as ONE straight-line block, so the four dependent load -> multiply -> convert -> store chains overlap
+            // instead of each paying its latency behind a branch (only 16 warps per SM are resident to hide it).
 #pragma unroll
-            for (int j = NIN - 1; j >= 0; --j) {
-                if ((omask >> j) & 1u) {                           // register test: no load feeds this branch
-                    const float sc = s_scale[j];
-                    float2 x = __fmul2_rn(__fmul2_rn(pre[j], suf), make_float2(sc, sc));
-                    if (!(sc > 0.f)) x = make_float2(uni, uni);
-                    const __half2 hi = __float22half2_rn(x);
-                    const float2 back = __half22float2(hi);
-                    const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
-                    const size_t o = s_first[b][j] + 2 * (size_t)e2;          // even: 4-byte aligned
-                    if (!odd) {
-                        *reinterpret_cast<__half2 *>(A_hi + o) = hi;
-                        *reinterpret_cast<__half2 *>(A_lo + o) = lo;
-                    } else {
-                        A_hi[o] = __low2half(hi);
-                        A_lo[o] = __low2half(lo);
+            for (int j0 = NIN - 1; j0 >= 0; j0 -= 4) {
+                if (j0 >= 3 && ((omask >> (j0 - 3)) & 0xFu) == 0xFu) {
+                    const float2 s0 = suf, s1 = __fmul2_rn(s0, d[j0]), s2 = __fmul2_rn(s1, d[j0 - 1]),
+                                 s3 = __fmul2_rn(s2, d[j0 - 2]);
+                    emit(j0, s0); emit(j0 - 1, s1); emit(j0 - 2, s2); emit(j0 - 3, s3);
+                    suf = __fmul2_rn(s3, d[j0 - 3]);
+                } else {
+#pragma unroll
+                    for (int j = j0; j > j0 - 4 && j >= 0; --j) {
+                        if ((omask >> j) & 1u) emit(j, suf);           // register test: no load feeds this branch
+                        suf = __fmul2_rn(suf, d[j]);
                     }
                 }
-                suf = __fmul2_rn(suf, d[j]);
             }
         }
         if (multi) {                                               // block-uniform
@@ -389,13 +431,13 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         }
         __syncthreads();                                           // shared memory is reused by the next group
         K3_TICK(5);
-        first = false;
     }
 #ifdef MLBP_K3_STAGE_TIMES
     if (dbg && threadIdx.x == 0)
         for (int i = 0; i < 6; ++i) dbg[(size_t)blockIdx.x * 6 + i] = tacc[i];
 #endif
-    if (!first) cl.barrier_wait();                                 // no CTA leaves while a peer may still read it
+    // A CTA leaves its last exchange only after every peer's sums for it have ARRIVED here, and nothing is ever read from
+    // a peer, so no CTA can exit while another still needs its shared memory.
 }
 
 // Top-K masking of message rows: the reference's approximate paths (use_approx_inference / use_approx_beliefs,
@@ -536,7 +578,7 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     const size_t smem = (size_t)(NIN + 1) * S * sizeof(float);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)C * 148u * 2u);
-    cfg.blockDim = dim3(K3_THREADS);
+    cfg.blockDim = dim3(K3R_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
