@@ -309,7 +309,7 @@ def ours(a):
     flops = 2.0 * gemm_rows * a.V * a.V
     ach = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     traffic, traffic_note = None, None
-    tr_path = os.path.join(REPO, 'profiles', 'r1b_k4_traffic.json')
+    tr_path = os.path.join(REPO, 'profiles', 'r1c_k4_traffic.json')
     if os.path.exists(tr_path) and a.V == 10000:
         tr = json.load(open(tr_path))
         traffic = tr['dram_bytes_per_launch']
