@@ -264,6 +264,13 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
             const int32_t *r = roots + (size_t)gi * (1 + sweeps);
             for (int i = 0; i <= sweeps; ++i)
                 if (r[i] < 0 || r[i] >= g.nv) { err[c] = 3; return; }
+            {   // one allocation per vector: 4 np updates per sweep, a variable update reads deg - 1 messages
+                size_t reads = 0;
+                for (int v = 0; v < g.nv; ++v) reads += g.facset[v].size() * g.facset[v].size();
+                g.ops.reserve((size_t)4 * g.np * sweeps + 8);
+                g.inputs.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
+                g.in_edge.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
+            }
             build_sequence(g, r, sweeps);
             // liveness, reverse pass: an update is live iff a live update (or a final stage) reads its result
             needed.assign(g.ops.size(), 0);
@@ -456,6 +463,16 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     Plan *P = new (std::nothrow) Plan();
     if (!P) { mlbp::set_error("plan_compile: out of memory"); return MLBP_ERR_ALLOC; }
     std::vector<int32_t> &B = P->blob;
+    {
+        size_t total = H_WORDS + (size_t)n_levels * LEV_WORDS + 64;           // one allocation for the whole blob
+        for (const ChunkOut &co : CO) {
+            for (int L = 0; L <= n_levels; ++L)
+                total += co.grp_u[L].size() + co.grp_off[L].size() + co.in_row[L].size() + co.dest_off[L].size() +
+                         co.dest[L].size() + co.first[L].size() + 24;
+            total += co.init_rows.size() + 9 * co.pair_c.size() + co.mu.size() + co.moff.size() + co.min_.size() + 16;
+        }
+        B.reserve(total);
+    }
     B.assign(H_WORDS + (size_t)n_levels * LEV_WORDS, 0);
     auto append = [&](const std::vector<int32_t> &v) { int32_t o = (int32_t)B.size(); B.insert(B.end(), v.begin(), v.end()); return o; };
     // concatenation of one member over the chunks; `shift` adds a running offset (CSR offsets) and prepends a 0
