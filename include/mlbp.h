@@ -118,15 +118,16 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   group g multiplies U[grp_u[g]] with the factor->variable rows D[in_row[i]], i in [grp_off[g], grp_off[g+1]);
  *   for every i with destinations it emits the leave-one-out product (all inputs except i), renormalised
  *   (sum <= 0 or non-finite -> uniform, LBP.py:650-657; nan_to_num LBP.py:729), scaled by 2^14 and split into
- *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]); first_dest[i] = dest[dest_off[i]] (or -1 if the range is empty),
- *   stored per slot so that the kernels need one index load less.  in_row < 0 means "uniform message": the kernels read the
+ *   A_hi/A_lo rows dest[dest_off[i] .. dest_off[i+1]); first_dest[i] / second_dest[i] = dest[dest_off[i]] /
+ *   dest[dest_off[i] + 1] (-1 if absent), stored per slot so that the kernels need no dependent index load for the two
+ *   readers a message usually has (a message GEMM row and a gradient-stage row).  in_row < 0 means "uniform message": the kernels read the
  *   constant-one row D[0] in its place (messages are scale-free), so the caller keeps D row 0 filled with 1.0f.
  *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
  *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow). */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
-                       const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest, const float *U,
-                       const float *D, int ldv, int V, void *A_hi, void *A_lo, int max_in, float range_log2,
-                       void *stream);
+                       const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
+                       const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
+                       void *A_lo, int max_in, float range_log2, void *stream);
 /* Approximate paths (use_approx_inference LBP.py:506-507, :515-516 -> au.sparse_vec_mat_dot pyx:193-205;
  *   use_approx_beliefs LBP.py:554-563 -> au.sparse_dot / sparse_pointwise_multiply / sparse_normalize pyx:108-129, :23-26):
  *   keep the K largest entries of each of the n_rows operand rows A[row0 ..], zero the others (K = 100 in the reference);

@@ -18,7 +18,7 @@ _SIGNATURES = {
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
     'mlbp_fill_uniform_rows': 'ppiipipp',
-    'mlbp_var_to_factor': 'ipppppp' + 'ppii' + 'ppifp',
+    'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppifp',
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppfp',

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <cooperative_groups.h>
+#include <cuda/std/type_traits>
 
 #include "common.cuh"
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(K3_THREADS, OCC)
 var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                      const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
-                     const float *__restrict__ U, const float *__restrict__ D, int ldv, int V,
+                     const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V,
                      __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
     __shared__ const float *s_src[NMAX];
     __shared__ int s_d0[NMAX], s_nd[NMAX];
@@ -152,9 +153,9 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     }
 }
 
-// Messages with more than one reader (final versions read by a message GEMM row and by the gradient stage): the slice
-// just written to the first reader's row is copied into the other readers' rows (L1/L2 hits).  The caller puts a
-// __syncthreads() between the writes and this copy.
+// Messages with more than TWO readers (the first two are written directly): the slice just written to the first reader's
+// row is copied into the third and further readers' rows (L1/L2 hits).  The caller puts a __syncthreads() between the
+// writes and this copy.
 template <int NIN>
 __device__ __forceinline__ void k3_copy_extras(const int *__restrict__ s_nd, const int *__restrict__ s_d0,
                                                const size_t *__restrict__ s_first, const int32_t *__restrict__ dest,
@@ -163,7 +164,7 @@ __device__ __forceinline__ void k3_copy_extras(const int *__restrict__ s_nd, con
     for (int j = 0; j < NIN; ++j) {
         const int nd = s_nd[j];
 #pragma unroll 1
-        for (int t = 1; t < nd; ++t) {
+        for (int t = 2; t < nd; ++t) {
             const size_t src = s_first[j], dst = (size_t)dest[s_d0[j] + t] * ldv + col0;
             for (int e = threadIdx.x; e < ncol; e += K3_THREADS) {
                 A_hi[dst + e] = A_hi[src + e];
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(K3R_THREADS, 2)
 var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                               const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                               const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
-                              const float *__restrict__ U, const float *__restrict__ D, int ldv, int V, int S,
+                              const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V, int S,
                               __half *__restrict__ A_hi, __half *__restrict__ A_lo, long long *dbg) {
 #ifdef MLBP_K3_STAGE_TIMES                                      // scripts/k3_probe.py: cycles per stage, per CTA
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -201,7 +202,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ const float *s_src[2][NIN + 1];                // [buffer][0] = U row, [1 + j] = input j (nullptr: ones)
     __shared__ int s_d0[2][NIN], s_nd[2][NIN];
-    __shared__ size_t s_first[2][NIN];
+    __shared__ size_t s_first[2][NIN], s_second[2][NIN];
     __shared__ double s_warp[K3R_WARPS][NIN];
     __shared__ double s_gather[2][8][NIN];                     // [exchange parity][source rank][output]
     __shared__ __align__(8) unsigned long long s_gbar[2];
@@ -239,10 +240,11 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                 // group moves the same number of bytes and phase 1 / 2 need no special cases
                 s_src[b][1 + j] = D + (size_t)(r >= 0 ? r : 0) * ldv + col0;
                 const int d0 = j < n ? dest_off[i0 + j] : 0, d1 = j < n ? dest_off[i0 + j + 1] : 0;
-                const int f = j < n ? first_dest[i0 + j] : -1;
+                const int f = j < n ? first_dest[i0 + j] : -1, f2 = j < n ? second_dest[i0 + j] : -1;
                 s_d0[b][j] = d0;
                 s_nd[b][j] = d1 - d0;
                 s_first[b][j] = f >= 0 ? (size_t)f * ldv + col0 : 0;
+                s_second[b][j] = f2 >= 0 ? (size_t)f2 * ldv + col0 : 0;
             }
         }
     };
@@ -371,61 +373,78 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         K3_TICK(4);
 
         // ---- phase 2: recompute from shared memory, normalise, split, scatter to the consuming GEMM blocks
-        unsigned omask = 0, multi = 0;                             // bit j: message j has a reader / several readers
+        unsigned omask = 0, multi = 0, many = 0;                   // bit j: message j has >= 1 / >= 2 / >= 3 readers
 #pragma unroll
         for (int j = 0; j < NIN; ++j) {
             const int nd = s_nd[b][j];
             omask |= (nd > 0 ? 1u : 0u) << j;
             multi |= (nd > 1 ? 1u : 0u) << j;
+            many |= (nd > 2 ? 1u : 0u) << j;
         }
-        for (int e2 = threadIdx.x; e2 < npair; e2 += K3R_THREADS) {
-            const float2 *col = reinterpret_cast<const float2 *>(s_rows) + e2;
-            const bool odd = 2 * e2 + 1 >= ncol;
-            float2 d[NIN];
-#pragma unroll
-            for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * (S >> 1)];
-            float2 pre[NIN];
-            float2 p = col[0];
-#pragma unroll
-            for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
-            float2 suf = make_float2(1.f, 1.f);
-            // one output: scale, split into fp16 hi / lo pairs, store to the first reader's row
-            auto emit = [&](int j, float2 sufj) {
-                const float sc = s_scale[j];
-                float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
-                if (!(sc > 0.f)) x = make_float2(uni, uni);
-                const __half2 hi = __float22half2_rn(x);
-                const float2 back = __half22float2(hi);
-                const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
-                const size_t o = s_first[b][j] + 2 * (size_t)e2;              // even: 4-byte aligned
-                if (!odd) {
-                    *reinterpret_cast<__half2 *>(A_hi + o) = hi;
-                    *reinterpret_cast<__half2 *>(A_lo + o) = lo;
-                } else {
-                    A_hi[o] = __low2half(hi);
-                    A_lo[o] = __low2half(lo);
-                }
-            };
-            // Outputs are walked four at a time: when all four have a reader (the common case) their chains are emitted
-            // as ONE straight-line block, so the four dependent load -> multiply -> convert -> store chains overlap
-            // instead of each paying its latency behind a branch (only 16 warps per SM are resident to hide it).
-#pragma unroll
-            for (int j0 = NIN - 1; j0 >= 0; j0 -= 4) {
-                if (j0 >= 3 && ((omask >> (j0 - 3)) & 0xFu) == 0xFu) {
-                    const float2 s0 = suf, s1 = __fmul2_rn(s0, d[j0]), s2 = __fmul2_rn(s1, d[j0 - 1]),
-                                 s3 = __fmul2_rn(s2, d[j0 - 2]);
-                    emit(j0, s0); emit(j0 - 1, s1); emit(j0 - 2, s2); emit(j0 - 3, s3);
-                    suf = __fmul2_rn(s3, d[j0 - 3]);
-                } else {
-#pragma unroll
-                    for (int j = j0; j > j0 - 4 && j >= 0; --j) {
-                        if ((omask >> j) & 1u) emit(j, suf);           // register test: no load feeds this branch
-                        suf = __fmul2_rn(suf, d[j]);
+        // two instantiations of the loop: levels whose messages all have one reader (most) do not carry the code and
+        // registers of the second store
+        auto phase2 = [&](auto second_tag) {
+            constexpr bool SECOND = decltype(second_tag)::value;
+            for (int e2 = threadIdx.x; e2 < npair; e2 += K3R_THREADS) {
+                const float2 *col = reinterpret_cast<const float2 *>(s_rows) + e2;
+                const bool odd = 2 * e2 + 1 >= ncol;
+                float2 d[NIN];
+    #pragma unroll
+                for (int j = 0; j < NIN; ++j) d[j] = col[(1 + j) * (S >> 1)];
+                float2 pre[NIN];
+                float2 p = col[0];
+    #pragma unroll
+                for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
+                float2 suf = make_float2(1.f, 1.f);
+                // one output: scale, split into fp16 hi / lo pairs, store to the first reader's row
+                auto emit = [&](int j, float2 sufj) {
+                    const float sc = s_scale[j];
+                    float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
+                    if (!(sc > 0.f)) x = make_float2(uni, uni);
+                    const __half2 hi = __float22half2_rn(x);
+                    const float2 back = __half22float2(hi);
+                    const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
+                    const size_t o = s_first[b][j] + 2 * (size_t)e2;              // even: 4-byte aligned
+                    if (!odd) {
+                        *reinterpret_cast<__half2 *>(A_hi + o) = hi;
+                        *reinterpret_cast<__half2 *>(A_lo + o) = lo;
+                    } else {
+                        A_hi[o] = __low2half(hi);
+                        A_lo[o] = __low2half(lo);
+                    }
+                    if (SECOND && ((multi >> j) & 1u)) {                // second reader (final versions: message GEMM + gradient stage)
+                        const size_t o2 = s_second[b][j] + 2 * (size_t)e2;
+                        if (!odd) {
+                            *reinterpret_cast<__half2 *>(A_hi + o2) = hi;
+                            *reinterpret_cast<__half2 *>(A_lo + o2) = lo;
+                        } else {
+                            A_hi[o2] = __low2half(hi);
+                            A_lo[o2] = __low2half(lo);
+                        }
+                    }
+                };
+                // Outputs are walked four at a time: when all four have a reader (the common case) their chains are emitted
+                // as ONE straight-line block, so the four dependent load -> multiply -> convert -> store chains overlap
+                // instead of each paying its latency behind a branch (only 16 warps per SM are resident to hide it).
+    #pragma unroll
+                for (int j0 = NIN - 1; j0 >= 0; j0 -= 4) {
+                    if (j0 >= 3 && ((omask >> (j0 - 3)) & 0xFu) == 0xFu) {
+                        const float2 s0 = suf, s1 = __fmul2_rn(s0, d[j0]), s2 = __fmul2_rn(s1, d[j0 - 1]),
+                                     s3 = __fmul2_rn(s2, d[j0 - 2]);
+                        emit(j0, s0); emit(j0 - 1, s1); emit(j0 - 2, s2); emit(j0 - 3, s3);
+                        suf = __fmul2_rn(s3, d[j0 - 3]);
+                    } else {
+    #pragma unroll
+                        for (int j = j0; j > j0 - 4 && j >= 0; --j) {
+                            if ((omask >> j) & 1u) emit(j, suf);           // register test: no load feeds this branch
+                            suf = __fmul2_rn(suf, d[j]);
+                        }
                     }
                 }
             }
-        }
-        if (multi) {                                               // block-uniform
+        };
+        if (multi) phase2(cuda::std::true_type{}); else phase2(cuda::std::false_type{});
+        if (many) {                                                // block-uniform, rare: third and further readers
             __syncthreads();                                       // the copy below reads elements other threads wrote
             k3_copy_extras<NIN>(s_nd[b], s_d0[b], s_first[b], dest, ldv, col0, ncol, A_hi, A_lo);
         }
@@ -566,8 +585,8 @@ extern "C" void mlbp_debug_k3_times(long long *p) { g_k3_dbg = p; }
 template <int NIN>
 static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, const int32_t *grp_u,
                                    const int32_t *grp_off, const int32_t *in_row, const int32_t *dest_off,
-                                   const int32_t *dest, const int32_t *first_dest, const float *U, const float *D,
-                                   int ldv, int V, __half *A_hi, __half *A_lo) {
+                                   const int32_t *dest, const int32_t *first_dest, const int32_t *second_dest, const float *U,
+                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo) {
     static bool configured = false;
     auto kern = var_to_factor_resident_kernel<NIN>;
     if (!configured) {
@@ -597,18 +616,18 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     }
     const int n_clusters = n_groups < resident[C] ? n_groups : resident[C];
     cfg.gridDim = dim3((unsigned)n_clusters * (unsigned)C);
-    return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, S,
-                              A_hi, A_lo, g_k3_dbg);
+    return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv,
+                              V, S, A_hi, A_lo, g_k3_dbg);
 }
 
 constexpr int K3_RESIDENT_MAX_IN = 24;
 
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                                   const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
-                                  const float *U, const float *D, int ldv, int V, void *A_hi, void *A_lo, int max_in,
-                                  float range_log2, void *stream) {
+                                  const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
+                                  void *A_lo, int max_in, float range_log2, void *stream) {
     if (n_groups == 0) return MLBP_OK;
-    MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && U && D && A_hi && A_lo,
+    MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && second_dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
     const bool fp32_ok = range_log2 >= 0.f && range_log2 < 100.f;   // products provably stay inside 2^+-100
     MLBP_CHECK_ARG(V > 0 && ldv >= V && (ldv % 4) == 0, "var_to_factor: bad V/ldv");
@@ -634,7 +653,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         if ((int64_t)n_groups * C > 0x7fffffffll) { set_error("var_to_factor: too many groups"); return MLBP_ERR_INVALID; }
 #define MLBP_K3_RES(N)                                                                                             \
         case N:                                                                                                    \
-            MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, \
+            MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, \
                                          (__half *)A_hi, (__half *)A_lo));                                         \
             break;
         switch (nin) {
@@ -653,13 +672,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     do {                                                                                                         \
         if (fp32_ok && occ3 && N <= 20)                                                                          \
             var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else if (fp32_ok)                                                                                        \
             var_to_factor_kernel<N, float, 1><<<n_groups, K3_THREADS, 0, st>>>(                                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else                                                                                                     \
             var_to_factor_kernel<N, double, 1><<<n_groups, K3_THREADS, 0, st>>>(                                 \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);

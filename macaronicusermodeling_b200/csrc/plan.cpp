@@ -48,7 +48,7 @@ enum {
     H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
     H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_WORDS = 32
 };
-enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_FIRST, LEV_WORDS = 10 };
+enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_FIRST, LEV_SECOND, LEV_WORDS = 10 };
 enum { GEMM_TABLE = 0, GEMM_A0, GEMM_D0, GEMM_N, GEMM_WORDS = 4 };
 
 struct Op {
@@ -208,7 +208,7 @@ void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
 
 // per-thread output of the emit phase for a contiguous range of graphs
 struct ChunkOut {
-    std::vector<std::vector<int32_t>> grp_u, grp_off, in_row, dest_off, dest, first;   // [level]
+    std::vector<std::vector<int32_t>> grp_u, grp_off, in_row, dest_off, dest, first, second;   // [level]
     std::vector<int32_t> init_rows, pair_c, pair_r, pair_z, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
 };
 
@@ -350,6 +350,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         ChunkOut &co = CO[c];
         co.grp_u.resize(n_levels + 1); co.grp_off.resize(n_levels + 1); co.in_row.resize(n_levels + 1);
         co.dest_off.resize(n_levels + 1); co.dest.resize(n_levels + 1); co.first.resize(n_levels + 1);
+        co.second.resize(n_levels + 1);
         std::vector<int32_t> dcount, dstart, dflat, ver, tgt;
         std::vector<std::vector<int32_t>> lev_ops(n_levels + 1);
         for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
@@ -443,6 +444,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
                             co.dest[L].insert(co.dest[L].end(), dflat.begin() + dstart[tgt[s]], dflat.begin() + dstart[tgt[s] + 1]);
                         // first reader's row per slot (-1: none): spares the kernels one dependent index load
                         co.first[L].push_back(tgt[s] >= 0 && dstart[tgt[s] + 1] > dstart[tgt[s]] ? dflat[dstart[tgt[s]]] : -1);
+                        co.second[L].push_back(tgt[s] >= 0 && dstart[tgt[s] + 1] > dstart[tgt[s]] + 1 ? dflat[dstart[tgt[s]] + 1] : -1);
                         co.dest_off[L].push_back((int32_t)co.dest[L].size());
                     }
                     co.grp_off[L].push_back((int32_t)co.in_row[L].size());
@@ -468,7 +470,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         for (const ChunkOut &co : CO) {
             for (int L = 0; L <= n_levels; ++L)
                 total += co.grp_u[L].size() + co.grp_off[L].size() + co.in_row[L].size() + co.dest_off[L].size() +
-                         co.dest[L].size() + co.first[L].size() + 24;
+                         co.dest[L].size() + co.first[L].size() + co.second[L].size() + 24;
             total += co.init_rows.size() + 9 * co.pair_c.size() + co.mu.size() + co.moff.size() + co.min_.size() + 16;
         }
         B.reserve(total);
@@ -498,6 +500,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         const int32_t o_doff = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.dest_off[L]; }, true);
         const int32_t o_dest = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.dest[L]; }, false);
         const int32_t o_first = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.first[L]; }, false);
+        const int32_t o_second = concat([&](ChunkOut &x) -> std::vector<int32_t> & { return x.second[L]; }, false);
         std::vector<int32_t> gemm;
         for (int t = 0; t < 4; ++t)
             if (cnt[(size_t)L * 4 + t] > 0) {
@@ -510,7 +513,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         const size_t rec = H_WORDS + (size_t)(L - 1) * LEV_WORDS;
         B[rec + LEV_NGROUPS] = ng; B[rec + LEV_GRP_U] = o_u; B[rec + LEV_GRP_OFF] = o_off; B[rec + LEV_IN_ROW] = o_in;
         B[rec + LEV_DEST_OFF] = o_doff; B[rec + LEV_DEST] = o_dest; B[rec + LEV_NGEMM] = (int32_t)(gemm.size() / GEMM_WORDS);
-        B[rec + LEV_GEMM] = o_gemm; B[rec + LEV_FIRST] = o_first;
+        B[rec + LEV_GEMM] = o_gemm; B[rec + LEV_FIRST] = o_first; B[rec + LEV_SECOND] = o_second;
     }
     {
         int32_t n_init = 0;

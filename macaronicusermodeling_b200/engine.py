@@ -470,7 +470,8 @@ class Engine(object):
                     return (ng + present + n_dest) * V * 4.0           # U row + D rows read (fp32), A hi+lo rows written
                 self._timed('K3 var_to_factor', k3_bytes,
                             lambda: k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])),
-                                           _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(U), _p(D), ld,
+                                           _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(bd, int(rec[9])),
+                                           _p(U), _p(D), ld,
                                            V, _p(A_hi), _p(A_lo), max_in, range_log2))
                 self.launches += 1
             gemm_calls(int(rec[7]), int(rec[6]), approx_inference)

@@ -32,7 +32,7 @@ def main():
     U = torch.rand((G, ld), device=dev, generator=g) + 0.5
     D = torch.rand((G * n + 1, ld), device=dev, generator=g) + 0.5
     D[0].fill_(1.0)                                              # the constant-one row of the ABI
-    A = torch.zeros((2, 2, G * n, ld), dtype=torch.float16, device=dev)      # [variant, hi/lo, rows, ld]
+    A = torch.zeros((2, 2, 2 * G * n, ld), dtype=torch.float16, device=dev)  # [variant, hi/lo, rows, ld]
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     peak = 6541.8
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
@@ -44,25 +44,27 @@ def main():
     lib.mlbp_debug_k3_times.restype = None
     lib.mlbp_debug_k3_times(ctypes.c_void_p(dbg.data_ptr()))
     out = {}
-    for shape, (ng, outs) in {'down (18 outputs)': (G, list(range(1, n))), 'up-b (1 output)': (G, [5 % n]),
-                              'root (19 outputs, 128 groups)': (min(128, G), list(range(n)))}.items():
+    for shape, (ng, outs, readers) in {'down (18 outputs)': (G, list(range(1, n)), 1), 'up-b (1 output)': (G, [5 % n], 1),
+                                       'root (19 outputs, 128 groups)': (min(128, G), list(range(n)), 1),
+                                       'last sweep down (18 outputs, 2 readers each)': (G, list(range(1, n)), 2)}.items():
         grp_u = np.arange(ng, dtype=np.int32)
         grp_off = (np.arange(ng + 1) * n).astype(np.int32)
         in_row = 1 + np.arange(ng * n, dtype=np.int32)
         dest_off = np.zeros(ng * n + 1, dtype=np.int32)
-        has = np.zeros(n, dtype=np.int32); has[outs] = 1
+        has = np.zeros(n, dtype=np.int32); has[outs] = readers
         dest_off[1:] = np.cumsum(np.tile(has, ng))
         dest = np.arange(int(dest_off[-1]), dtype=np.int32)
         first = np.where(np.diff(dest_off) > 0, dest[np.minimum(dest_off[:-1], len(dest) - 1)], -1).astype(np.int32)
         t = lambda x: torch.from_numpy(x).to(dev)
-        d_u, d_off, d_in, d_doff, d_dest, d_first = t(grp_u), t(grp_off), t(in_row), t(dest_off), t(dest), t(first)
+        second = np.where(np.diff(dest_off) > 1, dest[np.minimum(dest_off[:-1] + 1, len(dest) - 1)], -1).astype(np.int32)
+        d_u, d_off, d_in, d_doff, d_dest, d_first, d_second = t(grp_u), t(grp_off), t(in_row), t(dest_off), t(dest), t(first), t(second)
         nbytes = (ng + ng * n + len(dest)) * V * 4.0
         res = {}
         for variant, impl, occ in (('streaming', '1', '3'), ('resident', '2', '3')):
             os.environ['MLBP_K3_IMPL'] = impl
             os.environ['MLBP_K3_OCC'] = occ
             Ah, Al = A[0 if impl == '1' else 1, 0], A[0 if impl == '1' else 1, 1]
-            call = lambda: _lib.check(lib.mlbp_var_to_factor(ng, _p(d_u), _p(d_off), _p(d_in), _p(d_doff), _p(d_dest), _p(d_first), _p(U),
+            call = lambda: _lib.check(lib.mlbp_var_to_factor(ng, _p(d_u), _p(d_off), _p(d_in), _p(d_doff), _p(d_dest), _p(d_first), _p(d_second), _p(U),
                                                              _p(D), ld, V, _p(Ah), _p(Al), n, 30.0, st))
             for _ in range(2):
                 call()

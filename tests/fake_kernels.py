@@ -159,14 +159,15 @@ class FakeKernels(object):
         H[r, :V], L[r, :V] = np.where(km, hi[0], 0), np.where(km, lo[0], 0)
         H[r, V:], L[r, V:] = 0, 0
 
-    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2):
+    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         n_in = int(go[-1])
         ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
         de = _arr(dest, np.int32, max(int(do[-1]), 1))
-        fd = _arr(first_dest, np.int32, n_in)
-        for i in range(n_in):     # the plan's per-slot shortcut must agree with the CSR lists
+        fd, sd = _arr(first_dest, np.int32, n_in), _arr(second_dest, np.int32, n_in)
+        for i in range(n_in):     # the plan's per-slot shortcuts must agree with the CSR lists
             assert fd[i] == (de[do[i]] if do[i + 1] > do[i] else -1), (i, fd[i])
+            assert sd[i] == (de[do[i] + 1] if do[i + 1] > do[i] + 1 else -1), (i, sd[i])
         big = 1 << 40
         Uo = _arr(U, np.float32, (int(gu.max()) + 1) * ldv).reshape(-1, ldv)
         Dm = _arr(D, np.float32, (max(int(ir.max()), 0) + 1) * ldv).reshape(-1, ldv)
