@@ -197,3 +197,25 @@ def test_random_layout_sweep_vs_oracle(sweeps):
     # peaked beliefs of degree-35 variables: the error is ~sqrt(degree) * 2^-22 relative, i.e. up to ~2e-6 absolute
     common_checks.check_against_oracle(make_engine, model, sents, roots, [1.1, 0.6, -0.4], [1.3, -0.8, 0.7, 0.4, 0.5, -0.1],
                                        sweeps=sweeps, belief_atol=5e-6)
+
+
+@pytest.mark.parametrize('V,k', [(1500, 6), (4096, 10), (9000, 10), (10000, 20)], ids=['cluster1', 'cluster2', 'cluster4', 'cluster8'])
+def test_k3_resident_matches_streaming(V, k, monkeypatch):
+    """The single-read cluster kernel (1 / 2 / 4 / 8 CTAs per group, chosen from V and the largest variable degree) and the
+    streaming two-read kernel produce the same beliefs, arg-maxes and gradients."""
+    model = synth.make_model(V, 64, seed=17, dtype=np.float32)
+    sents = synth.make_corpus(model, 3, k=k, g=1, seed=5)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=6))
+    te, td = [0.7, 0.4, -0.2], [0.9, -0.5, 0.5, 0.3, 0.4, -0.2]
+    out = []
+    for impl in ('1', '2'):
+        monkeypatch.setenv('MLBP_K3_IMPL', impl)
+        eng = Engine(model)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_beliefs=True)
+        out.append((r.beliefs.cpu().numpy()[:, :V], r.top1.cpu().numpy(), r.grad.cpu().numpy(), r.logp.cpu().numpy()))
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-6
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-6)
