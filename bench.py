@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--ref-sample', type=int, default=2, help='sentences per step of the --impl reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--grad-b-terms', type=int, default=1, help='2 = keep the table lo half in the gradient rows (A/B probe)')
     return ap.parse_args()
 
 
@@ -218,7 +219,7 @@ def ours(a):
     assert world == a.gpus or world == 1, (world, a.gpus)
 
     model, sents = make_inputs(a, rank, a.sentences)
-    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)))
+    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)), grad_b_terms=a.grad_b_terms)
     tr = Trainer(eng, reg_param=0.2, N=a.sentences * world, sweeps=a.sweeps)
     tr.theta_ee, tr.theta_ed = theta0()
     corpus = Corpus(sents)

@@ -142,6 +142,8 @@ int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, in
  *   expectation N/Z of a pairwise belief is a RATIO of two rows computed from the same message r, so the 2^-12
  *   rounding of r largely cancels (measured <= 2e-7 relative on a sentence's gradient; the contract is 1e-4).      */
 #define MLBP_GEMM_A_HI_ONLY 256
+/* additionally drops the B_lo term: one pass, plain fp16 x fp16 with fp32 accumulation (gradient rows at large V only) */
+#define MLBP_GEMM_B_HI_ONLY 512
 int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                             const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
                             float alpha, int impl, void *stream);

@@ -10,7 +10,7 @@ constexpr int ST = 64, SK = 16;
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const __half *__restrict__ A_hi, const __half *__restrict__ A_lo, int64_t a_rows_total, int a_row0,
                  int n_rows, const __half *__restrict__ B_hi, const __half *__restrict__ B_lo, int V, int ldv,
-                 float *__restrict__ D, int64_t d_row0, int ldd, float alpha, int a_terms) {
+                 float *__restrict__ D, int64_t d_row0, int ldd, float alpha, int a_terms, int b_terms) {
     __shared__ float sA[SK][ST + 1], sB[SK][ST + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST;
@@ -23,7 +23,7 @@ gemm_simt_kernel(const __half *__restrict__ A_hi, const __half *__restrict__ A_l
             if (m0 + r < n_rows && ar < a_rows_total && k < V)
                 a = __half2float(A_hi[ar * ldv + k]) + (a_terms == 2 ? __half2float(A_lo[ar * ldv + k]) : 0.f);
             if (n0 + r < V && k < V)
-                b = __half2float(B_hi[(size_t)(n0 + r) * ldv + k]) + __half2float(B_lo[(size_t)(n0 + r) * ldv + k]);
+                b = __half2float(B_hi[(size_t)(n0 + r) * ldv + k]) + (b_terms == 2 ? __half2float(B_lo[(size_t)(n0 + r) * ldv + k]) : 0.f);
             sA[kk][r] = a;
             sB[kk][r] = b;
         }
@@ -51,10 +51,10 @@ gemm_simt_kernel(const __half *__restrict__ A_hi, const __half *__restrict__ A_l
 
 int launch_gemm_simt(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                      const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
-                     int a_terms, cudaStream_t st) {
+                     int a_terms, int b_terms, cudaStream_t st) {
     dim3 grid((V + ST - 1) / ST, (n_rows + ST - 1) / ST);
     gemm_simt_kernel<<<grid, 256, 0, st>>>((const __half *)A_hi, (const __half *)A_lo, a_rows_total, a_row0, n_rows,
-                                           (const __half *)B_hi, (const __half *)B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms);
+                                           (const __half *)B_hi, (const __half *)B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

@@ -36,7 +36,7 @@
 namespace mlbp {
 
 int launch_gemm_simt(const void *, const void *, int64_t, int, int, const void *, const void *, int, int, float *,
-                     int64_t, int, float, int, cudaStream_t);
+                     int64_t, int, float, int, int, cudaStream_t);
 
 constexpr int BM = 128;
 constexpr int UMMA_K = 16;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(Cfg<BN, STAGES, BK>::THREADS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                       float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                      int m_tiles, int n_tiles, int a_terms, int *err_flag) {
+                      int m_tiles, int n_tiles, int a_terms, int b_terms, int *err_flag) {
     using C = Cfg<BN, STAGES, BK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -210,12 +210,12 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u, err_flag, 1);
                 // a_terms == 1 (gradient rows): A.lo is neither loaded nor multiplied
-                mbar_expect_tx(full_bar(s), (uint32_t)(a_terms == 2 ? C::STAGE_BYTES : C::STAGE_BYTES - C::A_BYTES));
+                mbar_expect_tx(full_bar(s), (uint32_t)(C::STAGE_BYTES - (a_terms == 2 ? 0 : C::A_BYTES) - (b_terms == 2 ? 0 : C::B_BYTES)));
                 const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
                 tma_load_2d(&tm_a_hi, full_bar(s), st, kb * BK, row_a);
                 if (a_terms == 2) tma_load_2d(&tm_a_lo, full_bar(s), st + C::A_BYTES, kb * BK, row_a);
                 tma_load_2d(&tm_b_hi, full_bar(s), st + 2 * C::A_BYTES, kb * BK, row_b);
-                tma_load_2d(&tm_b_lo, full_bar(s), st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
+                if (b_terms == 2) tma_load_2d(&tm_b_lo, full_bar(s), st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
@@ -243,7 +243,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 bytes per K step inside the atom
                     tc_mma_f16(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
-                    tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    if (b_terms == 2) tc_mma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
                     if (a_terms == 2) tc_mma_f16(acc, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
                 tc_commit(empty_bar(s));                          // frees the stage when the MMAs above have read it
@@ -369,7 +369,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES>::THR
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                            float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                           int m_pairs, int n_tiles, int a_terms, int *err_flag) {
+                           int m_pairs, int n_tiles, int a_terms, int b_terms, int *err_flag) {
     using C = PairCfg<STAGES>;
     constexpr int BN = C::BN, BK = C::BK;
     extern __shared__ uint8_t smem_raw[];
@@ -427,7 +427,7 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
             // ===================== TMA producer (both CTAs) =====================
             const int row_a = a_row0 + m_blk * BM;
             const int row_b = n_blk * BN + (int)rank * (n_cur >> 1);      // this CTA's half of the N extent in use
-            const uint32_t bytes_cta = (uint32_t)(a_terms == 2 ? C::STAGE_BYTES : C::STAGE_BYTES - C::A_BYTES);
+            const uint32_t bytes_cta = (uint32_t)(C::STAGE_BYTES - (a_terms == 2 ? 0 : C::A_BYTES) - (b_terms == 2 ? 0 : C::B_BYTES));
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -438,7 +438,7 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
                 tma_load_2d_pair(&tm_a_hi, lb, st, kb * BK, row_a);
                 if (a_terms == 2) tma_load_2d_pair(&tm_a_lo, lb, st + C::A_BYTES, kb * BK, row_a);
                 tma_load_2d_pair(&tm_b_hi, lb, st + 2 * C::A_BYTES, kb * BK, row_b);
-                tma_load_2d_pair(&tm_b_lo, lb, st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
+                if (b_terms == 2) tma_load_2d_pair(&tm_b_lo, lb, st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
             }
         } else if (warp == 1 && lane == 0 && rank == 0) {
             // ===================== MMA issuer (leader only, for both SMs) =====================
@@ -463,7 +463,7 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
                     tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
-                    tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    if (b_terms == 2) tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
                     if (a_terms == 2) tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
                 tc_commit_pair(empty_bar(s));                     // frees the stage in both CTAs
@@ -582,7 +582,7 @@ static int *g_err_flag = nullptr;   // pinned, mapped: the kernel records which 
 template <int BN, int STAGES, int CHUNK_KB, int BK = 64>
 static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                      const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                     cudaStream_t st) {
+                     int b_terms, cudaStream_t st) {
     using C = Cfg<BN, STAGES, BK>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
@@ -604,7 +604,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_tiles = (n_rows + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
     gemm_split_f16_kernel<BN, STAGES, CHUNK_KB, BK><<<m_tiles * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, a_terms, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, a_terms, b_terms, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -612,7 +612,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
 template <int STAGES, int CHUNK_KB>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                        const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                       cudaStream_t st) {
+                       int b_terms, cudaStream_t st) {
     using C = PairCfg<STAGES>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
@@ -634,7 +634,7 @@ static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total,
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
     gemm_split_f16_pair_kernel<STAGES, CHUNK_KB><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, a_terms, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, a_terms, b_terms, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -658,17 +658,17 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
                    (reinterpret_cast<uintptr_t>(B_hi) % 128) == 0 && (reinterpret_cast<uintptr_t>(B_lo) % 128) == 0 &&
                    (reinterpret_cast<uintptr_t>(D) % 16) == 0, "factor_to_var_gemm: misaligned buffer");
     cudaStream_t st = as_stream(stream);
-    const int a_terms = (impl & MLBP_GEMM_A_HI_ONLY) ? 1 : 2;
-    impl &= ~MLBP_GEMM_A_HI_ONLY;
+    const int a_terms = (impl & MLBP_GEMM_A_HI_ONLY) ? 1 : 2, b_terms = (impl & MLBP_GEMM_B_HI_ONLY) ? 1 : 2;
+    impl &= ~(MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY);
     if (impl == 1)
-        return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
+        return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
     // impl 0: product configuration (CTA-pair kernel for large V).  impl 10..: one-CTA variants, impl 30..: CTA-pair
     // variants, exposed for scripts/gemm_probe.py and the kernel tests only.
 #define MLBP_TC(BN_, ST_, CH_) \
-    return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st)
+    return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st)
     switch (impl) {
         case 0:                                       // product configuration
-            if (V > 2048) return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
+            if (V > 2048) return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
             MLBP_TC(128, 3, 2);
         case 10: MLBP_TC(256, 2, 1);
         case 11: MLBP_TC(256, 2, 2);
@@ -678,12 +678,12 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
-        case 30: return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
-        case 31: return launch_pair<3, 1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
-        case 32: return launch_pair<2, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
-        case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
-        case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
-        case 22: return launch_tc<128, 6, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, st);
+        case 30: return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 31: return launch_pair<3, 1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 32: return launch_pair<2, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 22: return launch_tc<128, 6, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         default: break;
     }
 #undef MLBP_TC

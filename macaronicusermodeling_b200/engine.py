@@ -29,6 +29,7 @@ H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
  PLAN_N_DEAD) = range(9)
 A_SCALE_LOG2 = 14
 GEMM_A_HI_ONLY = 256          # include/mlbp.h MLBP_GEMM_A_HI_ONLY
+GEMM_B_HI_ONLY = 512          # include/mlbp.h MLBP_GEMM_B_HI_ONLY
 N_PLANES = 14
 N_SUMS = 7
 D_CONST_ROWS = 5
@@ -207,7 +208,7 @@ class Result(object):
 
 
 class Engine(object):
-    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1):
+    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -218,6 +219,7 @@ class Engine(object):
         # expectation N/Z is a ratio of two rows built from the same r, so its 2^-12 rounding largely cancels (<= 2e-7
         # relative on a sentence's gradient, measured against the float64 oracle).  2 = all three passes.
         self.grad_a_terms = int(grad_a_terms)
+        self.grad_b_terms = int(grad_b_terms)     # 1: the table's lo half is dropped too where grad_one_pass_ok (set_theta)
         self.theta_ee = None
         self.theta_ed = None
         self.planes = None
@@ -272,6 +274,10 @@ class Engine(object):
         # expectation is bounded by 2^-12 x the belief's mean absolute deviation of the feature, measured 2e-7 relative
         # on a sentence's gradient at log-ranges ~1.5 and 9e-6 at ~6.5; beyond e^3 the third pass is kept
         self.grad_hi_only_ok = (zmax - zmin) <= 3.0 and (abs(td[0]) * erange + abs(td[1]) * prange) <= 3.0
+        # ... and ONE pass (plain fp16 x fp16, fp32 accumulate) when, in addition, the vocabulary is large: the fp16 rounding of
+        # the table entries is random per entry and averages over the ~V^2 entries a belief spreads over (measured on a
+        # sentence's gradient against the float64 oracle: 7e-8 relative at V = 10 000, 3e-6 at V = 2 000)
+        self.grad_one_pass_ok = self.grad_hi_only_ok and self.V >= 4096
         self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
         n_planes = N_PLANES if with_grad else 8
         if self.planes is None or self.planes.shape[0] < n_planes:
@@ -454,7 +460,7 @@ class Engine(object):
                        _p(self.plane(t, 1)), V, ld, _p(D), d0, ld, alpha, self.gemm_impl | impl_flags)
                 if self.profile_gemm:
                     e1.record()
-                    self.gemm_events.append((e0, e1, rows, 2 if impl_flags & GEMM_A_HI_ONLY else 3))
+                    self.gemm_events.append((e0, e1, rows, 3 - (1 if impl_flags & GEMM_A_HI_ONLY else 0) - (1 if impl_flags & GEMM_B_HI_ONLY else 0)))
                 self.launches += 1
                 self.gemm_launches += 1
                 self.gemm_rows += rows
@@ -485,8 +491,9 @@ class Engine(object):
             rows = torch.cat([bd[oc:oc + n_pair], bd[orr:orr + n_pair]]).long()
             v2f_rows = (A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)
         if want_grad and n_pair:
+            one_pass = grad_hi_only and self.grad_one_pass_ok and self.grad_a_terms == 1 and self.grad_b_terms == 1
             gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
-                       GEMM_A_HI_ONLY if grad_hi_only else 0)
+                       (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0)
             if approx_beliefs:                                    # the c rows follow the r rows in the A buffer
                 c0 = int(blob[int(blob[H_PAIR_C])])
                 k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, c0, n_pair, topk)

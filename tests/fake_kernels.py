@@ -211,7 +211,7 @@ class FakeKernels(object):
         L = _arr(A_lo, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, :V].astype(np.float64)
         Bh = _arr(B_hi, np.float16, V * ldv).reshape(V, ldv)[:, :V].astype(np.float64)
         Bl = _arr(B_lo, np.float16, V * ldv).reshape(V, ldv)[:, :V].astype(np.float64)
-        out = H @ Bh.T + H @ Bl.T + (0.0 if impl & 256 else L @ Bh.T)     # MLBP_GEMM_A_HI_ONLY drops the A_lo term
+        out = H @ Bh.T + (0.0 if impl & 512 else H @ Bl.T) + (0.0 if impl & 256 else L @ Bh.T)   # MLBP_GEMM_{A,B}_HI_ONLY
         Dm = _arr(D, np.float32, (d_row0 + n_rows) * ldd).reshape(-1, ldd)
         Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
 

@@ -110,6 +110,24 @@ def test_two_pass_gradient_rows(scale):
     np.testing.assert_array_equal(g[0][:, 2:], g[1][:, 2:])     # bias and unary components do not use those rows
 
 
+def test_one_pass_gradient_rows_large_vocabulary():
+    """V >= 4096 and moderately peaked potentials: gradient rows are ONE fp16 pass; against the full 3-pass gradient the
+    difference stays two orders of magnitude inside the 1e-4 contract"""
+    model = synth.make_model(4608, 256, seed=9, dtype=np.float32)
+    sents = synth.make_corpus(model, 4, k=12, g=2, seed=13)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=14))
+    te, td = np.array([0.8, 0.5, -0.3]), np.array([1.0, -0.6, 0.5, 0.3, 0.4, -0.2])
+    g = []
+    for terms in (2, 1):
+        eng = Engine(model, grad_a_terms=terms, grad_b_terms=terms)
+        eng.set_theta(te, td)
+        g.append(eng.run(corpus, roots, 3).grad.cpu().numpy())
+    assert eng.grad_one_pass_ok
+    rel = np.abs(g[0][:, :2] - g[1][:, :2]) / np.maximum(np.abs(g[0][:, :2]), 1e-3)
+    assert 0.0 < rel.max() < 1e-5, rel.max()
+
+
 def test_c5_inference_only_many_sweeps():
     """BASELINE config C5 shape scaled to what the oracle can check: inference only, 10 sweeps, k = 12; dead-update
     elimination must not change any belief."""

@@ -85,6 +85,25 @@ def test_gradient_gemm_a_hi_only(lib, M, V, impl):
     assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
 
 
+@pytest.mark.parametrize('impl', [1, 0, 30, 11], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
+def test_gradient_gemm_one_pass(lib, impl):
+    """MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY: exactly  A_hi . B_hi'  (plain fp16 operands, fp32 accumulation)"""
+    M, V = 257, 4100
+    rng = np.random.default_rng(5)
+    A = rng.random((M + 9, V)) * 2.0 ** 14 / V * 2
+    B = np.exp(rng.normal(size=(V, V)) * 0.7) * 8.0
+    Ah, Al, Ax, ld = split_planes(A)
+    Bh, Bl, Bx, _ = split_planes(B)
+    D = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
+    _lib.check(lib.mlbp_factor_to_var_gemm(P(Ah), P(Al), A.shape[0], 4, M, P(Bh), P(Bl), V, ld, P(D), 1, ld,
+                                           2.0 ** -17, impl | 256 | 512, S()))
+    torch.cuda.synchronize()
+    ref = 2.0 ** -17 * (Ah.cpu().numpy()[4:4 + M, :V].astype(np.float64) @ Bh.cpu().numpy()[:, :V].astype(np.float64).T)
+    got = D.cpu().numpy()[1:1 + M, :V]
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
+    assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
+
+
 def test_message_gemm_peaked_rows(lib):
     """near-delta messages: one element carries (almost) all mass -- the split must keep the small ones"""
     rng = np.random.default_rng(3)
