@@ -666,11 +666,10 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         MLBP_LAUNCH_CHECK();
         return MLBP_OK;
     }
-    const char *env_occ = getenv("MLBP_K3_OCC");                     // probing only: 2 = do not cap registers for 3 CTAs per SM
-    const bool occ3 = !(env_occ && atoi(env_occ) == 2);
+    // up to 20 inputs the fp32 kernel is compiled for 3 CTAs per SM (80 registers): measured 1.28 ms vs 1.66 ms uncapped
 #define MLBP_K3_LAUNCH(N)                                                                                        \
     do {                                                                                                         \
-        if (fp32_ok && occ3 && N <= 20)                                                                          \
+        if (fp32_ok && N <= 20)                                                                                  \
             var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
                 grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else if (fp32_ok)                                                                                        \

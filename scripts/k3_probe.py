@@ -60,9 +60,8 @@ def main():
         d_u, d_off, d_in, d_doff, d_dest, d_first, d_second = t(grp_u), t(grp_off), t(in_row), t(dest_off), t(dest), t(first), t(second)
         nbytes = (ng + ng * n + len(dest)) * V * 4.0
         res = {}
-        for variant, impl, occ in (('streaming', '1', '3'), ('resident', '2', '3')):
+        for variant, impl in (('streaming', '1'), ('resident', '2')):
             os.environ['MLBP_K3_IMPL'] = impl
-            os.environ['MLBP_K3_OCC'] = occ
             Ah, Al = A[0 if impl == '1' else 1, 0], A[0 if impl == '1' else 1, 1]
             call = lambda: _lib.check(lib.mlbp_var_to_factor(ng, _p(d_u), _p(d_off), _p(d_in), _p(d_doff), _p(d_dest), _p(d_first), _p(d_second), _p(U),
                                                              _p(D), ld, V, _p(Ah), _p(Al), n, 30.0, st))
