@@ -323,7 +323,7 @@ def ours(a):
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(n_gemm, 1),
                 'algorithmic_flops_per_launch': flops / max(n_gemm, 1), 'share_of_step': gemm_ms / ms,
                 'note': 'algorithmic flops 2*rows*V*V counted once; message rows issue 3 fp16 MMA passes (hi*hi, hi*lo, lo*hi), '
-                        'gradient rows 2 (hi*hi, hi*lo): %.2f passes per row on average' % (gemm_pass_rows / max(gemm_rows, 1))}
+                        'gradient rows 1 (hi*hi; V >= 4096 and potentials within e^3, else 2 or 3): %.2f passes per row on average' % (gemm_pass_rows / max(gemm_rows, 1))}
     # HBM-bound kernels: algorithmic bytes (each input / output row counted once) over the CUDA-event time of every launch
     peak_gbs = float(peaks.get('hbm_gbs', 6500.0))
     hbm = {}
