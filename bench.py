@@ -268,6 +268,10 @@ def ours(a):
     gemm_rows = sum(r for _, _, r, _ in eng.gemm_events)
     gemm_pass_rows = sum(r * p for _, _, r, p in eng.gemm_events)
     n_gemm = len(eng.gemm_events)
+    by_passes = {}
+    for x, y, r, p in eng.gemm_events:
+        d = by_passes.setdefault(p, {'launches': 0, 'rows': 0, 'ms': 0.0})
+        d['launches'] += 1; d['rows'] += r; d['ms'] += x.elapsed_time(y)
     t = torch.tensor([ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,6 +324,10 @@ def ours(a):
     roofline = {'bound': 'tensor', 'kernel': 'gemm_split_f16_kernel (K4)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': ach / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': which,
                 'executed_tflops': ach * gemm_pass_rows / max(gemm_rows, 1), 'executed_frac': ach * gemm_pass_rows / max(gemm_rows, 1) / peak_tf,
+                'by_passes': {str(p): {'launches': d['launches'], 'rows': d['rows'], 'ms': d['ms'],
+                                       'algorithmic_tflops': 2.0 * d['rows'] * a.V * a.V / (d['ms'] / 1e3) / 1e12 if d['ms'] > 0 else 0.0,
+                                       'executed_tflops': p * 2.0 * d['rows'] * a.V * a.V / (d['ms'] / 1e3) / 1e12 if d['ms'] > 0 else 0.0}
+                              for p, d in sorted(by_passes.items())},
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(n_gemm, 1),
                 'algorithmic_flops_per_launch': flops / max(n_gemm, 1), 'share_of_step': gemm_ms / ms,
                 'note': 'algorithmic flops 2*rows*V*V counted once; message rows issue 3 fp16 MMA passes (hi*hi, hi*lo, lo*hi), '
