@@ -68,6 +68,7 @@ struct Graph {
     std::vector<int32_t> v0, v1, gap1;
     std::vector<std::vector<int32_t>> facset;   // incident pairwise factors per variable, attach order
     std::vector<Op> ops;
+    std::vector<int32_t> lvl;                   // ops[i].level, kept densely: the level lookups dominate build_sequence
     std::vector<int32_t> inputs;                // flat producer lists
     std::vector<int32_t> in_edge;               // parallel to inputs: edge id (f * 2 + side) of the message read
     std::vector<int32_t> fin_v2f, fin_f2v;      // producer op of the final version per edge (f * 2 + side)
@@ -137,7 +138,7 @@ struct Tracker {
     std::vector<int32_t> rd_v2f, rd_f2v;       // highest level that read the current version
 };
 
-inline int lvl_of(const Graph &g, int op) { return op < 0 ? 0 : g.ops[op].level; }
+inline int lvl_of(const Graph &g, int op) { return op < 0 ? 0 : g.lvl[op]; }
 
 void add_f2v(Graph &g, Tracker &t, int f, int side) {           // FactorNode.update_message_to, LBP.py:499-526
     const int e_out = 2 * f + side, e_in = 2 * f + (1 - side);
@@ -155,6 +156,7 @@ void add_f2v(Graph &g, Tracker &t, int f, int side) {           // FactorNode.up
     t.cur_f2v[e_out] = (int32_t)g.ops.size();
     t.rd_f2v[e_out] = 0;
     g.ops.push_back(op);
+    g.lvl.push_back(op.level);
 }
 
 void add_v2f(Graph &g, Tracker &t, int v, int f) {              // VariableNode.update_message_to, LBP.py:377-389
@@ -177,6 +179,7 @@ void add_v2f(Graph &g, Tracker &t, int v, int f) {              // VariableNode.
     t.cur_v2f[e_out] = (int32_t)g.ops.size();
     t.rd_v2f[e_out] = 0;
     g.ops.push_back(op);
+    g.lvl.push_back(op.level);
 }
 
 void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
@@ -268,6 +271,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
                 size_t reads = 0;
                 for (int v = 0; v < g.nv; ++v) reads += g.facset[v].size() * g.facset[v].size();
                 g.ops.reserve((size_t)4 * g.np * sweeps + 8);
+                g.lvl.reserve((size_t)4 * g.np * sweeps + 8);
                 g.inputs.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
                 g.in_edge.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
             }
