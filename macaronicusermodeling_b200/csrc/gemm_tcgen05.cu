@@ -310,7 +310,9 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
 // rows) and arrive on the leader's tmem-empty barrier.
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the even CTA of a pair
 
-template <int STAGES>
+// A_T / B_T: how many fp16 planes of A / B a stage holds (2 = hi + lo, 1 = hi only).  Fewer planes -> smaller stages ->
+// more of them: the one-pass rows need ~6 stages, their k-block lasts only ~512 clk against a ~1000 clk TMA round trip.
+template <int STAGES, int A_T = 2, int B_T = 2>
 struct PairCfg {
     static constexpr int BN = 256, BK = 64;
     static constexpr int EPI_WARPS = 8;
@@ -318,10 +320,12 @@ struct PairCfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int A_BYTES = BM * BK * 2;                // 128 rows of A (this CTA's half of M = 256)
     static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the B tile
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGE_BYTES = A_T * A_BYTES + B_T * B_BYTES;
+    static constexpr int B_OFF = A_T * A_BYTES;                 // A.hi [A.lo] B.hi [B.lo]
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(2 * STAGES + 4 <= 24, "barrier block");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -364,13 +368,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t rank) 
     }
 }
 
-template <int STAGES, int CHUNK_KB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES>::THREADS, 1)
+template <int STAGES, int CHUNK_KB, int A_T, int B_T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES, A_T, B_T>::THREADS, 1)
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                            float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                           int m_pairs, int n_tiles, int a_terms, int b_terms, int *err_flag) {
-    using C = PairCfg<STAGES>;
+                           int m_pairs, int n_tiles, int *err_flag) {
+    using C = PairCfg<STAGES, A_T, B_T>;
+    constexpr int a_terms = A_T, b_terms = B_T;
     constexpr int BN = C::BN, BK = C::BK;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -427,7 +432,7 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
             // ===================== TMA producer (both CTAs) =====================
             const int row_a = a_row0 + m_blk * BM;
             const int row_b = n_blk * BN + (int)rank * (n_cur >> 1);      // this CTA's half of the N extent in use
-            const uint32_t bytes_cta = (uint32_t)(C::STAGE_BYTES - (a_terms == 2 ? 0 : C::A_BYTES) - (b_terms == 2 ? 0 : C::B_BYTES));
+            const uint32_t bytes_cta = (uint32_t)C::STAGE_BYTES;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -437,8 +442,8 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
                 const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
                 tma_load_2d_pair(&tm_a_hi, lb, st, kb * BK, row_a);
                 if (a_terms == 2) tma_load_2d_pair(&tm_a_lo, lb, st + C::A_BYTES, kb * BK, row_a);
-                tma_load_2d_pair(&tm_b_hi, lb, st + 2 * C::A_BYTES, kb * BK, row_b);
-                if (b_terms == 2) tma_load_2d_pair(&tm_b_lo, lb, st + 2 * C::A_BYTES + C::B_BYTES, kb * BK, row_b);
+                tma_load_2d_pair(&tm_b_hi, lb, st + C::B_OFF, kb * BK, row_b);
+                if (b_terms == 2) tma_load_2d_pair(&tm_b_lo, lb, st + C::B_OFF + C::B_BYTES, kb * BK, row_b);
             }
         } else if (warp == 1 && lane == 0 && rank == 0) {
             // ===================== MMA issuer (leader only, for both SMs) =====================
@@ -457,8 +462,8 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
                 const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
                 const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + C::A_BYTES);
-                const uint64_t b_hi = umma_desc_kmajor<BK>(st + 2 * C::A_BYTES);
-                const uint64_t b_lo = umma_desc_kmajor<BK>(st + 2 * C::A_BYTES + C::B_BYTES);
+                const uint64_t b_hi = umma_desc_kmajor<BK>(st + C::B_OFF);
+                const uint64_t b_lo = umma_desc_kmajor<BK>(st + C::B_OFF + C::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -609,11 +614,10 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     return MLBP_OK;
 }
 
-template <int STAGES, int CHUNK_KB>
-static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
-                       const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                       int b_terms, cudaStream_t st) {
-    using C = PairCfg<STAGES>;
+template <int STAGES, int CHUNK_KB, int A_T, int B_T>
+static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
+                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, cudaStream_t st) {
+    using C = PairCfg<STAGES, A_T, B_T>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
     if ((rc = cached_map(&ma_hi, A_hi, a_rows_total, V, ldv, BM, C::BK)) != MLBP_OK) return rc;
@@ -622,7 +626,7 @@ static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total,
     if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, C::BN / 2, C::BK)) != MLBP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_pair_kernel<STAGES, CHUNK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
         attr_set = true;
     }
@@ -633,10 +637,24 @@ static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total,
     int *d_flag = nullptr;
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
-    gemm_split_f16_pair_kernel<STAGES, CHUNK_KB><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, a_terms, b_terms, d_flag);
+    gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
+}
+
+// stages per operand-plane count: 3 x 64 KB (hi+lo, hi+lo), 4 x 48 KB, 6 x 32 KB (hi, hi); `stages_scale`: probe variants
+template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6>
+static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
+                       const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
+                       int b_terms, cudaStream_t st) {
+#define MLBP_PAIR(S, AT, BT) \
+    return launch_pair_t<S, CHUNK_KB, AT, BT>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st)
+    if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2);
+    if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2);
+    if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1);
+    MLBP_PAIR(S11, 1, 1);
+#undef MLBP_PAIR
 }
 
 }  // namespace mlbp
@@ -668,7 +686,7 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
     return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st)
     switch (impl) {
         case 0:                                       // product configuration
-            if (V > 2048) return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+            if (V > 2048) return launch_pair<2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
             MLBP_TC(128, 3, 2);
         case 10: MLBP_TC(256, 2, 1);
         case 11: MLBP_TC(256, 2, 2);
@@ -678,9 +696,9 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
-        case 30: return launch_pair<3, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
-        case 31: return launch_pair<3, 1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
-        case 32: return launch_pair<2, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 30: return launch_pair<2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 31: return launch_pair<1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 32: return launch_pair<2, 2, 3, 3>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 22: return launch_tc<128, 6, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
