@@ -2,20 +2,21 @@
 //
 // Both multiply the messages coming into one variable.  The reference does it one np.multiply per incoming
 // message and per OUTGOING edge (LBP.py:377-389, :717-730): O(deg^2) vector passes per variable and sweep.
-// Here one CTA owns one (variable, schedule level) group, reads each incoming row once per phase and emits
-// every needed leave-one-out product from a prefix / suffix product in registers.  Products are carried in
-// float64: a variable can have ~40 incoming messages and the raw product of fp32 values would leave the fp32
-// range (the reference multiplies fp64 values of size 1/V and never rescales, LBP.py:381-385).
+// Here every needed leave-one-out product of a (variable, schedule level) group comes from a prefix / suffix product
+// in registers.  Phase 1 sums every outgoing product (the renormalisation of Message.renormalize, LBP.py:649-657);
+// phase 2 recomputes it, scales to 2^14 / sum and splits into the fp16 hi / lo operand rows the pairwise GEMM (K4)
+// consumes through TMA.  The sums only have to be deterministic, not exact: a row-uniform factor cancels downstream.
 //
-// Phase 1 sums every outgoing product (the renormalisation of Message.renormalize, LBP.py:649-657);
-// phase 2 recomputes it, scales to 2^14 / sum and splits into the fp16 hi / lo operand rows the pairwise GEMM
-// (K4) consumes through TMA.
-//
-// T = float when the caller's bound (range_log2) proves that no product can leave the fp32 range, else double.
-// Measured on B200 the fp64 pipe issues only ~3 lanes/clk/SM (profiles/README.md), so the double variant is
-// compute-bound at ~16 % of HBM bandwidth; it is the always-safe fallback.  A bulk-async (cp.async.bulk + mbarrier)
-// shared-memory staging of the inputs, and a cluster/DSMEM single-read variant (8 CTAs per group, slices kept in shared
-// memory between the phases), were both tried in round 1 and were slower than these plain coalesced loads.
+// Two kernels:
+//   var_to_factor_resident_kernel  (default) a thread-block cluster per group keeps the inputs in shared memory
+//                                  (bulk-async copies), exchanges partial sums by st.async pushes: every input is
+//                                  read from HBM once.  fp32 products; needs the slices to fit (V = 10k: 8 CTAs).
+//   var_to_factor_kernel           one CTA per group, inputs streamed from HBM in both phases; T = float when the
+//                                  caller's bound (range_log2) proves that no product can leave the fp32 range, else
+//                                  double (the reference multiplies fp64 values of size 1/V and never rescales,
+//                                  LBP.py:381-385).  Measured on B200 the fp64 pipe issues only ~3 lanes/clk/SM
+//                                  (profiles/README.md): the double variant is compute-bound at ~16 % of HBM bandwidth;
+//                                  it is the always-safe fallback.
 #include <stdlib.h>
 
 #include <cooperative_groups.h>
