@@ -17,6 +17,9 @@
 // accumulators and the epilogue warps drain the finished one into fp32 registers (round-to-nearest adds), which
 // brings the error back to ~1e-6 relative.
 //
+// Two kernels share this structure: gemm_split_f16_pair_kernel (further down; a CTA PAIR per 256 x 256 tile with
+// tcgen05.mma.cta_group::2 -- the product path for V > 2048) and the one-CTA kernel described here (small V, probes).
+//
 // Structure (one 128 x BN output tile per CTA, K = V streamed in 64-wide slabs):
 //   warp 0 lane 0 : TMA producer  -- 4 cp.async.bulk.tensor loads per stage (A.hi A.lo B.hi B.lo, swizzle-128B)
 //   warp 1 lane 0 : MMA issuer    -- 3 x (BK/16) tcgen05.mma.cta_group::1.kind::f16 per stage, tcgen05.commit
