@@ -237,3 +237,14 @@ def test_k3_resident_matches_streaming(V, k, monkeypatch):
     np.testing.assert_array_equal(out[0][1], out[1][1])
     np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-6)
+
+
+def test_long_sentence_streaming_k3_path():
+    """26 predicted tokens: 25 pairwise messages per variable is beyond the resident K3 kernel's 24 -> streaming kernel
+    (32-input bucket); parity with the oracle as everywhere else"""
+    model = synth.make_model(300, 40, seed=23)
+    sents = synth.make_corpus(model, 2, k=26, g=0, seed=31)
+    roots = synth.draw_roots(sents, 3, seed=32)
+    worst = common_checks.check_against_oracle(make_engine, model, sents, roots, [0.5, 0.3, -0.2],
+                                               [0.8, -0.4, 0.5, 0.3, 0.4, -0.2])
+    assert worst < 1e-6
