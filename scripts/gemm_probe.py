@@ -17,6 +17,8 @@ def main():
     ap.add_argument('--V', type=int, default=10000)
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--impl', type=int, nargs='+', default=[0])
+    ap.add_argument('--b-times-uniform', action='store_true', help='B := B o U[0,1): the value distribution of a T o PMI plane')
+    ap.add_argument('--table-like', action='store_true', help='B := exp(N(0, 0.5)) like a potential table, A := message-like')
     a = ap.parse_args()
     build.build()
     lib = _lib.require_device()
@@ -27,6 +29,13 @@ def main():
     Al = (torch.rand((M, ld), device='cuda', generator=g) * 1e-3).half()
     Bh = (torch.rand((V, ld), device='cuda', generator=g) * 4).half()
     Bl = (torch.rand((V, ld), device='cuda', generator=g) * 1e-3).half()
+    if a.table_like or a.b_times_uniform:
+        Bf = torch.exp(torch.randn((V, ld), device='cuda', generator=g) * 0.5) * 8.0
+        if a.b_times_uniform:
+            Bf = Bf * torch.rand((V, ld), device='cuda', generator=g)
+        Bh = Bf.half(); Bl = (Bf - Bh.float()).half()
+        Af = torch.rand((M, ld), device='cuda', generator=g) * (2.0 ** 14 / V * 2)
+        Ah = Af.half(); Al = (Af - Ah.float()).half()
     D = torch.empty((M, ld), dtype=torch.float32, device='cuda')
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
