@@ -3,6 +3,8 @@
 
     python bench.py --gpus N --steps K --warmup W            our arm (torchrun launches N ranks for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  the CPU arm: the oracle port of the reference's path
+                                                             (one process with threaded BLAS AND a train_mp.py-style pool of
+                                                             forked single-threaded workers; the faster one is the value)
 
 A step = one synchronous minibatch SGD step of the hot path over one batch of synthetic macaronic sentences:
 table build for the current theta (K2), unary products (K1), 3 sweeps of level-batched message passing
@@ -47,7 +49,7 @@ def parse():
     ap.add_argument('--sweeps', type=int, default=3)
     ap.add_argument('--workspace-gb', type=float, default=96.0)
     ap.add_argument('--cpu-sample', type=int, default=6, help='sentences timed on the CPU for cpu_baseline')
-    ap.add_argument('--ref-sample', type=int, default=2, help='sentences per step of the --impl reference arm')
+    ap.add_argument('--ref-sample', type=int, default=0, help='sentences per step of the process-pool CPU variant (0 = one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--grad-b-terms', type=int, default=1, help='2 = keep the table lo half in the gradient rows (A/B probe)')
@@ -155,14 +157,43 @@ def host_threads():
     return os.cpu_count() or 1
 
 
+# train_mp.py-style CPU variant (train_mp.py:634-649: a multiprocessing.Pool, one sentence per task): the workers are
+# forked AFTER the theta-only tables exist, so they inherit them copy-on-write instead of unpickling 4.8 GB per task
+# (SURVEY.md section 8(d) names this deviation), and every worker runs single-threaded BLAS.
+_POOL = {}
+
+
+def _pool_init():
+    from threadpoolctl import threadpool_limits
+    _POOL['limit'] = threadpool_limits(limits=1, user_api='blas')
+
+
+def _pool_sentence(i):
+    _POOL['orc'].run_fast(_POOL['tb'], _POOL['sents'][i], _POOL['roots'][i], _POOL['sweeps'])
+    return i
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def reference_arm(a):
+    """Two CPU variants of the same port are timed over the same K steps and the FASTER one is the arm's value:
+    `blas_threads` = one process, every level's dgemm threaded by the BLAS; `process_pool` = train_mp.py's layout,
+    one worker process per host core, one sentence per task."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    import multiprocessing as mp
     from oracle import lbp_oracle as orc
     from macaronicusermodeling_b200 import synth
-    n = a.ref_sample
-    model, sents = make_inputs(a, 0, max(n, 1))
+    workers = host_cores()
+    n_thr = 2
+    n_pool = a.ref_sample if a.ref_sample > 0 else workers
+    model, sents = make_inputs(a, 0, max(n_pool, n_thr))
     m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
     te, td = theta0()
     roots = synth.draw_roots(sents, a.sweeps, seed=5)
@@ -173,18 +204,30 @@ def reference_arm(a):
     tb = orc.Tables(m64, te, td)
     t_tab = time.perf_counter() - t0
 
-    def step():
-        for s, r in zip(sents[:n], roots[:n]):
+    def timed(step, n):
+        for _ in range(a.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step()
+        dt = time.perf_counter() - t0 + a.steps * t_tab * n / float(a.sentences)
+        return n * a.steps / dt, dt
+
+    def step_threads():
+        for s, r in zip(sents[:n_thr], roots[:n_thr]):
             orc.run_fast(tb, s, r, a.sweeps)
 
-    for _ in range(a.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step()
-    dt = time.perf_counter() - t0 + a.steps * t_tab * n / float(a.sentences)
-    v = n * a.steps / dt
-    cores = host_threads()
+    v_thr, dt_thr = timed(step_threads, n_thr)
+    blas_threads = host_threads()
+
+    _POOL.update(orc=orc, tb=tb, sents=sents, roots=roots, sweeps=a.sweeps)
+    with mp.get_context('fork').Pool(workers, initializer=_pool_init) as pool:
+        v_pool, dt_pool = timed(lambda: pool.map(_pool_sentence, range(n_pool), chunksize=1), n_pool)
+
+    if v_pool >= v_thr:
+        v, dt, n, variant, cores = v_pool, dt_pool, n_pool, 'process_pool', workers
+    else:
+        v, dt, n, variant, cores = v_thr, dt_thr, n_thr, 'blas_threads', blas_threads
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': 1e3 * dt / a.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -193,11 +236,32 @@ def reference_arm(a):
                                'per step, closed-form gradient, level-batched dgemm); each step is a bounded sample of '
                                '%d sentences of the workload; the literal per-message reference restatement is ~100x '
                                'slower (BASELINE.md section 2)' % n},
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': '%d sentences x %d steps + the amortised share of one %.1f s table build per %d-sentence step' % (n, a.steps, t_tab, a.sentences)},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'variant': variant,
+                             'variants': {'process_pool': {'value': v_pool, 'workers': workers, 'blas_threads_per_worker': 1,
+                                                           'sentences_per_step': n_pool},
+                                          'blas_threads': {'value': v_thr, 'threads': blas_threads, 'sentences_per_step': n_thr}},
+                             'sample': '%d sentences x %d steps (%s: %s) + the amortised share of one %.1f s table build per '
+                                       '%d-sentence step' % (n, a.steps, variant,
+                                                             'train_mp.py-style pool of %d forked single-threaded workers' % workers
+                                                             if variant == 'process_pool' else 'one process, %d BLAS threads' % blas_threads,
+                                                             t_tab, a.sentences)},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(a):
+    """cpu_baseline of the GPU arm = the reference arm run in a FRESH interpreter (no CUDA context, no NCCL threads in the
+    process that forks the worker pool), one timed step after one warm-up step."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+           '--sentences', str(a.sentences), '--V', str(a.V), '--Vd', str(a.Vd), '--k', str(a.k), '--g', str(a.g),
+           '--sweeps', str(a.sweeps), '--ref-sample', str(a.ref_sample)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'LOCAL_WORLD_SIZE')}
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env, check=True).stdout
+    for ln in reversed(out.splitlines()):
+        if ln.startswith('{'):
+            return json.loads(ln)['cpu_baseline']
+    raise RuntimeError('no JSON line from the CPU arm')
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -321,7 +385,7 @@ def ours(a):
         traffic_note = ('dram__bytes_read+write per launch from the committed ncu --set full capture (%d-row launches: %.2fx their '
                         'algorithmic A + D + table bytes); launches of this run average %d rows'
                         % (tr['rows_per_launch'], tr['ratio'], gemm_rows // max(n_gemm, 1)))
-    roofline = {'bound': 'tensor', 'kernel': 'gemm_split_f16_kernel (K4)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+    roofline = {'bound': 'tensor', 'kernel': 'gemm_split_f16_pair_kernel (K4, CTA pair, tcgen05.mma.cta_group::2)' if a.V > 2048 else 'gemm_split_f16_kernel (K4)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': ach / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': which,
                 'executed_tflops': ach * gemm_pass_rows / max(gemm_rows, 1), 'executed_frac': ach * gemm_pass_rows / max(gemm_rows, 1) / peak_tf,
                 'by_passes': {str(p): {'launches': d['launches'], 'rows': d['rows'], 'ms': d['ms'],
@@ -344,14 +408,17 @@ def ours(a):
                      'frac': gbs / peak_gbs, 'algorithmic_bytes_per_launch': d['bytes'] / max(d['launches'], 1),
                      'avg_launch_ms': d['ms'] / max(d['launches'], 1), 'share_of_step': d['ms'] / ms}
     cpu_baseline = None
-    if not a.no_cpu_baseline:
-        n = a.cpu_sample
-        t_tab, t_sent, _ = cpu_run(a, n, model, sents)
-        # one table build per SGD step is amortised over the step's sentences exactly like on the GPU
-        per_sent = t_sent / n + t_tab / float(a.sentences)
-        cpu_baseline = {'value': 1.0 / per_sent, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port',
-                        'sample': '%d sentences of the workload (%.1f s) + one table build (%.1f s, amortised over %d '
-                                  'sentences/step); oracle fast variant, float64, all BLAS threads' % (n, t_sent, t_tab, a.sentences)}
+    if not a.no_cpu_baseline and world == 1:
+        try:
+            cpu_baseline = cpu_baseline_subprocess(a)
+        except Exception as e:                                   # still report a CPU number: the in-process threaded variant
+            n = a.cpu_sample
+            t_tab, t_sent, _ = cpu_run(a, n, model, sents)
+            per_sent = t_sent / n + t_tab / float(a.sentences)
+            cpu_baseline = {'value': 1.0 / per_sent, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'variant': 'blas_threads',
+                            'sample': '%d sentences of the workload (%.1f s) + one table build (%.1f s, amortised over %d '
+                                      'sentences/step); oracle fast variant, float64, all BLAS threads; the process-pool '
+                                      'variant failed: %s' % (n, t_sent, t_tab, a.sentences, str(e)[:200])}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 (tensor-core operands split into fp16 hi+lo, fp32 accumulate; fp32 message products, f64 sums)', 'data': 'synthetic',
