@@ -359,6 +359,26 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same A tile feeds two consecutive MMAs of a k-step (hi*hi, hi*lo): the first keeps it in the tensor core's A
+// collector buffer (SASS UTCHMMA ... .A_KEEP), the second reads it from there (.A_REUSE) instead of shared memory.
+__device__ __forceinline__ void tc_mma_f16_pair_a_fill(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair_a_lastuse(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t rank) {   // arrive on the leader CTA's barrier
     if (rank == 0) {
         mbar_arrive(bar);
@@ -371,7 +391,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t rank) 
     }
 }
 
-template <int STAGES, int CHUNK_KB, int A_T, int B_T>
+template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES, A_T, B_T>::THREADS, 1)
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -470,8 +490,13 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                    tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
-                    if (b_terms == 2) tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    if (A_REUSE && b_terms == 2) {
+                        tc_mma_f16_pair_a_fill(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
+                        tc_mma_f16_pair_a_lastuse(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    } else {
+                        tc_mma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, (in_chunk | k) != 0 ? 1u : 0u);
+                        if (b_terms == 2) tc_mma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    }
                     if (a_terms == 2) tc_mma_f16_pair(acc, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
                 tc_commit_pair(empty_bar(s));                     // frees the stage in both CTAs
@@ -617,7 +642,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     return MLBP_OK;
 }
 
-template <int STAGES, int CHUNK_KB, int A_T, int B_T>
+template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE = false>
 static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                          const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, cudaStream_t st) {
     using C = PairCfg<STAGES, A_T, B_T>;
@@ -629,7 +654,7 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, C::BN / 2, C::BK)) != MLBP_OK) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
         attr_set = true;
     }
@@ -640,19 +665,19 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     int *d_flag = nullptr;
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
-    gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
+    gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
 
 // stages per operand-plane count: 3 x 64 KB (hi+lo, hi+lo), 4 x 48 KB, 6 x 32 KB (hi, hi); `stages_scale`: probe variants
-template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6>
+template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                        const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
                        int b_terms, cudaStream_t st) {
 #define MLBP_PAIR(S, AT, BT) \
-    return launch_pair_t<S, CHUNK_KB, AT, BT>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st)
+    return launch_pair_t<S, CHUNK_KB, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st)
     if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2);
     if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2);
     if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1);
@@ -689,7 +714,7 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
     return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st)
     switch (impl) {
         case 0:                                       // product configuration
-            if (V > 2048) return launch_pair<2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+            if (V > 2048) return launch_pair<2, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
             MLBP_TC(128, 3, 2);
         case 10: MLBP_TC(256, 2, 1);
         case 11: MLBP_TC(256, 2, 2);
@@ -701,6 +726,8 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 17: MLBP_TC(128, 3, 1 << 20);
         case 30: return launch_pair<2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 31: return launch_pair<1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 33:                                      // = impl 0 at large V; impl 30 is the same kernel without the A collector reuse
+            return launch_pair<2, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 32: return launch_pair<2, 2, 3, 3>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);

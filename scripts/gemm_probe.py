@@ -18,6 +18,7 @@ def main():
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--impl', type=int, nargs='+', default=[0])
     ap.add_argument('--b-times-uniform', action='store_true', help='B := B o U[0,1): the value distribution of a T o PMI plane')
+    ap.add_argument('--b-sparse', type=float, default=0.0, help='with --table-like: fraction of B entries set to zero (a sparse T o PMI plane)')
     ap.add_argument('--table-like', action='store_true', help='B := exp(N(0, 0.5)) like a potential table, A := message-like')
     a = ap.parse_args()
     build.build()
@@ -29,10 +30,12 @@ def main():
     Al = (torch.rand((M, ld), device='cuda', generator=g) * 1e-3).half()
     Bh = (torch.rand((V, ld), device='cuda', generator=g) * 4).half()
     Bl = (torch.rand((V, ld), device='cuda', generator=g) * 1e-3).half()
-    if a.table_like or a.b_times_uniform:
+    if a.table_like or a.b_times_uniform or a.b_sparse > 0:
         Bf = torch.exp(torch.randn((V, ld), device='cuda', generator=g) * 0.5) * 8.0
         if a.b_times_uniform:
             Bf = Bf * torch.rand((V, ld), device='cuda', generator=g)
+        if a.b_sparse > 0:
+            Bf = Bf * (torch.rand((V, ld), device='cuda', generator=g) >= a.b_sparse).float()
         Bh = Bf.half(); Bl = (Bf - Bh.float()).half()
         Af = torch.rand((M, ld), device='cuda', generator=g) * (2.0 ** 14 / V * 2)
         Ah = Af.half(); Al = (Af - Ah.float()).half()
