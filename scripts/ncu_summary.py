@@ -41,5 +41,30 @@ def main(path):
                     '%.3f' % (k['bytes'] / 1e9), '%.0f' % (k['bytes'] / 1e9 / (k['ms'] / 1e3) if k['ms'] > 0 else 0.0)])
 
 
+COLS = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'gpu__time_duration.sum', 'launch__block_size', 'launch__cluster_dim_x', 'launch__grid_size',
+        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'lts__t_sector_hit_rate.pct',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__cycles_elapsed.avg.per_second',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active']
+
+
+def raw(path):
+    """`ncu -i x.ncu-rep --page raw --csv > raw.csv; python scripts/ncu_summary.py --raw raw.csv`: the columns the
+    roofline discussion uses, one row per captured launch (second CSV row = units)."""
+    with open(path, newline='') as f:
+        rows = list(csv.reader(l for l in f if l.startswith('"')))
+    head, units, body = rows[0], rows[1], rows[2:]
+    idx = [head.index(c) for c in COLS if c in head]
+    w = csv.writer(sys.stdout)
+    w.writerow(['Kernel Name'] + ['%s [%s]' % (head[i], units[i]) for i in idx])
+    k = head.index('Kernel Name')
+    for r in body:
+        w.writerow([r[k][:60]] + [r[i] for i in idx])
+
+
 if __name__ == '__main__':
-    main(sys.argv[1])
+    if sys.argv[1] == '--raw':
+        raw(sys.argv[2])
+    else:
+        main(sys.argv[1])
