@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--ref-sample', type=int, default=0, help='sentences per step of the process-pool CPU variant (0 = one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--gemm-slice-pairs', type=int, default=None, help='M pairs per three-pass K4 launch (default: Engine rule; 0 = one launch per level, A/B probe)')
     ap.add_argument('--grad-b-terms', type=int, default=1, help='2 = keep the table lo half in the gradient rows (A/B probe)')
     return ap.parse_args()
 
@@ -283,7 +284,7 @@ def ours(a):
     assert world == a.gpus or world == 1, (world, a.gpus)
 
     model, sents = make_inputs(a, rank, a.sentences)
-    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)), grad_b_terms=a.grad_b_terms)
+    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)), grad_b_terms=a.grad_b_terms, gemm_slice_pairs=a.gemm_slice_pairs)
     tr = Trainer(eng, reg_param=0.2, N=a.sentences * world, sweeps=a.sweeps)
     tr.theta_ee, tr.theta_ed = theta0()
     corpus = Corpus(sents)
@@ -429,7 +430,7 @@ def ours(a):
             'config': {'workload': workload_name(a), 'global_sentences_per_step': a.sentences * world,
                        'parallelism': 'dp%d (sentences sharded, 16 x f64 all-reduce per step)' % world,
                        'l2': 'inputs larger than L2: table planes 2.8 GB, message blocks > 10 GB per micro-batch',
-                       'micro_batches_per_step': len(parts)},
+                       'micro_batches_per_step': len(parts), 'k4_rows_per_three_pass_launch': eng.gemm_slice_rows},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'hbm_kernels': hbm,
             'cpu_baseline': cpu_baseline}
     print(json.dumps(line), flush=True)

@@ -208,7 +208,8 @@ class Result(object):
 
 
 class Engine(object):
-    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1):
+    def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
+                 gemm_slice_pairs=None):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -220,6 +221,7 @@ class Engine(object):
         # relative on a sentence's gradient, measured against the float64 oracle).  2 = all three passes.
         self.grad_a_terms = int(grad_a_terms)
         self.grad_b_terms = int(grad_b_terms)     # 1: the table's lo half is dropped too where grad_one_pass_ok (set_theta)
+        self.gemm_slice_rows = self._gemm_slice_rows(gemm_slice_pairs)
         self.theta_ee = None
         self.theta_ed = None
         self.planes = None
@@ -239,6 +241,23 @@ class Engine(object):
         self.gemm_events = []
         self.profile_kernels = False  # same for the HBM-bound kernels: (name, event, event, algorithmic bytes)
         self.kernel_events = []
+
+    def _gemm_slice_rows(self, pairs):
+        """Rows per K4 launch of the three-pass message GEMMs (0 = never slice).  The CTA pairs of one launch start in step and
+        share A / B slabs in L2, but drift apart in K from wave to wave (ncu: 1.5x the wave-ideal DRAM bytes after 5 waves, 1.9x
+        after 40) and the re-reads cost power under the cap; a kernel boundary re-aligns them.  Measured at 87 552 rows, V = 10 000
+        (profiles/r1f_gemm_probe_split.txt): slices of 11-37 M-pairs are 4-6 % faster than one launch.  The slice is the pair count
+        worth 8 to 24 waves of the resident pairs whose tiles fill whole waves best (V = 10 000 on 148 SMs: 37 pairs = exactly 20
+        waves)."""
+        if pairs is not None:
+            return int(pairs) * 256
+        if self.V <= 2048 or self.device.type != 'cuda':
+            return 0
+        resident = max(torch.cuda.get_device_properties(self.device).multi_processor_count // 2, 1)
+        n_tiles = (self.V + 255) // 256
+        waste = lambda p: -(-p * n_tiles // resident) * resident / float(p * n_tiles)
+        lo, hi = max(-(-8 * resident // n_tiles), 1), max(24 * resident // n_tiles, 1)
+        return 256 * min(range(lo, max(hi, lo) + 1), key=lambda p: (round(waste(p), 4), -p))
 
     def _timed(self, name, nbytes, fn):
         """launch through fn(); with profile_kernels the launch is bracketed by CUDA events on the launching stream and
@@ -453,16 +472,21 @@ class Engine(object):
                     k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, a0, rows, topk)
                     masked.add((a0, rows))
                     self.launches += 1
-                if self.profile_gemm:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0, rows, _p(self.plane(t, 0)),
-                       _p(self.plane(t, 1)), V, ld, _p(D), d0, ld, alpha, self.gemm_impl | impl_flags)
-                if self.profile_gemm:
-                    e1.record()
-                    self.gemm_events.append((e0, e1, rows, 3 - (1 if impl_flags & GEMM_A_HI_ONLY else 0) - (1 if impl_flags & GEMM_B_HI_ONLY else 0)))
-                self.launches += 1
-                self.gemm_launches += 1
+                passes = 3 - (1 if impl_flags & GEMM_A_HI_ONLY else 0) - (1 if impl_flags & GEMM_B_HI_ONLY else 0)
+                # one-pass rows are L2-bandwidth-bound, not power-bound: slicing does not help them (measured)
+                step = self.gemm_slice_rows if (self.gemm_slice_rows and passes > 1) else rows
+                for r0 in range(0, rows, max(step, 1)):
+                    n = min(step, rows - r0)
+                    if self.profile_gemm:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
+                           _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags)
+                    if self.profile_gemm:
+                        e1.record()
+                        self.gemm_events.append((e0, e1, n, passes))
+                    self.launches += 1
+                    self.gemm_launches += 1
                 self.gemm_rows += rows
 
         for L in range(int(blob[H_NLEVELS])):

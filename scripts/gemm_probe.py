@@ -19,6 +19,7 @@ def main():
     ap.add_argument('--impl', type=int, nargs='+', default=[0])
     ap.add_argument('--b-times-uniform', action='store_true', help='B := B o U[0,1): the value distribution of a T o PMI plane')
     ap.add_argument('--b-sparse', type=float, default=0.0, help='with --table-like: fraction of B entries set to zero (a sparse T o PMI plane)')
+    ap.add_argument('--split-pairs', type=int, nargs='+', default=[0], help='launch the GEMM in slices of this many 256-row M pairs (0 = one launch)')
     ap.add_argument('--table-like', action='store_true', help='B := exp(N(0, 0.5)) like a potential table, A := message-like')
     a = ap.parse_args()
     build.build()
@@ -45,9 +46,12 @@ def main():
 
     ref = (Ah[:64, :V].double() + Al[:64, :V].double()) @ (Bh[:, :V].double() + Bl[:, :V].double()).T
     ref -= Al[:64, :V].double() @ Bl[:, :V].double().T          # the kernel drops lo*lo by design
-    for impl in a.impl:
+    for impl, split in [(i, sp) for i in a.impl for sp in a.split_pairs]:
         def run():
-            _lib.check(lib.mlbp_factor_to_var_gemm(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, impl, st))
+            step = split * 256 if split > 0 else M
+            for r0 in range(0, M, step):
+                n = min(step, M - r0)
+                _lib.check(lib.mlbp_factor_to_var_gemm(P(Ah), P(Al), M, r0, n, P(Bh), P(Bl), V, ld, P(D), r0, ld, 1.0, impl, st))
 
         for _ in range(2):
             run()
@@ -61,7 +65,7 @@ def main():
         ms = e0.elapsed_time(e1) / a.iters
         flops = 2.0 * M * V * V
         rel = ((D[:64, :V].double() - ref) / ref)
-        print(json.dumps({'impl': impl, 'M': M, 'V': V, 'ms': round(ms, 4), 'algorithmic_tflops': round(flops / ms / 1e9, 1),
+        print(json.dumps({'impl': impl, 'split_pairs': split, 'M': M, 'V': V, 'ms': round(ms, 4), 'algorithmic_tflops': round(flops / ms / 1e9, 1),
                           'executed_tflops': round(3 * flops / ms / 1e9, 1), 'rel_err_max': rel.abs().max().item(),
                           'rel_err_mean': rel.mean().item(), 'rel_err_std': rel.std().item(),
                           'timeout_code': lib.mlbp_gemm_barrier_timeout_code()}), flush=True)

@@ -171,6 +171,32 @@ def test_properties_at_scale():
     assert np.abs(g0[:, 2]).max() < 1e-9 and np.abs(g0[:, 8]).max() < 1e-9      # bias components
 
 
+def test_sliced_message_gemms_are_bit_transparent():
+    """the three-pass message GEMMs of a level are launched in slices of whole M pairs (Engine.gemm_slice_rows: a kernel boundary
+    re-aligns the CTA pairs in K); a row's result does not depend on which launch computed it"""
+    model = synth.make_model(2304, 128, seed=41, dtype=np.float32)
+    sents = synth.make_corpus(model, 40, k=8, g=1, seed=3)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=4))
+    te, td = [0.9, 0.4, -0.1], [1.1, -0.5, 0.5, 0.3, 0.4, -0.2]
+    out = []
+    for pairs in (0, 1, 3):
+        eng = Engine(model, gemm_slice_pairs=pairs)
+        assert eng.gemm_slice_rows == 256 * pairs
+        eng.set_theta(te, td)
+        n0 = eng.gemm_launches
+        r = eng.run(corpus, roots, 3, want_grad=True, want_marg=True, want_beliefs=True)
+        out.append((r.beliefs.cpu().numpy(), r.top1.cpu().numpy(), r.logp.cpu().numpy(), r.grad.cpu().numpy(), eng.gemm_launches - n0))
+    assert out[1][4] > out[2][4] > out[0][4]
+    for o in out[1:]:
+        for x, y in zip(out[0][:3], o[:3]):
+            np.testing.assert_array_equal(x, y)
+        # the unary part of the gradient uses K2's float64 column sums, accumulated with atomics: last-bit run-to-run noise
+        np.testing.assert_allclose(o[3], out[0][3], rtol=1e-10, atol=1e-13)
+    auto = Engine(model).gemm_slice_rows                      # 9 N tiles: a slice worth 8..24 waves of the resident pairs
+    assert auto % 256 == 0 and 8 * 74 <= (auto // 256) * 9 <= 25 * 74
+
+
 @pytest.mark.parametrize('V,Vd', [(203, 37), (1001, 129), (67, 5)])
 def test_odd_vocabulary_sizes(V, Vd):
     """V not a multiple of 4 / 8 / 64: padded rows, TMA out-of-bounds zero fill, partial tiles"""
