@@ -53,6 +53,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--gemm-slice-pairs', type=int, default=None, help='M pairs per three-pass K4 launch (default: Engine rule; 0 = one launch per level, A/B probe)')
+    ap.add_argument('--gemm-impl', type=int, default=0, help='K4 variant / flags (include/mlbp.h; A/B probes)')
     ap.add_argument('--grad-b-terms', type=int, default=1, help='2 = keep the table lo half in the gradient rows (A/B probe)')
     return ap.parse_args()
 
@@ -284,7 +285,8 @@ def ours(a):
     assert world == a.gpus or world == 1, (world, a.gpus)
 
     model, sents = make_inputs(a, rank, a.sentences)
-    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)), grad_b_terms=a.grad_b_terms, gemm_slice_pairs=a.gemm_slice_pairs)
+    eng = Engine(model, workspace_bytes=int(a.workspace_gb * (1 << 30)), grad_b_terms=a.grad_b_terms, gemm_slice_pairs=a.gemm_slice_pairs,
+                 gemm_impl=a.gemm_impl)
     tr = Trainer(eng, reg_param=0.2, N=a.sentences * world, sweeps=a.sweeps)
     tr.theta_ee, tr.theta_ed = theta0()
     corpus = Corpus(sents)

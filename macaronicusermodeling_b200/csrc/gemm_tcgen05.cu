@@ -671,17 +671,22 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     return MLBP_OK;
 }
 
-// stages per operand-plane count: 3 x 64 KB (hi+lo, hi+lo), 4 x 48 KB, 6 x 32 KB (hi, hi); `stages_scale`: probe variants
-template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false>
+// stages per operand-plane count: 3 x 64 KB (hi+lo, hi+lo), 4 x 48 KB, 6 x 32 KB (hi, hi); `stages_scale`: probe variants.
+// CHUNK_11: k-blocks per accumulator drain of the ONE-pass rows.  Their k-block lasts a third of a three-pass one, so at
+// CHUNK_KB = 2 the epilogue warps had to drain 128 x 256 accumulators every ~1 000 clk and held the MMA issuer back:
+// 4 k-blocks per drain is +13 % on these rows in the bench (0.93 -> 1.05 PFLOP/s).  The accumulation bias grows with the
+// chunk (-2.2e-6 -> -4.4e-6, uniform) but these rows only feed the ratio N/Z, where it cancels (<= 3e-6 even between a
+// dense and a 90 % sparse plane, scaled from profiles/r1f_gemm_probe_bias_sparse.txt).
+template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false, int CHUNK_11 = CHUNK_KB>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                        const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
                        int b_terms, cudaStream_t st) {
-#define MLBP_PAIR(S, AT, BT) \
-    return launch_pair_t<S, CHUNK_KB, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st)
-    if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2);
-    if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2);
-    if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1);
-    MLBP_PAIR(S11, 1, 1);
+#define MLBP_PAIR(S, AT, BT, CH) \
+    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, st)
+    if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2, CHUNK_KB);
+    if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2, CHUNK_KB);
+    if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1, CHUNK_KB);
+    MLBP_PAIR(S11, 1, 1, CHUNK_11);
 #undef MLBP_PAIR
 }
 
@@ -714,7 +719,7 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
     return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st)
     switch (impl) {
         case 0:                                       // product configuration
-            if (V > 2048) return launch_pair<2, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
             MLBP_TC(128, 3, 2);
         case 10: MLBP_TC(256, 2, 1);
         case 11: MLBP_TC(256, 2, 2);
@@ -728,6 +733,9 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 31: return launch_pair<1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 33:                                      // = impl 0 at large V; impl 30 is the same kernel without the A collector reuse
             return launch_pair<2, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 34: return launch_pair<4, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);      // all rows drained every 4 k-blocks
+        case 35: return launch_pair<2, 3, 4, 6, true, 8>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);   // one-pass rows drained every 8
+        case 36: return launch_pair<2, 3, 4, 6, true, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);   // ... every 2 (the product path before)
         case 32: return launch_pair<2, 2, 3, 3>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
         case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);

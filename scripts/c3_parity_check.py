@@ -19,13 +19,14 @@ from oracle import lbp_oracle as orc  # noqa: E402  (the checker)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--n', type=int, default=16)
+    ap.add_argument('--gemm-impl', type=int, default=0, help='K4 variant (include/mlbp.h, csrc/gemm_tcgen05.cu)')
     ap.add_argument('--grad-terms', type=int, default=1, help='2 = three-pass gradient rows (for comparison)')
     a = ap.parse_args()
     model = synth.make_model(10000, 2000, seed=1234, dtype=np.float32)
     sents = synth.make_corpus(model, a.n, k=20, g=0, seed=4242)
     roots_pos = synth.draw_roots(sents, 3, seed=11)
     te, td = [0.8, 0.5, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]
-    eng = Engine(model, grad_a_terms=a.grad_terms, grad_b_terms=a.grad_terms)
+    eng = Engine(model, grad_a_terms=a.grad_terms, grad_b_terms=a.grad_terms, gemm_impl=a.gemm_impl)
     eng.set_theta(te, td)
     corpus = Corpus(sents)
     r = eng.run(corpus, corpus.roots_from_positions(roots_pos), 3, want_beliefs=True)
