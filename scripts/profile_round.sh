@@ -10,8 +10,8 @@ mkdir -p $OUT
 $CMD > $OUT/${TAG}_plain.log 2>&1 || { echo "plain run failed" >> $OUT/${TAG}_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file $OUT/${TAG}_ncu_launches_128sent.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_split_f16_pair -s 58 -c 16 -f -o $OUT/${TAG}_gemm $CMD \
+ncu --set full --clock-control none --import-source on -k regex:gemm_split_f16_pair -s ${GEMM_SKIP:-58} -c ${GEMM_COUNT:-16} -f -o $OUT/${TAG}_gemm $CMD \
     > $OUT/${TAG}_ncu_gemm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:var_to_factor_resident -s 9 -c 4 -f -o $OUT/${TAG}_k3 $CMD \
+[ -n "$SKIP_K3" ] || ncu --set full --clock-control none --import-source on -k regex:var_to_factor_resident -s 9 -c 4 -f -o $OUT/${TAG}_k3 $CMD \
     > $OUT/${TAG}_ncu_k3.log 2>&1
 ls -la $OUT | grep ${TAG}
