@@ -200,6 +200,12 @@ def reference_arm(a):
     te, td = theta0()
     roots = synth.draw_roots(sents, a.sweeps, seed=5)
 
+    try:                                                        # torchrun exports OMP_NUM_THREADS=1: give the BLAS every host core back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=workers, user_api='blas')
+    except Exception:
+        pass
+
     # theta changes once per SGD step, so the theta-only tables are rebuilt once per step of a.sentences sentences;
     # the bounded sample below is charged its share of that build (n / a.sentences), like the GPU arm amortises K2
     t0 = time.perf_counter()
