@@ -60,6 +60,26 @@ def test_microbatching_is_transparent():
     np.testing.assert_array_equal(t1.numpy(), whole.top1.numpy())
 
 
+def test_sliced_level_gemms_are_transparent():
+    """Engine.gemm_slice_rows: a level's message GEMM issued as several launches over row slices (the GPU engine does it to
+    re-align the CTA pairs of the tcgen05 kernel) addresses the same A / D rows as one launch"""
+    model = synth.make_model(64, 16, seed=6)
+    sents = synth.make_corpus(model, 30, k=6, g=1, seed=5)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=2))
+    te, td = [0.4, 0.3, 0.0], [0.5, 0.2, 0.1, 0.1, 0.1, 0.0]
+    res = []
+    for pairs in (None, 1):
+        eng = Engine(model, kernels=FakeKernels(), gemm_slice_pairs=pairs)
+        assert eng.gemm_slice_rows == (256 if pairs else 0)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_beliefs=True)
+        res.append((r.grad.numpy(), r.logp.numpy(), r.top1.numpy(), r.beliefs.numpy(), eng.gemm_launches))
+    assert res[1][4] > res[0][4]
+    for x, y in zip(res[0][:4], res[1][:4]):
+        np.testing.assert_array_equal(x, y)
+
+
 def test_inference_only_drops_dead_updates():
     """without the gradient stage the last sweep's variable->factor messages feed nothing (dead code)"""
     model = synth.make_model(64, 16, seed=5)
