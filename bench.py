@@ -390,13 +390,13 @@ def ours(a):
     tr_path = os.path.join(REPO, 'profiles', 'r1f_k4_traffic.json')
     if os.path.exists(tr_path) and a.V == 10000:
         tr = json.load(open(tr_path))
-        big = tr['three_pass_big']
+        big = tr['three_pass_37_pairs'] if (eng.gemm_slice_rows == 37 * 256 and 'three_pass_37_pairs' in tr) else tr['three_pass_big']
         traffic = big['dram_bytes_per_launch']
-        traffic_note = ('dram__bytes_read+write of one three-pass launch of %d rows from the committed ncu --set full capture (%s): '
+        traffic_note = ('dram__bytes_read+write of one three-pass launch of %d rows from the committed ncu capture (%s): '
                         '%.1fx its algorithmic A + D + table bytes and %.2fx what a 126 MB L2 allows when 74 resident CTA pairs '
                         'stream their A and B slabs once per wave; %.0f %% of DRAM peak while the tensor pipe is %.0f %% active, so '
                         'the re-reads cost power, not time; launches of this run average %d rows'
-                        % (big['rows_per_launch_padded'], 'profiles/r1f_ncu_full_gemm.csv', big['ratio'], big['ratio_to_wave_ideal'],
+                        % (big['rows_per_launch_padded'], big.get('source', 'profiles/r1f_ncu_full_gemm.csv').split(' ')[0], big['ratio'], big['ratio_to_wave_ideal'],
                            big['dram_pct_of_peak'], big['tensor_pipe_active_pct'], gemm_rows // max(n_gemm, 1)))
     roofline = {'bound': 'tensor', 'kernel': 'gemm_split_f16_pair_kernel (K4, CTA pair, tcgen05.mma.cta_group::2)' if a.V > 2048 else 'gemm_split_f16_kernel (K4)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': ach / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': which,
