@@ -144,6 +144,9 @@ int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, in
 #define MLBP_GEMM_A_HI_ONLY 256
 /* additionally drops the B_lo term: one pass, plain fp16 x fp16 with fp32 accumulation (gradient rows at large V only) */
 #define MLBP_GEMM_B_HI_ONLY 512
+/* CTA-pair kernel, probe switch: the narrow last N tile (V not a multiple of 256) of every M pair is issued at the END of the
+ * launch instead of inside the raster, so that all tiles of the raster take the same time (same results, different tile order) */
+#define MLBP_GEMM_NARROW_LAST 2048
 int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                             const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
                             float alpha, int impl, void *stream);
