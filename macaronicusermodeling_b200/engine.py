@@ -30,6 +30,7 @@ H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 A_SCALE_LOG2 = 14
 GEMM_A_HI_ONLY = 256          # include/mlbp.h MLBP_GEMM_A_HI_ONLY
 GEMM_B_HI_ONLY = 512          # include/mlbp.h MLBP_GEMM_B_HI_ONLY
+GEMM_NARROW_LAST = 2048       # include/mlbp.h MLBP_GEMM_NARROW_LAST (probe switch)
 N_PLANES = 14
 N_SUMS = 7
 D_CONST_ROWS = 5
@@ -255,6 +256,8 @@ class Engine(object):
             return 0
         resident = max(torch.cuda.get_device_properties(self.device).multi_processor_count // 2, 1)
         n_tiles = (self.V + 255) // 256
+        if (self.gemm_impl & GEMM_NARROW_LAST) and self.V % 256:   # probe switch: the narrow last tiles run after the raster
+            n_tiles -= 1
         waste = lambda p: -(-p * n_tiles // resident) * resident / float(p * n_tiles)
         lo, hi = max(-(-8 * resident // n_tiles), 1), max(24 * resident // n_tiles, 1)
         return 256 * min(range(lo, max(hi, lo) + 1), key=lambda p: (round(waste(p), 4), -p))
