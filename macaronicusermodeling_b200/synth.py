@@ -24,16 +24,32 @@ F_CORRECT, F_FULL_HISTORY, F_HIT_HISTORY = 2, 3, 4
 KIND_GIVEN, KIND_PREDICTED = 0, 1
 
 
-def make_model(V, Vd, seed=1234, w1_density=1.0, dtype=np.float64):
-    """iid U[0,1] feature planes; PMI_w1 optionally sparsified (most adjacent-PMI entries are 0)."""
+def make_model(V, Vd, seed=1234, w1_density=1.0, dtype=np.float64, pmi_density=1.0):
+    """iid U[0,1] feature planes; PMI and PMI_w1 optionally sparsified (real PMI matrices are mostly zeros: only word
+    pairs that co-occur carry a value; the ``*.scaled.01`` files of run-training.sh:10 keep the zeros)."""
     rng = np.random.default_rng(seed)
     pmi = rng.random((V, V)).astype(dtype)
     pmi_w1 = rng.random((V, V)).astype(dtype)
     if w1_density < 1.0:
         pmi_w1 *= (rng.random((V, V)) < w1_density)
+    if pmi_density < 1.0:
+        pmi *= (np.random.default_rng(seed + 7).random((V, V)) < pmi_density)
     ed = rng.random((V, Vd)).astype(dtype)
     ped = rng.random((V, Vd)).astype(dtype)
     return {'V': V, 'Vd': Vd, 'pmi': pmi, 'pmi_w1': pmi_w1, 'ed': ed, 'ped': ped}
+
+
+def make_model_large(V, Vd, seed=1234, block=4096):
+    """float32 feature planes generated in row blocks (BASELINE config C5: V = 50 000 -> 10 GB per plane; a float64
+    intermediate of the whole plane would not be affordable)"""
+    rng = np.random.default_rng(seed)
+
+    def plane(rows, cols):
+        out = np.empty((rows, cols), dtype=np.float32)
+        for r0 in range(0, rows, block):
+            out[r0:r0 + block] = rng.random((min(block, rows - r0), cols), dtype=np.float32)
+        return out
+    return {'V': V, 'Vd': Vd, 'pmi': plane(V, V), 'pmi_w1': plane(V, V), 'ed': plane(V, Vd), 'ped': plane(V, Vd)}
 
 
 def en_word(i):

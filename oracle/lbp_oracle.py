@@ -513,3 +513,168 @@ def sgd_trajectory_user_adapt(model, sentences, users_of, roots_per_epoch, users
                 row += [d2t[uu][0][0], d2t[uu][1][0]]
             traj.append(np.concatenate(row))
     return np.array(traj)
+
+
+# ----------------------------------------------------------------------------------------- chunked evaluator (large V)
+def run_chunked(model, sents, theta_ee, theta_ed, roots_list, sweeps, block=1024, workers=None):
+    """Inference (marginals, top-1, log-posterior, label rank) of several sentences at vocabulary sizes whose V x V float64
+    tables do not fit in memory (BASELINE config C5: V = 50 000 -> 20 GB per table).  Same numbers as run_fast / run_literal
+    (LBP.py:218-245, :377-400, :490-526, :247-259); the pairwise tables exp(phi . theta) (train.py:218-219, :252-253) are never
+    materialised: every schedule level of ALL sentences is contracted in one pass over row blocks of the float32 feature
+    planes, T[a0:a1, :] = exp(te0 * pmi[a0:a1, :] + te2) built on the fly in float64 and discarded.
+
+    Sentences advance in lock step through their own update sequences (generators yield the GEMV requests of their next
+    run of factor->variable updates).  `model` needs 'pmi', 'pmi_w1' (any float dtype), 'ed', 'ped'."""
+    import os as _os
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:                                                             # pragma: no cover
+        threadpool_limits = None
+    te = np.asarray(theta_ee, dtype=np.float64).reshape(3)
+    td = np.asarray(theta_ed, dtype=np.float64).reshape(6)
+    pmi, w1p = model['pmi'], model['pmi_w1']
+    V = pmi.shape[0]
+    uni = np.full(V, 1.0 / V)
+    workers = workers or min(32, _os.cpu_count() or 1)
+
+    def sentence(sent, roots):
+        g = Graph(sent)
+        unary = {}
+        for f in g.factors:
+            if f.arity != 1:
+                continue
+            if f.ftype == T_EN_DE:
+                z = td[0] * np.asarray(model['ed'][:, f.obs], dtype=np.float64) + \
+                    td[1] * np.asarray(model['ped'][:, f.obs], dtype=np.float64) + td[5]
+                for e, d, k, val in sent.sparse:
+                    if int(d) == f.obs:
+                        z[int(e)] += td[int(k)] * val
+                t = np.exp(z)
+            else:                                                                 # column of pot_en_en(_w1), LBP.py:702-703
+                z = te[0] * np.asarray(pmi[:, f.obs], dtype=np.float64) + te[2]
+                if f.gap == 1:
+                    z = z + te[1] * np.asarray(w1p[:, f.obs], dtype=np.float64)
+                t = np.exp(z)
+            unary[f.id] = t
+        uprod = {}
+        for v in g.var_ids:
+            m = uni.copy()
+            for fid in g.facset[v]:
+                if g.factors[fid].arity == 1:
+                    m = m * (unary[fid] / unary[fid].sum())
+            uprod[v] = m
+        v2f, f2v = {}, {}
+        for f in g.factors:
+            if f.arity == 2:
+                for v in f.vars:
+                    v2f[v, f.id] = uni
+                    f2v[f.id, v] = uni
+        loopy, seq = g.update_sequence(roots, sweeps)
+        i = 0
+        while i < len(seq):
+            frm, to = seq[i]
+            if frm[0] == 'X':
+                v, fid = frm[1], to[1]
+                m = uprod[v]
+                for of in g.facset[v]:
+                    if of != fid and g.factors[of].arity == 2:
+                        m = m * f2v[of, v]
+                s = m.sum()
+                v2f[v, fid] = m / s if s > 0 else uni
+                i += 1
+                continue
+            run = []
+            while i < len(seq) and seq[i][0][0] == 'F':
+                fid, v = seq[i][0][1], seq[i][1][1]
+                if g.factors[fid].arity == 2:
+                    run.append((fid, v))
+                i += 1
+            req = []
+            for fid, v in run:
+                f = g.factors[fid]
+                to_dim0 = (f.vars[0] == v)
+                o = f.vars[1] if to_dim0 else f.vars[0]
+                req.append(((f.gap == 1, to_dim0), v2f[o, fid]))
+            if req:
+                res = yield req
+                for (fid, v), row in zip(run, res):
+                    s = row.sum()
+                    f2v[fid, v] = row / s if s > 0 else uni
+        marg = []
+        for v in g.var_ids:
+            m = uprod[v]
+            for fid in g.facset[v]:
+                if g.factors[fid].arity == 2:
+                    m = m * f2v[fid, v]
+            s = m.sum()
+            marg.append(m / s if s > 0 else uni)
+        marg = np.stack(marg)
+        logp = 0.0
+        for i_, v in enumerate(g.var_ids):
+            p = marg[i_, g.label[v]]
+            logp += np.log(p) if p > 0 else -99.99
+        z13 = np.zeros((1, 3)); z16 = np.zeros((1, 6))
+        return _finish(g, loopy, marg, logp, z13, z16, te.reshape(1, 3), td.reshape(1, 6), 0.0, 1.0)
+
+    def contract(requests):
+        """requests: list of (key, vector); key = (gap1, to_dim0).  One pass over the row blocks of the planes."""
+        by_key = {}
+        for n, (key, vec) in enumerate(requests):
+            by_key.setdefault(key, []).append(n)
+        M = {key: np.stack([requests[n][1] for n in idx]) for key, idx in by_key.items()}
+        need_w1 = any(k[0] for k in M)
+        out = {key: np.zeros((len(idx), V)) for key, idx in by_key.items()}
+        blocks = [(a0, min(V, a0 + block)) for a0 in range(0, V, block)]
+        n_w = max(1, min(workers, len(blocks)))
+        partial = [{key: np.zeros((len(idx), V)) for key, idx in by_key.items() if not key[1]} for _ in range(n_w)]
+
+        def work(w):
+            for bi in range(w, len(blocks), n_w):
+                a0, a1 = blocks[bi]
+                Tb = np.exp(te[0] * np.asarray(pmi[a0:a1], dtype=np.float64) + te[2])
+                T1b = Tb * np.exp(te[1] * np.asarray(w1p[a0:a1], dtype=np.float64)) if need_w1 else None
+                for key, m in M.items():
+                    tb = T1b if key[0] else Tb
+                    if key[1]:                                                    # out[a] = sum_b T[a, b] m[b]
+                        out[key][:, a0:a1] = m.dot(tb.T)
+                    else:                                                         # out[b] = sum_a m[a] T[a, b]
+                        partial[w][key] += m[:, a0:a1].dot(tb)
+
+        from contextlib import nullcontext
+        with (threadpool_limits(limits=1, user_api='blas') if threadpool_limits else nullcontext()):
+            with ThreadPoolExecutor(n_w) as ex:                                   # NumPy releases the GIL inside exp / dot
+                list(ex.map(work, range(n_w)))
+        for key in out:
+            if not key[1]:
+                for w in range(n_w):
+                    out[key] += partial[w][key]
+        res = [None] * len(requests)
+        for key, idx in by_key.items():
+            for j, n in enumerate(idx):
+                res[n] = out[key][j]
+        return res
+
+    gens = [sentence(s, r) for s, r in zip(sents, roots_list)]
+    results = [None] * len(gens)
+    pending = {}
+    for i, gen in enumerate(gens):
+        try:
+            pending[i] = next(gen)
+        except StopIteration as e:
+            results[i] = e.value
+    while pending:
+        order = sorted(pending)
+        flat = [rq for i in order for rq in pending[i]]
+        res = contract(flat)
+        pos = 0
+        nxt = {}
+        for i in order:
+            n = len(pending[i])
+            try:
+                nxt[i] = gens[i].send(res[pos:pos + n])
+            except StopIteration as e:
+                results[i] = e.value
+            pos += n
+        pending = nxt
+    return results

@@ -1,0 +1,89 @@
+"""GPU tier: the reduced-pass GEMM rows on HOSTILE data.  Engine.set_theta enables two-pass / one-pass gradient rows (and, at
+large V, two-pass message rows) from the span of the potentials; these tests put sparse feature planes (real PMI matrices are
+mostly zeros), theta at the edge of that gate, and hand-peaked sentences (a sparse history feature with a large weight puts
+~40 % of a belief on one word) together at V >= 4608, against the float64 oracle: gradients 1e-4 relative (LBP.py:544-569,
+:610), exact top-1, beliefs."""
+import numpy as np
+import pytest
+
+import common_checks
+from macaronicusermodeling_b200 import build, synth
+from macaronicusermodeling_b200.engine import Corpus, Engine
+from oracle import lbp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _built():
+    build.build()
+
+
+def _peaked_sentences(model, n, k, g, seed):
+    """sentences whose history features hit their own German words (train.py:190-215), several times over"""
+    sents = []
+    for i in range(n):
+        raw = synth.make_sentence(model, 'p' * k + 'g' * g, seed=seed + i, n_history=6, p_correct=0.6)
+        sents.append(synth.sentence_to_arrays(raw))
+    return sents
+
+
+CASES = {
+    # name: (pmi_density, w1_density, theta_ee, theta_ed)
+    'dense_edge': (1.0, 1.0, [1.9, 1.0, -0.3], [1.6, -1.3, 0.5, 0.3, 0.4, -0.2]),           # span 2.9 of the e^3 gate
+    'sparse_pmi': (0.1, 1.0, [1.9, 1.0, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]),
+    'sparse_both_peaked': (0.1, 0.05, [2.0, 0.9, -0.5], [1.2, -0.8, 8.0, 6.0, 3.0, -0.2]),    # history weights: peaked beliefs
+    'sparse_w1_negative': (0.3, 0.05, [-1.8, 1.1, 0.2], [1.0, -0.6, 7.0, 0.3, 0.4, -0.2]),
+}
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_reduced_pass_rows_on_sparse_and_peaked_data(name):
+    pd, wd, te, td = CASES[name]
+    V = 4608
+    model = synth.make_model(V, 256, seed=77, dtype=np.float32, pmi_density=pd, w1_density=wd)
+    sents = _peaked_sentences(model, 5, k=9, g=2, seed=300)
+    roots = synth.draw_roots(sents, 3, seed=6)
+    eng_holder = {}
+
+    def make_engine(m):
+        eng_holder['e'] = Engine(m)
+        return eng_holder['e']
+
+    m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
+    r, corpus = common_checks.run_engine(make_engine, model, sents, te, td, roots, 3)
+    eng = eng_holder['e']
+    assert eng.grad_one_pass_ok, 'the case must sit INSIDE the gate (otherwise it tests nothing)'
+    tb = orc.Tables(m64, te, td)
+    off = corpus.var_off
+    B, T1, LP, G = (x.cpu().numpy() for x in (r.beliefs, r.top1, r.logp, r.grad))
+    worst_g = worst_b = peak = 0.0
+    for i, s in enumerate(sents):
+        o = orc.run_fast(tb, s, roots[i], 3)
+        b = B[off[i]:off[i + 1], :V]
+        peak = max(peak, float(o['marginals'].max()))
+        worst_b = max(worst_b, float(np.abs(b - o['marginals']).max()))
+        np.testing.assert_array_equal(T1[off[i]:off[i + 1]], o['top1'])
+        ref = np.concatenate([o['g_ee_unreg'][0], o['g_ed_unreg'][0]])
+        np.testing.assert_allclose(G[i], ref, rtol=1e-4, atol=2e-6)
+        nz = np.abs(ref) > 1e-3
+        worst_g = max(worst_g, float((np.abs(G[i] - ref)[nz] / np.abs(ref)[nz]).max()))
+        np.testing.assert_allclose(LP[i], o['logp'], rtol=2e-6)
+    print('%s: largest belief %.3f, worst belief abs err %.2e, worst rel gradient err %.2e' % (name, peak, worst_b, worst_g))
+    assert worst_b < 1e-5                      # contract: 1e-4
+    if 'peaked' in name:
+        assert peak > 0.2, 'the peaked case must actually be peaked'
+
+
+def test_c3_full_size_six_sentences_vs_oracle():
+    """BASELINE config C3 at full size (V = 10 000, Vd = 2 000, k = 20, 3 sweeps), six sentences = 120 variables and 1 140
+    pairwise factors against the float64 oracle: exact top-1, beliefs, log-posterior, gradients, label ranks (the 24-sentence
+    run of scripts/c3_parity_check.py is the larger one-off under profiles/)."""
+    model = synth.make_model(10000, 2000, seed=1234, dtype=np.float32)
+    sents = synth.make_corpus(model, 6, k=20, g=0, seed=4242)
+    roots = synth.draw_roots(sents, 3, seed=11)
+    m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
+    worst = common_checks.check_against_oracle(lambda m: Engine(m), m64, sents, roots, [0.8, 0.5, -0.3],
+                                               [1.0, -0.6, 0.5, 0.3, 0.4, -0.2])
+    assert worst < 1e-7
+    print('C3 x 6 worst belief abs err', worst)

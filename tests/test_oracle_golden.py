@@ -117,3 +117,22 @@ def test_user_adapt_trajectory_matches_reference():
     traj = orc.sgd_trajectory_user_adapt(model, sents, [r['user_id'] for r in raw], z['roots'].tolist(), users,
                                          epochs=2, ua_scale=0.5)
     np.testing.assert_allclose(traj, z['traj'], rtol=1e-8, atol=1e-12)
+
+
+def test_chunked_evaluator_matches_fast():
+    """run_chunked (tables built on the fly in row blocks: the checker of BASELINE config C5 at V = 50 000) gives run_fast's
+    numbers, incl. given tokens (unary en_en columns), a tree, a single variable and 10 sweeps"""
+    model = synth.make_model(300, 40, seed=3, dtype=np.float32)
+    lay = ['ppppp', 'pgppgp', 'pp', 'p', 'pprpp']
+    sents = [synth.sentence_to_arrays(synth.make_sentence(model, l, seed=5 + i, n_history=3)) for i, l in enumerate(lay)]
+    roots = synth.draw_roots(sents, 10, seed=2)
+    te, td = [0.8, 0.5, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]
+    m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
+    tb = orc.Tables(m64, te, td)
+    res = orc.run_chunked(model, sents, te, td, roots, 10, block=64, workers=3)
+    for s, r, o in zip(sents, roots, res):
+        f = orc.run_fast(tb, s, r, 10, want_grad=False)
+        assert np.abs(f['marginals'] - o['marginals']).max() < 1e-15
+        np.testing.assert_array_equal(f['top1'], o['top1'])
+        np.testing.assert_array_equal(f['label_rank'], o['label_rank'])
+        assert abs(f['logp'] - o['logp']) < 1e-12
