@@ -123,11 +123,15 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   readers a message usually has (a message GEMM row and a gradient-stage row).  in_row < 0 means "uniform message": the kernels read the
  *   constant-one row D[0] in its place (messages are scale-free), so the caller keeps D row 0 filled with 1.0f.
  *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
- *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow). */
+ *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow).
+ *   peak_flag (optional, may be NULL): device int32 that is SET to 1 (never cleared) when any element of any message
+ *   written by this call exceeds the probability peak_prob.  mlbp_factor_to_var_gemm_gated reads it: a message whose
+ *   mass sits on few words does not average its fp16 rounding away, so rows written after the flag went up keep
+ *   all three tensor-core passes.                                                                              */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                        const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
-                       void *A_lo, int max_in, float range_log2, void *stream);
+                       void *A_lo, int max_in, float range_log2, int32_t *peak_flag, float peak_prob, void *stream);
 /* Approximate paths (use_approx_inference LBP.py:506-507, :515-516 -> au.sparse_vec_mat_dot pyx:193-205;
  *   use_approx_beliefs LBP.py:554-563 -> au.sparse_dot / sparse_pointwise_multiply / sparse_normalize pyx:108-129, :23-26):
  *   keep the K largest entries of each of the n_rows operand rows A[row0 ..], zero the others (K = 100 in the reference);
@@ -137,7 +141,9 @@ int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, in
  *   D[d_row0 + r, n] = alpha * sum_k (A_hi + A_lo)[a_row0 + r, k] * (B_hi + B_lo)[n, k],  r < n_rows, n < V
  *   as three tcgen05 passes hi*hi + hi*lo + lo*hi with fp32 accumulation in tensor memory.
  *   A_*: [a_rows_total, ldv] fp16, B_*: one plane pair [V, ldv] fp16, D: [*, ldd] fp32.
- *   impl: 0 = tcgen05 (product path), 1 = SIMT cross-check kernel (tests only); OR-ed with MLBP_GEMM_A_HI_ONLY the
+ *   impl: 0 = tcgen05 (product path: the CTA-pair kernel for V > 2048, the one-CTA kernel below), 1 = SIMT cross-check
+ *   kernel (tests only), 2 / 3 = the CTA-pair / one-CTA kernel of the product path at any V (tests); further tile and
+ *   pipeline variants exist only in a -DMLBP_PROBES build (scripts/gemm_probe.py).  OR-ed with MLBP_GEMM_A_HI_ONLY the
  *   A_lo term is dropped (two passes hi*hi + hi*lo, A_lo is not even loaded).  The gradient stage uses it: the
  *   expectation N/Z of a pairwise belief is a RATIO of two rows computed from the same message r, so the 2^-12
  *   rounding of r largely cancels (measured <= 2e-7 relative on a sentence's gradient; the contract is 1e-4).      */
@@ -150,14 +156,46 @@ int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, in
 int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                             const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
                             float alpha, int impl, void *stream);
+/* The same launch, DECIDED ON THE DEVICE: every CTA first reads *gate (device int32) and returns at once unless
+ * (*gate != 0) == (run_if_set != 0).  The engine issues a level's message rows twice -- two passes (A_HI_ONLY) with
+ * run_if_set = 0 and all three passes with run_if_set = 1 -- on the flag that mlbp_var_to_factor raises when it writes
+ * a peaked message; exactly one of the two launches does the work and no host synchronisation is needed.
+ * gate == NULL runs unconditionally.  tcgen05 kernels only (impl 1, the SIMT cross-check, ignores the gate on the host: error). */
+int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
+                                  const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
+                                  float alpha, int impl, const int32_t *gate, int run_if_set, void *stream);
 /* K5.  VariableNode.get_marginal / get_posterior_probs / get_precision_counts / argmax
  *   (LBP.py:392-411, :247-259, :80-106).  Same group layout as K3, all inputs multiplied.
  *   logp[g] = log b[label] (-99.99 if b[label] == 0), top1[g] = argmax b (first index on ties),
  *   rank[g] = #{e : b[e] > b[label]}, beliefs (optional, may be NULL): [n_groups, ldv] fp32 normalised.
- *   range_log2 as in mlbp_var_to_factor (bound for ALL incoming messages of a variable; at most 64 of them).    */
+ *   range_log2 as in mlbp_var_to_factor (bound for ALL incoming messages of a variable); max_in = the largest number of
+ *   incoming pairwise messages of any variable (MLBP_ERR_UNSUPPORTED above 64).
+ *   Near-tie detection (flags != NULL, else the five pointers may be NULL): flags[g] bit 0 = the runner-up product is within
+ *   the relative band tau of the largest, bit 1 = some other candidate is within tau_label of the label's product while at
+ *   most 50 candidates are certainly above the label (its rank can still decide P@25 / P@50, LBP.py:80-106);
+ *   aux[g] = {largest product, label's product} (float64), cnts[g] = {#products > label's, #of those inside the band};
+ *   flagged[0 .. *n_flagged) lists the variables with flags != 0 (atomic append: zero *n_flagged before the call).   */
 int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                    const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
-                   int32_t *top1, int32_t *rank, float *beliefs, float range_log2, void *stream);
+                   int32_t *top1, int32_t *rank, float *beliefs, float range_log2, int max_in, float tau,
+                   float tau_label, double *aux, int32_t *cnts, int32_t *flags, int32_t *flagged, int32_t *n_flagged,
+                   void *stream);
+/* K5b. Exact re-score of the flagged variables' near-tied candidates (LBP.py:392-411: arg-max; :80-106: label rank).
+ *   For every candidate e inside the bands of mlbp_marginals and every incoming message row the ONE element
+ *   D_j[e] = sum_k (A_hi + A_lo)[row_j, k] * (B_hi + B_lo)[table_j][e, k] is recomputed from the full 22-bit operands
+ *   (fp32 products, float64 reduction), the ratios are multiplied in float64, and top1[g] / rank[g] are overwritten with
+ *   the decisions taken on those values.  This makes the last hop into a belief -- the only place where the rounding of a
+ *   reduced-pass message row is not damped by a later contraction -- exact wherever it can change a decision.
+ *   msg_blocks: the plan's flat list of message GEMM blocks, 4 int32 each {table, first A row, first D row, rows}, ascending
+ *   (blob header H_MSG_BLK_*); a D row r of a message block has A row r - MLBP_D_CONST_ROWS.  planes / plane_stride as in
+ *   mlbp_build_pairwise_tables.  counters[8] (device int32, accumulated): [0] variables re-scored, [1] skipped (more than 64
+ *   candidates: a mass tie), [2] skipped (degenerate products), [3] arg-max decisions changed, [4] ranks changed.          */
+int mlbp_rescore_candidates(int n_vars, const int32_t *flagged, const int32_t *n_flagged, const int32_t *flags,
+                            const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row, const int32_t *label,
+                            const float *U, const float *D, int ldv, int V, const void *A_hi, const void *A_lo,
+                            const void *planes, int64_t plane_stride, const int32_t *msg_blocks, int n_blocks,
+                            int n_msg_rows, const double *aux, const int32_t *cnts, float tau, float tau_label,
+                            float range_log2, int32_t *top1, int32_t *rank, int32_t *counters, void *stream);
 /* K6a. pairwise factor beliefs contracted with the features (LBP.py:544-569 + :610) in closed form:
  *   stats[f] = { z.u0, c.u1, c.u2 } with c = (A_hi + A_lo)[c_row[f]], z = (A_hi + A_lo)[z_row[f]],
  *   u* = D[u*_row[f]] (u2_row < 0 -> 0).  z_row == c_row with u0 = T r, or z_row = the r row with u0 = T'c
@@ -174,6 +212,14 @@ int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t 
                          const double *pair_stats, const int32_t *pair_l0, const int32_t *pair_l1,
                          const int32_t *pair_gap1, const float *pmi, const float *pmi_w1, int ldf,
                          const double *logp_var, double *grad, double *logp_sent, void *stream);
+
+/* 0, or the code of the mbarrier wait (1 = stage empty, 2 = stage full, 3 = accumulator full, 4 = accumulator drained) that
+ * exceeded its ~4 s bound inside a tcgen05 GEMM kernel: the kernel records it in mapped host memory and traps (the launch
+ * fails with a CUDA error) instead of hanging the GPU.                                                              */
+int mlbp_gemm_barrier_timeout_code(void);
+
+/* zero n device int32 words on the stream: the flag / counter words the kernels above communicate through */
+int mlbp_zero_words(int32_t *words, int n, void *stream);
 
 /* probe hook (scripts/k3_probe.py): per-CTA stage cycle counters of the resident K3 kernel are written to p[6 * CTA]
  * when the library is built with -DMLBP_K3_STAGE_TIMES; a no-op otherwise.  NULL switches it off.               */

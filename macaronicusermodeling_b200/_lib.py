@@ -18,10 +18,13 @@ _SIGNATURES = {
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
     'mlbp_fill_uniform_rows': 'ppiipipp',
-    'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppifp',
+    'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppif' + 'pfp',
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
-    'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppfp',
+    'mlbp_factor_to_var_gemm_gated': 'pplii' + 'ppii' + 'plifi' + 'pip',
+    'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppf' + 'iff' + 'ppppp' + 'p',
+    'mlbp_rescore_candidates': 'ippp' + 'pppp' + 'ppii' + 'pppl' + 'pii' + 'ppff' + 'f' + 'ppp' + 'p',
+    'mlbp_zero_words': 'pip',
     'mlbp_pair_expectations': 'ippppp' + 'pppii' + 'pp',
     'mlbp_gradient_reduce': 'ippppppp' + 'ppi' + 'pppp',
     'mlbp_plan_compile': 'ipppppp' + 'iip',
@@ -64,7 +67,7 @@ def load():
 def exported_symbols():
     """Every symbol include/mlbp.h declares (used by the CPU-side ABI test)."""
     return sorted(list(_SIGNATURES) + ['mlbp_last_error', 'mlbp_version', 'mlbp_device_ok', 'mlbp_plan_destroy',
-                                       'mlbp_debug_k3_times'])
+                                       'mlbp_debug_k3_times', 'mlbp_gemm_barrier_timeout_code'])
 
 
 def require_device():

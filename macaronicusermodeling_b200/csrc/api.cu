@@ -31,3 +31,11 @@ extern "C" int mlbp_device_ok(void) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
     return major == 10 ? 1 : 0;
 }
+
+/* zero n int32 words on the stream (flags and counters the kernels communicate through) */
+extern "C" int mlbp_zero_words(int32_t *p, int n, void *stream) {
+    if (n == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(p && n > 0, "zero_words: bad argument");
+    MLBP_CUDA(cudaMemsetAsync(p, 0, sizeof(int32_t) * (size_t)n, mlbp::as_stream(stream)));
+    return MLBP_OK;
+}

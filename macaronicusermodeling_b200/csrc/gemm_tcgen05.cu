@@ -160,8 +160,11 @@ __global__ void __launch_bounds__(Cfg<BN, STAGES, BK>::THREADS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                       float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                      int m_tiles, int n_tiles, int a_terms, int b_terms, int *err_flag) {
+                      int m_tiles, int n_tiles, int a_terms, int b_terms, const int32_t *__restrict__ gate, int run_if_set,
+                      int *err_flag) {
     using C = Cfg<BN, STAGES, BK>;
+    // device-side launch decision (mlbp_factor_to_var_gemm_gated): the whole grid returns unless the gate matches
+    if (gate != nullptr && ((*reinterpret_cast<const volatile int32_t *>(gate) != 0) != (run_if_set != 0))) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * C::STAGE_BYTES);
@@ -396,8 +399,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES, A_T,
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                            float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                           int m_pairs, int n_tiles, int narrow_last, int *err_flag) {
+                           int m_pairs, int n_tiles, int narrow_last, const int32_t *__restrict__ gate, int run_if_set,
+                           int *err_flag) {
     using C = PairCfg<STAGES, A_T, B_T>;
+    // device-side launch decision (mlbp_factor_to_var_gemm_gated): every CTA of every pair reads the same word, written by an
+    // earlier kernel of the stream, and returns before any barrier or tensor-memory allocation unless the gate matches
+    if (gate != nullptr && ((*reinterpret_cast<const volatile int32_t *>(gate) != 0) != (run_if_set != 0))) return;
     constexpr int a_terms = A_T, b_terms = B_T;
     constexpr int BN = C::BN, BK = C::BK;
     extern __shared__ uint8_t smem_raw[];
@@ -627,7 +634,7 @@ static int *g_err_flag = nullptr;   // pinned, mapped: the kernel records which 
 template <int BN, int STAGES, int CHUNK_KB, int BK = 64>
 static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                      const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                     int b_terms, cudaStream_t st) {
+                     int b_terms, const int32_t *gate, int run_if_set, cudaStream_t st) {
     using C = Cfg<BN, STAGES, BK>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
@@ -649,7 +656,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_tiles = (n_rows + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
     gemm_split_f16_kernel<BN, STAGES, CHUNK_KB, BK><<<m_tiles * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, a_terms, b_terms, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, a_terms, b_terms, gate, run_if_set, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -657,7 +664,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
 template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE = false>
 static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                          const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int narrow_last,
-                         cudaStream_t st) {
+                         const int32_t *gate, int run_if_set, cudaStream_t st) {
     using C = PairCfg<STAGES, A_T, B_T>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
@@ -679,7 +686,7 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
     gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, narrow_last, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, narrow_last, gate, run_if_set, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -693,9 +700,9 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false, int CHUNK_11 = CHUNK_KB>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                        const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                       int b_terms, int narrow_last, cudaStream_t st) {
+                       int b_terms, int narrow_last, const int32_t *gate, int run_if_set, cudaStream_t st) {
 #define MLBP_PAIR(S, AT, BT, CH) \
-    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, narrow_last, st)
+    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, narrow_last, gate, run_if_set, st)
     if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2, CHUNK_KB);
     if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2, CHUNK_KB);
     if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1, CHUNK_KB);
@@ -709,9 +716,9 @@ using namespace mlbp;
 
 extern "C" int mlbp_gemm_barrier_timeout_code(void) { return g_err_flag ? *g_err_flag : 0; }
 
-extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
-                                       int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
-                                       int64_t d_row0, int ldd, float alpha, int impl, void *stream) {
+static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
+                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int impl,
+                         const int32_t *gate, int run_if_set, void *stream) {
     if (n_rows == 0) return MLBP_OK;
     MLBP_CHECK_ARG(A_hi && A_lo && B_hi && B_lo && D, "factor_to_var_gemm: null pointer");
     MLBP_CHECK_ARG(n_rows > 0 && V > 0 && a_row0 >= 0 && a_row0 + (int64_t)n_rows <= a_rows_total,
@@ -725,16 +732,19 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
     const int a_terms = (impl & MLBP_GEMM_A_HI_ONLY) ? 1 : 2, b_terms = (impl & MLBP_GEMM_B_HI_ONLY) ? 1 : 2;
     const int narrow_last = (impl & MLBP_GEMM_NARROW_LAST) ? 1 : 0;
     impl &= ~(MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY | MLBP_GEMM_NARROW_LAST);
-    if (impl == 1)
+    if (impl == 1) {
+        MLBP_CHECK_ARG(gate == nullptr, "factor_to_var_gemm_gated: the SIMT cross-check kernel has no device-side gate");
         return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
-    // impl 0: product configuration (CTA-pair kernel for large V).  impl 10..: one-CTA variants, impl 30..: CTA-pair
-    // variants, exposed for scripts/gemm_probe.py and the kernel tests only.
-#define MLBP_TC(BN_, ST_, CH_) \
-    return launch_tc<BN_, ST_, CH_>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st)
+    }
+#define MLBP_ARGS A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms
+#define MLBP_TC(BN_, ST_, CH_) return launch_tc<BN_, ST_, CH_>(MLBP_ARGS, gate, run_if_set, st)
     switch (impl) {
-        case 0:                                       // product configuration
-            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);
+        case 0:                                       // product configuration: CTA-pair kernel for large V
+            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
             MLBP_TC(128, 3, 2);
+        case 2: return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, narrow_last, gate, run_if_set, st);   // the CTA-pair kernel at any V (tests)
+        case 3: MLBP_TC(128, 3, 2);                                                                        // the one-CTA kernel at any V (tests)
+#ifdef MLBP_PROBES                                    // variants for scripts/gemm_probe.py only (build with -DMLBP_PROBES)
         case 10: MLBP_TC(256, 2, 1);
         case 11: MLBP_TC(256, 2, 2);
         case 12: MLBP_TC(256, 2, 4);
@@ -743,20 +753,33 @@ extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
-        case 30: return launch_pair<2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);
-        case 31: return launch_pair<1>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);
-        case 33:                                      // = impl 0 at large V; impl 30 is the same kernel without the A collector reuse
-            return launch_pair<2, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);
-        case 34: return launch_pair<4, 3, 4, 6, true>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);      // all rows drained every 4 k-blocks
-        case 35: return launch_pair<2, 3, 4, 6, true, 8>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);   // one-pass rows drained every 8
-        case 36: return launch_pair<2, 3, 4, 6, true, 2>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);   // ... every 2 (the product path before)
-        case 32: return launch_pair<2, 2, 3, 3>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, narrow_last, st);
-        case 20: return launch_tc<256, 4, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
-        case 21: return launch_tc<256, 4, 2, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
-        case 22: return launch_tc<128, 6, 4, 32>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
+        case 30: return launch_pair<2>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
+        case 31: return launch_pair<1>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
+        case 33: return launch_pair<2, 3, 4, 6, true>(MLBP_ARGS, narrow_last, gate, run_if_set, st);       // one-pass rows drained every 2 too
+        case 34: return launch_pair<4, 3, 4, 6, true>(MLBP_ARGS, narrow_last, gate, run_if_set, st);       // all rows drained every 4 k-blocks
+        case 35: return launch_pair<2, 3, 4, 6, true, 8>(MLBP_ARGS, narrow_last, gate, run_if_set, st);    // one-pass rows drained every 8
+        case 32: return launch_pair<2, 2, 3, 3>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
+        case 20: return launch_tc<256, 4, 4, 32>(MLBP_ARGS, gate, run_if_set, st);
+        case 21: return launch_tc<256, 4, 2, 32>(MLBP_ARGS, gate, run_if_set, st);
+        case 22: return launch_tc<128, 6, 4, 32>(MLBP_ARGS, gate, run_if_set, st);
+#endif
         default: break;
     }
 #undef MLBP_TC
-    set_error("factor_to_var_gemm: unknown impl %d", impl);
+#undef MLBP_ARGS
+    set_error("factor_to_var_gemm: unknown impl %d (probe variants need a -DMLBP_PROBES build)", impl);
     return MLBP_ERR_INVALID;
+}
+
+extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
+                                       int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
+                                       int64_t d_row0, int ldd, float alpha, int impl, void *stream) {
+    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, nullptr, 0, stream);
+}
+
+extern "C" int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
+                                             int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
+                                             int64_t d_row0, int ldd, float alpha, int impl, const int32_t *gate,
+                                             int run_if_set, void *stream) {
+    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, gate, run_if_set, stream);
 }

@@ -72,7 +72,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                      const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
                      const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V,
-                     __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
+                     __half *__restrict__ A_hi, __half *__restrict__ A_lo, int32_t *__restrict__ peak_flag, float peak_limit) {
     __shared__ const float *s_src[NMAX];
     __shared__ int s_d0[NMAX], s_nd[NMAX];
     __shared__ size_t s_first[NMAX];
@@ -132,6 +132,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     // ---- phase 2: recompute, normalise, split, scatter to the consuming GEMM blocks
     // (walking the columns backwards to catch the L2-resident tail of phase 1 was measured 12 % slower)
     const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
+    float mx = 0.f;                                               // largest element written (2^14 * probability)
     for (int e = threadIdx.x; e < V; e += K3_THREADS) {
         float d[NMAX];
 #pragma unroll
@@ -147,11 +148,13 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
             if (nd > 0) {
                 const float sc = s_scale[j];
                 const float x = sc > 0.f ? (float)(pre[j] * suf * (T)sc) : uni;
+                mx = fmaxf(mx, x);
                 k3_store(x, s_first[j] + e, nd, dest, s_d0[j], ldv, e, A_hi, A_lo);
             }
             suf *= (T)d[j];
         }
     }
+    if (peak_flag && !(mx <= peak_limit)) *peak_flag = 1;         // a peaked message: see mlbp_var_to_factor
 }
 
 // Messages with more than TWO readers (the first two are written directly): the slice just written to the first reader's
@@ -192,7 +195,8 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                               const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                               const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
                               const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V, int S,
-                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, long long *dbg) {
+                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, int32_t *__restrict__ peak_flag, float peak_limit,
+                              long long *dbg) {
 #ifdef MLBP_K3_STAGE_TIMES                                      // scripts/k3_probe.py: cycles per stage, per CTA
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define K3_TICK(i) do { const long long tn_ = clock64(); tacc[i] += tn_ - tprev; tprev = tn_; } while (0)
@@ -272,6 +276,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     // loops are written as straight-line code (no branch on a value loaded inside the loop): measured with clock64
     // per stage, a data-dependent branch per input cost ~100 cycles per input and column pair.
     const int npair = (ncol + 1) >> 1;
+    float mx = 0.f;                                                // largest element written (2^14 * probability)
     for (; g < n_groups; g += n_clusters, b ^= 1) {
         if (ncol > 0) {
             if (threadIdx.x == 0)
@@ -402,6 +407,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                     const float sc = s_scale[j];
                     float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
                     if (!(sc > 0.f)) x = make_float2(uni, uni);
+                    mx = fmaxf(mx, fmaxf(x.x, odd ? 0.f : x.y));
                     const __half2 hi = __float22half2_rn(x);
                     const float2 back = __half22float2(hi);
                     const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
@@ -452,6 +458,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         __syncthreads();                                           // shared memory is reused by the next group
         K3_TICK(5);
     }
+    if (peak_flag && !(mx <= peak_limit)) *peak_flag = 1;          // a peaked message: see mlbp_var_to_factor
 #ifdef MLBP_K3_STAGE_TIMES
     if (dbg && threadIdx.x == 0)
         for (int i = 0; i < 6; ++i) dbg[(size_t)blockIdx.x * 6 + i] = tacc[i];
@@ -501,63 +508,90 @@ topk_mask_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int 
     }
 }
 
-// one CTA per variable: total product of all incoming messages (T = float under the same range bound as K3)
+// one CTA per variable: total product of all incoming messages (T = float under the same range bound as K3).
+// Optional near-tie detection (flags != nullptr; see rescore.cu): besides the arg-max and the label's rank the kernel keeps
+// the SECOND largest product and counts the candidates inside a relative band around the label's product; variables whose
+// decisions an error of relative size << tau could change are appended to `flagged` for the exact re-score.
 template <typename T>
 __global__ void __launch_bounds__(256)
 marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                  const int32_t *__restrict__ in_row, const int32_t *__restrict__ label, const float *__restrict__ U,
                  const float *__restrict__ D, int ldv, int V, double *__restrict__ logp, int32_t *__restrict__ top1,
-                 int32_t *__restrict__ rank, float *__restrict__ beliefs) {
+                 int32_t *__restrict__ rank, float *__restrict__ beliefs, float tau, float tau_label,
+                 double *__restrict__ aux, int32_t *__restrict__ cnts, int32_t *__restrict__ flags,
+                 int32_t *__restrict__ flagged, int32_t *__restrict__ n_flagged) {
     __shared__ double red[32];
-    __shared__ T s_best[8];
+    __shared__ T s_best[8], s_second[8];
     __shared__ int s_besti[8];
     const int g = blockIdx.x;
     const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
     const float *urow = U + (size_t)grp_u[g] * ldv;
     const int lab = label[g];
     __shared__ const float *s_rows[64];
-    const int nn = min(n, 64);
+    const int nn = min(n, 64);                                    // the host entry point rejects n > 64
     if (threadIdx.x < 64) {
         const int r = threadIdx.x < nn ? in_row[i0 + threadIdx.x] : -1;
         s_rows[threadIdx.x] = r >= 0 ? D + (size_t)r * ldv : nullptr;
     }
     __syncthreads();
-    auto prod = [&](int e) {
+    auto prod = [&](int e) {                                      // rescore.cu evaluates the same expression in the same order
         T p = (T)__ldg(urow + e);
         for (int j = 0; j < nn; ++j)
             if (s_rows[j]) p *= (T)__ldg(s_rows[j] + e);
         return p;
     };
     const T plab = prod(lab);
-    T sp = (T)0, best = (T)-1;
-    int besti = 0x7fffffff, cnt = 0;
+    const T lab_lo = plab * (T)(1.0f - tau_label), lab_hi = plab * (T)(1.0f + tau_label);
+    T sp = (T)0, best = (T)-1, second = (T)-1;
+    int besti = 0x7fffffff, cnt = 0, near_hi = 0, near_lo = 0;
     for (int e = threadIdx.x; e < V; e += blockDim.x) {
         const T p = prod(e);
         sp += p;
         cnt += (p > plab) ? 1 : 0;
-        if (p > best) { best = p; besti = e; }                    // strided ascending e: first index wins per thread
+        near_hi += (p > plab && p <= lab_hi) ? 1 : 0;
+        near_lo += (e != lab && p <= plab && p >= lab_lo) ? 1 : 0;
+        if (p > best) { second = best; best = p; besti = e; }     // strided ascending e: first index wins per thread
+        else if (p > second) second = p;
     }
     double s = block_sum((double)sp, red);
     const double c = block_sum((double)cnt, red);
-    // argmax with first-index tie break (np.argmax)
+    const double nh = block_sum((double)near_hi, red), nl = block_sum((double)near_lo, red);
+    // argmax with first-index tie break (np.argmax); the runner-up value rides along
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const T ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
         const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        const T lose = ob < best ? ob : best;                     // the smaller of the two bests is a runner-up candidate
+        second = second > os ? second : os;
+        second = second > lose ? second : lose;
         if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_besti[threadIdx.x >> 5] = besti; }
+    if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_besti[threadIdx.x >> 5] = besti; s_second[threadIdx.x >> 5] = second; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            const T lose = s_best[w] < best ? s_best[w] : best;
+            second = second > s_second[w] ? second : s_second[w];
+            second = second > lose ? second : lose;
             if (s_best[w] > best || (s_best[w] == best && s_besti[w] < besti)) { best = s_best[w]; besti = s_besti[w]; }
+        }
         const bool ok = s > 0.0 && isfinite(s);
         // renormalize falls back to uniform when the sum is not positive (LBP.py:650-657)
         const double b = ok ? (double)plab / s : 1.0 / (double)V;
         logp[g] = b > 0.0 ? log(b) : -99.99;                      // LBP.py:252-258
         top1[g] = ok ? besti : 0;
         rank[g] = ok ? (int)(c + 0.5) : 0;
+        if (flags) {
+            const int icnt = (int)(c + 0.5), inh = (int)(nh + 0.5), inl = (int)(nl + 0.5);
+            int f = 0;
+            if (ok && V > 1 && second >= best * (T)(1.0f - tau)) f |= 1;                 // the arg-max has a neighbour inside tau
+            if (ok && (inh + inl) > 0 && icnt - inh <= 50) f |= 2;                        // the label's rank can change and can matter
+            flags[g] = f;
+            aux[2 * (size_t)g] = (double)best; aux[2 * (size_t)g + 1] = (double)plab;
+            cnts[2 * (size_t)g] = icnt; cnts[2 * (size_t)g + 1] = inh;
+            if (f) flagged[atomicAdd(n_flagged, 1)] = g;
+        }
     }
     if (beliefs) {
         const bool ok = s > 0.0 && isfinite(s);
@@ -587,7 +621,8 @@ template <int NIN>
 static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, const int32_t *grp_u,
                                    const int32_t *grp_off, const int32_t *in_row, const int32_t *dest_off,
                                    const int32_t *dest, const int32_t *first_dest, const int32_t *second_dest, const float *U,
-                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo) {
+                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo, int32_t *peak_flag,
+                                   float peak_limit) {
     static bool configured = false;
     auto kern = var_to_factor_resident_kernel<NIN>;
     if (!configured) {
@@ -618,7 +653,7 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     const int n_clusters = n_groups < resident[C] ? n_groups : resident[C];
     cfg.gridDim = dim3((unsigned)n_clusters * (unsigned)C);
     return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv,
-                              V, S, A_hi, A_lo, g_k3_dbg);
+                              V, S, A_hi, A_lo, peak_flag, peak_limit, g_k3_dbg);
 }
 
 constexpr int K3_RESIDENT_MAX_IN = 24;
@@ -626,7 +661,8 @@ constexpr int K3_RESIDENT_MAX_IN = 24;
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                                   const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                                   const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
-                                  void *A_lo, int max_in, float range_log2, void *stream) {
+                                  void *A_lo, int max_in, float range_log2, int32_t *peak_flag, float peak_prob,
+                                  void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && second_dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
@@ -638,6 +674,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = as_stream(stream);
+    const float peak_limit = ldexpf(peak_prob, MLBP_A_SCALE_LOG2);   // rows are stored as 2^14 * probability
     // The resident single-read kernel runs whenever the products fit fp32 and the cluster's slices fit shared memory;
     // MLBP_K3_IMPL=1 forces the streaming two-read kernel (used by scripts/k3_probe.py to time both).
     const char *env_impl = getenv("MLBP_K3_IMPL");
@@ -655,7 +692,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
 #define MLBP_K3_RES(N)                                                                                             \
         case N:                                                                                                    \
             MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, \
-                                         (__half *)A_hi, (__half *)A_lo));                                         \
+                                         (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit));                  \
             break;
         switch (nin) {
             MLBP_K3_RES(1) MLBP_K3_RES(2) MLBP_K3_RES(3) MLBP_K3_RES(4) MLBP_K3_RES(5) MLBP_K3_RES(6) MLBP_K3_RES(7)
@@ -672,13 +709,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     do {                                                                                                         \
         if (fp32_ok && N <= 20)                                                                                  \
             var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit); \
         else if (fp32_ok)                                                                                        \
             var_to_factor_kernel<N, float, 1><<<n_groups, K3_THREADS, 0, st>>>(                                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit); \
         else                                                                                                     \
             var_to_factor_kernel<N, double, 1><<<n_groups, K3_THREADS, 0, st>>>(                                 \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit); \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);
@@ -703,16 +740,26 @@ extern "C" int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64
 
 extern "C" int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                               const int32_t *label, const float *U, const float *D, int ldv, int V, double *logp,
-                              int32_t *top1, int32_t *rank, float *beliefs, float range_log2, void *stream) {
+                              int32_t *top1, int32_t *rank, float *beliefs, float range_log2, int max_in, float tau,
+                              float tau_label, double *aux, int32_t *cnts, int32_t *flags, int32_t *flagged,
+                              int32_t *n_flagged, void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && label && U && D && logp && top1 && rank,
                    "marginals: null pointer");
+    if (max_in > 64) {                                            // the reference has no limit; this kernel's row table does
+        set_error("marginals: a variable with %d incoming pairwise messages exceeds the supported 64", max_in);
+        return MLBP_ERR_UNSUPPORTED;
+    }
+    MLBP_CHECK_ARG(!flags || (aux && cnts && flagged && n_flagged && tau >= 0.f && tau < 0.5f && tau_label >= 0.f && tau_label < 0.5f),
+                   "marginals: near-tie detection needs aux, cnts, flagged, n_flagged and bands in [0, 0.5)");
     if (range_log2 >= 0.f && range_log2 < 100.f)
         marginals_kernel<float><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V,
-                                                                         logp, top1, rank, beliefs);
+                                                                         logp, top1, rank, beliefs, tau, tau_label, aux,
+                                                                         cnts, flags, flagged, n_flagged);
     else
         marginals_kernel<double><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V,
-                                                                          logp, top1, rank, beliefs);
+                                                                          logp, top1, rank, beliefs, tau, tau_label, aux,
+                                                                          cnts, flags, flagged, n_flagged);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

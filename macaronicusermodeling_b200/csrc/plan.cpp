@@ -46,7 +46,7 @@ namespace {
 enum {
     H_NLEVELS = 0, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
     H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
-    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_WORDS = 32
+    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS, H_WORDS = 32
 };
 enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_FIRST, LEV_SECOND, LEV_WORDS = 10 };
 enum { GEMM_TABLE = 0, GEMM_A0, GEMM_D0, GEMM_N, GEMM_WORDS = 4 };
@@ -475,7 +475,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
             for (int L = 0; L <= n_levels; ++L)
                 total += co.grp_u[L].size() + co.grp_off[L].size() + co.in_row[L].size() + co.dest_off[L].size() +
                          co.dest[L].size() + co.first[L].size() + co.second[L].size() + 24;
-            total += co.init_rows.size() + 9 * co.pair_c.size() + co.mu.size() + co.moff.size() + co.min_.size() + 16;
+            total += (size_t)n_levels * 16 / n_chunks + 16 + co.init_rows.size() + 9 * co.pair_c.size() + co.mu.size() + co.moff.size() + co.min_.size() + 16;
         }
         B.reserve(total);
     }
@@ -495,6 +495,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     };
     B[H_NLEVELS] = n_levels; B[H_LEVELS_OFF] = H_WORDS; B[H_NGRAPHS] = n_graphs;
     B[H_A_ROWS] = (int32_t)a_rows; B[H_D_ROWS] = (int32_t)d_rows; B[H_MAX_IN] = max_in; B[H_NVARS] = var_off[n_graphs];
+    std::vector<int32_t> msg_blocks;                               // every message GEMM block, ascending in A / D rows
     for (int L = 1; L <= n_levels; ++L) {
         int32_t ng = 0;
         for (int c = 0; c < n_chunks; ++c) ng += (int32_t)CO[c].grp_u[L].size();
@@ -514,6 +515,7 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
                 gemm.push_back((int32_t)cnt[(size_t)L * 4 + t]);
             }
         const int32_t o_gemm = append(gemm);
+        msg_blocks.insert(msg_blocks.end(), gemm.begin(), gemm.end());
         const size_t rec = H_WORDS + (size_t)(L - 1) * LEV_WORDS;
         B[rec + LEV_NGROUPS] = ng; B[rec + LEV_GRP_U] = o_u; B[rec + LEV_GRP_OFF] = o_off; B[rec + LEV_IN_ROW] = o_in;
         B[rec + LEV_DEST_OFF] = o_doff; B[rec + LEV_DEST] = o_dest; B[rec + LEV_NGEMM] = (int32_t)(gemm.size() / GEMM_WORDS);
@@ -525,6 +527,11 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         B[H_INIT_N] = n_init;
         B[H_INIT_OFF] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.init_rows; }, false);
     }
+    // flat copy of the per-level GEMM records {table, A row, D row, rows}: the exact re-score (rescore.cu) finds the table of
+    // a message's D row by bisection over it
+    B[H_MSG_BLK_N] = (int32_t)(msg_blocks.size() / GEMM_WORDS);
+    B[H_MSG_BLK_OFF] = append(msg_blocks);
+    B[H_MSG_ROWS] = (int32_t)n_msg_rows;
     B[H_NPAIR] = (int32_t)n_pair;
     B[H_PAIR_C] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_c; }, false);
     B[H_PAIR_R] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.pair_r; }, false);

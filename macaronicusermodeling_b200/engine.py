@@ -23,7 +23,7 @@ from . import _lib
 # plan blob header (csrc/plan.cpp)
 (H_NLEVELS, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
  H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
- H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z) = range(25)
+ H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS) = range(28)
 H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
  PLAN_N_DEAD) = range(9)
@@ -34,6 +34,9 @@ GEMM_NARROW_LAST = 2048       # include/mlbp.h MLBP_GEMM_NARROW_LAST (probe swit
 N_PLANES = 14
 N_SUMS = 7
 D_CONST_ROWS = 5
+# Engine._flags (device int32 words): the peak flag of the var->factor kernel (sticky per theta), the flagged-variable count of
+# one marginals launch, and the re-score counters (mlbp_rescore_candidates)
+FLAG_PEAK, FLAG_NFLAGGED, FLAG_COUNTERS, FLAG_WORDS = 0, 1, 8, 16
 
 
 def round_up(x, m):
@@ -210,7 +213,7 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None):
+                 gemm_slice_pairs=None, msg_passes=None, tau=2e-3, tau_label=5e-4, peak_mult=8.0):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -223,6 +226,20 @@ class Engine(object):
         self.grad_a_terms = int(grad_a_terms)
         self.grad_b_terms = int(grad_b_terms)     # 1: the table's lo half is dropped too where grad_one_pass_ok (set_theta)
         self.gemm_slice_rows = self._gemm_slice_rows(gemm_slice_pairs)
+        # Message rows with TWO tensor-core passes (A_hi . (B_hi + B_lo): the lo half of the message is dropped) plus an exact
+        # re-score of every near-tied decision (csrc/rescore.cu).  Why this is safe: a rounding error upstream is damped by
+        # every later contraction (a message D = T a averages V terms), so the only error of the two-pass scheme that reaches
+        # a belief undamped is the rounding of the LAST hop -- measured 2.3e-6 relative rms on a belief at V = 10 000 (flat
+        # synthetic messages; it shrinks like 1 / sqrt(V_eff)) -- and that hop is recomputed from the full 22-bit operands
+        # for every candidate within `tau` of the arg-max (or within `tau_label` of the label while its rank can matter).
+        # Guards: (i) the potentials span at most e^3 (set_theta), (ii) no message puts more than peak_mult / V of its mass
+        # on one word -- checked on the DEVICE by the var->factor kernel, which raises a flag that switches all later message
+        # GEMMs of this theta to three passes (mlbp_factor_to_var_gemm_gated; no host synchronisation).
+        # msg_passes: None = two passes where V >= 4096 (where the error above was measured), 2 = at any V, 3 = never.
+        self.msg_passes = msg_passes
+        self.tau, self.tau_label, self.peak_mult = float(tau), float(tau_label), float(peak_mult)
+        self.msg_two_pass_ok = False
+        self._flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device=self.device)
         self.theta_ee = None
         self.theta_ed = None
         self.planes = None
@@ -242,6 +259,8 @@ class Engine(object):
         self.gemm_events = []
         self.profile_kernels = False  # same for the HBM-bound kernels: (name, event, event, algorithmic bytes)
         self.kernel_events = []
+        self.event_tag = 0          # copied into every gemm_events record (bench.py: which step a launch belongs to)
+        self.plan_seconds = 0.0     # host time spent in the schedule compiler (mlbp_plan_compile + export)
 
     def _gemm_slice_rows(self, pairs):
         """Rows per K4 launch of the three-pass message GEMMs (0 = never slice).  The CTA pairs of one launch start in step and
@@ -300,6 +319,9 @@ class Engine(object):
         # the table entries is random per entry and averages over the ~V^2 entries a belief spreads over (measured on a
         # sentence's gradient against the float64 oracle: <= 3.2e-6 relative over 24 sentences at V = 10 000, 3e-6 at V = 2 000)
         self.grad_one_pass_ok = self.grad_hi_only_ok and self.V >= 4096
+        self.msg_two_pass_ok = (zmax - zmin) <= 3.0 and (self.msg_passes == 2 or (self.msg_passes is None and self.V >= 4096)) \
+            and (self.gemm_impl & 0xff) != 1                      # the SIMT cross-check kernel has no device-side gate
+        self.k.call('mlbp_zero_words', _p(self._flags), FLAG_WORDS)   # the peak flag is sticky per theta
         self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
         n_planes = N_PLANES if with_grad else 8
         if self.planes is None or self.planes.shape[0] < n_planes:
@@ -315,6 +337,15 @@ class Engine(object):
         # constant rows by table id (T: row sums, Tt: column sums, T1, T1t), mean-one scaled (messages are scale-free)
         cs = self.colsums[[5, 0, 6, 1]]
         self.const_rows = (cs / cs.mean(dim=1, keepdim=True)).to(torch.float32)
+
+    def pass_stats(self):
+        """Host copy of the device-side decisions since the last set_theta (one small D2H read): whether a peaked message
+        switched the message GEMMs back to three passes, and what the exact re-score did."""
+        f = self._flags.cpu().numpy()
+        c = f[FLAG_COUNTERS:FLAG_COUNTERS + 5]
+        return {'msg_two_pass': bool(self.msg_two_pass_ok), 'peak_flag': int(f[FLAG_PEAK]), 'rescored': int(c[0]),
+                'skipped_mass_tie': int(c[1]), 'skipped_degenerate': int(c[2]), 'top1_changed': int(c[3]),
+                'rank_changed': int(c[4])}
 
     def plane(self, table, lo):
         return self.planes[2 * table + (1 if lo else 0)]
@@ -414,6 +445,8 @@ class Engine(object):
         grad_hi_only = self.grad_a_terms == 1 and self.grad_hi_only_ok and not approx
         # Z = c'Tr may reuse the D row of a message update only if that row was built from the same operand as the
         # numerator rows: not with masked (top-K) messages, and not when the gradient rows drop the lo half of r
+        import time as _time
+        t_plan = _time.perf_counter()
         handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference,
                                      reuse_z=not approx and not grad_hi_only)
         try:
@@ -425,6 +458,7 @@ class Engine(object):
             _lib.check(lib.mlbp_plan_export(handle, ctypes.c_void_p(self._blob_host.data_ptr())))
         finally:
             lib.mlbp_plan_destroy(handle)
+        self.plan_seconds += _time.perf_counter() - t_plan
         blob = self._blob_host.numpy()[:words]
         self._blob_dev[:words].copy_(self._blob_host[:words], non_blocking=True)
         self.blob_bytes += 4 * words
@@ -437,6 +471,8 @@ class Engine(object):
         a_cap = int(self._A.shape[1])
         td = self.theta_ed
         c = lambda name: _p(corpus.dev(name, dev))
+        two_pass = self.msg_two_pass_ok and not approx
+        peak_flag = _p(self._flags, FLAG_PEAK) if two_pass else None
 
         D[0].fill_(1.0)                                           # the constant-one row: messages still uniform read it
         D[1:D_CONST_ROWS, :V].copy_(self.const_rows)
@@ -467,7 +503,7 @@ class Engine(object):
         g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
         range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
 
-        def gemm_calls(off, n, mask, impl_flags=0):
+        def gemm_calls(off, n, mask, impl_flags=0, gated=False):
             masked = set()
             for i in range(n):
                 t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
@@ -483,11 +519,18 @@ class Engine(object):
                     if self.profile_gemm:
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                    k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
-                           _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags)
+                    if gated:
+                        # decided on the device: two passes while no message of this theta was peaked, else all three
+                        for fl, run_if_set in ((impl_flags, 0), (0, 1)):
+                            k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
+                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | fl, peak_flag, run_if_set)
+                        self.launches += 1
+                    else:
+                        k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
+                               _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags)
                     if self.profile_gemm:
                         e1.record()
-                        self.gemm_events.append((e0, e1, n, passes))
+                        self.gemm_events.append((e0, e1, n, passes, gated, self.event_tag))
                     self.launches += 1
                     self.gemm_launches += 1
                 self.gemm_rows += rows
@@ -505,9 +548,12 @@ class Engine(object):
                             lambda: k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])),
                                            _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(bd, int(rec[9])),
                                            _p(U), _p(D), ld,
-                                           V, _p(A_hi), _p(A_lo), max_in, range_log2))
+                                           V, _p(A_hi), _p(A_lo), max_in, range_log2, peak_flag, self.peak_mult / V))
                 self.launches += 1
-            gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
+            if two_pass:
+                gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
+            else:
+                gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
         n_pair = int(blob[H_NPAIR])
         pair_stats = torch.zeros((max(n_pair, 1), 3), dtype=torch.float64, device=dev)
@@ -550,11 +596,28 @@ class Engine(object):
                 mo, mi = int(blob[H_MARG_OFF]), int(blob[H_MARG_IN])
                 n_in = int(blob[mo + n_m])
                 return (n_m + int((blob[mi:mi + n_in] >= 0).sum()) + (n_m if want_beliefs else 0)) * V * 4.0
+            aux = cnts = vflags = flagged = None
+            if two_pass:                                          # near-tie detection + exact re-score (csrc/rescore.cu)
+                aux = torch.empty((n_m, 2), dtype=torch.float64, device=dev)
+                cnts = torch.empty((n_m, 2), dtype=torch.int32, device=dev)
+                vflags = torch.empty(n_m, dtype=torch.int32, device=dev)
+                flagged = torch.empty(n_m, dtype=torch.int32, device=dev)
+                k.call('mlbp_zero_words', _p(self._flags, FLAG_NFLAGGED), 1)
             self._timed('K5 marginals', k5_bytes,
                         lambda: k.call('mlbp_marginals', n_m, _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])),
                                        _p(bd, int(blob[H_MARG_IN])), c('var_label'), _p(U), _p(D), ld, V, _p(logp_var),
-                                       _p(top1), _p(rank), _p(beliefs), range_log2 + self.half_range_log2))
+                                       _p(top1), _p(rank), _p(beliefs), range_log2 + self.half_range_log2, max_in,
+                                       self.tau, self.tau_label, _p(aux), _p(cnts), _p(vflags), _p(flagged),
+                                       _p(self._flags, FLAG_NFLAGGED) if two_pass else None))
             self.launches += 1
+            if two_pass:
+                k.call('mlbp_rescore_candidates', n_m, _p(flagged), _p(self._flags, FLAG_NFLAGGED), _p(vflags),
+                       _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])), _p(bd, int(blob[H_MARG_IN])),
+                       c('var_label'), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), _p(self.planes), V * ld,
+                       _p(bd, int(blob[H_MSG_BLK_OFF])), int(blob[H_MSG_BLK_N]), int(blob[H_MSG_ROWS]), _p(aux), _p(cnts),
+                       self.tau, self.tau_label, range_log2 + self.half_range_log2, _p(top1), _p(rank),
+                       _p(self._flags, FLAG_COUNTERS))
+                self.launches += 2
         grad = torch.zeros((corpus.n_sent, 9), dtype=torch.float64, device=dev)
         logp = torch.zeros(corpus.n_sent, dtype=torch.float64, device=dev)
         # per-sentence segmented sums (deterministic, no atomics); without the gradient stage only log-posteriors matter
@@ -585,7 +648,8 @@ class Engine(object):
             for v in range(n_m):
                 messages['f2v'].append([dr[j] if rows[j] >= 0 else None for j in range(int(off[v]), int(off[v + 1]))])
         stats = {'a_rows': int(sizes[PLAN_A_ROWS]), 'd_rows': int(sizes[PLAN_D_ROWS]), 'levels': int(sizes[PLAN_N_LEVELS]),
-                 'gemm_rows': int(sizes[PLAN_N_GEMM_ROWS]), 'dead': int(sizes[PLAN_N_DEAD]), 'blob_words': words}
+                 'gemm_rows': int(sizes[PLAN_N_GEMM_ROWS]), 'dead': int(sizes[PLAN_N_DEAD]), 'blob_words': words,
+                 'msg_two_pass': bool(two_pass)}
         return Result(grad, logp, logp_var, top1, rank, beliefs, stats, messages)
 
     # ------------------------------------------------------------------ micro-batching

@@ -39,13 +39,21 @@ class Trainer(object):
 
     def step(self, parts_or_corpus, roots, lr, all_reduce=True):
         """One synchronous minibatch SGD step over this rank's sentences.  Returns the 16-vector
-        [g_ee(3), g_ed(6), sum logp, p@0, p@25, p@50, n_vars, n_sent, 0] summed over all ranks (device tensor)."""
+        [g_ee(3), g_ed(6), sum logp, p@0, p@25, p@50, n_vars, n_sent, peaked] summed over all ranks (device tensor);
+        `peaked` counts the ranks whose var->factor kernel saw a peaked message (their message GEMMs ran three passes)."""
+        return self._reduce(parts_or_corpus, roots, True, all_reduce)
+
+    def eval_step(self, parts_or_corpus, roots, all_reduce=True):
+        """batch_predictions (train.py:308-338) for this rank's sentences: inference only; same 16-vector, gradient slots 0"""
+        return self._reduce(parts_or_corpus, roots, False, all_reduce)
+
+    def _reduce(self, parts_or_corpus, roots, want_grad, all_reduce):
         eng = self.engine
-        eng.set_theta(self.theta_ee, self.theta_ed)
+        eng.set_theta(self.theta_ee, self.theta_ed, with_grad=want_grad)
         if isinstance(parts_or_corpus, Corpus):
-            grad, logp, top1, rank = eng.run_many(parts_or_corpus, roots, self.sweeps, True, True)
+            grad, logp, top1, rank = eng.run_many(parts_or_corpus, roots, self.sweeps, want_grad, True)
         else:
-            grad, logp, top1, rank = eng.run_prepared(parts_or_corpus, roots, self.sweeps, True, True)
+            grad, logp, top1, rank = eng.run_prepared(parts_or_corpus, roots, self.sweeps, want_grad, True)
         red = torch.zeros(16, dtype=torch.float64, device=grad.device)
         red[:9] = grad.sum(dim=0)
         red[9] = logp.sum()
@@ -54,6 +62,7 @@ class Trainer(object):
         red[12] = (rank < 50).sum()
         red[13] = rank.numel()
         red[14] = grad.shape[0]
+        red[15] = eng._flags[0]
         if all_reduce and dist_info()[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(red, op=dist.ReduceOp.SUM)
@@ -118,6 +127,7 @@ class AdaptTrainer(Trainer):
             total[9] += logp.sum()
             total[10] += (rank == 0).sum(); total[11] += (rank < 26).sum(); total[12] += (rank < 50).sum()
             total[13] += rank.numel(); total[14] += grad.shape[0]
+            total[15] += eng._flags[0]
             h = g.cpu().numpy()
             n = corpus.n_sent
             self.domain2theta[d] = (te + lr * (h[:3] - n * reg * self.ua_scale * te),

@@ -159,7 +159,11 @@ class FakeKernels(object):
         H[r, :V], L[r, :V] = np.where(km, hi[0], 0), np.where(km, lo[0], 0)
         H[r, V:], L[r, V:] = 0, 0
 
-    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2):
+    def mlbp_zero_words(self, p, n):
+        _arr(p, np.int32, n)[:] = 0
+
+    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2,
+                           peak_flag=None, peak_prob=1.0):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         n_in = int(go[-1])
         ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
@@ -190,6 +194,8 @@ class FakeKernels(object):
                 s = p.sum()
                 x = p * (A_SCALE / s) if (s > 0 and np.isfinite(s)) else np.full(V, A_SCALE / V)
                 hi, lo = _split(x)
+                if peak_flag is not None and peak_flag.value and x.max() > peak_prob * A_SCALE:
+                    _arr(peak_flag, np.int32, 1)[0] = 1
                 for tdest in de[do[i]:do[i + 1]]:
                     H[tdest, :V], L[tdest, :V] = hi, lo
 
@@ -215,7 +221,14 @@ class FakeKernels(object):
         Dm = _arr(D, np.float32, (d_row0 + n_rows) * ldd).reshape(-1, ldd)
         Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
 
-    def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs, range_log2):
+    def mlbp_factor_to_var_gemm_gated(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
+                                      impl, gate, run_if_set):
+        if gate is not None and gate.value and (int(_arr(gate, np.int32, 1)[0]) != 0) != (run_if_set != 0):
+            return
+        self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl)
+
+    def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs, range_log2,
+                       max_in=0, tau=0.0, tau_label=0.0, aux=None, cnts=None, flags=None, flagged=None, n_flagged=None):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         ir = _arr(in_row, np.int32, max(int(go[-1]), 1)); lab = _arr(label, np.int32, n_groups)
         Uo = _arr(U, np.float32, (int(gu.max()) + 1) * ldv).reshape(-1, ldv)
@@ -233,6 +246,77 @@ class FakeKernels(object):
             t1[g] = int(np.argmax(b)); rk[g] = int((b > b[lab[g]]).sum())
             if B is not None:
                 B[g, :V] = b
+            if flags is not None and flags.value:
+                srt = np.sort(p)
+                pl = p[lab[g]]
+                near_hi = int(((p > pl) & (p <= pl * (1 + tau_label))).sum())
+                near_lo = int(((p <= pl) & (p >= pl * (1 - tau_label))).sum()) - 1       # the label itself
+                f = (1 if (V > 1 and srt[-2] >= srt[-1] * (1 - tau)) else 0) | (2 if (near_hi + near_lo > 0 and rk[g] - near_hi <= 50) else 0)
+                _arr(flags, np.int32, n_groups)[g] = f
+                _arr(aux, np.float64, 2 * n_groups)[2 * g:2 * g + 2] = (srt[-1], pl)
+                _arr(cnts, np.int32, 2 * n_groups)[2 * g:2 * g + 2] = (rk[g], near_hi)
+                if f:
+                    nf = _arr(n_flagged, np.int32, 1)
+                    _arr(flagged, np.int32, n_groups)[nf[0]] = g
+                    nf[0] += 1
+
+    def mlbp_rescore_candidates(self, n_vars, flagged, n_flagged, flags, grp_u, grp_off, in_row, label, U, D, ldv, V, A_hi, A_lo,
+                                planes, ps, msg_blocks, n_blocks, n_msg_rows, aux, cnts, tau, tau_label, range_log2, top1, rank,
+                                counters):
+        nf = int(_arr(n_flagged, np.int32, 1)[0])
+        fl, fg = _arr(flagged, np.int32, n_vars), _arr(flags, np.int32, n_vars)
+        gu = _arr(grp_u, np.int32, n_vars); go = _arr(grp_off, np.int32, n_vars + 1)
+        ir = _arr(in_row, np.int32, max(int(go[-1]), 1)); lab = _arr(label, np.int32, n_vars)
+        Uo = _arr(U, np.float32, (int(gu.max()) + 1) * ldv).reshape(-1, ldv)
+        Dm = _arr(D, np.float32, (max(int(ir.max()), 0) + 1) * ldv).reshape(-1, ldv)
+        blk = _arr(msg_blocks, np.int32, 4 * max(n_blocks, 1)).reshape(-1, 4)[:n_blocks]
+        ax, cn = _arr(aux, np.float64, 2 * n_vars).reshape(-1, 2), _arr(cnts, np.int32, 2 * n_vars).reshape(-1, 2)
+        t1, rk, ct = _arr(top1, np.int32, n_vars), _arr(rank, np.int32, n_vars), _arr(counters, np.int32, 8)
+        H = _arr(A_hi, np.float16, (n_msg_rows + 1) * ldv).reshape(-1, ldv)
+        L = _arr(A_lo, np.float16, (n_msg_rows + 1) * ldv).reshape(-1, ldv)
+        pl = _arr(planes, np.float16, 8 * ps)
+        for g in fl[:nf]:
+            rows = ir[go[g]:go[g + 1]]
+            p = Uo[gu[g], :V].astype(np.float64)
+            for r in rows:
+                if r >= 0:
+                    p = p * Dm[r, :V].astype(np.float64)
+            best, plab = ax[g]
+            bits = np.zeros(V, dtype=np.int32)
+            if fg[g] & 1:
+                bits[p >= best * (1 - tau)] |= 1
+            if fg[g] & 2:
+                m = (p >= plab * (1 - tau_label)) & (p <= plab * (1 + tau_label)); m[lab[g]] = False
+                bits[m] |= 2
+            cand = [int(lab[g])] + [int(e) for e in np.nonzero(bits)[0] if e != lab[g]]
+            if len(cand) > 64:
+                ct[1] += 1
+                continue
+            score = Uo[gu[g], cand].astype(np.float64) / float(Uo[gu[g], cand[0]])
+            for r in rows:
+                if r < 0:
+                    continue
+                a_row = r - 5
+                t = -1
+                for b in blk:
+                    if b[1] <= a_row < b[1] + b[3] and r >= 5 and a_row < n_msg_rows:
+                        t = int(b[0])
+                if t < 0:
+                    d = Dm[r, cand].astype(np.float64)
+                else:
+                    a = H[a_row, :V].astype(np.float64) + L[a_row, :V].astype(np.float64)
+                    d = np.array([a @ (pl[2 * t * ps + e * ldv: 2 * t * ps + e * ldv + V].astype(np.float64) +
+                                       pl[(2 * t + 1) * ps + e * ldv:(2 * t + 1) * ps + e * ldv + V].astype(np.float64)) for e in cand])
+                score = score * d / d[0]
+            cb = np.array([bits[e] for e in cand]); cb[0] = bits[lab[g]]
+            if fg[g] & 1:
+                sel = [i for i in range(len(cand)) if cb[i] & 1]
+                bi = min(sel, key=lambda i: (-score[i], cand[i]))
+                ct[3] += int(t1[g] != cand[bi]); t1[g] = cand[bi]
+            if fg[g] & 2:
+                new = int(cn[g, 0] - cn[g, 1] + sum(1 for i in range(1, len(cand)) if (cb[i] & 2) and score[i] > score[0]))
+                ct[4] += int(rk[g] != new); rk[g] = new
+            ct[0] += 1
 
     def mlbp_pair_expectations(self, n_factors, c_row, z_row, u0_row, u1_row, u2_row, A_hi, A_lo, D, ldv, V, stats):
         cr, zr, r0, r1, r2 = (_arr(x, np.int32, n_factors) for x in (c_row, z_row, u0_row, u1_row, u2_row))

@@ -274,3 +274,89 @@ def test_long_sentence_streaming_k3_path():
     worst = common_checks.check_against_oracle(make_engine, model, sents, roots, [0.5, 0.3, -0.2],
                                                [0.8, -0.4, 0.5, 0.3, 0.4, -0.2])
     assert worst < 1e-6
+
+
+# ------------------------------------------------------------------ two-pass message rows + exact re-score
+def engineer_near_ties(model, sents, roots_pos, te, td, margin, sweeps=3, iters=3):
+    """see tests/test_engine_host.py: every variable gets a runner-up within `margin` (relative) of its arg-max"""
+    from oracle import lbp_oracle as orc
+    nv = sum(len(s.predicted) for s in sents)
+    rng = np.random.default_rng(0)
+    model = dict(model)
+    model['Vd'] = nv
+    model['ed'], model['ped'] = rng.random((model['V'], nv)), rng.random((model['V'], nv))
+    d = 0
+    for s in sents:
+        for p in s.predicted:
+            s.de[p] = d
+            d += 1
+        s.sparse = s.sparse[:0]
+    tb = orc.Tables(model, te, td)
+    for _ in range(iters):
+        for s, r in zip(sents, roots_pos):
+            m = orc.run_fast(tb, s, r, sweeps, want_grad=False)['marginals']
+            for i, p in enumerate(s.predicted):
+                b, a = np.argsort(m[i])[-2:]
+                step = np.log(m[i, a] / m[i, b] / (1.0 + margin)) / td[0]
+                model['ed'][b, s.de[p]] += step
+                tb.edT[s.de[p], b] += step
+    return model, tb
+
+
+def test_two_pass_message_rows_with_engineered_near_ties():
+    """V = 4608: every variable's runner-up sits 3e-6 (relative) below its arg-max -- inside the error of two-pass message rows,
+    outside the float64 oracle's.  Raw two-pass rows (re-score bands 0) flip some of them; the default engine (two passes +
+    exact re-score) reproduces the oracle's top-1 for all, and so does the three-pass engine."""
+    from oracle import lbp_oracle as orc
+    V = 4608
+    model = synth.make_model(V, 8, seed=61)
+    sents = synth.make_corpus(model, 8, k=6, g=1, seed=62)
+    roots_pos = synth.draw_roots(sents, 3, seed=63)
+    te, td = [0.8, 0.5, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]
+    model, tb = engineer_near_ties(model, sents, roots_pos, te, td, 3e-6)
+    ref = [orc.run_fast(tb, s, r, 3) for s, r in zip(sents, roots_pos)]
+    want = np.concatenate([o['top1'] for o in ref])
+    srt = np.sort(np.concatenate([o['marginals'] for o in ref]), axis=1)
+    margins = (srt[:, -1] - srt[:, -2]) / srt[:, -1]
+    assert 1e-6 < margins.min() and margins.max() < 1e-5, (margins.min(), margins.max())
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(roots_pos)
+    got = {}
+    for name, kw in (('three', dict(msg_passes=3)), ('two_raw', dict(tau=0.0, tau_label=0.0)), ('two', dict())):
+        eng = Engine(model, **kw)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_beliefs=True)
+        got[name] = (r.top1.cpu().numpy(), r.beliefs.cpu().numpy()[:, :V], r.grad.cpu().numpy(), eng.pass_stats(), r.stats)
+    assert got['two'][4]['msg_two_pass'] and got['two'][3]['peak_flag'] == 0 and not got['three'][4]['msg_two_pass']
+    flips = {k: int((v[0] != want).sum()) for k, v in got.items()}
+    print('top-1 mismatches vs the float64 oracle (48 engineered near-ties):', flips, got['two'][3])
+    assert flips['two'] == 0
+    assert flips['two_raw'] > 0, 'the ties must sit inside the two-pass error, else this test shows nothing'
+    assert got['two'][3]['rescored'] >= len(want)
+    assert np.abs(got['two'][1] - got['three'][1]).max() < 1e-7
+    np.testing.assert_allclose(got['two'][2], got['three'][2], rtol=1e-5, atol=2e-6)
+
+
+def test_two_pass_equals_three_pass_decisions_at_scale():
+    """a batch too big for the oracle: the default engine (two-pass message rows + re-score at V >= 4096) and the three-pass engine
+    agree on every arg-max and label rank, beliefs within 1e-7, log-posterior 2e-6, gradients 1e-4"""
+    model = synth.make_model(4352, 512, seed=33, dtype=np.float32)
+    sents = synth.make_corpus(model, 48, k=10, g=2, seed=14)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=2))
+    te, td = [0.9, 0.4, -0.1], [1.1, -0.5, 0.5, 0.3, 0.4, -0.2]
+    out = []
+    for mp in (3, None):
+        eng = Engine(model, msg_passes=mp)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_grad=True, want_marg=True, want_beliefs=True)
+        out.append((r.beliefs.cpu().numpy()[:, :4352], r.top1.cpu().numpy(), r.rank.cpu().numpy(), r.logp.cpu().numpy(), r.grad.cpu().numpy(),
+                    eng.pass_stats()))
+    assert out[1][5]['msg_two_pass'] and out[1][5]['peak_flag'] == 0 and out[1][5]['rescored'] > 0
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    rk0, rk1 = out[0][2], out[1][2]
+    assert ((rk0 == rk1) | ((rk0 >= 50) & (rk1 >= 50))).all()
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-7
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=2e-6)
+    np.testing.assert_allclose(out[0][4], out[1][4], rtol=1e-4, atol=2e-6)
+    print('two-pass vs three-pass at V=4352:', out[1][5])

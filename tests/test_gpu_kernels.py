@@ -51,7 +51,7 @@ def gemm(lib, A, B, M, V, impl, a_row0=0, alpha=1.0):
 
 
 @pytest.mark.parametrize('M,V', [(128, 256), (5, 200), (300, 1000), (131, 2112), (700, 2500), (257, 4100)])
-@pytest.mark.parametrize('impl', [1, 0, 30, 11], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
+@pytest.mark.parametrize('impl', [1, 0, 2, 3], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
 def test_message_gemm_matches_float64(lib, M, V, impl):
     rng = np.random.default_rng(M * 7 + V)
     A = rng.random((M + 9, V)) * 2.0 ** 14 / V * 2       # message-like magnitudes (2^14 * normalised)
@@ -65,7 +65,7 @@ def test_message_gemm_matches_float64(lib, M, V, impl):
 
 
 @pytest.mark.parametrize('M,V', [(131, 2112), (300, 1000), (257, 4100)])
-@pytest.mark.parametrize('impl', [1, 0, 30, 11], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
+@pytest.mark.parametrize('impl', [1, 0, 2, 3], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
 def test_gradient_gemm_a_hi_only(lib, M, V, impl):
     """MLBP_GEMM_A_HI_ONLY (gradient rows): exactly  A_hi . (B_hi + B_lo)'  -- the A_lo plane must not contribute"""
     rng = np.random.default_rng(M + V)
@@ -85,7 +85,7 @@ def test_gradient_gemm_a_hi_only(lib, M, V, impl):
     assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
 
 
-@pytest.mark.parametrize('impl', [1, 0, 30, 11], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
+@pytest.mark.parametrize('impl', [1, 0, 2, 3], ids=['simt', 'tcgen05', 'tcgen05-pair', 'tcgen05-single'])
 def test_gradient_gemm_one_pass(lib, impl):
     """MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY: exactly  A_hi . B_hi'  (plain fp16 operands, fp32 accumulation)"""
     M, V = 257, 4100
@@ -155,3 +155,100 @@ def test_dense_array_utils(lib):
     np.testing.assert_allclose(au.dense_dot(np.ascontiguousarray(z['a'].T), z['T']), z['dense_dot_vT'], rtol=1e-12)
     np.testing.assert_allclose(au.dense_dot(z['a'], np.ascontiguousarray(z['b'].T)), z['dense_dot_outer'], rtol=1e-15)
     np.testing.assert_allclose(au.dense_pointwise_multiply(z['T'], z['T'].T.copy()), z['dense_pointwise_multiply'], rtol=1e-15)
+
+
+def test_gated_gemm_runs_only_when_the_device_flag_matches(lib):
+    """mlbp_factor_to_var_gemm_gated: every CTA reads the gate word and returns unless (*gate != 0) == run_if_set"""
+    M, V = 300, 2500
+    rng = np.random.default_rng(8)
+    A = rng.random((M, V)) * 2.0 ** 14 / V * 2
+    B = np.exp(rng.normal(size=(V, V)) * 0.5) * 8.0
+    Ah, Al, Ax, ld = split_planes(A)
+    Bh, Bl, Bx, _ = split_planes(B)
+    ref3 = Ax @ Bx.T
+    ref2 = Ah.cpu().numpy()[:, :V].astype(np.float64) @ Bx.T
+    gate = torch.zeros(4, dtype=torch.int32, device='cuda')
+    for flag in (0, 1):
+        gate[0] = flag
+        D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
+        for impl, run_if_set in ((256, 0), (0, 1)):               # what Engine issues for one slice of message rows
+            _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, impl,
+                                                         P(gate), run_if_set, S()))
+        torch.cuda.synchronize()
+        got = D.cpu().numpy()[:, :V]
+        want, other = (ref3, ref2) if flag else (ref2, ref3)
+        assert np.abs(got - want).max() / np.abs(want).max() < 3e-6
+        assert np.abs(got - other).max() / np.abs(other).max() > 1e-6, 'the wrong variant ran'
+    # nothing runs when neither launch matches
+    D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
+    gate[0] = 1
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 256, P(gate), 0, S()))
+    torch.cuda.synchronize()
+    assert (D == -7.0).all()
+    assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
+
+
+def test_marginals_flags_and_exact_rescore(lib):
+    """K5 near-tie detection + K5b: a variable whose D rows were computed WITHOUT the lo half of A has its near-tied top-2
+    swapped on purpose; the re-score recomputes the last hop from the full operands and restores the float64 decision."""
+    V, ld, n_in = 2304, 2304, 3
+    rng = np.random.default_rng(21)
+    A = rng.random((n_in, V)) * 2.0 ** 14 / V * 2
+    T = np.exp(rng.random((V, V)) * 0.8)
+    Ah, Al, Ax, _ = split_planes(A)
+    Th, Tl, Tx, _ = split_planes(T * 64.0)
+    planes = torch.zeros((8, V, ld), dtype=torch.float16, device='cuda')
+    planes[2], planes[3] = Th, Tl                                  # table id 1 (MLBP_TABLE_TT)
+    exact = Ax @ Tx.T                                              # the three-pass rows, float64
+    two = Ah.cpu().numpy()[:, :V].astype(np.float64) @ Tx.T        # what a two-pass GEMM writes
+    U = rng.random(V) + 0.5
+    belief = U * exact.prod(axis=0)
+    a, b = np.argsort(belief)[-2:][::-1]                           # arg-max a, runner-up b
+    # nudge U so that a beats b by 2e-6 on exact rows while the two-pass rows say the opposite (if they do not already)
+    U[b] *= belief[a] / belief[b] / (1.0 + 2e-6)
+    Uf = U.astype(np.float32)
+    bel_exact = Uf.astype(np.float64) * exact.prod(axis=0)
+    want = int(np.argmax(bel_exact))
+    D = torch.zeros((5 + n_in, ld), dtype=torch.float32, device='cuda')
+    D[0] = 1.0
+    D[5:, :V] = torch.from_numpy(two.astype(np.float32)).cuda()
+    Ud = torch.zeros((1, ld), dtype=torch.float32, device='cuda'); Ud[0, :V] = torch.from_numpy(Uf).cuda()
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device='cuda')
+    grp_u, grp_off, in_row = i32([0]), i32([0, n_in]), i32([5, 6, 7])
+    label = i32([int(np.argsort(belief)[-30])])                    # a label inside the top-50: its rank is re-scored too
+    logp = torch.zeros(1, dtype=torch.float64, device='cuda')
+    top1, rank = i32([0]), i32([0])
+    aux = torch.zeros((1, 2), dtype=torch.float64, device='cuda')
+    cnts, flags, flagged = torch.zeros((1, 2), dtype=torch.int32, device='cuda'), i32([0]), i32([0])
+    words = torch.zeros(16, dtype=torch.int32, device='cuda')
+    tau, tau_label = 2e-3, 5e-4
+    _lib.check(lib.mlbp_marginals(1, P(grp_u), P(grp_off), P(in_row), P(label), P(Ud), P(D), ld, V, P(logp), P(top1), P(rank), None,
+                                  50.0, n_in, tau, tau_label, P(aux), P(cnts), P(flags), P(flagged), P(words[1:]), S()))
+    torch.cuda.synchronize()
+    bel_two = Uf.astype(np.float64) * two.astype(np.float32).astype(np.float64).prod(axis=0)
+    assert int(top1[0]) == int(np.argmax(bel_two))
+    assert int(flags[0]) & 1 and int(words[1]) == 1 and int(flagged[0]) == 0
+    blocks = i32([1, 0, 5, n_in])                                  # one message block: table 1, A row 0, D row 5, n_in rows
+    _lib.check(lib.mlbp_rescore_candidates(1, P(flagged), P(words[1:]), P(flags), P(grp_u), P(grp_off), P(in_row), P(label), P(Ud),
+                                           P(D), ld, V, P(Ah), P(Al), P(planes), V * ld, P(blocks), 1, n_in, P(aux), P(cnts), tau,
+                                           tau_label, 50.0, P(top1), P(rank), P(words[8:]), S()))
+    torch.cuda.synchronize()
+    assert int(top1[0]) == want, (int(top1[0]), want, a, b)
+    lab = int(label[0])
+    assert int(rank[0]) == int((bel_exact > bel_exact[lab]).sum())
+    assert int(words[8]) == 1 and int(words[9]) == 0 and int(words[10]) == 0
+
+
+def test_var_to_factor_raises_the_peak_flag(lib):
+    """K3 sets the device flag when a message it writes puts more than peak_prob of its mass on one word"""
+    from macaronicusermodeling_b200.engine import Corpus, Engine
+    model = synth.make_model(2304, 64, seed=3, dtype=np.float32)
+    sents = synth.make_corpus(model, 3, k=5, g=1, seed=4)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=5))
+    for td, expect in (([0.9, -0.5, 0.5, 0.3, 0.4, -0.2], 0), ([0.9, -0.5, 9.0, 9.0, 3.0, -0.2], 1)):
+        eng = Engine(model, msg_passes=2)
+        eng.set_theta([0.7, 0.4, -0.2], td)
+        eng.run(corpus, roots, 3)
+        st = eng.pass_stats()
+        assert st['msg_two_pass'] and st['peak_flag'] == expect, st
