@@ -150,9 +150,6 @@ int mlbp_topk_mask_rows(void *A_hi, void *A_lo, int ldv, int V, int64_t row0, in
 #define MLBP_GEMM_A_HI_ONLY 256
 /* additionally drops the B_lo term: one pass, plain fp16 x fp16 with fp32 accumulation (gradient rows at large V only) */
 #define MLBP_GEMM_B_HI_ONLY 512
-/* CTA-pair kernel, probe switch: the narrow last N tile (V not a multiple of 256) of every M pair is issued at the END of the
- * launch instead of inside the raster, so that all tiles of the raster take the same time (same results, different tile order) */
-#define MLBP_GEMM_NARROW_LAST 2048
 int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                             const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
                             float alpha, int impl, void *stream);
@@ -205,13 +202,28 @@ int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *z
 const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D,
                            int ldv, int V, double *stats, void *stream);
 /* K6b. FactorGraph.get_unregularized_gradeint (LBP.py:301-320) as a segmented reduction:
- *   grad[s][9] = sum_{v in sentence s} g_unary[v] + sum_{pairwise f in s} (phi[l0,l1,:] - E_f[phi])
- *   sentence s owns variables [sent_var_off[s], sent_var_off[s+1]) and factors [sent_fac_off[s], ..).
+ *   grad[s][9] = sum_{v in sentence s} g_unary[v] + sum_{pairwise f in s} (phi[l0,l1,:] - E_f[phi]),
+ *   (l0, l1) = var_label[pair_v0[f]], var_label[pair_v1[f]] (the observed one-hot of LBP.py:584-589);
+ *   sentence s owns variables [sent_var_off[s], sent_var_off[s+1]) and factors [sent_fac_off[s], ..);
+ *   sent_fac_off == NULL: no pairwise factors (inference-only callers that want logp_sent).
  *   logp_sent[s] = sum of logp_var over the sentence (LBP.py:247-259).                                     */
 int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t *sent_fac_off, const double *g_unary,
-                         const double *pair_stats, const int32_t *pair_l0, const int32_t *pair_l1,
-                         const int32_t *pair_gap1, const float *pmi, const float *pmi_w1, int ldf,
-                         const double *logp_var, double *grad, double *logp_sent, void *stream);
+                         const double *pair_stats, const int32_t *pair_v0, const int32_t *pair_v1,
+                         const int32_t *var_label, const int32_t *pair_gap1, const float *pmi, const float *pmi_w1,
+                         int ldf, const double *logp_var, double *grad, double *logp_sent, void *stream);
+/* K6c. Batch level of the reduction: what train_mp.py's parent callback sums under its lock (train_mp.py:405-424), and the
+ *   precision counts of FactorGraph.get_precision_counts (LBP.py:80-106).  ADDS this micro-batch to out16 (device, 16 float64,
+ *   zeroed by the caller at the start of an SGD step; it is the buffer the NCCL all-reduce ships):
+ *   [0..8] sum of grad[s][9], [9] sum of logp_sent, [10] #rank == 0, [11] #rank < 26, [12] #rank < 50, [13] n_vars, [14] n_sent;
+ *   [15] is SET to 1 when *peak_flag != 0 (see mlbp_var_to_factor).  grad / logp_sent / rank / peak_flag may be NULL.
+ *   One CTA, fixed summation order (deterministic).                                                              */
+int mlbp_batch_reduce(int n_sent, const double *grad, const double *logp_sent, int n_vars, const int32_t *rank,
+                      const int32_t *peak_flag, double *out16, void *stream);
+/* rows[0] = 1.0f (the constant-one row the kernels read for a message that is still uniform), rows[1 + t] = the message of a
+ *   pairwise factor of message table t (MLBP_TABLE_T .. T1T) that is fed the uniform initial message (LBP.py:211-216 +
+ *   :509 / :518): the row / column sums of the table, mean-one scaled.  rows: [MLBP_D_CONST_ROWS, ldv] fp32; the engine
+ *   copies them to D rows 0..4 of every micro-batch.                                                            */
+int mlbp_const_rows(const double *colsums, int V, int ldv, float *rows, void *stream);
 
 /* 0, or the code of the mbarrier wait (1 = stage empty, 2 = stage full, 3 = accumulator full, 4 = accumulator drained) that
  * exceeded its ~4 s bound inside a tcgen05 GEMM kernel: the kernel records it in mapped host memory and traps (the launch

@@ -26,7 +26,9 @@ _SIGNATURES = {
     'mlbp_rescore_candidates': 'ippp' + 'pppp' + 'ppii' + 'pppl' + 'pii' + 'ppff' + 'f' + 'ppp' + 'p',
     'mlbp_zero_words': 'pip',
     'mlbp_pair_expectations': 'ippppp' + 'pppii' + 'pp',
-    'mlbp_gradient_reduce': 'ippppppp' + 'ppi' + 'pppp',
+    'mlbp_gradient_reduce': 'ippppppp' + 'p' + 'ppi' + 'pppp',
+    'mlbp_batch_reduce': 'ippipppp',
+    'mlbp_const_rows': 'piipp',
     'mlbp_plan_compile': 'ipppppp' + 'iip',
     'mlbp_plan_sizes': 'pp',
     'mlbp_plan_export': 'pp',

@@ -399,7 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES, A_T,
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                            float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                           int m_pairs, int n_tiles, int narrow_last, const int32_t *__restrict__ gate, int run_if_set,
+                           int m_pairs, int n_tiles, const int32_t *__restrict__ gate, int run_if_set,
                            int *err_flag) {
     using C = PairCfg<STAGES, A_T, B_T>;
     // device-side launch decision (mlbp_factor_to_var_gemm_gated): every CTA of every pair reads the same word, written by an
@@ -424,23 +424,15 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
 
     // rasterisation: GROUP_M / 2 pairs deep (the same 16 M-tiles as the one-CTA kernel), then along n
     constexpr int GROUP_P = GROUP_M / 2;
-    // narrow_last (probe switch, MLBP_GEMM_NARROW_LAST): a narrow last N tile (V = 10 000: 16 columns) costs 1/16 of a full one,
-    // so inside the raster the pairs that draw it run ahead of the pairs they share A and B slabs with.  With the switch the
-    // raster covers the full-width tiles only and the narrow tiles of all M pairs come at the very end of the launch.
-    const int n_rast = (narrow_last && n_tiles > 1 && V % BN != 0) ? n_tiles - 1 : n_tiles;
-    const int full = m_pairs * n_rast;
-    int p_blk, n_blk;
-    if (pair >= full) {
-        p_blk = pair - full;
-        n_blk = n_rast;
-    } else {
-        const int per_group = GROUP_P * n_rast;
-        const int grp = pair / per_group, in_grp = pair % per_group;
-        const int first_p = grp * GROUP_P;
-        const int gsize = min(GROUP_P, m_pairs - first_p);
-        p_blk = first_p + in_grp % gsize;
-        n_blk = in_grp / gsize;
-    }
+    // (Measured and removed in round 2: issuing the narrow last N tiles of all M pairs at the END of the launch instead of
+    // inside the raster -- the idea was that equal-length tiles keep co-resident pairs in step -- was +0.8 % in the bench,
+    // inside the run-to-run noise: profiles/r2a_bench_c3_ab_narrow_last.txt.)
+    const int per_group = GROUP_P * n_tiles;
+    const int grp = pair / per_group, in_grp = pair % per_group;
+    const int first_p = grp * GROUP_P;
+    const int gsize = min(GROUP_P, m_pairs - first_p);
+    const int p_blk = first_p + in_grp % gsize;
+    const int n_blk = in_grp / gsize;
     const int m_blk = 2 * p_blk + (int)rank;                      // this CTA's 128-row tile
     const int num_kb = (V + BK - 1) / BK;
     const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
@@ -663,7 +655,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
 
 template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE = false>
 static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
-                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int narrow_last,
+                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
                          const int32_t *gate, int run_if_set, cudaStream_t st) {
     using C = PairCfg<STAGES, A_T, B_T>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -686,7 +678,7 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
     gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, narrow_last, gate, run_if_set, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, gate, run_if_set, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -700,9 +692,9 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false, int CHUNK_11 = CHUNK_KB>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                        const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                       int b_terms, int narrow_last, const int32_t *gate, int run_if_set, cudaStream_t st) {
+                       int b_terms, const int32_t *gate, int run_if_set, cudaStream_t st) {
 #define MLBP_PAIR(S, AT, BT, CH) \
-    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, narrow_last, gate, run_if_set, st)
+    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, gate, run_if_set, st)
     if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2, CHUNK_KB);
     if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2, CHUNK_KB);
     if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1, CHUNK_KB);
@@ -730,8 +722,7 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
                    (reinterpret_cast<uintptr_t>(D) % 16) == 0, "factor_to_var_gemm: misaligned buffer");
     cudaStream_t st = as_stream(stream);
     const int a_terms = (impl & MLBP_GEMM_A_HI_ONLY) ? 1 : 2, b_terms = (impl & MLBP_GEMM_B_HI_ONLY) ? 1 : 2;
-    const int narrow_last = (impl & MLBP_GEMM_NARROW_LAST) ? 1 : 0;
-    impl &= ~(MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY | MLBP_GEMM_NARROW_LAST);
+    impl &= ~(MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY);
     if (impl == 1) {
         MLBP_CHECK_ARG(gate == nullptr, "factor_to_var_gemm_gated: the SIMT cross-check kernel has no device-side gate");
         return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
@@ -740,9 +731,9 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 #define MLBP_TC(BN_, ST_, CH_) return launch_tc<BN_, ST_, CH_>(MLBP_ARGS, gate, run_if_set, st)
     switch (impl) {
         case 0:                                       // product configuration: CTA-pair kernel for large V
-            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
+            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, gate, run_if_set, st);
             MLBP_TC(128, 3, 2);
-        case 2: return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, narrow_last, gate, run_if_set, st);   // the CTA-pair kernel at any V (tests)
+        case 2: return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, gate, run_if_set, st);   // the CTA-pair kernel at any V (tests)
         case 3: MLBP_TC(128, 3, 2);                                                                        // the one-CTA kernel at any V (tests)
 #ifdef MLBP_PROBES                                    // variants for scripts/gemm_probe.py only (build with -DMLBP_PROBES)
         case 10: MLBP_TC(256, 2, 1);
@@ -753,12 +744,12 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
-        case 30: return launch_pair<2>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
-        case 31: return launch_pair<1>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
-        case 33: return launch_pair<2, 3, 4, 6, true>(MLBP_ARGS, narrow_last, gate, run_if_set, st);       // one-pass rows drained every 2 too
-        case 34: return launch_pair<4, 3, 4, 6, true>(MLBP_ARGS, narrow_last, gate, run_if_set, st);       // all rows drained every 4 k-blocks
-        case 35: return launch_pair<2, 3, 4, 6, true, 8>(MLBP_ARGS, narrow_last, gate, run_if_set, st);    // one-pass rows drained every 8
-        case 32: return launch_pair<2, 2, 3, 3>(MLBP_ARGS, narrow_last, gate, run_if_set, st);
+        case 30: return launch_pair<2>(MLBP_ARGS, gate, run_if_set, st);
+        case 31: return launch_pair<1>(MLBP_ARGS, gate, run_if_set, st);
+        case 33: return launch_pair<2, 3, 4, 6, true>(MLBP_ARGS, gate, run_if_set, st);       // one-pass rows drained every 2 too
+        case 34: return launch_pair<4, 3, 4, 6, true>(MLBP_ARGS, gate, run_if_set, st);       // all rows drained every 4 k-blocks
+        case 35: return launch_pair<2, 3, 4, 6, true, 8>(MLBP_ARGS, gate, run_if_set, st);    // one-pass rows drained every 8
+        case 32: return launch_pair<2, 2, 3, 3>(MLBP_ARGS, gate, run_if_set, st);
         case 20: return launch_tc<256, 4, 4, 32>(MLBP_ARGS, gate, run_if_set, st);
         case 21: return launch_tc<256, 4, 2, 32>(MLBP_ARGS, gate, run_if_set, st);
         case 22: return launch_tc<128, 6, 4, 32>(MLBP_ARGS, gate, run_if_set, st);

@@ -39,11 +39,13 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
     if (threadIdx.x == 0) { stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2; }
 }
 
-// one warp per sentence; deterministic (no atomics)
+// one warp per sentence; deterministic (no atomics).  The observed feature values phi[l0, l1, :] are gathered here from the
+// supervised labels of the factor's two variables (FactorNode.get_observed_factor, LBP.py:584-589).
 __global__ void gradient_reduce_kernel(int n_sent, const int32_t *__restrict__ sent_var_off,
                                        const int32_t *__restrict__ sent_fac_off, const double *__restrict__ g_unary,
-                                       const double *__restrict__ pair_stats, const int32_t *__restrict__ l0,
-                                       const int32_t *__restrict__ l1, const int32_t *__restrict__ gap1,
+                                       const double *__restrict__ pair_stats, const int32_t *__restrict__ pair_v0,
+                                       const int32_t *__restrict__ pair_v1, const int32_t *__restrict__ var_label,
+                                       const int32_t *__restrict__ gap1,
                                        const float *__restrict__ pmi, const float *__restrict__ w1, int ldf,
                                        const double *__restrict__ logp_var, double *__restrict__ grad,
                                        double *__restrict__ logp_sent) {
@@ -56,9 +58,10 @@ __global__ void gradient_reduce_kernel(int n_sent, const int32_t *__restrict__ s
         for (int i = 0; i < 9; ++i) g[i] += g_unary[(size_t)v * 9 + i];
         if (logp_var) lp += logp_var[v];
     }
-    for (int f = sent_fac_off[s] + lane; f < sent_fac_off[s + 1]; f += 32) {
+    const int f0 = sent_fac_off ? sent_fac_off[s] : 0, f1 = sent_fac_off ? sent_fac_off[s + 1] : 0;
+    for (int f = f0 + lane; f < f1; f += 32) {
         const double z = pair_stats[3 * (size_t)f];
-        const size_t cell = (size_t)l0[f] * ldf + l1[f];
+        const size_t cell = (size_t)var_label[pair_v0[f]] * ldf + var_label[pair_v1[f]];
         // Z <= 0: the reference's normalize zero-fills the belief (pyx:39-40) -> expected counts are 0
         const double e1 = z > 0.0 ? pair_stats[3 * (size_t)f + 1] / z : 0.0;
         g[0] += (double)pmi[cell] - e1;
@@ -76,6 +79,62 @@ __global__ void gradient_reduce_kernel(int n_sent, const int32_t *__restrict__ s
         for (int i = 0; i < 9; ++i) grad[(size_t)s * 9 + i] = g[i];
         if (logp_sent) logp_sent[s] = lp;
     }
+}
+
+// Batch level of the reduction (train_mp.py:405-424: the parent sums what the workers return): ONE CTA adds this micro-batch's
+// per-sentence gradients, log-posteriors and precision counts (LBP.py:80-106: P@0 = rank 0, P@25 = rank < 26, P@50 = rank < 50
+// as counted by Result.precision_counts) into the 16-double vector the NCCL all-reduce ships,
+//   [g_ee(3), g_ed(6), sum logp, p@0, p@25, p@50, n_vars, n_sent, peaked].  Fixed summation order: deterministic.
+__global__ void __launch_bounds__(1024)
+batch_reduce_kernel(int n_sent, const double *__restrict__ grad, const double *__restrict__ logp_sent, int n_vars,
+                    const int32_t *__restrict__ rank, const int32_t *__restrict__ peak_flag, double *__restrict__ out16) {
+    __shared__ double red[32];
+    double acc[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) acc[i] = 0.0;
+    for (int s = threadIdx.x; s < n_sent; s += blockDim.x) {
+        if (grad) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc[i] += grad[(size_t)s * 9 + i];
+        }
+        if (logp_sent) acc[9] += logp_sent[s];
+    }
+    if (rank)
+        for (int v = threadIdx.x; v < n_vars; v += blockDim.x) {
+            const int r = rank[v];
+            acc[10] += r == 0 ? 1.0 : 0.0; acc[11] += r < 26 ? 1.0 : 0.0; acc[12] += r < 50 ? 1.0 : 0.0;
+        }
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const double t = block_sum(acc[i], red);
+        if (threadIdx.x == 0) out16[i] += t;
+    }
+    if (threadIdx.x == 0) {
+        out16[13] += rank ? (double)n_vars : 0.0;
+        out16[14] += (double)n_sent;
+        if (peak_flag && *peak_flag) out16[15] = 1.0;
+    }
+}
+
+// D rows 0..4 of a theta: row 0 = the constant-one row (messages still uniform), rows 1..4 = the factor->variable message
+// of a pairwise factor that is fed the uniform initial message (LBP.py:211-216, :509, :518): row / column sums of T, T1,
+// mean-one scaled (messages are scale-free).  Table order MLBP_TABLE_T, TT, T1, T1T <- colsums rows 5, 0, 6, 1.
+__global__ void __launch_bounds__(256)
+const_rows_kernel(const double *__restrict__ colsums, int V, int ldv, float *__restrict__ out) {
+    __shared__ double red[32];
+    const int t = blockIdx.x;                                      // 0: ones, 1..4: tables
+    float *row = out + (size_t)t * ldv;
+    if (t == 0) {
+        for (int e = threadIdx.x; e < ldv; e += blockDim.x) row[e] = 1.0f;
+        return;
+    }
+    const int src[4] = {5, 0, 6, 1};
+    const double *cs = colsums + (size_t)src[t - 1] * V;
+    double s = 0.0;
+    for (int e = threadIdx.x; e < V; e += blockDim.x) s += cs[e];
+    s = block_sum(s, red);
+    const double inv_mean = s > 0.0 ? (double)V / s : 1.0;
+    for (int e = threadIdx.x; e < ldv; e += blockDim.x) row[e] = e < V ? (float)(cs[e] * inv_mean) : 0.f;
 }
 
 }  // namespace mlbp
@@ -97,17 +156,34 @@ extern "C" int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const
 }
 
 extern "C" int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t *sent_fac_off,
-                                    const double *g_unary, const double *pair_stats, const int32_t *pair_l0,
-                                    const int32_t *pair_l1, const int32_t *pair_gap1, const float *pmi,
-                                    const float *pmi_w1, int ldf, const double *logp_var, double *grad,
+                                    const double *g_unary, const double *pair_stats, const int32_t *pair_v0,
+                                    const int32_t *pair_v1, const int32_t *var_label, const int32_t *pair_gap1,
+                                    const float *pmi, const float *pmi_w1, int ldf, const double *logp_var, double *grad,
                                     double *logp_sent, void *stream) {
     if (n_sent == 0) return MLBP_OK;
-    MLBP_CHECK_ARG(n_sent > 0 && sent_var_off && sent_fac_off && g_unary && pmi && pmi_w1 && grad,
-                   "gradient_reduce: null pointer");
+    MLBP_CHECK_ARG(n_sent > 0 && sent_var_off && g_unary && pmi && pmi_w1 && grad, "gradient_reduce: null pointer");
+    MLBP_CHECK_ARG(!sent_fac_off || (pair_stats && pair_v0 && pair_v1 && var_label && pair_gap1),
+                   "gradient_reduce: pairwise factors need pair_stats, pair_v0, pair_v1, var_label, pair_gap1");
     const int threads = 128, warps_per_block = threads / 32;
     gradient_reduce_kernel<<<(n_sent + warps_per_block - 1) / warps_per_block, threads, 0, as_stream(stream)>>>(
-        n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, pair_l0, pair_l1, pair_gap1, pmi, pmi_w1, ldf,
+        n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, pair_v0, pair_v1, var_label, pair_gap1, pmi, pmi_w1, ldf,
         logp_var, grad, logp_sent);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_batch_reduce(int n_sent, const double *grad, const double *logp_sent, int n_vars, const int32_t *rank,
+                                 const int32_t *peak_flag, double *out16, void *stream) {
+    MLBP_CHECK_ARG(n_sent >= 0 && n_vars >= 0 && out16, "batch_reduce: bad argument");
+    if (n_sent == 0 && n_vars == 0) return MLBP_OK;
+    batch_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(n_sent, grad, logp_sent, n_vars, rank, peak_flag, out16);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
+
+extern "C" int mlbp_const_rows(const double *colsums, int V, int ldv, float *rows, void *stream) {
+    MLBP_CHECK_ARG(colsums && rows && V > 0 && ldv >= V, "const_rows: bad argument");
+    const_rows_kernel<<<MLBP_D_CONST_ROWS, 256, 0, as_stream(stream)>>>(colsums, V, ldv, rows);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

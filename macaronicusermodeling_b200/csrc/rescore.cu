@@ -33,6 +33,17 @@ __device__ __forceinline__ T belief_product(const float *urow, const float *cons
     return p;
 }
 
+// 8 fp16 hi + 8 fp16 lo -> 8 floats hi + lo (exact: 22 significant bits)
+__device__ __forceinline__ void unpack8(const uint4 h, const uint4 l, float (&x)[8]) {
+    const __half2 *hh = reinterpret_cast<const __half2 *>(&h), *ll = reinterpret_cast<const __half2 *>(&l);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(hh[i]), b = __half22float2(ll[i]);
+        x[2 * i] = a.x + b.x;
+        x[2 * i + 1] = a.y + b.y;
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
 rescore_kernel(const int32_t *__restrict__ flagged, const int32_t *__restrict__ n_flagged,
@@ -83,16 +94,32 @@ rescore_kernel(const int32_t *__restrict__ flagged, const int32_t *__restrict__ 
         const T best = (T)aux[2 * (size_t)g], plab = (T)aux[2 * (size_t)g + 1];
         const T best_lo = best * (T)(1.0f - tau);
         const T lab_lo = plab * (T)(1.0f - tau_label), lab_hi = plab * (T)(1.0f + tau_label);
-        for (int e = threadIdx.x; e < V; e += RS_THREADS) {
-            const T p = belief_product<T>(urow, s_rows, nn, e);
-            int bits = 0;
-            if ((flag & 1) && p >= best_lo) bits |= 1;
-            if ((flag & 2) && e != lab && p >= lab_lo && p <= lab_hi) bits |= 2;
-            if (bits) {
-                if (e == lab) { atomicOr(&s_bits[0], bits); }
-                else {
-                    const int k = atomicAdd(&s_nc, 1);
-                    if (k < RS_MAX_CAND) { s_cand[k] = e; s_bits[k] = bits; }
+        // four elements per thread and iteration, each with its own chain of loads: the products are bit-identical to
+        // marginals_kernel's (same factors, same order), the loads of the four chains overlap
+        for (int e0 = threadIdx.x; e0 < V; e0 += 4 * RS_THREADS) {
+            T p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = e0 + u * RS_THREADS < V ? (T)__ldg(urow + e0 + u * RS_THREADS) : (T)0;
+            for (int j = 0; j < nn; ++j) {
+                const float *r = s_rows[j];
+                if (!r) continue;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + u * RS_THREADS < V) p[u] *= (T)__ldg(r + e0 + u * RS_THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * RS_THREADS;
+                if (e >= V) continue;
+                int bits = 0;
+                if ((flag & 1) && p[u] >= best_lo) bits |= 1;
+                if ((flag & 2) && e != lab && p[u] >= lab_lo && p[u] <= lab_hi) bits |= 2;
+                if (bits) {
+                    if (e == lab) { atomicOr(&s_bits[0], bits); }
+                    else {
+                        const int k = atomicAdd(&s_nc, 1);
+                        if (k < RS_MAX_CAND) { s_cand[k] = e; s_bits[k] = bits; }
+                    }
                 }
             }
         }
@@ -115,15 +142,27 @@ rescore_kernel(const int32_t *__restrict__ flagged, const int32_t *__restrict__ 
             } else {
                 const size_t arow = (size_t)(r - MLBP_D_CONST_ROWS) * ldv;
                 const __half *bh = planes + (size_t)(2 * t) * plane_stride, *bl = planes + (size_t)(2 * t + 1) * plane_stride;
+                // rows are padded with zeros up to ldv (a multiple of 64): whole 16-byte chunks of 8 fp16, no tail
+                const int n8 = ldv >> 3;
+                const uint4 *ah8 = reinterpret_cast<const uint4 *>(A_hi + arow), *al8 = reinterpret_cast<const uint4 *>(A_lo + arow);
                 for (int c0 = 0; c0 < nc; c0 += 4) {
                     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int k = threadIdx.x; k < V; k += RS_THREADS) {
-                        const float a = __half2float(A_hi[arow + k]) + __half2float(A_lo[arow + k]);
+                    const uint4 *bh8[4], *bl8[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const size_t o = (size_t)s_cand[min(c0 + c, nc - 1)] * ldv;
+                        bh8[c] = reinterpret_cast<const uint4 *>(bh + o); bl8[c] = reinterpret_cast<const uint4 *>(bl + o);
+                    }
+                    for (int k8 = threadIdx.x; k8 < n8; k8 += RS_THREADS) {
+                        float a[8];
+                        unpack8(__ldg(ah8 + k8), __ldg(al8 + k8), a);
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            if (c0 + c < nc) {
-                                const size_t o = (size_t)s_cand[c0 + c] * ldv + k;
-                                acc[c] = fmaf(a, __half2float(bh[o]) + __half2float(bl[o]), acc[c]);
+                            if (c0 + c < nc) {                     // block-uniform
+                                float b[8];
+                                unpack8(__ldg(bh8[c] + k8), __ldg(bl8[c] + k8), b);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) acc[c] = fmaf(a[i], b[i], acc[c]);
                             }
                     }
 #pragma unroll
@@ -185,10 +224,13 @@ extern "C" int mlbp_rescore_candidates(int n_vars, const int32_t *flagged, const
                    A_lo && planes && aux && cnts && top1 && rank && counters && (msg_blocks || n_blocks == 0),
                    "rescore_candidates: null pointer");
     MLBP_CHECK_ARG(tau >= 0.f && tau < 0.5f && tau_label >= 0.f && tau_label < 0.5f, "rescore_candidates: bad band");
+    MLBP_CHECK_ARG((ldv % 64) == 0 && ldv >= V && (plane_stride % 8) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) | reinterpret_cast<uintptr_t>(planes)) % 16) == 0,
+                   "rescore_candidates: rows must be 16-byte aligned and padded to a multiple of 64");
     int dev = 0, sms = 0;
     MLBP_CUDA(cudaGetDevice(&dev));
     MLBP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = n_vars < 4 * sms ? n_vars : 4 * sms;
+    const int grid = n_vars < 8 * sms ? n_vars : 8 * sms;
     if (range_log2 >= 0.f && range_log2 < 100.f)
         rescore_kernel<float><<<grid, RS_THREADS, 0, as_stream(stream)>>>(
             flagged, n_flagged, flags, grp_u, grp_off, in_row, label, U, D, ldv, V, (const __half *)A_hi, (const __half *)A_lo,

@@ -30,7 +30,6 @@ H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 A_SCALE_LOG2 = 14
 GEMM_A_HI_ONLY = 256          # include/mlbp.h MLBP_GEMM_A_HI_ONLY
 GEMM_B_HI_ONLY = 512          # include/mlbp.h MLBP_GEMM_B_HI_ONLY
-GEMM_NARROW_LAST = 2048       # include/mlbp.h MLBP_GEMM_NARROW_LAST (probe switch)
 N_PLANES = 14
 N_SUMS = 7
 D_CONST_ROWS = 5
@@ -213,7 +212,7 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None, msg_passes=None, tau=2e-3, tau_label=5e-4, peak_mult=8.0):
+                 gemm_slice_pairs=None, msg_passes=None, tau=5e-4, tau_label=2.5e-4, peak_mult=64.0):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -275,8 +274,6 @@ class Engine(object):
             return 0
         resident = max(torch.cuda.get_device_properties(self.device).multi_processor_count // 2, 1)
         n_tiles = (self.V + 255) // 256
-        if (self.gemm_impl & GEMM_NARROW_LAST) and self.V % 256:   # probe switch: the narrow last tiles run after the raster
-            n_tiles -= 1
         waste = lambda p: -(-p * n_tiles // resident) * resident / float(p * n_tiles)
         lo, hi = max(-(-8 * resident // n_tiles), 1), max(24 * resident // n_tiles, 1)
         return 256 * min(range(lo, max(hi, lo) + 1), key=lambda p: (round(waste(p), 4), -p))
@@ -334,9 +331,12 @@ class Engine(object):
                                         1 if with_grad else 0))
         self.k.call('mlbp_build_unary_tables', _p(m.edT), _p(m.pedT), self.V, self.Vd, self.ld, _hp(td), _p(self.edstats))
         self.launches += 2
-        # constant rows by table id (T: row sums, Tt: column sums, T1, T1t), mean-one scaled (messages are scale-free)
-        cs = self.colsums[[5, 0, 6, 1]]
-        self.const_rows = (cs / cs.mean(dim=1, keepdim=True)).to(torch.float32)
+        # D rows 0..4: the constant-one row and the constant messages by table id (T: row sums, Tt: column sums, T1, T1t),
+        # mean-one scaled (messages are scale-free); copied into every micro-batch's D buffer (device-to-device memcpy)
+        if self.const_rows is None:
+            self.const_rows = torch.empty((D_CONST_ROWS, self.ld), dtype=torch.float32, device=self.device)
+        self.k.call('mlbp_const_rows', _p(self.colsums), self.V, self.ld, _p(self.const_rows))
+        self.launches += 1
 
     def pass_stats(self):
         """Host copy of the device-side decisions since the last set_theta (one small D2H read): whether a peaked message
@@ -427,9 +427,11 @@ class Engine(object):
         return handle, sizes
 
     def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False,
-            approx_inference=False, approx_beliefs=False, topk=100):
+            approx_inference=False, approx_beliefs=False, topk=100, reduce_into=None):
         """All sentences of `corpus` (must fit the workspace; use run_many to micro-batch).  `roots`: int
-        [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176)."""
+        [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176).
+        `reduce_into`: optional device tensor of 16 float64 that this call's sums are ADDED to (mlbp_batch_reduce: the
+        vector trainer.Trainer all-reduces)."""
         assert self.theta_ee is not None, 'set_theta first'
         assert not want_grad or self.with_grad_planes
         if corpus.n_sent == 0:                                    # empty batch: nothing to launch
@@ -444,21 +446,25 @@ class Engine(object):
         approx = approx_inference or approx_beliefs
         grad_hi_only = self.grad_a_terms == 1 and self.grad_hi_only_ok and not approx
         # Z = c'Tr may reuse the D row of a message update only if that row was built from the same operand as the
-        # numerator rows: not with masked (top-K) messages, and not when the gradient rows drop the lo half of r
+        # numerator rows: not with masked (top-K) messages, not when the gradient rows drop the lo half of r, and not when
+        # the message rows do (two-pass message rows)
         import time as _time
         t_plan = _time.perf_counter()
+        two_pass = self.msg_two_pass_ok and not approx
         handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference,
-                                     reuse_z=not approx and not grad_hi_only)
+                                     reuse_z=not approx and not grad_hi_only and not two_pass)
+        self.plan_seconds += _time.perf_counter() - t_plan
         try:
             words = int(sizes[PLAN_BLOB_WORDS])
             nv = corpus.n_vars
             if self._blob_event is not None:
                 self._blob_event.synchronize()
             self._ensure(int(sizes[PLAN_A_ROWS]), int(sizes[PLAN_D_ROWS]), nv, words)
+            t_plan = _time.perf_counter()
             _lib.check(lib.mlbp_plan_export(handle, ctypes.c_void_p(self._blob_host.data_ptr())))
+            self.plan_seconds += _time.perf_counter() - t_plan   # (the wait for the previous blob's upload is not counted)
         finally:
             lib.mlbp_plan_destroy(handle)
-        self.plan_seconds += _time.perf_counter() - t_plan
         blob = self._blob_host.numpy()[:words]
         self._blob_dev[:words].copy_(self._blob_host[:words], non_blocking=True)
         self.blob_bytes += 4 * words
@@ -471,11 +477,9 @@ class Engine(object):
         a_cap = int(self._A.shape[1])
         td = self.theta_ed
         c = lambda name: _p(corpus.dev(name, dev))
-        two_pass = self.msg_two_pass_ok and not approx
         peak_flag = _p(self._flags, FLAG_PEAK) if two_pass else None
 
-        D[0].fill_(1.0)                                           # the constant-one row: messages still uniform read it
-        D[1:D_CONST_ROWS, :V].copy_(self.const_rows)
+        D[:D_CONST_ROWS].copy_(self.const_rows)                   # row 0: the constant-one row messages still uniform read
         inv_sigma = torch.empty(max(nv, 1), dtype=torch.float64, device=dev)
         g_unary = torch.empty((max(nv, 1), 9), dtype=torch.float64, device=dev)
         k.call('mlbp_unary_stats', nv, c('var_de'), c('var_label'), c('sp_off'), c('sp_en'), c('sp_feat'), c('sp_val'),
@@ -556,8 +560,7 @@ class Engine(object):
                 gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
         n_pair = int(blob[H_NPAIR])
-        pair_stats = torch.zeros((max(n_pair, 1), 3), dtype=torch.float64, device=dev)
-        pair_l0 = pair_l1 = None
+        pair_stats = torch.empty((max(n_pair, 1), 3), dtype=torch.float64, device=dev)   # every entry is written by K6a
         v2f_rows = None
         if want_messages and n_pair:                              # before any gradient-stage masking
             oc, orr = int(blob[H_PAIR_C]), int(blob[H_PAIR_R])
@@ -581,10 +584,6 @@ class Engine(object):
                                        _p(bd, int(blob[H_PAIR_U1])), _p(bd, int(blob[H_PAIR_U2])), _p(A_hi), _p(A_lo),
                                        _p(D), ld, V, _p(pair_stats)))
             self.launches += 1
-            lab = corpus.dev('var_label', dev)
-            o0, o1 = int(blob[H_PAIR_V0]), int(blob[H_PAIR_V1])
-            pair_l0 = lab[bd[o0:o0 + n_pair].long()].contiguous()
-            pair_l1 = lab[bd[o1:o1 + n_pair].long()].contiguous()
         logp_var = top1 = rank = beliefs = None
         if want_marg:
             n_m = int(blob[H_MARG_N])
@@ -618,16 +617,20 @@ class Engine(object):
                        self.tau, self.tau_label, range_log2 + self.half_range_log2, _p(top1), _p(rank),
                        _p(self._flags, FLAG_COUNTERS))
                 self.launches += 2
-        grad = torch.zeros((corpus.n_sent, 9), dtype=torch.float64, device=dev)
-        logp = torch.zeros(corpus.n_sent, dtype=torch.float64, device=dev)
+        grad = torch.empty((corpus.n_sent, 9), dtype=torch.float64, device=dev)
+        logp = torch.empty(corpus.n_sent, dtype=torch.float64, device=dev)
         # per-sentence segmented sums (deterministic, no atomics); without the gradient stage only log-posteriors matter
-        zero_off = torch.zeros(corpus.n_sent + 1, dtype=torch.int32, device=dev)
         use_pairs = want_grad and n_pair > 0
-        k.call('mlbp_gradient_reduce', corpus.n_sent, c('var_off'), c('pair_off') if use_pairs else _p(zero_off),
-               _p(g_unary), _p(pair_stats), _p(pair_l0) if use_pairs else _p(zero_off),
-               _p(pair_l1) if use_pairs else _p(zero_off), _p(bd, int(blob[H_PAIR_GAP1])) if use_pairs else _p(zero_off),
+        k.call('mlbp_gradient_reduce', corpus.n_sent, c('var_off'), c('pair_off') if use_pairs else None,
+               _p(g_unary), _p(pair_stats), _p(bd, int(blob[H_PAIR_V0])) if use_pairs else None,
+               _p(bd, int(blob[H_PAIR_V1])) if use_pairs else None, c('var_label'),
+               _p(bd, int(blob[H_PAIR_GAP1])) if use_pairs else None,
                _p(m.pmi), _p(m.w1), ld, _p(logp_var), _p(grad), _p(logp))
         self.launches += 1
+        if reduce_into is not None:                                # batch level: this micro-batch into the all-reduce buffer
+            k.call('mlbp_batch_reduce', corpus.n_sent, _p(grad), _p(logp), int(blob[H_MARG_N]) if want_marg else 0, _p(rank),
+                   _p(self._flags, FLAG_PEAK), _p(reduce_into))
+            self.launches += 1
         messages = None
         if want_messages:
             # final pairwise messages, normalised, float64 on the host (API read-back for LBP.FactorGraph.messages):
@@ -677,27 +680,36 @@ class Engine(object):
             parts.append((lo, hi, c))
         return parts
 
-    def run_prepared(self, parts, roots, sweeps=3, want_grad=True, want_marg=True):
+    def run_prepared(self, parts, roots, sweeps=3, want_grad=True, want_marg=True, reduce_into=None, collect=True, **kw):
+        """`collect` = False (with reduce_into): only the batch-level sums are wanted, nothing is concatenated"""
         roots = np.ascontiguousarray(roots, dtype=np.int32)
         grads, logps, top1s, ranks = [], [], [], []
         for lo, hi, c in parts:
-            r = self.run(c, roots[lo:hi], sweeps, want_grad, want_marg)
+            r = self.run(c, roots[lo:hi], sweeps, want_grad, want_marg, reduce_into=reduce_into, **kw)
+            if not collect:
+                continue
             grads.append(r.grad); logps.append(r.logp)
             if want_marg:
                 top1s.append(r.top1); ranks.append(r.rank)
+        if not collect:
+            return None, None, None, None
         cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs)
         return cat(grads), cat(logps), (cat(top1s) if top1s else None), (cat(ranks) if ranks else None)
 
-    def run_many(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True):
+    def run_many(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, reduce_into=None, collect=True, **kw):
         """Micro-batched run over a large corpus; returns (grad [B, 9], logp [B], top1 [NV], rank [NV]) on device.
         Launches are asynchronous: the host compiles the next micro-batch's schedule while the GPU works."""
         roots = np.ascontiguousarray(roots, dtype=np.int32)
         grads, logps, top1s, ranks = [], [], [], []
         for lo, hi in self.microbatches(corpus, sweeps, want_grad):
             r = self.run(corpus.slice(lo, hi) if (lo, hi) != (0, corpus.n_sent) else corpus, roots[lo:hi], sweeps,
-                         want_grad, want_marg)
+                         want_grad, want_marg, reduce_into=reduce_into, **kw)
+            if not collect:
+                continue
             grads.append(r.grad); logps.append(r.logp)
             if want_marg:
                 top1s.append(r.top1); ranks.append(r.rank)
+        if not collect:
+            return None, None, None, None
         cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs)
         return cat(grads), cat(logps), (cat(top1s) if top1s else None), (cat(ranks) if ranks else None)

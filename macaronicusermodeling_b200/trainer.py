@@ -10,6 +10,8 @@ identical update
     theta += lr * (sum_s g_s - n * (reg_param / N) * theta)
 which for a minibatch of one sentence on one GPU is exactly train.py's step (tests/test_gpu_trainer.py).
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -37,36 +39,28 @@ class Trainer(object):
     def lr(self, epoch):
         return self.init_lr / float(1.0 + epoch * 0.3)           # train.py:621
 
-    def step(self, parts_or_corpus, roots, lr, all_reduce=True):
+    def step(self, parts_or_corpus, roots, lr, all_reduce=True, **kw):
         """One synchronous minibatch SGD step over this rank's sentences.  Returns the 16-vector
         [g_ee(3), g_ed(6), sum logp, p@0, p@25, p@50, n_vars, n_sent, peaked] summed over all ranks (device tensor);
         `peaked` counts the ranks whose var->factor kernel saw a peaked message (their message GEMMs ran three passes)."""
-        return self._reduce(parts_or_corpus, roots, True, all_reduce)
+        return self._reduce(parts_or_corpus, roots, True, all_reduce, **kw)
 
-    def eval_step(self, parts_or_corpus, roots, all_reduce=True):
+    def eval_step(self, parts_or_corpus, roots, all_reduce=True, **kw):
         """batch_predictions (train.py:308-338) for this rank's sentences: inference only; same 16-vector, gradient slots 0"""
-        return self._reduce(parts_or_corpus, roots, False, all_reduce)
+        return self._reduce(parts_or_corpus, roots, False, all_reduce, **kw)
 
-    def _reduce(self, parts_or_corpus, roots, want_grad, all_reduce):
+    def _reduce(self, parts_or_corpus, roots, want_grad, all_reduce, **kw):
         eng = self.engine
         eng.set_theta(self.theta_ee, self.theta_ed, with_grad=want_grad)
-        if isinstance(parts_or_corpus, Corpus):
-            grad, logp, top1, rank = eng.run_many(parts_or_corpus, roots, self.sweeps, want_grad, True)
-        else:
-            grad, logp, top1, rank = eng.run_prepared(parts_or_corpus, roots, self.sweeps, want_grad, True)
-        red = torch.zeros(16, dtype=torch.float64, device=grad.device)
-        red[:9] = grad.sum(dim=0)
-        red[9] = logp.sum()
-        red[10] = (rank == 0).sum()
-        red[11] = (rank < 26).sum()
-        red[12] = (rank < 50).sum()
-        red[13] = rank.numel()
-        red[14] = grad.shape[0]
-        red[15] = eng._flags[0]
+        if self._red is None:
+            self._red = torch.zeros(16, dtype=torch.float64, device=eng.device)
+        red = self._red                                        # the all-reduce buffer: every micro-batch is added on the device
+        eng.k.call('mlbp_zero_words', ctypes.c_void_p(red.data_ptr()), 32)
+        fn = eng.run_many if isinstance(parts_or_corpus, Corpus) else eng.run_prepared
+        fn(parts_or_corpus, roots, self.sweeps, want_grad, True, reduce_into=red, collect=False, **kw)
         if all_reduce and dist_info()[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(red, op=dist.ReduceOp.SUM)
-        self._red = red
         return red
 
     def apply(self, red, lr):
@@ -113,25 +107,24 @@ class AdaptTrainer(Trainer):
         self.ua_scale = float(ua_scale)
         self.domain2theta = {d: (np.zeros(3), np.zeros(6)) for d in domains}
 
-    def step_domains(self, batches, lr):
-        """batches: list of (domain, Corpus, roots).  Returns the reduced 16-vector like Trainer.step."""
+    def step_domains(self, batches, lr, **kw):
+        """batches: list of (domain, Corpus, roots).  Returns the reduced 16-vector like Trainer.step.  `kw`: Engine.run options
+        (approx_inference, approx_beliefs, topk: the reference trains with them too, train.py:155-156)."""
         eng = self.engine
         total = torch.zeros(16, dtype=torch.float64, device=eng.device)
+        dom = torch.zeros(16, dtype=torch.float64, device=eng.device)
         reg = self.reg_param / float(self.N if self.N else sum(c.n_sent for _, c, _ in batches))
         for d, corpus, roots in batches:
             te, td = self.domain2theta[d]
             eng.set_theta(te, td)
-            grad, logp, top1, rank = eng.run_many(corpus, roots, self.sweeps, True, True)
-            g = grad.sum(dim=0)
-            total[:9] += g
-            total[9] += logp.sum()
-            total[10] += (rank == 0).sum(); total[11] += (rank < 26).sum(); total[12] += (rank < 50).sum()
-            total[13] += rank.numel(); total[14] += grad.shape[0]
-            total[15] += eng._flags[0]
-            h = g.cpu().numpy()
+            eng.k.call('mlbp_zero_words', ctypes.c_void_p(dom.data_ptr()), 32)
+            eng.run_many(corpus, roots, self.sweeps, True, True, reduce_into=dom, collect=False, **kw)
+            total += dom
+            h = dom.cpu().numpy()                               # the domain's theta is updated on the host, once per domain
             n = corpus.n_sent
             self.domain2theta[d] = (te + lr * (h[:3] - n * reg * self.ua_scale * te),
-                                    td + lr * (h[3:] - n * reg * self.ua_scale * td))
+                                    td + lr * (h[3:9] - n * reg * self.ua_scale * td))
+        total[15] = (total[15] > 0).to(total.dtype)
         if dist_info()[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(total, op=dist.ReduceOp.SUM)

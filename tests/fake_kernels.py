@@ -331,13 +331,39 @@ class FakeKernels(object):
             st[f, 1] = c @ Dm[r1[f], :V].astype(np.float64)
             st[f, 2] = c @ Dm[r2[f], :V].astype(np.float64) if r2[f] >= 0 else 0.0
 
-    def mlbp_gradient_reduce(self, n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, l0, l1, gap1, pmi, w1, ldf,
+    def mlbp_const_rows(self, colsums, V, ldv, rows):
+        cs = _arr(colsums, np.float64, 7 * V).reshape(7, V)
+        R = _arr(rows, np.float32, 5 * ldv).reshape(5, ldv)
+        R[0] = 1.0
+        for t, k in enumerate((5, 0, 6, 1)):
+            R[1 + t, :V] = (cs[k] / cs[k].mean()).astype(np.float32)
+            R[1 + t, V:] = 0
+
+    def mlbp_batch_reduce(self, n_sent, grad, logp_sent, n_vars, rank, peak_flag, out16):
+        o = _arr(out16, np.float64, 16)
+        if grad is not None and grad.value and n_sent:
+            o[:9] += _arr(grad, np.float64, n_sent * 9).reshape(-1, 9).sum(0)
+        if logp_sent is not None and logp_sent.value and n_sent:
+            o[9] += _arr(logp_sent, np.float64, n_sent).sum()
+        if rank is not None and rank.value and n_vars:
+            r = _arr(rank, np.int32, n_vars)
+            o[10] += (r == 0).sum(); o[11] += (r < 26).sum(); o[12] += (r < 50).sum(); o[13] += n_vars
+        o[14] += n_sent
+        if peak_flag is not None and peak_flag.value and _arr(peak_flag, np.int32, 1)[0]:
+            o[15] = 1.0
+
+    def mlbp_gradient_reduce(self, n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, v0, v1, var_label, gap1, pmi, w1, ldf,
                              logp_var, grad, logp_sent):
-        vo, fo = _arr(sent_var_off, np.int32, n_sent + 1), _arr(sent_fac_off, np.int32, n_sent + 1)
+        vo = _arr(sent_var_off, np.int32, n_sent + 1)
+        has_f = sent_fac_off is not None and sent_fac_off.value
+        fo = _arr(sent_fac_off, np.int32, n_sent + 1) if has_f else np.zeros(n_sent + 1, dtype=np.int32)
         nv, nf = int(vo[-1]), int(fo[-1])
         gu = _arr(g_unary, np.float64, nv * 9).reshape(-1, 9)
         st = _arr(pair_stats, np.float64, max(nf, 1) * 3).reshape(-1, 3)
-        a0, a1, g1 = (_arr(x, np.int32, max(nf, 1)) for x in (l0, l1, gap1))
+        if has_f:
+            lab = _arr(var_label, np.int32, nv)
+            a0, a1 = lab[_arr(v0, np.int32, max(nf, 1))], lab[_arr(v1, np.int32, max(nf, 1))]
+            g1 = _arr(gap1, np.int32, max(nf, 1))
         V = ldf   # only cells are read
         lv = _arr(logp_var, np.float64, nv) if logp_var is not None and logp_var.value else None
         G = _arr(grad, np.float64, n_sent * 9).reshape(-1, 9); LS = _arr(logp_sent, np.float64, n_sent)
