@@ -383,6 +383,7 @@ class Workload(object):
         self.tr.theta_ee, self.tr.theta_ed = theta0()
         self.parts = self.eng.prepare(self.corpus, a.sweeps, self.train) if self.corpus is not None else None
         self.peaked = []                                                    # red[15] of every step
+        self.all_peaked = []
 
     def roots(self, corpus):
         return local_roots(corpus, self.a.sweeps, self.rng)
@@ -393,6 +394,7 @@ class Workload(object):
         else:
             h = red.cpu().numpy()                                           # the step's device -> host read
         self.peaked.append(float(h[15]))
+        self.all_peaked.append(float(h[15]))
         return h
 
     def step(self):
@@ -582,6 +584,7 @@ def ours(a):
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'hbm_kernels': hbm,
             'host': {'plan_compile_s_per_step': plan_s_per_step, 'plan_threads': int(os.environ.get('MLBP_PLAN_THREADS', '0'))},
             'message_rows': {'two_pass_enabled': pass_stats['msg_two_pass'], 'ranks_switched_to_three_passes_per_step': peaked_value,
+                             'ranks_switched_all_steps_incl_warmup_e2e_profiling': w.all_peaked, 'max_message_prob_last_step': pass_stats['max_message_prob'],
                              'rescore': {k: pass_stats[k] for k in ('rescored', 'skipped_mass_tie', 'skipped_degenerate', 'top1_changed', 'rank_changed')},
                              'rescore_note': 'counters of the LAST step of the profiling pass (reset per theta)'},
             'cpu_baseline': cpu_baseline}

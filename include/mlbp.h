@@ -124,8 +124,9 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   constant-one row D[0] in its place (messages are scale-free), so the caller keeps D row 0 filled with 1.0f.
  *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
  *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow).
- *   peak_flag (optional, may be NULL): device int32 that is SET to 1 (never cleared) when any element of any message
- *   written by this call exceeds the probability peak_prob.  mlbp_factor_to_var_gemm_gated reads it: a message whose
+ *   peak_flag (optional, may be NULL): 3 device int32 words; word 0 is SET to 1 (never cleared) when any element of any message
+ *   written by this call exceeds the probability peak_prob, word 2 keeps the largest element seen so far as the bits of
+ *   the float 2^14 * probability (atomic max; diagnostics).  mlbp_factor_to_var_gemm_gated reads it: a message whose
  *   mass sits on few words does not average its fp16 rounding away, so rows written after the flag went up keep
  *   all three tensor-core passes.                                                                              */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,

@@ -33,6 +33,12 @@ void set_error(const char *fmt, ...);
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+constexpr int MLBP_MAX_DEVICES = 64;   // per-device caches of function attributes / occupancy (one process may drive several GPUs)
+static inline int current_device() {
+    int d = 0;
+    return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < MLBP_MAX_DEVICES) ? d : 0;
+}
+
 // x (already scaled into fp16 range) -> hi + lo, both fp16; hi + lo == x to ~2^-22 relative.
 __device__ __forceinline__ void split_f16(float x, __half &hi, __half &lo) {
     hi = __float2half_rn(x);

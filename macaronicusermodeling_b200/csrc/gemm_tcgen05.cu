@@ -634,7 +634,8 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     if ((rc = cached_map(&ma_lo, A_lo, a_rows_total, V, ldv, BM, BK)) != MLBP_OK) return rc;
     if ((rc = cached_map(&mb_hi, B_hi, V, V, ldv, BN, BK)) != MLBP_OK) return rc;
     if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, BN, BK)) != MLBP_OK) return rc;
-    static bool attr_set = false;
+    static bool attr_set_dev[MLBP_MAX_DEVICES] = {};
+    bool &attr_set = attr_set_dev[current_device()];
     if (!attr_set) {
         MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, STAGES, CHUNK_KB, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));
@@ -664,7 +665,8 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     if ((rc = cached_map(&ma_lo, A_lo, a_rows_total, V, ldv, BM, C::BK)) != MLBP_OK) return rc;
     if ((rc = cached_map(&mb_hi, B_hi, V, V, ldv, C::BN / 2, C::BK)) != MLBP_OK) return rc;
     if ((rc = cached_map(&mb_lo, B_lo, V, V, ldv, C::BN / 2, C::BK)) != MLBP_OK) return rc;
-    static bool attr_set = false;
+    static bool attr_set_dev[MLBP_MAX_DEVICES] = {};
+    bool &attr_set = attr_set_dev[current_device()];
     if (!attr_set) {
         MLBP_CUDA(cudaFuncSetAttribute(gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        C::SMEM_BYTES));

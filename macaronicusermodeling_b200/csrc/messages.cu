@@ -66,6 +66,16 @@ __device__ __forceinline__ void k3_store(float x, size_t first, int nd, const in
     }
 }
 
+// End of a K3 kernel: raise the peak flag (see mlbp_var_to_factor) and keep the largest element seen in peak_flag[2]
+// (2^14 * probability as float bits; non-negative floats order like their bit patterns) -- one atomic per warp.
+__device__ __forceinline__ void k3_report_peak(int32_t *peak_flag, float peak_limit, float mx) {
+    if (!peak_flag) return;
+    if (!(mx <= peak_limit)) *peak_flag = 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(peak_flag + 2, __float_as_int(mx));
+}
+
 template <int NMAX, typename T, int OCC>
 __global__ void __launch_bounds__(K3_THREADS, OCC)
 var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
@@ -154,7 +164,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
             suf *= (T)d[j];
         }
     }
-    if (peak_flag && !(mx <= peak_limit)) *peak_flag = 1;         // a peaked message: see mlbp_var_to_factor
+    k3_report_peak(peak_flag, peak_limit, mx);
 }
 
 // Messages with more than TWO readers (the first two are written directly): the slice just written to the first reader's
@@ -458,7 +468,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         __syncthreads();                                           // shared memory is reused by the next group
         K3_TICK(5);
     }
-    if (peak_flag && !(mx <= peak_limit)) *peak_flag = 1;          // a peaked message: see mlbp_var_to_factor
+    k3_report_peak(peak_flag, peak_limit, mx);
 #ifdef MLBP_K3_STAGE_TIMES
     if (dbg && threadIdx.x == 0)
         for (int i = 0; i < 6; ++i) dbg[(size_t)blockIdx.x * 6 + i] = tacc[i];
@@ -623,16 +633,20 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
                                    const int32_t *dest, const int32_t *first_dest, const int32_t *second_dest, const float *U,
                                    const float *D, int ldv, int V, __half *A_hi, __half *A_lo, int32_t *peak_flag,
                                    float peak_limit) {
-    static bool configured = false;
+    // function attributes and occupancy are per DEVICE: a process that drives several GPUs configures each one
+    static bool configured[MLBP_MAX_DEVICES] = {};
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    if (dev < 0 || dev >= MLBP_MAX_DEVICES) return cudaErrorInvalidDevice;
     auto kern = var_to_factor_resident_kernel<NIN>;
-    if (!configured) {
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_RESIDENT_SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     const size_t smem = (size_t)(NIN + 1) * S * sizeof(float);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)C * 148u * 2u);
+    cfg.gridDim = dim3((unsigned)C);                              // placeholder: set from the occupancy query below
     cfg.blockDim = dim3(K3R_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -642,10 +656,11 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // persistent grid: as many clusters as the device keeps resident for this shared-memory size (queried once per C)
-    static int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    static int resident_tab[MLBP_MAX_DEVICES][9] = {};
+    int *resident = resident_tab[dev];
     if (!resident[C]) {
         int nc = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);   // counts this device's SMs: nothing hard-coded
         if (e != cudaSuccess) return e;
         resident[C] = nc > 0 ? nc : 1;
         if (getenv("MLBP_DEBUG")) fprintf(stderr, "mlbp K3 resident<%d>: cluster %d, %zu B smem, %d resident clusters\n", NIN, C, smem, nc);

@@ -2,6 +2,14 @@
 // (V,V,3) and (V,Vd,6) tensors for EVERY sentence (train.py:218-253); here it is one pass per SGD step that
 // emits the tensor-core operand planes (fp16 hi/lo, both orientations) plus the small per-column /
 // per-German-word statistics that make every unary factor O(1) in the gradient.
+//
+// Arithmetic: the planes keep 22 bits (fp16 hi + lo), so the exponentials are evaluated in fp32 -- but on an argument that is
+// formed in double-float (a compensated fp32 pair): z = th_pmi * p + th_bias is split as z_hi + z_lo with |z_lo| ~ 2^-24 |z|,
+// exp(z) = expf(z_hi) * (1 + z_lo).  Result: ~1 ulp of fp32 per table entry, no float64 instruction per element (the fp64
+// pipe of this part issues only a few lanes per clock and SM: the float64 exp of round 1 ran at 0.27 of the HBM roofline).
+// Column sums are accumulated as compensated fp32 pairs over the 8 rows a thread owns and in float64 above that, row sums in
+// fp32 across the 64 columns of a tile and in float64 above; the rounding of the entries is random, so sums over V entries
+// are good to ~1e-9 (columns) / ~1e-8 (rows) relative -- their consumers, the unary gradient and the constant messages, need 1e-6.
 #include "common.cuh"
 
 namespace mlbp {
@@ -11,70 +19,138 @@ constexpr int TS = 64;  // tile edge
 struct ThetaEE { double pmi, w1, bias; };
 struct ThetaED { double t[6]; };
 
-// One 64x64 tile of the (a, b) plane per CTA, 256 threads: thread (tx = tid % 64, ty = tid / 64) walks rows
-// ty, ty+4, ... so global reads and the direct-orientation writes are coalesced along b; the transposed planes
-// go through shared memory and are written coalesced along a.
+struct F2 { float hi, lo; };                                      // unevaluated sum hi + lo
+
+__device__ __forceinline__ F2 split_double(double x) {
+    F2 r;
+    r.hi = (float)x;
+    r.lo = (float)(x - (double)r.hi);
+    return r;
+}
+// c * p + b with c = (c.hi + c.lo), b = (b.hi + b.lo), p an fp32 datum: result as hi + lo (error ~2^-46 relative)
+__device__ __forceinline__ F2 axpb(F2 c, float p, F2 b) {
+    const float ph = c.hi * p;
+    const float pe = fmaf(c.hi, p, -ph);                          // exact product error
+    const float s = ph + b.hi;
+    const float bb = s - ph;
+    const float se = (ph - (s - bb)) + (b.hi - bb);               // exact sum error (two-sum)
+    F2 r;
+    r.hi = s;
+    r.lo = se + pe + fmaf(c.lo, p, b.lo);
+    return r;
+}
+static F2 split_double_host(double x) {
+    F2 r;
+    r.hi = (float)x;
+    r.lo = (float)(x - (double)r.hi);
+    return r;
+}
+// s += x for an unevaluated sum s = (hi, lo): two-sum, the rounding error of every addition is kept in lo
+__device__ __forceinline__ void acc_f2(F2 &s, float x) {
+    const float t = s.hi + x;
+    const float bb = t - s.hi;
+    s.lo += (s.hi - (t - bb)) + (x - bb);
+    s.hi = t;
+}
+// exp(z.hi + z.lo), ~1 ulp: expf is IEEE-grade here (the library is built without fast-math)
+__device__ __forceinline__ float exp_f2(F2 z) { return expf(z.hi) * (1.0f + z.lo); }
+
+// One 64x64 tile of the (a, b) plane per CTA, 256 threads: thread (tx = tid % 32, ty = tid / 32) owns the column pair
+// b0 + 2 tx, + 1 of rows ty, ty + 8, ...: 8-byte global loads and 4-byte (half2) plane stores, 128 bytes per warp and plane.
+// The transposed planes go through shared memory and are written as half2 pairs along a.
 __global__ void __launch_bounds__(256)
-build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restrict__ w1, int V, int ldf, ThetaEE th,
-                             int scale_exp, __half *__restrict__ planes, int64_t ps, int ldv,
+build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restrict__ w1, int V, int ldf, F2 t_pmi, F2 t_w1,
+                             F2 t_bias, float scale, __half *__restrict__ planes, int64_t ps, int ldv,
                              double *__restrict__ colsums, int with_grad) {
-    __shared__ __half sT[4][TS][TS + 2];  // T.hi T.lo T1.hi T1.lo, indexed [a][b]
-    __shared__ double sSum[5][4][TS];
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    // T.hi T.lo T1.hi T1.lo tiles, indexed [a][b]; the column-sum partials reuse the storage once the tiles are written out
+    __shared__ __align__(16) unsigned char s_raw[4 * TS * (TS + 2) * sizeof(__half)];
+    __half (*sT)[TS][TS + 2] = reinterpret_cast<__half (*)[TS][TS + 2]>(s_raw);
+    double (*sSum)[8][TS] = reinterpret_cast<double (*)[8][TS]>(s_raw);
+    static_assert(sizeof(double) * 5 * 8 * TS <= sizeof(s_raw), "column-sum partials must fit the tile storage");
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int a0 = blockIdx.y * TS, b0 = blockIdx.x * TS;
-    const int b = b0 + tx;
-    double cs[5] = {0, 0, 0, 0, 0};
-    for (int r = ty; r < TS; r += 4) {
+    const int b = b0 + 2 * tx;
+    F2 cs[5][2];                                                  // column sums over this thread's 8 rows, compensated
+#pragma unroll
+    for (int i = 0; i < 5; ++i) cs[i][0] = cs[i][1] = F2{0.f, 0.f};
+    const F2 zero = {0.f, 0.f};
+    for (int r = ty; r < TS; r += 8) {
         const int a = a0 + r;
-        double rs_t = 0.0, rs_t1 = 0.0;
-        __half h[10];
+        float rs_t = 0.f, rs_t1 = 0.f;
+        __half2 h[10];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) h[i] = __float2half_rn(0.f);
-        if (a < V && b < V) {
-            const double p = (double)pmi[(size_t)a * ldf + b];
-            const double w = (double)w1[(size_t)a * ldf + b];
-            const double z = th.pmi * p + th.bias;
-            const double t = exp(z), t1 = exp(z + th.w1 * w);
-            const double g = t * p, g1 = t1 * p, g1w = t1 * w;
-            cs[0] += t; cs[1] += t1; cs[2] += g; cs[3] += g1; cs[4] += g1w;
-            rs_t = t; rs_t1 = t1;
-            const double v[5] = {t, t1, g, g1, g1w};
+        for (int i = 0; i < 10; ++i) h[i] = __floats2half2_rn(0.f, 0.f);
+        if (a < V && b < V) {                                     // ldf is even and >= V: the pair load stays inside the row
+            const float2 p2 = *reinterpret_cast<const float2 *>(pmi + (size_t)a * ldf + b);
+            const float2 w2 = *reinterpret_cast<const float2 *>(w1 + (size_t)a * ldf + b);
+            const float pp[2] = {p2.x, p2.y}, ww[2] = {w2.x, w2.y};
+            float v[5][2];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) split_f16((float)ldexp(v[i], scale_exp), h[2 * i], h[2 * i + 1]);
-            const size_t o = (size_t)a * ldv + b;
-            planes[0 * ps + o] = h[0];  planes[1 * ps + o] = h[1];      // T
-            planes[4 * ps + o] = h[2];  planes[5 * ps + o] = h[3];      // T1
+            for (int q = 0; q < 2; ++q) {
+                const bool in = b + q < V;
+                const F2 z = axpb(t_pmi, pp[q], t_bias);
+                const F2 zw = axpb(t_w1, ww[q], zero);
+                const float t = in ? exp_f2(z) : 0.f;
+                const float t1 = in ? t * exp_f2(zw) : 0.f;      // exp(z + th_w1 w) = exp(z) exp(th_w1 w)
+                v[0][q] = t; v[1][q] = t1; v[2][q] = t * pp[q]; v[3][q] = t1 * pp[q]; v[4][q] = t1 * ww[q];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) acc_f2(cs[i][q], v[i][q]);
+            }
+            rs_t = v[0][0] + v[0][1]; rs_t1 = v[1][0] + v[1][1];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float2 x = make_float2(v[i][0] * scale, v[i][1] * scale);
+                const __half2 hi = __float22half2_rn(x);
+                const float2 back = __half22float2(hi);
+                h[2 * i] = hi;
+                h[2 * i + 1] = __floats2half2_rn(x.x - back.x, x.y - back.y);
+            }
+            const size_t o = (size_t)a * ldv + b;                 // even: 4-byte aligned
+            auto st = [&](int plane, __half2 x) { *reinterpret_cast<__half2 *>(planes + plane * ps + o) = x; };
+            st(0, h[0]); st(1, h[1]);                             // T
+            st(4, h[2]); st(5, h[3]);                             // T1
             if (with_grad) {
-                planes[8 * ps + o] = h[4];   planes[9 * ps + o] = h[5];   // G   = T  o PMI
-                planes[10 * ps + o] = h[6];  planes[11 * ps + o] = h[7];  // G1  = T1 o PMI
-                planes[12 * ps + o] = h[8];  planes[13 * ps + o] = h[9];  // G1w = T1 o PMI_w1
+                st(8, h[4]); st(9, h[5]);                         // G   = T  o PMI
+                st(10, h[6]); st(11, h[7]);                       // G1  = T1 o PMI
+                st(12, h[8]); st(13, h[9]);                       // G1w = T1 o PMI_w1
             }
         }
-        sT[0][r][tx] = h[0]; sT[1][r][tx] = h[1]; sT[2][r][tx] = h[2]; sT[3][r][tx] = h[3];
-        // row sums of T and T1 (message of a pairwise factor whose input is still the uniform initial message)
-        rs_t = warp_sum(rs_t); rs_t1 = warp_sum(rs_t1);
-        if ((threadIdx.x & 31) == 0 && a < V) {
-            atomicAdd(&colsums[(size_t)5 * V + a], rs_t);
-            atomicAdd(&colsums[(size_t)6 * V + a], rs_t1);
-        }
-    }
 #pragma unroll
-    for (int i = 0; i < 5; ++i) sSum[i][ty][tx] = cs[i];
-    __syncthreads();
-    // transposed planes: Tt[b][a] = T[a][b]; threads now run along a
-    for (int r = ty; r < TS; r += 4) {
-        const int bb = b0 + r, aa = a0 + tx;
-        if (bb < V && aa < V) {
-            const size_t o = (size_t)bb * ldv + aa;
-            planes[2 * ps + o] = sT[0][tx][r];  planes[3 * ps + o] = sT[1][tx][r];
-            planes[6 * ps + o] = sT[2][tx][r];  planes[7 * ps + o] = sT[3][tx][r];
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<__half2 *>(&sT[i][r][2 * tx]) = h[i];
+        // row sums of T and T1 (message of a pairwise factor whose input is still the uniform initial message)
+        rs_t = warp_sum_f32(rs_t); rs_t1 = warp_sum_f32(rs_t1);
+        if (tx == 0 && a < V) {
+            atomicAdd(&colsums[(size_t)5 * V + a], (double)rs_t);
+            atomicAdd(&colsums[(size_t)6 * V + a], (double)rs_t1);
         }
     }
-    if (ty == 0 && b < V) {
+    __syncthreads();
+    // transposed planes: Tt[b][a] = T[a][b]; threads now run along a in pairs
+    for (int r = ty; r < TS; r += 8) {
+        const int bb = b0 + r, aa = a0 + 2 * tx;
+        if (bb < V && aa < V) {                                   // aa + 1 < ldv: the padding column receives the zero of sT
+            const size_t o = (size_t)bb * ldv + aa;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __half2 x = __halves2half2(sT[i][2 * tx][r], sT[i][2 * tx + 1][r]);
+                *reinterpret_cast<__half2 *>(planes + (i < 2 ? 2 + i : 4 + i) * ps + o) = x;    // planes 2, 3 (Tt) and 6, 7 (T1t)
+            }
+        }
+    }
+    __syncthreads();                                              // the tiles are dead: their storage takes the partial sums
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        sSum[i][ty][2 * tx] = (double)cs[i][0].hi + (double)cs[i][0].lo;
+        sSum[i][ty][2 * tx + 1] = (double)cs[i][1].hi + (double)cs[i][1].lo;
+    }
+    __syncthreads();
+    if (threadIdx.x < TS && b0 + threadIdx.x < V) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const double s = sSum[i][0][tx] + sSum[i][1][tx] + sSum[i][2][tx] + sSum[i][3][tx];
-            atomicAdd(&colsums[(size_t)i * V + b], s);
+            double s = 0.0;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) s += sSum[i][y][threadIdx.x];
+            atomicAdd(&colsums[(size_t)i * V + b0 + threadIdx.x], s);
         }
     }
 }
@@ -107,14 +183,18 @@ extern "C" int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1,
                                           int64_t plane_stride, int ldv, double *colsums, int with_grad_planes,
                                           void *stream) {
     MLBP_CHECK_ARG(pmi && pmi_w1 && planes && colsums && h_theta_ee, "build_pairwise_tables: null pointer");
-    MLBP_CHECK_ARG(V > 0 && ldf >= V && ldv >= V && (ldv % 64) == 0, "build_pairwise_tables: bad V/ld (%d,%d,%d)", V, ldf, ldv);
-    MLBP_CHECK_ARG(plane_stride >= (int64_t)V * ldv, "build_pairwise_tables: plane_stride too small");
+    MLBP_CHECK_ARG(V > 0 && ldf >= V && (ldf % 2) == 0 && ldv >= V && (ldv % 64) == 0, "build_pairwise_tables: bad V/ld (%d,%d,%d)", V, ldf, ldv);
+    MLBP_CHECK_ARG(plane_stride >= (int64_t)V * ldv && (plane_stride % 2) == 0, "build_pairwise_tables: plane_stride too small or odd");
+    MLBP_CHECK_ARG(((reinterpret_cast<uintptr_t>(pmi) | reinterpret_cast<uintptr_t>(pmi_w1)) % 8) == 0 &&
+                   (reinterpret_cast<uintptr_t>(planes) % 4) == 0, "build_pairwise_tables: misaligned buffer");
+    MLBP_CHECK_ARG(scale_exp > -120 && scale_exp < 120, "build_pairwise_tables: scale_exp out of range");
     cudaStream_t st = as_stream(stream);
     MLBP_CUDA(cudaMemsetAsync(colsums, 0, sizeof(double) * MLBP_N_SUMS * (size_t)V, st));
-    ThetaEE th{h_theta_ee[0], h_theta_ee[1], h_theta_ee[2]};
     dim3 grid((V + TS - 1) / TS, (V + TS - 1) / TS);
-    build_pairwise_tables_kernel<<<grid, 256, 0, st>>>(pmi, pmi_w1, V, ldf, th, scale_exp, (__half *)planes,
-                                                       plane_stride, ldv, colsums, with_grad_planes);
+    build_pairwise_tables_kernel<<<grid, 256, 0, st>>>(pmi, pmi_w1, V, ldf, split_double_host(h_theta_ee[0]),
+                                                       split_double_host(h_theta_ee[1]), split_double_host(h_theta_ee[2]),
+                                                       ldexpf(1.0f, scale_exp), (__half *)planes, plane_stride, ldv, colsums,
+                                                       with_grad_planes);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

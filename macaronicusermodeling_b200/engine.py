@@ -35,7 +35,7 @@ N_SUMS = 7
 D_CONST_ROWS = 5
 # Engine._flags (device int32 words): the peak flag of the var->factor kernel (sticky per theta), the flagged-variable count of
 # one marginals launch, and the re-score counters (mlbp_rescore_candidates)
-FLAG_PEAK, FLAG_NFLAGGED, FLAG_COUNTERS, FLAG_WORDS = 0, 1, 8, 16
+FLAG_PEAK, FLAG_NFLAGGED, FLAG_MAXBITS, FLAG_COUNTERS, FLAG_WORDS = 0, 1, 2, 8, 16
 
 
 def round_up(x, m):
@@ -102,6 +102,8 @@ class Corpus(object):
     (train.py:176-215) are kept only where their German index equals the variable's observed word: the only
     column of phi_en_de the variable's factor ever reads (LBP.py:602, :702-703)."""
 
+    MAX_PREDICTED = 49          # 48 pairwise factors per variable (mlbp_var_to_factor), 64 in mlbp_marginals
+
     FIELDS = ('var_off', 'var_de', 'var_label', 'var_pos', 'sp_off', 'sp_en', 'sp_feat', 'sp_val', 'giv_off',
               'giv_label', 'giv_gap1', 'pair_off', 'pair_v0', 'pair_v1', 'pair_gap1')
 
@@ -124,6 +126,10 @@ class Corpus(object):
             given = [p for p in range(len(kind)) if kind[p] == 0]
             if not pred:
                 raise ValueError('sentence without predicted tokens has no factor graph (LBP.py:193)')
+            if len(pred) > self.MAX_PREDICTED:
+                # the reference has no limit; the leave-one-out kernel (K3) handles at most 48 pairwise messages per variable.
+                # Raised HERE, when the batch is lowered, not from a kernel launch in the middle of an epoch.
+                raise ValueError('sentence with %d predicted tokens: at most %d are supported' % (len(pred), self.MAX_PREDICTED))
             for p in pred:
                 var_de.append(int(de[p])); var_label.append(int(label[p])); var_pos.append(p)
                 for e, d, f, val in s.sparse:
@@ -343,7 +349,8 @@ class Engine(object):
         switched the message GEMMs back to three passes, and what the exact re-score did."""
         f = self._flags.cpu().numpy()
         c = f[FLAG_COUNTERS:FLAG_COUNTERS + 5]
-        return {'msg_two_pass': bool(self.msg_two_pass_ok), 'peak_flag': int(f[FLAG_PEAK]), 'rescored': int(c[0]),
+        return {'msg_two_pass': bool(self.msg_two_pass_ok), 'peak_flag': int(f[FLAG_PEAK]),
+                'max_message_prob': float(f[FLAG_MAXBITS:FLAG_MAXBITS + 1].view(np.float32)[0]) * 2.0 ** -A_SCALE_LOG2, 'rescored': int(c[0]),
                 'skipped_mass_tie': int(c[1]), 'skipped_degenerate': int(c[2]), 'top1_changed': int(c[3]),
                 'rank_changed': int(c[4])}
 

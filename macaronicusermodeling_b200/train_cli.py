@@ -55,6 +55,19 @@ def parse(argv=None):
     return opt.parse_args(argv)
 
 
+def gather_domain_thetas(tr, owner, rank, world):
+    """Domain thetas never leave the rank that owns the domain during training; before a checkpoint is written rank 0
+    collects every owner's current values (no-op on one rank)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    mine = dict((d, t) for d, t in tr.domain2theta.items() if owner.get(d, 0) == rank)
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    for part in parts:
+        tr.domain2theta.update(part)
+
+
 def error_msg():
     sys.stderr.write('Usage: python -m macaronicusermodeling_b200.train_cli\n  --ti [training instance file]\n  --tune [dev set]\n'
                      '  --end [en domain file]\n  --ded [de domain file]\n  --phi_pmi [pmi file]\n  --phi_pmi_w1 [pmi w1 file]\n'
@@ -181,9 +194,19 @@ def main(argv=None):
         sys.stderr.write('Currently only supports 1 type of adaptation.')                  # train.py:489-491
         return 1
     adapt = options.user_adapt or options.experience_adapt
+    import os
     import torch
     from .engine import Corpus, Engine
     from .trainer import AdaptTrainer, Trainer, dist_info
+    # one process per GPU under torchrun: rank / world from the environment, NCCL over NVLink for the 16 x f64 all-reduce
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        if not dist.is_initialized():
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+    # the reference trains AND predicts with these flags (train.py:155-156 -> LBP.py:506-516, :554-563)
+    approx_kw = dict(approx_inference=options.use_approx_inference, approx_beliefs=options.use_approx_beliefs)
     random.seed(options.seed)
     rng = random.Random(options.seed + 1)
     en_domain, de_domain, en2id, de2id, model = load_inputs(options)
@@ -232,17 +255,21 @@ def main(argv=None):
                 for d in sorted(groups):
                     c = Corpus(groups[d])
                     batches.append((d, c, draw_roots(c, 3, rng)))
-                red = tr.step_domains(batches, lr)
+                red = tr.step_domains(batches, lr, **approx_kw)
                 logp += tr.apply(red, lr)[9]
             print('\nepoch:', epoch)
             print(f_en_en_names, tr.theta_ee)
             print(f_en_de_names, tr.theta_ed)
             print('\ntrain prediction probs:', logp / float(len(sents)))
+            if options.save_params_file:
+                gather_domain_thetas(tr, owner, rank, world)              # a domain's theta lives on the rank that owns it
             if rank == 0 and options.save_params_file:
                 save_params(codecs.open(options.save_params_file + ext + '.iter' + str(epoch), 'w', 'utf8'),
                             tr.theta_ee.reshape(1, -1), tr.theta_ed.reshape(1, -1), f_en_en_names, f_en_de_names, d2t_arrays(tr))
                 print('saved params')
         print('\ntheta final:', tr.theta_ee, tr.theta_ed)
+        if options.save_params_file:
+            gather_domain_thetas(tr, owner, rank, world)
         if rank == 0 and options.save_params_file:
             save_params(codecs.open(options.save_params_file + ext, 'w', 'utf8'), tr.theta_ee.reshape(1, -1),
                         tr.theta_ed.reshape(1, -1), f_en_en_names, f_en_de_names, d2t_arrays(tr))
@@ -259,10 +286,8 @@ def main(argv=None):
             logp = 0.0
             for lo in range(0, len(order), mb):
                 batch = [sents[i] for i in order[lo:lo + mb]][rank::world]
-                if not batch:
-                    batch = [sents[order[lo]]]
-                corpus = Corpus(batch)
-                red = tr.step(corpus, draw_roots(corpus, 3, rng), lr)
+                corpus = Corpus(batch)                  # an empty shard contributes a zero vector to the all-reduce
+                red = tr.step(corpus, draw_roots(corpus, 3, rng), lr, **approx_kw)
                 logp += tr.apply(red, lr)[9]
             print('\nepoch:', epoch)
             print(f_en_en_names, tr.theta_ee)

@@ -194,8 +194,11 @@ class FakeKernels(object):
                 s = p.sum()
                 x = p * (A_SCALE / s) if (s > 0 and np.isfinite(s)) else np.full(V, A_SCALE / V)
                 hi, lo = _split(x)
-                if peak_flag is not None and peak_flag.value and x.max() > peak_prob * A_SCALE:
-                    _arr(peak_flag, np.int32, 1)[0] = 1
+                if peak_flag is not None and peak_flag.value:
+                    pf = _arr(peak_flag, np.int32, 3)
+                    if x.max() > peak_prob * A_SCALE:
+                        pf[0] = 1
+                    pf[2:3].view(np.float32)[0] = max(float(pf[2:3].view(np.float32)[0]), float(np.float32(x.max())))
                 for tdest in de[do[i]:do[i + 1]]:
                     H[tdest, :V], L[tdest, :V] = hi, lo
 

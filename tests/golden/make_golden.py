@@ -388,17 +388,77 @@ def run_explicit_case(LBP, feeder):
 
 
 # ----------------------------------------------------------------------------- cases
+def run_formats_case(LBP, train, feeder, work):
+    """On-disk formats written BY THE REFERENCE: a parameter checkpoint from train.save_params
+    (train.py:77-99) with adapted domains, what train.read_params (:46-74) parses back from it, and the prediction / .dist
+    lines of FactorGraph.to_string / to_dist (LBP.py:109-143) for one graph."""
+    import codecs
+    rng = np.random.default_rng(77)
+    ee = rng.normal(size=(1, 3)) * 0.7
+    ed = rng.normal(size=(1, 6)) * 0.7
+    d2t = {}
+    for d in ('user_a', 'u2', 'a_rather_long_user_name'):
+        d2t['en_en', d] = rng.normal(size=(1, 3))
+        d2t['en_de', d] = rng.normal(size=(1, 6)) * 1e-3        # small values: the 6-decimal rounding is visible
+    ee_names, ed_names = ['pmi', 'pmi_w1', 'bias'], ['ed', 'ped', 'correct', 'full_history', 'hit_history', 'bias']
+    path = os.path.join(work, 'golden.params')
+    train.save_params(codecs.open(path, 'w', 'utf8'), ee, ed, ee_names, ed_names, d2t)
+    text = open(path, 'rb').read().decode('utf8')
+    een, eet, edn, edt, back = train.read_params(path)
+    out = {'params_text': np.array(text), 'ee': ee, 'ed': ed, 'domains': np.array([d for ft, d in d2t if ft == 'en_en']),
+           'd_ee': np.stack([d2t['en_en', d][0] for ft, d in d2t if ft == 'en_en']),
+           'd_ed': np.stack([d2t['en_de', d][0] for ft, d in d2t if ft == 'en_en']),
+           'read_een': np.array(een), 'read_edn': np.array(edn), 'read_ee': eet, 'read_ed': edt,
+           'read_d_ee': np.stack([back['en_en', d][0] for ft, d in d2t if ft == 'en_en']),
+           'read_d_ed': np.stack([back['en_de', d][0] for ft, d in d2t if ft == 'en_en'])}
+    # prediction + .dist lines of one graph (the toy5 case: given + predicted tokens, history features)
+    spec = synth.golden_case_specs()['toy5']
+    model = synth.make_model(spec['V'], spec['Vd'], seed=spec['model_seed'])
+    sent = synth.make_sentence(model, spec['layout'], seed=spec['sent_seed'], n_history=spec.get('n_history', 2))
+    r = np.random.default_rng(spec['sent_seed'] + 99)
+    pred = [p for p, k in enumerate(spec['layout']) if k == 'p']
+    roots = [int(r.choice(pred)) for _ in range(1 + spec['sweeps'])]
+    V, Vd = spec['V'], spec['Vd']
+    en_domain = ['e%d' % i for i in range(V)]
+    de_domain = ['d%d' % i for i in range(Vd)]
+    phi_ee, phi_ee_w1, phi_ed = make_phi(model)
+    pw = LBP.PhiWrapper(phi_ee, phi_ee_w1, phi_ed)
+    train.options = ref_options()
+    train.N = 10
+    train.de_domain = de_domain
+    train.domain2theta = {}
+    ti = train.TrainingInstance.from_dict(json.loads(synth.sentence_to_json(sent)))
+    fg = train.create_factor_graph(ti=ti, learning_rate=0.1, theta_en_en_names=ee_names, theta_en_de_names=ed_names,
+                                   theta_en_en=np.array(spec['theta_ee'], dtype=np.float64).reshape(1, -1),
+                                   theta_en_de=np.array(spec['theta_ed'], dtype=np.float64).reshape(1, -1), phi_wrapper=pw,
+                                   en_domain=en_domain, de2id=dict((d, i) for i, d in enumerate(de_domain)),
+                                   en2id=dict((e, i) for i, e in enumerate(en_domain)), d2t={})
+    feeder.queue = [roots[0]]
+    fg.initialize()
+    feeder.queue = list(roots[1:1 + (spec['sweeps'] if fg.isLoopy else 1)])
+    fg.treelike_inference(spec['sweeps'])
+    out['case'] = np.array('toy5')
+    out['roots'] = np.array(roots)
+    out['to_string'] = np.array(fg.to_string())
+    out['to_dist'] = np.array(fg.to_dist())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--ref', default='/root/reference')
     ap.add_argument('--out', default=HERE)
     ap.add_argument('--only-new', action='store_true', help='write only au_cases_more.npz and graphx_explicit.npz')
+    ap.add_argument('--only-formats', action='store_true', help='write only formats.npz (checkpoint / prediction / .dist text)')
     args = ap.parse_args()
     work = tempfile.mkdtemp(prefix='mlbp_ref_')
     try:
         build_patched_reference(args.ref, work)
         LBP, train, feeder = import_reference(work)
         au = importlib.import_module('array_utils.c_array_utils')
+        np.savez_compressed(os.path.join(args.out, 'formats.npz'), **run_formats_case(LBP, train, feeder, work))
+        if args.only_formats:
+            return
         np.savez_compressed(os.path.join(args.out, 'au_cases_more.npz'), **au_cases_more(au))
         np.savez_compressed(os.path.join(args.out, 'graphx_explicit.npz'), **run_explicit_case(LBP, feeder))
         if args.only_new:

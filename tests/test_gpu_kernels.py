@@ -138,10 +138,14 @@ def test_pairwise_tables(lib):
         assert np.abs(got - W).max() / W.max() < 1e-6, i
         assert (pl[2 * i][:, V:] == 0).all()
     c = cols.cpu().numpy()
+    # K2 evaluates exp in fp32 on a compensated argument (~1 ulp per entry, random) and sums in compensated fp32 / float64:
+    # column sums over V = 200 entries are good to ~1e-8, row sums (plain fp32 across the 64 columns of a tile) to ~1e-7.
+    # (Round 1 used a float64 exp per element and asserted 1e-12 here; the consumers of these sums -- the unary gradient and the
+    # constant messages -- need 1e-6.)
     for i, W in enumerate([T, T1, T * p32, T1 * p32, T1 * w32]):
-        np.testing.assert_allclose(c[i], W.sum(0), rtol=1e-12)
-    np.testing.assert_allclose(c[5], T.sum(1), rtol=1e-12)
-    np.testing.assert_allclose(c[6], T1.sum(1), rtol=1e-12)
+        np.testing.assert_allclose(c[i], W.sum(0), rtol=3e-8)
+    np.testing.assert_allclose(c[5], T.sum(1), rtol=2e-7)
+    np.testing.assert_allclose(c[6], T1.sum(1), rtol=2e-7)
 
 
 def test_dense_array_utils(lib):
