@@ -44,6 +44,7 @@ extern "C" {
 #define MLBP_N_SUMS           7   /* per-theta sum vectors written by mlbp_build_pairwise_tables                */
 #define MLBP_D_CONST_ROWS     5   /* D rows 1..4 hold the constant messages of the 4 message tables (row 0 spare) */
 #define MLBP_A_SCALE_LOG2    14   /* var->factor rows are stored as 2^14 * normalised message, split hi + lo fp16 */
+#define MLBP_SPIKE_SLOTS      4   /* spikes recorded per message row (mlbp_var_to_factor / mlbp_spike_correct)   */
 
 const char *mlbp_last_error(void);
 int mlbp_version(void);
@@ -124,15 +125,29 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   constant-one row D[0] in its place (messages are scale-free), so the caller keeps D row 0 filled with 1.0f.
  *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
  *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow).
- *   peak_flag (optional, may be NULL): 3 device int32 words; word 0 is SET to 1 (never cleared) when any element of any message
- *   written by this call exceeds the probability peak_prob, word 2 keeps the largest element seen so far as the bits of
- *   the float 2^14 * probability (atomic max; diagnostics).  mlbp_factor_to_var_gemm_gated reads it: a message whose
- *   mass sits on few words does not average its fp16 rounding away, so rows written after the flag went up keep
- *   all three tensor-core passes.                                                                              */
+ *   Spike tracking (spike_words != NULL, else the other spike_* arguments are ignored).  A two-pass message row
+ *   (MLBP_GEMM_A_HI_ONLY) drops the lo half of every message element; for the bulk of a message that rounding averages away
+ *   in the contraction, for an element that carries more than spike_prob of the mass (a history feature's word, say) it
+ *   does not.  For every such element written to a MESSAGE row (A row < n_msg_rows) the kernel records
+ *   (column, x - fp16(x)) in spike_entries[row][MLBP_SPIKE_SLOTS] (int32 pairs: column, float bits), counts them in
+ *   spike_cnt[row] (zeroed by the caller per batch) and lists rows with spikes in spike_rows; mlbp_spike_correct restores
+ *   the dropped contribution exactly.  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
+ *     [0] PEAK   set when a row has more spikes than slots: mlbp_factor_to_var_gemm_gated then keeps all three passes   (per theta)
+ *     [2] the largest element seen so far, bits of the float 2^14 * probability (atomic max; diagnostics)               (per theta)
+ *     [3] SPIKE  set when any spike was seen: the gradient rows then keep the lo half of the table planes               (per theta)
+ *     [4] number of rows in spike_rows                                                                                  (per batch) */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                        const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
-                       void *A_lo, int max_in, float range_log2, int32_t *peak_flag, float peak_prob, void *stream);
+                       void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
+                       int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_msg_rows, void *stream);
+/* K4b. Spike compensation of a two-pass message GEMM block (rows [a_row0, a_row0 + n_rows) of A -> D rows d_row0 ..):
+ *   D[r, n] += alpha * sum over the recorded spikes s of row r of  lo_s * B[n, col_s],  with B[n, col] read as row `col` of
+ *   the TRANSPOSED table's plane pair Bt_hi / Bt_lo (MLBP_TABLE_T <-> TT, T1 <-> T1T).  Returns at once (on the device) when
+ *   spike_words[0] is set: the block then ran with three passes.  Spikes of a row are applied in ascending column order.   */
+int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
+                       const int32_t *spike_rows, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo, int V,
+                       int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream);
 /* Approximate paths (use_approx_inference LBP.py:506-507, :515-516 -> au.sparse_vec_mat_dot pyx:193-205;
  *   use_approx_beliefs LBP.py:554-563 -> au.sparse_dot / sparse_pointwise_multiply / sparse_normalize pyx:108-129, :23-26):
  *   keep the K largest entries of each of the n_rows operand rows A[row0 ..], zero the others (K = 100 in the reference);
@@ -156,8 +171,9 @@ int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_t
                             float alpha, int impl, void *stream);
 /* The same launch, DECIDED ON THE DEVICE: every CTA first reads *gate (device int32) and returns at once unless
  * (*gate != 0) == (run_if_set != 0).  The engine issues a level's message rows twice -- two passes (A_HI_ONLY) with
- * run_if_set = 0 and all three passes with run_if_set = 1 -- on the flag that mlbp_var_to_factor raises when it writes
- * a peaked message; exactly one of the two launches does the work and no host synchronisation is needed.
+ * run_if_set = 0 and all three passes with run_if_set = 1 -- on the PEAK word that mlbp_var_to_factor raises when a message
+ * has more spikes than it can record (and the gradient rows, likewise, on the SPIKE word); exactly one of the two launches
+ * does the work and no host synchronisation is needed.
  * gate == NULL runs unconditionally.  tcgen05 kernels only (impl 1, the SIMT cross-check, ignores the gate on the host: error). */
 int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                                   const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
@@ -216,7 +232,8 @@ int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t 
  *   precision counts of FactorGraph.get_precision_counts (LBP.py:80-106).  ADDS this micro-batch to out16 (device, 16 float64,
  *   zeroed by the caller at the start of an SGD step; it is the buffer the NCCL all-reduce ships):
  *   [0..8] sum of grad[s][9], [9] sum of logp_sent, [10] #rank == 0, [11] #rank < 26, [12] #rank < 50, [13] n_vars, [14] n_sent;
- *   [15] is SET to 1 when *peak_flag != 0 (see mlbp_var_to_factor).  grad / logp_sent / rank / peak_flag may be NULL.
+ *   [15] = max([15], (spike_words[0] ? 1 : 0) + (spike_words[3] ? 2 : 0)) with peak_flag = the spike_words of
+ *   mlbp_var_to_factor (which reduced-pass GEMM variants this rank ran).  grad / logp_sent / rank / peak_flag may be NULL.
  *   One CTA, fixed summation order (deterministic).                                                              */
 int mlbp_batch_reduce(int n_sent, const double *grad, const double *logp_sent, int n_vars, const int32_t *rank,
                       const int32_t *peak_flag, double *out16, void *stream);

@@ -112,7 +112,10 @@ batch_reduce_kernel(int n_sent, const double *__restrict__ grad, const double *_
     if (threadIdx.x == 0) {
         out16[13] += rank ? (double)n_vars : 0.0;
         out16[14] += (double)n_sent;
-        if (peak_flag && *peak_flag) out16[15] = 1.0;
+        if (peak_flag) {                                           // 1 = PEAK (message rows ran three passes), 2 = SPIKE word
+            const double code = (peak_flag[0] ? 1.0 : 0.0) + (peak_flag[3] ? 2.0 : 0.0);
+            if (code > out16[15]) out16[15] = code;
+        }
     }
 }
 

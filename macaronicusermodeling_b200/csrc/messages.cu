@@ -66,14 +66,43 @@ __device__ __forceinline__ void k3_store(float x, size_t first, int nd, const in
     }
 }
 
-// End of a K3 kernel: raise the peak flag (see mlbp_var_to_factor) and keep the largest element seen in peak_flag[2]
-// (2^14 * probability as float bits; non-negative floats order like their bit patterns) -- one atomic per warp.
-__device__ __forceinline__ void k3_report_peak(int32_t *peak_flag, float peak_limit, float mx) {
-    if (!peak_flag) return;
-    if (!(mx <= peak_limit)) *peak_flag = 1;
+// Spikes.  A two-pass message row (A_hi . B) drops the lo half of every message element.  For the bulk of a message that
+// rounding averages away in the contraction; for an element that carries a visible share of the mass (a "spike": more than
+// spike_limit, e.g. the word a history feature points at) it does not.  K3 therefore records, per A row, the spikes it writes
+// -- (column, x - fp16(x)) -- and mlbp_spike_correct adds  alpha * lo * T[:, column]  to the row's GEMM output afterwards: the
+// exact contribution of the dropped part, a few AXPYs instead of a third tensor-core pass over the whole level.
+// words (device int32): [0] PEAK  set when a row has more spikes than slots (message rows fall back to three passes),
+//                       [2] MAXBITS largest element seen (bits of 2^14 * probability; diagnostics),
+//                       [3] SPIKE set when any spike was seen (gradient rows keep the lo half of the table),
+//                       [4] number of rows in the spiky-row list.
+struct K3Spikes {
+    int32_t *words;          // nullptr: no tracking
+    int32_t *cnt;            // [n_msg_rows] spikes recorded per message A row (zeroed by the caller per run)
+    int2 *entries;           // [n_msg_rows][MLBP_SPIKE_SLOTS] (column, float bits of lo)
+    int32_t *rows;           // [n_msg_rows] rows with at least one spike, in order of discovery
+    int n_msg_rows;          // A rows >= n_msg_rows are gradient-stage copies: not corrected
+    float limit;             // 2^14 * probability above which an element is a spike
+};
+
+__device__ __noinline__ void k3_record_spike(const K3Spikes sp, const int32_t *__restrict__ dest, int d0, int nd, int col, float x) {
+    const float lo = x - __half2float(__float2half_rn(x));        // what a two-pass row drops (exact in fp32)
+    sp.words[3] = 1;
+    for (int t = 0; t < nd; ++t) {
+        const int row = dest[d0 + t];
+        if (row >= sp.n_msg_rows) continue;
+        const int slot = atomicAdd(&sp.cnt[row], 1);
+        if (slot == 0) sp.rows[atomicAdd(&sp.words[4], 1)] = row;
+        if (slot < MLBP_SPIKE_SLOTS) sp.entries[(size_t)row * MLBP_SPIKE_SLOTS + slot] = make_int2(col, __float_as_int(lo));
+        else sp.words[0] = 1;
+    }
+}
+
+// End of a K3 kernel: keep the largest element seen (one atomic per warp)
+__device__ __forceinline__ void k3_report_max(const K3Spikes &sp, float mx) {
+    if (!sp.words) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(peak_flag + 2, __float_as_int(mx));
+    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(sp.words + 2, __float_as_int(mx));
 }
 
 template <int NMAX, typename T, int OCC>
@@ -82,7 +111,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                      const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
                      const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V,
-                     __half *__restrict__ A_hi, __half *__restrict__ A_lo, int32_t *__restrict__ peak_flag, float peak_limit) {
+                     __half *__restrict__ A_hi, __half *__restrict__ A_lo, const K3Spikes sp) {
     __shared__ const float *s_src[NMAX];
     __shared__ int s_d0[NMAX], s_nd[NMAX];
     __shared__ size_t s_first[NMAX];
@@ -159,12 +188,13 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
                 const float sc = s_scale[j];
                 const float x = sc > 0.f ? (float)(pre[j] * suf * (T)sc) : uni;
                 mx = fmaxf(mx, x);
+                if (sp.words && x > sp.limit) k3_record_spike(sp, dest, s_d0[j], nd, e, x);      // rare
                 k3_store(x, s_first[j] + e, nd, dest, s_d0[j], ldv, e, A_hi, A_lo);
             }
             suf *= (T)d[j];
         }
     }
-    k3_report_peak(peak_flag, peak_limit, mx);
+    k3_report_max(sp, mx);
 }
 
 // Messages with more than TWO readers (the first two are written directly): the slice just written to the first reader's
@@ -205,8 +235,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                               const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                               const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
                               const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V, int S,
-                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, int32_t *__restrict__ peak_flag, float peak_limit,
-                              long long *dbg) {
+                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, const K3Spikes sp, long long *dbg) {
 #ifdef MLBP_K3_STAGE_TIMES                                      // scripts/k3_probe.py: cycles per stage, per CTA
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define K3_TICK(i) do { const long long tn_ = clock64(); tacc[i] += tn_ - tprev; tprev = tn_; } while (0)
@@ -417,7 +446,12 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                     const float sc = s_scale[j];
                     float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
                     if (!(sc > 0.f)) x = make_float2(uni, uni);
-                    mx = fmaxf(mx, fmaxf(x.x, odd ? 0.f : x.y));
+                    const float xm = fmaxf(x.x, odd ? 0.f : x.y);
+                    mx = fmaxf(mx, xm);
+                    if (sp.words && xm > sp.limit) {                                  // rare: a spike (see K3Spikes)
+                        if (x.x > sp.limit) k3_record_spike(sp, dest, s_d0[b][j], s_nd[b][j], col0 + 2 * e2, x.x);
+                        if (!odd && x.y > sp.limit) k3_record_spike(sp, dest, s_d0[b][j], s_nd[b][j], col0 + 2 * e2 + 1, x.y);
+                    }
                     const __half2 hi = __float22half2_rn(x);
                     const float2 back = __half22float2(hi);
                     const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
@@ -468,7 +502,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
         __syncthreads();                                           // shared memory is reused by the next group
         K3_TICK(5);
     }
-    k3_report_peak(peak_flag, peak_limit, mx);
+    k3_report_max(sp, mx);
 #ifdef MLBP_K3_STAGE_TIMES
     if (dbg && threadIdx.x == 0)
         for (int i = 0; i < 6; ++i) dbg[(size_t)blockIdx.x * 6 + i] = tacc[i];
@@ -631,8 +665,7 @@ template <int NIN>
 static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, const int32_t *grp_u,
                                    const int32_t *grp_off, const int32_t *in_row, const int32_t *dest_off,
                                    const int32_t *dest, const int32_t *first_dest, const int32_t *second_dest, const float *U,
-                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo, int32_t *peak_flag,
-                                   float peak_limit) {
+                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo, const K3Spikes sp) {
     // function attributes and occupancy are per DEVICE: a process that drives several GPUs configures each one
     static bool configured[MLBP_MAX_DEVICES] = {};
     int dev = 0;
@@ -668,7 +701,7 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     const int n_clusters = n_groups < resident[C] ? n_groups : resident[C];
     cfg.gridDim = dim3((unsigned)n_clusters * (unsigned)C);
     return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv,
-                              V, S, A_hi, A_lo, peak_flag, peak_limit, g_k3_dbg);
+                              V, S, A_hi, A_lo, sp, g_k3_dbg);
 }
 
 constexpr int K3_RESIDENT_MAX_IN = 24;
@@ -676,7 +709,8 @@ constexpr int K3_RESIDENT_MAX_IN = 24;
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                                   const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                                   const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
-                                  void *A_lo, int max_in, float range_log2, int32_t *peak_flag, float peak_prob,
+                                  void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
+                                  int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_msg_rows,
                                   void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && second_dest && U && D && A_hi && A_lo,
@@ -689,7 +723,12 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = as_stream(stream);
-    const float peak_limit = ldexpf(peak_prob, MLBP_A_SCALE_LOG2);   // rows are stored as 2^14 * probability
+    MLBP_CHECK_ARG(!spike_words || (spike_cnt && spike_entries && spike_rows && n_msg_rows >= 0 && spike_prob > 0.f),
+                   "var_to_factor: spike tracking needs cnt, entries, rows and a positive threshold");
+    K3Spikes sp;
+    sp.words = spike_words; sp.cnt = spike_cnt; sp.entries = reinterpret_cast<int2 *>(spike_entries); sp.rows = spike_rows;
+    sp.n_msg_rows = n_msg_rows;
+    sp.limit = ldexpf(spike_prob, MLBP_A_SCALE_LOG2);              // rows are stored as 2^14 * probability
     // The resident single-read kernel runs whenever the products fit fp32 and the cluster's slices fit shared memory;
     // MLBP_K3_IMPL=1 forces the streaming two-read kernel (used by scripts/k3_probe.py to time both).
     const char *env_impl = getenv("MLBP_K3_IMPL");
@@ -707,7 +746,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
 #define MLBP_K3_RES(N)                                                                                             \
         case N:                                                                                                    \
             MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, \
-                                         (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit));                  \
+                                         (__half *)A_hi, (__half *)A_lo, sp));                                     \
             break;
         switch (nin) {
             MLBP_K3_RES(1) MLBP_K3_RES(2) MLBP_K3_RES(3) MLBP_K3_RES(4) MLBP_K3_RES(5) MLBP_K3_RES(6) MLBP_K3_RES(7)
@@ -724,13 +763,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     do {                                                                                                         \
         if (fp32_ok && N <= 20)                                                                                  \
             var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit); \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, sp); \
         else if (fp32_ok)                                                                                        \
             var_to_factor_kernel<N, float, 1><<<n_groups, K3_THREADS, 0, st>>>(                                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit); \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, sp); \
         else                                                                                                     \
             var_to_factor_kernel<N, double, 1><<<n_groups, K3_THREADS, 0, st>>>(                                 \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, peak_flag, peak_limit); \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, sp); \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);

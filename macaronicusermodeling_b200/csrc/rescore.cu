@@ -142,8 +142,9 @@ rescore_kernel(const int32_t *__restrict__ flagged, const int32_t *__restrict__ 
             } else {
                 const size_t arow = (size_t)(r - MLBP_D_CONST_ROWS) * ldv;
                 const __half *bh = planes + (size_t)(2 * t) * plane_stride, *bl = planes + (size_t)(2 * t + 1) * plane_stride;
-                // rows are padded with zeros up to ldv (a multiple of 64): whole 16-byte chunks of 8 fp16, no tail
-                const int n8 = ldv >> 3;
+                // 16-byte chunks of 8 fp16; rows are padded to ldv (a multiple of 64) so the last chunk may be loaded whole,
+                // but the padding of the A rows is never written (uninitialised memory, possibly NaN): it is masked below
+                const int n8 = (V + 7) >> 3;
                 const uint4 *ah8 = reinterpret_cast<const uint4 *>(A_hi + arow), *al8 = reinterpret_cast<const uint4 *>(A_lo + arow);
                 for (int c0 = 0; c0 < nc; c0 += 4) {
                     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -156,11 +157,21 @@ rescore_kernel(const int32_t *__restrict__ flagged, const int32_t *__restrict__ 
                     for (int k8 = threadIdx.x; k8 < n8; k8 += RS_THREADS) {
                         float a[8];
                         unpack8(__ldg(ah8 + k8), __ldg(al8 + k8), a);
+                        if (8 * k8 + 8 > V) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (8 * k8 + i >= V) a[i] = 0.f;
+                        }
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             if (c0 + c < nc) {                     // block-uniform
                                 float b[8];
                                 unpack8(__ldg(bh8[c] + k8), __ldg(bl8[c] + k8), b);
+                                if (8 * k8 + 8 > V) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (8 * k8 + i >= V) b[i] = 0.f;
+                                }
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) acc[c] = fmaf(a[i], b[i], acc[c]);
                             }

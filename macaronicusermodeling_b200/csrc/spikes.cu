@@ -1,0 +1,92 @@
+// K4b: spike compensation of two-pass message rows.
+//
+// A two-pass message GEMM (MLBP_GEMM_A_HI_ONLY) computes  D[r, :] = alpha * A_hi[r, :] . B'  and drops  A_lo[r, :] . B'.
+// For the elements of a message that carry a visible share of its mass (spikes, recorded by the var->factor kernel: see
+// K3Spikes in messages.cu) the dropped term is restored exactly here:
+//     D[r, n] += alpha * sum_s lo_s * B[n, col_s]
+// B[n, col] for all n is row `col` of the TRANSPOSED table's plane pair (K2 stores both orientations K-major), so a spike costs
+// one contiguous row read (hi + lo) and the row's spikes share one read-modify-write of D[r, :].  Reference semantics are
+// untouched: this is arithmetic the float64 dgemv of LBP.py:509 / :518 does implicitly.
+//
+// One launch per (level, table) GEMM block, after the block's gated launches.  Persistent CTAs walk the list of spiky rows and
+// pick those inside the block; the spikes of a row are applied in ascending column order (deterministic).  The kernel returns
+// at once when the gate word is set: then the block ran with all three passes and nothing was dropped.
+#include "common.cuh"
+
+namespace mlbp {
+
+constexpr int SP_THREADS = 256;
+
+__global__ void __launch_bounds__(SP_THREADS)
+spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restrict__ cnt, const int2 *__restrict__ entries,
+                     const int32_t *__restrict__ rows, int a0, int n_rows, const __half *__restrict__ Bt_hi,
+                     const __half *__restrict__ Bt_lo, int V, int ldv, float *__restrict__ D, int64_t d_row0, int ldd,
+                     float alpha) {
+    if (words[0] != 0) return;                                     // three passes ran: nothing to restore
+    __shared__ int s_col[MLBP_SPIKE_SLOTS];
+    __shared__ float s_lo[MLBP_SPIKE_SLOTS];
+    const int total = words[4];
+    for (int i = blockIdx.x; i < total; i += gridDim.x) {
+        const int row = rows[i];
+        if (row < a0 || row >= a0 + n_rows) continue;              // block-uniform
+        const int n = min(cnt[row], MLBP_SPIKE_SLOTS);
+        __syncthreads();
+        if (threadIdx.x == 0) {                                    // insertion sort by column: fixed summation order
+            for (int s = 0; s < n; ++s) {
+                const int2 e = entries[(size_t)row * MLBP_SPIKE_SLOTS + s];
+                int p = s;
+                while (p > 0 && s_col[p - 1] > e.x) { s_col[p] = s_col[p - 1]; s_lo[p] = s_lo[p - 1]; --p; }
+                s_col[p] = e.x; s_lo[p] = __int_as_float(e.y);
+            }
+        }
+        __syncthreads();
+        float *drow = D + (d_row0 + (int64_t)(row - a0)) * (int64_t)ldd;
+        // rows are padded to a multiple of 64 elements: whole chunks of 8 (the padding of the planes is zero)
+        for (int c8 = threadIdx.x; c8 < (ldv >> 3); c8 += SP_THREADS) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int s = 0; s < n; ++s) {
+                const size_t o = (size_t)s_col[s] * ldv + 8 * (size_t)c8;
+                const uint4 h = __ldg(reinterpret_cast<const uint4 *>(Bt_hi + o)), l = __ldg(reinterpret_cast<const uint4 *>(Bt_lo + o));
+                const __half2 *hh = reinterpret_cast<const __half2 *>(&h), *ll = reinterpret_cast<const __half2 *>(&l);
+                const float w = s_lo[s];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 a = __half22float2(hh[q]), b = __half22float2(ll[q]);
+                    acc[2 * q] = fmaf(w, a.x + b.x, acc[2 * q]);
+                    acc[2 * q + 1] = fmaf(w, a.y + b.y, acc[2 * q + 1]);
+                }
+            }
+            float4 *d4 = reinterpret_cast<float4 *>(drow + 8 * (size_t)c8);
+            float4 x = d4[0], y = d4[1];
+            const int e = 8 * c8;
+            x.x += e + 0 < V ? alpha * acc[0] : 0.f; x.y += e + 1 < V ? alpha * acc[1] : 0.f;
+            x.z += e + 2 < V ? alpha * acc[2] : 0.f; x.w += e + 3 < V ? alpha * acc[3] : 0.f;
+            y.x += e + 4 < V ? alpha * acc[4] : 0.f; y.y += e + 5 < V ? alpha * acc[5] : 0.f;
+            y.z += e + 6 < V ? alpha * acc[6] : 0.f; y.w += e + 7 < V ? alpha * acc[7] : 0.f;
+            d4[0] = x; d4[1] = y;
+        }
+    }
+}
+
+}  // namespace mlbp
+
+using namespace mlbp;
+
+extern "C" int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
+                                  const int32_t *spike_rows, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo,
+                                  int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream) {
+    if (n_rows == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(spike_words && spike_cnt && spike_entries && spike_rows && Bt_hi && Bt_lo && D && n_rows > 0 && a_row0 >= 0,
+                   "spike_correct: bad argument");
+    MLBP_CHECK_ARG((ldv % 64) == 0 && ldv >= V && (ldd % 64) == 0 && ldd >= V &&
+                   ((reinterpret_cast<uintptr_t>(Bt_hi) | reinterpret_cast<uintptr_t>(Bt_lo) | reinterpret_cast<uintptr_t>(D)) % 16) == 0,
+                   "spike_correct: rows must be 16-byte aligned and padded to a multiple of 64");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+    const int grid = n_rows < 2 * sms ? n_rows : 2 * sms;
+    spike_correct_kernel<<<grid, SP_THREADS, 0, as_stream(stream)>>>(spike_words, spike_cnt, reinterpret_cast<const int2 *>(spike_entries),
+                                                                    spike_rows, a_row0, n_rows, (const __half *)Bt_hi,
+                                                                    (const __half *)Bt_lo, V, ldv, D, d_row0, ldd, alpha);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}

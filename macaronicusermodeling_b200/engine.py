@@ -35,7 +35,8 @@ N_SUMS = 7
 D_CONST_ROWS = 5
 # Engine._flags (device int32 words): the peak flag of the var->factor kernel (sticky per theta), the flagged-variable count of
 # one marginals launch, and the re-score counters (mlbp_rescore_candidates)
-FLAG_PEAK, FLAG_NFLAGGED, FLAG_MAXBITS, FLAG_COUNTERS, FLAG_WORDS = 0, 1, 2, 8, 16
+FLAG_PEAK, FLAG_NFLAGGED, FLAG_MAXBITS, FLAG_SPIKE, FLAG_NSPIKY, FLAG_COUNTERS, FLAG_WORDS = 0, 1, 2, 3, 4, 8, 16
+SPIKE_SLOTS = 4               # include/mlbp.h MLBP_SPIKE_SLOTS
 
 
 def round_up(x, m):
@@ -218,7 +219,7 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None, msg_passes=None, tau=5e-4, tau_label=2.5e-4, peak_mult=64.0):
+                 gemm_slice_pairs=None, msg_passes=None, tau=5e-4, tau_label=2.5e-4, peak_mult=16.0):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -237,9 +238,13 @@ class Engine(object):
         # a belief undamped is the rounding of the LAST hop -- measured 2.3e-6 relative rms on a belief at V = 10 000 (flat
         # synthetic messages; it shrinks like 1 / sqrt(V_eff)) -- and that hop is recomputed from the full 22-bit operands
         # for every candidate within `tau` of the arg-max (or within `tau_label` of the label while its rank can matter).
-        # Guards: (i) the potentials span at most e^3 (set_theta), (ii) no message puts more than peak_mult / V of its mass
-        # on one word -- checked on the DEVICE by the var->factor kernel, which raises a flag that switches all later message
-        # GEMMs of this theta to three passes (mlbp_factor_to_var_gemm_gated; no host synchronisation).
+        # Guards: (i) the potentials span at most e^3 (set_theta); (ii) spikes: an element that carries more than peak_mult / V
+        # of a message's mass does not average its rounding away, so the var->factor kernel records it and
+        # mlbp_spike_correct restores its dropped lo part exactly after the GEMM (a few AXPYs per spiky row); a row with more
+        # spikes than slots raises a flag ON THE DEVICE that switches all later message GEMMs of this theta to three passes
+        # (mlbp_factor_to_var_gemm_gated; no host synchronisation).  The one-pass gradient rows are gated the same way: once
+        # any spike was seen they keep the lo half of the table planes (a peaked belief does not average the fp16 rounding
+        # of T o PMI away: tests/test_gpu_gates.py).
         # msg_passes: None = two passes where V >= 4096 (where the error above was measured), 2 = at any V, 3 = never.
         self.msg_passes = msg_passes
         self.tau, self.tau_label, self.peak_mult = float(tau), float(tau_label), float(peak_mult)
@@ -349,7 +354,8 @@ class Engine(object):
         switched the message GEMMs back to three passes, and what the exact re-score did."""
         f = self._flags.cpu().numpy()
         c = f[FLAG_COUNTERS:FLAG_COUNTERS + 5]
-        return {'msg_two_pass': bool(self.msg_two_pass_ok), 'peak_flag': int(f[FLAG_PEAK]),
+        return {'msg_two_pass': bool(self.msg_two_pass_ok), 'peak_flag': int(f[FLAG_PEAK]), 'spike_flag': int(f[FLAG_SPIKE]),
+                'spiky_rows_last_batch': int(f[FLAG_NSPIKY]),
                 'max_message_prob': float(f[FLAG_MAXBITS:FLAG_MAXBITS + 1].view(np.float32)[0]) * 2.0 ** -A_SCALE_LOG2, 'rescored': int(c[0]),
                 'skipped_mass_tie': int(c[1]), 'skipped_degenerate': int(c[2]), 'top1_changed': int(c[3]),
                 'rank_changed': int(c[4])}
@@ -485,6 +491,14 @@ class Engine(object):
         td = self.theta_ed
         c = lambda name: _p(corpus.dev(name, dev))
         peak_flag = _p(self._flags, FLAG_PEAK) if two_pass else None
+        n_msg = int(blob[H_MSG_ROWS])
+        spk_cnt = spk_ent = spk_rows = None
+        if two_pass:                                              # spike bookkeeping of this batch's message rows
+            spk_cnt = torch.empty(max(n_msg, 1), dtype=torch.int32, device=dev)
+            spk_ent = torch.empty((max(n_msg, 1), SPIKE_SLOTS, 2), dtype=torch.int32, device=dev)
+            spk_rows = torch.empty(max(n_msg, 1), dtype=torch.int32, device=dev)
+            k.call('mlbp_zero_words', _p(spk_cnt), max(n_msg, 1))
+            k.call('mlbp_zero_words', _p(self._flags, FLAG_NSPIKY), 1)
 
         D[:D_CONST_ROWS].copy_(self.const_rows)                   # row 0: the constant-one row messages still uniform read
         inv_sigma = torch.empty(max(nv, 1), dtype=torch.float64, device=dev)
@@ -531,17 +545,18 @@ class Engine(object):
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
                     if gated:
-                        # decided on the device: two passes while no message of this theta was peaked, else all three
-                        for fl, run_if_set in ((impl_flags, 0), (0, 1)):
+                        # decided on the device: the reduced-pass variant while the gate word is clear, else the fallback
+                        gate, fallback = gated if isinstance(gated, tuple) else (peak_flag, 0)
+                        for fl, run_if_set in ((impl_flags, 0), (fallback, 1)):
                             k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
-                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | fl, peak_flag, run_if_set)
+                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | fl, gate, run_if_set)
                         self.launches += 1
                     else:
                         k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
                                _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags)
                     if self.profile_gemm:
                         e1.record()
-                        self.gemm_events.append((e0, e1, n, passes, gated, self.event_tag))
+                        self.gemm_events.append((e0, e1, n, passes, (2 if isinstance(gated, tuple) else 1) if gated else 0, self.event_tag))
                     self.launches += 1
                     self.gemm_launches += 1
                 self.gemm_rows += rows
@@ -559,10 +574,16 @@ class Engine(object):
                             lambda: k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])),
                                            _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(bd, int(rec[9])),
                                            _p(U), _p(D), ld,
-                                           V, _p(A_hi), _p(A_lo), max_in, range_log2, peak_flag, self.peak_mult / V))
+                                           V, _p(A_hi), _p(A_lo), max_in, range_log2, peak_flag, self.peak_mult / V,
+                                           _p(spk_cnt), _p(spk_ent), _p(spk_rows), n_msg))
                 self.launches += 1
             if two_pass:
                 gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
+                for i in range(int(rec[6])):                      # restore what the dropped lo half of the spikes contributed
+                    t, a0, d0, rows = (int(x) for x in blob[int(rec[7]) + GEMM_WORDS * i: int(rec[7]) + GEMM_WORDS * (i + 1)])
+                    k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows), a0, rows,
+                           _p(self.plane(t ^ 1, 0)), _p(self.plane(t ^ 1, 1)), V, ld, _p(D), d0, ld, alpha)
+                    self.launches += 1
             else:
                 gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
@@ -575,8 +596,14 @@ class Engine(object):
             v2f_rows = (A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)
         if want_grad and n_pair:
             one_pass = grad_hi_only and self.grad_one_pass_ok and self.grad_a_terms == 1 and self.grad_b_terms == 1
-            gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
-                       (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0)
+            if one_pass and two_pass:
+                # one pass only while no spike was seen (device gate on the SPIKE word): a peaked belief does not average the
+                # fp16 rounding of the T o PMI plane away
+                gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), False, GEMM_A_HI_ONLY | GEMM_B_HI_ONLY,
+                           gated=(_p(self._flags, FLAG_SPIKE), GEMM_A_HI_ONLY))
+            else:
+                gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
+                           (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0)
             if approx_beliefs:                                    # the c rows follow the r rows in the A buffer
                 c0 = int(blob[int(blob[H_PAIR_C])])
                 k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, c0, n_pair, topk)

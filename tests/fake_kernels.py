@@ -163,7 +163,7 @@ class FakeKernels(object):
         _arr(p, np.int32, n)[:] = 0
 
     def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2,
-                           peak_flag=None, peak_prob=1.0):
+                           spike_words=None, spike_prob=1.0, spike_cnt=None, spike_entries=None, spike_rows=None, n_msg_rows=0):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         n_in = int(go[-1])
         ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
@@ -194,11 +194,27 @@ class FakeKernels(object):
                 s = p.sum()
                 x = p * (A_SCALE / s) if (s > 0 and np.isfinite(s)) else np.full(V, A_SCALE / V)
                 hi, lo = _split(x)
-                if peak_flag is not None and peak_flag.value:
-                    pf = _arr(peak_flag, np.int32, 3)
-                    if x.max() > peak_prob * A_SCALE:
-                        pf[0] = 1
+                if spike_words is not None and spike_words.value:
+                    pf = _arr(spike_words, np.int32, 5)
                     pf[2:3].view(np.float32)[0] = max(float(pf[2:3].view(np.float32)[0]), float(np.float32(x.max())))
+                    x32 = x.astype(np.float32)
+                    for col in np.nonzero(x32 > np.float32(spike_prob * A_SCALE))[0]:
+                        pf[3] = 1
+                        lo_exact = np.float32(x32[col] - np.float32(hi[col]))
+                        cnt = _arr(spike_cnt, np.int32, max(n_msg_rows, 1))
+                        ent = _arr(spike_entries, np.int32, max(n_msg_rows, 1) * 8).reshape(-1, 4, 2)
+                        rws = _arr(spike_rows, np.int32, max(n_msg_rows, 1))
+                        for tdest in de[do[i]:do[i + 1]]:
+                            if tdest >= n_msg_rows:
+                                continue
+                            slot = int(cnt[tdest]); cnt[tdest] += 1
+                            if slot == 0:
+                                rws[pf[4]] = tdest; pf[4] += 1
+                            if slot < 4:
+                                ent[tdest, slot, 0] = col
+                                ent[tdest, slot, 1:2].view(np.float32)[0] = lo_exact
+                            else:
+                                pf[0] = 1
                 for tdest in de[do[i]:do[i + 1]]:
                     H[tdest, :V], L[tdest, :V] = hi, lo
 
@@ -229,6 +245,27 @@ class FakeKernels(object):
         if gate is not None and gate.value and (int(_arr(gate, np.int32, 1)[0]) != 0) != (run_if_set != 0):
             return
         self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl)
+
+    def mlbp_spike_correct(self, words, cnt, entries, rows, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha):
+        w = _arr(words, np.int32, 5)
+        if w[0] != 0:
+            return
+        rws = _arr(rows, np.int32, max(int(w[4]), 1))[:int(w[4])]
+        sel = [int(r) for r in rws if a0 <= r < a0 + n_rows]
+        if not sel:
+            return
+        top = max(sel) + 1
+        c = _arr(cnt, np.int32, top)
+        ent = _arr(entries, np.int32, top * 8).reshape(-1, 4, 2)
+        Bh = _arr(Bt_hi, np.float16, V * ldv).reshape(V, ldv)
+        Bl = _arr(Bt_lo, np.float16, V * ldv).reshape(V, ldv)
+        Dm = _arr(D, np.float32, (d_row0 + n_rows) * ldd).reshape(-1, ldd)
+        for r in sel:
+            items = sorted((int(ent[r, s, 0]), float(ent[r, s, 1:2].view(np.float32)[0])) for s in range(min(int(c[r]), 4)))
+            acc = np.zeros(V, dtype=np.float32)
+            for col, lo in items:
+                acc = (acc + np.float32(lo) * (Bh[col, :V].astype(np.float32) + Bl[col, :V].astype(np.float32))).astype(np.float32)
+            Dm[d_row0 + r - a0, :V] += np.float32(alpha) * acc
 
     def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs, range_log2,
                        max_in=0, tau=0.0, tau_label=0.0, aux=None, cnts=None, flags=None, flagged=None, n_flagged=None):
@@ -352,8 +389,9 @@ class FakeKernels(object):
             r = _arr(rank, np.int32, n_vars)
             o[10] += (r == 0).sum(); o[11] += (r < 26).sum(); o[12] += (r < 50).sum(); o[13] += n_vars
         o[14] += n_sent
-        if peak_flag is not None and peak_flag.value and _arr(peak_flag, np.int32, 1)[0]:
-            o[15] = 1.0
+        if peak_flag is not None and peak_flag.value:
+            w = _arr(peak_flag, np.int32, 4)
+            o[15] = max(o[15], (1.0 if w[0] else 0.0) + (2.0 if w[3] else 0.0))
 
     def mlbp_gradient_reduce(self, n_sent, sent_var_off, sent_fac_off, g_unary, pair_stats, v0, v1, var_label, gap1, pmi, w1, ldf,
                              logp_var, grad, logp_sent):

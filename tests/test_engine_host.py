@@ -203,3 +203,34 @@ def test_peaked_message_switches_back_to_three_passes_on_device():
     # sweep 1's first GEMM level is constant-folded, so the first var->factor launch precedes every GEMM: all rows are three-pass
     np.testing.assert_array_equal(res[0][1][:, :96], res[1][1][:, :96])
     np.testing.assert_array_equal(res[0][3], res[1][3])
+
+
+def test_spike_compensation_restores_what_two_pass_rows_drop():
+    """history / correct features with large weights put ~half of a belief on one word.  A two-pass message row rounds that one
+    element to fp16 and the error does not average away; the var->factor kernel records such spikes and mlbp_spike_correct
+    adds alpha * lo * T[:, column] back after the GEMM.  With the compensation the beliefs are an order of magnitude closer to
+    the float64 oracle than raw two-pass rows, and the gradient rows keep the table's lo half (SPIKE word)."""
+    model = synth.make_model(160, 24, seed=11)
+    sents = [synth.sentence_to_arrays(synth.make_sentence(model, 'ppppg', seed=70 + i, n_history=4, p_correct=0.8)) for i in range(8)]
+    roots_pos = synth.draw_roots(sents, 3, seed=3)
+    te, td = [0.5, 0.3, -0.1], [0.6, -0.4, 5.0, 4.0, 2.0, -0.1]
+    tb = orc.Tables(model, te, td)
+    ref = np.concatenate([orc.run_fast(tb, s, r, 3)['marginals'] for s, r in zip(sents, roots_pos)])
+    assert ref.max() > 0.3                                      # the case is peaked
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(roots_pos)
+    err, st = {}, {}
+    for name, kw in (('three', dict(msg_passes=3)), ('raw', dict(msg_passes=2, peak_mult=1e9)), ('comp', dict(msg_passes=2, peak_mult=16.0))):
+        eng = Engine(model, kernels=FakeKernels(), **kw)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_beliefs=True)
+        st[name] = eng.pass_stats()
+        rel = np.abs(r.beliefs.numpy()[:, :160] / ref - 1.0)
+        err[name] = float(rel[ref > 1e-4].max())
+    print('max relative belief error: three-pass %.2e, two-pass raw %.2e, two-pass + spike compensation %.2e' % (
+        err['three'], err['raw'], err['comp']), st['comp'])
+    assert st['comp']['spike_flag'] == 1 and st['comp']['peak_flag'] == 0 and st['comp']['spiky_rows_last_batch'] > 0
+    assert st['raw']['spike_flag'] == 0
+    assert 'mlbp_spike_correct' in eng.k.calls
+    assert err['comp'] < 0.5 * err['raw']        # (V = 160: the un-spiky remainder of a message still carries 1/sqrt(V) rounding noise)
+    assert err['comp'] < 5e-5
