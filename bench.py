@@ -505,8 +505,8 @@ def ours(a):
         code = int(w.peaked[tag]) if world == 1 else (3 if w.peaked[tag] else 0)   # bit 0 PEAK, bit 1 SPIKE (summed over ranks: any)
         if gated == 1 and (code & 1):
             p = 3                                          # a message with too many spikes switched the message rows to three passes
-        if gated == 2 and (code & 2):
-            p = 2                                          # a spike was seen: the gradient rows kept the lo half of the table
+        if gated == 2 and (code & 1):
+            p = 2                                          # ... and the one-pass gradient rows to two
         t = x.elapsed_time(y)
         d = by_passes.setdefault(p, {'launches': 0, 'rows': 0, 'ms': 0.0})
         d['launches'] += 1; d['rows'] += r; d['ms'] += t
@@ -590,7 +590,7 @@ def ours(a):
             'host': {'plan_compile_s_per_step': plan_s_per_step, 'plan_threads': int(os.environ.get('MLBP_PLAN_THREADS', '0'))},
             'message_rows': {'two_pass_enabled': pass_stats['msg_two_pass'], 'ranks_switched_to_three_passes_per_step': peaked_value,
                              'ranks_switched_all_steps_incl_warmup_e2e_profiling': w.all_peaked, 'max_message_prob_last_step': pass_stats['max_message_prob'],
-                             'flag_code': 'bit 0 = a row had more spikes than slots (message rows: three passes), bit 1 = a spike was seen (gradient rows: two passes)',
+                             'flag_code': 'bit 0 = a row had more spikes than slots (message rows ran three passes, gradient rows two), bit 1 = a spike was seen and compensated',
                              'spiky_rows_last_batch': pass_stats['spiky_rows_last_batch'], 'theta_after_each_step': w.thetas,
                              'rescore': {k: pass_stats[k] for k in ('rescored', 'skipped_mass_tie', 'skipped_degenerate', 'top1_changed', 'rank_changed')},
                              'rescore_note': 'counters of the LAST step of the profiling pass (reset per theta)'},

@@ -128,19 +128,19 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   Spike tracking (spike_words != NULL, else the other spike_* arguments are ignored).  A two-pass message row
  *   (MLBP_GEMM_A_HI_ONLY) drops the lo half of every message element; for the bulk of a message that rounding averages away
  *   in the contraction, for an element that carries more than spike_prob of the mass (a history feature's word, say) it
- *   does not.  For every such element written to a MESSAGE row (A row < n_msg_rows) the kernel records
+ *   does not.  For every such element written to an A row < n_spike_rows the kernel records
  *   (column, x - fp16(x)) in spike_entries[row][MLBP_SPIKE_SLOTS] (int32 pairs: column, float bits), counts them in
  *   spike_cnt[row] (zeroed by the caller per batch) and lists rows with spikes in spike_rows; mlbp_spike_correct restores
- *   the dropped contribution exactly.  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
+ *   the dropped contribution of message rows exactly, mlbp_pair_expectations that of the gradient stage's spike cells.  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
  *     [0] PEAK   set when a row has more spikes than slots: mlbp_factor_to_var_gemm_gated then keeps all three passes   (per theta)
  *     [2] the largest element seen so far, bits of the float 2^14 * probability (atomic max; diagnostics)               (per theta)
- *     [3] SPIKE  set when any spike was seen: the gradient rows then keep the lo half of the table planes               (per theta)
+ *     [3] SPIKE  set when any spike was seen (diagnostics)                                                               (per theta)
  *     [4] number of rows in spike_rows                                                                                  (per batch) */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                        const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
                        void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
-                       int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_msg_rows, void *stream);
+                       int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows, void *stream);
 /* K4b. Spike compensation of a two-pass message GEMM block (rows [a_row0, a_row0 + n_rows) of A -> D rows d_row0 ..):
  *   D[r, n] += alpha * sum over the recorded spikes s of row r of  lo_s * B[n, col_s],  with B[n, col] read as row `col` of
  *   the TRANSPOSED table's plane pair Bt_hi / Bt_lo (MLBP_TABLE_T <-> TT, T1 <-> T1T).  Returns at once (on the device) when
@@ -213,11 +213,17 @@ int mlbp_rescore_candidates(int n_vars, const int32_t *flagged, const int32_t *n
 /* K6a. pairwise factor beliefs contracted with the features (LBP.py:544-569 + :610) in closed form:
  *   stats[f] = { z.u0, c.u1, c.u2 } with c = (A_hi + A_lo)[c_row[f]], z = (A_hi + A_lo)[z_row[f]],
  *   u* = D[u*_row[f]] (u2_row < 0 -> 0).  z_row == c_row with u0 = T r, or z_row = the r row with u0 = T'c
- *   (the plan reuses the D row of the factor's last message update when it read the final message).        */
+ *   (the plan reuses the D row of the factor's last message update when it read the final message).
+ *   Spike cells (spike_words != NULL, else the seven arguments after stats are ignored): when the u rows come from ONE-pass
+ *   gradient GEMMs (alpha * r_hi . B_hi) the lo half of the table planes is missing.  Its rounding averages away over the
+ *   cells a belief spreads over, except where both messages have a spike; for those cells (spike lists of rows c_row[f]
+ *   and r_row[f] from mlbp_var_to_factor) the kernel adds  alpha * c[a] * r_hi[b] * B_lo[a, b]  to the three sums, B = T / G /
+ *   G1w planes of the factor's gap class (pair_gap1).  Skipped on the device when spike_words[0] (PEAK) is set.        */
 int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *z_row, const int32_t *u0_row,
-                           const int32_t *u1_row,
-const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D,
-                           int ldv, int V, double *stats, void *stream);
+                           const int32_t *u1_row, const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D,
+                           int ldv, int V, double *stats, const int32_t *r_row, const int32_t *pair_gap1,
+                           const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
+                           const void *planes, int64_t plane_stride, float alpha, void *stream);
 /* K6b. FactorGraph.get_unregularized_gradeint (LBP.py:301-320) as a segmented reduction:
  *   grad[s][9] = sum_{v in sentence s} g_unary[v] + sum_{pairwise f in s} (phi[l0,l1,:] - E_f[phi]),
  *   (l0, l1) = var_label[pair_v0[f]], var_label[pair_v1[f]] (the observed one-hot of LBP.py:584-589);

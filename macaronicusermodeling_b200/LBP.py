@@ -147,46 +147,50 @@ class FactorGraph():
         self._res = None
 
     def get_message_schedule(self, root):
-        """LBP.py:155-172 (host logic; the engine's C++ compiler follows the same walk)"""
+        """The (child, parent) edge list one sweep walks (reference: LBP.py:155-172).  Breadth-first from `root` with the
+        reference's visiting rule: a node only counts as visited once it has been taken OFF the queue, so in a loopy graph a
+        node is queued -- and scheduled -- once for every neighbour that reaches it before its own turn comes.  Neighbours are
+        taken in attach order (facset / varset).  csrc/plan.cpp `schedule` is the batched twin of this walk."""
+        from collections import deque
         if __debug__: assert isinstance(root, VariableNode)
-        _schedule = []
-        _seen = []
-        _stack = [root]
-        while len(_stack) > 0:
-            _n = _stack.pop(0)
-            if str(_n) not in _seen:
-                _seen.append(str(_n))
-                if isinstance(_n, VariableNode):
-                    nb = [_fn for _fn in _n.facset if str(_fn) not in _seen]
-                elif isinstance(_n, FactorNode):
-                    nb = [_vn for _vn in _n.varset if str(_vn) not in _seen]
-                else:
-                    raise NotImplementedError("Only handles 2 kinds of nodes, variables and factors")
-                _schedule.extend((m, _n) for m in nb)
-                _stack.extend(nb)
-        return _schedule
+        done, edges, queue = set(), [], deque([root])
+        while queue:
+            node = queue.popleft()
+            if str(node) in done:
+                continue
+            done.add(str(node))
+            if isinstance(node, VariableNode):
+                around = node.facset
+            elif isinstance(node, FactorNode):
+                around = node.varset
+            else:
+                raise NotImplementedError("Only handles 2 kinds of nodes, variables and factors")
+            fresh = [nb for nb in around if str(nb) not in done]
+            edges += [(nb, node) for nb in fresh]
+            queue.extend(fresh)
+        return edges
 
     def _draw_root(self):
         return random.sample(sorted(self.variables.keys()), 1)[0]
 
     def has_loops(self, _root_id=None):
-        """LBP.py:174-190"""
-        _seen = []
-        _rand_key = self._draw_root() if _root_id is None else _root_id
-        self._last_loop_root = _rand_key
-        _root = self.variables[_rand_key]
-        _stack = [(_root, None)]
-        while len(_stack) > 0:
-            _n, _nparent = _stack.pop()
-            if str(_n) in _seen:
+        """True when a depth-first walk from one randomly drawn variable (the reference's single RNG draw, LBP.py:174-190)
+        meets a node twice without walking an edge straight back.  `_root_id` (not in the reference) pins the draw."""
+        start = self._draw_root() if _root_id is None else _root_id
+        self._last_loop_root = start
+        reached, todo = set(), [(self.variables[start], None)]
+        while todo:
+            node, came_from = todo.pop()
+            if str(node) in reached:
                 return True
-            _seen.append(str(_n))
-            if isinstance(_n, VariableNode):
-                [_stack.append((_fn, _n)) for _fn in _n.facset if _fn is not _nparent]
-            elif isinstance(_n, FactorNode):
-                [_stack.append((_vn, _n)) for _vn in _n.varset if _vn is not _nparent]
+            reached.add(str(node))
+            if isinstance(node, VariableNode):
+                around = node.facset
+            elif isinstance(node, FactorNode):
+                around = node.varset
             else:
                 raise NotImplementedError("Only handles 2 kinds of nodes, variables and factors")
+            todo.extend((nb, node) for nb in around if nb is not came_from)
         return False
 
     def initialize(self, root=None):
@@ -418,52 +422,52 @@ class FactorGraph():
             label_guesses.append(s + ' ' + sp + ' ' + g_str)
         return label_guesses
 
+    def _positioned(self):
+        """factors that carry a sentence position, by position (ties keep factor-id order: the lines they produce are equal)"""
+        return sorted((f for f in self.factors if f.position is not None), key=lambda f: f.position)
+
     def get_precision_counts(self):
-        """LBP.py:80-106"""
-        p_at_0 = p_at_25 = p_at_50 = totals = 0
+        """(P@0, P@25, P@50, n) over the en_de factors' variables: where the supervised label sits in the 50 most probable
+        words -- first / among the first 26 / listed at all (reference: LBP.py:80-106)."""
+        hits = [0, 0, 0]
+        n = 0
         for f in self.factors:
-            if f.factor_type == 'en_de':
-                sl, slp, prediction = f.varset[0].get_max_vocab(50)
-                totals += 1
-                for rank, (p_label, p_prob) in enumerate(prediction):
-                    if sl == p_label:
-                        if rank == 0:
-                            p_at_0 += 1; p_at_25 += 1; p_at_50 += 1
-                        elif rank < 26:
-                            p_at_25 += 1; p_at_50 += 1
-                        elif rank < 51:
-                            p_at_50 += 1
-        return p_at_0, p_at_25, p_at_50, totals
+            if f.factor_type != 'en_de':
+                continue
+            n += 1
+            label, _, top = f.varset[0].get_max_vocab(50)
+            words = [w for w, _ in top]
+            if label in words:
+                place = words.index(label)
+                for i, bound in enumerate((1, 26, 51)):
+                    hits[i] += 1 if place < bound else 0
+        return hits[0], hits[1], hits[2], n
 
     def to_string(self):
-        """LBP.py:109-123"""
-        position_factors = sorted([(f.position, f) for f in self.factors if f.position is not None], key=lambda t: t[0])
-        fg_dct = {}
-        for p, f in position_factors:
+        """One prediction line per sentence position (reference: LBP.py:109-123): for a predicted token
+        `<de word> <label> <log p(label)> <word log p> x 50`, for a given token ` <word> `."""
+        lines = {}
+        for f in self._positioned():
             if f.factor_type == 'en_de':
-                de_label = f.word_label
-                sl, slp, pred = f.varset[0].get_max_vocab(50)
-                pred = ' '.join([p1 + ' ' + p2 for p1, p2 in pred])
-                fg_dct[p] = ' '.join([de_label, sl, slp, pred])
-            if f.factor_type == 'en_en':
-                guess_label = f.word_label
-                fg_dct[p] = ' '.join(['', guess_label, ''])
-        return [fg_dct[k] for k in sorted(fg_dct)]
+                label, label_logp, top = f.varset[0].get_max_vocab(50)
+                lines[f.position] = ' '.join([f.word_label, label, label_logp] + ['%s %s' % wp for wp in top])
+            elif f.factor_type == 'en_en':
+                lines[f.position] = ' %s ' % f.word_label
+        return [lines[pos] for pos in sorted(lines)]
 
     def to_dist(self):
-        """LBP.py:125-143"""
-        factor_dist = []
-        position_factors = sorted([(f.position, f) for f in self.factors if f.position is not None], key=lambda t: t[0])
-        for p, f in position_factors:
-            if f.factor_type == 'en_de':
-                v = f.varset[0]
-                truth = v.truth_label if v.truth_label is not None else 'None'
-                guess = v.supervised_label if v.supervised_label is not None else 'None'
-                m = v.get_marginal()
-                with np.errstate(divide='ignore'):
-                    i = ' '.join(['%0.6f' % i for i in np.log(m.m)])
-                factor_dist.append(' ||| '.join([truth, guess, i]))
-        return '\n'.join(factor_dist)
+        """One `.dist` line per predicted token (reference: LBP.py:125-143): `truth ||| guess ||| log-marginal x V`, 6 decimals."""
+        out = []
+        for f in self._positioned():
+            if f.factor_type != 'en_de':
+                continue
+            v = f.varset[0]
+            with np.errstate(divide='ignore'):
+                logs = np.log(v.get_marginal().m).reshape(-1)
+            out.append(' ||| '.join(['None' if v.truth_label is None else v.truth_label,
+                                     'None' if v.supervised_label is None else v.supervised_label,
+                                     ' '.join('%0.6f' % x for x in logs)]))
+        return '\n'.join(out)
 
     def hw_inf(self, iterations):
         raise BaseException("This method assumes self.variables is a list.. depricated...")
@@ -577,16 +581,15 @@ class VariableNode():
         return Message(res['beliefs'][res['vids'].index(self.id)].reshape(-1, 1))
 
     def get_max_vocab(self, top):
-        """LBP.py:402-411"""
-        m = self.get_marginal()
-        a = np.reshape(m.m, (np.size(m.m, )))
-        max_idx = np.argpartition(a, -top)[-top:]
-        max_idx = max_idx[np.argsort(a[max_idx])]
+        """(label, '%0.4f' % log p(label), [(word, '%0.4f' % log p)] for the `top` most probable words, best first)
+        (reference: LBP.py:402-411; the same argpartition + argsort calls, so exact ties order alike)"""
+        belief = self.get_marginal().m.reshape(-1)
+        best = np.argpartition(belief, -top)[-top:]
+        best = best[np.argsort(belief[best])][::-1]
         with np.errstate(divide='ignore'):
-            al = np.log(a)
-        max_vocab = [(self.domain[i], '%0.4f' % al[i]) for i in max_idx]
-        max_vocab.reverse()
-        return self.supervised_label, '%0.4f' % al[self.supervised_label_index], max_vocab
+            logs = np.log(belief)
+        return (self.supervised_label, '%0.4f' % logs[self.supervised_label_index],
+                [(self.domain[i], '%0.4f' % logs[i]) for i in best])
 
 
 class FactorNode():
@@ -635,41 +638,33 @@ class FactorNode():
         FactorNode._seq[0] += 1
         self._attach_seq = FactorNode._seq[0]
 
-    def get_pot(self):
-        """LBP.py:456-467"""
+    def _table_kind(self, what):
+        """which of the graph's three tables this factor uses: en_de, or en_en by gap (== 1: the *_w1 table, > 1: the plain
+        one; reference: LBP.py:456-480)"""
+        if self.factor_type == 'en_de':
+            return 'en_de'
         if self.factor_type == 'en_en':
             if self.gap > 1:
-                return self.graph.pot_en_en
-            elif self.gap == 1:
-                return self.graph.pot_en_en_w1
-            else:
-                raise BaseException("only 2 kinds of distances are supported ...")
-        elif self.factor_type == 'en_de':
-            return self.graph.pot_en_de
-        else:
-            raise BaseException("only two kinds of potentials are supported...")
+                return 'en_en'
+            if self.gap == 1:
+                return 'en_en_w1'
+            raise BaseException("only 2 kinds of distances are supported ..." if what == 'pot' else
+                                "only 2 distances supported at the moment")
+        raise BaseException("only two kinds of potentials are supported..." if what == 'pot' else
+                            "only 2 feature value types are supported right now..")
+
+    def get_pot(self):
+        return getattr(self.graph, 'pot_' + self._table_kind('pot'))
 
     def get_phi(self):
-        """LBP.py:469-480"""
-        if self.factor_type == 'en_en':
-            if self.gap > 1:
-                return self.graph.phi_en_en
-            elif self.gap == 1:
-                return self.graph.phi_en_en_w1
-            else:
-                raise BaseException("only 2 distances supported at the moment")
-        elif self.factor_type == 'en_de':
-            return self.graph.phi_en_de
-        else:
-            raise BaseException("only 2 feature value types are supported right now..")
+        return getattr(self.graph, 'phi_' + self._table_kind('phi'))
 
     def get_shape(self):
-        if len(self.varset) == 1:
-            return len(self.varset[0].domain), self.observed_domain_size
-        elif len(self.varset) == 2:
-            return len(self.varset[0].domain), len(self.varset[1].domain)
-        else:
+        """(rows, columns) of the potential table: a unary factor's second axis is its observed domain (LBP.py:482-488)"""
+        if len(self.varset) not in (1, 2):
             raise BaseException("only unary or binary factors are supported...")
+        rows = len(self.varset[0].domain)
+        return rows, (self.observed_domain_size if len(self.varset) == 1 else len(self.varset[1].domain))
 
     def update_message_to(self, var):
         """LBP.py:490-526: unary -> normalize(copy(table)); pairwise -> T.m or m'.T through au.dense_dot (device), or

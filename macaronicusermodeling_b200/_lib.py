@@ -26,7 +26,7 @@ _SIGNATURES = {
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppf' + 'iff' + 'ppppp' + 'p',
     'mlbp_rescore_candidates': 'ippp' + 'pppp' + 'ppii' + 'pppl' + 'pii' + 'ppff' + 'f' + 'ppp' + 'p',
     'mlbp_zero_words': 'pip',
-    'mlbp_pair_expectations': 'ippppp' + 'pppii' + 'pp',
+    'mlbp_pair_expectations': 'ippppp' + 'pppii' + 'p' + 'ppppp' + 'plf' + 'p',
     'mlbp_gradient_reduce': 'ippppppp' + 'p' + 'ppi' + 'pppp',
     'mlbp_batch_reduce': 'ippipppp',
     'mlbp_const_rows': 'piipp',

@@ -16,7 +16,10 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
                          const int32_t *__restrict__ u0_row,
                          const int32_t *__restrict__ u1_row, const int32_t *__restrict__ u2_row,
                          const __half *__restrict__ A_hi, const __half *__restrict__ A_lo, const float *__restrict__ D,
-                         int ldv, int V, double *__restrict__ stats) {
+                         int ldv, int V, double *__restrict__ stats, const int32_t *__restrict__ r_row,
+                         const int32_t *__restrict__ gap1, const int32_t *__restrict__ spike_words,
+                         const int32_t *__restrict__ spike_cnt, const int2 *__restrict__ spike_entries,
+                         const __half *__restrict__ planes, int64_t ps, float alpha) {
     __shared__ double red[32];
     const int f = blockIdx.x;
     const __half *ch = A_hi + (size_t)c_row[f] * ldv, *cl = A_lo + (size_t)c_row[f] * ldv;
@@ -36,7 +39,35 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
         if (u2) n2f = fmaf(c, __ldg(u2 + e), n2f);
     }
     double z = block_sum((double)zf, red), n1 = block_sum((double)n1f, red), n2 = block_sum((double)n2f, red);
-    if (threadIdx.x == 0) { stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2; }
+    if (threadIdx.x == 0) {
+        // One-pass gradient rows (u = alpha * r_hi . B_hi) drop the lo half of the table planes.  Its rounding averages away
+        // over the cells a belief spreads over -- except where BOTH messages have a spike: those few cells are restored here,
+        //   sum over spikes a* of c, b* of r:  alpha * c[a*] * r_hi[b*] * B_lo[a*, b*]
+        // (spike lists: mlbp_var_to_factor; skipped when a row had more spikes than slots -- then the rows ran two passes).
+        if (spike_words && spike_words[0] == 0) {
+            const int rr = r_row[f], cr = c_row[f];
+            const int nc = min(spike_cnt[cr], MLBP_SPIKE_SLOTS), nr = min(spike_cnt[rr], MLBP_SPIKE_SLOTS);
+            if (nc > 0 && nr > 0) {
+                const int g1 = gap1[f];
+                const __half *t_lo = planes + (size_t)(2 * (g1 ? MLBP_TABLE_T1 : MLBP_TABLE_T) + 1) * ps;
+                const __half *g_lo = planes + (size_t)(2 * (g1 ? MLBP_TABLE_G1 : MLBP_TABLE_G) + 1) * ps;
+                const __half *w_lo = planes + (size_t)(2 * MLBP_TABLE_G1W + 1) * ps;
+                for (int i = 0; i < nc; ++i) {
+                    const int a = spike_entries[(size_t)cr * MLBP_SPIKE_SLOTS + i].x;
+                    const double ca = (double)(__half2float(ch[a]) + __half2float(cl[a]));
+                    for (int j = 0; j < nr; ++j) {
+                        const int b = spike_entries[(size_t)rr * MLBP_SPIKE_SLOTS + j].x;
+                        const double w = (double)alpha * ca * (double)__half2float(A_hi[(size_t)rr * ldv + b]);
+                        const size_t cell = (size_t)a * ldv + b;
+                        if (zc) z += w * (double)__half2float(t_lo[cell]);     // Z = c . (T r) from its own GEMM row
+                        n1 += w * (double)__half2float(g_lo[cell]);
+                        if (u2) n2 += w * (double)__half2float(w_lo[cell]);
+                    }
+                }
+            }
+        }
+        stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2;
+    }
 }
 
 // one warp per sentence; deterministic (no atomics).  The observed feature values phi[l0, l1, :] are gathered here from the
@@ -147,13 +178,19 @@ using namespace mlbp;
 extern "C" int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *z_row,
                                       const int32_t *u0_row, const int32_t *u1_row, const int32_t *u2_row, const void *A_hi,
                                       const void *A_lo, const float *D, int ldv, int V, double *stats,
-                                      void *stream) {
+                                      const int32_t *r_row, const int32_t *pair_gap1, const int32_t *spike_words,
+                                      const int32_t *spike_cnt, const int32_t *spike_entries, const void *planes,
+                                      int64_t plane_stride, float alpha, void *stream) {
     if (n_factors == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_factors > 0 && c_row && z_row && u0_row && u1_row && u2_row && A_hi && A_lo && D && stats,
                    "pair_expectations: null pointer");
+    MLBP_CHECK_ARG(!spike_words || (r_row && pair_gap1 && spike_cnt && spike_entries && planes),
+                   "pair_expectations: the spike-cell correction needs r_row, pair_gap1, the spike lists and the table planes");
     pair_expectations_kernel<<<n_factors, 256, 0, as_stream(stream)>>>(c_row, z_row, u0_row, u1_row, u2_row,
                                                                        (const __half *)A_hi, (const __half *)A_lo, D,
-                                                                       ldv, V, stats);
+                                                                       ldv, V, stats, r_row, pair_gap1, spike_words, spike_cnt,
+                                                                       reinterpret_cast<const int2 *>(spike_entries),
+                                                                       (const __half *)planes, plane_stride, alpha);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

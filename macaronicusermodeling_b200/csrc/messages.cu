@@ -80,21 +80,43 @@ struct K3Spikes {
     int32_t *cnt;            // [n_msg_rows] spikes recorded per message A row (zeroed by the caller per run)
     int2 *entries;           // [n_msg_rows][MLBP_SPIKE_SLOTS] (column, float bits of lo)
     int32_t *rows;           // [n_msg_rows] rows with at least one spike, in order of discovery
-    int n_msg_rows;          // A rows >= n_msg_rows are gradient-stage copies: not corrected
+    int n_rows;              // rows of the A buffers covered by cnt / entries / rows
     float limit;             // 2^14 * probability above which an element is a spike
 };
+
+// A spike seen in the hot loop is only MARKED in shared memory (one shared-memory atomic); the marks of a group are flushed by
+// as many threads in parallel after the loop.  (All leave-one-out products of a variable peak at the same word, so the thread
+// that owns that column would otherwise pay ~18 global atomic round trips in a row: measured, K3 ran 35 % slower.)
+constexpr int K3_MAX_MARKS = 96;
+struct K3Mark { int d0, nd, col; float x; };
+
+__device__ __forceinline__ void k3_mark_spike(int *s_nmark, K3Mark *s_mark, int d0, int nd, int col, float x) {
+    const int k = atomicAdd(s_nmark, 1);
+    if (k < K3_MAX_MARKS) s_mark[k] = K3Mark{d0, nd, col, x};
+}
 
 __device__ __noinline__ void k3_record_spike(const K3Spikes sp, const int32_t *__restrict__ dest, int d0, int nd, int col, float x) {
     const float lo = x - __half2float(__float2half_rn(x));        // what a two-pass row drops (exact in fp32)
     sp.words[3] = 1;
     for (int t = 0; t < nd; ++t) {
         const int row = dest[d0 + t];
-        if (row >= sp.n_msg_rows) continue;
+        if (row >= sp.n_rows) continue;
         const int slot = atomicAdd(&sp.cnt[row], 1);
         if (slot == 0) sp.rows[atomicAdd(&sp.words[4], 1)] = row;
         if (slot < MLBP_SPIKE_SLOTS) sp.entries[(size_t)row * MLBP_SPIKE_SLOTS + slot] = make_int2(col, __float_as_int(lo));
         else sp.words[0] = 1;
     }
+}
+
+// after a group's hot loop (all threads; the caller has synchronised the block): flush the marks, one thread per mark
+__device__ __forceinline__ void k3_flush_marks(const K3Spikes &sp, const int32_t *__restrict__ dest, int *s_nmark, K3Mark *s_mark) {
+    const int n = *s_nmark;                                        // block-uniform
+    if (n == 0) return;
+    if (n > K3_MAX_MARKS) sp.words[0] = 1;                         // more spikes than marks: three passes from here on
+    for (int m = threadIdx.x; m < min(n, K3_MAX_MARKS); m += blockDim.x)
+        k3_record_spike(sp, dest, s_mark[m].d0, s_mark[m].nd, s_mark[m].col, s_mark[m].x);
+    __syncthreads();
+    if (threadIdx.x == 0) *s_nmark = 0;
 }
 
 // End of a K3 kernel: keep the largest element seen (one atomic per warp)
@@ -117,6 +139,9 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     __shared__ size_t s_first[NMAX];
     __shared__ double s_warp[K3_WARPS][NMAX];
     __shared__ float s_scale[NMAX];
+    __shared__ int s_nmark;
+    __shared__ K3Mark s_mark[K3_MAX_MARKS];
+    if (threadIdx.x == 0) s_nmark = 0;
     const int g = blockIdx.x;
     const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
     const float *urow = U + (size_t)grp_u[g] * ldv;
@@ -188,11 +213,15 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
                 const float sc = s_scale[j];
                 const float x = sc > 0.f ? (float)(pre[j] * suf * (T)sc) : uni;
                 mx = fmaxf(mx, x);
-                if (sp.words && x > sp.limit) k3_record_spike(sp, dest, s_d0[j], nd, e, x);      // rare
+                if (sp.words && x > sp.limit) k3_mark_spike(&s_nmark, s_mark, s_d0[j], nd, e, x);  // rare
                 k3_store(x, s_first[j] + e, nd, dest, s_d0[j], ldv, e, A_hi, A_lo);
             }
             suf *= (T)d[j];
         }
+    }
+    if (sp.words) {
+        __syncthreads();
+        k3_flush_marks(sp, dest, &s_nmark, s_mark);
     }
     k3_report_max(sp, mx);
 }
@@ -251,6 +280,9 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     __shared__ double s_gather[2][8][NIN];                     // [exchange parity][source rank][output]
     __shared__ __align__(8) unsigned long long s_gbar[2];
     __shared__ float s_scale[NIN];
+    __shared__ int s_nmark;
+    __shared__ K3Mark s_mark[K3_MAX_MARKS];
+    if (threadIdx.x == 0) s_nmark = 0;
     cg::cluster_group cl = cg::this_cluster();
     const unsigned C = cl.num_blocks(), q = cl.block_rank();
     const int n_clusters = gridDim.x / C;
@@ -449,8 +481,8 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                     const float xm = fmaxf(x.x, odd ? 0.f : x.y);
                     mx = fmaxf(mx, xm);
                     if (sp.words && xm > sp.limit) {                                  // rare: a spike (see K3Spikes)
-                        if (x.x > sp.limit) k3_record_spike(sp, dest, s_d0[b][j], s_nd[b][j], col0 + 2 * e2, x.x);
-                        if (!odd && x.y > sp.limit) k3_record_spike(sp, dest, s_d0[b][j], s_nd[b][j], col0 + 2 * e2 + 1, x.y);
+                        if (x.x > sp.limit) k3_mark_spike(&s_nmark, s_mark, s_d0[b][j], s_nd[b][j], col0 + 2 * e2, x.x);
+                        if (!odd && x.y > sp.limit) k3_mark_spike(&s_nmark, s_mark, s_d0[b][j], s_nd[b][j], col0 + 2 * e2 + 1, x.y);
                     }
                     const __half2 hi = __float22half2_rn(x);
                     const float2 back = __half22float2(hi);
@@ -500,6 +532,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
             k3_copy_extras<NIN>(s_nd[b], s_d0[b], s_first[b], dest, ldv, col0, ncol, A_hi, A_lo);
         }
         __syncthreads();                                           // shared memory is reused by the next group
+        if (sp.words) k3_flush_marks(sp, dest, &s_nmark, s_mark);
         K3_TICK(5);
     }
     k3_report_max(sp, mx);
@@ -710,7 +743,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
                                   const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                                   const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
                                   void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
-                                  int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_msg_rows,
+                                  int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows,
                                   void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && second_dest && U && D && A_hi && A_lo,
@@ -723,11 +756,11 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = as_stream(stream);
-    MLBP_CHECK_ARG(!spike_words || (spike_cnt && spike_entries && spike_rows && n_msg_rows >= 0 && spike_prob > 0.f),
+    MLBP_CHECK_ARG(!spike_words || (spike_cnt && spike_entries && spike_rows && n_spike_rows >= 0 && spike_prob > 0.f),
                    "var_to_factor: spike tracking needs cnt, entries, rows and a positive threshold");
     K3Spikes sp;
     sp.words = spike_words; sp.cnt = spike_cnt; sp.entries = reinterpret_cast<int2 *>(spike_entries); sp.rows = spike_rows;
-    sp.n_msg_rows = n_msg_rows;
+    sp.n_rows = n_spike_rows;
     sp.limit = ldexpf(spike_prob, MLBP_A_SCALE_LOG2);              // rows are stored as 2^14 * probability
     // The resident single-read kernel runs whenever the products fit fp32 and the cluster's slices fit shared memory;
     // MLBP_K3_IMPL=1 forces the streaming two-read kernel (used by scripts/k3_probe.py to time both).

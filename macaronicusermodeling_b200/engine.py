@@ -219,7 +219,7 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None, msg_passes=None, tau=5e-4, tau_label=2.5e-4, peak_mult=16.0):
+                 gemm_slice_pairs=None, msg_passes=None, tau=5e-4, tau_label=2.5e-4, peak_mult=16.0, one_pass_min_v=4096):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -247,6 +247,7 @@ class Engine(object):
         # of T o PMI away: tests/test_gpu_gates.py).
         # msg_passes: None = two passes where V >= 4096 (where the error above was measured), 2 = at any V, 3 = never.
         self.msg_passes = msg_passes
+        self.one_pass_min_v = int(one_pass_min_v)   # one-pass gradient rows from this vocabulary size on (tests lower it)
         self.tau, self.tau_label, self.peak_mult = float(tau), float(tau_label), float(peak_mult)
         self.msg_two_pass_ok = False
         self._flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device=self.device)
@@ -326,7 +327,7 @@ class Engine(object):
         # ... and ONE pass (plain fp16 x fp16, fp32 accumulate) when, in addition, the vocabulary is large: the fp16 rounding of
         # the table entries is random per entry and averages over the ~V^2 entries a belief spreads over (measured on a
         # sentence's gradient against the float64 oracle: <= 3.2e-6 relative over 24 sentences at V = 10 000, 3e-6 at V = 2 000)
-        self.grad_one_pass_ok = self.grad_hi_only_ok and self.V >= 4096
+        self.grad_one_pass_ok = self.grad_hi_only_ok and self.V >= self.one_pass_min_v
         self.msg_two_pass_ok = (zmax - zmin) <= 3.0 and (self.msg_passes == 2 or (self.msg_passes is None and self.V >= 4096)) \
             and (self.gemm_impl & 0xff) != 1                      # the SIMT cross-check kernel has no device-side gate
         self.k.call('mlbp_zero_words', _p(self._flags), FLAG_WORDS)   # the peak flag is sticky per theta
@@ -490,14 +491,18 @@ class Engine(object):
         a_cap = int(self._A.shape[1])
         td = self.theta_ed
         c = lambda name: _p(corpus.dev(name, dev))
-        peak_flag = _p(self._flags, FLAG_PEAK) if two_pass else None
-        n_msg = int(blob[H_MSG_ROWS])
+        # one-pass gradient rows (A_hi . B_hi) and two-pass message rows both rely on the spike lists of the var->factor kernel
+        one_pass = want_grad and grad_hi_only and self.grad_one_pass_ok and self.grad_a_terms == 1 and self.grad_b_terms == 1 \
+            and (self.gemm_impl & 0xff) != 1
+        track = two_pass or one_pass
+        peak_flag = _p(self._flags, FLAG_PEAK) if track else None
+        n_spk = max(int(sizes[PLAN_A_ROWS]), 1)
         spk_cnt = spk_ent = spk_rows = None
-        if two_pass:                                              # spike bookkeeping of this batch's message rows
-            spk_cnt = torch.empty(max(n_msg, 1), dtype=torch.int32, device=dev)
-            spk_ent = torch.empty((max(n_msg, 1), SPIKE_SLOTS, 2), dtype=torch.int32, device=dev)
-            spk_rows = torch.empty(max(n_msg, 1), dtype=torch.int32, device=dev)
-            k.call('mlbp_zero_words', _p(spk_cnt), max(n_msg, 1))
+        if track:                                                 # spike bookkeeping of this batch's A rows
+            spk_cnt = torch.empty(n_spk, dtype=torch.int32, device=dev)
+            spk_ent = torch.empty((n_spk, SPIKE_SLOTS, 2), dtype=torch.int32, device=dev)
+            spk_rows = torch.empty(n_spk, dtype=torch.int32, device=dev)
+            k.call('mlbp_zero_words', _p(spk_cnt), n_spk)
             k.call('mlbp_zero_words', _p(self._flags, FLAG_NSPIKY), 1)
 
         D[:D_CONST_ROWS].copy_(self.const_rows)                   # row 0: the constant-one row messages still uniform read
@@ -575,7 +580,7 @@ class Engine(object):
                                            _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(bd, int(rec[9])),
                                            _p(U), _p(D), ld,
                                            V, _p(A_hi), _p(A_lo), max_in, range_log2, peak_flag, self.peak_mult / V,
-                                           _p(spk_cnt), _p(spk_ent), _p(spk_rows), n_msg))
+                                           _p(spk_cnt), _p(spk_ent), _p(spk_rows), n_spk))
                 self.launches += 1
             if two_pass:
                 gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
@@ -595,12 +600,12 @@ class Engine(object):
             rows = torch.cat([bd[oc:oc + n_pair], bd[orr:orr + n_pair]]).long()
             v2f_rows = (A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)
         if want_grad and n_pair:
-            one_pass = grad_hi_only and self.grad_one_pass_ok and self.grad_a_terms == 1 and self.grad_b_terms == 1
-            if one_pass and two_pass:
-                # one pass only while no spike was seen (device gate on the SPIKE word): a peaked belief does not average the
-                # fp16 rounding of the T o PMI plane away
+            if one_pass:
+                # one pass (r_hi . B_hi); the cells where BOTH messages of a factor have a spike -- the only ones whose fp16
+                # table rounding does not average away -- are restored in mlbp_pair_expectations from the spike lists.  A row
+                # with more spikes than slots (PEAK word, device gate) switches these rows to two passes instead.
                 gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), False, GEMM_A_HI_ONLY | GEMM_B_HI_ONLY,
-                           gated=(_p(self._flags, FLAG_SPIKE), GEMM_A_HI_ONLY))
+                           gated=(peak_flag, GEMM_A_HI_ONLY))
             else:
                 gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
                            (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0)
@@ -616,7 +621,9 @@ class Engine(object):
                         lambda: k.call('mlbp_pair_expectations', n_pair, _p(bd, int(blob[H_PAIR_C])),
                                        _p(bd, int(blob[H_PAIR_Z])), _p(bd, int(blob[H_PAIR_U0])),
                                        _p(bd, int(blob[H_PAIR_U1])), _p(bd, int(blob[H_PAIR_U2])), _p(A_hi), _p(A_lo),
-                                       _p(D), ld, V, _p(pair_stats)))
+                                       _p(D), ld, V, _p(pair_stats), _p(bd, int(blob[H_PAIR_R])), _p(bd, int(blob[H_PAIR_GAP1])),
+                                       peak_flag if one_pass else None, _p(spk_cnt), _p(spk_ent),
+                                       _p(self.planes), V * ld, alpha))
             self.launches += 1
         logp_var = top1 = rank = beliefs = None
         if want_marg:

@@ -206,7 +206,7 @@ class FakeKernels(object):
                         rws = _arr(spike_rows, np.int32, max(n_msg_rows, 1))
                         for tdest in de[do[i]:do[i + 1]]:
                             if tdest >= n_msg_rows:
-                                continue
+                                continue                          # (n_msg_rows = rows covered by the spike arrays)
                             slot = int(cnt[tdest]); cnt[tdest] += 1
                             if slot == 0:
                                 rws[pf[4]] = tdest; pf[4] += 1
@@ -358,7 +358,9 @@ class FakeKernels(object):
                 ct[4] += int(rk[g] != new); rk[g] = new
             ct[0] += 1
 
-    def mlbp_pair_expectations(self, n_factors, c_row, z_row, u0_row, u1_row, u2_row, A_hi, A_lo, D, ldv, V, stats):
+    def mlbp_pair_expectations(self, n_factors, c_row, z_row, u0_row, u1_row, u2_row, A_hi, A_lo, D, ldv, V, stats,
+                               r_row=None, pair_gap1=None, spike_words=None, spike_cnt=None, spike_entries=None, planes=None,
+                               ps=0, alpha=1.0):
         cr, zr, r0, r1, r2 = (_arr(x, np.int32, n_factors) for x in (c_row, z_row, u0_row, u1_row, u2_row))
         H = _arr(A_hi, np.float16, (int(cr.max()) + 1) * ldv).reshape(-1, ldv)
         L = _arr(A_lo, np.float16, (int(cr.max()) + 1) * ldv).reshape(-1, ldv)
@@ -370,6 +372,27 @@ class FakeKernels(object):
             st[f, 0] = z @ Dm[r0[f], :V].astype(np.float64)
             st[f, 1] = c @ Dm[r1[f], :V].astype(np.float64)
             st[f, 2] = c @ Dm[r2[f], :V].astype(np.float64) if r2[f] >= 0 else 0.0
+        if spike_words is not None and spike_words.value and _arr(spike_words, np.int32, 1)[0] == 0:
+            rr, g1 = _arr(r_row, np.int32, n_factors), _arr(pair_gap1, np.int32, n_factors)
+            top = max(int(cr.max()), int(rr.max())) + 1
+            cnt = _arr(spike_cnt, np.int32, top)
+            ent = _arr(spike_entries, np.int32, top * 8).reshape(-1, 4, 2)
+            Hr = _arr(A_hi, np.float16, top * ldv).reshape(-1, ldv)
+            Lr = _arr(A_lo, np.float16, top * ldv).reshape(-1, ldv)
+            pl = _arr(planes, np.float16, 14 * ps)
+            lo_of = lambda table, a, b: float(pl[(2 * table + 1) * ps + a * ldv + b])
+            for f in range(n_factors):
+                for i in range(min(int(cnt[cr[f]]), 4)):
+                    a = int(ent[cr[f], i, 0])
+                    ca = float(Hr[cr[f], a]) + float(Lr[cr[f], a])
+                    for j in range(min(int(cnt[rr[f]]), 4)):
+                        b = int(ent[rr[f], j, 0])
+                        w = float(np.float32(alpha)) * ca * float(Hr[rr[f], b])
+                        if zr[f] == cr[f]:
+                            st[f, 0] += w * lo_of(2 if g1[f] else 0, a, b)
+                        st[f, 1] += w * lo_of(5 if g1[f] else 4, a, b)
+                        if r2[f] >= 0:
+                            st[f, 2] += w * lo_of(6, a, b)
 
     def mlbp_const_rows(self, colsums, V, ldv, rows):
         cs = _arr(colsums, np.float64, 7 * V).reshape(7, V)
