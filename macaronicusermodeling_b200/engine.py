@@ -586,8 +586,9 @@ class Engine(object):
                 gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
                 for i in range(int(rec[6])):                      # restore what the dropped lo half of the spikes contributed
                     t, a0, d0, rows = (int(x) for x in blob[int(rec[7]) + GEMM_WORDS * i: int(rec[7]) + GEMM_WORDS * (i + 1)])
-                    k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows), a0, rows,
-                           _p(self.plane(t ^ 1, 0)), _p(self.plane(t ^ 1, 1)), V, ld, _p(D), d0, ld, alpha)
+                    self._timed('K4b spike_correct', 0.0,            # bytes depend on the data (spikes found on the device)
+                                lambda: k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows), a0, rows,
+                                               _p(self.plane(t ^ 1, 0)), _p(self.plane(t ^ 1, 1)), V, ld, _p(D), d0, ld, alpha))
                     self.launches += 1
             else:
                 gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
@@ -651,12 +652,13 @@ class Engine(object):
                                        _p(self._flags, FLAG_NFLAGGED) if two_pass else None))
             self.launches += 1
             if two_pass:
-                k.call('mlbp_rescore_candidates', n_m, _p(flagged), _p(self._flags, FLAG_NFLAGGED), _p(vflags),
-                       _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])), _p(bd, int(blob[H_MARG_IN])),
-                       c('var_label'), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), _p(self.planes), V * ld,
-                       _p(bd, int(blob[H_MSG_BLK_OFF])), int(blob[H_MSG_BLK_N]), int(blob[H_MSG_ROWS]), _p(aux), _p(cnts),
-                       self.tau, self.tau_label, range_log2 + self.half_range_log2, _p(top1), _p(rank),
-                       _p(self._flags, FLAG_COUNTERS))
+                self._timed('K5b rescore', 0.0,                   # bytes depend on the data (variables flagged on the device)
+                            lambda: k.call('mlbp_rescore_candidates', n_m, _p(flagged), _p(self._flags, FLAG_NFLAGGED), _p(vflags),
+                                           _p(bd, int(blob[H_MARG_U])), _p(bd, int(blob[H_MARG_OFF])), _p(bd, int(blob[H_MARG_IN])),
+                                           c('var_label'), _p(U), _p(D), ld, V, _p(A_hi), _p(A_lo), _p(self.planes), V * ld,
+                                           _p(bd, int(blob[H_MSG_BLK_OFF])), int(blob[H_MSG_BLK_N]), int(blob[H_MSG_ROWS]),
+                                           _p(aux), _p(cnts), self.tau, self.tau_label, range_log2 + self.half_range_log2,
+                                           _p(top1), _p(rank), _p(self._flags, FLAG_COUNTERS)))
                 self.launches += 2
         grad = torch.empty((corpus.n_sent, 9), dtype=torch.float64, device=dev)
         logp = torch.empty(corpus.n_sent, dtype=torch.float64, device=dev)
