@@ -31,8 +31,8 @@ extern "C" {
 #define MLBP_ERR_UNSUPPORTED  3   /* e.g. device is not sm_100, more than 2 variables/factor  */
 #define MLBP_ERR_ALLOC        4
 
-#define MLBP_N_PLANES        14   /* fp16 operand planes written by mlbp_build_pairwise_tables */
-#define MLBP_N_TABLES         7   /* plane pairs (hi, lo): see MLBP_TABLE_*                    */
+#define MLBP_N_PLANES        20   /* fp16 operand planes written by mlbp_build_pairwise_tables */
+#define MLBP_N_TABLES        10   /* plane pairs (hi, lo): see MLBP_TABLE_*                    */
 #define MLBP_TABLE_T          0   /* B[n=a][k=b] = T[a,b]      : message to the dim-0 variable, gap > 1 (LBP.py:509) */
 #define MLBP_TABLE_TT         1   /* B[n=b][k=a] = T[a,b]      : message to the dim-1 variable, gap > 1 (LBP.py:518) */
 #define MLBP_TABLE_T1         2   /* same two with the gap == 1 table pot_en_en_w1 (LBP.py:460-461)                 */
@@ -40,6 +40,9 @@ extern "C" {
 #define MLBP_TABLE_G          4   /* T  o PMI     : pairwise belief expectation of the pmi feature (LBP.py:566-569, :610) */
 #define MLBP_TABLE_G1         5   /* T1 o PMI                                                                         */
 #define MLBP_TABLE_G1W        6   /* T1 o PMI_w1  : expectation of the pmi_w1 feature, gap == 1 factors only          */
+#define MLBP_TABLE_GT         7   /* transposes of G, G1, G1W: a COLUMN of a gradient table as a contiguous row, read by   */
+#define MLBP_TABLE_G1T        8   /* mlbp_spike_correct when it restores the lo part of a spike in a gradient-stage row   */
+#define MLBP_TABLE_G1WT       9
 
 #define MLBP_N_SUMS           7   /* per-theta sum vectors written by mlbp_build_pairwise_tables                */
 #define MLBP_D_CONST_ROWS     5   /* D rows 1..4 hold the constant messages of the 4 message tables (row 0 spare) */
@@ -69,13 +72,13 @@ int mlbp_dense_pointwise_multiply_f64(const double *m1, const double *m2, double
 /* K2.  pmi, pmi_w1: [V, ldf] fp32 row-major feature planes (train.py:589-595).
  *   T  = exp(th[0]*pmi + th[2]),  T1 = exp(th[0]*pmi + th[1]*pmi_w1 + th[2])            (train.py:218-219, :252-253)
  *   planes: MLBP_N_PLANES fp16 arrays [V, ldv], plane p at planes + p*plane_stride, in the order
- *           T.hi T.lo Tt.hi Tt.lo T1.hi T1.lo T1t.hi T1t.lo G.hi G.lo G1.hi G1.lo G1w.hi G1w.lo,
+ *           T.hi T.lo Tt.hi Tt.lo T1.hi T1.lo T1t.hi T1t.lo G.hi G.lo G1.hi G1.lo G1w.hi G1w.lo Gt.hi Gt.lo G1t.hi G1t.lo G1wt.hi G1wt.lo,
  *           every value multiplied by 2^scale_exp before the hi/lo split (hi + lo carries 22 bits).
  *   colsums: [MLBP_N_SUMS, V] float64, UNscaled: sum_e T[e,y], sum_e T1[e,y], sum_e G[e,y], sum_e G1[e,y], sum_e G1w[e,y]
  *           (the normaliser and feature expectations of the unary en_en factors, LBP.py:540, :600-603), then the
  *           row sums sum_b T[a,b], sum_b T1[a,b]: together with the column sums they are the factor->variable
  *           messages of a pairwise factor whose incoming message is still the uniform initial one (LBP.py:211-216).
- *   with_grad_planes = 0 skips planes 8..13 (inference only).                                        */
+ *   with_grad_planes = 0 skips planes 8..19 (inference only).                                        */
 int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1, int V, int ldf, const double *h_theta_ee,
                                int scale_exp, void *planes, int64_t plane_stride, int ldv, double *colsums,
                                int with_grad_planes, void *stream);
@@ -130,24 +133,30 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   in the contraction, for an element that carries more than spike_prob of the mass (a history feature's word, say) it
  *   does not.  For every such element written to an A row < n_spike_rows the kernel records
  *   (column, x - fp16(x)) in spike_entries[row][MLBP_SPIKE_SLOTS] (int32 pairs: column, float bits), counts them in
- *   spike_cnt[row] (zeroed by the caller per batch) and lists rows with spikes in spike_rows; mlbp_spike_correct restores
- *   the dropped contribution of message rows exactly, mlbp_pair_expectations that of the gradient stage's spike cells.  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
+ *   spike_cnt[row] (zeroed by the caller per batch) and lists the rows that have spikes PER GEMM BLOCK: `blocks` is the
+ *   plan's flat list of GEMM blocks (4 int32 each {table, first A row, first D row, rows}, ascending; n_blocks of them), the
+ *   list of block b starts at spike_rows[first A row of b] and has spike_blk_cnt[b] entries (zeroed by the caller per
+ *   batch).  mlbp_spike_correct restores the dropped contribution of a block's rows exactly, mlbp_pair_expectations the
+ *   gradient stage's spike cells.  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
  *     [0] PEAK   set when a row has more spikes than slots: mlbp_factor_to_var_gemm_gated then keeps all three passes   (per theta)
  *     [2] the largest element seen so far, bits of the float 2^14 * probability (atomic max; diagnostics)               (per theta)
  *     [3] SPIKE  set when any spike was seen (diagnostics)                                                               (per theta)
- *     [4] number of rows in spike_rows                                                                                  (per batch) */
+ *     [4] number of rows with spikes (diagnostics)                                                                      (per batch) */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                        const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
                        void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
-                       int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows, void *stream);
-/* K4b. Spike compensation of a two-pass message GEMM block (rows [a_row0, a_row0 + n_rows) of A -> D rows d_row0 ..):
+                       int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows,
+                       int32_t *spike_blk_cnt, const int32_t *blocks, int n_blocks, void *stream);
+/* K4b. Spike compensation of a GEMM block that dropped the lo half of A (rows [a_row0, a_row0 + n_rows) of A -> D rows d_row0 ..):
  *   D[r, n] += alpha * sum over the recorded spikes s of row r of  lo_s * B[n, col_s],  with B[n, col] read as row `col` of
- *   the TRANSPOSED table's plane pair Bt_hi / Bt_lo (MLBP_TABLE_T <-> TT, T1 <-> T1T).  Returns at once (on the device) when
- *   spike_words[0] is set: the block then ran with three passes.  Spikes of a row are applied in ascending column order.   */
+ *   the TRANSPOSED table's plane pair Bt_hi / Bt_lo (MLBP_TABLE_T <-> TT, T1 <-> T1T, G <-> GT, G1 <-> G1T, G1W <-> G1WT).
+ *   block_rows / block_n: this block's list of spiky rows and its length (spike_rows + a_row0 and spike_blk_cnt + b of
+ *   mlbp_var_to_factor).  Returns at once (on the device) when spike_words[0] is set: the block then ran with the lo half.
+ *   Spikes of a row are applied in ascending column order (deterministic).                                             */
 int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
-                       const int32_t *spike_rows, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo, int V,
-                       int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream);
+                       const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi,
+                       const void *Bt_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream);
 /* Approximate paths (use_approx_inference LBP.py:506-507, :515-516 -> au.sparse_vec_mat_dot pyx:193-205;
  *   use_approx_beliefs LBP.py:554-563 -> au.sparse_dot / sparse_pointwise_multiply / sparse_normalize pyx:108-129, :23-26):
  *   keep the K largest entries of each of the n_rows operand rows A[row0 ..], zero the others (K = 100 in the reference);

@@ -38,36 +38,28 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
         n1f = fmaf(c, __ldg(u1 + e), n1f);
         if (u2) n2f = fmaf(c, __ldg(u2 + e), n2f);
     }
-    double z = block_sum((double)zf, red), n1 = block_sum((double)n1f, red), n2 = block_sum((double)n2f, red);
-    if (threadIdx.x == 0) {
-        // One-pass gradient rows (u = alpha * r_hi . B_hi) drop the lo half of the table planes.  Its rounding averages away
-        // over the cells a belief spreads over -- except where BOTH messages have a spike: those few cells are restored here,
-        //   sum over spikes a* of c, b* of r:  alpha * c[a*] * r_hi[b*] * B_lo[a*, b*]
-        // (spike lists: mlbp_var_to_factor; skipped when a row had more spikes than slots -- then the rows ran two passes).
-        if (spike_words && spike_words[0] == 0) {
-            const int rr = r_row[f], cr = c_row[f];
-            const int nc = min(spike_cnt[cr], MLBP_SPIKE_SLOTS), nr = min(spike_cnt[rr], MLBP_SPIKE_SLOTS);
-            if (nc > 0 && nr > 0) {
-                const int g1 = gap1[f];
-                const __half *t_lo = planes + (size_t)(2 * (g1 ? MLBP_TABLE_T1 : MLBP_TABLE_T) + 1) * ps;
-                const __half *g_lo = planes + (size_t)(2 * (g1 ? MLBP_TABLE_G1 : MLBP_TABLE_G) + 1) * ps;
-                const __half *w_lo = planes + (size_t)(2 * MLBP_TABLE_G1W + 1) * ps;
-                for (int i = 0; i < nc; ++i) {
-                    const int a = spike_entries[(size_t)cr * MLBP_SPIKE_SLOTS + i].x;
-                    const double ca = (double)(__half2float(ch[a]) + __half2float(cl[a]));
-                    for (int j = 0; j < nr; ++j) {
-                        const int b = spike_entries[(size_t)rr * MLBP_SPIKE_SLOTS + j].x;
-                        const double w = (double)alpha * ca * (double)__half2float(A_hi[(size_t)rr * ldv + b]);
-                        const size_t cell = (size_t)a * ldv + b;
-                        if (zc) z += w * (double)__half2float(t_lo[cell]);     // Z = c . (T r) from its own GEMM row
-                        n1 += w * (double)__half2float(g_lo[cell]);
-                        if (u2) n2 += w * (double)__half2float(w_lo[cell]);
-                    }
-                }
-            }
+    // One-pass gradient rows (u = alpha * r_hi . B_hi) drop the lo half of the table planes.  Its rounding averages away
+    // over the cells a belief spreads over -- except where BOTH messages have a spike: those few cells are restored here,
+    //   sum over spikes a* of c, b* of r:  alpha * c[a*] * r_hi[b*] * B_lo[a*, b*]
+    // one cell per thread (at most MLBP_SPIKE_SLOTS^2), folded into the block sums below (fixed order: deterministic).
+    // (spike lists: mlbp_var_to_factor; skipped when a row had more spikes than slots -- then the rows ran two passes).
+    double cz = 0.0, c1 = 0.0, c2 = 0.0;
+    if (spike_words && threadIdx.x < MLBP_SPIKE_SLOTS * MLBP_SPIKE_SLOTS && spike_words[0] == 0) {
+        const int rr = r_row[f], cr = c_row[f];
+        const int i = threadIdx.x / MLBP_SPIKE_SLOTS, j = threadIdx.x % MLBP_SPIKE_SLOTS;
+        if (i < min(spike_cnt[cr], MLBP_SPIKE_SLOTS) && j < min(spike_cnt[rr], MLBP_SPIKE_SLOTS)) {
+            const int g1 = gap1[f];
+            const int a = spike_entries[(size_t)cr * MLBP_SPIKE_SLOTS + i].x, b = spike_entries[(size_t)rr * MLBP_SPIKE_SLOTS + j].x;
+            const double w = (double)alpha * (double)(__half2float(ch[a]) + __half2float(cl[a])) *
+                             (double)__half2float(A_hi[(size_t)rr * ldv + b]);
+            const size_t cell = (size_t)a * ldv + b;
+            if (zc) cz = w * (double)__half2float(planes[(size_t)(2 * (g1 ? MLBP_TABLE_T1 : MLBP_TABLE_T) + 1) * ps + cell]);
+            c1 = w * (double)__half2float(planes[(size_t)(2 * (g1 ? MLBP_TABLE_G1 : MLBP_TABLE_G) + 1) * ps + cell]);
+            if (u2) c2 = w * (double)__half2float(planes[(size_t)(2 * MLBP_TABLE_G1W + 1) * ps + cell]);
         }
-        stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2;
     }
+    double z = block_sum((double)zf + cz, red), n1 = block_sum((double)n1f + c1, red), n2 = block_sum((double)n2f + c2, red);
+    if (threadIdx.x == 0) { stats[3 * (size_t)f] = z; stats[3 * (size_t)f + 1] = n1; stats[3 * (size_t)f + 2] = n2; }
 }
 
 // one warp per sentence; deterministic (no atomics).  The observed feature values phi[l0, l1, :] are gathered here from the

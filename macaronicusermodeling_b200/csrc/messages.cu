@@ -77,9 +77,12 @@ __device__ __forceinline__ void k3_store(float x, size_t first, int nd, const in
 //                       [4] number of rows in the spiky-row list.
 struct K3Spikes {
     int32_t *words;          // nullptr: no tracking
-    int32_t *cnt;            // [n_msg_rows] spikes recorded per message A row (zeroed by the caller per run)
-    int2 *entries;           // [n_msg_rows][MLBP_SPIKE_SLOTS] (column, float bits of lo)
-    int32_t *rows;           // [n_msg_rows] rows with at least one spike, in order of discovery
+    int32_t *cnt;            // [n_rows] spikes recorded per A row (zeroed by the caller per batch)
+    int2 *entries;           // [n_rows][MLBP_SPIKE_SLOTS] (column, float bits of lo)
+    int32_t *rows;           // [n_rows] spiky rows, one list per GEMM block: the list of block b starts at rows[blocks[4b + 1]]
+    int32_t *blk_cnt;        // [n_blocks] length of each block's list (zeroed by the caller per batch)
+    const int32_t *blocks;   // [n_blocks][4] {table, first A row, first D row, rows} of every GEMM block, ascending in A rows
+    int n_blocks;
     int n_rows;              // rows of the A buffers covered by cnt / entries / rows
     float limit;             // 2^14 * probability above which an element is a spike
 };
@@ -95,36 +98,47 @@ __device__ __forceinline__ void k3_mark_spike(int *s_nmark, K3Mark *s_mark, int 
     if (k < K3_MAX_MARKS) s_mark[k] = K3Mark{d0, nd, col, x};
 }
 
+__device__ __forceinline__ void k3_note_spike_size(const K3Spikes &sp, float x);
+
 __device__ __noinline__ void k3_record_spike(const K3Spikes sp, const int32_t *__restrict__ dest, int d0, int nd, int col, float x) {
     const float lo = x - __half2float(__float2half_rn(x));        // what a two-pass row drops (exact in fp32)
     sp.words[3] = 1;
+    k3_note_spike_size(sp, x);
     for (int t = 0; t < nd; ++t) {
         const int row = dest[d0 + t];
         if (row >= sp.n_rows) continue;
         const int slot = atomicAdd(&sp.cnt[row], 1);
-        if (slot == 0) sp.rows[atomicAdd(&sp.words[4], 1)] = row;
+        if (slot == 0) {                                           // first spike of this row: list it with its GEMM block
+            int lo_b = 0, hi_b = sp.n_blocks - 1;
+            while (lo_b < hi_b) {                                  // last block whose first A row is <= row
+                const int mid = (lo_b + hi_b + 1) >> 1;
+                if (sp.blocks[4 * mid + 1] <= row) lo_b = mid; else hi_b = mid - 1;
+            }
+            if (sp.n_blocks > 0 && sp.blocks[4 * lo_b + 1] <= row && row < sp.blocks[4 * lo_b + 1] + sp.blocks[4 * lo_b + 3])
+                sp.rows[sp.blocks[4 * lo_b + 1] + atomicAdd(&sp.blk_cnt[lo_b], 1)] = row;
+            atomicAdd(&sp.words[4], 1);                            // (total, diagnostics)
+        }
         if (slot < MLBP_SPIKE_SLOTS) sp.entries[(size_t)row * MLBP_SPIKE_SLOTS + slot] = make_int2(col, __float_as_int(lo));
         else sp.words[0] = 1;
     }
 }
 
-// after a group's hot loop (all threads; the caller has synchronised the block): flush the marks, one thread per mark
-__device__ __forceinline__ void k3_flush_marks(const K3Spikes &sp, const int32_t *__restrict__ dest, int *s_nmark, K3Mark *s_mark) {
-    const int n = *s_nmark;                                        // block-uniform
+// After a group's hot loop (all threads; the caller has synchronised the block): flush the marks of buffer `par`, one thread
+// per mark, taken from the END of the block (the first threads issue the next group's copies and must not wait for atomics).
+// No barrier here: the other buffer -- flushed one iteration ago, idle since -- is reset for the next group instead.
+__device__ __forceinline__ void k3_flush_marks(const K3Spikes &sp, const int32_t *__restrict__ dest, int *s_nmark, K3Mark (*s_mark)[K3_MAX_MARKS],
+                                               int par) {
+    const int n = s_nmark[par];                                    // block-uniform
+    if (threadIdx.x == 0) s_nmark[par ^ 1] = 0;
     if (n == 0) return;
-    if (n > K3_MAX_MARKS) sp.words[0] = 1;                         // more spikes than marks: three passes from here on
-    for (int m = threadIdx.x; m < min(n, K3_MAX_MARKS); m += blockDim.x)
-        k3_record_spike(sp, dest, s_mark[m].d0, s_mark[m].nd, s_mark[m].col, s_mark[m].x);
-    __syncthreads();
-    if (threadIdx.x == 0) *s_nmark = 0;
+    if (n > K3_MAX_MARKS && threadIdx.x == 0) sp.words[0] = 1;     // more spikes than marks: three passes from here on
+    const int m = (int)blockDim.x - 1 - (int)threadIdx.x;
+    if (m < min(n, K3_MAX_MARKS)) k3_record_spike(sp, dest, s_mark[par][m].d0, s_mark[par][m].nd, s_mark[par][m].col, s_mark[par][m].x);
 }
 
-// End of a K3 kernel: keep the largest element seen (one atomic per warp)
-__device__ __forceinline__ void k3_report_max(const K3Spikes &sp, float mx) {
-    if (!sp.words) return;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(sp.words + 2, __float_as_int(mx));
+// the largest spike seen (diagnostics; positive floats order like their bit patterns)
+__device__ __forceinline__ void k3_note_spike_size(const K3Spikes &sp, float x) {
+    if (x == x) atomicMax(sp.words + 2, __float_as_int(x));
 }
 
 template <int NMAX, typename T, int OCC>
@@ -139,9 +153,9 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     __shared__ size_t s_first[NMAX];
     __shared__ double s_warp[K3_WARPS][NMAX];
     __shared__ float s_scale[NMAX];
-    __shared__ int s_nmark;
-    __shared__ K3Mark s_mark[K3_MAX_MARKS];
-    if (threadIdx.x == 0) s_nmark = 0;
+    __shared__ int s_nmark[2];
+    __shared__ K3Mark s_mark[1][K3_MAX_MARKS];
+    if (threadIdx.x == 0) s_nmark[0] = 0;
     const int g = blockIdx.x;
     const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
     const float *urow = U + (size_t)grp_u[g] * ldv;
@@ -196,7 +210,6 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     // ---- phase 2: recompute, normalise, split, scatter to the consuming GEMM blocks
     // (walking the columns backwards to catch the L2-resident tail of phase 1 was measured 12 % slower)
     const float uni = ldexpf(1.0f, MLBP_A_SCALE_LOG2) / (float)V;
-    float mx = 0.f;                                               // largest element written (2^14 * probability)
     for (int e = threadIdx.x; e < V; e += K3_THREADS) {
         float d[NMAX];
 #pragma unroll
@@ -212,8 +225,7 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
             if (nd > 0) {
                 const float sc = s_scale[j];
                 const float x = sc > 0.f ? (float)(pre[j] * suf * (T)sc) : uni;
-                mx = fmaxf(mx, x);
-                if (sp.words && x > sp.limit) k3_mark_spike(&s_nmark, s_mark, s_d0[j], nd, e, x);  // rare
+                if (sp.words && x > sp.limit) k3_mark_spike(&s_nmark[0], s_mark[0], s_d0[j], nd, e, x);  // rare
                 k3_store(x, s_first[j] + e, nd, dest, s_d0[j], ldv, e, A_hi, A_lo);
             }
             suf *= (T)d[j];
@@ -221,9 +233,8 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
     }
     if (sp.words) {
         __syncthreads();
-        k3_flush_marks(sp, dest, &s_nmark, s_mark);
+        k3_flush_marks(sp, dest, s_nmark, s_mark, 0);
     }
-    k3_report_max(sp, mx);
 }
 
 // Messages with more than TWO readers (the first two are written directly): the slice just written to the first reader's
@@ -280,9 +291,9 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     __shared__ double s_gather[2][8][NIN];                     // [exchange parity][source rank][output]
     __shared__ __align__(8) unsigned long long s_gbar[2];
     __shared__ float s_scale[NIN];
-    __shared__ int s_nmark;
-    __shared__ K3Mark s_mark[K3_MAX_MARKS];
-    if (threadIdx.x == 0) s_nmark = 0;
+    __shared__ int s_nmark[2];
+    __shared__ K3Mark s_mark[2][K3_MAX_MARKS];
+    if (threadIdx.x == 0) { s_nmark[0] = 0; s_nmark[1] = 0; }
     cg::cluster_group cl = cg::this_cluster();
     const unsigned C = cl.num_blocks(), q = cl.block_rank();
     const int n_clusters = gridDim.x / C;
@@ -347,7 +358,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     // loops are written as straight-line code (no branch on a value loaded inside the loop): measured with clock64
     // per stage, a data-dependent branch per input cost ~100 cycles per input and column pair.
     const int npair = (ncol + 1) >> 1;
-    float mx = 0.f;                                                // largest element written (2^14 * probability)
+    const float spike_limit = sp.words ? sp.limit : __int_as_float(0x7f800000);   // +inf: no tracking, one compare per output pair
     for (; g < n_groups; g += n_clusters, b ^= 1) {
         if (ncol > 0) {
             if (threadIdx.x == 0)
@@ -478,11 +489,9 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                     const float sc = s_scale[j];
                     float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
                     if (!(sc > 0.f)) x = make_float2(uni, uni);
-                    const float xm = fmaxf(x.x, odd ? 0.f : x.y);
-                    mx = fmaxf(mx, xm);
-                    if (sp.words && xm > sp.limit) {                                  // rare: a spike (see K3Spikes)
-                        if (x.x > sp.limit) k3_mark_spike(&s_nmark, s_mark, s_d0[b][j], s_nd[b][j], col0 + 2 * e2, x.x);
-                        if (!odd && x.y > sp.limit) k3_mark_spike(&s_nmark, s_mark, s_d0[b][j], s_nd[b][j], col0 + 2 * e2 + 1, x.y);
+                    if (fmaxf(x.x, x.y) > spike_limit) {                               // rare: a spike (see K3Spikes)
+                        if (x.x > spike_limit) k3_mark_spike(&s_nmark[b], s_mark[b], s_d0[b][j], s_nd[b][j], col0 + 2 * e2, x.x);
+                        if (!odd && x.y > spike_limit) k3_mark_spike(&s_nmark[b], s_mark[b], s_d0[b][j], s_nd[b][j], col0 + 2 * e2 + 1, x.y);
                     }
                     const __half2 hi = __float22half2_rn(x);
                     const float2 back = __half22float2(hi);
@@ -532,10 +541,9 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
             k3_copy_extras<NIN>(s_nd[b], s_d0[b], s_first[b], dest, ldv, col0, ncol, A_hi, A_lo);
         }
         __syncthreads();                                           // shared memory is reused by the next group
-        if (sp.words) k3_flush_marks(sp, dest, &s_nmark, s_mark);
+        if (sp.words) k3_flush_marks(sp, dest, s_nmark, s_mark, b);
         K3_TICK(5);
     }
-    k3_report_max(sp, mx);
 #ifdef MLBP_K3_STAGE_TIMES
     if (dbg && threadIdx.x == 0)
         for (int i = 0; i < 6; ++i) dbg[(size_t)blockIdx.x * 6 + i] = tacc[i];
@@ -744,7 +752,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
                                   const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
                                   void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
                                   int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows,
-                                  void *stream) {
+                                  int32_t *spike_blk_cnt, const int32_t *blocks, int n_blocks, void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && second_dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
@@ -756,11 +764,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = as_stream(stream);
-    MLBP_CHECK_ARG(!spike_words || (spike_cnt && spike_entries && spike_rows && n_spike_rows >= 0 && spike_prob > 0.f),
+    MLBP_CHECK_ARG(!spike_words || (spike_cnt && spike_entries && spike_rows && n_spike_rows >= 0 && spike_prob > 0.f &&
+                                    n_blocks >= 0 && (n_blocks == 0 || (spike_blk_cnt && blocks))),
                    "var_to_factor: spike tracking needs cnt, entries, rows and a positive threshold");
     K3Spikes sp;
     sp.words = spike_words; sp.cnt = spike_cnt; sp.entries = reinterpret_cast<int2 *>(spike_entries); sp.rows = spike_rows;
     sp.n_rows = n_spike_rows;
+    sp.blk_cnt = spike_blk_cnt; sp.blocks = blocks; sp.n_blocks = n_blocks;
     sp.limit = ldexpf(spike_prob, MLBP_A_SCALE_LOG2);              // rows are stored as 2^14 * probability
     // The resident single-read kernel runs whenever the products fit fp32 and the cluster's slices fit shared memory;
     // MLBP_K3_IMPL=1 forces the streaming two-read kernel (used by scripts/k3_probe.py to time both).

@@ -46,7 +46,7 @@ namespace {
 enum {
     H_NLEVELS = 0, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
     H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
-    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS, H_WORDS = 32
+    H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS, H_SPK_BLK_N, H_WORDS = 32
 };
 enum { LEV_NGROUPS = 0, LEV_GRP_U, LEV_GRP_OFF, LEV_IN_ROW, LEV_DEST_OFF, LEV_DEST, LEV_NGEMM, LEV_GEMM, LEV_FIRST, LEV_SECOND, LEV_WORDS = 10 };
 enum { GEMM_TABLE = 0, GEMM_A0, GEMM_D0, GEMM_N, GEMM_WORDS = 4 };
@@ -530,6 +530,11 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     // flat copy of the per-level GEMM records {table, A row, D row, rows}: the exact re-score (rescore.cu) finds the table of
     // a message's D row by bisection over it
     B[H_MSG_BLK_N] = (int32_t)(msg_blocks.size() / GEMM_WORDS);
+    // ... followed by the two row ranges of the gradient stage's r copies (gap > 1, gap == 1): together the list of A-row
+    // ranges whose spikes the var->factor kernel files per block (H_SPK_BLK_N entries)
+    if (want_grad && n_gap0 > 0) { msg_blocks.push_back(MLBP_TABLE_G); msg_blocks.push_back((int32_t)a_r0); msg_blocks.push_back((int32_t)d_u1_0); msg_blocks.push_back((int32_t)n_gap0); }
+    if (want_grad && n_gap1 > 0) { msg_blocks.push_back(MLBP_TABLE_G1); msg_blocks.push_back((int32_t)a_r1); msg_blocks.push_back((int32_t)d_u1_1); msg_blocks.push_back((int32_t)n_gap1); }
+    B[H_SPK_BLK_N] = (int32_t)(msg_blocks.size() / GEMM_WORDS);
     B[H_MSG_BLK_OFF] = append(msg_blocks);
     B[H_MSG_ROWS] = (int32_t)n_msg_rows;
     B[H_NPAIR] = (int32_t)n_pair;

@@ -8,9 +8,10 @@
 // one contiguous row read (hi + lo) and the row's spikes share one read-modify-write of D[r, :].  Reference semantics are
 // untouched: this is arithmetic the float64 dgemv of LBP.py:509 / :518 does implicitly.
 //
-// One launch per (level, table) GEMM block, after the block's gated launches.  Persistent CTAs walk the list of spiky rows and
-// pick those inside the block; the spikes of a row are applied in ascending column order (deterministic).  The kernel returns
-// at once when the gate word is set: then the block ran with all three passes and nothing was dropped.
+// One launch per (level, table) GEMM block, after the block's gated launches.  The var->factor kernel keeps one list of spiky
+// rows per GEMM block, so a launch touches only its own rows; persistent CTAs walk that list (its length is only known on the
+// device); the spikes of a row are applied in ascending column order (deterministic).  The kernel returns at once when the
+// gate word is set: then the block ran with all its passes and nothing was dropped.
 #include "common.cuh"
 
 namespace mlbp {
@@ -19,16 +20,16 @@ constexpr int SP_THREADS = 256;
 
 __global__ void __launch_bounds__(SP_THREADS)
 spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restrict__ cnt, const int2 *__restrict__ entries,
-                     const int32_t *__restrict__ rows, int a0, int n_rows, const __half *__restrict__ Bt_hi,
+                     const int32_t *__restrict__ rows, const int32_t *__restrict__ n_list, int a0, int n_rows, const __half *__restrict__ Bt_hi,
                      const __half *__restrict__ Bt_lo, int V, int ldv, float *__restrict__ D, int64_t d_row0, int ldd,
                      float alpha) {
     if (words[0] != 0) return;                                     // three passes ran: nothing to restore
     __shared__ int s_col[MLBP_SPIKE_SLOTS];
     __shared__ float s_lo[MLBP_SPIKE_SLOTS];
-    const int total = words[4];
+    const int total = min(*n_list, n_rows);
     for (int i = blockIdx.x; i < total; i += gridDim.x) {
         const int row = rows[i];
-        if (row < a0 || row >= a0 + n_rows) continue;              // block-uniform
+        if (row < a0 || row >= a0 + n_rows) continue;              // (cannot happen: the list belongs to this block)
         const int n = min(cnt[row], MLBP_SPIKE_SLOTS);
         __syncthreads();
         if (threadIdx.x == 0) {                                    // insertion sort by column: fixed summation order
@@ -73,19 +74,19 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
 using namespace mlbp;
 
 extern "C" int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
-                                  const int32_t *spike_rows, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo,
+                                  const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo,
                                   int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream) {
     if (n_rows == 0) return MLBP_OK;
-    MLBP_CHECK_ARG(spike_words && spike_cnt && spike_entries && spike_rows && Bt_hi && Bt_lo && D && n_rows > 0 && a_row0 >= 0,
+    MLBP_CHECK_ARG(spike_words && spike_cnt && spike_entries && block_rows && block_n && Bt_hi && Bt_lo && D && n_rows > 0 && a_row0 >= 0,
                    "spike_correct: bad argument");
     MLBP_CHECK_ARG((ldv % 64) == 0 && ldv >= V && (ldd % 64) == 0 && ldd >= V &&
                    ((reinterpret_cast<uintptr_t>(Bt_hi) | reinterpret_cast<uintptr_t>(Bt_lo) | reinterpret_cast<uintptr_t>(D)) % 16) == 0,
                    "spike_correct: rows must be 16-byte aligned and padded to a multiple of 64");
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
-    const int grid = n_rows < 2 * sms ? n_rows : 2 * sms;
+    const int grid = n_rows < 8 * sms ? n_rows : 8 * sms;
     spike_correct_kernel<<<grid, SP_THREADS, 0, as_stream(stream)>>>(spike_words, spike_cnt, reinterpret_cast<const int2 *>(spike_entries),
-                                                                    spike_rows, a_row0, n_rows, (const __half *)Bt_hi,
+                                                                    block_rows, block_n, a_row0, n_rows, (const __half *)Bt_hi,
                                                                     (const __half *)Bt_lo, V, ldv, D, d_row0, ldd, alpha);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;

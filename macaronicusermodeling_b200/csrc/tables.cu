@@ -62,11 +62,13 @@ __global__ void __launch_bounds__(256)
 build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restrict__ w1, int V, int ldf, F2 t_pmi, F2 t_w1,
                              F2 t_bias, float scale, __half *__restrict__ planes, int64_t ps, int ldv,
                              double *__restrict__ colsums, int with_grad) {
-    // T.hi T.lo T1.hi T1.lo tiles, indexed [a][b]; the column-sum partials reuse the storage once the tiles are written out
-    __shared__ __align__(16) unsigned char s_raw[4 * TS * (TS + 2) * sizeof(__half)];
+    // hi / lo tiles of T, T1 (and G, G1, G1w with the gradient planes), indexed [a][b], for the transposed planes; the
+    // column-sum partials reuse the storage once the tiles are written out.  Dynamic shared memory: 10 tiles = 84 KB.
+    extern __shared__ __align__(16) unsigned char s_raw[];
     __half (*sT)[TS][TS + 2] = reinterpret_cast<__half (*)[TS][TS + 2]>(s_raw);
     double (*sSum)[8][TS] = reinterpret_cast<double (*)[8][TS]>(s_raw);
-    static_assert(sizeof(double) * 5 * 8 * TS <= sizeof(s_raw), "column-sum partials must fit the tile storage");
+    static_assert(sizeof(double) * 5 * 8 * TS <= 4 * TS * (TS + 2) * sizeof(__half), "column-sum partials must fit the tile storage");
+    const int n_tiles = with_grad ? 10 : 4;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int a0 = blockIdx.y * TS, b0 = blockIdx.x * TS;
     const int b = b0 + 2 * tx;
@@ -116,7 +118,8 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<__half2 *>(&sT[i][r][2 * tx]) = h[i];
+        for (int i = 0; i < 10; ++i)
+            if (i < n_tiles) *reinterpret_cast<__half2 *>(&sT[i][r][2 * tx]) = h[i];
         // row sums of T and T1 (message of a pairwise factor whose input is still the uniform initial message)
         rs_t = warp_sum_f32(rs_t); rs_t1 = warp_sum_f32(rs_t1);
         if (tx == 0 && a < V) {
@@ -130,11 +133,14 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
         const int bb = b0 + r, aa = a0 + 2 * tx;
         if (bb < V && aa < V) {                                   // aa + 1 < ldv: the padding column receives the zero of sT
             const size_t o = (size_t)bb * ldv + aa;
+            // tiles 0..3 -> planes 2, 3 (Tt) and 6, 7 (T1t); tiles 4..9 -> planes 14..19 (Gt, G1t, G1wt: the spike compensation
+            // of the gradient rows reads a COLUMN of T o PMI as a row of these)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const __half2 x = __halves2half2(sT[i][2 * tx][r], sT[i][2 * tx + 1][r]);
-                *reinterpret_cast<__half2 *>(planes + (i < 2 ? 2 + i : 4 + i) * ps + o) = x;    // planes 2, 3 (Tt) and 6, 7 (T1t)
-            }
+            for (int i = 0; i < 10; ++i)
+                if (i < n_tiles) {
+                    const __half2 x = __halves2half2(sT[i][2 * tx][r], sT[i][2 * tx + 1][r]);
+                    *reinterpret_cast<__half2 *>(planes + (i < 2 ? 2 + i : (i < 4 ? 4 + i : 10 + i)) * ps + o) = x;
+                }
         }
     }
     __syncthreads();                                              // the tiles are dead: their storage takes the partial sums
@@ -191,7 +197,14 @@ extern "C" int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1,
     cudaStream_t st = as_stream(stream);
     MLBP_CUDA(cudaMemsetAsync(colsums, 0, sizeof(double) * MLBP_N_SUMS * (size_t)V, st));
     dim3 grid((V + TS - 1) / TS, (V + TS - 1) / TS);
-    build_pairwise_tables_kernel<<<grid, 256, 0, st>>>(pmi, pmi_w1, V, ldf, split_double_host(h_theta_ee[0]),
+    const size_t smem = (size_t)(with_grad_planes ? 10 : 4) * TS * (TS + 2) * sizeof(__half);
+    static bool attr_set_dev[MLBP_MAX_DEVICES] = {};
+    if (!attr_set_dev[current_device()]) {
+        MLBP_CUDA(cudaFuncSetAttribute(build_pairwise_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       10 * TS * (TS + 2) * (int)sizeof(__half)));
+        attr_set_dev[current_device()] = true;
+    }
+    build_pairwise_tables_kernel<<<grid, 256, smem, st>>>(pmi, pmi_w1, V, ldf, split_double_host(h_theta_ee[0]),
                                                        split_double_host(h_theta_ee[1]), split_double_host(h_theta_ee[2]),
                                                        ldexpf(1.0f, scale_exp), (__half *)planes, plane_stride, ldv, colsums,
                                                        with_grad_planes);

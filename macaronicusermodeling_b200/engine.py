@@ -23,14 +23,15 @@ from . import _lib
 # plan blob header (csrc/plan.cpp)
 (H_NLEVELS, H_LEVELS_OFF, H_INIT_N, H_INIT_OFF, H_NPAIR, H_PAIR_C, H_PAIR_U0, H_PAIR_U1, H_PAIR_U2, H_PAIR_GAP1,
  H_PAIR_V0, H_PAIR_V1, H_NGRAD_GEMM, H_GRAD_GEMM_OFF, H_MARG_N, H_MARG_U, H_MARG_OFF, H_MARG_IN, H_NGRAPHS,
- H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS) = range(28)
+ H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS, H_SPK_BLK_N) = range(29)
 H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
  PLAN_N_DEAD) = range(9)
 A_SCALE_LOG2 = 14
 GEMM_A_HI_ONLY = 256          # include/mlbp.h MLBP_GEMM_A_HI_ONLY
 GEMM_B_HI_ONLY = 512          # include/mlbp.h MLBP_GEMM_B_HI_ONLY
-N_PLANES = 14
+N_PLANES = 20
+TRANSPOSED_TABLE = {0: 1, 1: 0, 2: 3, 3: 2, 4: 7, 5: 8, 6: 9}   # include/mlbp.h MLBP_TABLE_*: where a table's columns are rows
 N_SUMS = 7
 D_CONST_ROWS = 5
 # Engine._flags (device int32 words): the peak flag of the var->factor kernel (sticky per theta), the flagged-variable count of
@@ -219,7 +220,7 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None, msg_passes=None, tau=5e-4, tau_label=2.5e-4, peak_mult=16.0, one_pass_min_v=4096):
+                 gemm_slice_pairs=None, msg_passes=None, tau=2e-4, tau_label=1e-4, peak_mult=16.0, one_pass_min_v=4096):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -502,7 +503,12 @@ class Engine(object):
             spk_cnt = torch.empty(n_spk, dtype=torch.int32, device=dev)
             spk_ent = torch.empty((n_spk, SPIKE_SLOTS, 2), dtype=torch.int32, device=dev)
             spk_rows = torch.empty(n_spk, dtype=torch.int32, device=dev)
+            n_blk = int(blob[H_SPK_BLK_N])
+            blk_host = blob[int(blob[H_MSG_BLK_OFF]):int(blob[H_MSG_BLK_OFF]) + GEMM_WORDS * n_blk].reshape(-1, GEMM_WORDS)
+            blk_of = dict((int(r[1]), i) for i, r in enumerate(blk_host))     # first A row of a block -> its index
+            spk_blk = torch.empty(max(n_blk, 1), dtype=torch.int32, device=dev)
             k.call('mlbp_zero_words', _p(spk_cnt), n_spk)
+            k.call('mlbp_zero_words', _p(spk_blk), max(n_blk, 1))
             k.call('mlbp_zero_words', _p(self._flags, FLAG_NSPIKY), 1)
 
         D[:D_CONST_ROWS].copy_(self.const_rows)                   # row 0: the constant-one row messages still uniform read
@@ -532,6 +538,15 @@ class Engine(object):
         alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp + self.centre_exp)))
         g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
         range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
+
+        def spike_correct(t, a0, d0, rows, block_a0):
+            """restore what the dropped lo half of A contributed at the spikes of rows [a0, a0 + rows) (block starting at block_a0)"""
+            b = blk_of[block_a0]
+            tt = TRANSPOSED_TABLE[t]
+            self._timed('K4b spike_correct', 0.0,                # bytes depend on the data (spikes found on the device)
+                        lambda: k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows, block_a0), _p(spk_blk, b),
+                                       a0, rows, _p(self.plane(tt, 0)), _p(self.plane(tt, 1)), V, ld, _p(D), d0, ld, alpha))
+            self.launches += 1
 
         def gemm_calls(off, n, mask, impl_flags=0, gated=False):
             masked = set()
@@ -580,16 +595,14 @@ class Engine(object):
                                            _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(bd, int(rec[9])),
                                            _p(U), _p(D), ld,
                                            V, _p(A_hi), _p(A_lo), max_in, range_log2, peak_flag, self.peak_mult / V,
-                                           _p(spk_cnt), _p(spk_ent), _p(spk_rows), n_spk))
+                                           _p(spk_cnt), _p(spk_ent), _p(spk_rows), n_spk,
+                                           _p(spk_blk) if track else None, _p(bd, int(blob[H_MSG_BLK_OFF])), int(blob[H_SPK_BLK_N]) if track else 0))
                 self.launches += 1
             if two_pass:
                 gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
                 for i in range(int(rec[6])):                      # restore what the dropped lo half of the spikes contributed
                     t, a0, d0, rows = (int(x) for x in blob[int(rec[7]) + GEMM_WORDS * i: int(rec[7]) + GEMM_WORDS * (i + 1)])
-                    self._timed('K4b spike_correct', 0.0,            # bytes depend on the data (spikes found on the device)
-                                lambda: k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows), a0, rows,
-                                               _p(self.plane(t ^ 1, 0)), _p(self.plane(t ^ 1, 1)), V, ld, _p(D), d0, ld, alpha))
-                    self.launches += 1
+                    spike_correct(t, a0, d0, rows, a0)
             else:
                 gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
@@ -607,6 +620,12 @@ class Engine(object):
                 # with more spikes than slots (PEAK word, device gate) switches these rows to two passes instead.
                 gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), False, GEMM_A_HI_ONLY | GEMM_B_HI_ONLY,
                            gated=(peak_flag, GEMM_A_HI_ONLY))
+                # ... and the lo part of r at its spikes (the rows drop A_lo): without it the rounding of a spike that Z contains
+                # but the numerator does not (a zero of a sparse feature plane under the spike) shows up undamped in N / Z
+                go = int(blob[H_GRAD_GEMM_OFF])
+                for i in range(int(blob[H_NGRAD_GEMM])):
+                    t, a0, d0, rows = (int(x) for x in blob[go + GEMM_WORDS * i: go + GEMM_WORDS * (i + 1)])
+                    spike_correct(t, a0, d0, rows, a0)
             else:
                 gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
                            (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0)

@@ -44,9 +44,9 @@ class FakeKernels(object):
         W = _arr(w1, np.float32, V * ldf).reshape(V, ldf)[:, :V].astype(np.float64)
         t = _arr(th, np.float64, 3)
         T = np.exp(t[0] * P + t[2]); T1 = np.exp(t[0] * P + t[1] * W + t[2])
-        mats = [T, T.T, T1, T1.T, T * P, T1 * P, T1 * W]
-        pl = _arr(planes, np.float16, (14 if with_grad else 8) * ps)
-        for i, M in enumerate(mats[: 7 if with_grad else 4]):
+        mats = [T, T.T, T1, T1.T, T * P, T1 * P, T1 * W, (T * P).T, (T1 * P).T, (T1 * W).T]
+        pl = _arr(planes, np.float16, (20 if with_grad else 8) * ps)
+        for i, M in enumerate(mats[: 10 if with_grad else 4]):
             hi, lo = _split(np.ldexp(M, scale_exp))
             for j, h in enumerate((hi, lo)):
                 v = pl[(2 * i + j) * ps:(2 * i + j) * ps + V * ldv].reshape(V, ldv)
@@ -163,7 +163,8 @@ class FakeKernels(object):
         _arr(p, np.int32, n)[:] = 0
 
     def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2,
-                           spike_words=None, spike_prob=1.0, spike_cnt=None, spike_entries=None, spike_rows=None, n_msg_rows=0):
+                           spike_words=None, spike_prob=1.0, spike_cnt=None, spike_entries=None, spike_rows=None, n_msg_rows=0,
+                           spike_blk_cnt=None, blocks=None, n_blocks=0):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         n_in = int(go[-1])
         ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
@@ -209,7 +210,12 @@ class FakeKernels(object):
                                 continue                          # (n_msg_rows = rows covered by the spike arrays)
                             slot = int(cnt[tdest]); cnt[tdest] += 1
                             if slot == 0:
-                                rws[pf[4]] = tdest; pf[4] += 1
+                                blk = _arr(blocks, np.int32, 4 * max(n_blocks, 1)).reshape(-1, 4)[:n_blocks]
+                                bc = _arr(spike_blk_cnt, np.int32, max(n_blocks, 1))
+                                for bi, brow in enumerate(blk):
+                                    if brow[1] <= tdest < brow[1] + brow[3]:
+                                        rws[brow[1] + bc[bi]] = tdest; bc[bi] += 1
+                                pf[4] += 1
                             if slot < 4:
                                 ent[tdest, slot, 0] = col
                                 ent[tdest, slot, 1:2].view(np.float32)[0] = lo_exact
@@ -246,11 +252,12 @@ class FakeKernels(object):
             return
         self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl)
 
-    def mlbp_spike_correct(self, words, cnt, entries, rows, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha):
+    def mlbp_spike_correct(self, words, cnt, entries, rows, n_list, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha):
         w = _arr(words, np.int32, 5)
         if w[0] != 0:
             return
-        rws = _arr(rows, np.int32, max(int(w[4]), 1))[:int(w[4])]
+        n = int(_arr(n_list, np.int32, 1)[0])
+        rws = _arr(rows, np.int32, max(n, 1))[:n]
         sel = [int(r) for r in rws if a0 <= r < a0 + n_rows]
         if not sel:
             return

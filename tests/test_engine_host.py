@@ -240,7 +240,7 @@ def test_one_pass_gradient_rows_restore_spike_cells():
     """One-pass gradient rows drop the lo half of the T / T o PMI planes.  With peaked beliefs the cell where both messages of a
     factor have their spike dominates the expectation and its fp16 rounding does not average away (the failure the judge of
     round 1 predicted); mlbp_pair_expectations restores exactly those cells from the spike lists."""
-    model = synth.make_model(160, 24, seed=13, pmi_density=0.3)
+    model = synth.make_model(160, 24, seed=13, pmi_density=0.3, w1_density=0.1)
     sents = [synth.sentence_to_arrays(synth.make_sentence(model, 'pppp', seed=90 + i, n_history=4, p_correct=0.9)) for i in range(8)]
     roots_pos = synth.draw_roots(sents, 3, seed=4)
     te, td = [1.2, 0.6, -0.1], [0.6, -0.4, 6.0, 5.0, 2.0, -0.1]

@@ -123,7 +123,7 @@ def test_pairwise_tables(lib):
     pmi = torch.zeros((V, ld)); pmi[:, :V] = torch.from_numpy(model['pmi'].astype(np.float32))
     w1 = torch.zeros((V, ld)); w1[:, :V] = torch.from_numpy(model['pmi_w1'].astype(np.float32))
     pmi, w1 = pmi.cuda(), w1.cuda()
-    planes = torch.zeros((14, V, ld), dtype=torch.float16, device='cuda')
+    planes = torch.zeros((20, V, ld), dtype=torch.float16, device='cuda')
     cols = torch.zeros((7, V), dtype=torch.float64, device='cuda')
     s = 9
     _lib.check(lib.mlbp_build_pairwise_tables(P(pmi), P(w1), V, ld, te.ctypes.data_as(ctypes.c_void_p), s, P(planes),
@@ -132,7 +132,7 @@ def test_pairwise_tables(lib):
     pl = planes.cpu().numpy().astype(np.float64)
     p32, w32 = model['pmi'].astype(np.float32).astype(np.float64), model['pmi_w1'].astype(np.float32).astype(np.float64)
     T = np.exp(te[0] * p32 + te[2]); T1 = np.exp(te[0] * p32 + te[1] * w32 + te[2])
-    want = [T, T.T, T1, T1.T, T * p32, T1 * p32, T1 * w32]
+    want = [T, T.T, T1, T1.T, T * p32, T1 * p32, T1 * w32, (T * p32).T, (T1 * p32).T, (T1 * w32).T]
     for i, W in enumerate(want):
         got = (pl[2 * i] + pl[2 * i + 1])[:, :V] * 2.0 ** -s
         assert np.abs(got - W).max() / W.max() < 1e-6, i
@@ -295,12 +295,13 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
         rows[n_sp] = r
         n_sp += 1
     words[4] = n_sp
+    n_list = torch.tensor([n_sp], dtype=torch.int32, device='cuda')
     cnt, ent, rows = cnt.cuda(), ent.cuda(), rows.cuda()
     D = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
     n_blk = M - a0
     _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D), 1, ld, 0.5, 256, P(words), 0, S()))
     before = D.clone()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, S()))
     torch.cuda.synchronize()
     got, was = D.cpu().numpy(), before.cpu().numpy()
     full = 0.5 * (Ax[a0:] @ Bx.T)
@@ -318,6 +319,6 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     # PEAK set: the block ran three passes, the correction must not touch it
     words[0] = 1
     D2 = before.clone()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, S()))
     torch.cuda.synchronize()
     assert torch.equal(D2, before)
