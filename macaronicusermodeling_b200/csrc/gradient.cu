@@ -30,6 +30,12 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
     const float *u2 = u2_row[f] >= 0 ? D + (size_t)u2_row[f] * ldv : nullptr;
     // fp32 products, short per-thread fp32 partial sums (V / 256 terms), float64 across the block: the fp64 pipe of
     // B200 issues ~3 lanes/clk/SM, and the ratio N/Z only needs ~1e-6
+    // spike counts of the two messages: loaded with the row indices above (same dependency depth as the first loads of the loop)
+    int ncs = 0, nrs = 0;
+    if (spike_words && spike_words[0] == 0) {
+        ncs = min(spike_cnt[c_row[f]], MLBP_SPIKE_SLOTS);
+        nrs = min(spike_cnt[r_row[f]], MLBP_SPIKE_SLOTS);
+    }
     float zf = 0.f, n1f = 0.f, n2f = 0.f;
     for (int e = threadIdx.x; e < V; e += blockDim.x) {
         const float c = __half2float(ch[e]) + __half2float(cl[e]);
@@ -41,13 +47,14 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
     // One-pass gradient rows (u = alpha * r_hi . B_hi) drop the lo half of the table planes.  Its rounding averages away
     // over the cells a belief spreads over -- except where BOTH messages have a spike: those few cells are restored here,
     //   sum over spikes a* of c, b* of r:  alpha * c[a*] * r_hi[b*] * B_lo[a*, b*]
-    // one cell per thread (at most MLBP_SPIKE_SLOTS^2), folded into the block sums below (fixed order: deterministic).
+    // one cell per thread (at most MLBP_SPIKE_SLOTS^2), folded into the block sums below (fixed order: deterministic).  Only
+    // factors whose two messages BOTH have spikes pay for the chain of dependent loads (entries -> cells).
     // (spike lists: mlbp_var_to_factor; skipped when a row had more spikes than slots -- then the rows ran two passes).
     double cz = 0.0, c1 = 0.0, c2 = 0.0;
-    if (spike_words && threadIdx.x < MLBP_SPIKE_SLOTS * MLBP_SPIKE_SLOTS && spike_words[0] == 0) {
+    if (ncs > 0 && nrs > 0 && threadIdx.x < MLBP_SPIKE_SLOTS * MLBP_SPIKE_SLOTS) {
         const int rr = r_row[f], cr = c_row[f];
         const int i = threadIdx.x / MLBP_SPIKE_SLOTS, j = threadIdx.x % MLBP_SPIKE_SLOTS;
-        if (i < min(spike_cnt[cr], MLBP_SPIKE_SLOTS) && j < min(spike_cnt[rr], MLBP_SPIKE_SLOTS)) {
+        if (i < ncs && j < nrs) {
             const int g1 = gap1[f];
             const int a = spike_entries[(size_t)cr * MLBP_SPIKE_SLOTS + i].x, b = spike_entries[(size_t)rr * MLBP_SPIKE_SLOTS + j].x;
             const double w = (double)alpha * (double)(__half2float(ch[a]) + __half2float(cl[a])) *

@@ -43,28 +43,48 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
         __syncthreads();
         float *drow = D + (d_row0 + (int64_t)(row - a0)) * (int64_t)ldd;
         // rows are padded to a multiple of 64 elements: whole chunks of 8 (the padding of the planes is zero)
-        for (int c8 = threadIdx.x; c8 < (ldv >> 3); c8 += SP_THREADS) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int s = 0; s < n; ++s) {
-                const size_t o = (size_t)s_col[s] * ldv + 8 * (size_t)c8;
-                const uint4 h = __ldg(reinterpret_cast<const uint4 *>(Bt_hi + o)), l = __ldg(reinterpret_cast<const uint4 *>(Bt_lo + o));
-                const __half2 *hh = reinterpret_cast<const __half2 *>(&h), *ll = reinterpret_cast<const __half2 *>(&l);
-                const float w = s_lo[s];
+        // two 8-element chunks per thread and iteration: all loads of both are issued before the first store
+        for (int c8 = threadIdx.x; c8 < (ldv >> 3); c8 += 2 * SP_THREADS) {
+            const int cc[2] = {c8, c8 + SP_THREADS};
+            const bool on1 = cc[1] < (ldv >> 3);
+            float acc[2][8];
+            float4 x[2], y[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 a = __half22float2(hh[q]), b = __half22float2(ll[q]);
-                    acc[2 * q] = fmaf(w, a.x + b.x, acc[2 * q]);
-                    acc[2 * q + 1] = fmaf(w, a.y + b.y, acc[2 * q + 1]);
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[u][q] = 0.f;
+                if (u == 0 || on1) {
+                    const float4 *d4 = reinterpret_cast<const float4 *>(drow + 8 * (size_t)cc[u]);
+                    x[u] = d4[0]; y[u] = d4[1];
                 }
             }
-            float4 *d4 = reinterpret_cast<float4 *>(drow + 8 * (size_t)c8);
-            float4 x = d4[0], y = d4[1];
-            const int e = 8 * c8;
-            x.x += e + 0 < V ? alpha * acc[0] : 0.f; x.y += e + 1 < V ? alpha * acc[1] : 0.f;
-            x.z += e + 2 < V ? alpha * acc[2] : 0.f; x.w += e + 3 < V ? alpha * acc[3] : 0.f;
-            y.x += e + 4 < V ? alpha * acc[4] : 0.f; y.y += e + 5 < V ? alpha * acc[5] : 0.f;
-            y.z += e + 6 < V ? alpha * acc[6] : 0.f; y.w += e + 7 < V ? alpha * acc[7] : 0.f;
-            d4[0] = x; d4[1] = y;
+            for (int s = 0; s < n; ++s) {
+                const float w = s_lo[s];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 1 && !on1) continue;
+                    const size_t o = (size_t)s_col[s] * ldv + 8 * (size_t)cc[u];
+                    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(Bt_hi + o)), l = __ldg(reinterpret_cast<const uint4 *>(Bt_lo + o));
+                    const __half2 *hh = reinterpret_cast<const __half2 *>(&h), *ll = reinterpret_cast<const __half2 *>(&l);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 a = __half22float2(hh[q]), b = __half22float2(ll[q]);
+                        acc[u][2 * q] = fmaf(w, a.x + b.x, acc[u][2 * q]);
+                        acc[u][2 * q + 1] = fmaf(w, a.y + b.y, acc[u][2 * q + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !on1) continue;
+                const int e = 8 * cc[u];
+                x[u].x += e + 0 < V ? alpha * acc[u][0] : 0.f; x[u].y += e + 1 < V ? alpha * acc[u][1] : 0.f;
+                x[u].z += e + 2 < V ? alpha * acc[u][2] : 0.f; x[u].w += e + 3 < V ? alpha * acc[u][3] : 0.f;
+                y[u].x += e + 4 < V ? alpha * acc[u][4] : 0.f; y[u].y += e + 5 < V ? alpha * acc[u][5] : 0.f;
+                y[u].z += e + 6 < V ? alpha * acc[u][6] : 0.f; y[u].w += e + 7 < V ? alpha * acc[u][7] : 0.f;
+                float4 *d4 = reinterpret_cast<float4 *>(drow + 8 * (size_t)cc[u]);
+                d4[0] = x[u]; d4[1] = y[u];
+            }
         }
     }
 }

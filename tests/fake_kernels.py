@@ -29,6 +29,26 @@ def _split(x):
     return hi, lo
 
 
+def _cell_hash(a, b):
+    """csrc/tables.cu cell_hash"""
+    with np.errstate(over='ignore'):
+        h = (a.astype(np.uint32) * np.uint32(0x9E3779B1) + b.astype(np.uint32) * np.uint32(0x85EBCA77)).astype(np.uint32)
+        h ^= h >> np.uint32(15); h = (h * np.uint32(0x2C1B3C6D)).astype(np.uint32)
+        h ^= h >> np.uint32(12); h = (h * np.uint32(0x297A2D39)).astype(np.uint32)
+        h ^= h >> np.uint32(15)
+    return h
+
+
+def _split_stochastic(x, a, b, plane):
+    """K2's table split: the hi half is rounded stochastically (csrc/tables.cu half_stochastic), lo = RN(x - hi)"""
+    x32 = x.astype(np.float32)
+    r = (_cell_hash(a, b) >> np.uint32(3 * plane)) & np.uint32(0x1FFF)
+    bits = ((x32.view(np.uint32) + r) & np.uint32(0xFFFFE000)).astype(np.uint32)
+    hi = bits.view(np.float32).astype(np.float16)          # exact: the low 13 mantissa bits are zero
+    lo = (x32 - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
 class FakeKernels(object):
     def __init__(self):
         self.device = torch.device('cpu')
@@ -46,8 +66,14 @@ class FakeKernels(object):
         T = np.exp(t[0] * P + t[2]); T1 = np.exp(t[0] * P + t[1] * W + t[2])
         mats = [T, T.T, T1, T1.T, T * P, T1 * P, T1 * W, (T * P).T, (T1 * P).T, (T1 * W).T]
         pl = _arr(planes, np.float16, (20 if with_grad else 8) * ps)
+        ai, bi = np.meshgrid(np.arange(V), np.arange(V), indexing='ij')
+        base = {0: 0, 1: 0, 2: 1, 3: 1, 4: 2, 5: 3, 6: 4, 7: 2, 8: 3, 9: 4}      # which of the five tables a plane pair holds
         for i, M in enumerate(mats[: 10 if with_grad else 4]):
-            hi, lo = _split(np.ldexp(M, scale_exp))
+            transposed = i in (1, 3, 7, 8, 9)
+            src = M.T if transposed else M                                       # the cell (a, b) of the un-transposed table
+            hi, lo = _split_stochastic(np.ldexp(src, scale_exp), ai, bi, base[i])
+            if transposed:
+                hi, lo = hi.T, lo.T
             for j, h in enumerate((hi, lo)):
                 v = pl[(2 * i + j) * ps:(2 * i + j) * ps + V * ldv].reshape(V, ldv)
                 v[:, :V] = h
