@@ -183,10 +183,14 @@ int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_t
  * run_if_set = 0 and all three passes with run_if_set = 1 -- on the PEAK word that mlbp_var_to_factor raises when a message
  * has more spikes than it can record (and the gradient rows, likewise, on the SPIKE word); exactly one of the two launches
  * does the work and no host synchronisation is needed.
- * gate == NULL runs unconditionally.  tcgen05 kernels only (impl 1, the SIMT cross-check, ignores the gate on the host: error). */
+ * gate == NULL runs unconditionally.  tcgen05 kernels only (impl 1, the SIMT cross-check, ignores the gate on the host: error).
+ * K range: [k0, k0 + k_len) in elements, multiples of 64 (k_len == 0: up to V).  A launch whose range does not start at 0
+ * ADDS its product to D.  The engine splits a long K (V = 50 000) into several launches: the CTA pairs of one launch drift
+ * apart in K and stop sharing operand slabs in L2, a kernel boundary re-aligns them.  CTA-pair kernel only.              */
 int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                                   const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
-                                  float alpha, int impl, const int32_t *gate, int run_if_set, void *stream);
+                                  float alpha, int impl, const int32_t *gate, int run_if_set, int k0, int k_len,
+                                  void *stream);
 /* K5.  VariableNode.get_marginal / get_posterior_probs / get_precision_counts / argmax
  *   (LBP.py:392-411, :247-259, :80-106).  Same group layout as K3, all inputs multiplied.
  *   logp[g] = log b[label] (-99.99 if b[label] == 0), top1[g] = argmax b (first index on ties),

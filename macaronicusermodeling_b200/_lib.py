@@ -22,7 +22,7 @@ _SIGNATURES = {
     'mlbp_spike_correct': 'ppppp' + 'ii' + 'ppii' + 'plif' + 'p',
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
-    'mlbp_factor_to_var_gemm_gated': 'pplii' + 'ppii' + 'plifi' + 'pip',
+    'mlbp_factor_to_var_gemm_gated': 'pplii' + 'ppii' + 'plifi' + 'pi' + 'ii' + 'p',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppf' + 'iff' + 'ppppp' + 'p',
     'mlbp_rescore_candidates': 'ippp' + 'pppp' + 'ppii' + 'pppl' + 'pii' + 'ppff' + 'f' + 'ppp' + 'p',
     'mlbp_zero_words': 'pip',

@@ -399,7 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES, A_T,
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                            float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
-                           int m_pairs, int n_tiles, const int32_t *__restrict__ gate, int run_if_set,
+                           int m_pairs, int n_tiles, const int32_t *__restrict__ gate, int run_if_set, int kb0, int kb_n,
                            int *err_flag) {
     using C = PairCfg<STAGES, A_T, B_T>;
     // device-side launch decision (mlbp_factor_to_var_gemm_gated): every CTA of every pair reads the same word, written by an
@@ -434,7 +434,10 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
     const int p_blk = first_p + in_grp % gsize;
     const int n_blk = in_grp / gsize;
     const int m_blk = 2 * p_blk + (int)rank;                      // this CTA's 128-row tile
-    const int num_kb = (V + BK - 1) / BK;
+    // K range of this launch: k-blocks [kb0, kb0 + kb_n).  A long K (V = 50 000: 782 k-blocks) is issued as several launches
+    // that ADD into D (kb0 > 0): the CTA pairs of a launch drift apart in K and stop sharing A / B slabs in L2; a kernel
+    // boundary re-aligns them (same reason as the row slices of a level, see Engine._gemm_slice_rows).
+    const int num_kb = kb_n;
     const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
     const int n_valid = min(BN, V - n_blk * BN);
     const int n_cur = (n_valid + 15) & ~15;                       // UMMA N of this tile (cta_group::2: multiples of 16)
@@ -474,10 +477,11 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
                 if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes_cta);      // bytes of BOTH CTAs land on the leader
                 const uint32_t lb = full_bar(s) & PEER_BIT_MASK;
                 const uint32_t st = smem_base + (uint32_t)s * C::STAGE_BYTES;
-                tma_load_2d_pair(&tm_a_hi, lb, st, kb * BK, row_a);
-                if (a_terms == 2) tma_load_2d_pair(&tm_a_lo, lb, st + C::A_BYTES, kb * BK, row_a);
-                tma_load_2d_pair(&tm_b_hi, lb, st + C::B_OFF, kb * BK, row_b);
-                if (b_terms == 2) tma_load_2d_pair(&tm_b_lo, lb, st + C::B_OFF + C::B_BYTES, kb * BK, row_b);
+                const int kc = (kb0 + kb) * BK;
+                tma_load_2d_pair(&tm_a_hi, lb, st, kc, row_a);
+                if (a_terms == 2) tma_load_2d_pair(&tm_a_lo, lb, st + C::A_BYTES, kc, row_a);
+                tma_load_2d_pair(&tm_b_hi, lb, st + C::B_OFF, kc, row_b);
+                if (b_terms == 2) tma_load_2d_pair(&tm_b_lo, lb, st + C::B_OFF + C::B_BYTES, kc, row_b);
             }
         } else if (warp == 1 && lane == 0 && rank == 0) {
             // ===================== MMA issuer (leader only, for both SMs) =====================
@@ -549,6 +553,10 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
                     float4 o;                                     // columns >= V (row padding) are written as zeros
                     o.x = nc + 0 < V ? acc[4 * j + 0] * alpha : 0.f; o.y = nc + 1 < V ? acc[4 * j + 1] * alpha : 0.f;
                     o.z = nc + 2 < V ? acc[4 * j + 2] * alpha : 0.f; o.w = nc + 3 < V ? acc[4 * j + 3] * alpha : 0.f;
+                    if (kb0 > 0) {                                // a later K range of a split launch: add to what is there
+                        const float4 p = *reinterpret_cast<const float4 *>(drow + nc);
+                        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                    }
                     *reinterpret_cast<float4 *>(drow + nc) = o;
                 }
             }
@@ -657,7 +665,7 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
 template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE = false>
 static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                          const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
-                         const int32_t *gate, int run_if_set, cudaStream_t st) {
+                         const int32_t *gate, int run_if_set, int kb0, int kb_n, cudaStream_t st) {
     using C = PairCfg<STAGES, A_T, B_T>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
@@ -680,7 +688,7 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
     gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, gate, run_if_set, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, gate, run_if_set, kb0, kb_n, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -694,9 +702,9 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false, int CHUNK_11 = CHUNK_KB>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                        const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
-                       int b_terms, const int32_t *gate, int run_if_set, cudaStream_t st) {
+                       int b_terms, const int32_t *gate, int run_if_set, int kb0, int kb_n, cudaStream_t st) {
 #define MLBP_PAIR(S, AT, BT, CH) \
-    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, gate, run_if_set, st)
+    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, gate, run_if_set, kb0, kb_n, st)
     if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2, CHUNK_KB);
     if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2, CHUNK_KB);
     if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1, CHUNK_KB);
@@ -712,7 +720,7 @@ extern "C" int mlbp_gemm_barrier_timeout_code(void) { return g_err_flag ? *g_err
 
 static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
                          const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int impl,
-                         const int32_t *gate, int run_if_set, void *stream) {
+                         const int32_t *gate, int run_if_set, int k0, int k_len, void *stream) {
     if (n_rows == 0) return MLBP_OK;
     MLBP_CHECK_ARG(A_hi && A_lo && B_hi && B_lo && D, "factor_to_var_gemm: null pointer");
     MLBP_CHECK_ARG(n_rows > 0 && V > 0 && a_row0 >= 0 && a_row0 + (int64_t)n_rows <= a_rows_total,
@@ -723,8 +731,16 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
                    (reinterpret_cast<uintptr_t>(B_hi) % 128) == 0 && (reinterpret_cast<uintptr_t>(B_lo) % 128) == 0 &&
                    (reinterpret_cast<uintptr_t>(D) % 16) == 0, "factor_to_var_gemm: misaligned buffer");
     cudaStream_t st = as_stream(stream);
+    // K range [k0, k0 + k_len) in elements (k_len == 0: all of K); a range that does not start at 0 ADDS to D
+    const int kb_all = (V + 63) / 64;
+    MLBP_CHECK_ARG(k0 >= 0 && k_len >= 0 && (k0 % 64) == 0 && (k_len % 64 == 0 || k0 + k_len >= V) && k0 < V + 64,
+                   "factor_to_var_gemm: K range [%d, +%d) must be aligned to 64 elements", k0, k_len);
+    const int kb0 = k0 / 64, kb_n = k_len == 0 ? kb_all - kb0 : ((k0 + k_len >= V ? kb_all : (k0 + k_len) / 64) - kb0);
+    const bool whole_k = kb0 == 0 && kb_n == kb_all;
     const int a_terms = (impl & MLBP_GEMM_A_HI_ONLY) ? 1 : 2, b_terms = (impl & MLBP_GEMM_B_HI_ONLY) ? 1 : 2;
     impl &= ~(MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY);
+    MLBP_CHECK_ARG(whole_k || ((impl == 0 && V > 2048) || impl == 2), "factor_to_var_gemm: only the CTA-pair kernel takes a partial K range");
+    MLBP_CHECK_ARG(kb_n > 0, "factor_to_var_gemm: empty K range");
     if (impl == 1) {
         MLBP_CHECK_ARG(gate == nullptr, "factor_to_var_gemm_gated: the SIMT cross-check kernel has no device-side gate");
         return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
@@ -733,9 +749,9 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 #define MLBP_TC(BN_, ST_, CH_) return launch_tc<BN_, ST_, CH_>(MLBP_ARGS, gate, run_if_set, st)
     switch (impl) {
         case 0:                                       // product configuration: CTA-pair kernel for large V
-            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, gate, run_if_set, st);
+            if (V > 2048) return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);
             MLBP_TC(128, 3, 2);
-        case 2: return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, gate, run_if_set, st);   // the CTA-pair kernel at any V (tests)
+        case 2: return launch_pair<2, 3, 4, 6, true, 4>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);   // the CTA-pair kernel at any V (tests)
         case 3: MLBP_TC(128, 3, 2);                                                                        // the one-CTA kernel at any V (tests)
 #ifdef MLBP_PROBES                                    // variants for scripts/gemm_probe.py only (build with -DMLBP_PROBES)
         case 10: MLBP_TC(256, 2, 1);
@@ -746,12 +762,12 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
         case 15: MLBP_TC(128, 3, 2);
         case 16: MLBP_TC(128, 3, 4);
         case 17: MLBP_TC(128, 3, 1 << 20);
-        case 30: return launch_pair<2>(MLBP_ARGS, gate, run_if_set, st);
-        case 31: return launch_pair<1>(MLBP_ARGS, gate, run_if_set, st);
-        case 33: return launch_pair<2, 3, 4, 6, true>(MLBP_ARGS, gate, run_if_set, st);       // one-pass rows drained every 2 too
-        case 34: return launch_pair<4, 3, 4, 6, true>(MLBP_ARGS, gate, run_if_set, st);       // all rows drained every 4 k-blocks
-        case 35: return launch_pair<2, 3, 4, 6, true, 8>(MLBP_ARGS, gate, run_if_set, st);    // one-pass rows drained every 8
-        case 32: return launch_pair<2, 2, 3, 3>(MLBP_ARGS, gate, run_if_set, st);
+        case 30: return launch_pair<2>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);
+        case 31: return launch_pair<1>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);
+        case 33: return launch_pair<2, 3, 4, 6, true>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);       // one-pass rows drained every 2 too
+        case 34: return launch_pair<4, 3, 4, 6, true>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);       // all rows drained every 4 k-blocks
+        case 35: return launch_pair<2, 3, 4, 6, true, 8>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);    // one-pass rows drained every 8
+        case 32: return launch_pair<2, 2, 3, 3>(MLBP_ARGS, gate, run_if_set, kb0, kb_n, st);
         case 20: return launch_tc<256, 4, 4, 32>(MLBP_ARGS, gate, run_if_set, st);
         case 21: return launch_tc<256, 4, 2, 32>(MLBP_ARGS, gate, run_if_set, st);
         case 22: return launch_tc<128, 6, 4, 32>(MLBP_ARGS, gate, run_if_set, st);
@@ -767,12 +783,12 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
                                        int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
                                        int64_t d_row0, int ldd, float alpha, int impl, void *stream) {
-    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, nullptr, 0, stream);
+    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, nullptr, 0, 0, 0, stream);
 }
 
 extern "C" int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
                                              int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
                                              int64_t d_row0, int ldd, float alpha, int impl, const int32_t *gate,
-                                             int run_if_set, void *stream) {
-    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, gate, run_if_set, stream);
+                                             int run_if_set, int k0, int k_len, void *stream) {
+    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, gate, run_if_set, k0, k_len, stream);
 }

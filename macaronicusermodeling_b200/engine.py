@@ -220,7 +220,8 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None, msg_passes=None, tau=2e-4, tau_label=1e-4, peak_mult=16.0, one_pass_min_v=4096):
+                 gemm_slice_pairs=None, msg_passes=None, tau=2e-4, tau_label=1e-4, peak_mult=16.0, one_pass_min_v=4096,
+                 gemm_k_chunks=None):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
         self.model = model if isinstance(model, Model) else Model.from_dict(model, self.device)
@@ -233,6 +234,12 @@ class Engine(object):
         self.grad_a_terms = int(grad_a_terms)
         self.grad_b_terms = int(grad_b_terms)     # 1: the table's lo half is dropped too where grad_one_pass_ok (set_theta)
         self.gemm_slice_rows = self._gemm_slice_rows(gemm_slice_pairs)
+        # K ranges of one GEMM launch (elements, multiples of 64): a long contraction (V = 50 000: 782 k-blocks) is issued as
+        # several launches that add into D -- the CTA pairs of a launch drift apart in K and stop sharing operand slabs in
+        # L2; a kernel boundary re-aligns them, exactly as the row slices above do.  About 200 k-blocks per launch.
+        n_k = max(1, -(-self.V // 12800)) if (self.V > 16384 and (gemm_impl & 0xff) == 0 and gemm_k_chunks is None) else int(gemm_k_chunks or 1)
+        step = round_up(-(-self.V // n_k), 64)
+        self.gemm_k_ranges = [(k0, min(step, self.V - k0)) for k0 in range(0, self.V, step)] if n_k > 1 else [(0, 0)]
         # Message rows with TWO tensor-core passes (A_hi . (B_hi + B_lo): the lo half of the message is dropped) plus an exact
         # re-score of every near-tied decision (csrc/rescore.cu).  Why this is safe: a rounding error upstream is damped by
         # every later contraction (a message D = T a averages V terms), so the only error of the two-pass scheme that reaches
@@ -567,10 +574,19 @@ class Engine(object):
                     if gated:
                         # decided on the device: the reduced-pass variant while the gate word is clear, else the fallback
                         gate, fallback = gated if isinstance(gated, tuple) else (peak_flag, 0)
-                        for fl, run_if_set in ((impl_flags, 0), (fallback, 1)):
+                        for k0, k_len in self.gemm_k_ranges:
+                            for fl, run_if_set in ((impl_flags, 0), (fallback, 1)):
+                                k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
+                                       _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | fl, gate, run_if_set,
+                                       k0, k_len)
+                            self.launches += 2
+                        self.launches -= 1
+                    elif len(self.gemm_k_ranges) > 1:
+                        for k0, k_len in self.gemm_k_ranges:
                             k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
-                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | fl, gate, run_if_set)
-                        self.launches += 1
+                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags, None, 0, k0, k_len)
+                            self.launches += 1
+                        self.launches -= 1
                     else:
                         k.call('mlbp_factor_to_var_gemm', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
                                _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags)

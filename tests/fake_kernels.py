@@ -263,20 +263,25 @@ class FakeKernels(object):
             L[r, :V][drop] = 0
 
     def mlbp_factor_to_var_gemm(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
-                                impl):
-        H = _arr(A_hi, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, :V].astype(np.float64)
-        L = _arr(A_lo, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, :V].astype(np.float64)
-        Bh = _arr(B_hi, np.float16, V * ldv).reshape(V, ldv)[:, :V].astype(np.float64)
-        Bl = _arr(B_lo, np.float16, V * ldv).reshape(V, ldv)[:, :V].astype(np.float64)
+                                impl, k0=0, k_len=0):
+        k1 = V if k_len == 0 else min(V, k0 + k_len)                # K range of this launch; k0 > 0 adds to D
+        H = _arr(A_hi, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, k0:k1].astype(np.float64)
+        L = _arr(A_lo, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, k0:k1].astype(np.float64)
+        Bh = _arr(B_hi, np.float16, V * ldv).reshape(V, ldv)[:, k0:k1].astype(np.float64)
+        Bl = _arr(B_lo, np.float16, V * ldv).reshape(V, ldv)[:, k0:k1].astype(np.float64)
         out = H @ Bh.T + (0.0 if impl & 512 else H @ Bl.T) + (0.0 if impl & 256 else L @ Bh.T)   # MLBP_GEMM_{A,B}_HI_ONLY
         Dm = _arr(D, np.float32, (d_row0 + n_rows) * ldd).reshape(-1, ldd)
-        Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
+        if k0 > 0:
+            Dm[d_row0:d_row0 + n_rows, :V] += (alpha * out).astype(np.float32)
+        else:
+            Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
 
     def mlbp_factor_to_var_gemm_gated(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
-                                      impl, gate, run_if_set):
+                                      impl, gate, run_if_set, k0=0, k_len=0):
         if gate is not None and gate.value and (int(_arr(gate, np.int32, 1)[0]) != 0) != (run_if_set != 0):
             return
-        self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl)
+        self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl,
+                                     k0, k_len)
 
     def mlbp_spike_correct(self, words, cnt, entries, rows, n_list, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha):
         w = _arr(words, np.int32, 5)

@@ -263,3 +263,26 @@ def test_one_pass_gradient_rows_restore_spike_cells():
     # V = 160 is 29 x smaller than the smallest vocabulary this scheme runs at: the un-spiky remainder (elements up to 16 / V = 0.1
     # of the mass) still carries visible rounding here; it shrinks like sqrt(1 / V) (tests/test_gpu_gates.py asserts 1e-4 at V = 4608)
     assert err['one_cells'] < 3e-4 and err['one_cells'] < 0.5 * err['one_raw']
+
+
+def test_k_range_launches_are_transparent():
+    """Engine.gemm_k_ranges: a level's GEMM issued as several launches over K ranges that add into D (done at V = 50 000, where
+    one launch over 782 k-blocks lets the CTA pairs drift apart) gives the same messages up to the fp32 rounding of the partial sums"""
+    model = synth.make_model(200, 16, seed=6)
+    sents = synth.make_corpus(model, 6, k=5, g=1, seed=5)
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=2))
+    te, td = [0.4, 0.3, 0.0], [0.5, 0.2, 0.1, 0.1, 0.1, 0.0]
+    res = []
+    for chunks in (None, 3):
+        eng = Engine(model, kernels=FakeKernels(), gemm_k_chunks=chunks)
+        assert (len(eng.gemm_k_ranges) > 1) == bool(chunks)
+        if chunks:
+            assert sum(n for _, n in eng.gemm_k_ranges) == 200 and all(k0 % 64 == 0 for k0, _ in eng.gemm_k_ranges)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_beliefs=True)
+        res.append((r.grad.numpy(), r.logp.numpy(), r.top1.numpy(), r.beliefs.numpy()[:, :200]))
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    np.testing.assert_allclose(res[0][3], res[1][3], rtol=2e-6)
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)

@@ -178,7 +178,7 @@ def test_gated_gemm_runs_only_when_the_device_flag_matches(lib):
         D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
         for impl, run_if_set in ((256, 0), (0, 1)):               # what Engine issues for one slice of message rows
             _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, impl,
-                                                         P(gate), run_if_set, S()))
+                                                         P(gate), run_if_set, 0, 0, S()))
         torch.cuda.synchronize()
         got = D.cpu().numpy()[:, :V]
         want, other = (ref3, ref2) if flag else (ref2, ref3)
@@ -187,7 +187,7 @@ def test_gated_gemm_runs_only_when_the_device_flag_matches(lib):
     # nothing runs when neither launch matches
     D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
     gate[0] = 1
-    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 256, P(gate), 0, S()))
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 256, P(gate), 0, 0, 0, S()))
     torch.cuda.synchronize()
     assert (D == -7.0).all()
     assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
@@ -299,7 +299,7 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     cnt, ent, rows = cnt.cuda(), ent.cuda(), rows.cuda()
     D = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
     n_blk = M - a0
-    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D), 1, ld, 0.5, 256, P(words), 0, S()))
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D), 1, ld, 0.5, 256, P(words), 0, 0, 0, S()))
     before = D.clone()
     _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, S()))
     torch.cuda.synchronize()
@@ -322,3 +322,24 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, S()))
     torch.cuda.synchronize()
     assert torch.equal(D2, before)
+
+
+def test_gemm_k_ranges_accumulate(lib):
+    """a long contraction issued as several launches over K ranges (the engine does it at V = 50 000): ranges that do not start
+    at 0 add to D; the result equals one launch up to the fp32 rounding of the partial sums"""
+    M, V = 300, 2500
+    rng = np.random.default_rng(4)
+    A = rng.random((M, V)) * 2.0 ** 14 / V * 2
+    B = np.exp(rng.normal(size=(V, V)) * 0.5) * 8.0
+    Ah, Al, Ax, ld = split_planes(A)
+    Bh, Bl, Bx, _ = split_planes(B)
+    ref = Ax @ Bx.T
+    D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
+    for k0, k_len in ((0, 896), (896, 896), (1792, 708)):
+        _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 2, None, 0,
+                                                     k0, k_len if k0 + k_len < V else 0, S()))
+    torch.cuda.synchronize()
+    got = D.cpu().numpy()[:, :V]
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
+    assert (D.cpu().numpy()[:, V:] == 0).all()
+    assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
