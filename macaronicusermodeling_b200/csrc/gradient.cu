@@ -36,13 +36,45 @@ pair_expectations_kernel(const int32_t *__restrict__ c_row, const int32_t *__res
         ncs = min(spike_cnt[c_row[f]], MLBP_SPIKE_SLOTS);
         nrs = min(spike_cnt[r_row[f]], MLBP_SPIKE_SLOTS);
     }
+    // 8 consecutive elements per thread and step: 16-byte loads of the fp16 rows, two float4 per D row; rows are padded to a
+    // multiple of 64 elements, so whole chunks (the tail chunk is masked: the padding of the A rows is never written).  All
+    // loads of a step are independent -- the kernel is a stream of ~124 KB per factor and lives on memory-level parallelism.
     float zf = 0.f, n1f = 0.f, n2f = 0.f;
-    for (int e = threadIdx.x; e < V; e += blockDim.x) {
-        const float c = __half2float(ch[e]) + __half2float(cl[e]);
-        const float zz = zc ? c : __half2float(zh[e]) + __half2float(zl[e]);
-        zf = fmaf(zz, __ldg(u0 + e), zf);
-        n1f = fmaf(c, __ldg(u1 + e), n1f);
-        if (u2) n2f = fmaf(c, __ldg(u2 + e), n2f);
+    const int n8 = (V + 7) >> 3;
+    for (int k8 = threadIdx.x; k8 < n8; k8 += blockDim.x) {
+        const uint4 ch8 = __ldg(reinterpret_cast<const uint4 *>(ch) + k8), cl8 = __ldg(reinterpret_cast<const uint4 *>(cl) + k8);
+        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(u0) + 2 * k8), a1 = __ldg(reinterpret_cast<const float4 *>(u0) + 2 * k8 + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(u1) + 2 * k8), b1 = __ldg(reinterpret_cast<const float4 *>(u1) + 2 * k8 + 1);
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        if (u2) { c0 = __ldg(reinterpret_cast<const float4 *>(u2) + 2 * k8); c1 = __ldg(reinterpret_cast<const float4 *>(u2) + 2 * k8 + 1); }
+        uint4 zh8 = ch8, zl8 = cl8;
+        if (!zc) { zh8 = __ldg(reinterpret_cast<const uint4 *>(zh) + k8); zl8 = __ldg(reinterpret_cast<const uint4 *>(zl) + k8); }
+        float c[8], zz[8];
+        {
+            const __half2 *hh = reinterpret_cast<const __half2 *>(&ch8), *ll = reinterpret_cast<const __half2 *>(&cl8);
+            const __half2 *zhh = reinterpret_cast<const __half2 *>(&zh8), *zll = reinterpret_cast<const __half2 *>(&zl8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 h = __half22float2(hh[q]), l = __half22float2(ll[q]);
+                const float2 zh2 = __half22float2(zhh[q]), zl2 = __half22float2(zll[q]);
+                c[2 * q] = h.x + l.x; c[2 * q + 1] = h.y + l.y;
+                zz[2 * q] = zh2.x + zl2.x; zz[2 * q + 1] = zh2.y + zl2.y;
+            }
+        }
+        if (8 * k8 + 8 > V) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (8 * k8 + i >= V) { c[i] = 0.f; zz[i] = 0.f; }
+        }
+        const float ua[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float ub[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float uc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            zf = fmaf(zz[i], ua[i], zf);
+            n1f = fmaf(c[i], ub[i], n1f);
+            n2f = fmaf(c[i], uc[i], n2f);
+        }
     }
     // One-pass gradient rows (u = alpha * r_hi . B_hi) drop the lo half of the table planes.  Its rounding averages away
     // over the cells a belief spreads over -- except where BOTH messages have a spike: those few cells are restored here,
@@ -183,6 +215,9 @@ extern "C" int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const
     if (n_factors == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_factors > 0 && c_row && z_row && u0_row && u1_row && u2_row && A_hi && A_lo && D && stats,
                    "pair_expectations: null pointer");
+    MLBP_CHECK_ARG((ldv % 8) == 0 && ldv >= V && ((reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) |
+                                                  reinterpret_cast<uintptr_t>(D)) % 16) == 0,
+                   "pair_expectations: rows must be 16-byte aligned and padded to a multiple of 8 elements");
     MLBP_CHECK_ARG(!spike_words || (r_row && pair_gap1 && spike_cnt && spike_entries && planes),
                    "pair_expectations: the spike-cell correction needs r_row, pair_gap1, the spike lists and the table planes");
     pair_expectations_kernel<<<n_factors, 256, 0, as_stream(stream)>>>(c_row, z_row, u0_row, u1_row, u2_row,

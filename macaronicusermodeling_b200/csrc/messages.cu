@@ -123,6 +123,31 @@ __device__ __noinline__ void k3_record_spike(const K3Spikes sp, const int32_t *_
     }
 }
 
+// Slow path of the resident kernel's phase 2, taken for a column pair in which some output exceeded the spike limit: the
+// leave-one-out products are formed again from shared memory WITH THE SAME OPERATIONS IN THE SAME ORDER as the unrolled fast
+// path (prefix from the left, suffix from the right, scale last), so every x is bit-identical to the value that was split
+// and stored, and x - fp16(x) is exactly the lo part a two-pass row drops.  Rolled loops: compact code, no register arrays.
+template <int NIN>
+__device__ __noinline__ void k3_mark_column_pair(const float2 *col, int stride, unsigned omask, const float *s_scale, float uni,
+                                                 float limit, bool odd, int column, int *s_nmark, K3Mark *s_mark,
+                                                 const int *s_d0, const int *s_nd) {
+#pragma unroll 1
+    for (int j = 0; j < NIN; ++j) {
+        if (!((omask >> j) & 1u)) continue;
+        float2 p = col[0];
+#pragma unroll 1
+        for (int i = 0; i < j; ++i) p = __fmul2_rn(p, col[(1 + i) * stride]);
+        float2 sfx = make_float2(1.f, 1.f);
+#pragma unroll 1
+        for (int i = NIN - 1; i > j; --i) sfx = __fmul2_rn(sfx, col[(1 + i) * stride]);
+        const float sc = s_scale[j];
+        float2 x = __fmul2_rn(__fmul2_rn(p, sfx), make_float2(sc, sc));
+        if (!(sc > 0.f)) x = make_float2(uni, uni);
+        if (x.x > limit) k3_mark_spike(s_nmark, s_mark, s_d0[j], s_nd[j], column, x.x);
+        if (!odd && x.y > limit) k3_mark_spike(s_nmark, s_mark, s_d0[j], s_nd[j], column + 1, x.y);
+    }
+}
+
 // After a group's hot loop (all threads; the caller has synchronised the block): flush the marks of buffer `par`, one thread
 // per mark, taken from the END of the block (the first threads issue the next group's copies and must not wait for atomics).
 // No barrier here: the other buffer -- flushed one iteration ago, idle since -- is reset for the next group instead.
@@ -484,15 +509,15 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     #pragma unroll
                 for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
                 float2 suf = make_float2(1.f, 1.f);
+                bool spiky = false;
                 // one output: scale, split into fp16 hi / lo pairs, store to the first reader's row
                 auto emit = [&](int j, float2 sufj) {
                     const float sc = s_scale[j];
                     float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
                     if (!(sc > 0.f)) x = make_float2(uni, uni);
-                    if (fmaxf(x.x, x.y) > spike_limit) {                               // rare: a spike (see K3Spikes)
-                        if (x.x > spike_limit) k3_mark_spike(&s_nmark[b], s_mark[b], s_d0[b][j], s_nd[b][j], col0 + 2 * e2, x.x);
-                        if (!odd && x.y > spike_limit) k3_mark_spike(&s_nmark[b], s_mark[b], s_d0[b][j], s_nd[b][j], col0 + 2 * e2 + 1, x.y);
-                    }
+                    // spikes (see K3Spikes): only a predicate is accumulated here -- a branch per output put a reconvergence
+                    // point (BSSY / BSYNC) into every one of the 18 chains of a column pair (8 % of the kernel's stall samples)
+                    spiky = spiky || (fmaxf(x.x, x.y) > spike_limit);
                     const __half2 hi = __float22half2_rn(x);
                     const float2 back = __half22float2(hi);
                     const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
@@ -533,6 +558,9 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                         }
                     }
                 }
+                if (spiky)                                         // rare: find and mark the spikes of this column pair
+                    k3_mark_column_pair<NIN>(col, S >> 1, omask, s_scale, uni, spike_limit, odd, col0 + 2 * e2, &s_nmark[b], s_mark[b],
+                                             s_d0[b], s_nd[b]);
             }
         };
         if (multi) phase2(cuda::std::true_type{}); else phase2(cuda::std::false_type{});

@@ -234,10 +234,12 @@ class Engine(object):
         self.grad_a_terms = int(grad_a_terms)
         self.grad_b_terms = int(grad_b_terms)     # 1: the table's lo half is dropped too where grad_one_pass_ok (set_theta)
         self.gemm_slice_rows = self._gemm_slice_rows(gemm_slice_pairs)
-        # K ranges of one GEMM launch (elements, multiples of 64): a long contraction (V = 50 000: 782 k-blocks) is issued as
-        # several launches that add into D -- the CTA pairs of a launch drift apart in K and stop sharing operand slabs in
-        # L2; a kernel boundary re-aligns them, exactly as the row slices above do.  About 200 k-blocks per launch.
-        n_k = max(1, -(-self.V // 12800)) if (self.V > 16384 and (gemm_impl & 0xff) == 0 and gemm_k_chunks is None) else int(gemm_k_chunks or 1)
+        # K ranges of one GEMM launch (elements, multiples of 64): a long contraction can be issued as several launches that add
+        # into D (mlbp_factor_to_var_gemm_gated k0 / k_len).  The idea -- a kernel boundary re-aligns CTA pairs that drifted
+        # apart in K, as the row slices above do -- was MEASURED at V = 50 000 (782 k-blocks in four launches of 196) and did
+        # not pay: C5 25.8 vs 27.5 sentences/s, 970 vs 1 045 TFLOP/s executed (profiles/r2a_bench_c5_ab_k_ranges.txt): four
+        # epilogues and read-modify-writes of D per tile cost more than the re-alignment saves.  Off unless asked for.
+        n_k = int(gemm_k_chunks or 1)
         step = round_up(-(-self.V // n_k), 64)
         self.gemm_k_ranges = [(k0, min(step, self.V - k0)) for k0 in range(0, self.V, step)] if n_k > 1 else [(0, 0)]
         # Message rows with TWO tensor-core passes (A_hi . (B_hi + B_lo): the lo half of the message is dropped) plus an exact
