@@ -47,7 +47,7 @@ extern "C" {
 #define MLBP_N_SUMS           7   /* per-theta sum vectors written by mlbp_build_pairwise_tables                */
 #define MLBP_D_CONST_ROWS     5   /* D rows 1..4 hold the constant messages of the 4 message tables (row 0 spare) */
 #define MLBP_A_SCALE_LOG2    14   /* var->factor rows are stored as 2^14 * normalised message, split hi + lo fp16 */
-#define MLBP_SPIKE_SLOTS      4   /* spikes recorded per message row (mlbp_var_to_factor / mlbp_spike_correct)   */
+#define MLBP_SPIKE_SLOTS      4   /* spikes recorded per A row (mlbp_spike_scan / mlbp_spike_correct)             */
 
 const char *mlbp_last_error(void);
 int mlbp_version(void);
@@ -128,31 +128,29 @@ int mlbp_fill_uniform_rows(void *A_hi, void *A_lo, int ldv, int V, const int32_t
  *   constant-one row D[0] in its place (messages are scale-free), so the caller keeps D row 0 filled with 1.0f.
  *   range_log2: caller's bound on |log2| of any product of one U element with max_in D elements; in [0, 100) the
  *   products are formed in fp32, otherwise (or negative = unknown) in fp64 (slow on B200: the fp64 pipe is narrow).
- *   Spike tracking (spike_words != NULL, else the other spike_* arguments are ignored).  A two-pass message row
- *   (MLBP_GEMM_A_HI_ONLY) drops the lo half of every message element; for the bulk of a message that rounding averages away
- *   in the contraction, for an element that carries more than spike_prob of the mass (a history feature's word, say) it
- *   does not.  For every such element written to an A row < n_spike_rows the kernel records
- *   (column, x - fp16(x)) in spike_entries[row][MLBP_SPIKE_SLOTS] (int32 pairs: column, float bits), counts them in
- *   spike_cnt[row] (zeroed by the caller per batch) and lists the rows that have spikes PER GEMM BLOCK: `blocks` is the
- *   plan's flat list of GEMM blocks (4 int32 each {table, first A row, first D row, rows}, ascending; n_blocks of them), the
- *   list of block b starts at spike_rows[first A row of b] and has spike_blk_cnt[b] entries (zeroed by the caller per
- *   batch).  mlbp_spike_correct restores the dropped contribution of a block's rows exactly, mlbp_pair_expectations the
- *   gradient stage's spike cells.  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
- *     [0] PEAK   set when a row has more spikes than slots: mlbp_factor_to_var_gemm_gated then keeps all three passes   (per theta)
- *     [2] the largest element seen so far, bits of the float 2^14 * probability (atomic max; diagnostics)               (per theta)
- *     [3] SPIKE  set when any spike was seen (diagnostics)                                                               (per theta)
- *     [4] number of rows with spikes (diagnostics)                                                                      (per batch) */
+ */
 int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                        const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                        const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
-                       void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
-                       int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows,
-                       int32_t *spike_blk_cnt, const int32_t *blocks, int n_blocks, void *stream);
+                       void *A_lo, int max_in, float range_log2, void *stream);
+/* K4a. Spikes of the var->factor messages in A rows [a_row0, a_row0 + n_rows) (one GEMM block; run before the block's GEMM).
+ *   A reduced-pass GEMM row (MLBP_GEMM_A_HI_ONLY) drops the lo half of every message element; for the bulk of a message that
+ *   rounding averages away in the contraction, for an element that carries more than spike_prob of the mass (a history
+ *   feature's word, say) it does not.  For every row the kernel files up to MLBP_SPIKE_SLOTS such elements as
+ *   (column, float bits of the A_lo value) in spike_entries[row][slot] (int32 pairs, ascending columns), writes their number
+ *   to spike_cnt[row] (MLBP_SPIKE_SLOTS + 1 = more than fit), and appends rows with spikes to block_rows[0 .. *block_n)
+ *   (optional; *block_n zeroed by the caller).  spike_words (5 device int32, zeroed by the caller per theta / batch as noted):
+ *     [0] PEAK   set when a row has more spikes than slots: mlbp_factor_to_var_gemm_gated then keeps the lo half        (per theta)
+ *     [2] the largest spike seen so far, bits of the float 2^14 * probability (atomic max; diagnostics)                 (per theta)
+ *     [3] SPIKE  set when any spike was seen (diagnostics)                                                               (per theta)
+ *     [4] number of rows with spikes (diagnostics)                                                                      (per batch) */
+int mlbp_spike_scan(const void *A_hi, const void *A_lo, int ldv, int V, int a_row0, int n_rows, float spike_prob,
+                    int32_t *spike_words, int32_t *spike_cnt, int32_t *spike_entries, int32_t *block_rows, int32_t *block_n,
+                    void *stream);
 /* K4b. Spike compensation of a GEMM block that dropped the lo half of A (rows [a_row0, a_row0 + n_rows) of A -> D rows d_row0 ..):
  *   D[r, n] += alpha * sum over the recorded spikes s of row r of  lo_s * B[n, col_s],  with B[n, col] read as row `col` of
  *   the TRANSPOSED table's plane pair Bt_hi / Bt_lo (MLBP_TABLE_T <-> TT, T1 <-> T1T, G <-> GT, G1 <-> G1T, G1W <-> G1WT).
- *   block_rows / block_n: this block's list of spiky rows and its length (spike_rows + a_row0 and spike_blk_cnt + b of
- *   mlbp_var_to_factor).  Returns at once (on the device) when spike_words[0] is set: the block then ran with the lo half.
+ *   block_rows / block_n: this block's list of spiky rows and its length (mlbp_spike_scan).  Returns at once (on the device) when spike_words[0] is set: the block then ran with the lo half.
  *   Spikes of a row are applied in ascending column order (deterministic).                                             */
 int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
                        const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi,
@@ -180,8 +178,8 @@ int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_t
                             float alpha, int impl, void *stream);
 /* The same launch, DECIDED ON THE DEVICE: every CTA first reads *gate (device int32) and returns at once unless
  * (*gate != 0) == (run_if_set != 0).  The engine issues a level's message rows twice -- two passes (A_HI_ONLY) with
- * run_if_set = 0 and all three passes with run_if_set = 1 -- on the PEAK word that mlbp_var_to_factor raises when a message
- * has more spikes than it can record (and the gradient rows, likewise, on the SPIKE word); exactly one of the two launches
+ * run_if_set = 0 and all three passes with run_if_set = 1 -- on the PEAK word that mlbp_spike_scan raises when a message has
+ * more spikes than it can record (the one-pass gradient rows fall back to two passes on the same word); exactly one of the two launches
  * does the work and no host synchronisation is needed.
  * gate == NULL runs unconditionally.  tcgen05 kernels only (impl 1, the SIMT cross-check, ignores the gate on the host: error).
  * K range: [k0, k0 + k_len) in elements, multiples of 64 (k_len == 0: up to V).  A launch whose range does not start at 0
@@ -230,7 +228,7 @@ int mlbp_rescore_candidates(int n_vars, const int32_t *flagged, const int32_t *n
  *   Spike cells (spike_words != NULL, else the seven arguments after stats are ignored): when the u rows come from ONE-pass
  *   gradient GEMMs (alpha * r_hi . B_hi) the lo half of the table planes is missing.  Its rounding averages away over the
  *   cells a belief spreads over, except where both messages have a spike; for those cells (spike lists of rows c_row[f]
- *   and r_row[f] from mlbp_var_to_factor) the kernel adds  alpha * c[a] * r_hi[b] * B_lo[a, b]  to the three sums, B = T / G /
+ *   and r_row[f] from mlbp_spike_scan) the kernel adds  alpha * c[a] * r_hi[b] * B_lo[a, b]  to the three sums, B = T / G /
  *   G1w planes of the factor's gap class (pair_gap1).  Skipped on the device when spike_words[0] (PEAK) is set.        */
 int mlbp_pair_expectations(int n_factors, const int32_t *c_row, const int32_t *z_row, const int32_t *u0_row,
                            const int32_t *u1_row, const int32_t *u2_row, const void *A_hi, const void *A_lo, const float *D,
@@ -252,7 +250,7 @@ int mlbp_gradient_reduce(int n_sent, const int32_t *sent_var_off, const int32_t 
  *   zeroed by the caller at the start of an SGD step; it is the buffer the NCCL all-reduce ships):
  *   [0..8] sum of grad[s][9], [9] sum of logp_sent, [10] #rank == 0, [11] #rank < 26, [12] #rank < 50, [13] n_vars, [14] n_sent;
  *   [15] = max([15], (spike_words[0] ? 1 : 0) + (spike_words[3] ? 2 : 0)) with peak_flag = the spike_words of
- *   mlbp_var_to_factor (which reduced-pass GEMM variants this rank ran).  grad / logp_sent / rank / peak_flag may be NULL.
+ *   mlbp_spike_scan (which reduced-pass GEMM variants this rank ran).  grad / logp_sent / rank / peak_flag may be NULL.
  *   One CTA, fixed summation order (deterministic).                                                              */
 int mlbp_batch_reduce(int n_sent, const double *grad, const double *logp_sent, int n_vars, const int32_t *rank,
                       const int32_t *peak_flag, double *out16, void *stream);

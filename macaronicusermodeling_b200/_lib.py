@@ -18,7 +18,8 @@ _SIGNATURES = {
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
     'mlbp_fill_uniform_rows': 'ppiipipp',
-    'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppif' + 'pf' + 'pppi' + 'ppi' + 'p',
+    'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppif' + 'p',
+    'mlbp_spike_scan': 'ppii' + 'iif' + 'ppppp' + 'p',
     'mlbp_spike_correct': 'ppppp' + 'ii' + 'ppii' + 'plif' + 'p',
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',

@@ -66,121 +66,18 @@ __device__ __forceinline__ void k3_store(float x, size_t first, int nd, const in
     }
 }
 
-// Spikes.  A two-pass message row (A_hi . B) drops the lo half of every message element.  For the bulk of a message that
-// rounding averages away in the contraction; for an element that carries a visible share of the mass (a "spike": more than
-// spike_limit, e.g. the word a history feature points at) it does not.  K3 therefore records, per A row, the spikes it writes
-// -- (column, x - fp16(x)) -- and mlbp_spike_correct adds  alpha * lo * T[:, column]  to the row's GEMM output afterwards: the
-// exact contribution of the dropped part, a few AXPYs instead of a third tensor-core pass over the whole level.
-// words (device int32): [0] PEAK  set when a row has more spikes than slots (message rows fall back to three passes),
-//                       [2] MAXBITS largest element seen (bits of 2^14 * probability; diagnostics),
-//                       [3] SPIKE set when any spike was seen (gradient rows keep the lo half of the table),
-//                       [4] number of rows in the spiky-row list.
-struct K3Spikes {
-    int32_t *words;          // nullptr: no tracking
-    int32_t *cnt;            // [n_rows] spikes recorded per A row (zeroed by the caller per batch)
-    int2 *entries;           // [n_rows][MLBP_SPIKE_SLOTS] (column, float bits of lo)
-    int32_t *rows;           // [n_rows] spiky rows, one list per GEMM block: the list of block b starts at rows[blocks[4b + 1]]
-    int32_t *blk_cnt;        // [n_blocks] length of each block's list (zeroed by the caller per batch)
-    const int32_t *blocks;   // [n_blocks][4] {table, first A row, first D row, rows} of every GEMM block, ascending in A rows
-    int n_blocks;
-    int n_rows;              // rows of the A buffers covered by cnt / entries / rows
-    float limit;             // 2^14 * probability above which an element is a spike
-};
-
-// A spike seen in the hot loop is only MARKED in shared memory (one shared-memory atomic); the marks of a group are flushed by
-// as many threads in parallel after the loop.  (All leave-one-out products of a variable peak at the same word, so the thread
-// that owns that column would otherwise pay ~18 global atomic round trips in a row: measured, K3 ran 35 % slower.)
-constexpr int K3_MAX_MARKS = 96;
-struct K3Mark { int d0, nd, col; float x; };
-
-__device__ __forceinline__ void k3_mark_spike(int *s_nmark, K3Mark *s_mark, int d0, int nd, int col, float x) {
-    const int k = atomicAdd(s_nmark, 1);
-    if (k < K3_MAX_MARKS) s_mark[k] = K3Mark{d0, nd, col, x};
-}
-
-__device__ __forceinline__ void k3_note_spike_size(const K3Spikes &sp, float x);
-
-__device__ __noinline__ void k3_record_spike(const K3Spikes sp, const int32_t *__restrict__ dest, int d0, int nd, int col, float x) {
-    const float lo = x - __half2float(__float2half_rn(x));        // what a two-pass row drops (exact in fp32)
-    sp.words[3] = 1;
-    k3_note_spike_size(sp, x);
-    for (int t = 0; t < nd; ++t) {
-        const int row = dest[d0 + t];
-        if (row >= sp.n_rows) continue;
-        const int slot = atomicAdd(&sp.cnt[row], 1);
-        if (slot == 0) {                                           // first spike of this row: list it with its GEMM block
-            int lo_b = 0, hi_b = sp.n_blocks - 1;
-            while (lo_b < hi_b) {                                  // last block whose first A row is <= row
-                const int mid = (lo_b + hi_b + 1) >> 1;
-                if (sp.blocks[4 * mid + 1] <= row) lo_b = mid; else hi_b = mid - 1;
-            }
-            if (sp.n_blocks > 0 && sp.blocks[4 * lo_b + 1] <= row && row < sp.blocks[4 * lo_b + 1] + sp.blocks[4 * lo_b + 3])
-                sp.rows[sp.blocks[4 * lo_b + 1] + atomicAdd(&sp.blk_cnt[lo_b], 1)] = row;
-            atomicAdd(&sp.words[4], 1);                            // (total, diagnostics)
-        }
-        if (slot < MLBP_SPIKE_SLOTS) sp.entries[(size_t)row * MLBP_SPIKE_SLOTS + slot] = make_int2(col, __float_as_int(lo));
-        else sp.words[0] = 1;
-    }
-}
-
-// Slow path of the resident kernel's phase 2, taken for a column pair in which some output exceeded the spike limit: the
-// leave-one-out products are formed again from shared memory WITH THE SAME OPERATIONS IN THE SAME ORDER as the unrolled fast
-// path (prefix from the left, suffix from the right, scale last), so every x is bit-identical to the value that was split
-// and stored, and x - fp16(x) is exactly the lo part a two-pass row drops.  Rolled loops: compact code, no register arrays.
-template <int NIN>
-__device__ __noinline__ void k3_mark_column_pair(const float2 *col, int stride, unsigned omask, const float *s_scale, float uni,
-                                                 float limit, bool odd, int column, int *s_nmark, K3Mark *s_mark,
-                                                 const int *s_d0, const int *s_nd) {
-#pragma unroll 1
-    for (int j = 0; j < NIN; ++j) {
-        if (!((omask >> j) & 1u)) continue;
-        float2 p = col[0];
-#pragma unroll 1
-        for (int i = 0; i < j; ++i) p = __fmul2_rn(p, col[(1 + i) * stride]);
-        float2 sfx = make_float2(1.f, 1.f);
-#pragma unroll 1
-        for (int i = NIN - 1; i > j; --i) sfx = __fmul2_rn(sfx, col[(1 + i) * stride]);
-        const float sc = s_scale[j];
-        float2 x = __fmul2_rn(__fmul2_rn(p, sfx), make_float2(sc, sc));
-        if (!(sc > 0.f)) x = make_float2(uni, uni);
-        if (x.x > limit) k3_mark_spike(s_nmark, s_mark, s_d0[j], s_nd[j], column, x.x);
-        if (!odd && x.y > limit) k3_mark_spike(s_nmark, s_mark, s_d0[j], s_nd[j], column + 1, x.y);
-    }
-}
-
-// After a group's hot loop (all threads; the caller has synchronised the block): flush the marks of buffer `par`, one thread
-// per mark, taken from the END of the block (the first threads issue the next group's copies and must not wait for atomics).
-// No barrier here: the other buffer -- flushed one iteration ago, idle since -- is reset for the next group instead.
-__device__ __forceinline__ void k3_flush_marks(const K3Spikes &sp, const int32_t *__restrict__ dest, int *s_nmark, K3Mark (*s_mark)[K3_MAX_MARKS],
-                                               int par) {
-    const int n = s_nmark[par];                                    // block-uniform
-    if (threadIdx.x == 0) s_nmark[par ^ 1] = 0;
-    if (n == 0) return;
-    if (n > K3_MAX_MARKS && threadIdx.x == 0) sp.words[0] = 1;     // more spikes than marks: three passes from here on
-    const int m = (int)blockDim.x - 1 - (int)threadIdx.x;
-    if (m < min(n, K3_MAX_MARKS)) k3_record_spike(sp, dest, s_mark[par][m].d0, s_mark[par][m].nd, s_mark[par][m].col, s_mark[par][m].x);
-}
-
-// the largest spike seen (diagnostics; positive floats order like their bit patterns)
-__device__ __forceinline__ void k3_note_spike_size(const K3Spikes &sp, float x) {
-    if (x == x) atomicMax(sp.words + 2, __float_as_int(x));
-}
-
 template <int NMAX, typename T, int OCC>
 __global__ void __launch_bounds__(K3_THREADS, OCC)
 var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                      const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                      const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
                      const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V,
-                     __half *__restrict__ A_hi, __half *__restrict__ A_lo, const K3Spikes sp) {
+                     __half *__restrict__ A_hi, __half *__restrict__ A_lo) {
     __shared__ const float *s_src[NMAX];
     __shared__ int s_d0[NMAX], s_nd[NMAX];
     __shared__ size_t s_first[NMAX];
     __shared__ double s_warp[K3_WARPS][NMAX];
     __shared__ float s_scale[NMAX];
-    __shared__ int s_nmark[2];
-    __shared__ K3Mark s_mark[1][K3_MAX_MARKS];
-    if (threadIdx.x == 0) s_nmark[0] = 0;
     const int g = blockIdx.x;
     const int i0 = grp_off[g], n = grp_off[g + 1] - i0;
     const float *urow = U + (size_t)grp_u[g] * ldv;
@@ -250,15 +147,10 @@ var_to_factor_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restric
             if (nd > 0) {
                 const float sc = s_scale[j];
                 const float x = sc > 0.f ? (float)(pre[j] * suf * (T)sc) : uni;
-                if (sp.words && x > sp.limit) k3_mark_spike(&s_nmark[0], s_mark[0], s_d0[j], nd, e, x);  // rare
                 k3_store(x, s_first[j] + e, nd, dest, s_d0[j], ldv, e, A_hi, A_lo);
             }
             suf *= (T)d[j];
         }
-    }
-    if (sp.words) {
-        __syncthreads();
-        k3_flush_marks(sp, dest, s_nmark, s_mark, 0);
     }
 }
 
@@ -300,7 +192,7 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                               const int32_t *__restrict__ in_row, const int32_t *__restrict__ dest_off,
                               const int32_t *__restrict__ dest, const int32_t *__restrict__ first_dest,
                               const int32_t *__restrict__ second_dest, const float *__restrict__ U, const float *__restrict__ D, int ldv, int V, int S,
-                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, const K3Spikes sp, long long *dbg) {
+                              __half *__restrict__ A_hi, __half *__restrict__ A_lo, long long *dbg) {
 #ifdef MLBP_K3_STAGE_TIMES                                      // scripts/k3_probe.py: cycles per stage, per CTA
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define K3_TICK(i) do { const long long tn_ = clock64(); tacc[i] += tn_ - tprev; tprev = tn_; } while (0)
@@ -316,9 +208,6 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     __shared__ double s_gather[2][8][NIN];                     // [exchange parity][source rank][output]
     __shared__ __align__(8) unsigned long long s_gbar[2];
     __shared__ float s_scale[NIN];
-    __shared__ int s_nmark[2];
-    __shared__ K3Mark s_mark[2][K3_MAX_MARKS];
-    if (threadIdx.x == 0) { s_nmark[0] = 0; s_nmark[1] = 0; }
     cg::cluster_group cl = cg::this_cluster();
     const unsigned C = cl.num_blocks(), q = cl.block_rank();
     const int n_clusters = gridDim.x / C;
@@ -383,7 +272,6 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     // loops are written as straight-line code (no branch on a value loaded inside the loop): measured with clock64
     // per stage, a data-dependent branch per input cost ~100 cycles per input and column pair.
     const int npair = (ncol + 1) >> 1;
-    const float spike_limit = sp.words ? sp.limit : __int_as_float(0x7f800000);   // +inf: no tracking, one compare per output pair
     for (; g < n_groups; g += n_clusters, b ^= 1) {
         if (ncol > 0) {
             if (threadIdx.x == 0)
@@ -509,15 +397,11 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
     #pragma unroll
                 for (int j = 0; j < NIN; ++j) { pre[j] = p; p = __fmul2_rn(p, d[j]); }
                 float2 suf = make_float2(1.f, 1.f);
-                bool spiky = false;
                 // one output: scale, split into fp16 hi / lo pairs, store to the first reader's row
                 auto emit = [&](int j, float2 sufj) {
                     const float sc = s_scale[j];
                     float2 x = __fmul2_rn(__fmul2_rn(pre[j], sufj), make_float2(sc, sc));
                     if (!(sc > 0.f)) x = make_float2(uni, uni);
-                    // spikes (see K3Spikes): only a predicate is accumulated here -- a branch per output put a reconvergence
-                    // point (BSSY / BSYNC) into every one of the 18 chains of a column pair (8 % of the kernel's stall samples)
-                    spiky = spiky || (fmaxf(x.x, x.y) > spike_limit);
                     const __half2 hi = __float22half2_rn(x);
                     const float2 back = __half22float2(hi);
                     const __half2 lo = __float22half2_rn(__fadd2_rn(x, make_float2(-back.x, -back.y)));
@@ -558,9 +442,6 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
                         }
                     }
                 }
-                if (spiky)                                         // rare: find and mark the spikes of this column pair
-                    k3_mark_column_pair<NIN>(col, S >> 1, omask, s_scale, uni, spike_limit, odd, col0 + 2 * e2, &s_nmark[b], s_mark[b],
-                                             s_d0[b], s_nd[b]);
             }
         };
         if (multi) phase2(cuda::std::true_type{}); else phase2(cuda::std::false_type{});
@@ -569,7 +450,6 @@ var_to_factor_resident_kernel(int n_groups, const int32_t *__restrict__ grp_u, c
             k3_copy_extras<NIN>(s_nd[b], s_d0[b], s_first[b], dest, ldv, col0, ncol, A_hi, A_lo);
         }
         __syncthreads();                                           // shared memory is reused by the next group
-        if (sp.words) k3_flush_marks(sp, dest, s_nmark, s_mark, b);
         K3_TICK(5);
     }
 #ifdef MLBP_K3_STAGE_TIMES
@@ -734,12 +614,10 @@ template <int NIN>
 static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, const int32_t *grp_u,
                                    const int32_t *grp_off, const int32_t *in_row, const int32_t *dest_off,
                                    const int32_t *dest, const int32_t *first_dest, const int32_t *second_dest, const float *U,
-                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo, const K3Spikes sp) {
+                                   const float *D, int ldv, int V, __half *A_hi, __half *A_lo) {
     // function attributes and occupancy are per DEVICE: a process that drives several GPUs configures each one
     static bool configured[MLBP_MAX_DEVICES] = {};
-    int dev = 0;
-    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
-    if (dev < 0 || dev >= MLBP_MAX_DEVICES) return cudaErrorInvalidDevice;
+    const int dev = current_device();
     auto kern = var_to_factor_resident_kernel<NIN>;
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_RESIDENT_SMEM);
@@ -770,7 +648,7 @@ static cudaError_t launch_resident(int n_groups, int C, int S, cudaStream_t st, 
     const int n_clusters = n_groups < resident[C] ? n_groups : resident[C];
     cfg.gridDim = dim3((unsigned)n_clusters * (unsigned)C);
     return cudaLaunchKernelEx(&cfg, kern, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv,
-                              V, S, A_hi, A_lo, sp, g_k3_dbg);
+                              V, S, A_hi, A_lo, g_k3_dbg);
 }
 
 constexpr int K3_RESIDENT_MAX_IN = 24;
@@ -778,9 +656,7 @@ constexpr int K3_RESIDENT_MAX_IN = 24;
 extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int32_t *grp_off, const int32_t *in_row,
                                   const int32_t *dest_off, const int32_t *dest, const int32_t *first_dest,
                                   const int32_t *second_dest, const float *U, const float *D, int ldv, int V, void *A_hi,
-                                  void *A_lo, int max_in, float range_log2, int32_t *spike_words, float spike_prob,
-                                  int32_t *spike_cnt, int32_t *spike_entries, int32_t *spike_rows, int n_spike_rows,
-                                  int32_t *spike_blk_cnt, const int32_t *blocks, int n_blocks, void *stream) {
+                                  void *A_lo, int max_in, float range_log2, void *stream) {
     if (n_groups == 0) return MLBP_OK;
     MLBP_CHECK_ARG(n_groups > 0 && grp_u && grp_off && in_row && dest_off && dest && first_dest && second_dest && U && D && A_hi && A_lo,
                    "var_to_factor: null pointer");
@@ -792,14 +668,6 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
         return MLBP_ERR_UNSUPPORTED;
     }
     cudaStream_t st = as_stream(stream);
-    MLBP_CHECK_ARG(!spike_words || (spike_cnt && spike_entries && spike_rows && n_spike_rows >= 0 && spike_prob > 0.f &&
-                                    n_blocks >= 0 && (n_blocks == 0 || (spike_blk_cnt && blocks))),
-                   "var_to_factor: spike tracking needs cnt, entries, rows and a positive threshold");
-    K3Spikes sp;
-    sp.words = spike_words; sp.cnt = spike_cnt; sp.entries = reinterpret_cast<int2 *>(spike_entries); sp.rows = spike_rows;
-    sp.n_rows = n_spike_rows;
-    sp.blk_cnt = spike_blk_cnt; sp.blocks = blocks; sp.n_blocks = n_blocks;
-    sp.limit = ldexpf(spike_prob, MLBP_A_SCALE_LOG2);              // rows are stored as 2^14 * probability
     // The resident single-read kernel runs whenever the products fit fp32 and the cluster's slices fit shared memory;
     // MLBP_K3_IMPL=1 forces the streaming two-read kernel (used by scripts/k3_probe.py to time both).
     const char *env_impl = getenv("MLBP_K3_IMPL");
@@ -817,7 +685,7 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
 #define MLBP_K3_RES(N)                                                                                             \
         case N:                                                                                                    \
             MLBP_CUDA(launch_resident<N>(n_groups, C, S, st, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, \
-                                         (__half *)A_hi, (__half *)A_lo, sp));                                     \
+                                         (__half *)A_hi, (__half *)A_lo));                                         \
             break;
         switch (nin) {
             MLBP_K3_RES(1) MLBP_K3_RES(2) MLBP_K3_RES(3) MLBP_K3_RES(4) MLBP_K3_RES(5) MLBP_K3_RES(6) MLBP_K3_RES(7)
@@ -834,13 +702,13 @@ extern "C" int mlbp_var_to_factor(int n_groups, const int32_t *grp_u, const int3
     do {                                                                                                         \
         if (fp32_ok && N <= 20)                                                                                  \
             var_to_factor_kernel<(N <= 20 ? N : 4), float, 3><<<n_groups, K3_THREADS, 0, st>>>(                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, sp); \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else if (fp32_ok)                                                                                        \
             var_to_factor_kernel<N, float, 1><<<n_groups, K3_THREADS, 0, st>>>(                                  \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, sp); \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
         else                                                                                                     \
             var_to_factor_kernel<N, double, 1><<<n_groups, K3_THREADS, 0, st>>>(                                 \
-                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo, sp); \
+                grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, (__half *)A_hi, (__half *)A_lo);           \
     } while (0)
     if (max_in <= 4) MLBP_K3_LAUNCH(4);
     else if (max_in <= 8) MLBP_K3_LAUNCH(8);

@@ -1,8 +1,17 @@
-// K4b: spike compensation of two-pass message rows.
+// K4a / K4b: spikes of the var->factor messages and their compensation in reduced-pass GEMM rows.
 //
 // A two-pass message GEMM (MLBP_GEMM_A_HI_ONLY) computes  D[r, :] = alpha * A_hi[r, :] . B'  and drops  A_lo[r, :] . B'.
-// For the elements of a message that carry a visible share of its mass (spikes, recorded by the var->factor kernel: see
-// K3Spikes in messages.cu) the dropped term is restored exactly here:
+// For the bulk of a message that rounding averages away in the contraction; for an element that carries a visible share of
+// the mass (a "spike": the word a history feature points at, say) it does not.
+//
+// K4a, spike_scan_kernel: one CTA per A row of a GEMM block, run right before the block's GEMM.  It streams the row's hi
+// half (16-byte loads), collects the elements above the limit, and files up to MLBP_SPIKE_SLOTS of them as
+// (column, A_lo value) in ascending column order -- the lo half is exactly what the dropped pass would have multiplied; rows
+// with spikes are appended to the block's list; a row with more spikes than slots raises the PEAK word (the gated GEMMs then
+// keep the lo half).  (Round 2 first recorded spikes inside the var->factor kernel; the extra code in its hot loop cost
+// that kernel 25 % -- more than this separate pass over the hi halves, 8.7 GB per micro-batch of C3, costs.)
+//
+// K4b, spike_correct_kernel: the dropped term of the recorded spikes is restored exactly:
 //     D[r, n] += alpha * sum_s lo_s * B[n, col_s]
 // B[n, col] for all n is row `col` of the TRANSPOSED table's plane pair (K2 stores both orientations K-major), so a spike costs
 // one contiguous row read (hi + lo) and the row's spikes share one read-modify-write of D[r, :].  Reference semantics are
@@ -17,6 +26,71 @@
 namespace mlbp {
 
 constexpr int SP_THREADS = 256;
+constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_MAX = 64;          // spikes of one row collected before the overflow is certain anyway
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+spike_scan_kernel(const __half *__restrict__ A_hi, const __half *__restrict__ A_lo, int ldv, int V, int a0, int n_rows,
+                  float limit, int32_t *__restrict__ words, int32_t *__restrict__ cnt, int2 *__restrict__ entries,
+                  int32_t *__restrict__ block_rows, int32_t *__restrict__ block_n) {
+    __shared__ int s_n;
+    __shared__ int s_col[SCAN_MAX];
+    const __half2 lim2 = __float2half2_rn(limit);
+    for (int row = a0 + blockIdx.x; row < a0 + n_rows; row += gridDim.x) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const uint4 *h8 = reinterpret_cast<const uint4 *>(A_hi + (size_t)row * ldv);
+        // the padding of an A row is never written (uninitialised): only whole chunks below V, then the tail element-wise
+        const int n8 = V >> 3;
+        for (int k8 = threadIdx.x; k8 < n8; k8 += SCAN_THREADS) {
+            const uint4 v = __ldg(h8 + k8);
+            const __half2 *p = reinterpret_cast<const __half2 *>(&v);
+            const __half2 m = __hmax2(__hmax2(p[0], p[1]), __hmax2(p[2], p[3]));
+            const bool any = __hgt(__hmax(__low2half(m), __high2half(m)), __low2half(lim2));
+            if (any) {                                             // rare
+                const __half *e = reinterpret_cast<const __half *>(&v);
+                for (int i = 0; i < 8; ++i)
+                    if (__half2float(e[i]) > limit) {
+                        const int k = atomicAdd(&s_n, 1);
+                        if (k < SCAN_MAX) s_col[k] = 8 * k8 + i;
+                    }
+            }
+        }
+        for (int c = 8 * n8 + threadIdx.x; c < V; c += SCAN_THREADS)
+            if (__half2float(A_hi[(size_t)row * ldv + c]) > limit) {
+                const int k = atomicAdd(&s_n, 1);
+                if (k < SCAN_MAX) s_col[k] = c;
+            }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int n = s_n;
+            if (n > 0) {
+                words[3] = 1;                                      // SPIKE (diagnostics)
+                atomicAdd(&words[4], 1);
+                if (n > MLBP_SPIKE_SLOTS) {
+                    words[0] = 1;                                  // PEAK: reduced-pass rows of this theta keep the lo half
+                } else {
+                    for (int i = 1; i < n; ++i) {                  // ascending columns: deterministic order downstream
+                        const int c = s_col[i];
+                        int q = i;
+                        while (q > 0 && s_col[q - 1] > c) { s_col[q] = s_col[q - 1]; --q; }
+                        s_col[q] = c;
+                    }
+                    float mx = 0.f;
+                    for (int i = 0; i < n; ++i) {
+                        const size_t o = (size_t)row * ldv + s_col[i];
+                        entries[(size_t)row * MLBP_SPIKE_SLOTS + i] = make_int2(s_col[i], __float_as_int(__half2float(A_lo[o])));
+                        mx = fmaxf(mx, __half2float(A_hi[o]));
+                    }
+                    atomicMax(&words[2], __float_as_int(mx));     // largest spike seen (2^14 * probability; diagnostics)
+                    if (block_rows) block_rows[atomicAdd(block_n, 1)] = row;
+                }
+            }
+            cnt[row] = min(n, MLBP_SPIKE_SLOTS + 1);
+        }
+        __syncthreads();
+    }
+}
 
 __global__ void __launch_bounds__(SP_THREADS)
 spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restrict__ cnt, const int2 *__restrict__ entries,
@@ -32,13 +106,9 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
         if (row < a0 || row >= a0 + n_rows) continue;              // (cannot happen: the list belongs to this block)
         const int n = min(cnt[row], MLBP_SPIKE_SLOTS);
         __syncthreads();
-        if (threadIdx.x == 0) {                                    // insertion sort by column: fixed summation order
-            for (int s = 0; s < n; ++s) {
-                const int2 e = entries[(size_t)row * MLBP_SPIKE_SLOTS + s];
-                int p = s;
-                while (p > 0 && s_col[p - 1] > e.x) { s_col[p] = s_col[p - 1]; s_lo[p] = s_lo[p - 1]; --p; }
-                s_col[p] = e.x; s_lo[p] = __int_as_float(e.y);
-            }
+        if (threadIdx.x < n) {                                     // entries are filed in ascending column order (spike_scan_kernel)
+            const int2 e = entries[(size_t)row * MLBP_SPIKE_SLOTS + threadIdx.x];
+            s_col[threadIdx.x] = e.x; s_lo[threadIdx.x] = __int_as_float(e.y);
         }
         __syncthreads();
         float *drow = D + (d_row0 + (int64_t)(row - a0)) * (int64_t)ldd;
@@ -92,6 +162,24 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
 }  // namespace mlbp
 
 using namespace mlbp;
+
+extern "C" int mlbp_spike_scan(const void *A_hi, const void *A_lo, int ldv, int V, int a_row0, int n_rows, float spike_prob,
+                               int32_t *spike_words, int32_t *spike_cnt, int32_t *spike_entries, int32_t *block_rows,
+                               int32_t *block_n, void *stream) {
+    if (n_rows == 0) return MLBP_OK;
+    MLBP_CHECK_ARG(A_hi && A_lo && spike_words && spike_cnt && spike_entries && n_rows > 0 && a_row0 >= 0 && spike_prob > 0.f &&
+                   (!block_rows || block_n), "spike_scan: bad argument");
+    MLBP_CHECK_ARG((ldv % 64) == 0 && ldv >= V && (reinterpret_cast<uintptr_t>(A_hi) % 16) == 0,
+                   "spike_scan: rows must be 16-byte aligned and padded to a multiple of 64");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+    const int grid = n_rows < 64 * sms ? n_rows : 64 * sms;
+    spike_scan_kernel<<<grid, SCAN_THREADS, 0, as_stream(stream)>>>((const __half *)A_hi, (const __half *)A_lo, ldv, V, a_row0, n_rows,
+                                                                    ldexpf(spike_prob, MLBP_A_SCALE_LOG2), spike_words, spike_cnt,
+                                                                    reinterpret_cast<int2 *>(spike_entries), block_rows, block_n);
+    MLBP_LAUNCH_CHECK();
+    return MLBP_OK;
+}
 
 extern "C" int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
                                   const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo,

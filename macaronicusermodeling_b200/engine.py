@@ -516,7 +516,6 @@ class Engine(object):
             blk_host = blob[int(blob[H_MSG_BLK_OFF]):int(blob[H_MSG_BLK_OFF]) + GEMM_WORDS * n_blk].reshape(-1, GEMM_WORDS)
             blk_of = dict((int(r[1]), i) for i, r in enumerate(blk_host))     # first A row of a block -> its index
             spk_blk = torch.empty(max(n_blk, 1), dtype=torch.int32, device=dev)
-            k.call('mlbp_zero_words', _p(spk_cnt), n_spk)
             k.call('mlbp_zero_words', _p(spk_blk), max(n_blk, 1))
             k.call('mlbp_zero_words', _p(self._flags, FLAG_NSPIKY), 1)
 
@@ -547,6 +546,13 @@ class Engine(object):
         alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp + self.centre_exp)))
         g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
         range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
+
+        def spike_scan(a0, rows, listed=True):
+            """file the spikes of A rows [a0, a0 + rows) -- one GEMM block -- before its GEMM (mlbp_spike_scan)"""
+            self._timed('K4a spike_scan', rows * V * 2.0,
+                        lambda: k.call('mlbp_spike_scan', _p(A_hi), _p(A_lo), ld, V, a0, rows, self.peak_mult / V, peak_flag, _p(spk_cnt),
+                                       _p(spk_ent), _p(spk_rows, a0) if listed else None, _p(spk_blk, blk_of[a0]) if listed else None))
+            self.launches += 1
 
         def spike_correct(t, a0, d0, rows, block_a0):
             """restore what the dropped lo half of A contributed at the spikes of rows [a0, a0 + rows) (block starting at block_a0)"""
@@ -612,10 +618,13 @@ class Engine(object):
                             lambda: k.call('mlbp_var_to_factor', int(rec[0]), _p(bd, int(rec[1])), _p(bd, int(rec[2])),
                                            _p(bd, int(rec[3])), _p(bd, int(rec[4])), _p(bd, int(rec[5])), _p(bd, int(rec[8])), _p(bd, int(rec[9])),
                                            _p(U), _p(D), ld,
-                                           V, _p(A_hi), _p(A_lo), max_in, range_log2, peak_flag, self.peak_mult / V,
-                                           _p(spk_cnt), _p(spk_ent), _p(spk_rows), n_spk,
-                                           _p(spk_blk) if track else None, _p(bd, int(blob[H_MSG_BLK_OFF])), int(blob[H_SPK_BLK_N]) if track else 0))
+                                           V, _p(A_hi), _p(A_lo), max_in, range_log2))
                 self.launches += 1
+            if track:                                             # spikes of this level's GEMM blocks, before their GEMMs
+                for i in range(int(rec[6])):
+                    t, a0, d0, rows = (int(x) for x in blob[int(rec[7]) + GEMM_WORDS * i: int(rec[7]) + GEMM_WORDS * (i + 1)])
+                    if two_pass:
+                        spike_scan(a0, rows)
             if two_pass:
                 gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
                 for i in range(int(rec[6])):                      # restore what the dropped lo half of the spikes contributed
@@ -633,6 +642,10 @@ class Engine(object):
             v2f_rows = (A_hi[rows, :V].double() + A_lo[rows, :V].double()) * (2.0 ** -A_SCALE_LOG2)
         if want_grad and n_pair:
             if one_pass:
+                # spikes of the gradient stage's r rows (two ranges, listed for the AXPY below) and c rows (cells only)
+                for i in range(int(blob[H_MSG_BLK_N]), int(blob[H_SPK_BLK_N])):
+                    spike_scan(int(blk_host[i][1]), int(blk_host[i][3]))
+                spike_scan(int(blob[int(blob[H_PAIR_C])]), n_pair, listed=False)
                 # one pass (r_hi . B_hi); the cells where BOTH messages of a factor have a spike -- the only ones whose fp16
                 # table rounding does not average away -- are restored in mlbp_pair_expectations from the spike lists.  A row
                 # with more spikes than slots (PEAK word, device gate) switches these rows to two passes instead.

@@ -188,9 +188,7 @@ class FakeKernels(object):
     def mlbp_zero_words(self, p, n):
         _arr(p, np.int32, n)[:] = 0
 
-    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2,
-                           spike_words=None, spike_prob=1.0, spike_cnt=None, spike_entries=None, spike_rows=None, n_msg_rows=0,
-                           spike_blk_cnt=None, blocks=None, n_blocks=0):
+    def mlbp_var_to_factor(self, n_groups, grp_u, grp_off, in_row, dest_off, dest, first_dest, second_dest, U, D, ldv, V, A_hi, A_lo, max_in, range_log2):
         gu = _arr(grp_u, np.int32, n_groups); go = _arr(grp_off, np.int32, n_groups + 1)
         n_in = int(go[-1])
         ir = _arr(in_row, np.int32, n_in); do = _arr(dest_off, np.int32, n_in + 1)
@@ -221,32 +219,6 @@ class FakeKernels(object):
                 s = p.sum()
                 x = p * (A_SCALE / s) if (s > 0 and np.isfinite(s)) else np.full(V, A_SCALE / V)
                 hi, lo = _split(x)
-                if spike_words is not None and spike_words.value:
-                    pf = _arr(spike_words, np.int32, 5)
-                    pf[2:3].view(np.float32)[0] = max(float(pf[2:3].view(np.float32)[0]), float(np.float32(x.max())))
-                    x32 = x.astype(np.float32)
-                    for col in np.nonzero(x32 > np.float32(spike_prob * A_SCALE))[0]:
-                        pf[3] = 1
-                        lo_exact = np.float32(x32[col] - np.float32(hi[col]))
-                        cnt = _arr(spike_cnt, np.int32, max(n_msg_rows, 1))
-                        ent = _arr(spike_entries, np.int32, max(n_msg_rows, 1) * 8).reshape(-1, 4, 2)
-                        rws = _arr(spike_rows, np.int32, max(n_msg_rows, 1))
-                        for tdest in de[do[i]:do[i + 1]]:
-                            if tdest >= n_msg_rows:
-                                continue                          # (n_msg_rows = rows covered by the spike arrays)
-                            slot = int(cnt[tdest]); cnt[tdest] += 1
-                            if slot == 0:
-                                blk = _arr(blocks, np.int32, 4 * max(n_blocks, 1)).reshape(-1, 4)[:n_blocks]
-                                bc = _arr(spike_blk_cnt, np.int32, max(n_blocks, 1))
-                                for bi, brow in enumerate(blk):
-                                    if brow[1] <= tdest < brow[1] + brow[3]:
-                                        rws[brow[1] + bc[bi]] = tdest; bc[bi] += 1
-                                pf[4] += 1
-                            if slot < 4:
-                                ent[tdest, slot, 0] = col
-                                ent[tdest, slot, 1:2].view(np.float32)[0] = lo_exact
-                            else:
-                                pf[0] = 1
                 for tdest in de[do[i]:do[i + 1]]:
                     H[tdest, :V], L[tdest, :V] = hi, lo
 
@@ -282,6 +254,31 @@ class FakeKernels(object):
             return
         self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl,
                                      k0, k_len)
+
+    def mlbp_spike_scan(self, A_hi, A_lo, ldv, V, a0, n_rows, spike_prob, words, cnt, entries, block_rows, block_n):
+        w = _arr(words, np.int32, 5)
+        H = _arr(A_hi, np.float16, (a0 + n_rows) * ldv).reshape(-1, ldv)
+        L = _arr(A_lo, np.float16, (a0 + n_rows) * ldv).reshape(-1, ldv)
+        c = _arr(cnt, np.int32, a0 + n_rows)
+        ent = _arr(entries, np.int32, (a0 + n_rows) * 8).reshape(-1, 4, 2)
+        listed = block_rows is not None and block_rows.value
+        for r in range(a0, a0 + n_rows):
+            cols = np.nonzero(H[r, :V].astype(np.float32) > np.float32(spike_prob * A_SCALE))[0]
+            c[r] = min(len(cols), 5)
+            if len(cols) == 0:
+                continue
+            w[3] = 1; w[4] += 1
+            if len(cols) > 4:
+                w[0] = 1
+                continue
+            for i, col in enumerate(cols):
+                ent[r, i, 0] = col
+                ent[r, i, 1:2].view(np.float32)[0] = np.float32(L[r, col])
+            w[2:3].view(np.float32)[0] = max(float(w[2:3].view(np.float32)[0]), float(H[r, cols].astype(np.float32).max()))
+            if listed:
+                n = _arr(block_n, np.int32, 1)
+                _arr(block_rows, np.int32, n_rows)[n[0]] = r
+                n[0] += 1
 
     def mlbp_spike_correct(self, words, cnt, entries, rows, n_list, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha):
         w = _arr(words, np.int32, 5)

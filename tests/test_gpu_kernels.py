@@ -262,6 +262,44 @@ def test_var_to_factor_records_spikes(lib):
         assert (st['max_message_prob'] > 16.0 / 2304) == bool(expect), st
 
 
+def test_spike_scan_files_the_spikes_of_a_block(lib):
+    """K4a: per row the elements above the limit as (column, A_lo value) in ascending columns, their count, the block's list of
+    spiky rows; five spikes in one row raise PEAK; rows outside the block and the uninitialised row padding are not read"""
+    M, V = 70, 2500
+    rng = np.random.default_rng(2)
+    A = rng.random((M, V)) * 2.0 ** 14 / V * 2
+    want = {5: [17, 900, 2499], 31: [0], 64: [3, 4, 5, 6]}
+    for r, cols in want.items():
+        for c in cols:
+            A[r, c] = 2.0 ** 14 * 0.05 * (1 + 0.01 * c / V)
+    A[2, 100] = 2.0 ** 14 * 0.5                                    # row 2 is outside the scanned block
+    Ah, Al, Ax, ld = split_planes(A)
+    Ah[:, V:] = float('nan')                                       # the padding of A rows is never written: poison it
+    words = torch.zeros(8, dtype=torch.int32, device='cuda')
+    cnt = torch.full((M,), -1, dtype=torch.int32, device='cuda')
+    ent = torch.zeros((M, 4, 2), dtype=torch.int32, device='cuda')
+    rows = torch.full((M,), -1, dtype=torch.int32, device='cuda')
+    n_list = torch.zeros(1, dtype=torch.int32, device='cuda')
+    a0, n = 4, 62
+    _lib.check(lib.mlbp_spike_scan(P(Ah), P(Al), ld, V, a0, n, 16.0 / V, P(words), P(cnt), P(ent), P(rows), P(n_list), S()))
+    torch.cuda.synchronize()
+    c, e, w = cnt.cpu().numpy(), ent.cpu().numpy(), words.cpu().numpy()
+    assert (c[:a0] == -1).all() and (c[a0 + n:] == -1).all()
+    lo = Al.cpu().numpy().astype(np.float32)
+    for r in range(a0, a0 + n):
+        cols = want.get(r, [])
+        assert c[r] == len(cols), (r, c[r])
+        for i, col in enumerate(cols):
+            assert e[r, i, 0] == col and e[r, i, 1:2].view(np.float32)[0] == lo[r, col]
+    assert sorted(rows.cpu().numpy()[:int(n_list[0])].tolist()) == sorted(want) and int(n_list[0]) == 3
+    assert w[0] == 0 and w[3] == 1 and w[4] == 3
+    A[40, [1, 2, 3, 4, 5]] = 2.0 ** 14 * 0.05
+    Ah2, Al2, _, _ = split_planes(A)
+    _lib.check(lib.mlbp_spike_scan(P(Ah2), P(Al2), ld, V, a0, n, 16.0 / V, P(words), P(cnt), P(ent), None, None, S()))
+    torch.cuda.synchronize()
+    assert int(words[0]) == 1 and int(cnt[40]) == 5
+
+
 def test_spike_correct_restores_the_dropped_lo_part(lib):
     """two-pass GEMM (A_hi only) + mlbp_spike_correct on the recorded spikes == the full product up to the rounding of the
     un-spiky remainder; rows outside the block and rows without spikes are untouched; a set PEAK word disables it"""
@@ -288,7 +326,7 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     lo_exact = x32 - x32.astype(np.float16).astype(np.float32)
     n_sp = 0
     for r, cols in spikes.items():
-        for c in cols[::-1]:                                       # recorded in arbitrary (here: descending) order
+        for c in cols:                                             # ascending columns, as mlbp_spike_scan files them
             ent[r, cnt[r], 0] = c
             ent[r, cnt[r], 1] = int(np.float32(lo_exact[r, c]).view(np.int32))
             cnt[r] += 1
