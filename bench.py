@@ -55,7 +55,7 @@ def parse():
     ap.add_argument('--gemm-slice-pairs', type=int, default=None, help='M pairs per three-pass K4 launch (default: Engine rule; 0 = one launch per level, A/B probe)')
     ap.add_argument('--gemm-impl', type=int, default=0, help='K4 variant / flags (include/mlbp.h; A/B probes)')
     ap.add_argument('--grad-b-terms', type=int, default=1, help='2 = keep the table lo half in the gradient rows (A/B probe)')
-    ap.add_argument('--msg-passes', type=int, default=None, help='3 = three-pass message rows always (A/B probe); default: Engine rule')
+    ap.add_argument('--msg-passes', type=int, default=None, help='2 / 3 = two- / three-pass message rows (A/B probes); default: Engine rule (one pass where V >= 4096)')
     ap.add_argument('--config', default='c3', choices=['c3', 'c4', 'c5'],
                     help='BASELINE config: c3 batched training (the headline metric), c4 multi-user training (512 users x 100 '
                          'sentences, users sharded), c5 inference-only belief sweep (V=50k, 10 sweeps)')
@@ -501,7 +501,8 @@ def ours(a):
     pass_stats = eng.pass_stats()
     by_passes = {}
     gemm_ms = gemm_rows = gemm_pass_rows = 0.0
-    for x, y, r, p, gated, tag in eng.gemm_events:
+    by_role = {}
+    for x, y, r, p, gated, tag, role in eng.gemm_events:
         code = int(w.peaked[tag]) if world == 1 else (3 if w.peaked[tag] else 0)   # bit 0 PEAK, bit 1 SPIKE (summed over ranks: any)
         if gated == 1 and (code & 1):
             p = 3                                          # a message with too many spikes switched the message rows to three passes
@@ -509,6 +510,8 @@ def ours(a):
             p = 2                                          # ... and the one-pass gradient rows to two
         t = x.elapsed_time(y)
         d = by_passes.setdefault(p, {'launches': 0, 'rows': 0, 'ms': 0.0})
+        d['launches'] += 1; d['rows'] += r; d['ms'] += t
+        d = by_role.setdefault('%s rows, %d pass%s' % (role, p, '' if p == 1 else 'es'), {'launches': 0, 'rows': 0, 'ms': 0.0, 'p': p})
         d['launches'] += 1; d['rows'] += r; d['ms'] += t
         gemm_ms += t; gemm_rows += r; gemm_pass_rows += r * p
     n_gemm = len(eng.gemm_events)
@@ -526,11 +529,12 @@ def ours(a):
     which = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
     flops = 2.0 * gemm_rows * a.V * a.V
     ach = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic, traffic_note = None, None
+    traffic, traffic_note, key = None, None, None
     tr_path = os.path.join(REPO, 'profiles', a.traffic_file)
     if os.path.exists(tr_path) and a.V == 10000:
         tj = json.load(open(tr_path))
-        key = 'two_pass_37_pairs' if (2 in by_passes and 'two_pass_37_pairs' in tj) else ('three_pass_37_pairs' if 'three_pass_37_pairs' in tj else 'three_pass_big')
+        key = next((kk for kk in (('one_pass_message_rows',) if 2 not in by_passes and 3 not in by_passes else ()) + ('two_pass_37_pairs', 'three_pass_37_pairs', 'three_pass_big') if kk in tj), None)
+    if os.path.exists(tr_path) and a.V == 10000 and key:
         big = tj[key]
         traffic = big['dram_bytes_per_launch']
         traffic_note = ('dram__bytes_read+write of one %s launch of %d rows from the committed ncu --set full capture (%s): %.1fx its '
@@ -544,14 +548,20 @@ def ours(a):
                                        'algorithmic_tflops': 2.0 * d['rows'] * a.V * a.V / (d['ms'] / 1e3) / 1e12 if d['ms'] > 0 else 0.0,
                                        'executed_tflops': p * 2.0 * d['rows'] * a.V * a.V / (d['ms'] / 1e3) / 1e12 if d['ms'] > 0 else 0.0}
                               for p, d in sorted(by_passes.items())},
+                'by_role': {k: {'launches': d['launches'], 'rows': d['rows'], 'ms': d['ms'], 'share_of_step': d['ms'] / ms_prof,
+                                'algorithmic_tflops': 2.0 * d['rows'] * a.V * a.V / (d['ms'] / 1e3) / 1e12 if d['ms'] > 0 else 0.0,
+                                'executed_tflops': d['p'] * 2.0 * d['rows'] * a.V * a.V / (d['ms'] / 1e3) / 1e12 if d['ms'] > 0 else 0.0}
+                            for k, d in sorted(by_role.items())},
                 'launches_timed': n_gemm, 'avg_launch_ms': gemm_ms / max(n_gemm, 1),
                 'algorithmic_flops_per_launch': flops / max(n_gemm, 1), 'share_of_step': gemm_ms / ms_prof,
                 'measured_in': 'a separate profiling pass of %d steps (CUDA-event pair around every launch, %.1f ms/step); `value` and '
                                '`e2e` are timed without those events' % (p_steps, ms_prof / p_steps),
-                'note': 'algorithmic flops 2*rows*V*V counted once; message rows issue 2 fp16 MMA passes (hi*hi, hi*lo: the lo half of the '
-                        'message is dropped and every near-tied decision is re-scored exactly, csrc/rescore.cu) or 3 (hi*hi, hi*lo, lo*hi) '
-                        'when a message is peaked or the potentials span more than e^3; gradient rows 1 (hi*hi; V >= 4096 and potentials '
-                        'within e^3, else 2 or 3): %.2f passes per row on average' % (gemm_pass_rows / max(gemm_rows, 1))}
+                'note': 'algorithmic flops 2*rows*V*V counted once; message rows issue ONE fp16 MMA pass (hi*hi: the lo halves of the '
+                        'message and of the table are dropped, the spikes of a message get both dropped terms back exactly '
+                        '(csrc/spikes.cu) and every near-tied decision is re-scored from the full operands, csrc/rescore.cu), 2 with '
+                        '--msg-passes 2 (hi*hi, hi*lo) or 3 (hi*hi, hi*lo, lo*hi) when a message has more spikes than slots or the '
+                        'potentials span more than e^3; gradient rows 1 (hi*hi; V >= 4096 and potentials within e^3, else 2 or 3): '
+                        '%.2f passes per row on average' % (gemm_pass_rows / max(gemm_rows, 1))}
     # HBM-bound kernels: algorithmic bytes (each input / output row counted once) over the CUDA-event time of every launch
     peak_gbs = float(peaks.get('hbm_gbs', 6500.0))
     hbm = {}
@@ -588,7 +598,7 @@ def ours(a):
                        'k4_rows_per_sliced_launch': eng.gemm_slice_rows},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'hbm_kernels': hbm,
             'host': {'plan_compile_s_per_step': plan_s_per_step, 'plan_threads': int(os.environ.get('MLBP_PLAN_THREADS', '0'))},
-            'message_rows': {'two_pass_enabled': pass_stats['msg_two_pass'], 'ranks_switched_to_three_passes_per_step': peaked_value,
+            'message_rows': {'passes': pass_stats['msg_passes'], 'reduced_pass_enabled': pass_stats['msg_two_pass'], 'ranks_switched_to_three_passes_per_step': peaked_value,
                              'ranks_switched_all_steps_incl_warmup_e2e_profiling': w.all_peaked, 'max_message_prob_last_step': pass_stats['max_message_prob'],
                              'flag_code': 'bit 0 = a row had more spikes than slots (message rows ran three passes, gradient rows two), bit 1 = a spike was seen and compensated',
                              'spiky_rows_last_batch': pass_stats['spiky_rows_last_batch'], 'theta_after_each_step': w.thetas,

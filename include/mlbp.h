@@ -151,10 +151,21 @@ int mlbp_spike_scan(const void *A_hi, const void *A_lo, int ldv, int V, int a_ro
  *   D[r, n] += alpha * sum over the recorded spikes s of row r of  lo_s * B[n, col_s],  with B[n, col] read as row `col` of
  *   the TRANSPOSED table's plane pair Bt_hi / Bt_lo (MLBP_TABLE_T <-> TT, T1 <-> T1T, G <-> GT, G1 <-> G1T, G1W <-> G1WT).
  *   block_rows / block_n: this block's list of spiky rows and its length (mlbp_spike_scan).  Returns at once (on the device) when spike_words[0] is set: the block then ran with the lo half.
- *   Spikes of a row are applied in ascending column order (deterministic).                                             */
+ *   Spikes of a row are applied in ascending column order (deterministic).
+ *   A_hi_one_pass (or NULL): the block ran ONE pass (A_hi . B_hi, MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY), so the spikes' share
+ *   of the other dropped term is restored too:  D[r, n] += alpha * hi_s * B_lo[n, col_s]  with hi_s read from A_hi[r, col_s].  */
 int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
                        const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi,
-                       const void *Bt_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream);
+                       const void *Bt_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
+                       const void *A_hi_one_pass, void *stream);
+/* K5c. The K most probable words of each of n_rows belief rows X[r, 0..V) (fp32, row stride ldx), best first, on the device:
+ *   VariableNode.get_max_vocab (LBP.py:402-411: np.argpartition + np.argsort on the host marginal; K = 50 for
+ *   FactorGraph.to_string / get_precision_counts, LBP.py:87, :115).
+ *   idx[r, 0..K) / val[r, 0..K): word indices and probabilities, descending value, ascending index among equal values.
+ *   n_ties[r] (or NULL): > 0 when the order of row r is not decided by the values alone (equal neighbours inside the list, or
+ *   more entries equal to the K-th value than were listed): NumPy's order among exactly equal values is an implementation
+ *   detail, so a caller that has to reproduce it falls back to the host calls for that row.  1 <= K <= min(V, 1024).       */
+int mlbp_topk_rows(const float *X, int ldx, int V, int n_rows, int K, int32_t *idx, float *val, int32_t *n_ties, void *stream);
 /* Approximate paths (use_approx_inference LBP.py:506-507, :515-516 -> au.sparse_vec_mat_dot pyx:193-205;
  *   use_approx_beliefs LBP.py:554-563 -> au.sparse_dot / sparse_pointwise_multiply / sparse_normalize pyx:108-129, :23-26):
  *   keep the K largest entries of each of the n_rows operand rows A[row0 ..], zero the others (K = 100 in the reference);

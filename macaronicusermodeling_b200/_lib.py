@@ -20,8 +20,9 @@ _SIGNATURES = {
     'mlbp_fill_uniform_rows': 'ppiipipp',
     'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppif' + 'p',
     'mlbp_spike_scan': 'ppii' + 'iif' + 'ppppp' + 'p',
-    'mlbp_spike_correct': 'ppppp' + 'ii' + 'ppii' + 'plif' + 'p',
+    'mlbp_spike_correct': 'ppppp' + 'ii' + 'ppii' + 'plif' + 'pp',
     'mlbp_topk_mask_rows': 'ppiiliip',
+    'mlbp_topk_rows': 'piiiipppp',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
     'mlbp_factor_to_var_gemm_gated': 'pplii' + 'ppii' + 'plifi' + 'pi' + 'ii' + 'p',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppf' + 'iff' + 'ppppp' + 'p',

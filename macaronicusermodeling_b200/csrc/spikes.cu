@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(SP_THREADS)
 spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restrict__ cnt, const int2 *__restrict__ entries,
                      const int32_t *__restrict__ rows, const int32_t *__restrict__ n_list, int a0, int n_rows, const __half *__restrict__ Bt_hi,
                      const __half *__restrict__ Bt_lo, int V, int ldv, float *__restrict__ D, int64_t d_row0, int ldd,
-                     float alpha) {
+                     float alpha, const __half *__restrict__ A_hi) {
     if (words[0] != 0) return;                                     // three passes ran: nothing to restore
     __shared__ int s_col[MLBP_SPIKE_SLOTS];
-    __shared__ float s_lo[MLBP_SPIKE_SLOTS];
+    __shared__ float s_lo[MLBP_SPIKE_SLOTS], s_hi[MLBP_SPIKE_SLOTS];
     const int total = min(*n_list, n_rows);
     for (int i = blockIdx.x; i < total; i += gridDim.x) {
         const int row = rows[i];
@@ -109,6 +109,8 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
         if (threadIdx.x < n) {                                     // entries are filed in ascending column order (spike_scan_kernel)
             const int2 e = entries[(size_t)row * MLBP_SPIKE_SLOTS + threadIdx.x];
             s_col[threadIdx.x] = e.x; s_lo[threadIdx.x] = __int_as_float(e.y);
+            // one-pass rows (A_hi . B_hi) also dropped  A_hi . B_lo : restored at the spikes with the hi value as weight of B_lo
+            s_hi[threadIdx.x] = A_hi ? __half2float(A_hi[(size_t)row * ldv + e.x]) : 0.f;
         }
         __syncthreads();
         float *drow = D + (d_row0 + (int64_t)(row - a0)) * (int64_t)ldd;
@@ -129,7 +131,7 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
                 }
             }
             for (int s = 0; s < n; ++s) {
-                const float w = s_lo[s];
+                const float w = s_lo[s], wl = w + s_hi[s];          // weights of B_hi and of B_lo
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     if (u == 1 && !on1) continue;
@@ -139,8 +141,8 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float2 a = __half22float2(hh[q]), b = __half22float2(ll[q]);
-                        acc[u][2 * q] = fmaf(w, a.x + b.x, acc[u][2 * q]);
-                        acc[u][2 * q + 1] = fmaf(w, a.y + b.y, acc[u][2 * q + 1]);
+                        acc[u][2 * q] = fmaf(w, a.x, fmaf(wl, b.x, acc[u][2 * q]));
+                        acc[u][2 * q + 1] = fmaf(w, a.y, fmaf(wl, b.y, acc[u][2 * q + 1]));
                     }
                 }
             }
@@ -183,7 +185,8 @@ extern "C" int mlbp_spike_scan(const void *A_hi, const void *A_lo, int ldv, int 
 
 extern "C" int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
                                   const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo,
-                                  int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, void *stream) {
+                                  int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, const void *A_hi_one_pass,
+                                  void *stream) {
     if (n_rows == 0) return MLBP_OK;
     MLBP_CHECK_ARG(spike_words && spike_cnt && spike_entries && block_rows && block_n && Bt_hi && Bt_lo && D && n_rows > 0 && a_row0 >= 0,
                    "spike_correct: bad argument");
@@ -195,7 +198,8 @@ extern "C" int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spi
     const int grid = n_rows < 8 * sms ? n_rows : 8 * sms;
     spike_correct_kernel<<<grid, SP_THREADS, 0, as_stream(stream)>>>(spike_words, spike_cnt, reinterpret_cast<const int2 *>(spike_entries),
                                                                     block_rows, block_n, a_row0, n_rows, (const __half *)Bt_hi,
-                                                                    (const __half *)Bt_lo, V, ldv, D, d_row0, ldd, alpha);
+                                                                    (const __half *)Bt_lo, V, ldv, D, d_row0, ldd, alpha,
+                                                                    (const __half *)A_hi_one_pass);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

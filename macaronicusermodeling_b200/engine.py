@@ -14,6 +14,7 @@ PyTorch is used for device memory and streams only; all arithmetic is in libmlbp
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -207,10 +208,13 @@ class Corpus(object):
 class Result(object):
     """Outputs of one Engine.run: tensors stay on the device until read."""
 
-    def __init__(self, grad, logp, logp_var, top1, rank, beliefs, stats, messages=None):
+    def __init__(self, grad, logp, logp_var, top1, rank, beliefs, stats, messages=None, topk=None):
         self.grad, self.logp, self.logp_var, self.top1, self.rank, self.beliefs, self.stats = \
             grad, logp, logp_var, top1, rank, beliefs, stats
         self.messages = messages     # final pairwise messages (want_messages): see Engine.run
+        # want_topk = K: (idx [n_vars, K] int32, prob [n_vars, K] float32, n_ties [n_vars] int32), best first, made on the
+        # device by mlbp_topk_rows (VariableNode.get_max_vocab, LBP.py:402-411)
+        self.topk = topk
 
     def precision_counts(self):
         """FactorGraph.get_precision_counts (LBP.py:80-106) summed over the batch: (p@0, p@25, p@50, total)"""
@@ -220,7 +224,7 @@ class Result(object):
 
 class Engine(object):
     def __init__(self, model, kernels=None, workspace_bytes=24 << 30, gemm_impl=0, grad_a_terms=1, grad_b_terms=1,
-                 gemm_slice_pairs=None, msg_passes=None, tau=2e-4, tau_label=1e-4, peak_mult=16.0, one_pass_min_v=4096,
+                 gemm_slice_pairs=None, msg_passes=None, tau=None, tau_label=None, peak_mult=16.0, one_pass_min_v=4096,
                  gemm_k_chunks=None):
         self.k = kernels if kernels is not None else Kernels()
         self.device = self.k.device
@@ -242,23 +246,35 @@ class Engine(object):
         n_k = int(gemm_k_chunks or 1)
         step = round_up(-(-self.V // n_k), 64)
         self.gemm_k_ranges = [(k0, min(step, self.V - k0)) for k0 in range(0, self.V, step)] if n_k > 1 else [(0, 0)]
-        # Message rows with TWO tensor-core passes (A_hi . (B_hi + B_lo): the lo half of the message is dropped) plus an exact
-        # re-score of every near-tied decision (csrc/rescore.cu).  Why this is safe: a rounding error upstream is damped by
-        # every later contraction (a message D = T a averages V terms), so the only error of the two-pass scheme that reaches
-        # a belief undamped is the rounding of the LAST hop -- measured 2.3e-6 relative rms on a belief at V = 10 000 (flat
-        # synthetic messages; it shrinks like 1 / sqrt(V_eff)) -- and that hop is recomputed from the full 22-bit operands
-        # for every candidate within `tau` of the arg-max (or within `tau_label` of the label while its rank can matter).
+        # Message rows with REDUCED tensor-core passes plus an exact re-score of every near-tied decision (csrc/rescore.cu).
+        #   two passes  A_hi . (B_hi + B_lo): the lo half of the message is dropped;
+        #   ONE pass    A_hi . B_hi         : the lo half of the table is dropped too (the default where the gate below holds).
+        # Why this is safe: a rounding error upstream is damped by every later contraction (a message D = T a averages V terms,
+        # and K2 rounds the table's hi halves stochastically, so equal entries do not share one error), so the only error that
+        # reaches a belief undamped is the rounding of the LAST hop -- measured on the ratio of two candidates' beliefs at
+        # V = 10 000 in the bench's trained regime: 2.5e-7 relative (mean absolute) with two passes, 2.2e-5 with one -- and that
+        # hop is recomputed from the full 22-bit operands for every candidate within `tau` of the arg-max (or within
+        # `tau_label` of the label while its rank can matter): the bands are ~15x that error.  Against the float64 oracle with
+        # one pass (profiles/r2c_*): 0 top-1 mismatches, beliefs 4e-8 abs (contract 1e-4), gradients 2e-6 relative at C3 size and
+        # 6e-6 on the hostile cases of tests/test_gpu_gates.py (contract 1e-4), log-posterior 3e-6 relative.
         # Guards: (i) the potentials span at most e^3 (set_theta); (ii) spikes: an element that carries more than peak_mult / V
-        # of a message's mass does not average its rounding away, so the var->factor kernel records it and
-        # mlbp_spike_correct restores its dropped lo part exactly after the GEMM (a few AXPYs per spiky row); a row with more
-        # spikes than slots raises a flag ON THE DEVICE that switches all later message GEMMs of this theta to three passes
-        # (mlbp_factor_to_var_gemm_gated; no host synchronisation).  The one-pass gradient rows are gated the same way: once
-        # any spike was seen they keep the lo half of the table planes (a peaked belief does not average the fp16 rounding
-        # of T o PMI away: tests/test_gpu_gates.py).
-        # msg_passes: None = two passes where V >= 4096 (where the error above was measured), 2 = at any V, 3 = never.
+        # of a message's mass does not average its rounding away, so mlbp_spike_scan files it and mlbp_spike_correct restores
+        # the dropped terms of that element exactly after the GEMM (a few AXPYs per spiky row: its lo part times the full table
+        # row and, with one pass, its hi part times the table row's lo half); a row with more spikes than slots raises a flag
+        # ON THE DEVICE that switches all later message GEMMs of this theta to three passes (mlbp_factor_to_var_gemm_gated; no
+        # host synchronisation).  The one-pass gradient rows are gated the same way: once any spike was seen they keep the lo
+        # half of the table planes (a peaked belief does not average the fp16 rounding of T o PMI away: tests/test_gpu_gates.py).
+        # msg_passes: None = one pass where V >= 4096 (where the errors above were measured); 1 / 2 = one / two passes at any
+        # V; 3 = never reduced.  MLBP_MSG_PASSES in the environment overrides None (A/B runs of whole suites).
+        if msg_passes is None and os.environ.get('MLBP_MSG_PASSES'):
+            msg_passes = int(os.environ['MLBP_MSG_PASSES'])
         self.msg_passes = msg_passes
         self.one_pass_min_v = int(one_pass_min_v)   # one-pass gradient rows from this vocabulary size on (tests lower it)
-        self.tau, self.tau_label, self.peak_mult = float(tau), float(tau_label), float(peak_mult)
+        # bands of the near-tie detection: defaults 4e-4 / 2e-4 with one-pass message rows, 2e-4 / 1e-4 with two
+        one = self.msg_passes in (None, 1)
+        self.tau = float(tau) if tau is not None else (4e-4 if one else 2e-4)
+        self.tau_label = float(tau_label) if tau_label is not None else (2e-4 if one else 1e-4)
+        self.peak_mult = float(peak_mult)
         self.msg_two_pass_ok = False
         self._flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device=self.device)
         self.theta_ee = None
@@ -338,7 +354,7 @@ class Engine(object):
         # the table entries is random per entry and averages over the ~V^2 entries a belief spreads over (measured on a
         # sentence's gradient against the float64 oracle: <= 3.2e-6 relative over 24 sentences at V = 10 000, 3e-6 at V = 2 000)
         self.grad_one_pass_ok = self.grad_hi_only_ok and self.V >= self.one_pass_min_v
-        self.msg_two_pass_ok = (zmax - zmin) <= 3.0 and (self.msg_passes == 2 or (self.msg_passes is None and self.V >= 4096)) \
+        self.msg_two_pass_ok = (zmax - zmin) <= 3.0 and (self.msg_passes in (1, 2) or (self.msg_passes is None and self.V >= 4096)) \
             and (self.gemm_impl & 0xff) != 1                      # the SIMT cross-check kernel has no device-side gate
         self.k.call('mlbp_zero_words', _p(self._flags), FLAG_WORDS)   # the peak flag is sticky per theta
         self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
@@ -365,7 +381,8 @@ class Engine(object):
         switched the message GEMMs back to three passes, and what the exact re-score did."""
         f = self._flags.cpu().numpy()
         c = f[FLAG_COUNTERS:FLAG_COUNTERS + 5]
-        return {'msg_two_pass': bool(self.msg_two_pass_ok), 'peak_flag': int(f[FLAG_PEAK]), 'spike_flag': int(f[FLAG_SPIKE]),
+        return {'msg_two_pass': bool(self.msg_two_pass_ok),       # (name kept from the two-pass build: "reduced-pass message rows")
+                'msg_passes': (1 if self.msg_passes in (None, 1) else 2) if self.msg_two_pass_ok else 3, 'peak_flag': int(f[FLAG_PEAK]), 'spike_flag': int(f[FLAG_SPIKE]),
                 'spiky_rows_last_batch': int(f[FLAG_NSPIKY]),
                 'max_message_prob': float(f[FLAG_MAXBITS:FLAG_MAXBITS + 1].view(np.float32)[0]) * 2.0 ** -A_SCALE_LOG2, 'rescored': int(c[0]),
                 'skipped_mass_tie': int(c[1]), 'skipped_degenerate': int(c[2]), 'top1_changed': int(c[3]),
@@ -451,7 +468,7 @@ class Engine(object):
         return handle, sizes
 
     def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False,
-            approx_inference=False, approx_beliefs=False, topk=100, reduce_into=None):
+            approx_inference=False, approx_beliefs=False, topk=100, reduce_into=None, want_topk=0):
         """All sentences of `corpus` (must fit the workspace; use run_many to micro-batch).  `roots`: int
         [n_sent, 1 + sweeps] variable indices local to each sentence (draw 0 = has_loops, LBP.py:176).
         `reduce_into`: optional device tensor of 16 float64 that this call's sums are ADDED to (mlbp_batch_reduce: the
@@ -475,6 +492,7 @@ class Engine(object):
         import time as _time
         t_plan = _time.perf_counter()
         two_pass = self.msg_two_pass_ok and not approx
+        msg_one_pass = two_pass and self.msg_passes in (None, 1)  # message rows as A_hi . B_hi (see __init__)
         handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference,
                                      reuse_z=not approx and not grad_hi_only and not two_pass)
         self.plan_seconds += _time.perf_counter() - t_plan
@@ -554,16 +572,18 @@ class Engine(object):
                                        _p(spk_ent), _p(spk_rows, a0) if listed else None, _p(spk_blk, blk_of[a0]) if listed else None))
             self.launches += 1
 
-        def spike_correct(t, a0, d0, rows, block_a0):
-            """restore what the dropped lo half of A contributed at the spikes of rows [a0, a0 + rows) (block starting at block_a0)"""
+        def spike_correct(t, a0, d0, rows, block_a0, one_pass_rows=False):
+            """restore what the dropped lo half of A contributed at the spikes of rows [a0, a0 + rows) (block starting at block_a0);
+            one_pass_rows: the block also dropped the lo half of the table, restored at the spikes as well"""
             b = blk_of[block_a0]
             tt = TRANSPOSED_TABLE[t]
             self._timed('K4b spike_correct', 0.0,                # bytes depend on the data (spikes found on the device)
                         lambda: k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows, block_a0), _p(spk_blk, b),
-                                       a0, rows, _p(self.plane(tt, 0)), _p(self.plane(tt, 1)), V, ld, _p(D), d0, ld, alpha))
+                                       a0, rows, _p(self.plane(tt, 0)), _p(self.plane(tt, 1)), V, ld, _p(D), d0, ld, alpha,
+                                       _p(A_hi) if one_pass_rows else None))
             self.launches += 1
 
-        def gemm_calls(off, n, mask, impl_flags=0, gated=False):
+        def gemm_calls(off, n, mask, impl_flags=0, gated=False, role='message'):
             masked = set()
             for i in range(n):
                 t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
@@ -600,7 +620,7 @@ class Engine(object):
                                _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags)
                     if self.profile_gemm:
                         e1.record()
-                        self.gemm_events.append((e0, e1, n, passes, (2 if isinstance(gated, tuple) else 1) if gated else 0, self.event_tag))
+                        self.gemm_events.append((e0, e1, n, passes, (2 if isinstance(gated, tuple) else 1) if gated else 0, self.event_tag, role))
                     self.launches += 1
                     self.gemm_launches += 1
                 self.gemm_rows += rows
@@ -626,10 +646,10 @@ class Engine(object):
                     if two_pass:
                         spike_scan(a0, rows)
             if two_pass:
-                gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY, gated=True)
+                gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if msg_one_pass else 0), gated=True)
                 for i in range(int(rec[6])):                      # restore what the dropped lo half of the spikes contributed
                     t, a0, d0, rows = (int(x) for x in blob[int(rec[7]) + GEMM_WORDS * i: int(rec[7]) + GEMM_WORDS * (i + 1)])
-                    spike_correct(t, a0, d0, rows, a0)
+                    spike_correct(t, a0, d0, rows, a0, msg_one_pass)
             else:
                 gemm_calls(int(rec[7]), int(rec[6]), approx_inference)
 
@@ -650,7 +670,7 @@ class Engine(object):
                 # table rounding does not average away -- are restored in mlbp_pair_expectations from the spike lists.  A row
                 # with more spikes than slots (PEAK word, device gate) switches these rows to two passes instead.
                 gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), False, GEMM_A_HI_ONLY | GEMM_B_HI_ONLY,
-                           gated=(peak_flag, GEMM_A_HI_ONLY))
+                           gated=(peak_flag, GEMM_A_HI_ONLY), role='gradient')
                 # ... and the lo part of r at its spikes (the rows drop A_lo): without it the rounding of a spike that Z contains
                 # but the numerator does not (a zero of a sparse feature plane under the spike) shows up undamped in N / Z
                 go = int(blob[H_GRAD_GEMM_OFF])
@@ -659,7 +679,7 @@ class Engine(object):
                     spike_correct(t, a0, d0, rows, a0)
             else:
                 gemm_calls(int(blob[H_GRAD_GEMM_OFF]), int(blob[H_NGRAD_GEMM]), approx_beliefs,
-                           (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0)
+                           (GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if one_pass else 0)) if grad_hi_only else 0, role='gradient')
             if approx_beliefs:                                    # the c rows follow the r rows in the A buffer
                 c0 = int(blob[int(blob[H_PAIR_C])])
                 k.call('mlbp_topk_mask_rows', _p(A_hi), _p(A_lo), ld, V, c0, n_pair, topk)
@@ -682,7 +702,7 @@ class Engine(object):
             logp_var = torch.empty(n_m, dtype=torch.float64, device=dev)
             top1 = torch.empty(n_m, dtype=torch.int32, device=dev)
             rank = torch.empty(n_m, dtype=torch.int32, device=dev)
-            beliefs = torch.empty((n_m, ld), dtype=torch.float32, device=dev) if want_beliefs else None
+            beliefs = torch.empty((n_m, ld), dtype=torch.float32, device=dev) if (want_beliefs or want_topk) else None
             def k5_bytes():
                 mo, mi = int(blob[H_MARG_OFF]), int(blob[H_MARG_IN])
                 n_in = int(blob[mo + n_m])
@@ -710,6 +730,9 @@ class Engine(object):
                                            _p(aux), _p(cnts), self.tau, self.tau_label, range_log2 + self.half_range_log2,
                                            _p(top1), _p(rank), _p(self._flags, FLAG_COUNTERS)))
                 self.launches += 2
+        top_words = None
+        if want_marg and want_topk:                               # after the re-score: K5b only moves top1 / rank, not beliefs
+            top_words = self.topk_rows(beliefs, min(int(want_topk), V))
         grad = torch.empty((corpus.n_sent, 9), dtype=torch.float64, device=dev)
         logp = torch.empty(corpus.n_sent, dtype=torch.float64, device=dev)
         # per-sentence segmented sums (deterministic, no atomics); without the gradient stage only log-posteriors matter
@@ -745,8 +768,21 @@ class Engine(object):
                 messages['f2v'].append([dr[j] if rows[j] >= 0 else None for j in range(int(off[v]), int(off[v + 1]))])
         stats = {'a_rows': int(sizes[PLAN_A_ROWS]), 'd_rows': int(sizes[PLAN_D_ROWS]), 'levels': int(sizes[PLAN_N_LEVELS]),
                  'gemm_rows': int(sizes[PLAN_N_GEMM_ROWS]), 'dead': int(sizes[PLAN_N_DEAD]), 'blob_words': words,
-                 'msg_two_pass': bool(two_pass)}
-        return Result(grad, logp, logp_var, top1, rank, beliefs, stats, messages)
+                 'msg_two_pass': bool(two_pass), 'msg_passes': 1 if msg_one_pass else (2 if two_pass else 3)}
+        return Result(grad, logp, logp_var, top1, rank, beliefs, stats, messages, top_words)
+
+    def topk_rows(self, X, K):
+        """the K largest entries of every row of the fp32 device matrix X[:, :V], best first: (idx, value, n_ties) device
+        tensors (mlbp_topk_rows; get_max_vocab, LBP.py:402-411).  n_ties[r] > 0: the order of row r is not decided by the
+        values alone (exact ties) -- NumPy's order for those is an implementation detail of its introselect."""
+        n = int(X.shape[0])
+        idx = torch.empty((n, K), dtype=torch.int32, device=self.device)
+        val = torch.empty((n, K), dtype=torch.float32, device=self.device)
+        ties = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._timed('K5c topk_rows', n * self.V * 4.0,
+                    lambda: self.k.call('mlbp_topk_rows', _p(X), int(X.stride(0)), self.V, n, int(K), _p(idx), _p(val), _p(ties)))
+        self.launches += 1
+        return idx, val, ties
 
     # ------------------------------------------------------------------ micro-batching
     def microbatches(self, corpus, sweeps, want_grad):

@@ -21,12 +21,13 @@ def main():
     ap.add_argument('--n', type=int, default=16)
     ap.add_argument('--gemm-impl', type=int, default=0, help='K4 variant (include/mlbp.h, csrc/gemm_tcgen05.cu)')
     ap.add_argument('--grad-terms', type=int, default=1, help='2 = three-pass gradient rows (for comparison)')
+    ap.add_argument('--msg-passes', type=int, default=None, help='1 / 2 / 3 tensor-core passes on the message rows (default: Engine rule)')
     a = ap.parse_args()
     model = synth.make_model(10000, 2000, seed=1234, dtype=np.float32)
     sents = synth.make_corpus(model, a.n, k=20, g=0, seed=4242)
     roots_pos = synth.draw_roots(sents, 3, seed=11)
     te, td = [0.8, 0.5, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]
-    eng = Engine(model, grad_a_terms=a.grad_terms, grad_b_terms=a.grad_terms, gemm_impl=a.gemm_impl)
+    eng = Engine(model, grad_a_terms=a.grad_terms, grad_b_terms=a.grad_terms, gemm_impl=a.gemm_impl, msg_passes=a.msg_passes)
     eng.set_theta(te, td)
     corpus = Corpus(sents)
     r = eng.run(corpus, corpus.roots_from_positions(roots_pos), 3, want_beliefs=True)
@@ -49,7 +50,7 @@ def main():
         worst_lp = max(worst_lp, abs(float(LP[i]) - o['logp']) / abs(o['logp']))
     print(json.dumps({'config': 'C3 shape, %d sentences, V=10000, k=20, 3 sweeps' % a.n, 'variables': int(n_var),
                       'top1_mismatches': flips, 'max_abs_belief_error': worst_b, 'max_rel_gradient_error': worst_g,
-                      'max_rel_logposterior_error': worst_lp, 'gradient_rows_passes': 3 if a.grad_terms == 2 else (1 if eng.grad_one_pass_ok else 2),
+                      'max_rel_logposterior_error': worst_lp, 'message_rows_passes': a.msg_passes, 'gradient_rows_passes': 3 if a.grad_terms == 2 else (1 if eng.grad_one_pass_ok else 2),
                       'oracle_seconds': time.time() - t0}))
 
 

@@ -234,6 +234,18 @@ class FakeKernels(object):
             H[r, :V][drop] = 0
             L[r, :V][drop] = 0
 
+    def mlbp_topk_rows(self, X, ldx, V, n_rows, K, idx, val, n_ties):
+        Xm = _arr(X, np.float32, n_rows * ldx).reshape(-1, ldx)
+        I = _arr(idx, np.int32, n_rows * K).reshape(-1, K)
+        P = _arr(val, np.float32, n_rows * K).reshape(-1, K)
+        T = _arr(n_ties, np.int32, n_rows)
+        for r in range(n_rows):
+            x = np.maximum(Xm[r, :V], 0)
+            order = np.lexsort((np.arange(V), -x))[:K]              # descending value, ascending index among equals
+            I[r], P[r] = order, x[order]
+            if T is not None:
+                T[r] = int((np.diff(P[r]) == 0).sum()) + (1 if int((x == P[r, -1]).sum()) > int((P[r] == P[r, -1]).sum()) else 0)
+
     def mlbp_factor_to_var_gemm(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
                                 impl, k0=0, k_len=0):
         k1 = V if k_len == 0 else min(V, k0 + k_len)                # K range of this launch; k0 > 0 adds to D
@@ -280,7 +292,8 @@ class FakeKernels(object):
                 _arr(block_rows, np.int32, n_rows)[n[0]] = r
                 n[0] += 1
 
-    def mlbp_spike_correct(self, words, cnt, entries, rows, n_list, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha):
+    def mlbp_spike_correct(self, words, cnt, entries, rows, n_list, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha,
+                           A_hi_one_pass=None):
         w = _arr(words, np.int32, 5)
         if w[0] != 0:
             return
@@ -300,6 +313,9 @@ class FakeKernels(object):
             acc = np.zeros(V, dtype=np.float32)
             for col, lo in items:
                 acc = (acc + np.float32(lo) * (Bh[col, :V].astype(np.float32) + Bl[col, :V].astype(np.float32))).astype(np.float32)
+                if A_hi_one_pass is not None:
+                    hi = _arr(A_hi_one_pass, np.float16, (r + 1) * ldv).reshape(-1, ldv)[r, col]
+                    acc = (acc + np.float32(hi) * Bl[col, :V].astype(np.float32)).astype(np.float32)
             Dm[d_row0 + r - a0, :V] += np.float32(alpha) * acc
 
     def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs, range_log2,

@@ -220,7 +220,8 @@ def test_spike_compensation_restores_what_two_pass_rows_drop():
     corpus = Corpus(sents)
     roots = corpus.roots_from_positions(roots_pos)
     err, st = {}, {}
-    for name, kw in (('three', dict(msg_passes=3)), ('raw', dict(msg_passes=2, peak_mult=1e9)), ('comp', dict(msg_passes=2, peak_mult=16.0))):
+    for name, kw in (('three', dict(msg_passes=3)), ('raw', dict(msg_passes=2, peak_mult=1e9)), ('comp', dict(msg_passes=2, peak_mult=16.0)),
+                     ('raw1', dict(msg_passes=1, peak_mult=1e9)), ('comp1', dict(msg_passes=1, peak_mult=16.0))):
         eng = Engine(model, kernels=FakeKernels(), **kw)
         eng.set_theta(te, td)
         r = eng.run(corpus, roots, 3, want_beliefs=True)
@@ -234,6 +235,11 @@ def test_spike_compensation_restores_what_two_pass_rows_drop():
     assert 'mlbp_spike_correct' in eng.k.calls
     assert err['comp'] < 0.5 * err['raw']        # (V = 160: the un-spiky remainder of a message still carries 1/sqrt(V) rounding noise)
     assert err['comp'] < 5e-5
+    # ONE-pass message rows (A_hi . B_hi): the compensation also restores hi * T_lo[:, column] at the spikes
+    print('one-pass raw %.2e, one-pass + spike compensation %.2e' % (err['raw1'], err['comp1']), st['comp1'])
+    assert st['comp1']['msg_passes'] == 1 and st['comp1']['spike_flag'] == 1 and st['comp1']['peak_flag'] == 0
+    # (relative error at V = 160; the un-spiky remainder's rounding noise shrinks like 1 / sqrt(V): the default gate is V >= 4096)
+    assert err['comp1'] < 0.5 * err['raw1'] and err['comp1'] < 3e-4
 
 
 def test_one_pass_gradient_rows_restore_spike_cells():
@@ -286,3 +292,33 @@ def test_k_range_launches_are_transparent():
     np.testing.assert_allclose(res[0][3], res[1][3], rtol=2e-6)
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-6)
+
+
+def test_want_topk_lists_the_most_probable_words_best_first():
+    """Engine.run(want_topk=K): the device list of VariableNode.get_max_vocab (LBP.py:402-411) against the reference's own
+    argpartition + argsort calls on the beliefs, and against the oracle's marginals"""
+    model = synth.make_model(96, 24, seed=3)
+    sents = synth.make_corpus(model, 3, k=4, g=1, seed=8)
+    roots_pos = synth.draw_roots(sents, 3, seed=2)
+    corpus = Corpus(sents)
+    eng = make_engine(model)
+    te, td = [0.6, -0.5, 0.1], [0.8, -0.3, 0.6, 0.2, 0.5, -0.2]
+    eng.set_theta(te, td)
+    r = eng.run(corpus, corpus.roots_from_positions(roots_pos), 3, want_grad=False, want_topk=50)
+    idx, val, ties = (x.numpy() for x in r.topk)
+    assert idx.shape == (corpus.n_vars, 50) and (ties == 0).all()
+    B = r.beliefs.numpy()[:, :96]
+    tb = orc.Tables(model, te, td)
+    v = 0
+    for i, s in enumerate(sents):
+        o = orc.run_fast(tb, s, roots_pos[i], 3)
+        for j in range(o['marginals'].shape[0]):
+            a = B[v]
+            top = np.argpartition(a, -50)[-50:]
+            top = top[np.argsort(a[top])][::-1]
+            np.testing.assert_array_equal(idx[v], top)
+            np.testing.assert_array_equal(val[v], a[top])
+            want = np.argsort(-o['marginals'][j], kind='stable')[:50]
+            np.testing.assert_array_equal(idx[v][:10], want[:10])     # (far down the list fp32 beliefs may swap near-equal words)
+            v += 1
+    assert r.top1.numpy().tolist() == idx[:, 0].tolist()

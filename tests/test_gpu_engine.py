@@ -79,7 +79,7 @@ def test_c3_full_size_vs_oracle():
     m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
     worst = common_checks.check_against_oracle(make_engine, m64, sents, roots, [0.8, 0.5, -0.3],
                                                [1.0, -0.6, 0.5, 0.3, 0.4, -0.2])
-    assert worst < 1e-7          # beliefs are O(1e-3) here: 1e-7 absolute is ~1e-4 relative
+    assert worst < 2e-7          # beliefs are O(1e-3) here: 1e-7 absolute is ~1e-4 relative (one-pass message rows: measured 4e-8)
     print('C3 worst belief abs err', worst)
 
 
@@ -166,7 +166,7 @@ def test_properties_at_scale():
     np.testing.assert_allclose(b0.sum(axis=1), 1.0, atol=1e-5)
     assert (b0 >= 0).all()
     np.testing.assert_array_equal(t0, t1)
-    np.testing.assert_allclose(l0, l1, rtol=2e-6)
+    np.testing.assert_allclose(l0, l1, rtol=1e-5)        # (one-pass message rows on the tcgen05 side: measured 2.7e-6)
     np.testing.assert_allclose(g0, g1, rtol=1e-4, atol=2e-6)
     assert np.abs(g0[:, 2]).max() < 1e-9 and np.abs(g0[:, 8]).max() < 1e-9      # bias components
 
@@ -322,41 +322,54 @@ def test_two_pass_message_rows_with_engineered_near_ties():
     corpus = Corpus(sents)
     roots = corpus.roots_from_positions(roots_pos)
     got = {}
-    for name, kw in (('three', dict(msg_passes=3)), ('two_raw', dict(tau=0.0, tau_label=0.0)), ('two', dict())):
+    for name, kw in (('three', dict(msg_passes=3)), ('two_raw', dict(msg_passes=2, tau=0.0, tau_label=0.0)), ('two', dict(msg_passes=2)),
+                     ('one_raw', dict(msg_passes=1, tau=0.0, tau_label=0.0)), ('one', dict())):
         eng = Engine(model, **kw)
         eng.set_theta(te, td)
         r = eng.run(corpus, roots, 3, want_beliefs=True)
         got[name] = (r.top1.cpu().numpy(), r.beliefs.cpu().numpy()[:, :V], r.grad.cpu().numpy(), eng.pass_stats(), r.stats)
     assert got['two'][4]['msg_two_pass'] and got['two'][3]['peak_flag'] == 0 and not got['three'][4]['msg_two_pass']
+    assert got['one'][4]['msg_passes'] == 1 and got['two'][4]['msg_passes'] == 2 and got['one'][3]['peak_flag'] == 0
     flips = {k: int((v[0] != want).sum()) for k, v in got.items()}
-    print('top-1 mismatches vs the float64 oracle (48 engineered near-ties):', flips, got['two'][3])
-    assert flips['two'] == 0
-    assert flips['two_raw'] > 0, 'the ties must sit inside the two-pass error, else this test shows nothing'
-    assert got['two'][3]['rescored'] >= len(want)
+    print('top-1 mismatches vs the float64 oracle (48 engineered near-ties):', flips, got['one'][3])
+    assert flips['two'] == 0 and flips['one'] == 0                # the default engine is 'one'
+    assert flips['two_raw'] > 0 and flips['one_raw'] > 0, 'the ties must sit inside the reduced-pass error, else this test shows nothing'
+    assert got['two'][3]['rescored'] >= len(want) and got['one'][3]['rescored'] >= len(want)
     assert np.abs(got['two'][1] - got['three'][1]).max() < 1e-7
+    assert np.abs(got['one'][1] - got['three'][1]).max() < 5e-7   # (contract: 1e-4)
     np.testing.assert_allclose(got['two'][2], got['three'][2], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got['one'][2], got['three'][2], rtol=3e-5, atol=2e-6)
 
 
-def test_two_pass_equals_three_pass_decisions_at_scale():
-    """a batch too big for the oracle: the default engine (two-pass message rows + re-score at V >= 4096) and the three-pass engine
-    agree on every arg-max and label rank, beliefs within 1e-7, log-posterior 2e-6, gradients 1e-4"""
+@pytest.mark.parametrize('regime', ['flat', 'trained'])
+def test_reduced_pass_rows_equal_three_pass_decisions_at_scale(regime):
+    """a batch too big for the oracle: the default engine (ONE-pass message rows + spike compensation + re-score at V >= 4096),
+    the two-pass engine and the three-pass engine agree on every arg-max and label rank; beliefs within 5e-7 (1e-7 with two
+    passes), log-posterior 1e-5 (2e-6), gradients 1e-4.  'trained' = the theta the bench's SGD reaches after a few steps (the
+    history weight at 7.5: beliefs of 0.8 on the label of every correctly guessed token, spiky messages everywhere)."""
     model = synth.make_model(4352, 512, seed=33, dtype=np.float32)
     sents = synth.make_corpus(model, 48, k=10, g=2, seed=14)
     corpus = Corpus(sents)
     roots = corpus.roots_from_positions(synth.draw_roots(sents, 3, seed=2))
-    te, td = [0.9, 0.4, -0.1], [1.1, -0.5, 0.5, 0.3, 0.4, -0.2]
+    te, td = ([0.9, 0.4, -0.1], [1.1, -0.5, 0.5, 0.3, 0.4, -0.2]) if regime == 'flat' else \
+        ([-0.003, 0.049, -0.3], [0.101, -0.047, 7.534, 0.3, 0.4, -0.2])
     out = []
-    for mp in (3, None):
+    for mp in (3, 2, None):
         eng = Engine(model, msg_passes=mp)
         eng.set_theta(te, td)
         r = eng.run(corpus, roots, 3, want_grad=True, want_marg=True, want_beliefs=True)
         out.append((r.beliefs.cpu().numpy()[:, :4352], r.top1.cpu().numpy(), r.rank.cpu().numpy(), r.logp.cpu().numpy(), r.grad.cpu().numpy(),
                     eng.pass_stats()))
-    assert out[1][5]['msg_two_pass'] and out[1][5]['peak_flag'] == 0 and out[1][5]['rescored'] > 0
-    np.testing.assert_array_equal(out[0][1], out[1][1])
-    rk0, rk1 = out[0][2], out[1][2]
-    assert ((rk0 == rk1) | ((rk0 >= 50) & (rk1 >= 50))).all()
-    assert np.abs(out[0][0] - out[1][0]).max() < 1e-7
-    np.testing.assert_allclose(out[0][3], out[1][3], rtol=2e-6)
-    np.testing.assert_allclose(out[0][4], out[1][4], rtol=1e-4, atol=2e-6)
-    print('two-pass vs three-pass at V=4352:', out[1][5])
+    assert out[1][5]['msg_passes'] == 2 and out[2][5]['msg_passes'] == 1
+    if regime == 'trained':
+        assert out[2][5]['spike_flag'] == 1 and out[0][0].max() > 0.5, 'the trained regime must be peaked'
+    for o, b_tol, l_tol in ((out[1], 1e-7, 2e-6), (out[2], 5e-7, 1e-5)):
+        assert o[5]['msg_two_pass'] and o[5]['peak_flag'] == 0 and o[5]['rescored'] > 0
+        np.testing.assert_array_equal(out[0][1], o[1])
+        rk0, rk1 = out[0][2], o[2]
+        assert ((rk0 == rk1) | ((rk0 >= 50) & (rk1 >= 50))).all()
+        print(regime, 'passes', o[5]['msg_passes'], 'max belief diff %.2e' % np.abs(out[0][0] - o[0]).max(),
+              'max rel logp diff %.2e' % np.abs(o[3] / out[0][3] - 1).max(), o[5])
+        assert np.abs(out[0][0] - o[0]).max() < b_tol
+        np.testing.assert_allclose(out[0][3], o[3], rtol=l_tol)
+        np.testing.assert_allclose(out[0][4], o[4], rtol=1e-4, atol=2e-6)

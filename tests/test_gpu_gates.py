@@ -68,7 +68,7 @@ def test_reduced_pass_rows_on_sparse_and_peaked_data(name):
         np.testing.assert_allclose(G[i], ref, rtol=1e-4, atol=2e-6)
         nz = np.abs(ref) > 1e-3
         worst_g = max(worst_g, float((np.abs(G[i] - ref)[nz] / np.abs(ref)[nz]).max()))
-        np.testing.assert_allclose(LP[i], o['logp'], rtol=2e-6)
+        np.testing.assert_allclose(LP[i], o['logp'], rtol=1e-5)   # (one-pass message rows: measured 3.2e-6; two-pass 1e-6)
     print('%s: largest belief %.3f, worst belief abs err %.2e, worst rel gradient err %.2e' % (name, peak, worst_b, worst_g))
     assert worst_b < 1e-5                      # contract: 1e-4
     if 'peaked' in name:
@@ -85,5 +85,5 @@ def test_c3_full_size_six_sentences_vs_oracle():
     m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
     worst = common_checks.check_against_oracle(lambda m: Engine(m), m64, sents, roots, [0.8, 0.5, -0.3],
                                                [1.0, -0.6, 0.5, 0.3, 0.4, -0.2])
-    assert worst < 1e-7
+    assert worst < 2e-7                          # (one-pass message rows: measured 4e-8; contract 1e-4)
     print('C3 x 6 worst belief abs err', worst)

@@ -339,7 +339,7 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     n_blk = M - a0
     _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D), 1, ld, 0.5, 256, P(words), 0, 0, 0, S()))
     before = D.clone()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, None, S()))
     torch.cuda.synchronize()
     got, was = D.cpu().numpy(), before.cpu().numpy()
     full = 0.5 * (Ax[a0:] @ Bx.T)
@@ -357,9 +357,24 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     # PEAK set: the block ran three passes, the correction must not touch it
     words[0] = 1
     D2 = before.clone()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, None, S()))
     torch.cuda.synchronize()
     assert torch.equal(D2, before)
+    # ONE-pass rows (A_hi . B_hi): with A_hi passed the correction also restores hi_s * B_lo[:, col_s] at the spikes
+    words[0] = 0
+    D3 = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D3), 1, ld, 0.5, 256 | 512, P(words), 0, 0, 0, S()))
+    was3 = D3.cpu().numpy()
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D3), 1, ld, 0.5, P(Ah), S()))
+    torch.cuda.synchronize()
+    got3 = D3.cpu().numpy()
+    ah, bh = Ah.cpu().numpy()[:, :V].astype(np.float64), Bh.cpu().numpy()[:, :V].astype(np.float64)
+    for r, cols in spikes.items():
+        i = 1 + r - a0
+        want = was3[i, :V].astype(np.float64)
+        for c in cols:                                             # exact spike term minus what the one-pass product held of it
+            want += 0.5 * (Ax[r, c] * Bx[:, c] - ah[r, c] * bh[:, c])
+        assert np.abs(got3[i, :V] - want).max() / np.abs(want).max() < 2e-6, r
 
 
 def test_gemm_k_ranges_accumulate(lib):
@@ -381,3 +396,39 @@ def test_gemm_k_ranges_accumulate(lib):
     assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
     assert (D.cpu().numpy()[:, V:] == 0).all()
     assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
+
+
+@pytest.mark.parametrize('V,K', [(10000, 50), (67, 50), (2049, 1), (513, 513), (5000, 1024)])
+def test_topk_rows_matches_numpy(lib, V, K):
+    """mlbp_topk_rows == the reference's np.argpartition + np.argsort list (LBP.py:402-411) on rows without exact ties;
+    rows WITH exact ties are flagged and listed in (value descending, index ascending) order"""
+    rng = np.random.default_rng(V + K)
+    n = 37
+    ld = (V + 63) // 64 * 64
+    X = np.zeros((n, ld), dtype=np.float32)
+    X[:, :V] = rng.random((n, V), dtype=np.float32) ** 8                # a peaked, tie-free spread
+    X[:, :V] /= X[:, :V].sum(axis=1, keepdims=True)
+    X[:, V:] = 7.0                                                      # row padding must never be listed
+    X[3, :V] = 1.0 / V                                                  # all equal
+    if V > 200:
+        X[5, 100:110] = X[5, :V].max() * 2                               # ten equal maxima
+        X[7, :V] = 0; X[7, 11] = 1.0                                     # a delta: zeros tie at the boundary (when K > 1)
+    x = torch.from_numpy(X).cuda()
+    idx = torch.empty((n, K), dtype=torch.int32, device='cuda')
+    val = torch.empty((n, K), dtype=torch.float32, device='cuda')
+    ties = torch.empty(n, dtype=torch.int32, device='cuda')
+    _lib.check(lib.mlbp_topk_rows(P(x), ld, V, n, K, P(idx), P(val), P(ties), S()))
+    torch.cuda.synchronize()
+    I, Pv, T = idx.cpu().numpy(), val.cpu().numpy(), ties.cpu().numpy()
+    for r in range(n):
+        a = X[r, :V]
+        want = np.lexsort((np.arange(V), -a))[:K]
+        np.testing.assert_array_equal(I[r], want, err_msg='row %d' % r)
+        np.testing.assert_array_equal(Pv[r], a[want])
+        exact_ties = (np.diff(a[want]) == 0).any() or (K < V and np.sort(a)[::-1][K] == a[want][-1])
+        assert (T[r] > 0) == bool(exact_ties), (r, T[r])
+        if not exact_ties:                                              # the reference's own calls give the same list
+            top = np.argpartition(a, -K)[-K:]
+            top = top[np.argsort(a[top])][::-1]
+            np.testing.assert_array_equal(I[r], top)
+    assert lib.mlbp_topk_rows(P(x), ld, V, n, V + 1, P(idx), P(val), P(ties), S()) != 0   # K > V is rejected
