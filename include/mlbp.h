@@ -314,6 +314,8 @@ void mlbp_plan_destroy(mlbp_plan *p);
 #define MLBP_PLAN_MAX_IN       6   /* largest number of incoming pairwise messages of any variable            */
 #define MLBP_PLAN_HDR_WORDS    7   /* blob header length; layout documented in csrc/plan.cpp                  */
 #define MLBP_PLAN_N_DEAD       8   /* updates removed because nothing reads their result                      */
+#define MLBP_PLAN_TMPL_HITS    9   /* graphs whose schedule template was already compiled (csrc/plan.cpp)     */
+#define MLBP_PLAN_TMPL_MISSES 10   /* graphs whose template this call compiled                                */
 
 #ifdef __cplusplus
 }

@@ -27,12 +27,17 @@
 // Blob layout (int32 words), header first:
 //   [H_*] fixed header, then per-level records (LEV_WORDS each), then the index arrays they point to.
 #include <algorithm>
+#include <atomic>
+#include <deque>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
 #include <chrono>
 #include <cstdio>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mlbp.h"
@@ -213,7 +218,132 @@ void build_sequence(Graph &g, const int32_t *roots, int sweeps) {
 struct ChunkOut {
     std::vector<std::vector<int32_t>> grp_u, grp_off, in_row, dest_off, dest, first, second;   // [level]
     std::vector<int32_t> init_rows, pair_c, pair_r, pair_z, pair_u0, pair_u1, pair_u2, pair_g1, pair_gv0, pair_gv1, mu, moff, min_;
+    void set_levels(int n_levels) {
+        grp_u.resize(n_levels + 1); grp_off.resize(n_levels + 1); in_row.resize(n_levels + 1); dest_off.resize(n_levels + 1);
+        dest.resize(n_levels + 1); first.resize(n_levels + 1); second.resize(n_levels + 1);
+    }
 };
+
+// Where one graph's rows start.  Every row index the emit phase writes is `base + small local index`:
+//   blk[level * 4 + table]  A row of the graph's first GEMM row in that (level, table) block (its D row is MLBP_D_CONST_ROWS further)
+//   rz / rn [gap class]     gradient-stage copies of r: factors that need a Z GEMM row of their own / the others
+//   c                       gradient-stage c rows;  u0 / u1z / u1n / u2z / u2n: the D rows of the gradient-stage GEMMs
+//   var                     the graph's first variable
+struct Bases {
+    const int64_t *blk;
+    int64_t rz[2], rn[2], c, u0[2], u1z[2], u1n[2], u2z, u2n, var;
+};
+
+struct EmitScratch {
+    std::vector<int32_t> dcount, dstart, dflat, ver, tgt;
+    std::vector<std::vector<int32_t>> lev_ops;
+};
+
+// phase C for ONE graph: global rows, destinations, leave-one-out groups, gradient / marginal index lists appended to `co`
+static void emit_graph(const Graph &g, const Bases &B, bool want_grad, bool want_marg, ChunkOut &co, EmitScratch &sc) {
+    auto &dcount = sc.dcount; auto &dstart = sc.dstart; auto &dflat = sc.dflat; auto &ver = sc.ver; auto &tgt = sc.tgt;
+    auto &lev_ops = sc.lev_ops;
+    if ((int)lev_ops.size() < g.n_levels + 1) lev_ops.resize(g.n_levels + 1);
+    auto a_row = [&](const Op &o) -> int32_t { return (int32_t)(B.blk[(size_t)o.level * 4 + o.table] + o.row); };
+    // destinations of every variable->factor version = A rows of the GEMM rows that read it (counting sort)
+    const size_t nops = g.ops.size();
+    dcount.assign(nops + 1, 0);
+    // A row of the gradient-stage copy of r for factor f; advances the per-class counters
+    auto r_row_of = [&](int f, int64_t *iz, int64_t *in) -> int64_t {
+        const int k = g.gap1[f];
+        return g.zmode[f] ? B.rn[k] + in[k]++ : B.rz[k] + iz[k]++;
+    };
+    auto each_consumer = [&](auto &&fn) {
+        for (const Op &o : g.ops) {
+            if (!o.live || o.kind != 1 || o.folded) continue;
+            fn(g.inputs[o.in0], a_row(o));
+        }
+        if (want_grad) {
+            int64_t iz[2] = {0, 0}, in[2] = {0, 0};
+            for (int f = 0; f < g.np; ++f) {
+                fn(g.fin_v2f[2 * f + 1], (int32_t)r_row_of(f, iz, in));
+                fn(g.fin_v2f[2 * f + 0], (int32_t)(B.c + f));
+            }
+        }
+    };
+    each_consumer([&](int prod, int32_t row) { if (prod >= 0) ++dcount[prod]; else co.init_rows.push_back(row); });
+    dstart.assign(nops + 1, 0);
+    for (size_t i = 0; i < nops; ++i) dstart[i + 1] = dstart[i] + dcount[i];
+    dflat.resize(dstart[nops]);
+    std::fill(dcount.begin(), dcount.end(), 0);
+    each_consumer([&](int prod, int32_t row) { if (prod >= 0) dflat[dstart[prod] + dcount[prod]++] = row; });
+    if (want_grad) {
+        int64_t iz[2] = {0, 0}, in[2] = {0, 0};
+        for (int f = 0; f < g.np; ++f) {
+            const int k = g.gap1[f];
+            const bool zrow = !g.zmode[f];                       // the factor has a Z GEMM row of its own
+            const int64_t li = zrow ? iz[k] : in[k];             // index inside its class before r_row_of advances it
+            const int64_t rrow = r_row_of(f, iz, in);
+            co.pair_c.push_back((int32_t)(B.c + f));
+            co.pair_r.push_back((int32_t)rrow);
+            if (!zrow) {                                         // Z from the D row of a message update
+                const int side = g.zmode[f] - 1;
+                co.pair_u0.push_back(MLBP_D_CONST_ROWS + a_row(g.ops[g.fin_f2v[2 * f + side]]));
+                co.pair_z.push_back((int32_t)(side == 0 ? B.c + f : rrow));
+            } else {
+                co.pair_u0.push_back((int32_t)(B.u0[k] + li));
+                co.pair_z.push_back((int32_t)(B.c + f));
+            }
+            co.pair_u1.push_back((int32_t)((zrow ? B.u1z[k] : B.u1n[k]) + li));
+            co.pair_u2.push_back(k ? (int32_t)((zrow ? B.u2z : B.u2n) + li) : -1);
+            co.pair_g1.push_back(g.gap1[f]);
+            co.pair_gv0.push_back((int32_t)(B.var + g.v0[f]));
+            co.pair_gv1.push_back((int32_t)(B.var + g.v1[f]));
+        }
+    }
+    auto d_row_of = [&](int prod) -> int32_t {
+        if (prod < 0) return -1;
+        return g.ops[prod].folded ? 1 + g.ops[prod].table : MLBP_D_CONST_ROWS + a_row(g.ops[prod]);
+    };
+    // leave-one-out groups: live variable->factor updates of one (level, variable)
+    for (auto &v : lev_ops) v.clear();
+    for (size_t i = 0; i < nops; ++i)
+        if (g.ops[i].live && g.ops[i].kind == 0) lev_ops[g.ops[i].level].push_back((int32_t)i);
+    for (int L = 1; L <= g.n_levels; ++L) {
+        auto &lo = lev_ops[L];
+        if (lo.empty()) continue;
+        std::stable_sort(lo.begin(), lo.end(), [&](int32_t x, int32_t y) {
+            return var_of(g, g.ops[x].f, g.ops[x].side) < var_of(g, g.ops[y].f, g.ops[y].side);
+        });
+        size_t i = 0;
+        while (i < lo.size()) {
+            const int v = var_of(g, g.ops[lo[i]].f, g.ops[lo[i]].side);
+            size_t j = i;
+            while (j < lo.size() && var_of(g, g.ops[lo[j]].f, g.ops[lo[j]].side) == v) ++j;
+            const auto &fs = g.facset[v];
+            ver.assign(fs.size(), -2);                   // producer seen by a reader in this group; -2 = nobody reads
+            tgt.assign(fs.size(), -1);                   // update that targets this edge
+            for (size_t k = i; k < j; ++k) {
+                const Op &o = g.ops[lo[k]];
+                tgt[g.slot[2 * o.f + o.side]] = lo[k];
+                for (int q = o.in0; q < o.in1; ++q) ver[g.slot[g.in_edge[q]]] = g.inputs[q];
+            }
+            co.grp_u[L].push_back((int32_t)(B.var + v));
+            for (size_t s = 0; s < fs.size(); ++s) {
+                co.in_row[L].push_back(ver[s] == -2 ? -1 : d_row_of(ver[s]));
+                if (tgt[s] >= 0)
+                    co.dest[L].insert(co.dest[L].end(), dflat.begin() + dstart[tgt[s]], dflat.begin() + dstart[tgt[s] + 1]);
+                // first reader's row per slot (-1: none): spares the kernels one dependent index load
+                co.first[L].push_back(tgt[s] >= 0 && dstart[tgt[s] + 1] > dstart[tgt[s]] ? dflat[dstart[tgt[s]]] : -1);
+                co.second[L].push_back(tgt[s] >= 0 && dstart[tgt[s] + 1] > dstart[tgt[s]] + 1 ? dflat[dstart[tgt[s]] + 1] : -1);
+                co.dest_off[L].push_back((int32_t)co.dest[L].size());
+            }
+            co.grp_off[L].push_back((int32_t)co.in_row[L].size());
+            i = j;
+        }
+    }
+    if (want_marg)
+        for (int v = 0; v < g.nv; ++v) {
+            co.mu.push_back((int32_t)(B.var + v));
+            for (int f : g.facset[v]) co.min_.push_back(d_row_of(g.fin_f2v[2 * f + ((g.v0[f] == v) ? 0 : 1)]));
+            co.moff.push_back((int32_t)co.min_.size());
+        }
+}
 
 template <class F>
 static void parallel_for_chunks(int n_chunks, F f) {
@@ -223,6 +353,163 @@ static void parallel_for_chunks(int n_chunks, F f) {
     for (auto &t : th) t.join();
 }
 
+// ---- phase A for ONE graph: wiring, sequence, levels, liveness, Z sources.  Returns 0 or an error code (1 = no variables,
+// 2 = bad factor variables, 3 = root out of range)
+static int analyse_graph(Graph &g, int nv, int np, const int32_t *v0, const int32_t *v1, const int32_t *gap1, const int32_t *r,
+                         int sweeps, int flags, std::vector<char> &needed, int64_t &n_dead) {
+    const bool want_grad = flags & 1, want_marg = flags & 2, reuse_z = !(flags & 8);
+    g.fold = !(flags & 4);
+    g.nv = nv;
+    g.np = np;
+    if (g.nv <= 0) return 1;
+    g.facset.assign(g.nv, {});
+    g.v0.resize(g.np); g.v1.resize(g.np); g.gap1.resize(g.np);
+    g.slot.resize(2 * (size_t)g.np);
+    for (int f = 0; f < g.np; ++f) {
+        const int a = v0[f], b = v1[f];
+        if (a < 0 || b < 0 || a >= g.nv || b >= g.nv || a == b) return 2;
+        g.v0[f] = a; g.v1[f] = b; g.gap1[f] = gap1[f] ? 1 : 0;
+        g.slot[2 * f] = (int32_t)g.facset[a].size();
+        g.facset[a].push_back(f);
+        g.slot[2 * f + 1] = (int32_t)g.facset[b].size();
+        g.facset[b].push_back(f);
+    }
+    for (int i = 0; i <= sweeps; ++i)
+        if (r[i] < 0 || r[i] >= g.nv) return 3;
+    {   // one allocation per vector: 4 np updates per sweep, a variable update reads deg - 1 messages
+        size_t reads = 0;
+        for (int v = 0; v < g.nv; ++v) reads += g.facset[v].size() * g.facset[v].size();
+        g.ops.reserve((size_t)4 * g.np * sweeps + 8);
+        g.lvl.reserve((size_t)4 * g.np * sweeps + 8);
+        g.inputs.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
+        g.in_edge.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
+    }
+    build_sequence(g, r, sweeps);
+    // liveness, reverse pass: an update is live iff a live update (or a final stage) reads its result
+    needed.assign(g.ops.size(), 0);
+    for (int e = 0; e < 2 * g.np; ++e) {
+        if (want_grad && g.fin_v2f[e] >= 0) needed[g.fin_v2f[e]] = 1;
+        if (want_marg && g.fin_f2v[e] >= 0) needed[g.fin_f2v[e]] = 1;
+    }
+    for (size_t i = g.ops.size(); i-- > 0;) {
+        Op &o = g.ops[i];
+        o.live = needed[i];
+        if (!o.live) { ++n_dead; continue; }
+        for (int k = o.in0; k < o.in1; ++k)
+            if (g.inputs[k] >= 0) needed[g.inputs[k]] = 1;
+    }
+    // Z source per factor: 1 = D row of the last f->v0 update (= T r, dot with c), 2 = D row of the last
+    // f->v1 update (= T'c, dot with r), 0 = a GEMM row of its own
+    g.zmode.assign(g.np, 0);
+    if (want_grad && reuse_z)
+        for (int f = 0; f < g.np; ++f)
+            for (int side = 0; side < 2 && !g.zmode[f]; ++side) {
+                const int o = g.fin_f2v[2 * f + side], src = g.fin_v2f[2 * f + (1 - side)];
+                if (o >= 0 && src >= 0 && g.ops[o].live && !g.ops[o].folded && g.inputs[g.ops[o].in0] == src)
+                    g.zmode[f] = (int8_t)(1 + side);
+            }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Schedule TEMPLATES.  Everything phases A and C derive for a graph depends only on its wiring (variables of every pairwise
+// factor, gap classes), its roots and the flags -- not on where its rows land in the batch: every emitted index is
+// `base of one of the graph's row segments + small local index` (struct Bases).  A training corpus repeats a few wirings
+// (create_factor_graph builds a clique over the predicted tokens of a sentence, train.py:255-330) and draws the roots from a
+// small set, so a template is compiled once per (wiring, roots, flags) with SYMBOLIC bases -- entry = segment << 16 | local --
+// and kept; an instance of it is a relocation: entry -> base[segment] + local.  The literal path below stays as the
+// fallback (graphs too large for the 16-bit local index) and as the cross-check of the tests (MLBP_PLAN_TEMPLATES=0).
+namespace {
+
+enum { SEG_LIT = 0, SEG_BLK0 = 1, SEG_GRAD = 32700, SEG_RZ = SEG_GRAD, SEG_RN = SEG_GRAD + 2, SEG_C = SEG_GRAD + 4,
+       SEG_U0 = SEG_GRAD + 5, SEG_U1Z = SEG_GRAD + 7, SEG_U1N = SEG_GRAD + 9, SEG_U2Z = SEG_GRAD + 11, SEG_U2N = SEG_GRAD + 12,
+       SEG_VAR = SEG_GRAD + 13, SEG_N = 32768 };
+constexpr int64_t LOCAL_MAX = 65536 - 16;
+
+struct Tmpl {
+    int err = 0;                                 // analyse_graph's code; -1 = valid but too large for the 16-bit local index
+    int nv = 0, np = 0, n_levels = 0, max_in = 0;
+    int64_t n_dead = 0, nz[2] = {0, 0}, nn[2] = {0, 0};
+    std::vector<int32_t> lt, lt_rows;            // (level * 4 + table) blocks this graph has GEMM rows in, and how many
+    ChunkOut co;                                 // emit_graph's output for the graph alone, symbolic bases
+    size_t bytes = 0;
+};
+
+struct KeyHash {
+    size_t operator()(const std::vector<int32_t> &k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (int32_t x : k) { h ^= (uint32_t)x; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+
+std::mutex g_tmpl_mutex;
+std::unordered_map<std::vector<int32_t>, std::shared_ptr<const Tmpl>, KeyHash> g_tmpl_cache;
+size_t g_tmpl_bytes = 0;
+int64_t g_tmpl_hits = 0, g_tmpl_misses = 0;
+
+size_t chunk_bytes(const ChunkOut &co) {
+    size_t n = 0;
+    for (auto *vv : {&co.grp_u, &co.grp_off, &co.in_row, &co.dest_off, &co.dest, &co.first, &co.second})
+        for (const auto &v : *vv) n += v.capacity();
+    for (auto *v : {&co.init_rows, &co.pair_c, &co.pair_r, &co.pair_z, &co.pair_u0, &co.pair_u1, &co.pair_u2, &co.pair_g1,
+                    &co.pair_gv0, &co.pair_gv1, &co.mu, &co.moff, &co.min_})
+        n += v->capacity();
+    return n * sizeof(int32_t);
+}
+
+std::shared_ptr<const Tmpl> build_template(int nv, int np, const int32_t *v0, const int32_t *v1, const int32_t *gap1,
+                                           const int32_t *r, int sweeps, int flags) {
+    auto T = std::make_shared<Tmpl>();
+    Graph g;
+    std::vector<char> needed;
+    T->nv = nv; T->np = np;
+    T->err = analyse_graph(g, nv, np, v0, v1, gap1, r, sweeps, flags, needed, T->n_dead);
+    if (T->err) return T;
+    const bool want_grad = flags & 1, want_marg = flags & 2;
+    T->n_levels = g.n_levels;
+    for (int v = 0; v < g.nv; ++v) T->max_in = std::max(T->max_in, (int)g.facset[v].size());
+    const size_t LT = (size_t)(g.n_levels + 1) * 4;
+    if ((int64_t)LT + SEG_BLK0 >= SEG_GRAD || (int64_t)g.ops.size() >= LOCAL_MAX || nv >= LOCAL_MAX || np >= LOCAL_MAX) { T->err = -1; return T; }
+    // local rows inside each (level, table) block, in op order (what phase B of the literal path assigns)
+    std::vector<int32_t> cnt(LT, 0);
+    for (Op &o : g.ops)
+        if (o.live && o.kind == 1 && !o.folded) o.row = cnt[(size_t)o.level * 4 + o.table]++;
+    for (size_t i = 0; i < LT; ++i)
+        if (cnt[i]) { T->lt.push_back((int32_t)i); T->lt_rows.push_back(cnt[i]); }
+    if (want_grad)
+        for (int f = 0; f < g.np; ++f) (g.zmode[f] ? T->nn : T->nz)[g.gap1[f]]++;
+    std::vector<int64_t> blk(LT);
+    for (size_t i = 0; i < LT; ++i) blk[i] = (int64_t)(SEG_BLK0 + i) << 16;
+    Bases B;
+    B.blk = blk.data();
+    auto S = [](int seg) { return (int64_t)seg << 16; };
+    for (int k = 0; k < 2; ++k) { B.rz[k] = S(SEG_RZ + k); B.rn[k] = S(SEG_RN + k); B.u0[k] = S(SEG_U0 + k); B.u1z[k] = S(SEG_U1Z + k); B.u1n[k] = S(SEG_U1N + k); }
+    B.c = S(SEG_C); B.u2z = S(SEG_U2Z); B.u2n = S(SEG_U2N); B.var = S(SEG_VAR);
+    EmitScratch sc;
+    T->co.set_levels(g.n_levels);
+    emit_graph(g, B, want_grad, want_marg, T->co, sc);
+    T->bytes = chunk_bytes(T->co) + 256;
+    return T;
+}
+
+// relocation of one template entry
+inline int32_t reloc(int32_t x, const int64_t *SB) { return x < 65536 ? x : (int32_t)(SB[x >> 16] + (x & 0xffff)); }
+inline void append_reloc(std::vector<int32_t> &dst, const std::vector<int32_t> &src, const int64_t *SB) {
+    const size_t n0 = dst.size();
+    dst.resize(n0 + src.size());
+    int32_t *d = dst.data() + n0;
+    for (size_t i = 0; i < src.size(); ++i) d[i] = reloc(src[i], SB);
+}
+inline void append_shift(std::vector<int32_t> &dst, const std::vector<int32_t> &src, int32_t shift) {
+    const size_t n0 = dst.size();
+    dst.resize(n0 + src.size());
+    int32_t *d = dst.data() + n0;
+    for (size_t i = 0; i < src.size(); ++i) d[i] = src[i] + shift;
+}
+
+}  // namespace
+
 extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int32_t *pair_off, const int32_t *pair_v0,
                                  const int32_t *pair_v1, const int32_t *pair_gap1, const int32_t *roots, int sweeps,
                                  int flags, mlbp_plan **out) {
@@ -230,266 +517,304 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         mlbp::set_error("plan_compile: bad argument");
         return MLBP_ERR_INVALID;
     }
-    const bool want_grad = flags & 1, want_marg = flags & 2, reuse_z = !(flags & 8);
+    const bool want_grad = flags & 1, want_marg = flags & 2;
     const bool prof = std::getenv("MLBP_PLAN_PROFILE") != nullptr;
     auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_a = tnow();
-    std::vector<Graph> G(n_graphs);
     unsigned hw = std::thread::hardware_concurrency();
     const char *env = std::getenv("MLBP_PLAN_THREADS");
     int n_chunks = env ? std::atoi(env) : (int)std::min<unsigned>(hw ? hw : 1, 32);
     n_chunks = std::max(1, std::min(n_chunks, (n_graphs + 15) / 16));
     auto chunk_lo = [&](int c) { return (int)((int64_t)n_graphs * c / n_chunks); };
+    const char *env_t = std::getenv("MLBP_PLAN_TEMPLATES");
+    bool templated = !(env_t && std::atoi(env_t) == 0);
+    auto bad_graph = [](int code) {
+        mlbp::set_error("plan_compile: invalid graph (code %d: 1 = no variables, 2 = bad factor variables, 3 = root out of range)", code);
+        return MLBP_ERR_INVALID;
+    };
 
-    // ---- phase A (parallel): sequence, levels, liveness per graph
-    std::vector<int> err(n_chunks, 0), c_levels(n_chunks, 0), c_maxin(n_chunks, 0);
-    std::vector<int64_t> c_dead(n_chunks, 0);
-    parallel_for_chunks(n_chunks, [&](int c) {
-        std::vector<char> needed;
-        for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
-            Graph &g = G[gi];
-            g.fold = !(flags & 4);
-            g.nv = var_off[gi + 1] - var_off[gi];
-            g.np = pair_off[gi + 1] - pair_off[gi];
-            if (g.nv <= 0) { err[c] = 1; return; }
-            g.facset.assign(g.nv, {});
-            g.v0.resize(g.np); g.v1.resize(g.np); g.gap1.resize(g.np);
-            g.slot.resize(2 * (size_t)g.np);
-            for (int f = 0; f < g.np; ++f) {
-                const int a = pair_v0[pair_off[gi] + f], b = pair_v1[pair_off[gi] + f];
-                if (a < 0 || b < 0 || a >= g.nv || b >= g.nv || a == b) { err[c] = 2; return; }
-                g.v0[f] = a; g.v1[f] = b; g.gap1[f] = pair_gap1[pair_off[gi] + f] ? 1 : 0;
-                g.slot[2 * f] = (int32_t)g.facset[a].size();
-                g.facset[a].push_back(f);
-                g.slot[2 * f + 1] = (int32_t)g.facset[b].size();
-                g.facset[b].push_back(f);
-            }
-            const int32_t *r = roots + (size_t)gi * (1 + sweeps);
-            for (int i = 0; i <= sweeps; ++i)
-                if (r[i] < 0 || r[i] >= g.nv) { err[c] = 3; return; }
-            {   // one allocation per vector: 4 np updates per sweep, a variable update reads deg - 1 messages
-                size_t reads = 0;
-                for (int v = 0; v < g.nv; ++v) reads += g.facset[v].size() * g.facset[v].size();
-                g.ops.reserve((size_t)4 * g.np * sweeps + 8);
-                g.lvl.reserve((size_t)4 * g.np * sweeps + 8);
-                g.inputs.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
-                g.in_edge.reserve(((size_t)2 * g.np + reads) * sweeps + 8);
-            }
-            build_sequence(g, r, sweeps);
-            // liveness, reverse pass: an update is live iff a live update (or a final stage) reads its result
-            needed.assign(g.ops.size(), 0);
-            for (int e = 0; e < 2 * g.np; ++e) {
-                if (want_grad && g.fin_v2f[e] >= 0) needed[g.fin_v2f[e]] = 1;
-                if (want_marg && g.fin_f2v[e] >= 0) needed[g.fin_f2v[e]] = 1;
-            }
-            for (size_t i = g.ops.size(); i-- > 0;) {
-                Op &o = g.ops[i];
-                o.live = needed[i];
-                if (!o.live) { ++c_dead[c]; continue; }
-                for (int k = o.in0; k < o.in1; ++k)
-                    if (g.inputs[k] >= 0) needed[g.inputs[k]] = 1;
-            }
-            // Z source per factor: 1 = D row of the last f->v0 update (= T r, dot with c), 2 = D row of the last
-            // f->v1 update (= T'c, dot with r), 0 = a GEMM row of its own
-            g.zmode.assign(g.np, 0);
-            if (want_grad && reuse_z)
-                for (int f = 0; f < g.np; ++f)
-                    for (int side = 0; side < 2 && !g.zmode[f]; ++side) {
-                        const int o = g.fin_f2v[2 * f + side], src = g.fin_v2f[2 * f + (1 - side)];
-                        if (o >= 0 && src >= 0 && g.ops[o].live && !g.ops[o].folded && g.inputs[g.ops[o].in0] == src)
-                            g.zmode[f] = (int8_t)(1 + side);
-                    }
-            c_levels[c] = std::max(c_levels[c], g.n_levels);
-            for (int v = 0; v < g.nv; ++v) c_maxin[c] = std::max(c_maxin[c], (int)g.facset[v].size());
-        }
-    });
     int n_levels = 0, max_in = 0;
     int64_t n_dead = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-        if (err[c]) {
-            mlbp::set_error("plan_compile: invalid graph (code %d: 1 = no variables, 2 = bad factor variables, 3 = root out of range)", err[c]);
-            return MLBP_ERR_INVALID;
-        }
-        n_levels = std::max(n_levels, c_levels[c]); max_in = std::max(max_in, c_maxin[c]); n_dead += c_dead[c];
-    }
-
-    double t_b = tnow();
-    // ---- phase B (serial, cheap): one A/D block per (level, table); rows inside a block in graph order
-    const size_t LT = (size_t)(n_levels + 1) * 4;
-    std::vector<int64_t> cnt(LT, 0);
-    std::vector<int64_t> gbase((size_t)n_graphs * LT);            // first row index (inside the block) of each graph
-    // gradient-stage r rows per gap class: first the factors that need a Z GEMM row (z), then the others (n)
+    std::vector<int64_t> cnt, base;
+    size_t LT = 0;
+    int64_t n_pair = 0, n_z[2] = {0, 0}, n_n[2] = {0, 0}, n_gap0 = 0, n_gap1 = 0, n_msg_rows = 0, a_rows = 0, d_rows = 0;
+    int64_t a_r0 = 0, a_r1 = 0, a_c = 0, d_u0_0 = 0, d_u1_0 = 0, d_u0_1 = 0, d_u1_1 = 0, d_u2_1 = 0;
+    // block bases and the gradient-stage layout from the per-(level, table) row counts and the pair counts
+    auto layout = [&]() -> bool {
+        n_gap0 = n_z[0] + n_n[0]; n_gap1 = n_z[1] + n_n[1];
+        base.assign(LT, 0);
+        a_rows = 0;
+        for (int L = 1; L <= n_levels; ++L)
+            for (int t = 0; t < 4; ++t) { base[(size_t)L * 4 + t] = a_rows; a_rows += cnt[(size_t)L * 4 + t]; }
+        n_msg_rows = a_rows;
+        // gradient stage: r rows (gap>1 block, gap==1 block), then the c rows; D row = 1 + A row for message rows
+        a_r0 = a_rows; a_r1 = a_r0 + n_gap0; a_c = a_r1 + n_gap1;
+        a_rows = a_c + n_pair;
+        d_rows = MLBP_D_CONST_ROWS + n_msg_rows;
+        d_u0_0 = d_rows; d_u1_0 = d_u0_0 + n_z[0]; d_u0_1 = d_u1_0 + n_gap0; d_u1_1 = d_u0_1 + n_z[1]; d_u2_1 = d_u1_1 + n_gap1;
+        if (want_grad) d_rows = d_u2_1 + n_gap1;
+        return !(a_rows > 0x7fffff00ll || d_rows > 0x7fffff00ll);
+    };
+    // first rows of graph gi's segments (gradient stage and variables; the (level, table) blocks are set by the caller)
     std::vector<int64_t> g_iz[2], g_in[2], g_ip(n_graphs);
     for (int k = 0; k < 2; ++k) { g_iz[k].resize(n_graphs); g_in[k].resize(n_graphs); }
-    int64_t n_pair = 0, n_z[2] = {0, 0}, n_n[2] = {0, 0};
-    for (int gi = 0; gi < n_graphs; ++gi) {
-        Graph &g = G[gi];
-        int64_t *gb = &gbase[(size_t)gi * LT];
-        for (size_t i = 0; i < LT; ++i) gb[i] = cnt[i];
-        for (Op &o : g.ops)
-            if (o.live && o.kind == 1 && !o.folded) o.row = (int32_t)(cnt[(size_t)o.level * 4 + o.table]++ - gb[(size_t)o.level * 4 + o.table]);
-        for (int k = 0; k < 2; ++k) { g_iz[k][gi] = n_z[k]; g_in[k][gi] = n_n[k]; }
-        g_ip[gi] = n_pair;
-        if (want_grad) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.zmode[f] ? n_n : n_z)[g.gap1[f]]++; }
-    }
-    const int64_t n_gap0 = n_z[0] + n_n[0], n_gap1 = n_z[1] + n_n[1];
-    std::vector<int64_t> base(LT, 0);
-    int64_t a_rows = 0;
-    for (int L = 1; L <= n_levels; ++L)
-        for (int t = 0; t < 4; ++t) { base[(size_t)L * 4 + t] = a_rows; a_rows += cnt[(size_t)L * 4 + t]; }
-    const int64_t n_msg_rows = a_rows;
-    // gradient stage: r rows (gap>1 block, gap==1 block), then the c rows; D row = 1 + A row for message rows
-    const int64_t a_r0 = a_rows, a_r1 = a_r0 + n_gap0, a_c = a_r1 + n_gap1;
-    a_rows = a_c + n_pair;
-    int64_t d_rows = MLBP_D_CONST_ROWS + n_msg_rows;
-    const int64_t d_u0_0 = d_rows, d_u1_0 = d_u0_0 + n_z[0], d_u0_1 = d_u1_0 + n_gap0, d_u1_1 = d_u0_1 + n_z[1],
-                  d_u2_1 = d_u1_1 + n_gap1;
-    if (want_grad) d_rows = d_u2_1 + n_gap1;
-    if (a_rows > 0x7fffff00ll || d_rows > 0x7fffff00ll) { mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
-
-    double t_c = tnow();
-    // ---- phase C (parallel): global rows, destinations, leave-one-out groups per chunk
-    std::vector<ChunkOut> CO(n_chunks);
-    parallel_for_chunks(n_chunks, [&](int c) {
-        ChunkOut &co = CO[c];
-        co.grp_u.resize(n_levels + 1); co.grp_off.resize(n_levels + 1); co.in_row.resize(n_levels + 1);
-        co.dest_off.resize(n_levels + 1); co.dest.resize(n_levels + 1); co.first.resize(n_levels + 1);
-        co.second.resize(n_levels + 1);
-        std::vector<int32_t> dcount, dstart, dflat, ver, tgt;
-        std::vector<std::vector<int32_t>> lev_ops(n_levels + 1);
-        for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
-            Graph &g = G[gi];
-            const int64_t *gb = &gbase[(size_t)gi * LT];
-            for (Op &o : g.ops)
-                if (o.live && o.kind == 1 && !o.folded) o.row = (int32_t)(base[(size_t)o.level * 4 + o.table] + gb[(size_t)o.level * 4 + o.table] + o.row);
-            // destinations of every variable->factor version = A rows of the GEMM rows that read it (counting sort)
-            const size_t nops = g.ops.size();
-            dcount.assign(nops + 1, 0);
-            // A row of the gradient-stage copy of r for factor f; advances the per-class counters
-            auto r_row_of = [&](const Graph &gg, int f, int64_t *iz, int64_t *in) -> int64_t {
-                const int k = gg.gap1[f];
-                const int64_t blk = k ? a_r1 : a_r0;
-                return gg.zmode[f] ? blk + n_z[k] + in[k]++ : blk + iz[k]++;
-            };
-            auto each_consumer = [&](auto &&fn) {
-                for (const Op &o : g.ops) {
-                    if (!o.live || o.kind != 1 || o.folded) continue;
-                    fn(g.inputs[o.in0], o.row);
-                }
-                if (want_grad) {
-                    int64_t iz[2] = {g_iz[0][gi], g_iz[1][gi]}, in[2] = {g_in[0][gi], g_in[1][gi]}, ip = g_ip[gi];
-                    for (int f = 0; f < g.np; ++f) {
-                        fn(g.fin_v2f[2 * f + 1], (int32_t)r_row_of(g, f, iz, in));
-                        fn(g.fin_v2f[2 * f + 0], (int32_t)(a_c + ip));
-                        ++ip;
-                    }
-                }
-            };
-            each_consumer([&](int prod, int32_t row) { if (prod >= 0) ++dcount[prod]; else co.init_rows.push_back(row); });
-            dstart.assign(nops + 1, 0);
-            for (size_t i = 0; i < nops; ++i) dstart[i + 1] = dstart[i] + dcount[i];
-            dflat.resize(dstart[nops]);
-            std::fill(dcount.begin(), dcount.end(), 0);
-            each_consumer([&](int prod, int32_t row) { if (prod >= 0) dflat[dstart[prod] + dcount[prod]++] = row; });
-            if (want_grad) {
-                int64_t iz[2] = {g_iz[0][gi], g_iz[1][gi]}, in[2] = {g_in[0][gi], g_in[1][gi]}, ip = g_ip[gi];
-                for (int f = 0; f < g.np; ++f) {
-                    const int k = g.gap1[f];
-                    const int64_t rrow = r_row_of(g, f, iz, in), ri = rrow - (k ? a_r1 : a_r0);   // index inside the class block
-                    co.pair_c.push_back((int32_t)(a_c + ip));
-                    co.pair_r.push_back((int32_t)rrow);
-                    if (g.zmode[f]) {                            // Z from the D row of a message update
-                        const int side = g.zmode[f] - 1;
-                        co.pair_u0.push_back(MLBP_D_CONST_ROWS + g.ops[g.fin_f2v[2 * f + side]].row);
-                        co.pair_z.push_back((int32_t)(side == 0 ? a_c + ip : rrow));
-                    } else {
-                        co.pair_u0.push_back((int32_t)((k ? d_u0_1 : d_u0_0) + ri));
-                        co.pair_z.push_back((int32_t)(a_c + ip));
-                    }
-                    co.pair_u1.push_back((int32_t)((k ? d_u1_1 : d_u1_0) + ri));
-                    co.pair_u2.push_back(k ? (int32_t)(d_u2_1 + ri) : -1);
-                    co.pair_g1.push_back(g.gap1[f]);
-                    co.pair_gv0.push_back(var_off[gi] + g.v0[f]);
-                    co.pair_gv1.push_back(var_off[gi] + g.v1[f]);
-                    ++ip;
-                }
-            }
-            auto d_row_of = [&](int prod) -> int32_t {
-                if (prod < 0) return -1;
-                return g.ops[prod].folded ? 1 + g.ops[prod].table : MLBP_D_CONST_ROWS + g.ops[prod].row;
-            };
-            // leave-one-out groups: live variable->factor updates of one (level, variable)
-            for (auto &v : lev_ops) v.clear();
-            for (size_t i = 0; i < nops; ++i)
-                if (g.ops[i].live && g.ops[i].kind == 0) lev_ops[g.ops[i].level].push_back((int32_t)i);
-            for (int L = 1; L <= g.n_levels; ++L) {
-                auto &lo = lev_ops[L];
-                if (lo.empty()) continue;
-                std::stable_sort(lo.begin(), lo.end(), [&](int32_t x, int32_t y) {
-                    return var_of(g, g.ops[x].f, g.ops[x].side) < var_of(g, g.ops[y].f, g.ops[y].side);
-                });
-                size_t i = 0;
-                while (i < lo.size()) {
-                    const int v = var_of(g, g.ops[lo[i]].f, g.ops[lo[i]].side);
-                    size_t j = i;
-                    while (j < lo.size() && var_of(g, g.ops[lo[j]].f, g.ops[lo[j]].side) == v) ++j;
-                    const auto &fs = g.facset[v];
-                    ver.assign(fs.size(), -2);                   // producer seen by a reader in this group; -2 = nobody reads
-                    tgt.assign(fs.size(), -1);                   // update that targets this edge
-                    for (size_t k = i; k < j; ++k) {
-                        const Op &o = g.ops[lo[k]];
-                        tgt[g.slot[2 * o.f + o.side]] = lo[k];
-                        for (int q = o.in0; q < o.in1; ++q) ver[g.slot[g.in_edge[q]]] = g.inputs[q];
-                    }
-                    co.grp_u[L].push_back(var_off[gi] + v);
-                    for (size_t s = 0; s < fs.size(); ++s) {
-                        co.in_row[L].push_back(ver[s] == -2 ? -1 : d_row_of(ver[s]));
-                        if (tgt[s] >= 0)
-                            co.dest[L].insert(co.dest[L].end(), dflat.begin() + dstart[tgt[s]], dflat.begin() + dstart[tgt[s] + 1]);
-                        // first reader's row per slot (-1: none): spares the kernels one dependent index load
-                        co.first[L].push_back(tgt[s] >= 0 && dstart[tgt[s] + 1] > dstart[tgt[s]] ? dflat[dstart[tgt[s]]] : -1);
-                        co.second[L].push_back(tgt[s] >= 0 && dstart[tgt[s] + 1] > dstart[tgt[s]] + 1 ? dflat[dstart[tgt[s]] + 1] : -1);
-                        co.dest_off[L].push_back((int32_t)co.dest[L].size());
-                    }
-                    co.grp_off[L].push_back((int32_t)co.in_row[L].size());
-                    i = j;
-                }
-            }
-            if (want_marg)
-                for (int v = 0; v < g.nv; ++v) {
-                    co.mu.push_back(var_off[gi] + v);
-                    for (int f : g.facset[v]) co.min_.push_back(d_row_of(g.fin_f2v[2 * f + ((g.v0[f] == v) ? 0 : 1)]));
-                    co.moff.push_back((int32_t)co.min_.size());
-                }
+    auto grad_bases = [&](int gi, Bases &B) {
+        for (int k = 0; k < 2; ++k) {
+            const int64_t blk = k ? a_r1 : a_r0, du0 = k ? d_u0_1 : d_u0_0, du1 = k ? d_u1_1 : d_u1_0;
+            B.rz[k] = blk + g_iz[k][gi];
+            B.rn[k] = blk + n_z[k] + g_in[k][gi];
+            B.u0[k] = du0 + g_iz[k][gi];
+            B.u1z[k] = du1 + g_iz[k][gi];
+            B.u1n[k] = du1 + n_z[k] + g_in[k][gi];
         }
-    });
+        B.u2z = d_u2_1 + g_iz[1][gi];
+        B.u2n = d_u2_1 + n_z[1] + g_in[1][gi];
+        B.c = a_c + g_ip[gi];
+        B.var = var_off[gi];
+    };
+    std::vector<ChunkOut> CO(n_chunks);
+    double t_b = t_a, t_c = t_a;
+    int64_t hits = 0, misses = 0;
+
+    if (templated) {
+        // ---- phase A (parallel): one template per distinct (wiring, roots, flags), looked up or compiled
+        std::vector<std::shared_ptr<const Tmpl>> TP(n_graphs);
+        std::vector<int64_t> c_hits(n_chunks, 0), c_miss(n_chunks, 0);
+        size_t cache_cap = (size_t)1024 << 20;
+        if (const char *e = std::getenv("MLBP_PLAN_CACHE_MB")) cache_cap = (size_t)std::max(0, std::atoi(e)) << 20;
+        parallel_for_chunks(n_chunks, [&](int c) {
+            std::vector<int32_t> key, uf;
+            for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
+                const int nv = var_off[gi + 1] - var_off[gi], np = pair_off[gi + 1] - pair_off[gi], po = pair_off[gi];
+                const int32_t *r = roots + (size_t)gi * (1 + sweeps);
+                key.clear();
+                key.push_back(nv); key.push_back(np); key.push_back(sweeps); key.push_back(flags & 15);
+                // r[0] only feeds has_loops (LBP.py:176), whose answer does not depend on the start node when the graph is
+                // connected (create_factor_graph's cliques are): then it is left out of the key (union-find over the factors)
+                int first_root = r[0];
+                if (nv > 0 && nv < 65536 && r[0] >= 0 && r[0] < nv) {
+                    uf.resize(nv);
+                    for (int v = 0; v < nv; ++v) uf[v] = v;
+                    auto find = [&](int x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+                    int comps = nv;
+                    bool ok = true;
+                    for (int f = 0; f < np && ok; ++f) {
+                        const int a = pair_v0[po + f], b = pair_v1[po + f];
+                        if (a < 0 || b < 0 || a >= nv || b >= nv) { ok = false; break; }
+                        const int ra = find(a), rb = find(b);
+                        if (ra != rb) { uf[ra] = rb; --comps; }
+                    }
+                    if (ok && comps == 1) first_root = -1;
+                }
+                key.push_back(first_root);
+                key.insert(key.end(), r + 1, r + 1 + sweeps);
+                if (np > 0) {
+                    key.insert(key.end(), pair_v0 + po, pair_v0 + po + np);
+                    key.insert(key.end(), pair_v1 + po, pair_v1 + po + np);
+                    for (int f = 0; f < np; ++f) key.push_back(pair_gap1[po + f] ? 1 : 0);
+                }
+                std::shared_ptr<const Tmpl> T;
+                {
+                    std::lock_guard<std::mutex> lk(g_tmpl_mutex);
+                    auto it = g_tmpl_cache.find(key);
+                    if (it != g_tmpl_cache.end()) T = it->second;
+                }
+                if (T) { ++c_hits[c]; }
+                else {
+                    ++c_miss[c];
+                    T = build_template(nv, np, pair_v0 + po, pair_v1 + po, pair_gap1 + po, r, sweeps, flags);
+                    if (T->err <= 0 && cache_cap > 0) {
+                        std::lock_guard<std::mutex> lk(g_tmpl_mutex);
+                        if (g_tmpl_bytes + T->bytes > cache_cap) { g_tmpl_cache.clear(); g_tmpl_bytes = 0; }   // (templates in use stay alive)
+                        if (g_tmpl_cache.emplace(key, T).second) g_tmpl_bytes += T->bytes + key.size() * sizeof(int32_t);
+                    }
+                }
+                TP[gi] = T;
+            }
+        });
+        for (int c = 0; c < n_chunks; ++c) { hits += c_hits[c]; misses += c_miss[c]; }
+        {
+            std::lock_guard<std::mutex> lk(g_tmpl_mutex);
+            g_tmpl_hits += hits; g_tmpl_misses += misses;
+        }
+        for (int gi = 0; gi < n_graphs && templated; ++gi) {
+            if (TP[gi]->err > 0) return bad_graph(TP[gi]->err);
+            if (TP[gi]->err < 0) templated = false;              // too large for the 16-bit local index: literal path for the batch
+        }
+        if (templated) {
+            for (int gi = 0; gi < n_graphs; ++gi) {
+                n_levels = std::max(n_levels, TP[gi]->n_levels); max_in = std::max(max_in, TP[gi]->max_in); n_dead += TP[gi]->n_dead;
+            }
+            t_b = tnow();
+            // ---- phase B (serial, cheap): one A/D block per (level, table); rows inside a block in graph order
+            LT = (size_t)(n_levels + 1) * 4;
+            cnt.assign(LT, 0);
+            std::vector<int64_t> gb_off(n_graphs + 1, 0);
+            for (int gi = 0; gi < n_graphs; ++gi) gb_off[gi + 1] = gb_off[gi] + (int64_t)TP[gi]->lt.size();
+            std::vector<int64_t> gb(gb_off[n_graphs]);            // first row (inside the block) of each graph's used blocks
+            for (int gi = 0; gi < n_graphs; ++gi) {
+                const Tmpl &T = *TP[gi];
+                int64_t *g0 = gb.data() + gb_off[gi];
+                for (size_t j = 0; j < T.lt.size(); ++j) { g0[j] = cnt[T.lt[j]]; cnt[T.lt[j]] += T.lt_rows[j]; }
+                for (int k = 0; k < 2; ++k) { g_iz[k][gi] = n_z[k]; g_in[k][gi] = n_n[k]; n_z[k] += T.nz[k]; n_n[k] += T.nn[k]; }
+                g_ip[gi] = n_pair;
+                if (want_grad) n_pair += T.np;
+            }
+            if (!layout()) { mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
+            t_c = tnow();
+            // ---- phase C (parallel): every graph's template relocated to its rows
+            parallel_for_chunks(n_chunks, [&](int c) {
+                ChunkOut &co = CO[c];
+                co.set_levels(n_levels);
+                std::vector<int64_t> SB(SEG_N, 0);
+                {   // one allocation per output vector
+                    std::vector<size_t> need(7 * (size_t)(n_levels + 1), 0);
+                    size_t flat[13] = {0};
+                    for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
+                        const ChunkOut &t = TP[gi]->co;
+                        for (int L = 1; L <= TP[gi]->n_levels; ++L) {
+                            size_t *n = &need[7 * (size_t)L];
+                            n[0] += t.grp_u[L].size(); n[1] += t.grp_off[L].size(); n[2] += t.in_row[L].size(); n[3] += t.dest_off[L].size();
+                            n[4] += t.dest[L].size(); n[5] += t.first[L].size(); n[6] += t.second[L].size();
+                        }
+                        flat[0] += t.init_rows.size(); flat[1] += t.pair_c.size(); flat[2] += t.mu.size(); flat[3] += t.moff.size(); flat[4] += t.min_.size();
+                    }
+                    for (int L = 1; L <= n_levels; ++L) {
+                        const size_t *n = &need[7 * (size_t)L];
+                        co.grp_u[L].reserve(n[0]); co.grp_off[L].reserve(n[1]); co.in_row[L].reserve(n[2]); co.dest_off[L].reserve(n[3]);
+                        co.dest[L].reserve(n[4]); co.first[L].reserve(n[5]); co.second[L].reserve(n[6]);
+                    }
+                    co.init_rows.reserve(flat[0]);
+                    for (auto *v : {&co.pair_c, &co.pair_r, &co.pair_z, &co.pair_u0, &co.pair_u1, &co.pair_u2, &co.pair_g1, &co.pair_gv0, &co.pair_gv1})
+                        v->reserve(flat[1]);
+                    co.mu.reserve(flat[2]); co.moff.reserve(flat[3]); co.min_.reserve(flat[4]);
+                }
+                for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
+                    const Tmpl &T = *TP[gi];
+                    const int64_t *g0 = gb.data() + gb_off[gi];
+                    for (size_t j = 0; j < T.lt.size(); ++j) SB[SEG_BLK0 + T.lt[j]] = base[T.lt[j]] + g0[j];
+                    Bases B;
+                    B.blk = nullptr;
+                    grad_bases(gi, B);
+                    for (int k = 0; k < 2; ++k) {
+                        SB[SEG_RZ + k] = B.rz[k]; SB[SEG_RN + k] = B.rn[k]; SB[SEG_U0 + k] = B.u0[k]; SB[SEG_U1Z + k] = B.u1z[k]; SB[SEG_U1N + k] = B.u1n[k];
+                    }
+                    SB[SEG_C] = B.c; SB[SEG_U2Z] = B.u2z; SB[SEG_U2N] = B.u2n; SB[SEG_VAR] = B.var;
+                    const int64_t *sb = SB.data();
+                    const ChunkOut &t = T.co;
+                    for (int L = 1; L <= T.n_levels; ++L) {
+                        if (t.grp_u[L].empty()) continue;
+                        append_shift(co.grp_off[L], t.grp_off[L], (int32_t)co.in_row[L].size());
+                        append_shift(co.dest_off[L], t.dest_off[L], (int32_t)co.dest[L].size());
+                        append_reloc(co.grp_u[L], t.grp_u[L], sb);
+                        append_reloc(co.in_row[L], t.in_row[L], sb);
+                        append_reloc(co.dest[L], t.dest[L], sb);
+                        append_reloc(co.first[L], t.first[L], sb);
+                        append_reloc(co.second[L], t.second[L], sb);
+                    }
+                    append_reloc(co.init_rows, t.init_rows, sb);
+                    append_reloc(co.pair_c, t.pair_c, sb); append_reloc(co.pair_r, t.pair_r, sb); append_reloc(co.pair_z, t.pair_z, sb);
+                    append_reloc(co.pair_u0, t.pair_u0, sb); append_reloc(co.pair_u1, t.pair_u1, sb); append_reloc(co.pair_u2, t.pair_u2, sb);
+                    co.pair_g1.insert(co.pair_g1.end(), t.pair_g1.begin(), t.pair_g1.end());
+                    append_reloc(co.pair_gv0, t.pair_gv0, sb); append_reloc(co.pair_gv1, t.pair_gv1, sb);
+                    append_shift(co.moff, t.moff, (int32_t)co.min_.size());
+                    append_reloc(co.mu, t.mu, sb);
+                    append_reloc(co.min_, t.min_, sb);
+                }
+            });
+        }
+    }
+
+    if (!templated) {
+        n_levels = max_in = 0; n_dead = 0;
+        for (auto &co : CO) co = ChunkOut();
+        // ---- phase A (parallel): sequence, levels, liveness per graph
+        std::vector<Graph> G(n_graphs);
+        std::vector<int> err(n_chunks, 0), c_levels(n_chunks, 0), c_maxin(n_chunks, 0);
+        std::vector<int64_t> c_dead(n_chunks, 0);
+        parallel_for_chunks(n_chunks, [&](int c) {
+            std::vector<char> needed;
+            for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
+                Graph &g = G[gi];
+                const int po = pair_off[gi];
+                err[c] = analyse_graph(g, var_off[gi + 1] - var_off[gi], pair_off[gi + 1] - po, pair_v0 + po, pair_v1 + po, pair_gap1 + po,
+                                       roots + (size_t)gi * (1 + sweeps), sweeps, flags, needed, c_dead[c]);
+                if (err[c]) return;
+                c_levels[c] = std::max(c_levels[c], g.n_levels);
+                for (int v = 0; v < g.nv; ++v) c_maxin[c] = std::max(c_maxin[c], (int)g.facset[v].size());
+            }
+        });
+        for (int c = 0; c < n_chunks; ++c) {
+            if (err[c]) return bad_graph(err[c]);
+            n_levels = std::max(n_levels, c_levels[c]); max_in = std::max(max_in, c_maxin[c]); n_dead += c_dead[c];
+        }
+
+        t_b = tnow();
+        // ---- phase B (serial, cheap): one A/D block per (level, table); rows inside a block in graph order
+        LT = (size_t)(n_levels + 1) * 4;
+        cnt.assign(LT, 0);
+        std::vector<int64_t> gbase((size_t)n_graphs * LT);            // first row index (inside the block) of each graph
+        n_pair = 0; n_z[0] = n_z[1] = n_n[0] = n_n[1] = 0;
+        for (int gi = 0; gi < n_graphs; ++gi) {
+            Graph &g = G[gi];
+            int64_t *gb = &gbase[(size_t)gi * LT];
+            for (size_t i = 0; i < LT; ++i) gb[i] = cnt[i];
+            for (Op &o : g.ops)
+                if (o.live && o.kind == 1 && !o.folded) o.row = (int32_t)(cnt[(size_t)o.level * 4 + o.table]++ - gb[(size_t)o.level * 4 + o.table]);
+            for (int k = 0; k < 2; ++k) { g_iz[k][gi] = n_z[k]; g_in[k][gi] = n_n[k]; }
+            g_ip[gi] = n_pair;
+            if (want_grad) { n_pair += g.np; for (int f = 0; f < g.np; ++f) (g.zmode[f] ? n_n : n_z)[g.gap1[f]]++; }
+        }
+        if (!layout()) { mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
+
+        t_c = tnow();
+        // ---- phase C (parallel): global rows, destinations, leave-one-out groups per chunk
+        parallel_for_chunks(n_chunks, [&](int c) {
+            ChunkOut &co = CO[c];
+            co.set_levels(n_levels);
+            EmitScratch sc;
+            std::vector<int64_t> blk(LT);
+            for (int gi = chunk_lo(c); gi < chunk_lo(c + 1); ++gi) {
+                const int64_t *gb = &gbase[(size_t)gi * LT];
+                for (size_t i = 0; i < LT; ++i) blk[i] = base[i] + gb[i];
+                Bases B;
+                B.blk = blk.data();
+                grad_bases(gi, B);
+                emit_graph(G[gi], B, want_grad, want_marg, co, sc);
+            }
+        });
+    }
 
     double t_d = tnow();
     // ---- phase D: merge the chunks into the blob
     Plan *P = new (std::nothrow) Plan();
     if (!P) { mlbp::set_error("plan_compile: out of memory"); return MLBP_ERR_ALLOC; }
     std::vector<int32_t> &B = P->blob;
-    {
-        size_t total = H_WORDS + (size_t)n_levels * LEV_WORDS + 64;           // one allocation for the whole blob
-        for (const ChunkOut &co : CO) {
-            for (int L = 0; L <= n_levels; ++L)
-                total += co.grp_u[L].size() + co.grp_off[L].size() + co.in_row[L].size() + co.dest_off[L].size() +
-                         co.dest[L].size() + co.first[L].size() + co.second[L].size() + 24;
-            total += (size_t)n_levels * 16 / n_chunks + 16 + co.init_rows.size() + 9 * co.pair_c.size() + co.mu.size() + co.moff.size() + co.min_.size() + 16;
-        }
-        B.reserve(total);
-    }
-    B.assign(H_WORDS + (size_t)n_levels * LEV_WORDS, 0);
-    auto append = [&](const std::vector<int32_t> &v) { int32_t o = (int32_t)B.size(); B.insert(B.end(), v.begin(), v.end()); return o; };
-    // concatenation of one member over the chunks; `shift` adds a running offset (CSR offsets) and prepends a 0
+    // The header and the level records are written in place; every index array is only PLACED here (offset + copy job) and
+    // copied by all threads once the total size is known: the merge is memory traffic, 25 MB per 512 C3 sentences.
+    struct Job { size_t dst; const int32_t *src; size_t n; int32_t shift; };
+    std::vector<Job> jobs;
+    std::deque<std::vector<int32_t>> owned;                                   // small arrays built here (GEMM records)
+    size_t pos = H_WORDS + (size_t)n_levels * LEV_WORDS;
+    B.assign(pos, 0);
+    auto append = [&](const std::vector<int32_t> &v) {
+        owned.push_back(v);
+        const int32_t o = (int32_t)pos;
+        jobs.push_back({pos, owned.back().data(), v.size(), 0});
+        pos += v.size();
+        return o;
+    };
+    // concatenation of one member over the chunks; `csr` adds a running offset (CSR offsets) and prepends a 0
     auto concat = [&](auto member, bool csr) {
-        const int32_t o = (int32_t)B.size();
+        const int32_t o = (int32_t)pos;
         int32_t run = 0;
-        if (csr) B.push_back(0);
+        if (csr) ++pos;                                                        // the leading 0 (the blob is zero-filled)
         for (int c = 0; c < n_chunks; ++c) {
             const std::vector<int32_t> &v = member(CO[c]);
-            if (csr) { for (int32_t x : v) B.push_back(x + run); if (!v.empty()) run += v.back(); }
-            else B.insert(B.end(), v.begin(), v.end());
+            if (v.empty()) continue;
+            jobs.push_back({pos, v.data(), v.size(), csr ? run : 0});
+            pos += v.size();
+            if (csr) run += v.back();
         }
         return o;
     };
@@ -568,6 +893,19 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
         B[H_MARG_OFF] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.moff; }, true);
         B[H_MARG_IN] = concat([](ChunkOut &x) -> std::vector<int32_t> & { return x.min_; }, false);
     }
+    if (pos > 0x7fffff00ull) { delete P; mlbp::set_error("plan_compile: batch too large"); return MLBP_ERR_INVALID; }
+    B.resize(pos, 0);
+    {
+        std::atomic<size_t> next{0};
+        int32_t *dst = B.data();
+        parallel_for_chunks(n_chunks, [&](int) {
+            for (size_t j = next.fetch_add(1); j < jobs.size(); j = next.fetch_add(1)) {
+                const Job &jb = jobs[j];
+                if (jb.shift == 0) std::memcpy(dst + jb.dst, jb.src, jb.n * sizeof(int32_t));
+                else for (size_t i = 0; i < jb.n; ++i) dst[jb.dst + i] = jb.src[i] + jb.shift;
+            }
+        });
+    }
     int64_t gemm_rows = n_msg_rows + (want_grad ? n_z[0] + n_gap0 + n_z[1] + 2 * n_gap1 : 0);
     std::memset(P->sizes, 0, sizeof(P->sizes));
     P->sizes[MLBP_PLAN_BLOB_WORDS] = (int64_t)B.size();
@@ -579,7 +917,9 @@ extern "C" int mlbp_plan_compile(int n_graphs, const int32_t *var_off, const int
     P->sizes[MLBP_PLAN_MAX_IN] = max_in;
     P->sizes[MLBP_PLAN_HDR_WORDS] = H_WORDS;
     P->sizes[MLBP_PLAN_N_DEAD] = n_dead;
-    if (prof) std::fprintf(stderr, "plan_compile: A %.1f ms  B %.1f ms  C %.1f ms  D %.1f ms (chunks %d)\n", 1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_d - t_c), 1e3 * (tnow() - t_d), n_chunks);
+    P->sizes[MLBP_PLAN_TMPL_HITS] = hits;
+    P->sizes[MLBP_PLAN_TMPL_MISSES] = misses;
+    if (prof) std::fprintf(stderr, "plan_compile: A %.1f ms  B %.1f ms  C %.1f ms  D %.1f ms (chunks %d, templates %s: %lld hits, %lld compiled)\n", 1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (t_d - t_c), 1e3 * (tnow() - t_d), n_chunks, templated ? "on" : "off", (long long)hits, (long long)misses);
     *out = reinterpret_cast<mlbp_plan *>(P);
     return MLBP_OK;
 }

@@ -248,7 +248,7 @@ class Engine(object):
         self.gemm_k_ranges = [(k0, min(step, self.V - k0)) for k0 in range(0, self.V, step)] if n_k > 1 else [(0, 0)]
         # Message rows with REDUCED tensor-core passes plus an exact re-score of every near-tied decision (csrc/rescore.cu).
         #   two passes  A_hi . (B_hi + B_lo): the lo half of the message is dropped;
-        #   ONE pass    A_hi . B_hi         : the lo half of the table is dropped too (the default where the gate below holds).
+        #   ONE pass    A_hi . B_hi         : the lo half of the table is dropped too (the default at V >= 8192, see msg_passes).
         # Why this is safe: a rounding error upstream is damped by every later contraction (a message D = T a averages V terms,
         # and K2 rounds the table's hi halves stochastically, so equal entries do not share one error), so the only error that
         # reaches a belief undamped is the rounding of the LAST hop -- measured on the ratio of two candidates' beliefs at
@@ -264,14 +264,18 @@ class Engine(object):
         # ON THE DEVICE that switches all later message GEMMs of this theta to three passes (mlbp_factor_to_var_gemm_gated; no
         # host synchronisation).  The one-pass gradient rows are gated the same way: once any spike was seen they keep the lo
         # half of the table planes (a peaked belief does not average the fp16 rounding of T o PMI away: tests/test_gpu_gates.py).
-        # msg_passes: None = one pass where V >= 4096 (where the errors above were measured); 1 / 2 = one / two passes at any
-        # V; 3 = never reduced.  MLBP_MSG_PASSES in the environment overrides None (A/B runs of whole suites).
+        # msg_passes: None = one pass where V >= 8192, two where 4096 <= V < 8192 (the rounding noise of the un-spiky remainder of
+        # a message shrinks like 1 / sqrt(V); worst belief error seen with ONE pass on the hostile cases at V = 4608: 1.3e-5
+        # absolute against the contract's 1e-4, ten times the two-pass figure, so the smaller vocabularies keep the second
+        # pass); 1 / 2 = one / two passes at any V; 3 = never reduced.  MLBP_MSG_PASSES in the environment overrides None (A/B runs of whole suites).
         if msg_passes is None and os.environ.get('MLBP_MSG_PASSES'):
             msg_passes = int(os.environ['MLBP_MSG_PASSES'])
         self.msg_passes = msg_passes
         self.one_pass_min_v = int(one_pass_min_v)   # one-pass gradient rows from this vocabulary size on (tests lower it)
         # bands of the near-tie detection: defaults 4e-4 / 2e-4 with one-pass message rows, 2e-4 / 1e-4 with two
-        one = self.msg_passes in (None, 1)
+        self.msg_one_pass_min_v = 8192
+        one = self.msg_passes == 1 or (self.msg_passes is None and self.V >= self.msg_one_pass_min_v)
+        self.msg_one_pass = one                     # (only while msg_two_pass_ok: set_theta's gate on the potentials' span)
         self.tau = float(tau) if tau is not None else (4e-4 if one else 2e-4)
         self.tau_label = float(tau_label) if tau_label is not None else (2e-4 if one else 1e-4)
         self.peak_mult = float(peak_mult)
@@ -382,7 +386,7 @@ class Engine(object):
         f = self._flags.cpu().numpy()
         c = f[FLAG_COUNTERS:FLAG_COUNTERS + 5]
         return {'msg_two_pass': bool(self.msg_two_pass_ok),       # (name kept from the two-pass build: "reduced-pass message rows")
-                'msg_passes': (1 if self.msg_passes in (None, 1) else 2) if self.msg_two_pass_ok else 3, 'peak_flag': int(f[FLAG_PEAK]), 'spike_flag': int(f[FLAG_SPIKE]),
+                'msg_passes': (1 if self.msg_one_pass else 2) if self.msg_two_pass_ok else 3, 'peak_flag': int(f[FLAG_PEAK]), 'spike_flag': int(f[FLAG_SPIKE]),
                 'spiky_rows_last_batch': int(f[FLAG_NSPIKY]),
                 'max_message_prob': float(f[FLAG_MAXBITS:FLAG_MAXBITS + 1].view(np.float32)[0]) * 2.0 ** -A_SCALE_LOG2, 'rescored': int(c[0]),
                 'skipped_mass_tie': int(c[1]), 'skipped_degenerate': int(c[2]), 'top1_changed': int(c[3]),
@@ -492,7 +496,7 @@ class Engine(object):
         import time as _time
         t_plan = _time.perf_counter()
         two_pass = self.msg_two_pass_ok and not approx
-        msg_one_pass = two_pass and self.msg_passes in (None, 1)  # message rows as A_hi . B_hi (see __init__)
+        msg_one_pass = two_pass and self.msg_one_pass            # message rows as A_hi . B_hi (see __init__)
         handle, sizes = self.compile(corpus, roots, sweeps, want_grad, want_marg, fold=not approx_inference,
                                      reuse_z=not approx and not grad_hi_only and not two_pass)
         self.plan_seconds += _time.perf_counter() - t_plan

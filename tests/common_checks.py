@@ -3,7 +3,7 @@
 Tolerances (BASELINE.json north_star): top-1 exact, beliefs <= 1e-4 max-abs in probability space, gradients
 <= 1e-4 relative (with an absolute floor for the identically-zero components).  The checks here
 are tighter than that: 1e-6 on beliefs, 2e-6 relative on log-posteriors -- 1e-5 where the engine runs its ONE-pass message
-rows (V >= 4096: measured 1.3e-6 at C3 size, 3.2e-6 on the hostile cases of test_gpu_gates.py)."""
+rows (V >= 8192: measured 1.3e-6 at C3 size; 3.2e-6 on the hostile cases of test_gpu_gates.py at V = 4608)."""
 import json
 import os
 
@@ -59,7 +59,7 @@ def check_against_oracle(make_engine, model, sents, roots, te, td, sweeps=3, bel
         worst = max(worst, float(np.abs(b - o['marginals']).max()))
         assert np.abs(b - o['marginals']).max() < belief_atol, i
         np.testing.assert_array_equal(T1[off[i]:off[i + 1]], o['top1'])
-        lp_rtol = (1e-5 if model['V'] >= 4096 else 2e-6) * belief_atol / BELIEF_ATOL
+        lp_rtol = (1e-5 if model['V'] >= 8192 else 2e-6) * belief_atol / BELIEF_ATOL
         np.testing.assert_allclose(LP[i], o['logp'], rtol=lp_rtol)
         np.testing.assert_allclose(G[i][:3], o['g_ee_unreg'][0], rtol=GRAD_RTOL, atol=GRAD_ATOL)
         np.testing.assert_allclose(G[i][3:], o['g_ed_unreg'][0], rtol=GRAD_RTOL, atol=GRAD_ATOL)

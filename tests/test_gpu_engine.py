@@ -166,7 +166,7 @@ def test_properties_at_scale():
     np.testing.assert_allclose(b0.sum(axis=1), 1.0, atol=1e-5)
     assert (b0 >= 0).all()
     np.testing.assert_array_equal(t0, t1)
-    np.testing.assert_allclose(l0, l1, rtol=1e-5)        # (one-pass message rows on the tcgen05 side: measured 2.7e-6)
+    np.testing.assert_allclose(l0, l1, rtol=2e-6)
     np.testing.assert_allclose(g0, g1, rtol=1e-4, atol=2e-6)
     assert np.abs(g0[:, 2]).max() < 1e-9 and np.abs(g0[:, 8]).max() < 1e-9      # bias components
 
@@ -323,7 +323,7 @@ def test_two_pass_message_rows_with_engineered_near_ties():
     roots = corpus.roots_from_positions(roots_pos)
     got = {}
     for name, kw in (('three', dict(msg_passes=3)), ('two_raw', dict(msg_passes=2, tau=0.0, tau_label=0.0)), ('two', dict(msg_passes=2)),
-                     ('one_raw', dict(msg_passes=1, tau=0.0, tau_label=0.0)), ('one', dict())):
+                     ('one_raw', dict(msg_passes=1, tau=0.0, tau_label=0.0)), ('one', dict(msg_passes=1))):
         eng = Engine(model, **kw)
         eng.set_theta(te, td)
         r = eng.run(corpus, roots, 3, want_beliefs=True)
@@ -332,7 +332,7 @@ def test_two_pass_message_rows_with_engineered_near_ties():
     assert got['one'][4]['msg_passes'] == 1 and got['two'][4]['msg_passes'] == 2 and got['one'][3]['peak_flag'] == 0
     flips = {k: int((v[0] != want).sum()) for k, v in got.items()}
     print('top-1 mismatches vs the float64 oracle (48 engineered near-ties):', flips, got['one'][3])
-    assert flips['two'] == 0 and flips['one'] == 0                # the default engine is 'one'
+    assert flips['two'] == 0 and flips['one'] == 0                # ('two' is the default engine at this V, 'one' from V = 8192 on)
     assert flips['two_raw'] > 0 and flips['one_raw'] > 0, 'the ties must sit inside the reduced-pass error, else this test shows nothing'
     assert got['two'][3]['rescored'] >= len(want) and got['one'][3]['rescored'] >= len(want)
     assert np.abs(got['two'][1] - got['three'][1]).max() < 1e-7
@@ -343,8 +343,8 @@ def test_two_pass_message_rows_with_engineered_near_ties():
 
 @pytest.mark.parametrize('regime', ['flat', 'trained'])
 def test_reduced_pass_rows_equal_three_pass_decisions_at_scale(regime):
-    """a batch too big for the oracle: the default engine (ONE-pass message rows + spike compensation + re-score at V >= 4096),
-    the two-pass engine and the three-pass engine agree on every arg-max and label rank; beliefs within 5e-7 (1e-7 with two
+    """a batch too big for the oracle: ONE-pass message rows (+ spike compensation + re-score; the default from V = 8192 on),
+    two-pass rows (the default at this V) and the three-pass engine agree on every arg-max and label rank; beliefs within 5e-7 (1e-7 with two
     passes), log-posterior 1e-5 (2e-6), gradients 1e-4.  'trained' = the theta the bench's SGD reaches after a few steps (the
     history weight at 7.5: beliefs of 0.8 on the label of every correctly guessed token, spiky messages everywhere)."""
     model = synth.make_model(4352, 512, seed=33, dtype=np.float32)
@@ -354,7 +354,7 @@ def test_reduced_pass_rows_equal_three_pass_decisions_at_scale(regime):
     te, td = ([0.9, 0.4, -0.1], [1.1, -0.5, 0.5, 0.3, 0.4, -0.2]) if regime == 'flat' else \
         ([-0.003, 0.049, -0.3], [0.101, -0.047, 7.534, 0.3, 0.4, -0.2])
     out = []
-    for mp in (3, 2, None):
+    for mp in (3, 2, 1):                                          # (1 is the default from V = 8192 on)
         eng = Engine(model, msg_passes=mp)
         eng.set_theta(te, td)
         r = eng.run(corpus, roots, 3, want_grad=True, want_marg=True, want_beliefs=True)
@@ -362,7 +362,7 @@ def test_reduced_pass_rows_equal_three_pass_decisions_at_scale(regime):
                     eng.pass_stats()))
     assert out[1][5]['msg_passes'] == 2 and out[2][5]['msg_passes'] == 1
     if regime == 'trained':
-        assert out[2][5]['spike_flag'] == 1 and out[0][0].max() > 0.5, 'the trained regime must be peaked'
+        assert out[2][5]['spike_flag'] == 1 and out[0][0].max() > 0.2, 'the trained regime must be peaked'
     for o, b_tol, l_tol in ((out[1], 1e-7, 2e-6), (out[2], 5e-7, 1e-5)):
         assert o[5]['msg_two_pass'] and o[5]['peak_flag'] == 0 and o[5]['rescored'] > 0
         np.testing.assert_array_equal(out[0][1], o[1])

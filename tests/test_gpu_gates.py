@@ -37,8 +37,11 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize('msg_passes', [None, 1], ids=['default', 'one_pass_message_rows'])
 @pytest.mark.parametrize('name', sorted(CASES))
-def test_reduced_pass_rows_on_sparse_and_peaked_data(name):
+def test_reduced_pass_rows_on_sparse_and_peaked_data(name, msg_passes):
+    """default at V = 4608: two-pass message rows + one-pass gradient rows; msg_passes = 1 forces the ONE-pass message rows the
+    engine uses from V = 8192 on, at the hostile end (their rounding noise grows like 1 / sqrt(V) towards small V)"""
     pd, wd, te, td = CASES[name]
     V = 4608
     model = synth.make_model(V, 256, seed=77, dtype=np.float32, pmi_density=pd, w1_density=wd)
@@ -47,13 +50,14 @@ def test_reduced_pass_rows_on_sparse_and_peaked_data(name):
     eng_holder = {}
 
     def make_engine(m):
-        eng_holder['e'] = Engine(m)
+        eng_holder['e'] = Engine(m, msg_passes=msg_passes)
         return eng_holder['e']
 
     m64 = {k: (np.asarray(v, dtype=np.float64) if hasattr(v, 'dtype') else v) for k, v in model.items()}
     r, corpus = common_checks.run_engine(make_engine, model, sents, te, td, roots, 3)
     eng = eng_holder['e']
     assert eng.grad_one_pass_ok, 'the case must sit INSIDE the gate (otherwise it tests nothing)'
+    assert eng.pass_stats()['msg_passes'] == (1 if msg_passes == 1 else 2)
     tb = orc.Tables(m64, te, td)
     off = corpus.var_off
     B, T1, LP, G = (x.cpu().numpy() for x in (r.beliefs, r.top1, r.logp, r.grad))
@@ -68,9 +72,10 @@ def test_reduced_pass_rows_on_sparse_and_peaked_data(name):
         np.testing.assert_allclose(G[i], ref, rtol=1e-4, atol=2e-6)
         nz = np.abs(ref) > 1e-3
         worst_g = max(worst_g, float((np.abs(G[i] - ref)[nz] / np.abs(ref)[nz]).max()))
-        np.testing.assert_allclose(LP[i], o['logp'], rtol=1e-5)   # (one-pass message rows: measured 3.2e-6; two-pass 1e-6)
-    print('%s: largest belief %.3f, worst belief abs err %.2e, worst rel gradient err %.2e' % (name, peak, worst_b, worst_g))
-    assert worst_b < 1e-5                      # contract: 1e-4
+        np.testing.assert_allclose(LP[i], o['logp'], rtol=1e-5 if msg_passes == 1 else 2e-6)   # (measured 3.2e-6 / 1e-6)
+    print('%s (message rows: %d pass%s): largest belief %.3f, worst belief abs err %.2e, worst rel gradient err %.2e' % (
+        name, 1 if msg_passes == 1 else 2, '' if msg_passes == 1 else 'es', peak, worst_b, worst_g))
+    assert worst_b < (3e-5 if msg_passes == 1 else 1e-5)          # contract: 1e-4 (measured: 1.3e-5 / 1.2e-6 on sparse_w1_negative)
     if 'peaked' in name:
         assert peak > 0.2, 'the peaked case must actually be peaked'
 
