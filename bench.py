@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--ref-sample', type=int, default=0, help='sentences per step of the process-pool CPU variant (0 = one per host core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-literal', action='store_true', help='CPU arm: skip the timed sample of the literal (per-message) reference restatement')
     ap.add_argument('--gemm-slice-pairs', type=int, default=None, help='M pairs per three-pass K4 launch (default: Engine rule; 0 = one launch per level, A/B probe)')
     ap.add_argument('--gemm-impl', type=int, default=0, help='K4 variant / flags (include/mlbp.h; A/B probes)')
     ap.add_argument('--grad-b-terms', type=int, default=1, help='2 = keep the table lo half in the gradient rows (A/B probe)')
@@ -218,6 +219,36 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def literal_reference_sample(a, m64, te, td):
+    """SURVEY.md section 8(d) variant (i): the reference's path as it stands (train.py:357-397 -> LBP.py), restated op for op by
+    oracle.run_literal -- potentials exp(phi . theta) rebuilt per sentence (train.py:218-253), one V x V dgemv per message
+    (LBP.py:509 / :518), dense pairwise beliefs per factor (LBP.py:566-610).  A k = 20 sentence of the workload takes minutes
+    that way, so two SHORT sentences of the same model (3 and 4 predicted tokens: 3 and 6 pairwise factors) are timed and the
+    workload's sentence is extrapolated linearly in the number of pairwise factors (k (k - 1) / 2): every message update and
+    every belief belongs to one factor, the potentials are a per-sentence constant."""
+    from oracle import lbp_oracle as orc
+    from macaronicusermodeling_b200 import synth
+    try:
+        t = {}
+        for k in (3, 4):
+            sents = synth.make_corpus({'V': a.V, 'Vd': a.Vd}, 1, k=k, g=0, seed=99)
+            roots = synth.draw_roots(sents, a.sweeps, seed=5)
+            t0 = time.perf_counter()
+            orc.run_literal(m64, sents[0], te, td, roots[0], a.sweeps, keep_messages=False)
+            t[k] = time.perf_counter() - t0
+        per_factor = max((t[4] - t[3]) / 3.0, 0.0)
+        per_sentence = t[3] - 3.0 * per_factor
+        n_pair = a.k * (a.k - 1) // 2
+        est = per_sentence + n_pair * per_factor
+        return {'value': 1.0 / est, 'unit': UNIT, 'kind': 'port (literal: oracle.run_literal, op for op)', 'extrapolated': True,
+                'threads': host_threads(), 'measured_s': {'k=3 (3 pairwise factors)': t[3], 'k=4 (6 pairwise factors)': t[4]},
+                'per_pairwise_factor_s': per_factor, 'per_sentence_constant_s': per_sentence,
+                'seconds_per_workload_sentence': est,
+                'note': 'k = %d: %d pairwise factors; linear in the factor count, measured on two short sentences at V = %d' % (a.k, n_pair, a.V)}
+    except Exception as e:                                      # never lose the arm's line over the slow variant
+        return {'value': None, 'error': str(e)[:200]}
+
+
 def reference_arm(a):
     """Two CPU variants of the same port are timed over the same K steps and the FASTER one is the arm's value:
     `blas_threads` = one process, every level's dgemm threaded by the BLAS; `process_pool` = train_mp.py's layout,
@@ -270,6 +301,8 @@ def reference_arm(a):
     with mp.get_context('fork').Pool(workers, initializer=_pool_init) as pool:
         v_pool, dt_pool = timed(lambda: pool.map(_pool_sentence, range(n_pool), chunksize=1), n_pool)
 
+    literal = None if a.no_literal else literal_reference_sample(a, m64, te, td)
+
     if v_pool >= v_thr:
         v, dt, n, variant, cores = v_pool, dt_pool, n_pool, 'process_pool', workers
     else:
@@ -281,11 +314,12 @@ def reference_arm(a):
                        'note': 'CPU arm: oracle port of the reference path, fast variant (potentials hoisted to once '
                                'per step, closed-form gradient, level-batched dgemm); each step is a bounded sample of '
                                '%d sentences of the workload; the literal per-message reference restatement is ~100x '
-                               'slower (BASELINE.md section 2)' % n},
+                               'slower (cpu_baseline.variants.literal: timed on two short sentences, extrapolated)' % n},
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'variant': variant,
                              'variants': {'process_pool': {'value': v_pool, 'workers': workers, 'blas_threads_per_worker': 1,
                                                            'sentences_per_step': n_pool},
-                                          'blas_threads': {'value': v_thr, 'threads': blas_threads, 'sentences_per_step': n_thr}},
+                                          'blas_threads': {'value': v_thr, 'threads': blas_threads, 'sentences_per_step': n_thr},
+                                          'literal': literal},
                              'sample': '%d sentences x %d steps (%s: %s) + the amortised share of one %.1f s table build per '
                                        '%d-sentence step' % (n, a.steps, variant,
                                                              'train_mp.py-style pool of %d forked single-threaded workers' % workers
@@ -325,7 +359,8 @@ def cpu_baseline_subprocess(a):
     cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '1',
            '--sentences', str(a.sentences), '--V', str(a.V), '--Vd', str(a.Vd), '--k', str(a.k), '--g', str(a.g),
            '--sweeps', str(a.sweeps), '--ref-sample', str(a.ref_sample), '--config', a.config, '--scaling', a.scaling,
-           '--users', str(a.users), '--sentences-per-user', str(a.sentences_per_user)] + (['--user-adapt'] if a.user_adapt else [])
+           '--users', str(a.users), '--sentences-per-user', str(a.sentences_per_user)] + (['--user-adapt'] if a.user_adapt else []) + \
+        (['--no-literal'] if a.no_literal else [])
     env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'LOCAL_WORLD_SIZE')}
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env, check=True).stdout
     for ln in reversed(out.splitlines()):
@@ -469,10 +504,12 @@ def ours(a):
         sampler.start()
     l0, w.peaked = eng.launches, []
     t_plan0 = eng.plan_seconds
+    tm0 = (eng.plan_template_hits, eng.plan_template_misses)
     ms = timed(w.step, a.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launches - l0
     plan_s_per_step = (eng.plan_seconds - t_plan0) / a.steps
+    tm1 = (eng.plan_template_hits, eng.plan_template_misses)
     peaked_value = list(w.peaked)
     value = w.n_global * a.steps / (ms / 1e3)
 
@@ -597,7 +634,9 @@ def ours(a):
                        'micro_batches_per_step': len(w.parts) if w.parts is not None else len(w.batches),
                        'k4_rows_per_sliced_launch': eng.gemm_slice_rows},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'hbm_kernels': hbm,
-            'host': {'plan_compile_s_per_step': plan_s_per_step, 'plan_threads': int(os.environ.get('MLBP_PLAN_THREADS', '0'))},
+            'host': {'plan_compile_s_per_step': plan_s_per_step, 'plan_threads': int(os.environ.get('MLBP_PLAN_THREADS', '0')),
+                     'schedule_templates': {'hits_in_timed_steps': tm1[0] - tm0[0], 'compiled_in_timed_steps': tm1[1] - tm0[1],
+                                            'note': 'graphs whose schedule was relocated from a cached template vs compiled (csrc/plan.cpp); roots are redrawn every step'}},
             'message_rows': {'passes': pass_stats['msg_passes'], 'reduced_pass_enabled': pass_stats['msg_two_pass'], 'ranks_switched_to_three_passes_per_step': peaked_value,
                              'ranks_switched_all_steps_incl_warmup_e2e_profiling': w.all_peaked, 'max_message_prob_last_step': pass_stats['max_message_prob'],
                              'flag_code': 'bit 0 = a row had more spikes than slots (message rows ran three passes, gradient rows two), bit 1 = a spike was seen and compensated',

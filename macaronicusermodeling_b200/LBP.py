@@ -343,7 +343,8 @@ class FactorGraph():
         eng.set_theta(*self._pot_thetas())
         roots = corpus.roots_from_positions([list(self._roots)])
         r = eng.run(corpus, roots, self._sweeps, want_grad=True, want_marg=True, want_beliefs=True, want_messages=True,
-                    approx_inference=bool(self.use_approx_inference), approx_beliefs=bool(self.use_approx_beliefs))
+                    approx_inference=bool(self.use_approx_inference), approx_beliefs=bool(self.use_approx_beliefs),
+                    want_topk=min(50, eng.V))                 # get_max_vocab(50) lists (LBP.py:87, :115) made on the device
         V = eng.V
         # name the final pairwise messages like the reference's dict keys
         final = {}
@@ -362,7 +363,7 @@ class FactorGraph():
                      'vids': vids, 'pairs': pair_factors,
                      'beliefs': r.beliefs.cpu().numpy()[:, :V].astype(np.float64), 'grad': r.grad.cpu().numpy()[0],
                      'logp_var': r.logp_var.cpu().numpy(), 'top1': r.top1.cpu().numpy(), 'rank': r.rank.cpu().numpy(),
-                     'final': final}
+                     'topk': tuple(x.cpu().numpy() for x in r.topk), 'final': final}
         return self._res
 
     @property
@@ -584,8 +585,18 @@ class VariableNode():
         """(label, '%0.4f' % log p(label), [(word, '%0.4f' % log p)] for the `top` most probable words, best first)
         (reference: LBP.py:402-411; the same argpartition + argsort calls, so exact ties order alike)"""
         belief = self.get_marginal().m.reshape(-1)
-        best = np.argpartition(belief, -top)[-top:]
-        best = best[np.argsort(belief[best])][::-1]
+        best = None
+        if self.graph._eager is None:
+            # the list mlbp_topk_rows made on the device (descending probability); rows whose order exact ties leave open are
+            # re-listed with the reference's own calls, whose order among equal values is NumPy's
+            res = self.graph._run()
+            idx, _, ties = res['topk']
+            row = res['vids'].index(self.id)
+            if top <= idx.shape[1] and ties[row] == 0:
+                best = idx[row, :top]
+        if best is None:
+            best = np.argpartition(belief, -top)[-top:]
+            best = best[np.argsort(belief[best])][::-1]
         with np.errstate(divide='ignore'):
             logs = np.log(belief)
         return (self.supervised_label, '%0.4f' % logs[self.supervised_label_index],

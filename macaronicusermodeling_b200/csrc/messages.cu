@@ -505,7 +505,7 @@ topk_mask_rows_kernel(__half *__restrict__ A_hi, __half *__restrict__ A_lo, int 
 // Optional near-tie detection (flags != nullptr; see rescore.cu): besides the arg-max and the label's rank the kernel keeps
 // the SECOND largest product and counts the candidates inside a relative band around the label's product; variables whose
 // decisions an error of relative size << tau could change are appended to `flagged` for the exact re-score.
-template <typename T>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ grp_off,
                  const int32_t *__restrict__ in_row, const int32_t *__restrict__ label, const float *__restrict__ U,
@@ -521,30 +521,63 @@ marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ 
     const float *urow = U + (size_t)grp_u[g] * ldv;
     const int lab = label[g];
     __shared__ const float *s_rows[64];
-    const int nn = min(n, 64);                                    // the host entry point rejects n > 64
-    if (threadIdx.x < 64) {
-        const int r = threadIdx.x < nn ? in_row[i0 + threadIdx.x] : -1;
-        s_rows[threadIdx.x] = r >= 0 ? D + (size_t)r * ldv : nullptr;
+    __shared__ int s_nn;
+    const int n64 = min(n, 64);                                   // the host entry point rejects n > 64
+    if (threadIdx.x == 0) {                                       // messages still uniform (row < 0) drop out: order is kept
+        int c = 0;
+        for (int j = 0; j < n64; ++j) {
+            const int r = in_row[i0 + j];
+            if (r >= 0) s_rows[c++] = D + (size_t)r * ldv;
+        }
+        s_nn = c;
     }
     __syncthreads();
+    const int nn = s_nn;
     auto prod = [&](int e) {                                      // rescore.cu evaluates the same expression in the same order
         T p = (T)__ldg(urow + e);
-        for (int j = 0; j < nn; ++j)
-            if (s_rows[j]) p *= (T)__ldg(s_rows[j] + e);
+        for (int j = 0; j < nn; ++j) p *= (T)__ldg(s_rows[j] + e);
         return p;
+    };
+    // four adjacent columns per thread: 16-byte loads, the loads of four rows issued before their multiplies (the products
+    // are formed in the same left-to-right order as prod(), so every value is bit-identical to the scalar expression)
+    auto prod4 = [&](int e, T p[4]) {
+        const float4 u = __ldg(reinterpret_cast<const float4 *>(urow + e));
+        p[0] = (T)u.x; p[1] = (T)u.y; p[2] = (T)u.z; p[3] = (T)u.w;
+        int j = 0;
+        for (; j + 4 <= nn; j += 4) {
+            float4 d[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[q] = __ldg(reinterpret_cast<const float4 *>(s_rows[j + q] + e));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { p[0] *= (T)d[q].x; p[1] *= (T)d[q].y; p[2] *= (T)d[q].z; p[3] *= (T)d[q].w; }
+        }
+        for (; j < nn; ++j) {
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(s_rows[j] + e));
+            p[0] *= (T)d.x; p[1] *= (T)d.y; p[2] *= (T)d.z; p[3] *= (T)d.w;
+        }
     };
     const T plab = prod(lab);
     const T lab_lo = plab * (T)(1.0f - tau_label), lab_hi = plab * (T)(1.0f + tau_label);
     T sp = (T)0, best = (T)-1, second = (T)-1;
     int besti = 0x7fffffff, cnt = 0, near_hi = 0, near_lo = 0;
-    for (int e = threadIdx.x; e < V; e += blockDim.x) {
-        const T p = prod(e);
+    auto visit = [&](int e, T p) {
         sp += p;
         cnt += (p > plab) ? 1 : 0;
         near_hi += (p > plab && p <= lab_hi) ? 1 : 0;
         near_lo += (e != lab && p <= plab && p >= lab_lo) ? 1 : 0;
-        if (p > best) { second = best; best = p; besti = e; }     // strided ascending e: first index wins per thread
+        if (p > best) { second = best; best = p; besti = e; }     // ascending e inside a thread: first index wins per thread
         else if (p > second) second = p;
+    };
+    if (VEC) {
+        for (int e = 4 * threadIdx.x; e < V; e += 4 * blockDim.x) {   // rows are padded to a multiple of 4: loads stay inside
+            T p[4];
+            prod4(e, p);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (e + q < V) visit(e + q, p[q]);
+        }
+    } else {
+        for (int e = threadIdx.x; e < V; e += blockDim.x) visit(e, prod(e));
     }
     double s = block_sum((double)sp, red);
     const double c = block_sum((double)cnt, red);
@@ -589,7 +622,19 @@ marginals_kernel(const int32_t *__restrict__ grp_u, const int32_t *__restrict__ 
     if (beliefs) {
         const bool ok = s > 0.0 && isfinite(s);
         float *brow = beliefs + (size_t)g * ldv;
-        for (int e = threadIdx.x; e < V; e += blockDim.x) brow[e] = ok ? (float)((double)prod(e) / s) : 1.0f / (float)V;
+        if (VEC) {
+            for (int e = 4 * threadIdx.x; e < V; e += 4 * blockDim.x) {
+                T p[4];
+                prod4(e, p);
+                float4 o;                                          // (columns >= V of the padded row: whatever the products are)
+                o.x = ok ? (float)((double)p[0] / s) : 1.0f / (float)V; o.y = ok ? (float)((double)p[1] / s) : 1.0f / (float)V;
+                o.z = ok ? (float)((double)p[2] / s) : 1.0f / (float)V; o.w = ok ? (float)((double)p[3] / s) : 1.0f / (float)V;
+                if (e + 3 < V) *reinterpret_cast<float4 *>(brow + e) = o;
+                else { const float ov[4] = {o.x, o.y, o.z, o.w}; for (int q = 0; q < 4 && e + q < V; ++q) brow[e + q] = ov[q]; }
+            }
+        } else {
+            for (int e = threadIdx.x; e < V; e += blockDim.x) brow[e] = ok ? (float)((double)prod(e) / s) : 1.0f / (float)V;
+        }
     }
 }
 
@@ -745,14 +790,18 @@ extern "C" int mlbp_marginals(int n_groups, const int32_t *grp_u, const int32_t 
     }
     MLBP_CHECK_ARG(!flags || (aux && cnts && flagged && n_flagged && tau >= 0.f && tau < 0.5f && tau_label >= 0.f && tau_label < 0.5f),
                    "marginals: near-tie detection needs aux, cnts, flagged, n_flagged and bands in [0, 0.5)");
-    if (range_log2 >= 0.f && range_log2 < 100.f)
-        marginals_kernel<float><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V,
-                                                                         logp, top1, rank, beliefs, tau, tau_label, aux,
-                                                                         cnts, flags, flagged, n_flagged);
-    else
-        marginals_kernel<double><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V,
-                                                                          logp, top1, rank, beliefs, tau, tau_label, aux,
-                                                                          cnts, flags, flagged, n_flagged);
+    // 16-byte loads when every row starts 16-byte aligned (the engine's buffers do); else the element-wise variant
+    const bool vec = (ldv % 4) == 0 && ((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(D) |
+                                         reinterpret_cast<uintptr_t>(beliefs)) % 16) == 0;
+    const bool f32 = range_log2 >= 0.f && range_log2 < 100.f;
+#define MLBP_K5(TT, VV)                                                                                                \
+    marginals_kernel<TT, VV><<<n_groups, 256, 0, as_stream(stream)>>>(grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, \
+                                                                      rank, beliefs, tau, tau_label, aux, cnts, flags, flagged, n_flagged)
+    if (f32 && vec) MLBP_K5(float, true);
+    else if (f32) MLBP_K5(float, false);
+    else if (vec) MLBP_K5(double, true);
+    else MLBP_K5(double, false);
+#undef MLBP_K5
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

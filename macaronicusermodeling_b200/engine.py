@@ -27,7 +27,7 @@ from . import _lib
  H_A_ROWS, H_D_ROWS, H_MAX_IN, H_NVARS, H_PAIR_R, H_PAIR_Z, H_MSG_BLK_N, H_MSG_BLK_OFF, H_MSG_ROWS, H_SPK_BLK_N) = range(29)
 H_WORDS, LEV_WORDS, GEMM_WORDS = 32, 10, 4
 (PLAN_BLOB_WORDS, PLAN_A_ROWS, PLAN_D_ROWS, PLAN_N_LEVELS, PLAN_N_PAIR, PLAN_N_GEMM_ROWS, PLAN_MAX_IN, PLAN_HDR_WORDS,
- PLAN_N_DEAD) = range(9)
+ PLAN_N_DEAD, PLAN_TMPL_HITS, PLAN_TMPL_MISSES) = range(11)
 A_SCALE_LOG2 = 14
 GEMM_A_HI_ONLY = 256          # include/mlbp.h MLBP_GEMM_A_HI_ONLY
 GEMM_B_HI_ONLY = 512          # include/mlbp.h MLBP_GEMM_B_HI_ONLY
@@ -302,6 +302,7 @@ class Engine(object):
         self.kernel_events = []
         self.event_tag = 0          # copied into every gemm_events record (bench.py: which step a launch belongs to)
         self.plan_seconds = 0.0     # host time spent in the schedule compiler (mlbp_plan_compile + export)
+        self.plan_template_hits = self.plan_template_misses = 0   # graphs served from / added to the template cache (csrc/plan.cpp)
 
     def _gemm_slice_rows(self, pairs):
         """Rows per K4 launch of the three-pass message GEMMs (0 = never slice).  The CTA pairs of one launch start in step and
@@ -469,6 +470,8 @@ class Engine(object):
                                          ctypes.byref(handle)))
         sizes = np.zeros(16, dtype=np.int64)
         _lib.check(lib.mlbp_plan_sizes(handle, _hp(sizes)))
+        self.plan_template_hits += int(sizes[PLAN_TMPL_HITS])
+        self.plan_template_misses += int(sizes[PLAN_TMPL_MISSES])
         return handle, sizes
 
     def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False,

@@ -150,13 +150,14 @@ def predict(engine, sents, raw, en_domain, de_domain, options, rng, qp, batch=64
         chunk = sents[lo:lo + batch]
         corpus = Corpus(chunk)
         r = engine.run(corpus, draw_roots(corpus, 3, rng), 3, want_grad=False, want_marg=True, want_beliefs=not qp,
-                       approx_inference=options.use_approx_inference)
+                       approx_inference=options.use_approx_inference, want_topk=0 if qp else min(50, V - 1))
         logp_sum += float(r.logp.sum().item())
         rank = r.rank.cpu().numpy()
         p0 += int((rank == 0).sum()); p25 += int((rank < 26).sum()); p50 += int((rank < 50).sum()); tot += len(rank)
         if qp:
             continue
         B = r.beliefs.cpu().numpy()[:, :V].astype(np.float64)
+        TI, _, TT = (x.cpu().numpy() for x in r.topk)        # the 50 best words per variable, listed on the device (mlbp_topk_rows)
         for si, s in enumerate(chunk):
             ti = raw[lo + si]
             nodes = sorted(ti['current_sent'], key=lambda n: int(n['position']))
@@ -167,8 +168,11 @@ def predict(engine, sents, raw, en_domain, de_domain, options, rng, qp, batch=64
                     b = B[vi]
                     vi += 1
                     top = min(50, V - 1)
-                    idx = np.argpartition(b, -top)[-top:]
-                    idx = idx[np.argsort(b[idx])][::-1]
+                    if TT[vi - 1] == 0:
+                        idx = TI[vi - 1]
+                    else:                                    # exact ties: the reference's order is NumPy's (LBP.py:405-406)
+                        idx = np.argpartition(b, -top)[-top:]
+                        idx = idx[np.argsort(b[idx])][::-1]
                     with np.errstate(divide='ignore'):
                         lb = np.log(b)
                     sl = en_domain[int(s.label[p])]

@@ -14,3 +14,11 @@ print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d[
 print({k: round(v['frac'], 3) for k, v in d['hbm_kernels'].items()}, {k: round(v['share_of_step'], 4) for k, v in d['hbm_kernels'].items()})
 print(d['message_rows']['rescore'], d['host'])
 P
+if [ -n "${WITH_C5:-}" ]; then
+    python bench.py --config c5 --no-cpu-baseline > $O/${TAG}_bench_c5_n1.json 2> $O/${TAG}_bench_c5_n1.err; echo "bench c5 rc=$?"
+    python - <<P
+import json
+d = json.loads(open('$O/${TAG}_bench_c5_n1.json').read().strip().splitlines()[-1])
+print('c5', d['value'], d['e2e'], d['ms_per_step'], d['roofline']['frac'], d['roofline'].get('by_role'))
+P
+fi

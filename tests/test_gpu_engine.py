@@ -363,7 +363,8 @@ def test_reduced_pass_rows_equal_three_pass_decisions_at_scale(regime):
     assert out[1][5]['msg_passes'] == 2 and out[2][5]['msg_passes'] == 1
     if regime == 'trained':
         assert out[2][5]['spike_flag'] == 1 and out[0][0].max() > 0.2, 'the trained regime must be peaked'
-    for o, b_tol, l_tol in ((out[1], 1e-7, 2e-6), (out[2], 5e-7, 1e-5)):
+    # (beliefs are ~2e-4 in the flat regime and up to 0.3 in the trained one: the bounds are absolute, the contract is 1e-4)
+    for o, b_tol, l_tol in ((out[1], 1e-7 if regime == 'flat' else 1e-6, 2e-6), (out[2], 5e-7 if regime == 'flat' else 3e-5, 1e-5)):
         assert o[5]['msg_two_pass'] and o[5]['peak_flag'] == 0 and o[5]['rescored'] > 0
         np.testing.assert_array_equal(out[0][1], o[1])
         rk0, rk1 = out[0][2], o[2]
