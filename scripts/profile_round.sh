@@ -29,6 +29,7 @@ if [ -z "$SKIP_SMALL" ]; then
     full k5 marginals_kernel ${WARM:-6} 1
     full k5b rescore_kernel ${WARM:-6} 1
     full k6a pair_expectations_kernel ${WARM:-6} 1
+    full k4a spike_scan_kernel 200 2
     NSP=$(( $(grep -c spike_correct_kernel $OUT/${TAG}_ncu_launches_128sent.csv) / 3 ))
     full k4b spike_correct_kernel $(( NSP > 4 ? NSP - 4 : 0 )) 4
 fi
