@@ -424,6 +424,9 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
 
     // rasterisation: GROUP_M / 2 pairs deep (the same 16 M-tiles as the one-CTA kernel), then along n
     constexpr int GROUP_P = GROUP_M / 2;
+    // (Measured and removed in round 2: an L2 prefetch (cp.async.bulk.prefetch.tensor ... L2) of the A / B tiles 4-32 k-blocks
+    // ahead of the shared-memory ring, on the theory that the one-pass rows wait for DRAM misses of slabs their wave streams
+    // for the first time -- 3 % SLOWER at every distance, alone and in the bench: profiles/r2f_gemm_probe_l2_prefetch.txt.)
     // (Measured and removed in round 2: issuing the narrow last N tiles of all M pairs at the END of the launch instead of
     // inside the raster -- the idea was that equal-length tiles keep co-resident pairs in step -- was +0.8 % in the bench,
     // inside the run-to-run noise: profiles/r2a_bench_c3_ab_narrow_last.txt.)
