@@ -276,6 +276,7 @@ class FactorGraph():
         local = dict((vid, i) for i, vid in enumerate(vids))
         var_de, var_label = [-1] * len(vids), [0] * len(vids)
         giv = [[] for _ in vids]
+        ed_factor = [None] * len(vids)
         pairs = []
         for f in self.factors:
             if len(f.varset) == 1:
@@ -285,6 +286,7 @@ class FactorGraph():
                     if var_de[local[v.id]] != -1:
                         raise NotImplementedError('more than one en_de factor on a variable')
                     var_de[local[v.id]] = int(od)
+                    ed_factor[local[v.id]] = f
                 elif f.factor_type == 'en_en':
                     giv[local[v.id]].append((int(od), 1 if self._gap_class(f) else 0))
                 else:
@@ -299,15 +301,12 @@ class FactorGraph():
                 raise BaseException("only unary or binary factors are supported...")
         pairs.sort(key=lambda t: t[0])
         sp_off, sp_en, sp_feat, sp_val = [0], [], [], []
-        phi = self.phi_en_de
         for i, vid in enumerate(vids):
             var_label[i] = int(self.variables[vid].supervised_label_index)
             d = var_de[i]
-            if d >= 0:                                   # train.py:176-215 wrote the dynamic features into phi_en_de in place
-                col = phi[:, d, 2:5]
-                e_idx, k_idx = np.nonzero(col)
-                for e, k in zip(e_idx.tolist(), k_idx.tolist()):
-                    sp_en.append(e); sp_feat.append(2 + k); sp_val.append(float(col[e, k]))
+            if d >= 0:                                   # train.py:176-215 wrote the dynamic features into phi_en_de in place;
+                for e, feat, val in self._sparse_for(ed_factor[i]):     # the list is the snapshot slice_potentials() took
+                    sp_en.append(e); sp_feat.append(feat); sp_val.append(val)
             sp_off.append(len(sp_en))
         giv_off, giv_label, giv_gap1 = [0], [], []
         for g in giv:
@@ -386,12 +385,18 @@ class FactorGraph():
             self._messages = msgs
         return self._messages
 
-    def _sparse_for(self, f):
-        if f.factor_type != 'en_de':
-            return []
-        col = self.phi_en_de[:, f.potential_table.observed_dim, 2:5]
+    def _sparse_now(self, observed_dim):
+        col = self.phi_en_de[:, observed_dim, 2:5]
         e_idx, k_idx = np.nonzero(col)
         return [(int(e), 2 + int(k), float(col[e, k])) for e, k in zip(e_idx, k_idx)]
+
+    def _sparse_for(self, f):
+        """COO list of the dynamic features (train.py:176-215) of an en_de factor: the snapshot slice_potentials() took, else
+        (a table attached without slice_potentials) the planes as they are now"""
+        if f.factor_type != 'en_de':
+            return []
+        snap = getattr(f.potential_table, 'sparse', None)
+        return snap if snap is not None else self._sparse_now(f.potential_table.observed_dim)
 
     # ------------------------------------------------------------------ reference API: results
     def get_posterior_probs(self):
@@ -846,6 +851,12 @@ class PotentialTable():
         """LBP.py:695-710.  When the caller computed graph.pot_* (train.py:251-253) the table is sliced from it like the
         reference does (a view / column copy, no arithmetic); the GPU engine never reads it -- it rebuilds the potentials
         from theta and the features."""
+        # the per-sentence (dynamic) features of an en_de factor are fixed HERE, like the reference's potentials are
+        # (train.py:239-250 computes them right before this call): graphs built from one PhiWrapper one after the other must
+        # not see each other's history features when they are evaluated later
+        g = getattr(self.factor, 'graph', None)
+        if g is not None and self.factor.factor_type == 'en_de' and self.observed_dim is not None and not self.explicit:
+            self.sparse = g._sparse_now(self.observed_dim)
         table = self.factor.get_pot()
         if table is None:
             self.table = None

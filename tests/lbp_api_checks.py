@@ -25,6 +25,38 @@ def graph_from_fixture(z):
     return fg, spec
 
 
+def check_dynamic_features_are_fixed_at_build_time(path):
+    """train.py:176-215 writes a sentence's history features into the SHARED phi_en_de planes and train.py:239-250 turns them
+    into potentials right away; a second graph built from the same PhiWrapper before the first one is evaluated must not
+    change the first one's results (the lazy shim snapshots the features in PotentialTable.slice_potentials)"""
+    z = np.load(path, allow_pickle=False)
+    V, Vd = z['pmi'].shape[0], z['ed'].shape[1]
+    en_domain = ['e%d' % i for i in range(V)]
+    de_domain = ['d%d' % i for i in range(Vd)]
+    en2id = dict((e, i) for i, e in enumerate(en_domain))
+    de2id = dict((d, i) for i, d in enumerate(de_domain))
+    pw = tc.make_phi_wrapper(z['pmi'], z['pmi_w1'], z['ed'], z['ped'])
+    spec = json.loads(str(z['spec']))
+    t_ee = np.array(z['theta_ee'], dtype=np.float64).reshape(1, 3)
+    t_ed = np.array(z['theta_ed'], dtype=np.float64).reshape(1, 6)
+    opts = tc.default_options(session_history=True)
+    mk = lambda sent: tc.create_factor_graph(sent, spec.get('lr', 0.1), tc.F_EN_EN_NAMES, tc.F_EN_DE_NAMES, t_ee, t_ed, pw,
+                                             en_domain, de2id, en2id, {}, options=opts, N=spec.get('N', 10), de_domain=de_domain)
+    first = mk(str(z['sentence']))
+    other = json.loads(str(z['sentence']))
+    assert len(other['past_correct_guesses']) + len(other['past_guesses_for_current_sent']) > 0
+    other['past_correct_guesses'], other['past_guesses_for_current_sent'] = [], []
+    second = mk(json.dumps(other))                               # rewrites the dynamic planes of the shared wrapper
+    roots = [int(r) for r in z['roots']]
+    marg = []
+    for fg in (first, second):
+        fg.initialize(roots[0])
+        fg.treelike_inference(spec['sweeps'], roots[1:])
+        marg.append(np.stack([fg.variables[v].get_marginal().m[:, 0] for v in sorted(fg.variables.keys())]))
+    assert np.abs(marg[0] - z['marginals']).max() < 1e-6        # the first graph still sees ITS history features
+    assert np.abs(marg[1] - z['marginals']).max() > 1e-4        # ... and the second one its own (none)
+
+
 def check_lbp_api_fixture(path, check_messages=True):
     z = np.load(path, allow_pickle=False)
     fg, spec = graph_from_fixture(z)

@@ -27,6 +27,10 @@ def test_lbp_api_matches_reference_fixture(path):
     lbp_api_checks.check_lbp_api_fixture(path)
 
 
+def test_dynamic_features_are_fixed_when_the_graph_is_built():
+    lbp_api_checks.check_dynamic_features_are_fixed_at_build_time(os.path.join(GOLDEN, 'graph_peaked.npz'))
+
+
 def test_explicit_table_graph_initialises_like_the_reference():
     import numpy as np
     lbp_api_checks.check_explicit_graph_structure(np.load(os.path.join(GOLDEN, 'graphx_explicit.npz'), allow_pickle=False))
