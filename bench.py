@@ -417,6 +417,7 @@ class Workload(object):
             self.lr = 0.1 / float(self.n_global)    # minibatch sum of gradients: the reference's 0.1 per sentence, averaged
         self.tr.theta_ee, self.tr.theta_ed = theta0()
         self.parts = self.eng.prepare(self.corpus, a.sweeps, self.train) if self.corpus is not None else None
+        self._next_roots = None
         self.peaked = []                                                    # red[15] of every step
         self.all_peaked = []
         self.thetas = []
@@ -437,9 +438,13 @@ class Workload(object):
     def step(self):
         if self.corpus is None:                                             # c4 --user-adapt: one engine pass per user
             return self._finish(self.tr.step_domains([(u, c, self.roots(c)) for u, c in self.batches], self.lr))
+        # the roots of the NEXT step are drawn now (they do not depend on theta): the trainer compiles that step's first
+        # micro-batch schedule in the background while the host waits for this step's all-reduce
+        roots = self._next_roots if self._next_roots is not None else self.roots(self.corpus)
+        self._next_roots = self.roots(self.corpus)
         if self.train:
-            return self._finish(self.tr.step(self.parts, self.roots(self.corpus), self.lr))
-        return self._finish(self.tr.eval_step(self.parts, self.roots(self.corpus)))
+            return self._finish(self.tr.step(self.parts, roots, self.lr, next_roots=self._next_roots))
+        return self._finish(self.tr.eval_step(self.parts, roots, next_roots=self._next_roots))
 
     def step_e2e(self):
         fresh = lambda c: self.Corpus(**{f: getattr(c, f) for f in self.Corpus.FIELDS})   # nothing cached on the device
@@ -635,6 +640,7 @@ def ours(a):
                        'k4_rows_per_sliced_launch': eng.gemm_slice_rows},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'hbm_kernels': hbm,
             'host': {'plan_compile_s_per_step': plan_s_per_step, 'plan_threads': int(os.environ.get('MLBP_PLAN_THREADS', '0')),
+                     'schedules_compiled_ahead': eng.plan_prefetched,   # next step's first micro-batch, during the wait for the all-reduce
                      'schedule_templates': {'hits_in_timed_steps': tm1[0] - tm0[0], 'compiled_in_timed_steps': tm1[1] - tm0[1],
                                             'note': 'graphs whose schedule was relocated from a cached template vs compiled (csrc/plan.cpp); roots are redrawn every step'}},
             'message_rows': {'passes': pass_stats['msg_passes'], 'reduced_pass_enabled': pass_stats['msg_two_pass'], 'ranks_switched_to_three_passes_per_step': peaked_value,

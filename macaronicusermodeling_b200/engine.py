@@ -303,6 +303,8 @@ class Engine(object):
         self.event_tag = 0          # copied into every gemm_events record (bench.py: which step a launch belongs to)
         self.plan_seconds = 0.0     # host time spent in the schedule compiler (mlbp_plan_compile + export)
         self.plan_template_hits = self.plan_template_misses = 0   # graphs served from / added to the template cache (csrc/plan.cpp)
+        self._pre = {}              # schedules being compiled ahead of their run() call: key -> (thread, result box)
+        self.plan_prefetched = 0    # run() calls that found their schedule precompiled
 
     def _gemm_slice_rows(self, pairs):
         """Rows per K4 launch of the three-pass message GEMMs (0 = never slice).  The CTA pairs of one launch start in step and
@@ -458,21 +460,76 @@ class Engine(object):
             self._blob_dev = torch.empty(n, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------ one microbatch
-    def compile(self, corpus, roots, sweeps, want_grad, want_marg, fold=True, reuse_z=True):
-        roots = np.ascontiguousarray(roots, dtype=np.int32)
-        assert roots.shape[0] == corpus.n_sent and roots.shape[1] >= 1 + sweeps, roots.shape
-        roots = np.ascontiguousarray(roots[:, :1 + sweeps])
+    @staticmethod
+    def _compile_raw(corpus, roots, sweeps, flags):
         handle = ctypes.c_void_p()
         lib = _lib.load()
-        flags = (1 if want_grad else 0) | (2 if want_marg else 0) | (0 if fold else 4) | (0 if reuse_z else 8)
         _lib.check(lib.mlbp_plan_compile(corpus.n_sent, _hp(corpus.var_off), _hp(corpus.pair_off), _hp(corpus.pair_v0),
                                          _hp(corpus.pair_v1), _hp(corpus.pair_gap1), _hp(roots), sweeps, flags,
                                          ctypes.byref(handle)))
         sizes = np.zeros(16, dtype=np.int64)
         _lib.check(lib.mlbp_plan_sizes(handle, _hp(sizes)))
+        return handle, sizes
+
+    @staticmethod
+    def _plan_key(corpus, roots, sweeps, flags):
+        return (id(corpus), corpus.n_sent, int(sweeps), int(flags), roots.tobytes())
+
+    def _plan_flags(self, want_grad, want_marg, approx_inference=False, approx_beliefs=False):
+        """mlbp_plan_compile flags of a run() call under the CURRENT theta (the reduced-pass gates of set_theta decide reuse_z)"""
+        approx = approx_inference or approx_beliefs
+        grad_hi_only = self.grad_a_terms == 1 and self.grad_hi_only_ok and not approx
+        two_pass = self.msg_two_pass_ok and not approx
+        fold, reuse_z = not approx_inference, (not approx and not grad_hi_only and not two_pass)
+        return (1 if want_grad else 0) | (2 if want_marg else 0) | (0 if fold else 4) | (0 if reuse_z else 8)
+
+    def compile(self, corpus, roots, sweeps, want_grad, want_marg, fold=True, reuse_z=True):
+        roots = np.ascontiguousarray(roots, dtype=np.int32)
+        assert roots.shape[0] == corpus.n_sent and roots.shape[1] >= 1 + sweeps, roots.shape
+        roots = np.ascontiguousarray(roots[:, :1 + sweeps])
+        flags = (1 if want_grad else 0) | (2 if want_marg else 0) | (0 if fold else 4) | (0 if reuse_z else 8)
+        pre = self._pre.pop(self._plan_key(corpus, roots, sweeps, flags), None) if self._pre else None
+        if pre is not None:                                       # compiled ahead by precompile(): wait for it, take it
+            pre[0].join()
+            if 'error' in pre[1]:
+                raise pre[1]['error']
+            handle, sizes = pre[1]['plan']
+            self.plan_prefetched += 1
+        else:
+            handle, sizes = self._compile_raw(corpus, roots, sweeps, flags)
         self.plan_template_hits += int(sizes[PLAN_TMPL_HITS])
         self.plan_template_misses += int(sizes[PLAN_TMPL_MISSES])
         return handle, sizes
+
+    def precompile(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, approx_inference=False, approx_beliefs=False):
+        """Start compiling the schedule of a LATER run(corpus, roots, ...) call in a background thread (mlbp_plan_compile keeps
+        no Python state and ctypes releases the GIL): the roots of the next SGD step do not depend on theta, so the host can
+        compile its first micro-batch while it waits for the GPU to finish the current step.  run() picks the plan up when it
+        is called with the same Corpus object, roots and options; a plan nobody picks up (theta moved across a reduced-pass
+        gate and changed the flags, say) is dropped by the next precompile() / drop_precompiled()."""
+        import threading
+        self.drop_precompiled()
+        roots = np.ascontiguousarray(roots, dtype=np.int32)
+        roots = np.ascontiguousarray(roots[:, :1 + sweeps])
+        flags = self._plan_flags(want_grad, want_marg, approx_inference, approx_beliefs)
+        box = {}
+
+        def work():
+            try:
+                box['plan'] = self._compile_raw(corpus, roots, sweeps, flags)
+            except Exception as e:                                # re-raised by the run() that picks the plan up
+                box['error'] = e
+
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+        self._pre[self._plan_key(corpus, roots, sweeps, flags)] = (t, box)
+
+    def drop_precompiled(self):
+        for t, box in self._pre.values():
+            t.join()
+            if 'plan' in box:
+                _lib.load().mlbp_plan_destroy(box['plan'][0])
+        self._pre = {}
 
     def run(self, corpus, roots, sweeps=3, want_grad=True, want_marg=True, want_beliefs=False, want_messages=False,
             approx_inference=False, approx_beliefs=False, topk=100, reduce_into=None, want_topk=0):

@@ -39,17 +39,19 @@ class Trainer(object):
     def lr(self, epoch):
         return self.init_lr / float(1.0 + epoch * 0.3)           # train.py:621
 
-    def step(self, parts_or_corpus, roots, lr, all_reduce=True, **kw):
+    def step(self, parts_or_corpus, roots, lr, all_reduce=True, next_roots=None, **kw):
         """One synchronous minibatch SGD step over this rank's sentences.  Returns the 16-vector
         [g_ee(3), g_ed(6), sum logp, p@0, p@25, p@50, n_vars, n_sent, peaked] summed over all ranks (device tensor);
-        `peaked` counts the ranks whose var->factor kernel saw a peaked message (their message GEMMs ran three passes)."""
-        return self._reduce(parts_or_corpus, roots, True, all_reduce, **kw)
+        `peaked` counts the ranks whose var->factor kernel saw a peaked message (their message GEMMs ran three passes).
+        `next_roots` (with prepared parts): the roots of the NEXT step over the same parts -- its first micro-batch's schedule
+        is compiled in the background while the host waits for this step's result (Engine.precompile)."""
+        return self._reduce(parts_or_corpus, roots, True, all_reduce, next_roots, **kw)
 
-    def eval_step(self, parts_or_corpus, roots, all_reduce=True, **kw):
+    def eval_step(self, parts_or_corpus, roots, all_reduce=True, next_roots=None, **kw):
         """batch_predictions (train.py:308-338) for this rank's sentences: inference only; same 16-vector, gradient slots 0"""
-        return self._reduce(parts_or_corpus, roots, False, all_reduce, **kw)
+        return self._reduce(parts_or_corpus, roots, False, all_reduce, next_roots, **kw)
 
-    def _reduce(self, parts_or_corpus, roots, want_grad, all_reduce, **kw):
+    def _reduce(self, parts_or_corpus, roots, want_grad, all_reduce, next_roots=None, **kw):
         eng = self.engine
         eng.set_theta(self.theta_ee, self.theta_ed, with_grad=want_grad)
         if self._red is None:
@@ -58,6 +60,10 @@ class Trainer(object):
         eng.k.call('mlbp_zero_words', ctypes.c_void_p(red.data_ptr()), 32)
         fn = eng.run_many if isinstance(parts_or_corpus, Corpus) else eng.run_prepared
         fn(parts_or_corpus, roots, self.sweeps, want_grad, True, reduce_into=red, collect=False, **kw)
+        if next_roots is not None and not isinstance(parts_or_corpus, Corpus) and parts_or_corpus:
+            lo, hi, c = parts_or_corpus[0]                          # everything of this step is enqueued: the host is free
+            eng.precompile(c, np.ascontiguousarray(next_roots, dtype=np.int32)[lo:hi], self.sweeps, want_grad, True,
+                           **{k: v for k, v in kw.items() if k in ('approx_inference', 'approx_beliefs')})
         if all_reduce and dist_info()[1] > 1:
             import torch.distributed as dist
             dist.all_reduce(red, op=dist.ReduceOp.SUM)

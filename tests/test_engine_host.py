@@ -322,3 +322,37 @@ def test_want_topk_lists_the_most_probable_words_best_first():
             np.testing.assert_array_equal(idx[v][:10], want[:10])     # (far down the list fp32 beliefs may swap near-equal words)
             v += 1
     assert r.top1.numpy().tolist() == idx[:, 0].tolist()
+
+
+def test_next_steps_schedule_is_compiled_ahead():
+    """Trainer.step(next_roots=...) starts the next step's first schedule compile in the background (Engine.precompile); the
+    step that follows picks that plan up and computes exactly what an engine without the prefetch computes; a prefetched plan
+    nobody asks for is dropped"""
+    from macaronicusermodeling_b200.trainer import Trainer
+    model = synth.make_model(64, 16, seed=4)
+    sents = synth.make_corpus(model, 10, k=4, g=1, seed=2)
+    roots_pos = [synth.draw_roots(sents, 3, seed=s) for s in (1, 2, 3)]
+    out = {}
+    for name in ('plain', 'ahead'):
+        eng = Engine(model, kernels=FakeKernels())
+        eng.rows_budget = lambda: 150                              # several micro-batches per step
+        corpus = Corpus(sents)
+        parts = eng.prepare(corpus, 3, True)
+        assert len(parts) > 1
+        tr = Trainer(eng, reg_param=0.2, N=len(sents))
+        tr.theta_ee, tr.theta_ed = np.array([0.4, 0.3, 0.0]), np.array([0.5, 0.2, 0.1, 0.1, 0.1, 0.0])
+        roots = [corpus.roots_from_positions(r) for r in roots_pos]
+        hist = []
+        for i in range(3):
+            nxt = roots[i + 1] if (name == 'ahead' and i + 1 < 3) else None
+            red = tr.step(parts, roots[i], 0.01, next_roots=nxt)
+            hist.append(tr.apply(red, 0.01).copy())
+        out[name] = (hist, eng.plan_prefetched)
+        if name == 'ahead':                                        # a plan nobody picks up is joined and destroyed
+            eng.precompile(parts[0][2], roots[0][parts[0][0]:parts[0][1]], 3)
+            assert len(eng._pre) == 1
+            eng.drop_precompiled()
+            assert not eng._pre
+    assert out['plain'][1] == 0 and out['ahead'][1] == 2
+    for a, b in zip(out['plain'][0], out['ahead'][0]):
+        np.testing.assert_array_equal(a, b)
