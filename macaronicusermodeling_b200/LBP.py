@@ -743,8 +743,14 @@ class FactorNode():
                 r = np.reshape(m.m, (1, np.size(m.m)))
             else:
                 raise NotImplementedError("only supports pairwise factors..")
-        marginals = au.dense_dot(np.ascontiguousarray(c), np.ascontiguousarray(r))
-        beliefs = au.normalize(au.dense_pointwise_multiply(marginals, self._table()))
+        c, r = np.ascontiguousarray(c), np.ascontiguousarray(r)
+        if self.graph.use_approx_beliefs and np.size(c) > au.K:   # LBP.py:554-563: the top-K x top-K block only
+            approx_marginals, c_idx, r_idx = au.sparse_dot(c, r)
+            beliefs = au.sparse_pointwise_multiply(approx_marginals, c_idx, r_idx, self._table())
+            beliefs = au.sparse_normalize(beliefs, c_idx, r_idx)
+        else:
+            marginals = au.dense_dot(c, r)
+            beliefs = au.normalize(au.dense_pointwise_multiply(marginals, self._table()))
         if self.graph.report_times: self.graph.bb_times.append(time.time() - bb)
         return beliefs
 
