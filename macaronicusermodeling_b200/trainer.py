@@ -115,21 +115,27 @@ class AdaptTrainer(Trainer):
 
     def step_domains(self, batches, lr, **kw):
         """batches: list of (domain, Corpus, roots).  Returns the reduced 16-vector like Trainer.step.  `kw`: Engine.run options
-        (approx_inference, approx_beliefs, topk: the reference trains with them too, train.py:155-156)."""
+        (approx_inference, approx_beliefs, topk: the reference trains with them too, train.py:155-156).  A domain appears at most
+        once per call (its sentences of this minibatch form ONE batch): every batch sees the theta its domain had before the call."""
+        if len(set(d for d, _, _ in batches)) != len(batches):
+            raise ValueError('step_domains: one batch per domain and call')
         eng = self.engine
-        total = torch.zeros(16, dtype=torch.float64, device=eng.device)
-        dom = torch.zeros(16, dtype=torch.float64, device=eng.device)
+        # one row of sums per domain, all on the device: a domain's theta only needs ITS row, so nothing is read back before every
+        # domain is enqueued -- the host compiles the next domain's schedule while the GPU works on this one (a read-back per
+        # domain, as in round 1, left the GPU idle for one schedule compile per user: 16 % of a 64-user pass)
+        doms = torch.zeros((max(len(batches), 1), 16), dtype=torch.float64, device=eng.device)
         reg = self.reg_param / float(self.N if self.N else sum(c.n_sent for _, c, _ in batches))
-        for d, corpus, roots in batches:
+        for i, (d, corpus, roots) in enumerate(batches):
             te, td = self.domain2theta[d]
             eng.set_theta(te, td)
-            eng.k.call('mlbp_zero_words', ctypes.c_void_p(dom.data_ptr()), 32)
-            eng.run_many(corpus, roots, self.sweeps, True, True, reduce_into=dom, collect=False, **kw)
-            total += dom
-            h = dom.cpu().numpy()                               # the domain's theta is updated on the host, once per domain
+            eng.run_many(corpus, roots, self.sweeps, True, True, reduce_into=doms[i], collect=False, **kw)
+        total = doms.sum(dim=0)
+        hd = doms.cpu().numpy()                                     # the step's only device -> host read before the all-reduce
+        for i, (d, corpus, roots) in enumerate(batches):
+            te, td = self.domain2theta[d]
             n = corpus.n_sent
-            self.domain2theta[d] = (te + lr * (h[:3] - n * reg * self.ua_scale * te),
-                                    td + lr * (h[3:9] - n * reg * self.ua_scale * td))
+            self.domain2theta[d] = (te + lr * (hd[i, :3] - n * reg * self.ua_scale * te),
+                                    td + lr * (hd[i, 3:9] - n * reg * self.ua_scale * td))
         total[15] = (total[15] > 0).to(total.dtype)
         if dist_info()[1] > 1:
             import torch.distributed as dist
