@@ -22,11 +22,14 @@ def main():
     ap.add_argument('--gemm-impl', type=int, default=0, help='K4 variant (include/mlbp.h, csrc/gemm_tcgen05.cu)')
     ap.add_argument('--grad-terms', type=int, default=1, help='2 = three-pass gradient rows (for comparison)')
     ap.add_argument('--msg-passes', type=int, default=None, help='1 / 2 / 3 tensor-core passes on the message rows (default: Engine rule)')
+    ap.add_argument('--theta', default='flat', choices=['flat', 'trained'],
+                    help="trained = the theta bench.py's SGD reaches after ~12 steps (history weight 7.5: beliefs of 0.8 on the label, spiky messages)")
     a = ap.parse_args()
     model = synth.make_model(10000, 2000, seed=1234, dtype=np.float32)
     sents = synth.make_corpus(model, a.n, k=20, g=0, seed=4242)
     roots_pos = synth.draw_roots(sents, 3, seed=11)
-    te, td = [0.8, 0.5, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]
+    te, td = ([0.8, 0.5, -0.3], [1.0, -0.6, 0.5, 0.3, 0.4, -0.2]) if a.theta == 'flat' else \
+        ([-0.003, 0.049, -0.3], [0.101, -0.047, 7.534, 0.3, 0.4, -0.2])
     eng = Engine(model, grad_a_terms=a.grad_terms, grad_b_terms=a.grad_terms, gemm_impl=a.gemm_impl, msg_passes=a.msg_passes)
     eng.set_theta(te, td)
     corpus = Corpus(sents)
@@ -36,12 +39,13 @@ def main():
     t0 = time.time()
     tb = orc.Tables(m64, te, td)
     off = corpus.var_off
-    worst_b = worst_g = worst_lp = 0.0
+    worst_b = worst_g = worst_lp = peak = 0.0
     flips = n_var = 0
     for i, s in enumerate(sents):
         o = orc.run_fast(tb, s, roots_pos[i], 3)
         b = B[off[i]:off[i + 1], :10000]
         worst_b = max(worst_b, float(np.abs(b - o['marginals']).max()))
+        peak = max(peak, float(o['marginals'].max()))
         flips += int((T1[off[i]:off[i + 1]] != o['top1']).sum())
         n_var += off[i + 1] - off[i]
         ref = np.concatenate([o['g_ee_unreg'][0], o['g_ed_unreg'][0]])
@@ -49,7 +53,7 @@ def main():
         worst_g = max(worst_g, float((np.abs(G[i] - ref)[nz] / np.abs(ref)[nz]).max()))
         worst_lp = max(worst_lp, abs(float(LP[i]) - o['logp']) / abs(o['logp']))
     print(json.dumps({'config': 'C3 shape, %d sentences, V=10000, k=20, 3 sweeps' % a.n, 'variables': int(n_var),
-                      'top1_mismatches': flips, 'max_abs_belief_error': worst_b, 'max_rel_gradient_error': worst_g,
+                      'theta': a.theta, 'largest_belief': peak, 'top1_mismatches': flips, 'max_abs_belief_error': worst_b, 'pass_stats': eng.pass_stats(), 'max_rel_gradient_error': worst_g,
                       'max_rel_logposterior_error': worst_lp, 'message_rows_passes': a.msg_passes, 'gradient_rows_passes': 3 if a.grad_terms == 2 else (1 if eng.grad_one_pass_ok else 2),
                       'oracle_seconds': time.time() - t0}))
 
