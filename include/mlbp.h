@@ -78,10 +78,14 @@ int mlbp_dense_pointwise_multiply_f64(const double *m1, const double *m2, double
  *           (the normaliser and feature expectations of the unary en_en factors, LBP.py:540, :600-603), then the
  *           row sums sum_b T[a,b], sum_b T1[a,b]: together with the column sums they are the factor->variable
  *           messages of a pairwise factor whose incoming message is still the uniform initial one (LBP.py:211-216).
- *   with_grad_planes = 0 skips planes 8..19 (inference only).                                        */
+ *   with_grad_planes = 0 skips planes 8..19 (inference only).
+ *   r_planes (or NULL): four more fp16 planes [V, ldv], same stride, R.hi Rt.hi R1.hi R1t.hi with R = T - tbar, R1 = T1 - tbar
+ *           (scaled like the others, stochastic rounding of the magnitude), tbar = 2^scale_exp * exp(th[2]) = the table at
+ *           phi = 0, returned in *h_tbar: the operand of the ONE-pass message rows, whose GEMM adds tbar * sum(message) back as
+ *           a constant (mlbp_factor_to_var_gemm_gated add_const) -- the fp16 rounding is then relative to |T - tbar|.        */
 int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1, int V, int ldf, const double *h_theta_ee,
                                int scale_exp, void *planes, int64_t plane_stride, int ldv, double *colsums,
-                               int with_grad_planes, void *stream);
+                               int with_grad_planes, void *r_planes, float *h_tbar, void *stream);
 /* edT, pedT: [Vd, ldf] fp32, de-major (row d = phi_en_de[:, d, k] of LBP.py:602 made contiguous).
  *   edstats[d] = { sum_e psi, sum_e psi*ed, sum_e psi*ped },  psi = exp(th[0]*ed + th[1]*ped + th[5])  (train.py:240,251) */
 int mlbp_build_unary_tables(const float *edT, const float *pedT, int V, int Vd, int ldf, const double *h_theta_ed,
@@ -153,11 +157,13 @@ int mlbp_spike_scan(const void *A_hi, const void *A_lo, int ldv, int V, int a_ro
  *   block_rows / block_n: this block's list of spiky rows and its length (mlbp_spike_scan).  Returns at once (on the device) when spike_words[0] is set: the block then ran with the lo half.
  *   Spikes of a row are applied in ascending column order (deterministic).
  *   A_hi_one_pass (or NULL): the block ran ONE pass (A_hi . B_hi, MLBP_GEMM_A_HI_ONLY | MLBP_GEMM_B_HI_ONLY), so the spikes' share
- *   of the other dropped term is restored too:  D[r, n] += alpha * hi_s * B_lo[n, col_s]  with hi_s read from A_hi[r, col_s].  */
+ *   of the other dropped term is restored too:  D[r, n] += alpha * hi_s * B_lo[n, col_s]  with hi_s read from A_hi[r, col_s].
+ *   Rt_hi (or NULL; needs A_hi_one_pass) + tbar: the one-pass block contracted with the RESIDUAL plane R = T - tbar; Rt_hi is the
+ *   residual plane of the transposed table:  D[r, n] += alpha * ((hi_s + lo_s) * (B[n, col_s] - tbar) - hi_s * R_hi[n, col_s]).  */
 int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
                        const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi,
                        const void *Bt_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
-                       const void *A_hi_one_pass, void *stream);
+                       const void *A_hi_one_pass, const void *Rt_hi, float tbar, void *stream);
 /* K5c. The K most probable words of each of n_rows belief rows X[r, 0..V) (fp32, row stride ldx), best first, on the device:
  *   VariableNode.get_max_vocab (LBP.py:402-411: np.argpartition + np.argsort on the host marginal; K = 50 for
  *   FactorGraph.to_string / get_precision_counts, LBP.py:87, :115).
@@ -195,11 +201,14 @@ int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_t
  * gate == NULL runs unconditionally.  tcgen05 kernels only (impl 1, the SIMT cross-check, ignores the gate on the host: error).
  * K range: [k0, k0 + k_len) in elements, multiples of 64 (k_len == 0: up to V).  A launch whose range does not start at 0
  * ADDS its product to D.  The engine splits a long K (V = 50 000) into several launches: the CTA pairs of one launch drift
- * apart in K and stop sharing operand slabs in L2, a kernel boundary re-aligns them.  CTA-pair kernel only.              */
+ * apart in K and stop sharing operand slabs in L2, a kernel boundary re-aligns them.  CTA-pair kernel only.
+ * add_const: added to every element of the product (by the launch whose K range starts at 0):  D = alpha * A . B^T + add_const.
+ * With B_hi a residual plane R = T - tbar (mlbp_build_pairwise_tables r_planes) and message rows that sum to 2^14,
+ * add_const = alpha * 2^14 * tbar makes a ONE-pass launch (A_HI_ONLY | B_HI_ONLY) the product with T itself.                 */
 int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows,
                                   const void *B_hi, const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd,
                                   float alpha, int impl, const int32_t *gate, int run_if_set, int k0, int k_len,
-                                  void *stream);
+                                  float add_const, void *stream);
 /* K5.  VariableNode.get_marginal / get_posterior_probs / get_precision_counts / argmax
  *   (LBP.py:392-411, :247-259, :80-106).  Same group layout as K3, all inputs multiplied.
  *   logp[g] = log b[label] (-99.99 if b[label] == 0), top1[g] = argmax b (first index on ties),

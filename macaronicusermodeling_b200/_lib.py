@@ -13,18 +13,18 @@ _SIGNATURES = {
     'mlbp_normalize_f64': 'pplpp',
     'mlbp_dense_dot_f64': 'pppiiip',
     'mlbp_dense_pointwise_multiply_f64': 'ppplp',
-    'mlbp_build_pairwise_tables': 'ppiipiplipip',
+    'mlbp_build_pairwise_tables': 'ppiipiplipi' + 'pp' + 'p',
     'mlbp_build_unary_tables': 'ppiiippp',
     'mlbp_unary_stats': 'ipppppppppppppiipppppp',
     'mlbp_unary_products': 'ippppppppppiippplii' + 'ppp',
     'mlbp_fill_uniform_rows': 'ppiipipp',
     'mlbp_var_to_factor': 'ippppppp' + 'ppii' + 'ppif' + 'p',
     'mlbp_spike_scan': 'ppii' + 'iif' + 'ppppp' + 'p',
-    'mlbp_spike_correct': 'ppppp' + 'ii' + 'ppii' + 'plif' + 'pp',
+    'mlbp_spike_correct': 'ppppp' + 'ii' + 'ppii' + 'plif' + 'ppf' + 'p',
     'mlbp_topk_mask_rows': 'ppiiliip',
     'mlbp_topk_rows': 'piiiipppp',
     'mlbp_factor_to_var_gemm': 'pplii' + 'ppii' + 'plifip',
-    'mlbp_factor_to_var_gemm_gated': 'pplii' + 'ppii' + 'plifi' + 'pi' + 'ii' + 'p',
+    'mlbp_factor_to_var_gemm_gated': 'pplii' + 'ppii' + 'plifi' + 'pi' + 'ii' + 'f' + 'p',
     'mlbp_marginals': 'ipppp' + 'ppii' + 'ppppf' + 'iff' + 'ppppp' + 'p',
     'mlbp_rescore_candidates': 'ippp' + 'pppp' + 'ppii' + 'pppl' + 'pii' + 'ppff' + 'f' + 'ppp' + 'p',
     'mlbp_zero_words': 'pip',

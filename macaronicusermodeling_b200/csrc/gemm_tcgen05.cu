@@ -159,7 +159,7 @@ template <int BN, int STAGES, int CHUNK_KB, int BK>
 __global__ void __launch_bounds__(Cfg<BN, STAGES, BK>::THREADS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                       const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                      float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
+                      float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha, float add_const,
                       int m_tiles, int n_tiles, int a_terms, int b_terms, const int32_t *__restrict__ gate, int run_if_set,
                       int *err_flag) {
     using C = Cfg<BN, STAGES, BK>;
@@ -283,14 +283,15 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
         const int m = m_blk * BM + q * 32 + lane;
         if (m < n_rows) {
             float *drow = D + (d_row0 + (int64_t)m) * (int64_t)ldd;
+            const float c0 = add_const;
             const int n0 = n_blk * BN + half * 128;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int nc = n0 + 4 * j;
                 if (nc < ldd) {                                   // ldd is a multiple of 64: a float4 is all-in or all-out
                     float4 o;                                     // columns >= V (row padding) are written as zeros
-                    o.x = nc + 0 < V ? acc[4 * j + 0] * alpha : 0.f; o.y = nc + 1 < V ? acc[4 * j + 1] * alpha : 0.f;
-                    o.z = nc + 2 < V ? acc[4 * j + 2] * alpha : 0.f; o.w = nc + 3 < V ? acc[4 * j + 3] * alpha : 0.f;
+                    o.x = nc + 0 < V ? fmaf(acc[4 * j + 0], alpha, c0) : 0.f; o.y = nc + 1 < V ? fmaf(acc[4 * j + 1], alpha, c0) : 0.f;
+                    o.z = nc + 2 < V ? fmaf(acc[4 * j + 2], alpha, c0) : 0.f; o.w = nc + 3 < V ? fmaf(acc[4 * j + 3], alpha, c0) : 0.f;
                     *reinterpret_cast<float4 *>(drow + nc) = o;
                 }
             }
@@ -398,7 +399,7 @@ template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<STAGES, A_T, B_T>::THREADS, 1)
 gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                           float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha,
+                           float *__restrict__ D, int64_t d_row0, int ldd, int a_row0, int n_rows, int V, float alpha, float add_const,
                            int m_pairs, int n_tiles, const int32_t *__restrict__ gate, int run_if_set, int kb0, int kb_n,
                            int *err_flag) {
     using C = PairCfg<STAGES, A_T, B_T>;
@@ -548,14 +549,15 @@ gemm_split_f16_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __
         const int m = m_blk * BM + q * 32 + lane;
         if (m < n_rows) {
             float *drow = D + (d_row0 + (int64_t)m) * (int64_t)ldd;
+            const float c0 = kb0 > 0 ? 0.f : add_const;       // the constant of a residual-plane product: once per K
             const int n0 = n_blk * BN + half * 128;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int nc = n0 + 4 * j;
                 if (nc < ldd) {
                     float4 o;                                     // columns >= V (row padding) are written as zeros
-                    o.x = nc + 0 < V ? acc[4 * j + 0] * alpha : 0.f; o.y = nc + 1 < V ? acc[4 * j + 1] * alpha : 0.f;
-                    o.z = nc + 2 < V ? acc[4 * j + 2] * alpha : 0.f; o.w = nc + 3 < V ? acc[4 * j + 3] * alpha : 0.f;
+                    o.x = nc + 0 < V ? fmaf(acc[4 * j + 0], alpha, c0) : 0.f; o.y = nc + 1 < V ? fmaf(acc[4 * j + 1], alpha, c0) : 0.f;
+                    o.z = nc + 2 < V ? fmaf(acc[4 * j + 2], alpha, c0) : 0.f; o.w = nc + 3 < V ? fmaf(acc[4 * j + 3], alpha, c0) : 0.f;
                     if (kb0 > 0) {                                // a later K range of a split launch: add to what is there
                         const float4 p = *reinterpret_cast<const float4 *>(drow + nc);
                         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
@@ -636,7 +638,7 @@ static int *g_err_flag = nullptr;   // pinned, mapped: the kernel records which 
 
 template <int BN, int STAGES, int CHUNK_KB, int BK = 64>
 static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
-                     const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
+                     const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, float add_const, int a_terms,
                      int b_terms, const int32_t *gate, int run_if_set, cudaStream_t st) {
     using C = Cfg<BN, STAGES, BK>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -660,14 +662,14 @@ static int launch_tc(const void *A_hi, const void *A_lo, int64_t a_rows_total, i
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_tiles = (n_rows + BM - 1) / BM, n_tiles = (V + BN - 1) / BN;
     gemm_split_f16_kernel<BN, STAGES, CHUNK_KB, BK><<<m_tiles * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_tiles, n_tiles, a_terms, b_terms, gate, run_if_set, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, add_const, m_tiles, n_tiles, a_terms, b_terms, gate, run_if_set, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
 
 template <int STAGES, int CHUNK_KB, int A_T, int B_T, bool A_REUSE = false>
 static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
-                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha,
+                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, float add_const,
                          const int32_t *gate, int run_if_set, int kb0, int kb_n, cudaStream_t st) {
     using C = PairCfg<STAGES, A_T, B_T>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -691,7 +693,7 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     if (g_err_flag) cudaHostGetDevicePointer(&d_flag, g_err_flag, 0);
     const int m_pairs = (n_rows + 2 * BM - 1) / (2 * BM), n_tiles = (V + C::BN - 1) / C::BN;
     gemm_split_f16_pair_kernel<STAGES, CHUNK_KB, A_T, B_T, A_REUSE><<<2 * m_pairs * n_tiles, C::THREADS, C::SMEM_BYTES, st>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, m_pairs, n_tiles, gate, run_if_set, kb0, kb_n, d_flag);
+        ma_hi, ma_lo, mb_hi, mb_lo, D, d_row0, ldd, a_row0, n_rows, V, alpha, add_const, m_pairs, n_tiles, gate, run_if_set, kb0, kb_n, d_flag);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }
@@ -704,10 +706,10 @@ static int launch_pair_t(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 // dense and a 90 % sparse plane, scaled from profiles/r1f_gemm_probe_bias_sparse.txt).
 template <int CHUNK_KB, int S22 = 3, int S12 = 4, int S11 = 6, bool A_REUSE = false, int CHUNK_11 = CHUNK_KB>
 static int launch_pair(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
-                       const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int a_terms,
+                       const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, float add_const, int a_terms,
                        int b_terms, const int32_t *gate, int run_if_set, int kb0, int kb_n, cudaStream_t st) {
 #define MLBP_PAIR(S, AT, BT, CH) \
-    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, gate, run_if_set, kb0, kb_n, st)
+    return launch_pair_t<S, CH, AT, BT, A_REUSE>(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, add_const, gate, run_if_set, kb0, kb_n, st)
     if (a_terms == 2 && b_terms == 2) MLBP_PAIR(S22, 2, 2, CHUNK_KB);
     if (a_terms == 1 && b_terms == 2) MLBP_PAIR(S12, 1, 2, CHUNK_KB);
     if (a_terms == 2 && b_terms == 1) MLBP_PAIR(S12, 2, 1, CHUNK_KB);
@@ -722,7 +724,7 @@ using namespace mlbp;
 extern "C" int mlbp_gemm_barrier_timeout_code(void) { return g_err_flag ? *g_err_flag : 0; }
 
 static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0, int n_rows, const void *B_hi,
-                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, int impl,
+                         const void *B_lo, int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, float add_const, int impl,
                          const int32_t *gate, int run_if_set, int k0, int k_len, void *stream) {
     if (n_rows == 0) return MLBP_OK;
     MLBP_CHECK_ARG(A_hi && A_lo && B_hi && B_lo && D, "factor_to_var_gemm: null pointer");
@@ -745,10 +747,10 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
     MLBP_CHECK_ARG(whole_k || ((impl == 0 && V > 2048) || impl == 2), "factor_to_var_gemm: only the CTA-pair kernel takes a partial K range");
     MLBP_CHECK_ARG(kb_n > 0, "factor_to_var_gemm: empty K range");
     if (impl == 1) {
-        MLBP_CHECK_ARG(gate == nullptr, "factor_to_var_gemm_gated: the SIMT cross-check kernel has no device-side gate");
+        MLBP_CHECK_ARG(gate == nullptr && add_const == 0.f, "factor_to_var_gemm_gated: the SIMT cross-check kernel has no device-side gate and no constant term");
         return launch_gemm_simt(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms, st);
     }
-#define MLBP_ARGS A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, a_terms, b_terms
+#define MLBP_ARGS A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, add_const, a_terms, b_terms
 #define MLBP_TC(BN_, ST_, CH_) return launch_tc<BN_, ST_, CH_>(MLBP_ARGS, gate, run_if_set, st)
     switch (impl) {
         case 0:                                       // product configuration: CTA-pair kernel for large V
@@ -786,12 +788,12 @@ static int gemm_dispatch(const void *A_hi, const void *A_lo, int64_t a_rows_tota
 extern "C" int mlbp_factor_to_var_gemm(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
                                        int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
                                        int64_t d_row0, int ldd, float alpha, int impl, void *stream) {
-    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, nullptr, 0, 0, 0, stream);
+    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, 0.f, impl, nullptr, 0, 0, 0, stream);
 }
 
 extern "C" int mlbp_factor_to_var_gemm_gated(const void *A_hi, const void *A_lo, int64_t a_rows_total, int a_row0,
                                              int n_rows, const void *B_hi, const void *B_lo, int V, int ldv, float *D,
                                              int64_t d_row0, int ldd, float alpha, int impl, const int32_t *gate,
-                                             int run_if_set, int k0, int k_len, void *stream) {
-    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl, gate, run_if_set, k0, k_len, stream);
+                                             int run_if_set, int k0, int k_len, float add_const, void *stream) {
+    return gemm_dispatch(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, add_const, impl, gate, run_if_set, k0, k_len, stream);
 }

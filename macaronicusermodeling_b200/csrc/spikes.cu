@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SP_THREADS)
 spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restrict__ cnt, const int2 *__restrict__ entries,
                      const int32_t *__restrict__ rows, const int32_t *__restrict__ n_list, int a0, int n_rows, const __half *__restrict__ Bt_hi,
                      const __half *__restrict__ Bt_lo, int V, int ldv, float *__restrict__ D, int64_t d_row0, int ldd,
-                     float alpha, const __half *__restrict__ A_hi) {
+                     float alpha, const __half *__restrict__ A_hi, const __half *__restrict__ Rt_hi, float tbar) {
     if (words[0] != 0) return;                                     // three passes ran: nothing to restore
     __shared__ int s_col[MLBP_SPIKE_SLOTS];
     __shared__ float s_lo[MLBP_SPIKE_SLOTS], s_hi[MLBP_SPIKE_SLOTS];
@@ -138,6 +138,20 @@ spike_correct_kernel(const int32_t *__restrict__ words, const int32_t *__restric
                     const size_t o = (size_t)s_col[s] * ldv + 8 * (size_t)cc[u];
                     const uint4 h = __ldg(reinterpret_cast<const uint4 *>(Bt_hi + o)), l = __ldg(reinterpret_cast<const uint4 *>(Bt_lo + o));
                     const __half2 *hh = reinterpret_cast<const __half2 *>(&h), *ll = reinterpret_cast<const __half2 *>(&l);
+                    if (Rt_hi) {
+                        // residual-plane product: the GEMM held  hi_s * fp16(T - tbar)  of this element (+ the constant tbar * sum);
+                        // exact is (hi_s + lo_s) * (T - tbar):  add  (hi_s + lo_s) * (T - tbar) - hi_s * R_hi
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(Rt_hi + o));
+                        const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
+                        const float hs = s_hi[s];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 a = __half22float2(hh[q]), b = __half22float2(ll[q]), r2 = __half22float2(rh[q]);
+                            acc[u][2 * q] = fmaf(wl, (a.x - tbar) + b.x, fmaf(-hs, r2.x, acc[u][2 * q]));
+                            acc[u][2 * q + 1] = fmaf(wl, (a.y - tbar) + b.y, fmaf(-hs, r2.y, acc[u][2 * q + 1]));
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float2 a = __half22float2(hh[q]), b = __half22float2(ll[q]);
@@ -186,20 +200,22 @@ extern "C" int mlbp_spike_scan(const void *A_hi, const void *A_lo, int ldv, int 
 extern "C" int mlbp_spike_correct(const int32_t *spike_words, const int32_t *spike_cnt, const int32_t *spike_entries,
                                   const int32_t *block_rows, const int32_t *block_n, int a_row0, int n_rows, const void *Bt_hi, const void *Bt_lo,
                                   int V, int ldv, float *D, int64_t d_row0, int ldd, float alpha, const void *A_hi_one_pass,
-                                  void *stream) {
+                                  const void *Rt_hi, float tbar, void *stream) {
     if (n_rows == 0) return MLBP_OK;
     MLBP_CHECK_ARG(spike_words && spike_cnt && spike_entries && block_rows && block_n && Bt_hi && Bt_lo && D && n_rows > 0 && a_row0 >= 0,
                    "spike_correct: bad argument");
     MLBP_CHECK_ARG((ldv % 64) == 0 && ldv >= V && (ldd % 64) == 0 && ldd >= V &&
                    ((reinterpret_cast<uintptr_t>(Bt_hi) | reinterpret_cast<uintptr_t>(Bt_lo) | reinterpret_cast<uintptr_t>(D)) % 16) == 0,
                    "spike_correct: rows must be 16-byte aligned and padded to a multiple of 64");
+    MLBP_CHECK_ARG(!Rt_hi || (A_hi_one_pass && (reinterpret_cast<uintptr_t>(Rt_hi) % 16) == 0),
+                   "spike_correct: a residual plane goes with one-pass rows (A_hi) and must be 16-byte aligned");
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
     const int grid = n_rows < 8 * sms ? n_rows : 8 * sms;
     spike_correct_kernel<<<grid, SP_THREADS, 0, as_stream(stream)>>>(spike_words, spike_cnt, reinterpret_cast<const int2 *>(spike_entries),
                                                                     block_rows, block_n, a_row0, n_rows, (const __half *)Bt_hi,
                                                                     (const __half *)Bt_lo, V, ldv, D, d_row0, ldd, alpha,
-                                                                    (const __half *)A_hi_one_pass);
+                                                                    (const __half *)A_hi_one_pass, (const __half *)Rt_hi, tbar);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

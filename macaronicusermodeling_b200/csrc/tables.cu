@@ -69,6 +69,10 @@ __device__ __forceinline__ __half half_stochastic(float x, unsigned r) {        
     const unsigned bits = (__float_as_uint(x) + (r & 0x1FFFu)) & 0xFFFFE000u;    // fp32 has 13 mantissa bits more than fp16
     return __float2half_rz(__uint_as_float(bits));
 }
+__device__ __forceinline__ __half half_stochastic_signed(float x, unsigned r) {  // magnitude rounded as above, sign kept
+    const __half h = half_stochastic(fabsf(x), r);
+    return x < 0.f ? __hneg(h) : h;
+}
 
 // exp(z.hi + z.lo), ~1 ulp: expf is IEEE-grade here (the library is built without fast-math)
 __device__ __forceinline__ float exp_f2(F2 z) { return expf(z.hi) * (1.0f + z.lo); }
@@ -79,7 +83,7 @@ __device__ __forceinline__ float exp_f2(F2 z) { return expf(z.hi) * (1.0f + z.lo
 __global__ void __launch_bounds__(256)
 build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restrict__ w1, int V, int ldf, F2 t_pmi, F2 t_w1,
                              F2 t_bias, float scale, __half *__restrict__ planes, int64_t ps, int ldv,
-                             double *__restrict__ colsums, int with_grad) {
+                             double *__restrict__ colsums, int with_grad, __half *__restrict__ r_planes, float tbar) {
     // hi / lo tiles of T, T1 (and G, G1, G1w with the gradient planes), indexed [a][b], for the transposed planes; the
     // column-sum partials reuse the storage once the tiles are written out.  Dynamic shared memory: 10 tiles = 84 KB.
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -87,6 +91,7 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
     double (*sSum)[8][TS] = reinterpret_cast<double (*)[8][TS]>(s_raw);
     static_assert(sizeof(double) * 5 * 8 * TS <= 4 * TS * (TS + 2) * sizeof(__half), "column-sum partials must fit the tile storage");
     const int n_tiles = with_grad ? 10 : 4;
+    const int r_tile = n_tiles;                                   // two more tiles for the residual planes (r_planes != nullptr)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int a0 = blockIdx.y * TS, b0 = blockIdx.x * TS;
     const int b = b0 + 2 * tx;
@@ -100,6 +105,7 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
         __half2 h[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) h[i] = __floats2half2_rn(0.f, 0.f);
+        __half2 hr[2] = {h[0], h[0]};                             // residuals R = T - tbar, R1 = T1 - tbar (hi halves only)
         if (a < V && b < V) {                                     // ldf is even and >= V: the pair load stays inside the row
             const float2 p2 = *reinterpret_cast<const float2 *>(pmi + (size_t)a * ldf + b);
             const float2 w2 = *reinterpret_cast<const float2 *>(w1 + (size_t)a * ldf + b);
@@ -127,6 +133,18 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
                 h[2 * i + 1] = __floats2half2_rn(x.x - back.x, x.y - back.y);
             }
             const size_t o = (size_t)a * ldv + b;                 // even: 4-byte aligned
+            if (r_planes) {
+                // Residual planes for the ONE-pass message rows: T = tbar + R with tbar = T at phi = 0 (the value of every entry
+                // under a zero of a sparse feature plane, and close to all entries once the pairwise weights are small): the
+                // GEMM contracts the messages with fp16(R) and adds tbar * sum(message) -- a constant -- in its epilogue, so
+                // the fp16 rounding is relative to |T - tbar|, not to T (exactly zero under the zeros).
+                const unsigned q0 = cell_hash((unsigned)a ^ 0x5bd1e995u, (unsigned)b), q1 = cell_hash((unsigned)a ^ 0x5bd1e995u, (unsigned)b + 1u);
+                const bool in1 = b + 1 < V;
+                hr[0] = __halves2half2(half_stochastic_signed(v[0][0] * scale - tbar, q0), in1 ? half_stochastic_signed(v[0][1] * scale - tbar, q1) : __float2half_rn(0.f));
+                hr[1] = __halves2half2(half_stochastic_signed(v[1][0] * scale - tbar, q0 >> 13), in1 ? half_stochastic_signed(v[1][1] * scale - tbar, q1 >> 13) : __float2half_rn(0.f));
+                *reinterpret_cast<__half2 *>(r_planes + 0 * ps + o) = hr[0];
+                *reinterpret_cast<__half2 *>(r_planes + 2 * ps + o) = hr[1];
+            }
             auto st = [&](int plane, __half2 x) { *reinterpret_cast<__half2 *>(planes + plane * ps + o) = x; };
             st(0, h[0]); st(1, h[1]);                             // T
             st(4, h[2]); st(5, h[3]);                             // T1
@@ -139,6 +157,10 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
 #pragma unroll
         for (int i = 0; i < 10; ++i)
             if (i < n_tiles) *reinterpret_cast<__half2 *>(&sT[i][r][2 * tx]) = h[i];
+        if (r_planes) {
+            *reinterpret_cast<__half2 *>(&sT[r_tile][r][2 * tx]) = hr[0];
+            *reinterpret_cast<__half2 *>(&sT[r_tile + 1][r][2 * tx]) = hr[1];
+        }
         // row sums of T and T1 (message of a pairwise factor whose input is still the uniform initial message)
         rs_t = warp_sum_f32(rs_t); rs_t1 = warp_sum_f32(rs_t1);
         if (tx == 0 && a < V) {
@@ -160,6 +182,10 @@ build_pairwise_tables_kernel(const float *__restrict__ pmi, const float *__restr
                     const __half2 x = __halves2half2(sT[i][2 * tx][r], sT[i][2 * tx + 1][r]);
                     *reinterpret_cast<__half2 *>(planes + (i < 2 ? 2 + i : (i < 4 ? 4 + i : 10 + i)) * ps + o) = x;
                 }
+            if (r_planes) {                                       // Rt, R1t
+                *reinterpret_cast<__half2 *>(r_planes + 1 * ps + o) = __halves2half2(sT[r_tile][2 * tx][r], sT[r_tile][2 * tx + 1][r]);
+                *reinterpret_cast<__half2 *>(r_planes + 3 * ps + o) = __halves2half2(sT[r_tile + 1][2 * tx][r], sT[r_tile + 1][2 * tx + 1][r]);
+            }
         }
     }
     __syncthreads();                                              // the tiles are dead: their storage takes the partial sums
@@ -206,7 +232,7 @@ using namespace mlbp;
 extern "C" int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1, int V, int ldf,
                                           const double *h_theta_ee, int scale_exp, void *planes,
                                           int64_t plane_stride, int ldv, double *colsums, int with_grad_planes,
-                                          void *stream) {
+                                          void *r_planes, float *h_tbar, void *stream) {
     MLBP_CHECK_ARG(pmi && pmi_w1 && planes && colsums && h_theta_ee, "build_pairwise_tables: null pointer");
     MLBP_CHECK_ARG(V > 0 && ldf >= V && (ldf % 2) == 0 && ldv >= V && (ldv % 64) == 0, "build_pairwise_tables: bad V/ld (%d,%d,%d)", V, ldf, ldv);
     MLBP_CHECK_ARG(plane_stride >= (int64_t)V * ldv && (plane_stride % 2) == 0, "build_pairwise_tables: plane_stride too small or odd");
@@ -216,17 +242,21 @@ extern "C" int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1,
     cudaStream_t st = as_stream(stream);
     MLBP_CUDA(cudaMemsetAsync(colsums, 0, sizeof(double) * MLBP_N_SUMS * (size_t)V, st));
     dim3 grid((V + TS - 1) / TS, (V + TS - 1) / TS);
-    const size_t smem = (size_t)(with_grad_planes ? 10 : 4) * TS * (TS + 2) * sizeof(__half);
+    MLBP_CHECK_ARG(!r_planes || (reinterpret_cast<uintptr_t>(r_planes) % 4) == 0, "build_pairwise_tables: misaligned residual planes");
+    const size_t smem = (size_t)((with_grad_planes ? 10 : 4) + (r_planes ? 2 : 0)) * TS * (TS + 2) * sizeof(__half);
+    // tbar = T at phi = 0, scaled like the planes: what the one-pass message GEMM adds back as a constant (see the kernel)
+    const float tbar = (float)(exp(h_theta_ee[2]) * ldexp(1.0, scale_exp));
+    if (h_tbar) *h_tbar = tbar;
     static bool attr_set_dev[MLBP_MAX_DEVICES] = {};
     if (!attr_set_dev[current_device()]) {
         MLBP_CUDA(cudaFuncSetAttribute(build_pairwise_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       10 * TS * (TS + 2) * (int)sizeof(__half)));
+                                       12 * TS * (TS + 2) * (int)sizeof(__half)));
         attr_set_dev[current_device()] = true;
     }
     build_pairwise_tables_kernel<<<grid, 256, smem, st>>>(pmi, pmi_w1, V, ldf, split_double_host(h_theta_ee[0]),
                                                        split_double_host(h_theta_ee[1]), split_double_host(h_theta_ee[2]),
                                                        ldexpf(1.0f, scale_exp), (__half *)planes, plane_stride, ldv, colsums,
-                                                       with_grad_planes);
+                                                       with_grad_planes, (__half *)r_planes, tbar);
     MLBP_LAUNCH_CHECK();
     return MLBP_OK;
 }

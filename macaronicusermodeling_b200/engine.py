@@ -276,6 +276,11 @@ class Engine(object):
         self.msg_one_pass_min_v = 8192
         one = self.msg_passes == 1 or (self.msg_passes is None and self.V >= self.msg_one_pass_min_v)
         self.msg_one_pass = one                     # (only while msg_two_pass_ok: set_theta's gate on the potentials' span)
+        # ONE-pass rows multiply the hi half of R = T - tbar (tbar = the table at phi = 0) and add tbar * sum(message) back as
+        # a constant: the fp16 rounding of the table is then relative to |T - tbar| -- zero under the zeros of a sparse feature
+        # plane, small everywhere once the pairwise weights are small (the regime SGD drives the bench into) -- instead of to T.
+        # Measured against the float64 oracle in that regime at V = 10 000: beliefs 1.3e-5 -> see profiles/; False = plain T_hi.
+        self.msg_residual = os.environ.get('MLBP_MSG_RESIDUAL', '1') != '0'
         self.tau = float(tau) if tau is not None else (4e-4 if one else 2e-4)
         self.tau_label = float(tau_label) if tau_label is not None else (2e-4 if one else 1e-4)
         self.peak_mult = float(peak_mult)
@@ -301,6 +306,9 @@ class Engine(object):
         self.profile_kernels = False  # same for the HBM-bound kernels: (name, event, event, algorithmic bytes)
         self.kernel_events = []
         self.event_tag = 0          # copied into every gemm_events record (bench.py: which step a launch belongs to)
+        self._tbar = np.zeros(1, dtype=np.float32)
+        self.tbar = 0.0
+        self.r_plane0 = N_PLANES
         self.plan_seconds = 0.0     # host time spent in the schedule compiler (mlbp_plan_compile + export)
         self.plan_template_hits = self.plan_template_misses = 0   # graphs served from / added to the template cache (csrc/plan.cpp)
         self._pre = {}              # schedules being compiled ahead of their run() call: key -> (thread, result box)
@@ -366,14 +374,17 @@ class Engine(object):
         self.k.call('mlbp_zero_words', _p(self._flags), FLAG_WORDS)   # the peak flag is sticky per theta
         self.unary_range_log2 = (abs(td[0]) * erange + abs(td[1]) * prange + 4.0 * (abs(td[2]) + abs(td[3]) + abs(td[4]))) / math.log(2.0)
         n_planes = N_PLANES if with_grad else 8
-        if self.planes is None or self.planes.shape[0] < n_planes:
-            self.planes = torch.zeros((n_planes, self.V, self.ld), dtype=torch.float16, device=self.device)
+        # + 4 residual planes R = T - tbar (hi halves only), the operand of the ONE-pass message rows (include/mlbp.h, K2)
+        self.r_plane0 = n_planes
+        if self.planes is None or self.planes.shape[0] < n_planes + 4:
+            self.planes = torch.zeros((n_planes + 4, self.V, self.ld), dtype=torch.float16, device=self.device)
         self.with_grad_planes = with_grad
         m = self.model
-        self._timed('K2 build_pairwise_tables', 2.0 * self.V * self.V * 4 + n_planes * self.V * self.V * 2.0,
+        self._timed('K2 build_pairwise_tables', 2.0 * self.V * self.V * 4 + (n_planes + 4) * self.V * self.V * 2.0,
                     lambda: self.k.call('mlbp_build_pairwise_tables', _p(m.pmi), _p(m.w1), self.V, self.ld, _hp(te),
                                         self.scale_exp, _p(self.planes), self.V * self.ld, self.ld, _p(self.colsums),
-                                        1 if with_grad else 0))
+                                        1 if with_grad else 0, _p(self.planes[self.r_plane0]), _hp(self._tbar)))
+        self.tbar = float(self._tbar[0])                          # 2^scale_exp * exp(theta_bias): written by the entry point on the host
         self.k.call('mlbp_build_unary_tables', _p(m.edT), _p(m.pedT), self.V, self.Vd, self.ld, _hp(td), _p(self.edstats))
         self.launches += 2
         # D rows 0..4: the constant-one row and the constant messages by table id (T: row sums, Tt: column sums, T1, T1t),
@@ -397,6 +408,11 @@ class Engine(object):
 
     def plane(self, table, lo):
         return self.planes[2 * table + (1 if lo else 0)]
+
+    def r_plane(self, table):
+        """residual plane (T - tbar, hi half) of message table 0..3 (T, Tt, T1, T1t)"""
+        assert 0 <= table < 4
+        return self.planes[self.r_plane0 + table]
 
     # ------------------------------------------------------------------ API read-back helpers (LBP.py drop-in)
     def unary_message(self, factor_type, observed_dim, gap1=False, sparse=(), normalized=True):
@@ -626,6 +642,10 @@ class Engine(object):
             self.launches += 1
         max_in = int(blob[H_MAX_IN])
         alpha = float(2.0 ** (-(A_SCALE_LOG2 + self.scale_exp + self.centre_exp)))
+        # one-pass message rows contract with the residual planes; every message row sums to 2^14, so the dropped constant is
+        # the same for every element of the product (K4's add_const)
+        msg_residual = msg_one_pass and self.msg_residual and len(self.gemm_k_ranges) == 1
+        msg_const = float(alpha * (2.0 ** A_SCALE_LOG2) * self.tbar)
         g_max = int(np.diff(corpus.giv_off).max()) if corpus.n_vars else 0
         range_log2 = float((max_in + 2 * g_max) * self.half_range_log2 + self.unary_range_log2)
 
@@ -644,10 +664,11 @@ class Engine(object):
             self._timed('K4b spike_correct', 0.0,                # bytes depend on the data (spikes found on the device)
                         lambda: k.call('mlbp_spike_correct', peak_flag, _p(spk_cnt), _p(spk_ent), _p(spk_rows, block_a0), _p(spk_blk, b),
                                        a0, rows, _p(self.plane(tt, 0)), _p(self.plane(tt, 1)), V, ld, _p(D), d0, ld, alpha,
-                                       _p(A_hi) if one_pass_rows else None))
+                                       _p(A_hi) if one_pass_rows else None,
+                                       _p(self.r_plane(tt)) if (one_pass_rows and msg_residual and t < 4) else None, self.tbar))
             self.launches += 1
 
-        def gemm_calls(off, n, mask, impl_flags=0, gated=False, role='message'):
+        def gemm_calls(off, n, mask, impl_flags=0, gated=False, role='message', residual=False):
             masked = set()
             for i in range(n):
                 t, a0, d0, rows = (int(x) for x in blob[off + GEMM_WORDS * i: off + GEMM_WORDS * (i + 1)])
@@ -668,15 +689,17 @@ class Engine(object):
                         gate, fallback = gated if isinstance(gated, tuple) else (peak_flag, 0)
                         for k0, k_len in self.gemm_k_ranges:
                             for fl, run_if_set in ((impl_flags, 0), (fallback, 1)):
-                                k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
-                                       _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | fl, gate, run_if_set,
-                                       k0, k_len)
+                                # residual: the reduced (one-pass) variant contracts with R = T - tbar and adds the constant
+                                res = residual and run_if_set == 0
+                                k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n,
+                                       _p(self.r_plane(t) if res else self.plane(t, 0)), _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld,
+                                       alpha, self.gemm_impl | fl, gate, run_if_set, k0, k_len, msg_const if res else 0.0)
                             self.launches += 2
                         self.launches -= 1
                     elif len(self.gemm_k_ranges) > 1:
                         for k0, k_len in self.gemm_k_ranges:
                             k.call('mlbp_factor_to_var_gemm_gated', _p(A_hi), _p(A_lo), a_cap, a0 + r0, n, _p(self.plane(t, 0)),
-                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags, None, 0, k0, k_len)
+                                   _p(self.plane(t, 1)), V, ld, _p(D), d0 + r0, ld, alpha, self.gemm_impl | impl_flags, None, 0, k0, k_len, 0.0)
                             self.launches += 1
                         self.launches -= 1
                     else:
@@ -710,7 +733,8 @@ class Engine(object):
                     if two_pass:
                         spike_scan(a0, rows)
             if two_pass:
-                gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if msg_one_pass else 0), gated=True)
+                gemm_calls(int(rec[7]), int(rec[6]), False, GEMM_A_HI_ONLY | (GEMM_B_HI_ONLY if msg_one_pass else 0), gated=True,
+                           residual=msg_residual)
                 for i in range(int(rec[6])):                      # restore what the dropped lo half of the spikes contributed
                     t, a0, d0, rows = (int(x) for x in blob[int(rec[7]) + GEMM_WORDS * i: int(rec[7]) + GEMM_WORDS * (i + 1)])
                     spike_correct(t, a0, d0, rows, a0, msg_one_pass)

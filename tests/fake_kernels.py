@@ -59,7 +59,8 @@ class FakeKernels(object):
         getattr(self, name)(*args)
 
     # ---- K2
-    def mlbp_build_pairwise_tables(self, pmi, w1, V, ldf, th, scale_exp, planes, ps, ldv, colsums, with_grad):
+    def mlbp_build_pairwise_tables(self, pmi, w1, V, ldf, th, scale_exp, planes, ps, ldv, colsums, with_grad, r_planes=None,
+                                   h_tbar=None):
         P = _arr(pmi, np.float32, V * ldf).reshape(V, ldf)[:, :V].astype(np.float64)
         W = _arr(w1, np.float32, V * ldf).reshape(V, ldf)[:, :V].astype(np.float64)
         t = _arr(th, np.float64, 3)
@@ -80,6 +81,18 @@ class FakeKernels(object):
         cs = _arr(colsums, np.float64, 7 * V).reshape(7, V)
         cs[0], cs[1], cs[2], cs[3], cs[4] = T.sum(0), T1.sum(0), (T * P).sum(0), (T1 * P).sum(0), (T1 * W).sum(0)
         cs[5], cs[6] = T.sum(1), T1.sum(1)
+        tbar = np.float32(np.exp(t[2]) * 2.0 ** scale_exp)
+        if h_tbar is not None and getattr(h_tbar, 'value', h_tbar):
+            _arr(h_tbar, np.float32, 1)[0] = tbar
+        if r_planes is not None and getattr(r_planes, 'value', r_planes):
+            # residual planes R = T - tbar, R1 = T1 - tbar (hi halves, stochastic rounding of the magnitude), both orientations
+            rp = _arr(r_planes, np.float16, 4 * ps)
+            for i, M in enumerate((T, T1)):
+                x = (np.ldexp(M, scale_exp).astype(np.float32) - tbar).astype(np.float32)
+                hi, _ = _split_stochastic(np.abs(x).astype(np.float64), ai ^ 0x5bd1e995, bi, 0)
+                hi = np.where(x < 0, -hi, hi).astype(np.float16)
+                rp[(2 * i) * ps:(2 * i) * ps + V * ldv].reshape(V, ldv)[:, :V] = hi
+                rp[(2 * i + 1) * ps:(2 * i + 1) * ps + V * ldv].reshape(V, ldv)[:, :V] = hi.T
 
     def mlbp_build_unary_tables(self, edT, pedT, V, Vd, ldf, th, edstats):
         E = _arr(edT, np.float32, Vd * ldf).reshape(Vd, ldf)[:, :V].astype(np.float64)
@@ -247,7 +260,7 @@ class FakeKernels(object):
                 T[r] = int((np.diff(P[r]) == 0).sum()) + (1 if int((x == P[r, -1]).sum()) > int((P[r] == P[r, -1]).sum()) else 0)
 
     def mlbp_factor_to_var_gemm(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
-                                impl, k0=0, k_len=0):
+                                impl, k0=0, k_len=0, add_const=0.0):
         k1 = V if k_len == 0 else min(V, k0 + k_len)                # K range of this launch; k0 > 0 adds to D
         H = _arr(A_hi, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, k0:k1].astype(np.float64)
         L = _arr(A_lo, np.float16, (a_row0 + n_rows) * ldv).reshape(-1, ldv)[a_row0:, k0:k1].astype(np.float64)
@@ -258,14 +271,14 @@ class FakeKernels(object):
         if k0 > 0:
             Dm[d_row0:d_row0 + n_rows, :V] += (alpha * out).astype(np.float32)
         else:
-            Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out).astype(np.float32)
+            Dm[d_row0:d_row0 + n_rows, :V] = (alpha * out + add_const).astype(np.float32)
 
     def mlbp_factor_to_var_gemm_gated(self, A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha,
-                                      impl, gate, run_if_set, k0=0, k_len=0):
+                                      impl, gate, run_if_set, k0=0, k_len=0, add_const=0.0):
         if gate is not None and gate.value and (int(_arr(gate, np.int32, 1)[0]) != 0) != (run_if_set != 0):
             return
         self.mlbp_factor_to_var_gemm(A_hi, A_lo, a_rows_total, a_row0, n_rows, B_hi, B_lo, V, ldv, D, d_row0, ldd, alpha, impl,
-                                     k0, k_len)
+                                     k0, k_len, add_const)
 
     def mlbp_spike_scan(self, A_hi, A_lo, ldv, V, a0, n_rows, spike_prob, words, cnt, entries, block_rows, block_n):
         w = _arr(words, np.int32, 5)
@@ -293,7 +306,7 @@ class FakeKernels(object):
                 n[0] += 1
 
     def mlbp_spike_correct(self, words, cnt, entries, rows, n_list, a0, n_rows, Bt_hi, Bt_lo, V, ldv, D, d_row0, ldd, alpha,
-                           A_hi_one_pass=None):
+                           A_hi_one_pass=None, Rt_hi=None, tbar=0.0):
         w = _arr(words, np.int32, 5)
         if w[0] != 0:
             return
@@ -312,10 +325,17 @@ class FakeKernels(object):
             items = sorted((int(ent[r, s, 0]), float(ent[r, s, 1:2].view(np.float32)[0])) for s in range(min(int(c[r]), 4)))
             acc = np.zeros(V, dtype=np.float32)
             for col, lo in items:
-                acc = (acc + np.float32(lo) * (Bh[col, :V].astype(np.float32) + Bl[col, :V].astype(np.float32))).astype(np.float32)
-                if A_hi_one_pass is not None:
-                    hi = _arr(A_hi_one_pass, np.float16, (r + 1) * ldv).reshape(-1, ldv)[r, col]
-                    acc = (acc + np.float32(hi) * Bl[col, :V].astype(np.float32)).astype(np.float32)
+                full = Bh[col, :V].astype(np.float32) + Bl[col, :V].astype(np.float32)
+                hi = None
+                if A_hi_one_pass is not None and getattr(A_hi_one_pass, 'value', A_hi_one_pass):
+                    hi = np.float32(_arr(A_hi_one_pass, np.float16, (r + 1) * ldv).reshape(-1, ldv)[r, col])
+                if hi is not None and Rt_hi is not None and getattr(Rt_hi, 'value', Rt_hi):   # residual-plane product
+                    Rh = _arr(Rt_hi, np.float16, V * ldv).reshape(V, ldv)[col, :V].astype(np.float32)
+                    acc = (acc + (hi + np.float32(lo)) * (full - np.float32(tbar)) - hi * Rh).astype(np.float32)
+                    continue
+                acc = (acc + np.float32(lo) * full).astype(np.float32)
+                if hi is not None:
+                    acc = (acc + hi * Bl[col, :V].astype(np.float32)).astype(np.float32)
             Dm[d_row0 + r - a0, :V] += np.float32(alpha) * acc
 
     def mlbp_marginals(self, n_groups, grp_u, grp_off, in_row, label, U, D, ldv, V, logp, top1, rank, beliefs, range_log2,

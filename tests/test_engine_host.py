@@ -356,3 +356,32 @@ def test_next_steps_schedule_is_compiled_ahead():
     assert out['plain'][1] == 0 and out['ahead'][1] == 2
     for a, b in zip(out['plain'][0], out['ahead'][0]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_residual_planes_remove_the_table_rounding_of_one_pass_rows(monkeypatch):
+    """ONE-pass message rows contract with fp16(T - tbar) and add tbar * sum(message) as a constant (K2 r_planes, K4
+    add_const): once the pairwise weights are small (where SGD drives the bench) or the feature planes are sparse, T - tbar is
+    tiny or zero and the table's fp16 rounding all but disappears from the messages -- one pass is then as close to the
+    float64 oracle as two passes.  With MLBP_MSG_RESIDUAL=0 (plain T_hi operands) the same rows are an order of magnitude off."""
+    model = synth.make_model(160, 24, seed=11, pmi_density=0.3)
+    sents = [synth.sentence_to_arrays(synth.make_sentence(model, 'ppppg', seed=70 + i, n_history=4, p_correct=0.8)) for i in range(8)]
+    roots_pos = synth.draw_roots(sents, 3, seed=3)
+    te, td = [-0.003, 0.049, -0.3], [0.101, -0.047, 5.0, 0.3, 0.4, -0.2]          # the bench's trained regime
+    tb = orc.Tables(model, te, td)
+    ref = np.concatenate([orc.run_fast(tb, s, r, 3)['marginals'] for s, r in zip(sents, roots_pos)])
+    assert ref.max() > 0.3
+    corpus = Corpus(sents)
+    roots = corpus.roots_from_positions(roots_pos)
+    err = {}
+    for name, env, kw in (('two', '1', dict(msg_passes=2)), ('one_plain', '0', dict(msg_passes=1)), ('one_residual', '1', dict(msg_passes=1))):
+        monkeypatch.setenv('MLBP_MSG_RESIDUAL', env)
+        eng = Engine(model, kernels=FakeKernels(), **kw)
+        eng.set_theta(te, td)
+        r = eng.run(corpus, roots, 3, want_beliefs=True)
+        assert eng.pass_stats()['peak_flag'] == 0
+        err[name] = float(np.abs(r.beliefs.numpy()[:, :160] - ref).max())
+        if name == 'one_residual':
+            np.testing.assert_array_equal(r.top1.numpy(), np.concatenate([orc.run_fast(tb, s, q, 3)['top1'] for s, q in zip(sents, roots_pos)]))
+    print('max abs belief error vs the oracle: two-pass %.2e, one-pass plain %.2e, one-pass residual %.2e' % (err['two'], err['one_plain'], err['one_residual']))
+    assert err['one_residual'] < 0.2 * err['one_plain']
+    assert err['one_residual'] < 3.0 * err['two'] + 1e-7

@@ -126,10 +126,15 @@ def test_pairwise_tables(lib):
     planes = torch.zeros((20, V, ld), dtype=torch.float16, device='cuda')
     cols = torch.zeros((7, V), dtype=torch.float64, device='cuda')
     s = 9
+    rpl = torch.zeros((4, V, ld), dtype=torch.float16, device='cuda')
+    tbar = np.zeros(1, dtype=np.float32)
     _lib.check(lib.mlbp_build_pairwise_tables(P(pmi), P(w1), V, ld, te.ctypes.data_as(ctypes.c_void_p), s, P(planes),
-                                              V * ld, ld, P(cols), 1, S()))
+                                              V * ld, ld, P(cols), 1, P(rpl), tbar.ctypes.data_as(ctypes.c_void_p), S()))
     torch.cuda.synchronize()
     pl = planes.cpu().numpy().astype(np.float64)
+    # residual planes R = T - tbar, R1 = T1 - tbar and their transposes (hi halves only: 11 bits of the RESIDUAL), tbar = T(phi = 0)
+    np.testing.assert_allclose(tbar[0], np.exp(te[2]) * 2.0 ** s, rtol=1e-6)
+    rp = rpl.cpu().numpy().astype(np.float64)
     p32, w32 = model['pmi'].astype(np.float32).astype(np.float64), model['pmi_w1'].astype(np.float32).astype(np.float64)
     T = np.exp(te[0] * p32 + te[2]); T1 = np.exp(te[0] * p32 + te[1] * w32 + te[2])
     want = [T, T.T, T1, T1.T, T * p32, T1 * p32, T1 * w32, (T * p32).T, (T1 * p32).T, (T1 * w32).T]
@@ -137,6 +142,10 @@ def test_pairwise_tables(lib):
         got = (pl[2 * i] + pl[2 * i + 1])[:, :V] * 2.0 ** -s
         assert np.abs(got - W).max() / W.max() < 1e-6, i
         assert (pl[2 * i][:, V:] == 0).all()
+    for i, W in enumerate(want[:4]):
+        R = W * 2.0 ** s - float(tbar[0])
+        assert np.abs(rp[i][:, :V] - R).max() <= 2.0 ** -10 * np.abs(R).max() + 1e-6, i      # one fp16 ulp (stochastic rounding)
+        assert (rp[i][:, V:] == 0).all()
     c = cols.cpu().numpy()
     # K2 evaluates exp in fp32 on a compensated argument (~1 ulp per entry, random) and sums in compensated fp32 / float64:
     # column sums over V = 200 entries are good to ~3e-8 (measured; expf's rounding is not quite unbiased), row sums (plain
@@ -178,7 +187,7 @@ def test_gated_gemm_runs_only_when_the_device_flag_matches(lib):
         D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
         for impl, run_if_set in ((256, 0), (0, 1)):               # what Engine issues for one slice of message rows
             _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, impl,
-                                                         P(gate), run_if_set, 0, 0, S()))
+                                                         P(gate), run_if_set, 0, 0, 0.0, S()))
         torch.cuda.synchronize()
         got = D.cpu().numpy()[:, :V]
         want, other = (ref3, ref2) if flag else (ref2, ref3)
@@ -187,7 +196,7 @@ def test_gated_gemm_runs_only_when_the_device_flag_matches(lib):
     # nothing runs when neither launch matches
     D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
     gate[0] = 1
-    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 256, P(gate), 0, 0, 0, S()))
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 256, P(gate), 0, 0, 0, 0.0, S()))
     torch.cuda.synchronize()
     assert (D == -7.0).all()
     assert _lib.load().mlbp_gemm_barrier_timeout_code() == 0
@@ -337,9 +346,9 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     cnt, ent, rows = cnt.cuda(), ent.cuda(), rows.cuda()
     D = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
     n_blk = M - a0
-    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D), 1, ld, 0.5, 256, P(words), 0, 0, 0, S()))
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D), 1, ld, 0.5, 256, P(words), 0, 0, 0, 0.0, S()))
     before = D.clone()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, None, S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D), 1, ld, 0.5, None, None, 0.0, S()))
     torch.cuda.synchronize()
     got, was = D.cpu().numpy(), before.cpu().numpy()
     full = 0.5 * (Ax[a0:] @ Bx.T)
@@ -357,15 +366,15 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
     # PEAK set: the block ran three passes, the correction must not touch it
     words[0] = 1
     D2 = before.clone()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, None, S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D2), 1, ld, 0.5, None, None, 0.0, S()))
     torch.cuda.synchronize()
     assert torch.equal(D2, before)
     # ONE-pass rows (A_hi . B_hi): with A_hi passed the correction also restores hi_s * B_lo[:, col_s] at the spikes
     words[0] = 0
     D3 = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
-    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D3), 1, ld, 0.5, 256 | 512, P(words), 0, 0, 0, S()))
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Bh), P(Bl), V, ld, P(D3), 1, ld, 0.5, 256 | 512, P(words), 0, 0, 0, 0.0, S()))
     was3 = D3.cpu().numpy()
-    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D3), 1, ld, 0.5, P(Ah), S()))
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D3), 1, ld, 0.5, P(Ah), None, 0.0, S()))
     torch.cuda.synchronize()
     got3 = D3.cpu().numpy()
     ah, bh = Ah.cpu().numpy()[:, :V].astype(np.float64), Bh.cpu().numpy()[:, :V].astype(np.float64)
@@ -375,6 +384,30 @@ def test_spike_correct_restores_the_dropped_lo_part(lib):
         for c in cols:                                             # exact spike term minus what the one-pass product held of it
             want += 0.5 * (Ax[r, c] * Bx[:, c] - ah[r, c] * bh[:, c])
         assert np.abs(got3[i, :V] - want).max() / np.abs(want).max() < 2e-6, r
+    # RESIDUAL-plane one-pass rows: B_hi := fp16(T - tbar), the GEMM adds the constant alpha * tbar * sum(row); at the spikes the
+    # correction brings the element's term to (hi + lo) * (T - tbar) exactly
+    tbar = float(np.median(T))
+    Rh = torch.zeros((V, ld), dtype=torch.float16); Rh[:, :V] = torch.from_numpy((T - tbar).astype(np.float32).astype(np.float16))
+    Rth = torch.zeros((V, ld), dtype=torch.float16); Rth[:, :V] = torch.from_numpy((T.T - tbar).astype(np.float32).astype(np.float16))
+    Rh, Rth = Rh.cuda(), Rth.cuda()
+    row_sum = 1000.0                                               # any constant: the test rows do not sum to 2^14
+    D4 = torch.full((M + 3, ld), -7.0, dtype=torch.float32, device='cuda')
+    _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, a0, n_blk, P(Rh), P(Bl), V, ld, P(D4), 1, ld, 0.5, 256 | 512, P(words), 0, 0, 0,
+                                                 0.5 * tbar * row_sum, S()))
+    was4 = D4.cpu().numpy()
+    rh = Rh.cpu().numpy()[:, :V].astype(np.float64)
+    plain = 0.5 * (ah[a0:] @ rh.T) + 0.5 * tbar * row_sum
+    assert np.abs(was4[1:1 + n_blk, :V] - plain).max() / np.abs(plain).max() < 3e-6          # D = alpha A_hi R_hi' + add_const
+    _lib.check(lib.mlbp_spike_correct(P(words), P(cnt), P(ent), P(rows), P(n_list), a0, n_blk, P(Th), P(Tl), V, ld, P(D4), 1, ld, 0.5, P(Ah),
+                                      P(Rth), tbar, S()))
+    torch.cuda.synchronize()
+    got4 = D4.cpu().numpy()
+    for r, cols in spikes.items():
+        i = 1 + r - a0
+        want = was4[i, :V].astype(np.float64)
+        for c in cols:
+            want += 0.5 * (Ax[r, c] * (Bx[:, c] - tbar) - ah[r, c] * rh[:, c])
+        assert np.abs(got4[i, :V] - want).max() / np.abs(want).max() < 2e-6, r
 
 
 def test_gemm_k_ranges_accumulate(lib):
@@ -390,7 +423,7 @@ def test_gemm_k_ranges_accumulate(lib):
     D = torch.full((M, ld), -7.0, dtype=torch.float32, device='cuda')
     for k0, k_len in ((0, 896), (896, 896), (1792, 708)):
         _lib.check(lib.mlbp_factor_to_var_gemm_gated(P(Ah), P(Al), M, 0, M, P(Bh), P(Bl), V, ld, P(D), 0, ld, 1.0, 2, None, 0,
-                                                     k0, k_len if k0 + k_len < V else 0, S()))
+                                                     k0, k_len if k0 + k_len < V else 0, 0.0, S()))
     torch.cuda.synchronize()
     got = D.cpu().numpy()[:, :V]
     assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
