@@ -81,7 +81,7 @@ int mlbp_dense_pointwise_multiply_f64(const double *m1, const double *m2, double
  *   with_grad_planes = 0 skips planes 8..19 (inference only).
  *   r_planes (or NULL): four more fp16 planes [V, ldv], same stride, R.hi Rt.hi R1.hi R1t.hi with R = T - tbar, R1 = T1 - tbar
  *           (scaled like the others, stochastic rounding of the magnitude), tbar = 2^scale_exp * exp(th[2]) = the table at
- *           phi = 0, returned in *h_tbar: the operand of the ONE-pass message rows, whose GEMM adds tbar * sum(message) back as
+ *           phi = 0, returned in *h_tbar (a positive *h_tbar on entry overrides it): the operand of the ONE-pass message rows, whose GEMM adds tbar * sum(message) back as
  *           a constant (mlbp_factor_to_var_gemm_gated add_const) -- the fp16 rounding is then relative to |T - tbar|.        */
 int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1, int V, int ldf, const double *h_theta_ee,
                                int scale_exp, void *planes, int64_t plane_stride, int ldv, double *colsums,

@@ -245,7 +245,8 @@ extern "C" int mlbp_build_pairwise_tables(const float *pmi, const float *pmi_w1,
     MLBP_CHECK_ARG(!r_planes || (reinterpret_cast<uintptr_t>(r_planes) % 4) == 0, "build_pairwise_tables: misaligned residual planes");
     const size_t smem = (size_t)((with_grad_planes ? 10 : 4) + (r_planes ? 2 : 0)) * TS * (TS + 2) * sizeof(__half);
     // tbar = T at phi = 0, scaled like the planes: what the one-pass message GEMM adds back as a constant (see the kernel)
-    const float tbar = (float)(exp(h_theta_ee[2]) * ldexp(1.0, scale_exp));
+    // (*h_tbar > 0 on entry: the caller's choice of the constant, already scaled; else the default, written back)
+    const float tbar = (h_tbar && *h_tbar > 0.f) ? *h_tbar : (float)(exp(h_theta_ee[2]) * ldexp(1.0, scale_exp));
     if (h_tbar) *h_tbar = tbar;
     static bool attr_set_dev[MLBP_MAX_DEVICES] = {};
     if (!attr_set_dev[current_device()]) {

@@ -281,7 +281,11 @@ class Engine(object):
         # plane, small everywhere once the pairwise weights are small (the regime SGD drives the bench into) -- instead of to T.
         # Measured against the float64 oracle in that regime at V = 10 000 (profiles/r2h_*, r2i_*): worst belief error 1.3e-5 ->
         # 6.4e-8 absolute, log-posterior 2e-6 -> 8e-9, decisions moved by the re-score 1 405 -> 6 per 82 k variables; hostile sparse
-        # case at V = 4 608: 1.3e-5 -> 3.9e-6.  MLBP_MSG_RESIDUAL=0: plain T_hi operands (A/B runs).
+        # case at V = 4 608: 1.3e-5 -> 3.9e-6.  Price: 3.5 % of the step (same-box A/B 3 496 vs 3 632 sentences/s,
+        # profiles/r2j_bench_c3_ab_residual_planes.txt): the kernels are the same, but residuals spread over many binades toggle
+        # more bits in the tensor cores than table entries that share two exponents, and the step is power-capped -- the SM clock
+        # drops from 1 631 to 1 603 MHz and the untouched gradient rows slow down with the message rows.
+        # MLBP_MSG_RESIDUAL=0: plain T_hi operands (A/B runs).
         self.msg_residual = os.environ.get('MLBP_MSG_RESIDUAL', '1') != '0'
         self.tau = float(tau) if tau is not None else (4e-4 if one else 2e-4)
         self.tau_label = float(tau_label) if tau_label is not None else (2e-4 if one else 1e-4)
@@ -382,6 +386,9 @@ class Engine(object):
             self.planes = torch.zeros((n_planes + 4, self.V, self.ld), dtype=torch.float16, device=self.device)
         self.with_grad_planes = with_grad
         m = self.model
+        # tbar: 0 = the entry point's default, the table at phi = 0.  (The smallest possible entry, exp(zmin) -- every residual
+        # non-negative -- was measured too: same accuracy, same speed: profiles/r2j_bench_c3_ab_residual_planes.txt.)
+        self._tbar[0] = 0.0
         self._timed('K2 build_pairwise_tables', 2.0 * self.V * self.V * 4 + (n_planes + 4) * self.V * self.V * 2.0,
                     lambda: self.k.call('mlbp_build_pairwise_tables', _p(m.pmi), _p(m.w1), self.V, self.ld, _hp(te),
                                         self.scale_exp, _p(self.planes), self.V * self.ld, self.ld, _p(self.colsums),

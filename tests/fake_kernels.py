@@ -83,6 +83,8 @@ class FakeKernels(object):
         cs[5], cs[6] = T.sum(1), T1.sum(1)
         tbar = np.float32(np.exp(t[2]) * 2.0 ** scale_exp)
         if h_tbar is not None and getattr(h_tbar, 'value', h_tbar):
+            if _arr(h_tbar, np.float32, 1)[0] > 0:
+                tbar = np.float32(_arr(h_tbar, np.float32, 1)[0])
             _arr(h_tbar, np.float32, 1)[0] = tbar
         if r_planes is not None and getattr(r_planes, 'value', r_planes):
             # residual planes R = T - tbar, R1 = T1 - tbar (hi halves, stochastic rounding of the magnitude), both orientations
