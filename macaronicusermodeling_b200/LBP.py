@@ -205,6 +205,11 @@ class FactorGraph():
             if __debug__: assert len(f.potential_table.var_id2dim) == len(f.varset)
             if f.potential_table.explicit:
                 self._explicit = True
+            # The batched schedule compiler walks a pairwise factor's variables in TABLE order (dim 0, dim 1); the reference's
+            # BFS walks f.varset (LBP.py:165-171).  create_factor_graph attaches them in table order (train.py:273-275); a graph
+            # that does not is run one message at a time, where the walk is the reference's own
+            if len(f.varset) == 2 and f.potential_table.var_id2dim.get(f.varset[0].id) != 0:
+                self._explicit = True
         self._roots = [self._last_loop_root]
         self._sweeps = 0
         self._initialized = True
