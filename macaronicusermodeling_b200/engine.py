@@ -498,7 +498,7 @@ class Engine(object):
 
     @staticmethod
     def _plan_key(corpus, roots, sweeps, flags):
-        return (id(corpus), corpus.n_sent, int(sweeps), int(flags), roots.tobytes())
+        return (id(corpus), corpus.n_sent, int(corpus.var_off[-1]), int(corpus.pair_off[-1]), int(sweeps), int(flags), roots.tobytes())
 
     def _plan_flags(self, want_grad, want_marg, approx_inference=False, approx_beliefs=False):
         """mlbp_plan_compile flags of a run() call under the CURRENT theta (the reduced-pass gates of set_theta decide reuse_z)"""
