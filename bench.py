@@ -632,7 +632,7 @@ def ours(a):
                                           'variant failed: %s' % (n, t_sent, t_tab, a.sentences, str(e)[:200])}
     line = {'metric': metric_name(a), 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': scaling_name(a), 'vs_baseline': None,
-            'dtype': 'f32 (tensor-core operands split into fp16 hi+lo, fp32 accumulate; fp32 message products, f64 sums)', 'data': 'synthetic',
+            'dtype': 'f16 x f16 -> f32 (one tensor-core pass per GEMM row, fp32 accumulate; the hi+lo operand split serves the exact re-score, the spike compensation and the three-pass fallback; fp32 message products, f64 sums)', 'data': 'synthetic',
             'config': {'workload': workload_name(a), 'global_sentences_per_step': w.n_global,
                        'parallelism': 'dp%d (%s sharded, 16 x f64 all-reduce per step)' % (world, 'users' if a.config == 'c4' else 'sentences'),
                        'l2': 'inputs larger than L2: table planes %.1f GB, message blocks > 10 GB per micro-batch' % (eng.planes.numel() * 2 / 1e9),
