@@ -26,7 +26,10 @@ def test_reference_arm_line():
     assert line['impl'] == 'reference' and line['value'] > 0 and line['steps'] == 2 and line['gpu_launches'] == 0
     cb = line['cpu_baseline']
     assert cb['kind'] == 'port' and cb['variant'] in ('process_pool', 'blas_threads') and cb['cores'] >= 1
-    assert cb['value'] == line['value'] == max(v['value'] for v in cb['variants'].values())
+    assert cb['value'] == line['value'] == max(cb['variants'][k]['value'] for k in ('process_pool', 'blas_threads'))
+    lit = cb['variants']['literal']                          # the op-for-op restatement, timed on two short sentences, never the arm's value
+    assert lit['extrapolated'] and lit['value'] > 0 and set(lit['measured_s']) == {'k=3 (3 pairwise factors)', 'k=4 (6 pairwise factors)'}
+    assert abs(lit['seconds_per_workload_sentence'] - (lit['per_sentence_constant_s'] + 6 * lit['per_pairwise_factor_s'])) < 1e-9   # k = 4
     assert cb['variants']['process_pool']['sentences_per_step'] == 3
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 
